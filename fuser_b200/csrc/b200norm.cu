@@ -1,0 +1,861 @@
+// b200norm.cu — C ABI, planner (dispatch heuristics) and kernel launches.
+//
+// The planner plays the role of nvFuser's canSchedule + computeHeuristics for
+// the matched segments (reference: scheduler/normalization_inner.cpp:73-231,
+// normalization_inner_non_tma.cpp:367-613,1144-1173,
+// normalization_inner_outer.cpp:246-535): it decides the kernel family, the
+// cluster size (row split), threads per row, ring depth and grid. The rules are
+// re-derived for the ring design used here, not transcribed from the reference.
+#include "../../include/b200norm.h"
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "kernels_generic.cuh"
+#include "kernels_tma_bwd.cuh"
+#include "kernels_tma_fwd.cuh"
+
+using namespace b200norm;
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+struct DeviceInfo {
+  int has_device = 0;
+  int sm_count = 148;
+  int smem_optin = 232448;  // 227 KB
+  int cc_major = 10;
+  int cc_minor = 0;
+};
+
+const DeviceInfo& device_info() {
+  static DeviceInfo info;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+      (void)cudaGetLastError();
+      return;
+    }
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return;
+    }
+    info.has_device = 1;
+    cudaDeviceGetAttribute(&info.sm_count, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&info.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    cudaDeviceGetAttribute(&info.cc_major, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&info.cc_minor, cudaDevAttrComputeCapabilityMinor, dev);
+  });
+  return info;
+}
+
+int elem_size(int dt) { return dt == B200NORM_DT_F32 ? 4 : 2; }
+
+bool is_row_op(int op) { return op >= B200NORM_OP_LAYERNORM_FWD && op <= B200NORM_OP_LOGSOFTMAX_BWD; }
+bool is_norm_bwd(int op) { return op == B200NORM_OP_LAYERNORM_BWD || op == B200NORM_OP_RMSNORM_BWD; }
+int n_streams(int op) {
+  switch (op) {
+    case B200NORM_OP_LAYERNORM_BWD:
+    case B200NORM_OP_RMSNORM_BWD:
+    case B200NORM_OP_SOFTMAX_BWD:
+    case B200NORM_OP_LOGSOFTMAX_BWD:
+      return 2;
+    default:
+      return 1;
+  }
+}
+int partial_k(int op) { return op == B200NORM_OP_LAYERNORM_BWD ? 2 : 1; }
+
+uint64_t algorithmic_bytes(const b200norm_desc& d) {
+  // The reference's own *_iobytes formulas (benchmarks/python/test_*_{fwd,bwd}.py).
+  const uint64_t s = elem_size(d.io_dtype), M = d.rows, N = d.cols;
+  switch (d.op) {
+    case B200NORM_OP_LAYERNORM_FWD: return s * 2 * (M * N + N) + 4 * 2 * M;
+    case B200NORM_OP_LAYERNORM_BWD: return s * 3 * (M * N + N) + 4 * 2 * M;
+    case B200NORM_OP_RMSNORM_FWD: return s * (2 * M * N + N) + 4 * M;
+    case B200NORM_OP_RMSNORM_BWD: return s * (3 * M * N + 2 * N) + 4 * M;
+    case B200NORM_OP_SOFTMAX_FWD:
+    case B200NORM_OP_LOGSOFTMAX_FWD: return s * 2 * M * N;
+    case B200NORM_OP_SOFTMAX_BWD:
+    case B200NORM_OP_LOGSOFTMAX_BWD: return s * 3 * M * N;
+    case B200NORM_OP_REDUCE_INNER: return s * (M * N + M);
+    case B200NORM_OP_REDUCE_OUTER: return s * (M * N + N);
+    case B200NORM_OP_FINALIZE_PARTIALS: return 4 * M * N + s * M * N;
+    default: return 0;
+  }
+}
+
+// Everything the launch needs, derived from (desc, device, alignment).
+struct Plan {
+  int variant = B200NORM_VARIANT_GENERIC;
+  int cluster = 1;
+  int grid = 1;
+  int block = kGenericThreads;
+  int tpr = 0;
+  int groups = 0;
+  int stages = 0;
+  int tile_rows = 1;
+  int contiguous = 0;
+  int ch = 0;
+  int nparts = 0;          // partial rows produced by the main kernel
+  int rows_per_split = 0;  // generic colsum
+  int n_launches = 1;
+  uint32_t slice_bytes = 0, stream_bytes = 0, stage_bytes = 0;
+  uint32_t off_red = 0, off_cls = 0, off_weight = 0, off_bias = 0, off_ring = 0;
+  uint32_t smem = 0;
+  uint64_t ws_bytes = 0;
+};
+
+uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
+
+constexpr int kConsumerThreads = 512;
+constexpr int kBwdCH_RMS = 4;  // fp32 column accumulators per thread = CH * VEC (x2 for LayerNorm)
+constexpr int kBwdCH_LN = 3;
+constexpr int kSoftmaxCH = 4;
+constexpr int kMaxStages = 32;
+
+int generic_nsplit(int64_t rows) {
+  int64_t n = rows / 64;
+  if (n < 1) n = 1;
+  if (n > 256) n = 256;
+  return (int)n;
+}
+
+// Try to build a ring plan with cluster size C. Returns false if infeasible.
+bool try_ring_plan(const b200norm_desc& d, const DeviceInfo& dev, int C, bool rows_contiguous, Plan* out) {
+  const int es = elem_size(d.io_dtype);
+  const int vec = 16 / es;
+  const int64_t N = d.cols;
+  if (N % C != 0) return false;
+  const int64_t slice_cols = N / C;
+  if ((slice_cols * es) % 16 != 0) return false;
+  if (slice_cols * es > (int64_t)200 * 1024) return false;
+  const int nchunks = (int)(slice_cols / vec);
+  const int ns = n_streams(d.op);
+  const bool bwd = is_norm_bwd(d.op);
+  const bool softmax_fwd = d.op == B200NORM_OP_SOFTMAX_FWD || d.op == B200NORM_OP_LOGSOFTMAX_FWD;
+
+  // threads per row slice
+  int tpr;
+  const int bwd_ch = d.op == B200NORM_OP_LAYERNORM_BWD ? kBwdCH_LN : kBwdCH_RMS;
+  if (bwd) {
+    if (nchunks <= 32 * bwd_ch) tpr = 32;
+    else if (nchunks <= 128 * bwd_ch) tpr = 128;
+    else if (nchunks <= 256 * bwd_ch) tpr = 256;
+    else if (nchunks <= 512 * bwd_ch) tpr = 512;
+    else return false;
+  } else if (softmax_fwd) {
+    if (nchunks <= 32 * kSoftmaxCH) tpr = 32;
+    else if (nchunks <= 128 * kSoftmaxCH) tpr = 128;
+    else if (nchunks <= 256 * kSoftmaxCH) tpr = 256;
+    else tpr = 512;
+  } else {
+    if (nchunks <= 32 * 16) tpr = 32;
+    else if (nchunks <= 128 * 16) tpr = 128;
+    else if (nchunks <= 256 * 16) tpr = 256;
+    else tpr = 512;
+  }
+  int groups = kConsumerThreads / tpr;
+
+  Plan p;
+  p.variant = C > 1 ? B200NORM_VARIANT_CLUSTER : B200NORM_VARIANT_TMA;
+  p.cluster = C;
+  p.tpr = tpr;
+  p.ch = bwd ? bwd_ch : (softmax_fwd ? kSoftmaxCH : 0);
+  p.slice_bytes = (uint32_t)(slice_cols * es);
+
+  // rows per tile: aim for >= 8 KB bulk copies when rows are short and contiguous
+  int tile_rows = 1;
+  if (C == 1 && rows_contiguous && p.slice_bytes < 8192) {
+    tile_rows = (int)(8192 / p.slice_bytes);
+    if (tile_rows > 32) tile_rows = 32;
+    if (tile_rows < 1) tile_rows = 1;
+    // do not starve the grid: keep at least ~4 tiles per consumer group per SM
+    while (tile_rows > 1 && ceil_div64(d.rows, tile_rows) < (int64_t)dev.sm_count * groups * 2) tile_rows /= 2;
+  }
+  p.tile_rows = tile_rows;
+  p.contiguous = (C == 1 && rows_contiguous) ? 1 : 0;
+  p.stream_bytes = (uint32_t)tile_rows * p.slice_bytes;
+  p.stage_bytes = align_up((uint32_t)ns * p.stream_bytes, 128);
+
+  const bool has_w = (d.flags & B200NORM_F_HAS_WEIGHT) != 0;
+  const bool has_b = (d.flags & B200NORM_F_HAS_BIAS) != 0 && d.op == B200NORM_OP_LAYERNORM_FWD;
+
+  for (;;) {
+    uint32_t off = 8u * (2 * kMaxStages + groups);
+    off = align_up(off, 128);
+    p.off_red = off;
+    off += (uint32_t)groups * 2 * kMaxWarpsPerGroup * kRedNV * 4;
+    p.off_cls = off;
+    off += (uint32_t)groups * 2 * kMaxCluster * kRedNV * 4;
+    off = align_up(off, 128);
+    p.off_weight = off;
+    if (has_w) off += align_up(p.slice_bytes, 128);
+    p.off_bias = off;
+    if (has_b) off += align_up(p.slice_bytes, 128);
+    p.off_ring = off;
+    const int64_t budget = (int64_t)dev.smem_optin - 1024 - off;
+    int stages = (int)(budget / p.stage_bytes);
+    if (stages > kMaxStages) stages = kMaxStages;
+    const int want = C > 1 ? 2 : 2;
+    if (stages < want) return false;
+    // every group needs its own stage in flight, plus prefetch depth
+    if (groups > 1 && stages < groups + 1) {
+      groups = groups / 2;
+      if (groups < 1) groups = 1;
+      continue;
+    }
+    if (stages > 2 * groups + 8) stages = 2 * groups + 8;
+    p.stages = stages;
+    break;
+  }
+  p.groups = groups;
+  p.block = groups * tpr + 32;
+  const uint32_t ring_bytes = (uint32_t)p.stages * p.stage_bytes;
+  if (bwd) {
+    const uint32_t acc_bytes = (uint32_t)partial_k(d.op) * (uint32_t)slice_cols * 4;
+    if (acc_bytes > ring_bytes) return false;
+  }
+  p.smem = p.off_ring + ring_bytes;
+
+  const int64_t ntiles = ceil_div64(d.rows, tile_rows);
+  int64_t nclusters = dev.sm_count / C;
+  if (nclusters > ntiles) nclusters = ntiles;
+  if (nclusters < 1) nclusters = 1;
+  p.grid = (int)(nclusters * C);
+  p.nparts = (int)nclusters;
+  p.n_launches = 1;
+  if (bwd && (d.flags & (B200NORM_F_OUT_DW | B200NORM_F_OUT_DB))) p.n_launches = 2;
+  *out = p;
+  return true;
+}
+
+int make_plan(const b200norm_desc& d, bool aligned, bool rows_contiguous, Plan* out) {
+  const DeviceInfo& dev = device_info();
+  Plan p;
+  const bool bwd = is_norm_bwd(d.op);
+  const bool want_cols = bwd && (d.flags & (B200NORM_F_OUT_DW | B200NORM_F_OUT_DB));
+
+  // workspace: large enough for whichever family ends up running
+  uint64_t ws = B200NORM_WS_HEADER_BYTES;
+  if (want_cols) {
+    int maxparts = generic_nsplit(d.rows);
+    if (dev.sm_count > maxparts) maxparts = dev.sm_count;
+    ws += (uint64_t)maxparts * partial_k(d.op) * d.cols * 4;
+  } else if (d.op == B200NORM_OP_REDUCE_OUTER) {
+    ws += (uint64_t)generic_nsplit(d.rows) * d.cols * 4;
+  }
+
+  bool ring_ok = false;
+  if (is_row_op(d.op) && aligned && d.variant != B200NORM_VARIANT_GENERIC && d.rows > 0 && d.cols > 0) {
+    const int forced_c = d.cluster_size;
+    static const int cs[] = {1, 2, 4, 8, 16};
+    Plan best;
+    for (int C : cs) {
+      if (forced_c > 0 && C != forced_c) continue;
+      if (forced_c == 0 && d.variant == B200NORM_VARIANT_TMA && C != 1) continue;
+      if (forced_c == 0 && d.variant == B200NORM_VARIANT_CLUSTER && C == 1) continue;
+      Plan cand;
+      if (!try_ring_plan(d, dev, C, rows_contiguous, &cand)) continue;
+      if (!ring_ok) {
+        best = cand;
+        ring_ok = true;
+      }
+      // prefer the smallest cluster that gives a reasonably deep ring
+      const int depth_goal = cand.groups + 2;
+      if (cand.stages >= depth_goal || forced_c > 0) {
+        best = cand;
+        break;
+      }
+      if (cand.stages > best.stages) best = cand;
+    }
+    if (ring_ok) p = best;
+  }
+  if (!ring_ok) {
+    if (d.variant == B200NORM_VARIANT_TMA || d.variant == B200NORM_VARIANT_CLUSTER) {
+      return fail(B200NORM_ERR_UNSUPPORTED, "requested kernel family cannot run rows=%lld cols=%lld",
+                  (long long)d.rows, (long long)d.cols);
+    }
+    p = Plan();
+    p.variant = B200NORM_VARIANT_GENERIC;
+    p.block = kGenericThreads;
+    int64_t g = d.rows;
+    const int64_t cap = (int64_t)dev.sm_count * 8;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    p.grid = (int)g;
+    p.n_launches = 1;
+    if (want_cols) {
+      p.nparts = generic_nsplit(d.rows);
+      p.rows_per_split = (int)ceil_div64(d.rows, p.nparts);
+      p.n_launches = 3;
+    }
+    if (d.op == B200NORM_OP_REDUCE_OUTER) {
+      p.nparts = generic_nsplit(d.rows);
+      p.rows_per_split = (int)ceil_div64(d.rows, p.nparts);
+      p.n_launches = 2;
+      p.block = 128;
+    }
+    if (d.op == B200NORM_OP_FINALIZE_PARTIALS) {
+      p.block = 256;
+      p.grid = (int)ceil_div64(d.cols, 32);
+    }
+  }
+  p.ws_bytes = ws;
+  *out = p;
+  return B200NORM_OK;
+}
+
+int check_desc(const b200norm_desc* d) {
+  if (d == nullptr) return fail(B200NORM_ERR_BAD_ARG, "null desc");
+  if (d->abi_version != B200NORM_ABI_VERSION)
+    return fail(B200NORM_ERR_BAD_ARG, "abi_version %d != %d", d->abi_version, B200NORM_ABI_VERSION);
+  if (d->op < 0 || d->op >= B200NORM_OP_COUNT_) return fail(B200NORM_ERR_UNSUPPORTED, "unknown op %d", d->op);
+  if (d->io_dtype < 0 || d->io_dtype > B200NORM_DT_F16)
+    return fail(B200NORM_ERR_UNSUPPORTED, "unsupported io dtype %d", d->io_dtype);
+  if (d->rows < 0 || d->cols < 0) return fail(B200NORM_ERR_BAD_ARG, "negative extent");
+  if (d->cols > 0x7fffffffLL) return fail(B200NORM_ERR_UNSUPPORTED, "cols %lld exceeds int32", (long long)d->cols);
+  if (d->cluster_size != 0 && d->cluster_size != 1 && d->cluster_size != 2 && d->cluster_size != 4 &&
+      d->cluster_size != 8 && d->cluster_size != 16)
+    return fail(B200NORM_ERR_BAD_ARG, "cluster_size must be 0,1,2,4,8,16");
+  if (d->variant < 0 || d->variant > B200NORM_VARIANT_CLUSTER) return fail(B200NORM_ERR_BAD_ARG, "bad variant");
+  if ((d->flags & B200NORM_F_OUT_DW) && !(d->flags & B200NORM_F_HAS_WEIGHT) && is_norm_bwd(d->op))
+    return fail(B200NORM_ERR_BAD_ARG, "dweight requested without a weight (the builders return none)");
+  return B200NORM_OK;
+}
+
+void fill_public_plan(const b200norm_desc& d, const Plan& p, b200norm_plan* out) {
+  memset(out, 0, sizeof(*out));
+  out->variant = p.variant;
+  out->cluster_size = p.cluster;
+  out->grid_x = p.grid;
+  out->block_x = p.block;
+  out->threads_per_row = p.tpr ? p.tpr : p.block;
+  out->stages = p.stages;
+  out->tile_rows = p.tile_rows;
+  out->smem_bytes = (int32_t)p.smem;
+  out->n_launches = p.n_launches;
+  out->workspace_bytes = p.ws_bytes;
+  out->algorithmic_bytes = algorithmic_bytes(d);
+}
+
+// ---------------------------------------------------------------------------
+// kernel tables
+// ---------------------------------------------------------------------------
+using RingKernel = void (*)(const RowParams);
+
+template <typename T>
+RingKernel ring_kernel_for(int op, int tpr) {
+#define B200_TPR_SWITCH(EXPR32, EXPR128, EXPR256, EXPR512) \
+  switch (tpr) {                                            \
+    case 32: return EXPR32;                                 \
+    case 128: return EXPR128;                               \
+    case 256: return EXPR256;                               \
+    case 512: return EXPR512;                               \
+    default: return nullptr;                                \
+  }
+  switch (op) {
+    case B200NORM_OP_RMSNORM_FWD:
+      B200_TPR_SWITCH((rmsnorm_fwd_tma_kernel<T, 32>), (rmsnorm_fwd_tma_kernel<T, 128>),
+                      (rmsnorm_fwd_tma_kernel<T, 256>), (rmsnorm_fwd_tma_kernel<T, 512>))
+    case B200NORM_OP_LAYERNORM_FWD:
+      B200_TPR_SWITCH((layernorm_fwd_tma_kernel<T, 32>), (layernorm_fwd_tma_kernel<T, 128>),
+                      (layernorm_fwd_tma_kernel<T, 256>), (layernorm_fwd_tma_kernel<T, 512>))
+    case B200NORM_OP_SOFTMAX_FWD:
+      B200_TPR_SWITCH((softmax_fwd_tma_kernel<T, 32, kSoftmaxCH, false>),
+                      (softmax_fwd_tma_kernel<T, 128, kSoftmaxCH, false>),
+                      (softmax_fwd_tma_kernel<T, 256, kSoftmaxCH, false>),
+                      (softmax_fwd_tma_kernel<T, 512, kSoftmaxCH, false>))
+    case B200NORM_OP_LOGSOFTMAX_FWD:
+      B200_TPR_SWITCH((softmax_fwd_tma_kernel<T, 32, kSoftmaxCH, true>),
+                      (softmax_fwd_tma_kernel<T, 128, kSoftmaxCH, true>),
+                      (softmax_fwd_tma_kernel<T, 256, kSoftmaxCH, true>),
+                      (softmax_fwd_tma_kernel<T, 512, kSoftmaxCH, true>))
+    case B200NORM_OP_SOFTMAX_BWD:
+      B200_TPR_SWITCH((softmax_bwd_tma_kernel<T, 32, false>), (softmax_bwd_tma_kernel<T, 128, false>),
+                      (softmax_bwd_tma_kernel<T, 256, false>), (softmax_bwd_tma_kernel<T, 512, false>))
+    case B200NORM_OP_LOGSOFTMAX_BWD:
+      B200_TPR_SWITCH((softmax_bwd_tma_kernel<T, 32, true>), (softmax_bwd_tma_kernel<T, 128, true>),
+                      (softmax_bwd_tma_kernel<T, 256, true>), (softmax_bwd_tma_kernel<T, 512, true>))
+    case B200NORM_OP_LAYERNORM_BWD:
+      B200_TPR_SWITCH((norm_bwd_tma_kernel<T, 32, kBwdCH_LN, true>), (norm_bwd_tma_kernel<T, 128, kBwdCH_LN, true>),
+                      (norm_bwd_tma_kernel<T, 256, kBwdCH_LN, true>), (norm_bwd_tma_kernel<T, 512, kBwdCH_LN, true>))
+    case B200NORM_OP_RMSNORM_BWD:
+      B200_TPR_SWITCH((norm_bwd_tma_kernel<T, 32, kBwdCH_RMS, false>), (norm_bwd_tma_kernel<T, 128, kBwdCH_RMS, false>),
+                      (norm_bwd_tma_kernel<T, 256, kBwdCH_RMS, false>), (norm_bwd_tma_kernel<T, 512, kBwdCH_RMS, false>))
+    default:
+      return nullptr;
+  }
+#undef B200_TPR_SWITCH
+}
+
+template <typename T>
+RingKernel generic_kernel_for(int op) {
+  switch (op) {
+    case B200NORM_OP_LAYERNORM_FWD: return generic_row_kernel<T, G_LAYERNORM_FWD>;
+    case B200NORM_OP_LAYERNORM_BWD: return generic_row_kernel<T, G_LAYERNORM_BWD>;
+    case B200NORM_OP_RMSNORM_FWD: return generic_row_kernel<T, G_RMSNORM_FWD>;
+    case B200NORM_OP_RMSNORM_BWD: return generic_row_kernel<T, G_RMSNORM_BWD>;
+    case B200NORM_OP_SOFTMAX_FWD: return generic_row_kernel<T, G_SOFTMAX_FWD>;
+    case B200NORM_OP_SOFTMAX_BWD: return generic_row_kernel<T, G_SOFTMAX_BWD>;
+    case B200NORM_OP_LOGSOFTMAX_FWD: return generic_row_kernel<T, G_LOGSOFTMAX_FWD>;
+    case B200NORM_OP_LOGSOFTMAX_BWD: return generic_row_kernel<T, G_LOGSOFTMAX_BWD>;
+    case B200NORM_OP_REDUCE_INNER: return generic_row_kernel<T, G_REDUCE_INNER>;
+    default: return nullptr;
+  }
+}
+
+template <typename T>
+int launch_typed(const b200norm_desc& d, const Plan& plan, RowParams& rp, void* dw, void* db, float* sums_f32,
+                 cudaStream_t stream) {
+  const bool want_cols = is_norm_bwd(d.op) && (d.flags & (B200NORM_F_OUT_DW | B200NORM_F_OUT_DB));
+  const int K = partial_k(d.op);
+  cudaError_t err;
+
+  if (plan.variant == B200NORM_VARIANT_GENERIC) {
+    if (d.op == B200NORM_OP_REDUCE_OUTER) {
+      dim3 grid((unsigned)ceil_div64(d.cols, 128), (unsigned)plan.nparts);
+      generic_colsum_kernel<T, 0><<<grid, 128, 0, stream>>>(rp, plan.rows_per_split);
+      g_launches++;
+      dim3 fgrid((unsigned)ceil_div64(d.cols, 32), 1);
+      finalize_partials_kernel<T><<<fgrid, dim3(32, 8), 0, stream>>>(rp.partials, plan.nparts, 1, (int)d.cols, dw,
+                                                                      nullptr, sums_f32);
+      g_launches++;
+    } else if (d.op == B200NORM_OP_FINALIZE_PARTIALS) {
+      dim3 fgrid((unsigned)ceil_div64(d.cols, 32), (unsigned)d.rows);
+      finalize_partials_kernel<T><<<fgrid, dim3(32, 8), 0, stream>>>(static_cast<const float*>(rp.in0), 1,
+                                                                      (int)d.rows, (int)d.cols, dw, db, nullptr);
+      g_launches++;
+    } else {
+      const bool need_rows = !is_norm_bwd(d.op) || (d.flags & B200NORM_F_OUT_DX);
+      if (need_rows) {
+        RingKernel k = generic_kernel_for<T>(d.op);
+        if (k == nullptr) return fail(B200NORM_ERR_UNSUPPORTED, "no generic kernel for op %d", d.op);
+        k<<<plan.grid, kGenericThreads, 0, stream>>>(rp);
+        g_launches++;
+      }
+      if (want_cols) {
+        dim3 grid((unsigned)ceil_div64(d.cols, 128), (unsigned)plan.nparts);
+        if (d.op == B200NORM_OP_LAYERNORM_BWD) {
+          generic_colsum_kernel<T, 1><<<grid, 128, 0, stream>>>(rp, plan.rows_per_split);
+        } else {
+          generic_colsum_kernel<T, 2><<<grid, 128, 0, stream>>>(rp, plan.rows_per_split);
+        }
+        g_launches++;
+        dim3 fgrid((unsigned)ceil_div64(d.cols, 32), (unsigned)K);
+        finalize_partials_kernel<T><<<fgrid, dim3(32, 8), 0, stream>>>(rp.partials, plan.nparts, K, (int)d.cols,
+                                                                        dw, db, sums_f32);
+        g_launches++;
+      }
+    }
+    err = cudaGetLastError();
+    if (err != cudaSuccess) return fail(B200NORM_ERR_CUDA + (int)err, "launch failed: %s", cudaGetErrorString(err));
+    return B200NORM_OK;
+  }
+
+  // ---- ring kernels ----
+  RingKernel k = ring_kernel_for<T>(d.op, plan.tpr);
+  if (k == nullptr) return fail(B200NORM_ERR_UNSUPPORTED, "no ring kernel for op %d tpr %d", d.op, plan.tpr);
+  err = cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
+  if (err != cudaSuccess) return fail(B200NORM_ERR_CUDA + (int)err, "smem attr: %s", cudaGetErrorString(err));
+  if (plan.cluster > 8) {
+    err = cudaFuncSetAttribute((const void*)k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (err != cudaSuccess) return fail(B200NORM_ERR_CUDA + (int)err, "cluster attr: %s", cudaGetErrorString(err));
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)plan.grid);
+  cfg.blockDim = dim3((unsigned)plan.block);
+  cfg.dynamicSmemBytes = plan.smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeClusterDimension;
+  attrs[0].val.clusterDim.x = (unsigned)plan.cluster;
+  attrs[0].val.clusterDim.y = 1;
+  attrs[0].val.clusterDim.z = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = 1;
+  err = cudaLaunchKernelEx(&cfg, k, (const RowParams)rp);
+  if (err != cudaSuccess) return fail(B200NORM_ERR_CUDA + (int)err, "ring launch failed: %s", cudaGetErrorString(err));
+  g_launches++;
+  if (want_cols) {
+    dim3 fgrid((unsigned)ceil_div64(d.cols, 32), (unsigned)K);
+    finalize_partials_kernel<T><<<fgrid, dim3(32, 8), 0, stream>>>(rp.partials, plan.nparts, K, (int)d.cols, dw, db,
+                                                                    sums_f32);
+    g_launches++;
+    err = cudaGetLastError();
+    if (err != cudaSuccess) return fail(B200NORM_ERR_CUDA + (int)err, "finalize launch failed: %s", cudaGetErrorString(err));
+  }
+  return B200NORM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// argument checks
+// ---------------------------------------------------------------------------
+bool is_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int check_matrix(const b200norm_tensor& t, const b200norm_desc& d, int dtype, const char* name, int64_t* row_stride) {
+  if (t.dtype != dtype) return fail(B200NORM_ERR_BAD_ARG, "%s: dtype %d, expected %d", name, t.dtype, dtype);
+  if (t.ndim != 2) return fail(B200NORM_ERR_BAD_ARG, "%s: expected a 2-D [rows, cols] view, got ndim %d", name, t.ndim);
+  if (t.sizes[0] != d.rows || t.sizes[1] != d.cols)
+    return fail(B200NORM_ERR_BAD_ARG, "%s: shape [%lld,%lld] != [%lld,%lld]", name, (long long)t.sizes[0],
+                (long long)t.sizes[1], (long long)d.rows, (long long)d.cols);
+  if (d.cols > 1 && t.strides[1] != 1)
+    return fail(B200NORM_ERR_UNSUPPORTED, "%s: innermost stride %lld != 1", name, (long long)t.strides[1]);
+  if (d.rows > 1 && t.strides[0] < d.cols)
+    return fail(B200NORM_ERR_UNSUPPORTED, "%s: overlapping rows (stride %lld < cols)", name, (long long)t.strides[0]);
+  if (t.data == nullptr && d.rows * d.cols > 0) return fail(B200NORM_ERR_BAD_ARG, "%s: null data", name);
+  *row_stride = d.rows > 1 ? t.strides[0] : d.cols;
+  return B200NORM_OK;
+}
+
+int check_vector(const b200norm_tensor& t, int64_t n, int dtype, const char* name) {
+  if (t.dtype != dtype) return fail(B200NORM_ERR_BAD_ARG, "%s: dtype %d, expected %d", name, t.dtype, dtype);
+  int64_t numel = 1;
+  int64_t expect_stride = 1;
+  bool contiguous = true;
+  for (int i = t.ndim - 1; i >= 0; --i) {
+    if (t.sizes[i] != 1 && t.strides[i] != expect_stride) contiguous = false;
+    expect_stride *= t.sizes[i];
+    numel *= t.sizes[i];
+  }
+  if (t.ndim < 1 || t.ndim > B200NORM_MAX_DIMS || numel != n)
+    return fail(B200NORM_ERR_BAD_ARG, "%s: expected %lld elements, got %lld", name, (long long)n, (long long)numel);
+  if (!contiguous) return fail(B200NORM_ERR_UNSUPPORTED, "%s: must be contiguous", name);
+  if (t.data == nullptr && n > 0) return fail(B200NORM_ERR_BAD_ARG, "%s: null data", name);
+  return B200NORM_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// exported C ABI
+// ---------------------------------------------------------------------------
+extern "C" {
+
+int b200norm_abi_version(void) { return B200NORM_ABI_VERSION; }
+
+const char* b200norm_last_error(void) { return g_err; }
+
+uint64_t b200norm_launch_count(void) { return g_launches.load(); }
+
+const char* b200norm_variant_name(int variant) {
+  switch (variant) {
+    case B200NORM_VARIANT_AUTO: return "auto";
+    case B200NORM_VARIANT_GENERIC: return "generic";
+    case B200NORM_VARIANT_TMA: return "tma";
+    case B200NORM_VARIANT_CLUSTER: return "cluster";
+    default: return "?";
+  }
+}
+
+int b200norm_device_info(int* has_device, int* sm_count, int* smem_per_block_optin, int* cc_major, int* cc_minor) {
+  const DeviceInfo& d = device_info();
+  if (has_device) *has_device = d.has_device;
+  if (sm_count) *sm_count = d.sm_count;
+  if (smem_per_block_optin) *smem_per_block_optin = d.smem_optin;
+  if (cc_major) *cc_major = d.cc_major;
+  if (cc_minor) *cc_minor = d.cc_minor;
+  return 0;
+}
+
+int b200norm_query(const b200norm_desc* desc, b200norm_plan* plan) {
+  int rc = check_desc(desc);
+  if (rc != B200NORM_OK) return rc;
+  Plan p;
+  // rows are assumed 16-byte aligned and contiguous at query time; the launch
+  // re-plans with the real pointers (the workspace bound covers both outcomes).
+  rc = make_plan(*desc, /*aligned=*/true, /*rows_contiguous=*/true, &p);
+  if (rc != B200NORM_OK) return rc;
+  if (plan != nullptr) fill_public_plan(*desc, p, plan);
+  return B200NORM_OK;
+}
+
+size_t b200norm_workspace_bytes(const b200norm_desc* desc) {
+  b200norm_plan plan;
+  if (b200norm_query(desc, &plan) != B200NORM_OK) return 0;
+  return (size_t)plan.workspace_bytes;
+}
+
+int b200norm_launch(const b200norm_desc* desc, const b200norm_tensor* inputs, int n_inputs,
+                    const b200norm_tensor* outputs, int n_outputs, void* workspace, size_t workspace_bytes,
+                    void* stream_v) {
+  int rc = check_desc(desc);
+  if (rc != B200NORM_OK) return rc;
+  const b200norm_desc& d = *desc;
+  const DeviceInfo& dev = device_info();
+  if (!dev.has_device) return fail(B200NORM_ERR_NO_DEVICE, "no CUDA device visible (there is no CPU fallback)");
+  if (dev.cc_major != 10)
+    return fail(B200NORM_ERR_NO_DEVICE, "device is sm_%d%d; this library contains sm_100a code only", dev.cc_major,
+                dev.cc_minor);
+  if ((n_inputs > 0 && inputs == nullptr) || (n_outputs > 0 && outputs == nullptr))
+    return fail(B200NORM_ERR_BAD_ARG, "null tensor list");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+
+  const int dt = d.io_dtype;
+  const bool has_w = (d.flags & B200NORM_F_HAS_WEIGHT) != 0;
+  const bool has_b = (d.flags & B200NORM_F_HAS_BIAS) != 0;
+  RowParams rp;
+  memset(&rp, 0, sizeof(rp));
+  rp.rows = d.rows;
+  rp.cols = (int32_t)d.cols;
+  rp.eps = (float)d.eps;
+  rp.inv_n = d.cols > 0 ? (float)(1.0 / (double)d.cols) : 0.f;
+  rp.n_f = (float)d.cols;
+  rp.flags = d.flags;
+  void* dw = nullptr;
+  void* db = nullptr;
+  float* sums_f32 = nullptr;
+  int ii = 0, oi = 0;
+  bool aligned = true;
+  bool rows_contiguous = true;
+
+#define NEED_IN(n)  if (ii + (n) > n_inputs) return fail(B200NORM_ERR_BAD_ARG, "op %d: too few inputs (%d)", d.op, n_inputs)
+#define NEED_OUT(n) if (oi + (n) > n_outputs) return fail(B200NORM_ERR_BAD_ARG, "op %d: too few outputs (%d)", d.op, n_outputs)
+#define CHECK(expr) do { rc = (expr); if (rc != B200NORM_OK) return rc; } while (0)
+
+  auto bind_in_matrix = [&](const void** ptr, int64_t* stride, const char* name) -> int {
+    const b200norm_tensor& t = inputs[ii++];
+    int r = check_matrix(t, d, dt, name, stride);
+    if (r != B200NORM_OK) return r;
+    *ptr = t.data;
+    if (!is_aligned16(t.data) || ((*stride * elem_size(dt)) % 16) != 0) aligned = false;
+    if (*stride != d.cols) rows_contiguous = false;
+    return B200NORM_OK;
+  };
+  auto bind_out_matrix = [&](void** ptr, int64_t* stride, const char* name) -> int {
+    const b200norm_tensor& t = outputs[oi++];
+    int r = check_matrix(t, d, dt, name, stride);
+    if (r != B200NORM_OK) return r;
+    *ptr = t.data;
+    if (!is_aligned16(t.data) || ((*stride * elem_size(dt)) % 16) != 0) aligned = false;
+    return B200NORM_OK;
+  };
+  auto bind_vec = [&](const b200norm_tensor& t, int64_t n, int dtype, const char* name, void** ptr) -> int {
+    int r = check_vector(t, n, dtype, name);
+    if (r != B200NORM_OK) return r;
+    *ptr = t.data;
+    return B200NORM_OK;
+  };
+
+  switch (d.op) {
+    case B200NORM_OP_LAYERNORM_FWD:
+    case B200NORM_OP_RMSNORM_FWD: {
+      const bool ln = d.op == B200NORM_OP_LAYERNORM_FWD;
+      NEED_IN(1 + (has_w ? 1 : 0) + ((ln && has_b) ? 1 : 0));
+      CHECK(bind_in_matrix(&rp.in0, &rp.in0_stride, "x"));
+      if (has_w) {
+        void* w = nullptr;
+        CHECK(bind_vec(inputs[ii++], d.cols, dt, "weight", &w));
+        rp.weight = w;
+        if (!is_aligned16(w)) aligned = false;
+      }
+      if (ln && has_b) {
+        void* b = nullptr;
+        CHECK(bind_vec(inputs[ii++], d.cols, dt, "bias", &b));
+        rp.bias = b;
+        if (!is_aligned16(b)) aligned = false;
+      }
+      NEED_OUT(1);
+      CHECK(bind_out_matrix(&rp.out0, &rp.out_stride, "y"));
+      if (ln) {
+        if (d.flags & B200NORM_F_OUT_MEAN) {
+          NEED_OUT(1);
+          void* m = nullptr;
+          CHECK(bind_vec(outputs[oi++], d.rows, B200NORM_DT_F32, "mean", &m));
+          rp.stat0 = static_cast<float*>(m);
+        }
+        if (d.flags & B200NORM_F_OUT_INVSTD) {
+          NEED_OUT(1);
+          void* m = nullptr;
+          CHECK(bind_vec(outputs[oi++], d.rows, B200NORM_DT_F32, "invstd", &m));
+          rp.stat1 = static_cast<float*>(m);
+        }
+      } else {
+        NEED_OUT(1);
+        void* m = nullptr;
+        CHECK(bind_vec(outputs[oi++], d.rows, B200NORM_DT_F32, "stat", &m));
+        rp.stat1 = static_cast<float*>(m);
+      }
+      break;
+    }
+    case B200NORM_OP_LAYERNORM_BWD:
+    case B200NORM_OP_RMSNORM_BWD: {
+      const bool ln = d.op == B200NORM_OP_LAYERNORM_BWD;
+      NEED_IN(2 + (ln ? 2 : 1) + (has_w ? 1 : 0));
+      CHECK(bind_in_matrix(&rp.in0, &rp.in0_stride, "dy"));
+      CHECK(bind_in_matrix(&rp.in1, &rp.in1_stride, "x"));
+      if (ln) {
+        void* m = nullptr;
+        CHECK(bind_vec(inputs[ii++], d.rows, B200NORM_DT_F32, "mean", &m));
+        rp.stat0 = static_cast<float*>(m);
+      }
+      {
+        void* m = nullptr;
+        CHECK(bind_vec(inputs[ii++], d.rows, B200NORM_DT_F32, ln ? "invstd" : "stat", &m));
+        rp.stat1 = static_cast<float*>(m);
+      }
+      if (has_w) {
+        void* w = nullptr;
+        CHECK(bind_vec(inputs[ii++], d.cols, dt, "weight", &w));
+        rp.weight = w;
+        if (!is_aligned16(w)) aligned = false;
+      }
+      if (d.flags & B200NORM_F_OUT_DX) {
+        NEED_OUT(1);
+        CHECK(bind_out_matrix(&rp.out0, &rp.out_stride, "dx"));
+      }
+      const bool want_dw = (d.flags & B200NORM_F_OUT_DW) != 0;
+      const bool want_db = ln && (d.flags & B200NORM_F_OUT_DB) != 0;
+      if (want_dw || want_db) {
+        if (d.flags & B200NORM_F_PARTIALS_F32) {
+          NEED_OUT(1);
+          void* s = nullptr;
+          CHECK(bind_vec(outputs[oi++], (int64_t)partial_k(d.op) * d.cols, B200NORM_DT_F32, "column sums", &s));
+          sums_f32 = static_cast<float*>(s);
+        } else {
+          if (want_dw) {
+            NEED_OUT(1);
+            CHECK(bind_vec(outputs[oi++], d.cols, dt, "dweight", &dw));
+          }
+          if (want_db) {
+            NEED_OUT(1);
+            CHECK(bind_vec(outputs[oi++], d.cols, dt, "dbias", &db));
+          }
+        }
+      }
+      break;
+    }
+    case B200NORM_OP_SOFTMAX_FWD:
+    case B200NORM_OP_LOGSOFTMAX_FWD:
+      NEED_IN(1);
+      NEED_OUT(1);
+      CHECK(bind_in_matrix(&rp.in0, &rp.in0_stride, "x"));
+      CHECK(bind_out_matrix(&rp.out0, &rp.out_stride, "y"));
+      break;
+    case B200NORM_OP_SOFTMAX_BWD:
+    case B200NORM_OP_LOGSOFTMAX_BWD:
+      NEED_IN(2);
+      NEED_OUT(1);
+      CHECK(bind_in_matrix(&rp.in0, &rp.in0_stride, "dy"));
+      CHECK(bind_in_matrix(&rp.in1, &rp.in1_stride, "y"));
+      CHECK(bind_out_matrix(&rp.out0, &rp.out_stride, "dx"));
+      break;
+    case B200NORM_OP_REDUCE_INNER: {
+      NEED_IN(1);
+      NEED_OUT(1);
+      CHECK(bind_in_matrix(&rp.in0, &rp.in0_stride, "x"));
+      void* r = nullptr;
+      CHECK(bind_vec(outputs[oi++], d.rows, dt, "result", &r));
+      rp.out0 = r;
+      break;
+    }
+    case B200NORM_OP_REDUCE_OUTER: {
+      NEED_IN(1);
+      NEED_OUT(1);
+      CHECK(bind_in_matrix(&rp.in0, &rp.in0_stride, "x"));
+      if (d.flags & (B200NORM_F_REDUCE_MAX | B200NORM_F_REDUCE_FMAX))
+        return fail(B200NORM_ERR_UNSUPPORTED, "outer max reductions are not on the hot path");
+      if (d.flags & B200NORM_F_PARTIALS_F32) {
+        void* s = nullptr;
+        CHECK(bind_vec(outputs[oi++], d.cols, B200NORM_DT_F32, "column sums", &s));
+        sums_f32 = static_cast<float*>(s);
+      } else {
+        CHECK(bind_vec(outputs[oi++], d.cols, dt, "result", &dw));
+      }
+      break;
+    }
+    case B200NORM_OP_FINALIZE_PARTIALS: {
+      NEED_IN(1);
+      if (d.rows < 1 || d.rows > 2) return fail(B200NORM_ERR_BAD_ARG, "finalize: rows (K) must be 1 or 2");
+      NEED_OUT((int)d.rows);
+      void* s = nullptr;
+      CHECK(bind_vec(inputs[ii++], d.rows * d.cols, B200NORM_DT_F32, "sums", &s));
+      rp.in0 = s;
+      CHECK(bind_vec(outputs[oi++], d.cols, dt, "out0", &dw));
+      if (d.rows == 2) CHECK(bind_vec(outputs[oi++], d.cols, dt, "out1", &db));
+      break;
+    }
+    default:
+      return fail(B200NORM_ERR_UNSUPPORTED, "op %d", d.op);
+  }
+#undef NEED_IN
+#undef NEED_OUT
+#undef CHECK
+
+  // outputs aliased to inputs are rejected, as the precedent does
+  // (cutlass_executor.cpp:101-104)
+  for (int o = 0; o < n_outputs; ++o) {
+    for (int i = 0; i < n_inputs; ++i) {
+      if (outputs[o].data != nullptr && outputs[o].data == inputs[i].data)
+        return fail(B200NORM_ERR_UNSUPPORTED, "output %d aliases input %d", o, i);
+    }
+  }
+
+  Plan plan;
+  rc = make_plan(d, aligned, rows_contiguous, &plan);
+  if (rc != B200NORM_OK) return rc;
+
+  if (d.rows == 0 || d.cols == 0) {
+    // empty iteration or reduction domain: outer sums are zero-filled, nothing else to do
+    if (d.cols > 0 && d.rows == 0) {
+      const size_t es = elem_size(dt);
+      if (dw != nullptr) cudaMemsetAsync(dw, 0, d.cols * es, stream);
+      if (db != nullptr) cudaMemsetAsync(db, 0, d.cols * es, stream);
+      if (sums_f32 != nullptr) cudaMemsetAsync(sums_f32, 0, (size_t)partial_k(d.op) * d.cols * 4, stream);
+    }
+    return B200NORM_OK;
+  }
+
+  const bool needs_ws = plan.ws_bytes > B200NORM_WS_HEADER_BYTES;
+  if (needs_ws) {
+    if (workspace == nullptr || workspace_bytes < plan.ws_bytes)
+      return fail(B200NORM_ERR_WORKSPACE, "workspace %zu bytes, need %llu", workspace_bytes,
+                  (unsigned long long)plan.ws_bytes);
+    if ((reinterpret_cast<uintptr_t>(workspace) & 255u) != 0)
+      return fail(B200NORM_ERR_WORKSPACE, "workspace must be 256-byte aligned");
+    rp.partials = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + B200NORM_WS_HEADER_BYTES);
+  }
+
+  rp.groups = plan.groups;
+  rp.stages = plan.stages;
+  rp.tile_rows = plan.tile_rows;
+  rp.cols_cta = plan.cluster > 0 ? (int32_t)(d.cols / plan.cluster) : (int32_t)d.cols;
+  rp.nstreams = n_streams(d.op);
+  rp.contiguous = plan.contiguous;
+  rp.slice_bytes = plan.slice_bytes;
+  rp.stream_bytes = plan.stream_bytes;
+  rp.stage_bytes = plan.stage_bytes;
+  rp.off_red = plan.off_red;
+  rp.off_cls = plan.off_cls;
+  rp.off_weight = plan.off_weight;
+  rp.off_bias = plan.off_bias;
+  rp.off_ring = plan.off_ring;
+  rp.off_acc = plan.off_ring;
+
+  switch (dt) {
+    case B200NORM_DT_F32: return launch_typed<float>(d, plan, rp, dw, db, sums_f32, stream);
+    case B200NORM_DT_BF16: return launch_typed<__nv_bfloat16>(d, plan, rp, dw, db, sums_f32, stream);
+    case B200NORM_DT_F16: return launch_typed<__half>(d, plan, rp, dw, db, sums_f32, stream);
+    default: return fail(B200NORM_ERR_UNSUPPORTED, "dtype %d", dt);
+  }
+}
+
+}  // extern "C"

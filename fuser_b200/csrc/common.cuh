@@ -1,0 +1,331 @@
+// common.cuh — device-side building blocks for the b200norm kernels (sm_100a only).
+//
+// What lives here is the hand-written equivalent of the helper layer nvFuser
+// stringifies into every generated kernel (reference: runtime/warp.cu,
+// runtime/mbarrier.cu, runtime/memory.cu:104-130, runtime/cluster.cu:15-130,
+// runtime/array.cu:202-400, runtime/casts.cu:431-447). Nothing is copied from
+// there; the primitives are re-derived from the PTX ISA for the pipeline shape
+// used in this library: a ring of shared-memory stages filled by 1-D bulk
+// copies (TMA) and drained by groups of consumer warps.
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200norm {
+
+// ----------------------------------------------------------------------------
+// small utilities
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// A spin that can never hang the device: after ~4 s of waiting the kernel traps
+// (the launch then surfaces cudaErrorLaunchFailed instead of wedging the box).
+struct Watchdog {
+  uint32_t spins = 0;
+  uint64_t t0 = 0;
+  __device__ __forceinline__ void tick() {
+    if ((++spins & 0x3fffu) == 0) {
+      uint64_t now = global_timer_ns();
+      if (t0 == 0) {
+        t0 = now;
+      } else if (now - t0 > 4000000000ull) {
+        __trap();
+      }
+    }
+  }
+};
+
+// ----------------------------------------------------------------------------
+// mbarrier (shared::cta) — arrive / expect_tx / parity wait
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  Watchdog wd;
+  while (!mbar_try_wait(bar, parity)) {
+    wd.tick();
+  }
+}
+
+// ----------------------------------------------------------------------------
+// TMA 1-D bulk copy global -> shared with mbarrier completion
+// (SASS: UBLKCP). Address and size must be multiples of 16 bytes.
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes,
+                                         uint32_t bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1], %2, [%3], %4;"
+      ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+      : "memory");
+}
+// shared -> global bulk store (SASS: UBLKCP / UTMASTG family), bulk_group completion.
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
+               "r"(src_smem), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+
+// ----------------------------------------------------------------------------
+// named barriers (bar.sync id, nthreads) for sub-CTA consumer groups
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// ----------------------------------------------------------------------------
+// thread-block cluster / DSMEM
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n"
+               "barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+// Remote (or local) shared store of one float that completes 4 tx-bytes on the
+// destination CTA's mbarrier.
+__device__ __forceinline__ void st_async_f32(uint32_t remote_addr, float v, uint32_t remote_bar) {
+  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.f32 [%0], %1, [%2];"
+               ::"r"(remote_addr), "f"(v), "r"(remote_bar)
+               : "memory");
+}
+
+// ----------------------------------------------------------------------------
+// global memory access with cache hints
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ void stg_128_stream(void* p, const uint4& v) {
+  asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y),
+               "r"(v.z), "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ uint4 ldg_128_nc(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint4 lds_128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y),
+               "r"(v.z), "r"(v.w)
+               : "memory");
+}
+
+// ----------------------------------------------------------------------------
+// dtype traits: a "chunk" is 16 bytes = VEC elements
+// bf16/fp16 -> fp32 is exact; fp32 -> bf16/fp16 is round-to-nearest-even, the
+// same rounding ATen's .to() and the reference's casts use (runtime/casts.cu:431-447).
+// ----------------------------------------------------------------------------
+template <typename T>
+struct IO;
+
+template <>
+struct IO<float> {
+  static constexpr int VEC = 4;
+  static constexpr int DT = 0;
+  __device__ __forceinline__ static void unpack(const uint4& v, float (&f)[4]) {
+    f[0] = __uint_as_float(v.x);
+    f[1] = __uint_as_float(v.y);
+    f[2] = __uint_as_float(v.z);
+    f[3] = __uint_as_float(v.w);
+  }
+  __device__ __forceinline__ static uint4 pack(const float (&f)[4]) {
+    return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]),
+                      __float_as_uint(f[3]));
+  }
+  __device__ __forceinline__ static float to_f32(float v) { return v; }
+  __device__ __forceinline__ static float from_f32(float v) { return v; }
+  __device__ __forceinline__ static float round_trip(float v) { return v; }
+};
+
+template <>
+struct IO<__nv_bfloat16> {
+  static constexpr int VEC = 8;
+  static constexpr int DT = 1;
+  __device__ __forceinline__ static void unpack(const uint4& v, float (&f)[8]) {
+    f[0] = __uint_as_float(v.x << 16);
+    f[1] = __uint_as_float(v.x & 0xffff0000u);
+    f[2] = __uint_as_float(v.y << 16);
+    f[3] = __uint_as_float(v.y & 0xffff0000u);
+    f[4] = __uint_as_float(v.z << 16);
+    f[5] = __uint_as_float(v.z & 0xffff0000u);
+    f[6] = __uint_as_float(v.w << 16);
+    f[7] = __uint_as_float(v.w & 0xffff0000u);
+  }
+  __device__ __forceinline__ static uint32_t pack2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+  }
+  __device__ __forceinline__ static uint4 pack(const float (&f)[8]) {
+    return make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
+  }
+  __device__ __forceinline__ static float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+  __device__ __forceinline__ static __nv_bfloat16 from_f32(float v) {
+    return __float2bfloat16_rn(v);
+  }
+  __device__ __forceinline__ static float round_trip(float v) {
+    return __bfloat162float(__float2bfloat16_rn(v));
+  }
+};
+
+template <>
+struct IO<__half> {
+  static constexpr int VEC = 8;
+  static constexpr int DT = 2;
+  __device__ __forceinline__ static void unpack2(uint32_t u, float& lo, float& hi) {
+    __half2 h = *reinterpret_cast<__half2*>(&u);
+    float2 f = __half22float2(h);
+    lo = f.x;
+    hi = f.y;
+  }
+  __device__ __forceinline__ static void unpack(const uint4& v, float (&f)[8]) {
+    unpack2(v.x, f[0], f[1]);
+    unpack2(v.y, f[2], f[3]);
+    unpack2(v.z, f[4], f[5]);
+    unpack2(v.w, f[6], f[7]);
+  }
+  __device__ __forceinline__ static uint32_t pack2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+  }
+  __device__ __forceinline__ static uint4 pack(const float (&f)[8]) {
+    return make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
+  }
+  __device__ __forceinline__ static float to_f32(__half v) { return __half2float(v); }
+  __device__ __forceinline__ static __half from_f32(float v) { return __float2half_rn(v); }
+  __device__ __forceinline__ static float round_trip(float v) {
+    return __half2float(__float2half_rn(v));
+  }
+};
+
+// ----------------------------------------------------------------------------
+// reductions
+// ----------------------------------------------------------------------------
+struct SumOp {
+  __device__ __forceinline__ static float identity() { return 0.f; }
+  __device__ __forceinline__ static float apply(float a, float b) { return a + b; }
+};
+// NaN-propagating max (at::amax semantics, ir/internal_nodes.cpp:1763-1765).
+struct MaxOp {
+  __device__ __forceinline__ static float identity() { return -INFINITY; }
+  __device__ __forceinline__ static float apply(float a, float b) {
+    float r;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+  }
+};
+// NaN-ignoring max (fmax semantics; all-NaN rows still give NaN because the
+// identity never enters: handled by the callers through a separate flag).
+struct FMaxOp {
+  __device__ __forceinline__ static float identity() { return -INFINITY; }
+  __device__ __forceinline__ static float apply(float a, float b) { return fmaxf(a, b); }
+};
+
+template <typename Op, int NV>
+__device__ __forceinline__ void warp_allreduce(float (&v)[NV]) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      v[i] = Op::apply(v[i], __shfl_xor_sync(0xffffffffu, v[i], off));
+    }
+  }
+}
+
+// Fast exp for 16-bit outputs (one MUFU.EX2 per element); accurate expf for fp32.
+template <typename T>
+__device__ __forceinline__ float exp_for(float x) {
+  if constexpr (sizeof(T) == 4) {
+    return expf(x);
+  } else {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+    return y;
+  }
+}
+
+__host__ __device__ __forceinline__ constexpr int64_t ceil_div64(int64_t a, int64_t b) {
+  return (a + b - 1) / b;
+}
+__host__ __device__ __forceinline__ constexpr int round_up_int(int a, int b) {
+  return (a + b - 1) / b * b;
+}
+
+}  // namespace b200norm

@@ -1,0 +1,265 @@
+// kernels_generic.cuh — shape-agnostic kernels: any N, any row stride, any
+// alignment. One CTA per row (grid-stride over rows), scalar coalesced accesses,
+// the row is re-read from L1/L2 between passes. These are the landing spot for
+// the shapes the reference tests that no vectorised path can take (hidden sizes
+// 3, 1987, N+2 ..., tests/cpp/test_combined_inner_outer_reduction.cpp:143-166) and
+// for rows too wide for any persistent variant (the reference then segments into
+// Reduction + pointwise kernels, scheduler/normalization_inner.cpp:153-161).
+// Also here: the outer (column) reduction used for dgamma/dbeta in that case
+// (scheduler/reduction.cpp, the Reduction scheduler's outer case) and the
+// finishing kernel for fp32 partial column sums.
+#pragma once
+
+#include "kernels_tma_fwd.cuh"
+
+namespace b200norm {
+
+constexpr int kGenericThreads = 256;
+
+template <typename Op, int NV>
+__device__ __forceinline__ void block_allreduce(float (&v)[NV], float* red /* [2][8][kRedNV] */,
+                                                uint32_t& phase) {
+  warp_allreduce<Op, NV>(v);
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  float* slots = red + phase * (kGenericThreads / 32) * kRedNV;
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) slots[warp * kRedNV + i] = v[i];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = Op::identity();
+#pragma unroll
+  for (int w = 0; w < kGenericThreads / 32; ++w) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = Op::apply(v[i], slots[w * kRedNV + i]);
+  }
+  phase ^= 1u;
+}
+
+enum GenericOp : int {
+  G_LAYERNORM_FWD = 0,
+  G_LAYERNORM_BWD = 1,
+  G_RMSNORM_FWD = 2,
+  G_RMSNORM_BWD = 3,
+  G_SOFTMAX_FWD = 4,
+  G_SOFTMAX_BWD = 5,
+  G_LOGSOFTMAX_FWD = 6,
+  G_LOGSOFTMAX_BWD = 7,
+  G_REDUCE_INNER = 8
+};
+
+template <typename T, int OP>
+__global__ void __launch_bounds__(kGenericThreads) generic_row_kernel(const RowParams p) {
+  __shared__ float red[2 * (kGenericThreads / 32) * kRedNV];
+  uint32_t phase = 0;
+  const T* __restrict__ in0 = static_cast<const T*>(p.in0);
+  const T* __restrict__ in1 = static_cast<const T*>(p.in1);
+  T* __restrict__ out0 = static_cast<T*>(p.out0);
+  const T* __restrict__ wgt = static_cast<const T*>(p.weight);
+  const T* __restrict__ bia = static_cast<const T*>(p.bias);
+  const int N = p.cols;
+  const int tid = threadIdx.x;
+  for (int64_t row = blockIdx.x; row < p.rows; row += gridDim.x) {
+    const T* a = in0 + row * p.in0_stride;
+    const T* b = in1 != nullptr ? in1 + row * p.in1_stride : nullptr;
+    T* o = out0 != nullptr ? out0 + row * p.out_stride : nullptr;
+
+    if constexpr (OP == G_RMSNORM_FWD) {
+      float ss[1] = {0.f};
+      for (int c = tid; c < N; c += kGenericThreads) {
+        const float x = IO<T>::to_f32(a[c]);
+        ss[0] = fmaf(x, x, ss[0]);
+      }
+      block_allreduce<SumOp, 1>(ss, red, phase);
+      const float ve = ss[0] * p.inv_n + p.eps;
+      const float invstd = __frsqrt_rn(ve);
+      const float rms = __fsqrt_rn(ve);
+      const float scale = (p.flags & kFlagStatIsRms) ? __frcp_rn(rms) : invstd;
+      for (int c = tid; c < N; c += kGenericThreads) {
+        float y = IO<T>::to_f32(a[c]) * scale;
+        if (wgt != nullptr) y *= IO<T>::to_f32(wgt[c]);
+        o[c] = IO<T>::from_f32(y);
+      }
+      if (tid == 0 && p.stat1 != nullptr) p.stat1[row] = (p.flags & kFlagStatIsRms) ? rms : invstd;
+    } else if constexpr (OP == G_LAYERNORM_FWD) {
+      float s[1] = {0.f};
+      for (int c = tid; c < N; c += kGenericThreads) s[0] += IO<T>::to_f32(a[c]);
+      block_allreduce<SumOp, 1>(s, red, phase);
+      const float mean = s[0] * p.inv_n;
+      float m2[1] = {0.f};
+      for (int c = tid; c < N; c += kGenericThreads) {
+        const float d = IO<T>::to_f32(a[c]) - mean;
+        m2[0] = fmaf(d, d, m2[0]);
+      }
+      block_allreduce<SumOp, 1>(m2, red, phase);
+      const float invstd = __frsqrt_rn(m2[0] * p.inv_n + p.eps);
+      for (int c = tid; c < N; c += kGenericThreads) {
+        float y = (IO<T>::to_f32(a[c]) - mean) * invstd;
+        if (wgt != nullptr) y *= IO<T>::to_f32(wgt[c]);
+        if (bia != nullptr) y += IO<T>::to_f32(bia[c]);
+        o[c] = IO<T>::from_f32(y);
+      }
+      if (tid == 0) {
+        if (p.stat0 != nullptr) p.stat0[row] = mean;
+        if (p.stat1 != nullptr) p.stat1[row] = invstd;
+      }
+    } else if constexpr (OP == G_SOFTMAX_FWD || OP == G_LOGSOFTMAX_FWD) {
+      constexpr bool LOG = OP == G_LOGSOFTMAX_FWD;
+      float m[1] = {-INFINITY};
+      for (int c = tid; c < N; c += kGenericThreads) m[0] = MaxOp::apply(m[0], IO<T>::to_f32(a[c]));
+      block_allreduce<MaxOp, 1>(m, red, phase);
+      float s[1] = {0.f};
+      for (int c = tid; c < N; c += kGenericThreads) s[0] += exp_for<T>(IO<T>::to_f32(a[c]) - m[0]);
+      block_allreduce<SumOp, 1>(s, red, phase);
+      const float fin = LOG ? logf(s[0]) : __frcp_rn(s[0]);
+      for (int c = tid; c < N; c += kGenericThreads) {
+        const float d = IO<T>::to_f32(a[c]) - m[0];
+        o[c] = IO<T>::from_f32(LOG ? (d - fin) : (exp_for<T>(d) * fin));
+      }
+    } else if constexpr (OP == G_SOFTMAX_BWD || OP == G_LOGSOFTMAX_BWD) {
+      constexpr bool LOG = OP == G_LOGSOFTMAX_BWD;
+      float s[1] = {0.f};
+      for (int c = tid; c < N; c += kGenericThreads) {
+        const float dy = IO<T>::to_f32(a[c]);
+        if constexpr (LOG) {
+          s[0] += dy;
+        } else {
+          s[0] = fmaf(dy, IO<T>::to_f32(b[c]), s[0]);
+        }
+      }
+      block_allreduce<SumOp, 1>(s, red, phase);
+      float sum = s[0];
+      if (p.flags & kFlagRoundRowsum) sum = IO<T>::round_trip(sum);
+      for (int c = tid; c < N; c += kGenericThreads) {
+        const float dy = IO<T>::to_f32(a[c]);
+        const float y = IO<T>::to_f32(b[c]);
+        o[c] = IO<T>::from_f32(LOG ? (dy - expf(y) * sum) : (y * dy - y * sum));
+      }
+    } else if constexpr (OP == G_LAYERNORM_BWD || OP == G_RMSNORM_BWD) {
+      constexpr bool LN = OP == G_LAYERNORM_BWD;
+      // a = dy, b = x; dx only (dgamma/dbeta come from generic_colsum_kernel)
+      const bool centered = LN || (p.flags & kFlagRmsBwdCentered) != 0;
+      const float mean = LN ? p.stat0[row] : 0.f;
+      const float st = p.stat1[row];
+      const float invstd = (!LN && (p.flags & kFlagStatIsRms)) ? __frcp_rn(st) : st;
+      float s[2] = {0.f, 0.f};
+      for (int c = tid; c < N; c += kGenericThreads) {
+        const float xh = (IO<T>::to_f32(b[c]) - mean) * invstd;
+        float gg = IO<T>::to_f32(a[c]);
+        if (wgt != nullptr) gg *= IO<T>::to_f32(wgt[c]);
+        s[0] += gg;
+        s[1] = fmaf(gg, xh, s[1]);
+      }
+      block_allreduce<SumOp, 2>(s, red, phase);
+      const float s1 = centered ? s[0] : 0.f;
+      const float aa = invstd * p.inv_n;
+      for (int c = tid; c < N; c += kGenericThreads) {
+        const float xh = (IO<T>::to_f32(b[c]) - mean) * invstd;
+        float gg = IO<T>::to_f32(a[c]);
+        if (wgt != nullptr) gg *= IO<T>::to_f32(wgt[c]);
+        o[c] = IO<T>::from_f32(aa * ((p.n_f * gg - s1) - xh * s[1]));
+      }
+    } else if constexpr (OP == G_REDUCE_INNER) {
+      // sum / amax / fmax over the row -> stat1-less: result goes to out0[row] (io dtype)
+      T* r = static_cast<T*>(p.out0);
+      if (p.flags & (kFlagReduceMax | kFlagReduceFmax)) {
+        const bool nan_prop = (p.flags & kFlagReduceMax) != 0;
+        float m[2] = {-INFINITY, 0.f};  // m[1] counts non-NaN elements (for all-NaN rows under fmax)
+        if (nan_prop) {
+          for (int c = tid; c < N; c += kGenericThreads) m[0] = MaxOp::apply(m[0], IO<T>::to_f32(a[c]));
+          float mm[1] = {m[0]};
+          block_allreduce<MaxOp, 1>(mm, red, phase);
+          if (tid == 0) r[row] = IO<T>::from_f32(mm[0]);
+        } else {
+          for (int c = tid; c < N; c += kGenericThreads) {
+            const float x = IO<T>::to_f32(a[c]);
+            if (x == x) {
+              m[0] = fmaxf(m[0], x);
+              m[1] += 1.f;
+            }
+          }
+          float mm[1] = {m[0]};
+          float cnt[1] = {m[1]};
+          block_allreduce<FMaxOp, 1>(mm, red, phase);
+          block_allreduce<SumOp, 1>(cnt, red, phase);
+          if (tid == 0) r[row] = IO<T>::from_f32(cnt[0] > 0.f ? mm[0] : __int_as_float(0x7fc00000));
+        }
+      } else {
+        float s[1] = {0.f};
+        for (int c = tid; c < N; c += kGenericThreads) s[0] += IO<T>::to_f32(a[c]);
+        block_allreduce<SumOp, 1>(s, red, phase);
+        if (tid == 0) r[row] = IO<T>::from_f32(s[0]);
+      }
+    }
+  }
+}
+
+// Column sums over a row range: partials[split][K][N] (fp32).
+//   MODE 0: plain sum of in0                               (K = 1)
+//   MODE 1: LayerNorm  dw = sum dy*x_hat, db = sum dy      (K = 2)
+//   MODE 2: RMSNorm    dw = sum dy*x_hat                   (K = 1)
+// grid = (ceil(N/128), nsplit), block = 128: one column per thread, coalesced.
+template <typename T, int MODE>
+__global__ void __launch_bounds__(128) generic_colsum_kernel(const RowParams p, int rows_per_split) {
+  const int col = blockIdx.x * 128 + threadIdx.x;
+  if (col >= p.cols) return;
+  const T* __restrict__ in0 = static_cast<const T*>(p.in0);
+  const T* __restrict__ in1 = static_cast<const T*>(p.in1);
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_split;
+  const int64_t r1 = min(p.rows, r0 + rows_per_split);
+  float acc_w = 0.f, acc_b = 0.f;
+  for (int64_t r = r0; r < r1; ++r) {
+    const float a = IO<T>::to_f32(in0[r * p.in0_stride + col]);
+    if constexpr (MODE == 0) {
+      acc_w += a;
+    } else {
+      const float mean = MODE == 1 ? p.stat0[r] : 0.f;
+      const float st = p.stat1[r];
+      const float invstd = (MODE == 2 && (p.flags & kFlagStatIsRms)) ? __frcp_rn(st) : st;
+      const float xh = (IO<T>::to_f32(in1[r * p.in1_stride + col]) - mean) * invstd;
+      acc_w = fmaf(a, xh, acc_w);
+      acc_b += a;
+    }
+  }
+  constexpr int K = MODE == 1 ? 2 : 1;
+  float* dst = p.partials + (size_t)blockIdx.y * K * p.cols;
+  dst[col] = acc_w;
+  if constexpr (MODE == 1) dst[p.cols + col] = acc_b;
+}
+
+// Finish fp32 partial column sums: out_k[n] = cast(sum_p partials[p][k][n]).
+// block = (32, 8): x walks columns, y splits the partial rows; smem tree over y.
+// With out_f32 != nullptr the fp32 sums are written instead (multi-GPU: the
+// caller allreduces them, then runs this kernel again with nparts = 1).
+template <typename T>
+__global__ void __launch_bounds__(256) finalize_partials_kernel(const float* __restrict__ partials,
+                                                                int nparts, int K, int N,
+                                                                void* out_a, void* out_b,
+                                                                float* out_f32) {
+  __shared__ float sm[8][33];
+  const int col = blockIdx.x * 32 + threadIdx.x;
+  const int k = blockIdx.y;
+  float acc = 0.f;
+  if (col < N) {
+    for (int pidx = threadIdx.y; pidx < nparts; pidx += 8) {
+      acc += partials[((size_t)pidx * K + k) * N + col];
+    }
+  }
+  sm[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && col < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) t += sm[y][threadIdx.x];
+    if (out_f32 != nullptr) {
+      out_f32[(size_t)k * N + col] = t;
+    } else {
+      T* o = static_cast<T*>(k == 0 ? out_a : out_b);
+      if (o != nullptr) o[col] = IO<T>::from_f32(t);
+    }
+  }
+}
+
+}  // namespace b200norm

@@ -1,0 +1,223 @@
+/*
+ * b200norm.h — C ABI of the B200-native normalization / reduction kernel library.
+ *
+ * This is the drop-in boundary for the ONE hot path this repository implements:
+ * the LayerNorm / RMSNorm / softmax forward+backward segments that nvFuser's
+ * InnerPersistent / InnerOuterPersistent / Reduction schedulers would otherwise
+ * lower to NVRTC-generated code.
+ *
+ * Reference interfaces each entry point replaces (paths under the reference tree):
+ *   - ExecutorDispatch::{makeExecutor,compile,isCompiled,run}
+ *       csrc/runtime/executor_dispatch.cpp:18-156            (the executor seam)
+ *   - the dlopen'd "run_kernel"/"workspace_size" pair of CutlassCompiledKernel
+ *       csrc/runtime/cutlass_compiled_kernel.h:69-82, .cpp:346-362
+ *       (the in-tree precedent for an executor that bypasses lowering/codegen/NVRTC)
+ *   - KernelExecutor::run launch + workspace contract
+ *       csrc/runtime/executor.cpp:1013-1365 (outputs/workspaces are caller-allocated,
+ *       semaphores come from a zero-initialised pool :1160-1170)
+ *
+ * Contract (same as the precedent):
+ *   - plain C, no C++ types, no exceptions cross this boundary; integer status
+ *     codes, b200norm_last_error() for the message (thread-local).
+ *   - the caller owns every buffer; the library never allocates, frees or
+ *     synchronises; kernels are enqueued on the stream handed in.
+ *   - the workspace must be at least b200norm_workspace_bytes(desc) bytes,
+ *     256-byte aligned, and its first B200NORM_WS_HEADER_BYTES bytes must be
+ *     ZERO before the first launch that uses it. The library returns the header
+ *     to zero at the end of every launch, so one zero-fill at allocation time
+ *     is enough (this mirrors nvFuser's zeroed semaphore pool).
+ *   - there is NO CPU fallback: on a machine without an sm_100 device the
+ *     launch entry points fail with B200NORM_ERR_NO_DEVICE.
+ */
+#ifndef B200NORM_H_
+#define B200NORM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200NORM_ABI_VERSION 1
+#define B200NORM_WS_HEADER_BYTES 256
+#define B200NORM_MAX_DIMS 4
+
+/* Status codes. 0 = success; 1..99 library codes; >= 1000 = 1000 + cudaError_t. */
+enum {
+  B200NORM_OK = 0,
+  B200NORM_ERR_UNSUPPORTED = 1, /* segment not handled: caller falls through  */
+  B200NORM_ERR_BAD_ARG = 2,     /* malformed desc / tensor list               */
+  B200NORM_ERR_NO_DEVICE = 3,   /* no sm_100 device: there is no CPU fallback */
+  B200NORM_ERR_WORKSPACE = 4,   /* workspace missing / too small / misaligned */
+  B200NORM_ERR_CUDA = 1000      /* + cudaError_t                              */
+};
+
+/* Segment kinds (what SchedulerType + pattern the matched segment is).
+ * Math follows csrc/ops/normalization.cpp of the reference:
+ *   softmax :169-189, softmax_backward :191-210, layer_norm :304-342,
+ *   rms_norm :352-380, layer_norm_backward :382-436, rms_norm_backward :438-485,
+ *   thunder_rms_norm_backward :487-535, log_softmax :212-231,
+ *   log_softmax_backward :233-249; plain reductions scheduler/reduction.cpp. */
+typedef enum {
+  B200NORM_OP_LAYERNORM_FWD = 0,
+  B200NORM_OP_LAYERNORM_BWD = 1,
+  B200NORM_OP_RMSNORM_FWD = 2,
+  B200NORM_OP_RMSNORM_BWD = 3,
+  B200NORM_OP_SOFTMAX_FWD = 4,
+  B200NORM_OP_SOFTMAX_BWD = 5,
+  B200NORM_OP_LOGSOFTMAX_FWD = 6,
+  B200NORM_OP_LOGSOFTMAX_BWD = 7,
+  B200NORM_OP_REDUCE_INNER = 8, /* [M,N] -> [M]   sum / max / amax            */
+  B200NORM_OP_REDUCE_OUTER = 9, /* [M,N] -> [N]   sum (the dgamma/dbeta shape) */
+  B200NORM_OP_FINALIZE_PARTIALS = 10, /* fp32 [K,N] sums -> io dtype (after allreduce) */
+  B200NORM_OP_COUNT_
+} b200norm_op;
+
+typedef enum {
+  B200NORM_DT_F32 = 0,
+  B200NORM_DT_BF16 = 1,
+  B200NORM_DT_F16 = 2
+} b200norm_dtype;
+
+/* desc.flags */
+enum {
+  B200NORM_F_HAS_WEIGHT = 1u << 0,
+  B200NORM_F_HAS_BIAS = 1u << 1,
+  /* RMSNorm: the saved per-row statistic is rms = sqrt(mean(x^2)+eps) (the
+   * Thunder/Python spelling, benchmarks/python/test_rmsnorm_fwd.py:26-45)
+   * instead of invstd = rsqrt(mean(x^2)+eps) (C++ rms_norm, normalization.cpp:365-379). */
+  B200NORM_F_STAT_IS_RMS = 1u << 2,
+  /* RMSNorm backward keeps the "- sum(g)" centring term exactly as the C++
+   * rms_norm_backward builder does (normalization.cpp:461-476). Without the flag
+   * the textbook / thunder form is computed (:487-535). */
+  B200NORM_F_RMS_BWD_CENTERED = 1u << 3,
+  /* Backward: which gradients to produce (output_mask of the builders). */
+  B200NORM_F_OUT_DX = 1u << 4,
+  B200NORM_F_OUT_DW = 1u << 5,
+  B200NORM_F_OUT_DB = 1u << 6,
+  /* Backward, multi-GPU: write dgamma/dbeta as fp32 partial sums (no cast) so the
+   * caller can allreduce them and cast afterwards with OP_FINALIZE_PARTIALS. */
+  B200NORM_F_PARTIALS_F32 = 1u << 7,
+  /* softmax backward: round the per-row sum through the io dtype before use, as
+   * the Python benchmark definition does (benchmarks/python/test_softmax_bwd.py:49-60). */
+  B200NORM_F_ROUND_ROWSUM = 1u << 8,
+  /* reductions: 0 = sum, MAX = NaN-propagating amax, FMAX = NaN-ignoring
+   * (ir/internal_nodes.cpp:1746-1775). Also selects softmax's max flavour. */
+  B200NORM_F_REDUCE_MAX = 1u << 9,
+  B200NORM_F_REDUCE_FMAX = 1u << 10,
+  /* LayerNorm forward: mean / invstd outputs requested. */
+  B200NORM_F_OUT_MEAN = 1u << 11,
+  B200NORM_F_OUT_INVSTD = 1u << 12
+};
+
+/* desc.variant: 0 lets the library choose (the dispatch rule mirrors the accept
+ * rules of scheduler/normalization_inner*.cpp); the others force a kernel family
+ * and make b200norm_query fail if that family cannot run the shape. */
+typedef enum {
+  B200NORM_VARIANT_AUTO = 0,
+  B200NORM_VARIANT_GENERIC = 1, /* any shape/stride/alignment; multi-pass LDG     */
+  B200NORM_VARIANT_TMA = 2,     /* bulk-copy ring in smem, one CTA per row slice  */
+  B200NORM_VARIANT_CLUSTER = 3  /* TMA ring + DSMEM reduction across a cluster    */
+} b200norm_variant;
+
+typedef struct {
+  int32_t abi_version; /* B200NORM_ABI_VERSION */
+  int32_t op;          /* b200norm_op          */
+  int32_t io_dtype;    /* dtype of activations, gradients, weight, bias */
+  int32_t variant;     /* b200norm_variant     */
+  int64_t rows;        /* M: product of the outer (iteration) extents   */
+  int64_t cols;        /* N: product of the normalized / reduced extents */
+  double eps;          /* scalars are doubles in the fusion IR          */
+  uint32_t flags;
+  int32_t cluster_size; /* 0 = auto; else 1,2,4,8,16 */
+  int32_t reserved[4];
+} b200norm_desc;
+
+/* Tensor argument: same fields as CutlassCompiledKernel::TensorArg
+ * (cutlass_compiled_kernel.h:69-74) with the arrays held inline. Strides are in
+ * elements. The innermost stride must be 1 (or the extent 1). */
+typedef struct {
+  void* data;
+  int32_t dtype; /* b200norm_dtype */
+  int32_t ndim;
+  int64_t sizes[B200NORM_MAX_DIMS];
+  int64_t strides[B200NORM_MAX_DIMS];
+} b200norm_tensor;
+
+/* What the library decided for a desc on the current device: reported for
+ * NVFUSER_DUMP=launch_param-style logging and for tests that assert which
+ * kernel family ran (the reference tests assert the heuristic the same way,
+ * tests/cpp/test_cluster.cpp:181-188). */
+typedef struct {
+  int32_t variant;       /* b200norm_variant actually chosen                 */
+  int32_t cluster_size;  /* CTAs per row                                     */
+  int32_t grid_x;        /* CTAs launched                                    */
+  int32_t block_x;       /* threads per CTA                                  */
+  int32_t threads_per_row; /* consumer threads cooperating on one row slice  */
+  int32_t stages;        /* depth of the smem ring                           */
+  int32_t tile_rows;     /* rows per bulk copy                               */
+  int32_t smem_bytes;    /* dynamic shared memory per CTA                    */
+  int32_t n_launches;    /* kernels enqueued per b200norm_launch             */
+  int32_t reserved[3];
+  uint64_t workspace_bytes;
+  uint64_t algorithmic_bytes; /* the reference's *_iobytes for this desc      */
+} b200norm_plan;
+
+/*
+ * Tensor order per op (absent optional tensors are simply left out):
+ *   LAYERNORM_FWD  in : x[M,N], weight[N]?, bias[N]?        out: y[M,N], mean[M]?, invstd[M]?
+ *   LAYERNORM_BWD  in : dy[M,N], x[M,N], mean[M], invstd[M], weight[N]?
+ *                  out: dx[M,N]?, dweight[N]?, dbias[N]?
+ *   RMSNORM_FWD    in : x[M,N], weight[N]?                   out: y[M,N], stat[M]
+ *   RMSNORM_BWD    in : dy[M,N], x[M,N], stat[M], weight[N]? out: dx[M,N]?, dweight[N]?
+ *   SOFTMAX_FWD / LOGSOFTMAX_FWD   in : x[M,N]               out: y[M,N]
+ *   SOFTMAX_BWD / LOGSOFTMAX_BWD   in : dy[M,N], y[M,N]      out: dx[M,N]
+ *   REDUCE_INNER   in : x[M,N]                               out: r[M]   (io dtype)
+ *   REDUCE_OUTER   in : x[M,N]                               out: r[N]   (io dtype, or fp32 with PARTIALS_F32)
+ *   FINALIZE_PARTIALS in: p[K,N] fp32 (rows=K)               out: K tensors [N] io dtype
+ * Per-row statistics are always fp32; [M] and [M,1] are both accepted.
+ */
+
+/* ABI version of the loaded library. */
+int b200norm_abi_version(void);
+
+/* 0 if this desc can run on the current device; fills *plan when non-NULL.
+ * Pure host logic when no device is present (plans for a nominal B200: 148 SMs,
+ * 227 KB smem), so callers can test dispatch rules without a GPU.
+ * Replaces: SchedulerEntry::canSchedule / computeHeuristics for the matched
+ * segment (scheduler/registry.cpp:192-227, normalization_inner.cpp:73-231). */
+int b200norm_query(const b200norm_desc* desc, b200norm_plan* plan);
+
+/* Workspace size in bytes (0 on error). Replaces workspace_size()
+ * (cutlass_compiled_kernel.cpp:145-152). */
+size_t b200norm_workspace_bytes(const b200norm_desc* desc);
+
+/* Enqueue the segment. `stream` is a cudaStream_t passed as void*.
+ * Replaces run_kernel(args, workspace, stream) (cutlass_compiled_kernel.cpp:113-157)
+ * / KernelExecutor::run's cuLaunchKernelEx (executor.cpp:1270-1346). */
+int b200norm_launch(const b200norm_desc* desc,
+                    const b200norm_tensor* inputs, int n_inputs,
+                    const b200norm_tensor* outputs, int n_outputs,
+                    void* workspace, size_t workspace_bytes,
+                    void* stream);
+
+/* Number of kernels this library has enqueued so far in this process
+ * (monotonic; used by the bench's gpu_launches counter). */
+uint64_t b200norm_launch_count(void);
+
+/* Message for the last non-zero status on this thread ("" if none). */
+const char* b200norm_last_error(void);
+
+/* Name of the kernel family for a variant id ("generic", "tma", "cluster"). */
+const char* b200norm_variant_name(int variant);
+
+/* Device facts the planner uses; returns 0 and fills nominal B200 values with
+ * *has_device = 0 when no CUDA device is visible. */
+int b200norm_device_info(int* has_device, int* sm_count, int* smem_per_block_optin,
+                         int* cc_major, int* cc_minor);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200NORM_H_ */

@@ -1,0 +1,118 @@
+"""CPU tests of the C-ABI boundary: the library builds, loads, exports every symbol
+include/b200norm.h declares, plans the BASELINE.json configs sensibly, and refuses to
+compute without a device (there is no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from fuser_b200 import _lib as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "b200norm.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200norm_[a-z_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported(lib):
+    declared = _declared_symbols()
+    assert set(declared) == set(L.EXPORTED_SYMBOLS), declared
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.b200norm_abi_version() == L.ABI_VERSION
+
+
+def test_struct_layouts_match_header():
+    # sizes computed by hand from include/b200norm.h (LP64)
+    assert ctypes.sizeof(L.Desc) == 4 * 4 + 8 + 8 + 8 + 4 + 4 + 16
+    assert ctypes.sizeof(L.Tensor) == 8 + 4 + 4 + 8 * 4 + 8 * 4
+    assert ctypes.sizeof(L.Plan) == 4 * 12 + 8 + 8
+
+
+CONFIGS = [
+    # (name, op, dtype, rows, cols, flags)
+    ("C1 layernorm fwd fp32", L.OP_LAYERNORM_FWD, L.DT_F32, 2048, 4096, L.F_HAS_WEIGHT | L.F_HAS_BIAS | L.F_OUT_MEAN | L.F_OUT_INVSTD),
+    ("C2 rmsnorm fwd", L.OP_RMSNORM_FWD, L.DT_BF16, 16384, 4096, L.F_HAS_WEIGHT),
+    ("C2 rmsnorm bwd", L.OP_RMSNORM_BWD, L.DT_BF16, 16384, 4096, L.F_HAS_WEIGHT | L.F_OUT_DX | L.F_OUT_DW),
+    ("C3 softmax fwd", L.OP_SOFTMAX_FWD, L.DT_BF16, 65536, 8192, 0),
+    ("C3 softmax bwd", L.OP_SOFTMAX_BWD, L.DT_BF16, 65536, 8192, 0),
+    ("C4 layernorm bwd", L.OP_LAYERNORM_BWD, L.DT_BF16, 32768, 12288, L.F_HAS_WEIGHT | L.F_OUT_DX | L.F_OUT_DW | L.F_OUT_DB),
+    ("C5 rmsnorm fwd", L.OP_RMSNORM_FWD, L.DT_BF16, 4096, 65536, L.F_HAS_WEIGHT),
+    ("C5 rmsnorm bwd", L.OP_RMSNORM_BWD, L.DT_BF16, 4096, 65536, L.F_HAS_WEIGHT | L.F_OUT_DX | L.F_OUT_DW),
+]
+
+# the reference's own IO-byte accounting
+EXPECTED_BYTES = {
+    "C1 layernorm fwd fp32": 67_158_016,
+    "C2 rmsnorm fwd": 268_509_184,
+    "C2 rmsnorm bwd": 402_735_104,
+    "C3 softmax fwd": 2_147_483_648,
+    "C3 softmax bwd": 3_221_225_472,
+    "C4 layernorm bwd": 2_416_254_976,
+    "C5 rmsnorm fwd": 1_073_889_280,
+    "C5 rmsnorm bwd": 1_610_891_264,
+}
+
+
+@pytest.mark.parametrize("cfg", CONFIGS, ids=lambda c: c[0])
+def test_plans_for_baseline_configs(lib, cfg):
+    name, op, dt, m, n, flags = cfg
+    plan = L.query(L.make_desc(op, dt, m, n, 1e-5, flags)).as_dict()
+    assert plan["algorithmic_bytes"] == EXPECTED_BYTES[name]
+    assert plan["variant"] in ("tma", "cluster")
+    assert plan["smem_bytes"] <= 227 * 1024
+    assert plan["stages"] >= 2
+    assert plan["grid"] % plan["cluster_size"] == 0 and plan["grid"] <= 148
+    if name.startswith("C5"):
+        assert plan["variant"] == "cluster" and plan["cluster_size"] >= 2
+    else:
+        assert plan["cluster_size"] == 1
+    if op in (L.OP_RMSNORM_BWD, L.OP_LAYERNORM_BWD):
+        k = 2 if op == L.OP_LAYERNORM_BWD else 1
+        assert plan["workspace_bytes"] >= L.WS_HEADER_BYTES + plan["grid"] // plan["cluster_size"] * k * n * 4
+
+
+def test_unaligned_and_tiny_shapes_fall_to_generic(lib):
+    # N*2 bytes not a multiple of 16 -> no bulk-copy path (hidden sizes 3, 1987 of the reference's LN-bwd sweep)
+    for n in (3, 1987, 4098):
+        plan = L.query(L.make_desc(L.OP_LAYERNORM_BWD, L.DT_BF16, 216, n, 0.0, L.F_HAS_WEIGHT | L.F_OUT_DX | L.F_OUT_DW | L.F_OUT_DB))
+        assert L.variant_name(plan.variant) == "generic"
+    with pytest.raises(L.UnsupportedSegment):
+        L.query(L.make_desc(L.OP_RMSNORM_FWD, L.DT_BF16, 216, 1987, 1e-5, 0, variant=L.VARIANT_TMA))
+
+
+def test_bad_descriptors_are_rejected(lib):
+    d = L.make_desc(L.OP_RMSNORM_FWD, L.DT_BF16, 4, 64)
+    d.abi_version = 99
+    with pytest.raises(L.B200NormError) as e:
+        L.query(d)
+    assert e.value.code == L.ERR_BAD_ARG
+    with pytest.raises(L.UnsupportedSegment):
+        L.query(L.make_desc(77, L.DT_BF16, 4, 64))
+    with pytest.raises(L.B200NormError):
+        L.query(L.make_desc(L.OP_RMSNORM_BWD, L.DT_BF16, 4, 64, 0.0, L.F_OUT_DW))  # dweight without weight
+    with pytest.raises(L.B200NormError):
+        L.query(L.make_desc(L.OP_RMSNORM_FWD, L.DT_BF16, 4, 64, cluster_size=3))
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-device behaviour")
+def test_no_cpu_fallback(lib):
+    info = L.device_info()
+    assert info["has_device"] == 0 and info["sm_count"] == 148  # nominal B200 for planning only
+    x = torch.zeros(4, 64, dtype=torch.bfloat16)
+    y = torch.empty_like(x)
+    stat = torch.empty(4, dtype=torch.float32)
+    d = L.make_desc(L.OP_RMSNORM_FWD, L.DT_BF16, 4, 64, 1e-5, 0)
+    mk = lambda t, dt: L.make_tensor(t.data_ptr(), dt, list(t.shape), list(t.stride()))
+    with pytest.raises(L.B200NormError) as e:
+        L.launch(d, [mk(x, L.DT_BF16)], [mk(y, L.DT_BF16), mk(stat, L.DT_F32)], 0, 0, 0)
+    assert e.value.code == L.ERR_NO_DEVICE
+    from fuser_b200 import ops
+
+    with pytest.raises(L.B200NormError):
+        ops.rms_norm_fwd(x, None, 1e-5)
