@@ -13,6 +13,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -111,9 +112,11 @@ struct Plan {
   int tpr = 0;
   int groups = 0;
   int stages = 0;
+  int depth = 0;
   int tile_rows = 1;
   int contiguous = 0;
   int ch = 0;
+  bool cached = false;
   int nparts = 0;          // partial rows produced by the main kernel
   int rows_per_split = 0;  // generic colsum
   int n_launches = 1;
@@ -126,10 +129,19 @@ struct Plan {
 uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
 constexpr int kConsumerThreads = 512;
-constexpr int kBwdCH_RMS = 4;  // fp32 column accumulators per thread = CH * VEC (x2 for LayerNorm)
+constexpr int kFwdCH = 4;        // chunks per thread kept in registers by the forward kernels
+constexpr int kBwdCacheCH = 2;   // backward, g / xc cached in registers
+constexpr int kBwdCH_RMS = 4;    // backward re-read variant: column accumulators = CH * VEC (x2 for LayerNorm)
 constexpr int kBwdCH_LN = 3;
-constexpr int kSoftmaxCH = 4;
 constexpr int kMaxStages = 32;
+const int kTprMenu[] = {32, 64, 128, 256, 512};
+
+// Tuning overrides (like NVFUSER_ENABLE/DISABLE options): B200NORM_TPR, B200NORM_GROUPS,
+// B200NORM_DEPTH (stages per group), B200NORM_TILE_ROWS. Unset = planner's choice.
+int env_int(const char* name) {
+  const char* v = getenv(name);
+  return (v != nullptr && *v != 0) ? atoi(v) : 0;
+}
 
 int generic_nsplit(int64_t rows) {
   int64_t n = rows / 64;
@@ -150,35 +162,43 @@ bool try_ring_plan(const b200norm_desc& d, const DeviceInfo& dev, int C, bool ro
   const int nchunks = (int)(slice_cols / vec);
   const int ns = n_streams(d.op);
   const bool bwd = is_norm_bwd(d.op);
-  const bool softmax_fwd = d.op == B200NORM_OP_SOFTMAX_FWD || d.op == B200NORM_OP_LOGSOFTMAX_FWD;
+  const bool ln_bwd = d.op == B200NORM_OP_LAYERNORM_BWD;
 
-  // threads per row slice
-  int tpr;
-  const int bwd_ch = d.op == B200NORM_OP_LAYERNORM_BWD ? kBwdCH_LN : kBwdCH_RMS;
-  if (bwd) {
-    if (nchunks <= 32 * bwd_ch) tpr = 32;
-    else if (nchunks <= 128 * bwd_ch) tpr = 128;
-    else if (nchunks <= 256 * bwd_ch) tpr = 256;
-    else if (nchunks <= 512 * bwd_ch) tpr = 512;
-    else return false;
-  } else if (softmax_fwd) {
-    if (nchunks <= 32 * kSoftmaxCH) tpr = 32;
-    else if (nchunks <= 128 * kSoftmaxCH) tpr = 128;
-    else if (nchunks <= 256 * kSoftmaxCH) tpr = 256;
-    else tpr = 512;
-  } else {
-    if (nchunks <= 32 * 16) tpr = 32;
-    else if (nchunks <= 128 * 16) tpr = 128;
-    else if (nchunks <= 256 * 16) tpr = 256;
-    else tpr = 512;
+  // threads per row slice: the smallest group that keeps the slice in registers
+  // (forward: kFwdCH chunks per thread; backward: kBwdCacheCH with g/xc cached).
+  // Wider slices: 512 threads, re-reading the stage from shared memory.
+  Plan p;
+  int tpr = 0;
+  const int cache_ch = bwd ? kBwdCacheCH : kFwdCH;
+  for (int t : kTprMenu) {
+    if (nchunks <= t * cache_ch) {
+      tpr = t;
+      break;
+    }
+  }
+  p.cached = tpr != 0;
+  p.ch = cache_ch;
+  if (tpr == 0) {
+    tpr = 512;
+    if (bwd) {
+      p.ch = ln_bwd ? kBwdCH_LN : kBwdCH_RMS;
+      if (nchunks > tpr * p.ch) return false;  // column accumulators would not fit: split the row further
+    }
+  }
+  if (int t = env_int("B200NORM_TPR")) {
+    bool ok = false;
+    for (int m : kTprMenu) ok = ok || (m == t);
+    if (ok && t >= tpr && (p.cached || t == 512)) tpr = t;
   }
   int groups = kConsumerThreads / tpr;
+  if (groups > 8) groups = 8;  // named-barrier ids / diminishing returns for warp-sized groups
+  if (int gmax = env_int("B200NORM_GROUPS")) {
+    if (gmax >= 1 && gmax < groups) groups = gmax;
+  }
 
-  Plan p;
   p.variant = C > 1 ? B200NORM_VARIANT_CLUSTER : B200NORM_VARIANT_TMA;
   p.cluster = C;
   p.tpr = tpr;
-  p.ch = bwd ? bwd_ch : (softmax_fwd ? kSoftmaxCH : 0);
   p.slice_bytes = (uint32_t)(slice_cols * es);
 
   // rows per tile: aim for >= 8 KB bulk copies when rows are short and contiguous
@@ -187,8 +207,11 @@ bool try_ring_plan(const b200norm_desc& d, const DeviceInfo& dev, int C, bool ro
     tile_rows = (int)(8192 / p.slice_bytes);
     if (tile_rows > 32) tile_rows = 32;
     if (tile_rows < 1) tile_rows = 1;
-    // do not starve the grid: keep at least ~4 tiles per consumer group per SM
+    // do not starve the grid: keep at least a few tiles per consumer group per SM
     while (tile_rows > 1 && ceil_div64(d.rows, tile_rows) < (int64_t)dev.sm_count * groups * 2) tile_rows /= 2;
+  }
+  if (int tr = env_int("B200NORM_TILE_ROWS")) {
+    if (C == 1 && rows_contiguous && tr >= 1 && tr <= 64) tile_rows = tr;
   }
   p.tile_rows = tile_rows;
   p.contiguous = (C == 1 && rows_contiguous) ? 1 : 0;
@@ -197,9 +220,13 @@ bool try_ring_plan(const b200norm_desc& d, const DeviceInfo& dev, int C, bool ro
 
   const bool has_w = (d.flags & B200NORM_F_HAS_WEIGHT) != 0;
   const bool has_b = (d.flags & B200NORM_F_HAS_BIAS) != 0 && d.op == B200NORM_OP_LAYERNORM_FWD;
+  const uint32_t param_bytes = align_up((uint32_t)slice_cols * 4, 128);  // staged as fp32
 
+  // Ring depth. Stage s is always drained by group (s % groups): stages must be a
+  // multiple of groups, otherwise a group could wait on a stage whose outstanding
+  // phase belongs to another group's tile and alias the mbarrier parity.
   for (;;) {
-    uint32_t off = 8u * (2 * kMaxStages + groups);
+    uint32_t off = 8u * (kMaxStages + groups);
     off = align_up(off, 128);
     p.off_red = off;
     off += (uint32_t)groups * 2 * kMaxWarpsPerGroup * kRedNV * 4;
@@ -207,27 +234,29 @@ bool try_ring_plan(const b200norm_desc& d, const DeviceInfo& dev, int C, bool ro
     off += (uint32_t)groups * 2 * kMaxCluster * kRedNV * 4;
     off = align_up(off, 128);
     p.off_weight = off;
-    if (has_w) off += align_up(p.slice_bytes, 128);
+    if (has_w) off += param_bytes;
     p.off_bias = off;
-    if (has_b) off += align_up(p.slice_bytes, 128);
+    if (has_b) off += param_bytes;
     p.off_ring = off;
     const int64_t budget = (int64_t)dev.smem_optin - 1024 - off;
-    int stages = (int)(budget / p.stage_bytes);
-    if (stages > kMaxStages) stages = kMaxStages;
-    const int want = C > 1 ? 2 : 2;
-    if (stages < want) return false;
-    // every group needs its own stage in flight, plus prefetch depth
-    if (groups > 1 && stages < groups + 1) {
+    int max_stages = (int)(budget / p.stage_bytes);
+    if (max_stages > kMaxStages) max_stages = kMaxStages;
+    int depth = max_stages / groups;  // stages per group
+    if (depth < 2 && groups > 1) {
       groups = groups / 2;
-      if (groups < 1) groups = 1;
       continue;
     }
-    if (stages > 2 * groups + 8) stages = 2 * groups + 8;
-    p.stages = stages;
+    if (depth < 2) return false;
+    if (depth > 6) depth = 6;
+    if (int dd = env_int("B200NORM_DEPTH")) {
+      if (dd >= 1 && dd <= max_stages / groups) depth = dd;
+    }
+    p.stages = depth * groups;
+    p.depth = depth;
     break;
   }
   p.groups = groups;
-  p.block = groups * tpr + 32;
+  p.block = groups * tpr;
   const uint32_t ring_bytes = (uint32_t)p.stages * p.stage_bytes;
   if (bwd) {
     const uint32_t acc_bytes = (uint32_t)partial_k(d.op) * (uint32_t)slice_cols * 4;
@@ -265,7 +294,7 @@ int make_plan(const b200norm_desc& d, bool aligned, bool rows_contiguous, Plan* 
 
   bool ring_ok = false;
   if (is_row_op(d.op) && aligned && d.variant != B200NORM_VARIANT_GENERIC && d.rows > 0 && d.cols > 0) {
-    const int forced_c = d.cluster_size;
+    const int forced_c = d.cluster_size != 0 ? d.cluster_size : env_int("B200NORM_CLUSTER");
     static const int cs[] = {1, 2, 4, 8, 16};
     Plan best;
     for (int C : cs) {
@@ -278,13 +307,13 @@ int make_plan(const b200norm_desc& d, bool aligned, bool rows_contiguous, Plan* 
         best = cand;
         ring_ok = true;
       }
-      // prefer the smallest cluster that gives a reasonably deep ring
-      const int depth_goal = cand.groups + 2;
-      if (cand.stages >= depth_goal || forced_c > 0) {
+      // prefer the smallest cluster whose slice stays register-resident with >= 3 stages per group
+      const bool good = cand.cached && cand.stages >= 3 * cand.groups;
+      if (good || forced_c > 0) {
         best = cand;
         break;
       }
-      if (cand.stages > best.stages) best = cand;
+      if ((cand.cached && !best.cached) || (cand.cached == best.cached && cand.stages > best.stages)) best = cand;
     }
     if (ring_ok) p = best;
   }
@@ -362,44 +391,29 @@ void fill_public_plan(const b200norm_desc& d, const Plan& p, b200norm_plan* out)
 using RingKernel = void (*)(const RowParams);
 
 template <typename T>
-RingKernel ring_kernel_for(int op, int tpr) {
-#define B200_TPR_SWITCH(EXPR32, EXPR128, EXPR256, EXPR512) \
-  switch (tpr) {                                            \
-    case 32: return EXPR32;                                 \
-    case 128: return EXPR128;                               \
-    case 256: return EXPR256;                               \
-    case 512: return EXPR512;                               \
-    default: return nullptr;                                \
+RingKernel ring_kernel_for(int op, int tpr, bool cached) {
+#define B200_TPR_SWITCH(K, ...)                       \
+  switch (tpr) {                                      \
+    case 32: return K<T, 32, __VA_ARGS__>;            \
+    case 64: return K<T, 64, __VA_ARGS__>;            \
+    case 128: return K<T, 128, __VA_ARGS__>;          \
+    case 256: return K<T, 256, __VA_ARGS__>;          \
+    case 512: return K<T, 512, __VA_ARGS__>;          \
+    default: return nullptr;                          \
   }
   switch (op) {
-    case B200NORM_OP_RMSNORM_FWD:
-      B200_TPR_SWITCH((rmsnorm_fwd_tma_kernel<T, 32>), (rmsnorm_fwd_tma_kernel<T, 128>),
-                      (rmsnorm_fwd_tma_kernel<T, 256>), (rmsnorm_fwd_tma_kernel<T, 512>))
-    case B200NORM_OP_LAYERNORM_FWD:
-      B200_TPR_SWITCH((layernorm_fwd_tma_kernel<T, 32>), (layernorm_fwd_tma_kernel<T, 128>),
-                      (layernorm_fwd_tma_kernel<T, 256>), (layernorm_fwd_tma_kernel<T, 512>))
-    case B200NORM_OP_SOFTMAX_FWD:
-      B200_TPR_SWITCH((softmax_fwd_tma_kernel<T, 32, kSoftmaxCH, false>),
-                      (softmax_fwd_tma_kernel<T, 128, kSoftmaxCH, false>),
-                      (softmax_fwd_tma_kernel<T, 256, kSoftmaxCH, false>),
-                      (softmax_fwd_tma_kernel<T, 512, kSoftmaxCH, false>))
-    case B200NORM_OP_LOGSOFTMAX_FWD:
-      B200_TPR_SWITCH((softmax_fwd_tma_kernel<T, 32, kSoftmaxCH, true>),
-                      (softmax_fwd_tma_kernel<T, 128, kSoftmaxCH, true>),
-                      (softmax_fwd_tma_kernel<T, 256, kSoftmaxCH, true>),
-                      (softmax_fwd_tma_kernel<T, 512, kSoftmaxCH, true>))
-    case B200NORM_OP_SOFTMAX_BWD:
-      B200_TPR_SWITCH((softmax_bwd_tma_kernel<T, 32, false>), (softmax_bwd_tma_kernel<T, 128, false>),
-                      (softmax_bwd_tma_kernel<T, 256, false>), (softmax_bwd_tma_kernel<T, 512, false>))
-    case B200NORM_OP_LOGSOFTMAX_BWD:
-      B200_TPR_SWITCH((softmax_bwd_tma_kernel<T, 32, true>), (softmax_bwd_tma_kernel<T, 128, true>),
-                      (softmax_bwd_tma_kernel<T, 256, true>), (softmax_bwd_tma_kernel<T, 512, true>))
+    case B200NORM_OP_RMSNORM_FWD: B200_TPR_SWITCH(rmsnorm_fwd_tma_kernel, kFwdCH)
+    case B200NORM_OP_LAYERNORM_FWD: B200_TPR_SWITCH(layernorm_fwd_tma_kernel, kFwdCH)
+    case B200NORM_OP_SOFTMAX_FWD: B200_TPR_SWITCH(softmax_fwd_tma_kernel, kFwdCH, false)
+    case B200NORM_OP_LOGSOFTMAX_FWD: B200_TPR_SWITCH(softmax_fwd_tma_kernel, kFwdCH, true)
+    case B200NORM_OP_SOFTMAX_BWD: B200_TPR_SWITCH(softmax_bwd_tma_kernel, kFwdCH, false)
+    case B200NORM_OP_LOGSOFTMAX_BWD: B200_TPR_SWITCH(softmax_bwd_tma_kernel, kFwdCH, true)
     case B200NORM_OP_LAYERNORM_BWD:
-      B200_TPR_SWITCH((norm_bwd_tma_kernel<T, 32, kBwdCH_LN, true>), (norm_bwd_tma_kernel<T, 128, kBwdCH_LN, true>),
-                      (norm_bwd_tma_kernel<T, 256, kBwdCH_LN, true>), (norm_bwd_tma_kernel<T, 512, kBwdCH_LN, true>))
+      if (!cached) return tpr == 512 ? norm_bwd_tma_kernel<T, 512, kBwdCH_LN, true, false> : nullptr;
+      B200_TPR_SWITCH(norm_bwd_tma_kernel, kBwdCacheCH, true, true)
     case B200NORM_OP_RMSNORM_BWD:
-      B200_TPR_SWITCH((norm_bwd_tma_kernel<T, 32, kBwdCH_RMS, false>), (norm_bwd_tma_kernel<T, 128, kBwdCH_RMS, false>),
-                      (norm_bwd_tma_kernel<T, 256, kBwdCH_RMS, false>), (norm_bwd_tma_kernel<T, 512, kBwdCH_RMS, false>))
+      if (!cached) return tpr == 512 ? norm_bwd_tma_kernel<T, 512, kBwdCH_RMS, false, false> : nullptr;
+      B200_TPR_SWITCH(norm_bwd_tma_kernel, kBwdCacheCH, false, true)
     default:
       return nullptr;
   }
@@ -471,7 +485,7 @@ int launch_typed(const b200norm_desc& d, const Plan& plan, RowParams& rp, void* 
   }
 
   // ---- ring kernels ----
-  RingKernel k = ring_kernel_for<T>(d.op, plan.tpr);
+  RingKernel k = ring_kernel_for<T>(d.op, plan.tpr, plan.cached);
   if (k == nullptr) return fail(B200NORM_ERR_UNSUPPORTED, "no ring kernel for op %d tpr %d", d.op, plan.tpr);
   err = cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
   if (err != cudaSuccess) return fail(B200NORM_ERR_CUDA + (int)err, "smem attr: %s", cudaGetErrorString(err));
@@ -835,7 +849,7 @@ int b200norm_launch(const b200norm_desc* desc, const b200norm_tensor* inputs, in
   }
 
   rp.groups = plan.groups;
-  rp.stages = plan.stages;
+  rp.depth = plan.depth;
   rp.tile_rows = plan.tile_rows;
   rp.cols_cta = plan.cluster > 0 ? (int32_t)(d.cols / plan.cluster) : (int32_t)d.cols;
   rp.nstreams = n_streams(d.op);

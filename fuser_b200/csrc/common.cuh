@@ -187,6 +187,19 @@ __device__ __forceinline__ void sts_128(uint32_t addr, const uint4& v) {
 }
 
 // ----------------------------------------------------------------------------
+// packed fp32x2 math (sm_100: FFMA2 / FMUL2 / FADD2 — one issue slot, two lanes;
+// each lane is an IEEE round-to-nearest op, bit-identical to the scalar form)
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ float2 f2(float s) { return make_float2(s, s); }
+__device__ __forceinline__ float2 f2mul(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 f2add(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 f2fma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 f2sub(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.f, -1.f), a); }
+__device__ __forceinline__ float2 bf16x2_to_f2(uint32_t u) {
+  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
+
+// ----------------------------------------------------------------------------
 // dtype traits: a "chunk" is 16 bytes = VEC elements
 // bf16/fp16 -> fp32 is exact; fp32 -> bf16/fp16 is round-to-nearest-even, the
 // same rounding ATen's .to() and the reference's casts use (runtime/casts.cu:431-447).
@@ -207,6 +220,14 @@ struct IO<float> {
   __device__ __forceinline__ static uint4 pack(const float (&f)[4]) {
     return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]),
                       __float_as_uint(f[3]));
+  }
+  __device__ __forceinline__ static void unpack2(const uint4& v, float2 (&f)[2]) {
+    f[0] = make_float2(__uint_as_float(v.x), __uint_as_float(v.y));
+    f[1] = make_float2(__uint_as_float(v.z), __uint_as_float(v.w));
+  }
+  __device__ __forceinline__ static uint4 pack2(const float2 (&f)[2]) {
+    return make_uint4(__float_as_uint(f[0].x), __float_as_uint(f[0].y), __float_as_uint(f[1].x),
+                      __float_as_uint(f[1].y));
   }
   __device__ __forceinline__ static float to_f32(float v) { return v; }
   __device__ __forceinline__ static float from_f32(float v) { return v; }
@@ -234,6 +255,15 @@ struct IO<__nv_bfloat16> {
   }
   __device__ __forceinline__ static uint4 pack(const float (&f)[8]) {
     return make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
+  }
+  __device__ __forceinline__ static void unpack2(const uint4& v, float2 (&f)[4]) {
+    f[0] = bf16x2_to_f2(v.x);
+    f[1] = bf16x2_to_f2(v.y);
+    f[2] = bf16x2_to_f2(v.z);
+    f[3] = bf16x2_to_f2(v.w);
+  }
+  __device__ __forceinline__ static uint4 pack2(const float2 (&f)[4]) {
+    return make_uint4(pack2(f[0].x, f[0].y), pack2(f[1].x, f[1].y), pack2(f[2].x, f[2].y), pack2(f[3].x, f[3].y));
   }
   __device__ __forceinline__ static float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
   __device__ __forceinline__ static __nv_bfloat16 from_f32(float v) {
@@ -267,6 +297,15 @@ struct IO<__half> {
   }
   __device__ __forceinline__ static uint4 pack(const float (&f)[8]) {
     return make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
+  }
+  __device__ __forceinline__ static void unpack2(const uint4& v, float2 (&f)[4]) {
+    f[0] = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
+    f[1] = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+    f[2] = __half22float2(*reinterpret_cast<const __half2*>(&v.z));
+    f[3] = __half22float2(*reinterpret_cast<const __half2*>(&v.w));
+  }
+  __device__ __forceinline__ static uint4 pack2(const float2 (&f)[4]) {
+    return make_uint4(pack2(f[0].x, f[0].y), pack2(f[1].x, f[1].y), pack2(f[2].x, f[2].y), pack2(f[3].x, f[3].y));
   }
   __device__ __forceinline__ static float to_f32(__half v) { return __half2float(v); }
   __device__ __forceinline__ static __half from_f32(float v) { return __float2half_rn(v); }

@@ -68,9 +68,12 @@ def test_plans_for_baseline_configs(lib, cfg):
     assert plan["smem_bytes"] <= 227 * 1024
     assert plan["stages"] >= 2
     assert plan["grid"] % plan["cluster_size"] == 0 and plan["grid"] <= 148
+    assert plan["block"] <= 512 and plan["block"] % plan["threads_per_row"] == 0
+    groups = plan["block"] // plan["threads_per_row"]
+    assert plan["stages"] % groups == 0  # a stage always belongs to one consumer group
     if name.startswith("C5"):
         assert plan["variant"] == "cluster" and plan["cluster_size"] >= 2
-    else:
+    elif not name.startswith("C4"):
         assert plan["cluster_size"] == 1
     if op in (L.OP_RMSNORM_BWD, L.OP_LAYERNORM_BWD):
         k = 2 if op == L.OP_LAYERNORM_BWD else 1

@@ -119,7 +119,7 @@ def test_backward_ops(shape, dt, variant):
     lsm = AO.log_softmax_fwd(x)
     smd, lsmd = dev(sm, lsm)
     dx = ops.softmax_bwd(dyd, smd, variant=variant)
-    check(dx, AO.softmax_bwd(dy, sm), CO.softmax_bwd(dy, sm), n, "softmax dx", 1e-3)
+    check(dx, AO.softmax_bwd(dy, sm), CO.softmax_bwd(dy, sm), n, "softmax dx", 1e-3 if dt != torch.float32 else 1e-1)
     dx = ops.softmax_bwd(dyd, smd, round_rowsum=True, variant=variant)
     AO.assert_close(dx, AO.softmax_bwd_python(sm, dy), n, "softmax(py) dx")
     dx = ops.softmax_bwd(dyd, lsmd, log=True, variant=variant)
@@ -138,8 +138,14 @@ def test_cluster_dsmem_reduction(shape, dt, cluster):
     xd, dyd, wd, bd = dev(x, dy, w, b)
     kw = dict(variant=L.VARIANT_CLUSTER, cluster_size=cluster)
     fl = 1.0 if dt == torch.float32 else 1e-2
-    plan = ops.plan_for(L.OP_RMSNORM_FWD, dt, m, n, L.F_HAS_WEIGHT, eps, L.VARIANT_CLUSTER, cluster)
-    assert plan["variant"] == "cluster" and plan["cluster_size"] == cluster
+    try:
+        for op, fl_ in ((L.OP_RMSNORM_FWD, L.F_HAS_WEIGHT), (L.OP_SOFTMAX_BWD, 0),
+                        (L.OP_LAYERNORM_BWD, L.F_HAS_WEIGHT | L.F_OUT_DX | L.F_OUT_DW | L.F_OUT_DB),
+                        (L.OP_RMSNORM_BWD, L.F_HAS_WEIGHT | L.F_OUT_DX | L.F_OUT_DW)):
+            plan = ops.plan_for(op, dt, m, n, fl_, eps, L.VARIANT_CLUSTER, cluster)
+            assert plan["variant"] == "cluster" and plan["cluster_size"] == cluster
+    except L.UnsupportedSegment:
+        pytest.skip(f"a {n // cluster}-column slice does not fit one CTA's ring for every op")
     y, stat = ops.rms_norm_fwd(xd, wd, eps, **kw)
     ye, se = AO.rms_norm_fwd(x, w, eps)
     check(y, ye, CO.rms_norm_fwd(x, w, eps)[0], n, "rms y", fl)
