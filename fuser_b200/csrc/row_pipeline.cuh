@@ -273,10 +273,9 @@ struct Ring {
     const size_t col0_bytes = (size_t)g.crank * p.slice_bytes;
     const uint8_t* base0 = static_cast<const uint8_t*>(p.in0) + col0_bytes;
     const uint8_t* base1 = static_cast<const uint8_t*>(p.in1) + col0_bytes;
-    if (g.lane == 0) {
-      fence_proxy_async_smem();  // the group's generic-proxy reads of this stage precede the async write
-      mbar_arrive_expect_tx(fb, bytes * (uint32_t)p.nstreams);
-    }
+    // No proxy fence is needed for this write-after-read: every reader consumed its loads
+    // (the values fed the reduction) before the group barrier that precedes refill().
+    if (g.lane == 0) mbar_arrive_expect_tx(fb, bytes * (uint32_t)p.nstreams);
     __syncwarp();
     if (p.contiguous) {
       if (g.lane == 0) {

@@ -1,0 +1,572 @@
+"""Segment matcher: recognise LayerNorm / RMSNorm / softmax forward+backward fusions.
+
+In the reference, the segmenter hands every segment to a priority list of schedulers
+(csrc/scheduler/registry.cpp:192-227) and InnerPersistent / InnerOuterPersistent accept
+*any* fusion with the right reduction topology, then generate code for it. This library
+has a fixed set of hand-written kernels instead, so the question asked here is narrower:
+"is this fusion, as written, mathematically one of the normalization ops the kernels
+implement?" — and it must be answered for every spelling the frontends produce (the C++
+builders of csrc/ops/normalization.cpp, the Thunder traces in benchmarks/python/*.py with
+their 40-op backward, pow(x,2) vs mul(x,x), rsqrt vs 1/sqrt, reciprocal(size) vs div ...).
+
+The matcher therefore does not compare graph shapes. It canonicalises every fusion output
+to a polynomial normal form over atoms (inputs, reductions of monomials, max / exp / log of
+canonical sub-expressions, non-integer powers of multi-term expressions) and compares it
+with the normal form of candidate op definitions instantiated on the fusion's own inputs.
+Two spellings match iff their normal forms agree term by term. Casts are value-preserving
+in this algebra (they decide io dtypes, not the match); parity against the fusion as written
+is then what the validator tolerances check.
+"""
+from __future__ import annotations
+
+import itertools
+from dataclasses import dataclass, field
+from fractions import Fraction
+from typing import Optional
+
+from . import _lib as L
+from .ir import REDUCED, DataType, Scalar, Tensor, Val
+
+# ---------------------------------------------------------------------------
+# polynomial normal form
+# ---------------------------------------------------------------------------
+_COEF_DIGITS = 9
+
+
+def _round(c: float) -> float:
+    return float(f"{c:.{_COEF_DIGITS}e}")
+
+
+class Poly:
+    """sum_i coef_i * prod_j atom_ij ^ exp_ij   (exponents are Fractions)."""
+
+    __slots__ = ("terms",)
+
+    def __init__(self, terms: Optional[dict] = None):
+        self.terms: dict[tuple, float] = terms or {}
+
+    # -- constructors
+    @staticmethod
+    def const(c: float) -> "Poly":
+        return Poly({(): float(c)}) if c != 0 else Poly()
+
+    @staticmethod
+    def atom(a: tuple, e: Fraction = Fraction(1)) -> "Poly":
+        return Poly({((a, e),): 1.0})
+
+    # -- helpers
+    def clean(self) -> "Poly":
+        if not self.terms:
+            return self
+        mx = max(abs(c) for c in self.terms.values())
+        self.terms = {k: c for k, c in self.terms.items() if abs(c) > 1e-9 * max(mx, 1e-300) and c == c}
+        return self
+
+    def key(self) -> tuple:
+        return tuple(sorted((k, _round(c)) for k, c in self.terms.items()))
+
+    def is_monomial(self) -> bool:
+        return len(self.terms) == 1
+
+    # -- arithmetic
+    def __add__(self, o: "Poly") -> "Poly":
+        t = dict(self.terms)
+        for k, c in o.terms.items():
+            t[k] = t.get(k, 0.0) + c
+        return Poly(t).clean()
+
+    def scale(self, c: float) -> "Poly":
+        return Poly({k: v * c for k, v in self.terms.items()}).clean()
+
+    def __neg__(self) -> "Poly":
+        return self.scale(-1.0)
+
+    def __sub__(self, o: "Poly") -> "Poly":
+        return self + (-o)
+
+    @staticmethod
+    def _mul_keys(a: tuple, b: tuple) -> tuple:
+        d: dict = {}
+        for atom, e in itertools.chain(a, b):
+            d[atom] = d.get(atom, Fraction(0)) + e
+        return tuple(sorted(((atom, e) for atom, e in d.items() if e != 0), key=repr))
+
+    def __mul__(self, o: "Poly") -> "Poly":
+        t: dict = {}
+        for ka, ca in self.terms.items():
+            for kb, cb in o.terms.items():
+                k = Poly._mul_keys(ka, kb)
+                t[k] = t.get(k, 0.0) + ca * cb
+        return Poly(t).clean()
+
+    def pow(self, e: Fraction) -> "Poly":
+        if e == 1:
+            return self
+        if e == 0:
+            return Poly.const(1.0)
+        if not self.terms:
+            return Poly()
+        if self.is_monomial():
+            (k, c), = self.terms.items()
+            if c > 0 or e.denominator == 1:
+                nk = tuple(sorted(((a, x * e) for a, x in k if x * e != 0), key=repr))
+                return Poly({nk: float(c) ** float(e)})
+        if e.denominator == 1 and 0 < e <= 4:
+            r = self
+            for _ in range(int(e) - 1):
+                r = r * self
+            return r
+        # non-integer / negative power of a multi-term expression: opaque atom
+        return Poly.atom(("expr", self.key()), e)
+
+
+# ---------------------------------------------------------------------------
+# canonicaliser: DAG -> Poly (with axis bookkeeping)
+# ---------------------------------------------------------------------------
+class Unmatchable(Exception):
+    """The fusion uses an op or shape pattern outside the normalization hot path."""
+
+
+class Canon:
+    def __init__(self, fd):
+        self.fd = fd
+        self.uf = fd._uf
+        self.cache: dict[int, Poly] = {}
+        self.axes_of_key: dict[tuple, frozenset] = {}
+
+    def cls(self, dim):
+        return None if dim is None else self.uf.find(dim)
+
+    # axes an atom's value depends on
+    def atom_axes(self, atom: tuple) -> frozenset:
+        kind = atom[0]
+        if kind == "in":
+            t = self.fd._vals[atom[1]]
+            return frozenset(self.cls(d) for d in t.dims if d is not None)
+        if kind == "dim":
+            return frozenset()
+        if kind in ("sum", "max"):
+            return self.axes_of_key[atom[2]] - atom[1]
+        if kind in ("exp", "log", "expr"):
+            return self.axes_of_key[atom[1]]
+        raise KeyError(kind)
+
+    def poly_axes(self, p: Poly) -> frozenset:
+        ax: set = set()
+        for k in p.terms:
+            for atom, _ in k:
+                ax |= self.atom_axes(atom)
+        return frozenset(ax)
+
+    def register(self, p: Poly) -> tuple:
+        key = p.key()
+        self.axes_of_key[key] = self.poly_axes(p)
+        return key
+
+    def reduce_sum(self, p: Poly, tensor_dims: list, red_idx: list) -> Poly:
+        """sum over the logical axes red_idx of a tensor whose shape classes are tensor_dims."""
+        red_real = [self.cls(tensor_dims[i]) for i in red_idx if tensor_dims[i] is not None]
+        if not red_real:
+            return p  # reduction over broadcast (size-1) axes only: identity
+        red = frozenset(red_real)
+        out = Poly()
+        for k, c in p.terms.items():
+            dep, indep = [], []
+            for atom, e in k:
+                (dep if self.atom_axes(atom) & red else indep).append((atom, e))
+            dep_axes = frozenset().union(*[self.atom_axes(a) for a, _ in dep]) if dep else frozenset()
+            term = Poly({tuple(indep): c})
+            # axes being reduced that nothing in the term depends on contribute their extent
+            for ax in red - dep_axes:
+                term = term * Poly.atom(("dim", ax))
+            inner_red = red & dep_axes
+            if inner_red:
+                inner = Poly({tuple(sorted(dep, key=repr)): 1.0})
+                ik = self.register(inner)
+                term = term * Poly.atom(("sum", inner_red, ik))
+            out = out + term
+        return out
+
+    def scalar(self, s: Scalar) -> Poly:
+        if s.id in self.cache:
+            return self.cache[s.id]
+        if s.value is not None and s.dim is None:
+            r = Poly.const(float(s.value))
+        elif s.op == "size":
+            r = Poly.atom(("dim", self.cls(s.dim)))
+        elif s.op == "cast":
+            r = self.scalar(s.args[0])
+        elif s.op in ("neg", "reciprocal", "sqrt", "rsqrt"):
+            a = self.scalar(s.args[0])
+            r = {"neg": lambda: -a, "reciprocal": lambda: a.pow(Fraction(-1)),
+                 "sqrt": lambda: a.pow(Fraction(1, 2)), "rsqrt": lambda: a.pow(Fraction(-1, 2))}[s.op]()
+        elif s.op in ("add", "sub", "mul", "div", "pow"):
+            r = self.binary(s.op, self.scalar(s.args[0]), self.scalar(s.args[1]), s.args[1])
+        else:
+            raise Unmatchable(f"scalar op {s.op}")
+        self.cache[s.id] = r
+        return r
+
+    def binary(self, op: str, a: Poly, b: Poly, b_val: Val) -> Poly:
+        if op == "add":
+            return a + b
+        if op == "sub":
+            return a - b
+        if op == "mul":
+            return a * b
+        if op == "div":
+            return a * b.pow(Fraction(-1))
+        if op == "pow":
+            if isinstance(b_val, Scalar) and b_val.value is not None:
+                e = Fraction(float(b_val.value)).limit_denominator(64)
+                return a.pow(e)
+            raise Unmatchable("pow with a non-constant exponent")
+        raise Unmatchable(op)
+
+    def value(self, v: Val) -> Poly:
+        if isinstance(v, Scalar):
+            return self.scalar(v)
+        if v.id in self.cache:
+            return self.cache[v.id]
+        r = self._tensor(v)
+        self.cache[v.id] = r
+        return r
+
+    def _tensor(self, t: Tensor) -> Poly:
+        op = t.op
+        if op == "input":
+            return Poly.atom(("in", t.id))
+        if op in ("cast", "broadcast", "broadcast_in_dim"):
+            return self.value(t.args[0])
+        if op == "neg":
+            return -self.value(t.args[0])
+        if op == "reciprocal":
+            return self.value(t.args[0]).pow(Fraction(-1))
+        if op == "sqrt":
+            return self.value(t.args[0]).pow(Fraction(1, 2))
+        if op == "rsqrt":
+            return self.value(t.args[0]).pow(Fraction(-1, 2))
+        if op in ("exp", "log"):
+            inner = self.value(t.args[0])
+            return Poly.atom((op, self.register(inner)))
+        if op in ("add", "sub", "mul", "div", "pow"):
+            return self.binary(op, self.value(t.args[0]), self.value(t.args[1]), t.args[1])
+        if op in ("sum", "max", "mean", "var", "m2"):
+            src: Tensor = t.args[0]
+            x = self.value(src)
+            idx = t.attrs["dims"]
+            if op == "sum":
+                return self.reduce_sum(x, src.dims, idx)
+            red = frozenset(self.cls(src.dims[i]) for i in idx if src.dims[i] is not None)
+            if op == "max":
+                if not red:
+                    return x
+                return Poly.atom(("max", red, self.register(x)))
+            n = Poly.const(1.0)
+            for ax in red:
+                n = n * Poly.atom(("dim", ax))
+            mean = self.reduce_sum(x, src.dims, idx) * n.pow(Fraction(-1))
+            if op == "mean":
+                return mean
+            d = x - mean
+            m2 = self.reduce_sum(d * d, src.dims, idx)
+            if op == "m2":
+                return m2
+            corr = int(t.attrs.get("correction", 0))
+            denom = n - Poly.const(float(corr)) if corr else n
+            return m2 * denom.pow(Fraction(-1))
+        raise Unmatchable(f"op {op} is not on the normalization hot path")
+
+
+# ---------------------------------------------------------------------------
+# candidate op definitions, written against the recorder's own ops
+# (math of csrc/ops/normalization.cpp, cited per function)
+# ---------------------------------------------------------------------------
+def _bcast_last(ops, t: Tensor, like: Tensor) -> Tensor:
+    """[N] -> [.., N] aligned with the last axis of `like`."""
+    return ops.broadcast_in_dim(t, shape=like.shape(), broadcast_dims=[like.ndim - 1])
+
+
+def _bcast_rows(ops, t: Tensor, like: Tensor) -> Tensor:
+    """per-row statistic ([..] or [.., 1]) -> broadcastable against `like`."""
+    if t.ndim == like.ndim:
+        return t
+    return ops.broadcast_in_dim(t, shape=like.shape()[:-1] + [1], broadcast_dims=list(range(like.ndim - 1)))
+
+
+def def_layer_norm_fwd(ops, x, w, b, eps):
+    """normalization.cpp:304-342"""
+    last = [x.ndim - 1]
+    var, mean = ops.var_mean(x, dims=last, correction=0, keepdim=True)
+    invstd = ops.rsqrt(ops.add(var, eps))
+    y = ops.mul(ops.sub(x, mean), invstd)
+    if w is not None:
+        y = ops.mul(y, _bcast_last(ops, w, x))
+    if b is not None:
+        y = ops.add(y, _bcast_last(ops, b, x))
+    return {"y": y, "mean": mean, "invstd": invstd}
+
+
+def def_rms_norm_fwd(ops, x, w, eps):
+    """normalization.cpp:352-380 (+ the rms statistic of benchmarks/python/test_rmsnorm_fwd.py:26-45)"""
+    last = [x.ndim - 1]
+    ms = ops.mul(ops.sum(ops.mul(x, x), dims=last, keepdim=True), ops.reciprocal(x.size(-1)))
+    var_eps = ops.add(ms, eps)
+    invstd = ops.rsqrt(var_eps)
+    y = ops.mul(x, invstd)
+    if w is not None:
+        y = ops.mul(y, _bcast_last(ops, w, x))
+    return {"y": y, "invstd": invstd, "rms": ops.sqrt(var_eps)}
+
+
+def def_softmax_fwd(ops, x, log):
+    """normalization.cpp:169-189 / :212-231"""
+    last = [x.ndim - 1]
+    d = ops.sub(x, ops.max(x, dims=last, keepdim=True))
+    e = ops.exp(d)
+    s = ops.sum(e, dims=last, keepdim=True)
+    return {"y": ops.sub(d, ops.log(s)) if log else ops.mul(e, ops.reciprocal(s))}
+
+
+def def_softmax_bwd(ops, dy, y, log):
+    """normalization.cpp:191-210 / :233-249"""
+    last = [y.ndim - 1]
+    if log:
+        return {"dx": ops.sub(dy, ops.mul(ops.exp(y), ops.sum(dy, dims=last, keepdim=True)))}
+    g = ops.mul(dy, y)
+    return {"dx": ops.sub(g, ops.mul(y, ops.sum(g, dims=last, keepdim=True)))}
+
+
+def def_norm_bwd(ops, dy, x, mean, stat, w, stat_is_rms, centered):
+    """normalization.cpp:382-436 (LayerNorm), :438-485 (RMSNorm, centred), :487-535 / the Python
+    trace benchmarks/python/test_rmsnorm_bwd.py:20-76 (RMSNorm, textbook)."""
+    last = [x.ndim - 1]
+    outer = list(range(x.ndim - 1))
+    st = _bcast_rows(ops, stat, x)
+    invstd = ops.reciprocal(st) if stat_is_rms else st
+    xc = ops.sub(x, _bcast_rows(ops, mean, x)) if mean is not None else x
+    xh = ops.mul(xc, invstd)
+    g = ops.mul(dy, _bcast_last(ops, w, x)) if w is not None else dy
+    n = x.size(-1)
+    inner = ops.mul(n, g)
+    if centered:
+        inner = ops.sub(inner, ops.sum(g, dims=last, keepdim=True))
+    inner = ops.sub(inner, ops.mul(xh, ops.sum(ops.mul(g, xh), dims=last, keepdim=True)))
+    dx = ops.mul(ops.mul(ops.reciprocal(n), invstd), inner)
+    out = {"dx": dx, "db": ops.sum(dy, dims=outer)}
+    out["dw"] = ops.sum(ops.mul(dy, xh), dims=outer)
+    return out
+
+
+# ---------------------------------------------------------------------------
+# the match result
+# ---------------------------------------------------------------------------
+@dataclass
+class Match:
+    op: int                    # L.OP_*
+    flags: int                 # L.F_* (without output-selection bits for fwd stats)
+    eps: float
+    io_dtype: DataType
+    roles: dict                # role -> index into fusion inputs (x, dy, y, w, b, mean, stat)
+    outputs: list              # per fusion output: role name (y, mean, invstd, rms, dx, dw, db)
+    norm_ndim: int = 1
+    description: str = ""
+    notes: list = field(default_factory=list)
+
+
+def _tensor_inputs(fd):
+    return [(i, v) for i, v in enumerate(fd._inputs) if isinstance(v, Tensor)]
+
+
+def _eps_candidates(fd) -> list[float]:
+    """Scalar constants added to a tensor: the epsilon is one of them."""
+    out = []
+    for v in fd._vals:
+        if isinstance(v, Tensor) and v.op in ("add", "sub"):
+            for a in v.args:
+                if isinstance(a, Scalar) and a.value is not None and a.dim is None:
+                    val = float(a.value)
+                    if 0 < abs(val) < 1.0 and val not in out:
+                        out.append(val)
+    return out or [0.0]
+
+
+def _has_intermediate_round(fd) -> bool:
+    """A cast to a reduced-precision dtype whose result is consumed by more arithmetic
+    (the row-sum round trip of benchmarks/python/test_softmax_bwd.py:49-60)."""
+    outs = {v.id for v in fd._outputs}
+    consumed = set()
+    for v in fd._vals:
+        for a in v.args:
+            consumed.add(a.id)
+    for v in fd._vals:
+        if isinstance(v, Tensor) and v.op == "cast" and v.dtype in REDUCED and v.id in consumed and v.id not in outs:
+            src = v.args[0]
+            if isinstance(src, Tensor) and src.op != "input":
+                return True
+    return False
+
+
+def match_fusion(fd) -> Match:
+    """Classify the recorded fusion or raise Unmatchable."""
+    if not fd._outputs:
+        raise Unmatchable("fusion has no outputs")
+    tin = _tensor_inputs(fd)
+    if any(isinstance(v, Scalar) for v in fd._inputs):
+        raise Unmatchable("symbolic scalar inputs are not supported by the normalization kernels")
+
+    canon = Canon(fd)
+    try:
+        out_keys = [canon.value(o).key() for o in fd._outputs]
+    except Unmatchable:
+        raise
+
+    # classify inputs by signature once the extent classes are final
+    cls = canon.cls
+    mats = [(i, t) for i, t in tin if t.ndim >= 2 and all(d is not None for d in t.dims)]
+    if not mats:
+        raise Unmatchable("no [rows, cols] input")
+    x_like = mats[0][1]
+    nd = x_like.ndim
+    col_cls = cls(x_like.dims[-1])
+    row_cls = tuple(cls(d) for d in x_like.dims[:-1])
+    if col_cls in row_cls:
+        raise Unmatchable("square symbolic shapes: rows and cols were unified")
+    mats = [(i, t) for i, t in mats if t.ndim == nd and tuple(cls(d) for d in t.dims) == row_cls + (col_cls,)]
+    vecs = [(i, t) for i, t in tin if t.ndim == 1 and cls(t.dims[0]) == col_cls]
+    stats = [(i, t) for i, t in tin
+             if (t.ndim == nd - 1 and tuple(cls(d) for d in t.dims) == row_cls)
+             or (t.ndim == nd and t.dims[-1] is None and tuple(cls(d) for d in t.dims[:-1]) == row_cls)]
+    used = {i for i, _ in mats} | {i for i, _ in vecs} | {i for i, _ in stats}
+    if len(used) != len(tin):
+        raise Unmatchable("an input is neither [rows, cols], [cols] nor a per-row statistic")
+    io = mats[0][1].dtype
+    if io not in (DataType.Float, DataType.Half, DataType.BFloat16):
+        raise Unmatchable(f"io dtype {io.name}")
+    if any(t.dtype != io for _, t in mats + vecs):
+        raise Unmatchable("activations / weights of mixed dtypes")
+    if any(t.dtype != DataType.Float for _, t in stats):
+        raise Unmatchable("per-row statistics must be Float")
+
+    ops = fd.ops
+    eps_list = _eps_candidates(fd)
+
+    def try_candidate(build, roles_by_name: dict):
+        """Instantiate a candidate definition on the fusion's inputs; compare normal forms."""
+        snap = fd._uf.snapshot()
+        nvals = len(fd._vals)
+        try:
+            cand = build()
+            c2 = Canon(fd)
+            keys = {name: c2.value(t).key() for name, t in cand.items() if t is not None}
+            # extent classes must not have been merged by the candidate (wrong role guess)
+            if c2.cls(x_like.dims[-1]) in tuple(c2.cls(d) for d in x_like.dims[:-1]):
+                return None
+            c3 = Canon(fd)
+            mine = [c3.value(o).key() for o in fd._outputs]
+        except (Unmatchable, ValueError):
+            return None
+        finally:
+            del fd._vals[nvals:]
+            fd._uf.restore(snap)
+        names = []
+        for k in mine:
+            hit = [n for n, kk in keys.items() if kk == k]
+            if not hit:
+                return None
+            names.append(hit[0])
+        return names
+
+    n_m, n_v, n_s = len(mats), len(vecs), len(stats)
+
+    def T(pair):  # candidate definitions work on Float values, like every frontend spelling does
+        t = pair[1]
+        return ops.cast(t, DataType.Float) if t.dtype in REDUCED else t
+
+    I = lambda pair: pair[0]  # noqa: E731
+
+    # ---- forward ops: one matrix input ----
+    if n_m == 1 and n_s == 0:
+        x = mats[0]
+        if n_v == 0:
+            for log in (False, True):
+                names = try_candidate(lambda: def_softmax_fwd(ops, T(x), log), {})
+                if names:
+                    return Match(L.OP_LOGSOFTMAX_FWD if log else L.OP_SOFTMAX_FWD, 0, 0.0, io, {"x": I(x)}, names,
+                                 description="log_softmax" if log else "softmax")
+        for eps in eps_list:
+            e = ops._scalar(float(eps))
+            # RMSNorm: 0 or 1 vectors
+            if n_v <= 1:
+                w = vecs[0] if n_v == 1 else None
+                names = try_candidate(lambda: def_rms_norm_fwd(ops, T(x), T(w) if w else None, e), {})
+                if names:
+                    flags = (L.F_HAS_WEIGHT if w else 0) | (L.F_STAT_IS_RMS if "rms" in names else 0)
+                    if "rms" in names and "invstd" in names:
+                        raise Unmatchable("both rms and invstd requested")
+                    roles = {"x": I(x)}
+                    if w:
+                        roles["w"] = I(w)
+                    return Match(L.OP_RMSNORM_FWD, flags, eps, io, roles, names, description="rms_norm")
+            # LayerNorm: 0, 1 (weight only) or 2 vectors (weight, bias in either order)
+            combos = [(None, None)]
+            if n_v == 1:
+                combos = [(vecs[0], None)]
+            elif n_v == 2:
+                combos = [(vecs[0], vecs[1]), (vecs[1], vecs[0])]
+            for w, b in combos:
+                names = try_candidate(
+                    lambda: def_layer_norm_fwd(ops, T(x), T(w) if w else None, T(b) if b else None, e), {})
+                if names:
+                    flags = (L.F_HAS_WEIGHT if w else 0) | (L.F_HAS_BIAS if b else 0)
+                    roles = {"x": I(x)}
+                    if w:
+                        roles["w"] = I(w)
+                    if b:
+                        roles["b"] = I(b)
+                    return Match(L.OP_LAYERNORM_FWD, flags, eps, io, roles, names, description="layer_norm")
+        raise Unmatchable("single-input fusion is not rms_norm / layer_norm / softmax")
+
+    # ---- backward ops: two matrix inputs ----
+    if n_m == 2:
+        round_sum = _has_intermediate_round(fd)
+        for a, b_ in ((mats[0], mats[1]), (mats[1], mats[0])):
+            if n_s == 0 and n_v == 0:
+                for log in (False, True):
+                    names = try_candidate(lambda: def_softmax_bwd(ops, T(a), T(b_), log), {})
+                    if names:
+                        flags = L.F_ROUND_ROWSUM if (round_sum and not log) else 0
+                        return Match(L.OP_LOGSOFTMAX_BWD if log else L.OP_SOFTMAX_BWD, flags, 0.0, io,
+                                     {"dy": I(a), "y": I(b_)}, names,
+                                     description="log_softmax_backward" if log else "softmax_backward")
+            w = vecs[0] if n_v == 1 else None
+            if n_v > 1:
+                continue
+            if n_s == 1:  # RMSNorm backward
+                for stat_is_rms in (False, True):
+                    for centered in (False, True):
+                        names = try_candidate(
+                            lambda: def_norm_bwd(ops, T(a), T(b_), None, T(stats[0]), T(w) if w else None,
+                                                 stat_is_rms, centered), {})
+                        if names and "db" not in names:
+                            flags = (L.F_HAS_WEIGHT if w else 0) | (L.F_STAT_IS_RMS if stat_is_rms else 0)
+                            flags |= L.F_RMS_BWD_CENTERED if centered else 0
+                            roles = {"dy": I(a), "x": I(b_), "stat": I(stats[0])}
+                            if w:
+                                roles["w"] = I(w)
+                            return Match(L.OP_RMSNORM_BWD, flags, 0.0, io, roles, names,
+                                         description="rms_norm_backward")
+            if n_s == 2:  # LayerNorm backward
+                for mean, st in ((stats[0], stats[1]), (stats[1], stats[0])):
+                    names = try_candidate(
+                        lambda: def_norm_bwd(ops, T(a), T(b_), T(mean), T(st), T(w) if w else None, False, True), {})
+                    if names:
+                        flags = L.F_HAS_WEIGHT if w else 0
+                        roles = {"dy": I(a), "x": I(b_), "mean": I(mean), "stat": I(st)}
+                        if w:
+                            roles["w"] = I(w)
+                        return Match(L.OP_LAYERNORM_BWD, flags, 0.0, io, roles, names,
+                                     description="layer_norm_backward")
+        raise Unmatchable("two-input fusion is not a normalization / softmax backward")
+
+    raise Unmatchable(f"unsupported input signature: {n_m} matrices, {n_v} vectors, {n_s} row statistics")

@@ -1,0 +1,151 @@
+"""CPU tests of the frontend: the recorder keeps nvfuser_direct's call surface, and the matcher
+classifies every spelling of the hot path (Thunder traces and C++ builders) while rejecting
+fusions that are not normalization segments."""
+import pytest
+import torch
+
+from fuser_b200 import _lib as L
+from fuser_b200.frontend import DataType, FusionDefinition, UnsupportedSegment, get_tolerance
+from tests import fusions as F
+
+DTS = [DataType.Float, DataType.BFloat16, DataType.Half]
+
+
+def build(fn, *a, **k):
+    with FusionDefinition() as fd:
+        fn(fd, *a, **k)
+    return fd
+
+
+@pytest.mark.parametrize("dt", DTS, ids=lambda d: d.name)
+def test_python_benchmark_fusions_are_matched(dt):
+    m = build(F.layernorm_fwd_py, dt).segment()
+    assert (m.op, m.outputs, m.eps) == (L.OP_LAYERNORM_FWD, ["y", "mean", "invstd"], 1e-5)
+    assert m.flags & L.F_HAS_WEIGHT and m.flags & L.F_HAS_BIAS and m.roles == {"x": 0, "w": 1, "b": 2}
+    m = build(F.layernorm_bwd_py, dt).segment()
+    assert (m.op, m.outputs) == (L.OP_LAYERNORM_BWD, ["dx", "dw", "db"])
+    assert m.roles == {"dy": 1, "x": 0, "mean": 2, "stat": 3, "w": 4}
+    m = build(F.rmsnorm_fwd_py, dt).segment()
+    assert (m.op, m.outputs) == (L.OP_RMSNORM_FWD, ["y", "rms"]) and m.flags & L.F_STAT_IS_RMS
+    m = build(F.rmsnorm_bwd_py, dt).segment()
+    assert (m.op, m.outputs) == (L.OP_RMSNORM_BWD, ["dx", "dw"])
+    assert m.flags & L.F_STAT_IS_RMS and not (m.flags & L.F_RMS_BWD_CENTERED)
+    assert m.roles == {"dy": 2, "x": 0, "stat": 1, "w": 3}
+    m = build(F.softmax_fwd_py, dt).segment()
+    assert (m.op, m.outputs) == (L.OP_SOFTMAX_FWD, ["y"])
+    m = build(F.softmax_bwd_py, dt).segment()
+    assert (m.op, m.outputs, m.roles) == (L.OP_SOFTMAX_BWD, ["dx"], {"dy": 1, "y": 0})
+    assert bool(m.flags & L.F_ROUND_ROWSUM) == (dt is not DataType.Float)
+
+
+@pytest.mark.parametrize("dt", DTS, ids=lambda d: d.name)
+def test_cpp_builder_fusions_are_matched(dt):
+    m = build(F.layer_norm_cpp, dt, eps=1e-5).segment()
+    assert (m.op, m.outputs) == (L.OP_LAYERNORM_FWD, ["y", "mean", "invstd"])
+    m = build(F.layer_norm_cpp, dt, ndim=3, bias=False).segment()
+    assert m.op == L.OP_LAYERNORM_FWD and not (m.flags & L.F_HAS_BIAS)
+    m = build(F.layer_norm_cpp, dt, weight=False, bias=False).segment()
+    assert m.op == L.OP_LAYERNORM_FWD and not (m.flags & (L.F_HAS_BIAS | L.F_HAS_WEIGHT))
+    m = build(F.rms_norm_cpp, dt, eps=1e-6).segment()
+    assert (m.op, m.outputs, m.eps) == (L.OP_RMSNORM_FWD, ["y", "invstd"], 1e-6)
+    assert not (m.flags & L.F_STAT_IS_RMS)
+    m = build(F.norm_bwd_cpp, dt, layer_norm=True).segment()
+    assert (m.op, m.outputs) == (L.OP_LAYERNORM_BWD, ["dx", "dw", "db"])
+    assert m.roles == {"dy": 0, "x": 1, "mean": 2, "stat": 3, "w": 4}
+    m = build(F.norm_bwd_cpp, dt, layer_norm=True, mask=(True, False, False)).segment()
+    assert m.outputs == ["dx"]
+    # the C++ rms_norm_backward keeps the -sum(g) term: a different polynomial from the textbook form
+    m = build(F.norm_bwd_cpp, dt, layer_norm=False).segment()
+    assert (m.op, m.outputs) == (L.OP_RMSNORM_BWD, ["dx", "dw"])
+    assert m.flags & L.F_RMS_BWD_CENTERED and not (m.flags & L.F_STAT_IS_RMS)
+    for log in (False, True):
+        m = build(F.softmax_cpp, dt, log=log).segment()
+        assert m.op == (L.OP_LOGSOFTMAX_FWD if log else L.OP_SOFTMAX_FWD)
+        m = build(F.softmax_bwd_cpp, dt, log=log).segment()
+        assert m.op == (L.OP_LOGSOFTMAX_BWD if log else L.OP_SOFTMAX_BWD) and m.roles == {"dy": 0, "y": 1}
+
+
+def test_equivalent_respellings_match_and_near_misses_do_not():
+    # 1/sqrt instead of rsqrt, x*x*(1/N) as div, weight multiplied first
+    def respelled(fd):
+        x = fd.define_tensor(shape=[-1, -1], dtype=DataType.Float)
+        w = fd.define_tensor(shape=[-1], dtype=DataType.Float)
+        ms = fd.ops.div(fd.ops.sum(fd.ops.pow(x, 2.0), dims=[1], keepdim=True), x.size(1))
+        inv = fd.ops.reciprocal(fd.ops.sqrt(fd.ops.add(ms, 1e-6)))
+        wb = fd.ops.broadcast_in_dim(w, shape=x.shape(), broadcast_dims=[1])
+        fd.add_output(fd.ops.mul(fd.ops.mul(wb, x), inv))
+        fd.add_output(inv)
+    m = build(respelled).segment()
+    assert (m.op, m.outputs, m.eps) == (L.OP_RMSNORM_FWD, ["y", "invstd"], 1e-6)
+
+    # near miss 1: variance with Bessel's correction is not LayerNorm's statistic
+    def unbiased_ln(fd):
+        x = fd.define_tensor(shape=[-1, -1], dtype=DataType.Float)
+        var, mean = fd.ops.var_mean(x, dims=[1], correction=1, keepdim=True)
+        fd.add_output(fd.ops.mul(fd.ops.sub(x, mean), fd.ops.rsqrt(fd.ops.add(var, 1e-5))))
+    with pytest.raises(UnsupportedSegment):
+        build(unbiased_ln).segment()
+
+    # near miss 2: softmax without the max subtraction
+    def unsafe_softmax(fd):
+        x = fd.define_tensor(shape=[-1, -1], dtype=DataType.Float)
+        e = fd.ops.exp(x)
+        fd.add_output(fd.ops.mul(e, fd.ops.reciprocal(fd.ops.sum(e, dims=[1], keepdim=True))))
+    with pytest.raises(UnsupportedSegment):
+        build(unsafe_softmax).segment()
+
+    # near miss 3: reduction over the outer axis (an OuterPersistent segment)
+    with pytest.raises(UnsupportedSegment):
+        build(F.softmax_fwd_py, DataType.Float, reduction_axis=0).segment()
+
+    # near miss 4: a pointwise fusion is somebody else's segment
+    def pointwise(fd):
+        x = fd.define_tensor(shape=[-1, -1], dtype=DataType.Float)
+        fd.add_output(fd.ops.mul(x, x))
+    with pytest.raises(UnsupportedSegment):
+        build(pointwise).segment()
+
+    # near miss 5: the C++ thunder_rms_norm_backward text halves the projection term
+    # (csrc/ops/normalization.cpp:487-535); it is not the textbook backward and no kernel computes it
+    def thunder_cpp(fd):
+        dy = fd.define_tensor(shape=[-1, -1], dtype=DataType.Float)
+        x = fd.define_tensor(shape=[-1, -1], dtype=DataType.Float)
+        rms = fd.define_tensor(shape=[-1, 1], dtype=DataType.Float)
+        w = fd.define_tensor(shape=[-1], dtype=DataType.Float)
+        gw = fd.ops.mul(dy, fd.ops.broadcast(w, is_broadcast_dim=[True, False]))
+        t = fd.ops.mul(fd.ops.mul(fd.ops.neg(gw), x), fd.ops.reciprocal(fd.ops.mul(rms, rms)))
+        inner = fd.ops.broadcast(fd.ops.sum(t, dims=[1]), is_broadcast_dim=[False, True])
+        k = fd.ops.mul(fd.ops.reciprocal(fd.ops.mul(rms, 2.0)), fd.ops.reciprocal(x.size(1)))
+        fd.add_output(fd.ops.add(fd.ops.mul(inner, fd.ops.mul(x, k)), fd.ops.mul(gw, fd.ops.reciprocal(rms))))
+    with pytest.raises(UnsupportedSegment):
+        build(thunder_cpp).segment()
+
+
+def test_api_surface_and_errors():
+    with FusionDefinition() as fd:
+        x = fd.define_tensor(shape=[-1, -1], contiguity=[True, True], dtype=DataType.BFloat16, is_cpu=False)
+        assert x.ndim == 2 and len(x.shape()) == 2 and x.size(1).is_symbolic()
+        with pytest.raises(ValueError):  # same user error as csrc/ops/normalization.cpp:101-108
+            fd.ops.var_mean(x, dims=[1])
+        with pytest.raises(ValueError):  # ranks must match: broadcasts are explicit in nvFuser
+            fd.ops.add(x, fd.define_tensor(shape=[-1], dtype=DataType.BFloat16))
+    with pytest.raises(NotImplementedError):
+        FusionDefinition().execute([])
+    fd = build(F.rmsnorm_fwd_py, DataType.BFloat16)
+    with pytest.raises(ValueError):
+        fd.execute([torch.zeros(4, 8, dtype=torch.bfloat16)])  # wrong arity
+    if not torch.cuda.is_available():
+        with pytest.raises(L.B200NormError):  # CPU tensors: no fallback
+            fd.execute([torch.zeros(4, 8, dtype=torch.bfloat16), torch.zeros(8, dtype=torch.bfloat16)])
+
+
+def test_reduction_sizes_follow_the_validator():
+    # softmax output: the max-reduce feeds the sum-reduce -> N*N (csrc/validator_utils.cpp:233-254)
+    fd = build(F.softmax_fwd_py, DataType.BFloat16)
+    x = torch.zeros(16, 128, dtype=torch.bfloat16)
+    assert fd.reduction_sizes([x]) == [128 * 128]
+    fd = build(F.layernorm_bwd_py, DataType.Float)
+    ins = [torch.zeros(16, 128), torch.zeros(16, 128), torch.zeros(16), torch.zeros(16, 1), torch.zeros(128)]
+    rs = fd.reduction_sizes(ins)
+    assert rs[1] == 16 and rs[2] == 16 and rs[0] >= 128
+    assert get_tolerance(torch.float32, 4096) == pytest.approx((0.00012207, 0.00012207 * 0.01))

@@ -1,0 +1,79 @@
+"""GPU tests through the reference-facing API: FusionDefinition.execute / validate on every
+spelling of the hot path. The expectation is produced the way testValidate produces it
+(auto-inferred: the unscheduled fusion evaluated node by node with ATen — oracle.fusion_eval)
+and, like the reference's benchmark files, from explicit eager references."""
+import pytest
+import torch
+
+from fuser_b200 import _lib as L
+from fuser_b200.frontend import DataType, FusionDefinition
+from oracle import aten_oracle as AO
+from oracle import fusion_eval
+from tests import fusions as F
+
+pytestmark = pytest.mark.gpu
+
+DT = {DataType.Float: torch.float32, DataType.BFloat16: torch.bfloat16, DataType.Half: torch.float16}
+SHAPES = [(64, 768), (33, 4096), (7, 1987), (16, 12288)]
+
+
+def build(fn, *a, **k):
+    with FusionDefinition() as fd:
+        fn(fd, *a, **k)
+    return fd
+
+
+def auto_validate(fd, inputs):
+    """testValidate with auto-inferred outputs (csrc/validator_utils.cpp:364-368)."""
+    ref = fusion_eval.evaluate(fd, [t.cpu() for t in inputs])
+    before = L.launch_count()
+    outs = fd.validate(inputs, ref)
+    assert L.launch_count() > before, "no kernel of libb200norm.so was launched"
+    for o, r in zip(outs, ref):
+        assert o.is_cuda and o.dtype == r.dtype and o.shape == r.shape
+    return outs
+
+
+@pytest.mark.parametrize("dt", list(DT), ids=lambda d: d.name)
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: f"{s[0]}x{s[1]}")
+def test_benchmark_fusions_execute_and_validate(shape, dt):
+    m, n = shape
+    td = DT[dt]
+    g = torch.Generator().manual_seed(m + n)
+    x = torch.randn(m, n, generator=g).to(td).cuda()
+    dy = torch.randn(m, n, generator=g).to(td).cuda()
+    w = torch.randn(n, generator=g).to(td).cuda()
+    b = torch.randn(n, generator=g).to(td).cuda()
+    eps = 1e-5
+    # forward
+    y, mean, invstd = auto_validate(build(F.layernorm_fwd_py, dt), [x, w, b])
+    assert mean.shape == (m,) and invstd.shape == (m, 1)
+    y2, rms = auto_validate(build(F.rmsnorm_fwd_py, dt), [x, w])
+    sm, = auto_validate(build(F.softmax_fwd_py, dt), [x])
+    # explicit eager references, as the benchmark files validate (test_layernorm_fwd.py:84-95)
+    eager = torch.nn.functional.layer_norm(x.float(), (n,), w.float(), b.float(), eps).to(td)
+    AO.assert_close(y, eager.cpu(), n, "layer_norm vs eager")
+    AO.assert_close(sm, torch.softmax(x.float(), -1).to(td).cpu(), n * n, "softmax vs eager")
+    # backward
+    auto_validate(build(F.layernorm_bwd_py, dt), [x, dy, mean, invstd, w])
+    auto_validate(build(F.rmsnorm_bwd_py, dt), [x, rms, dy, w])
+    auto_validate(build(F.softmax_bwd_py, dt), [sm, dy])
+    # C++ builder spellings
+    auto_validate(build(F.layer_norm_cpp, dt), [x, w, b])
+    yc, istd = auto_validate(build(F.rms_norm_cpp, dt), [x, w])
+    auto_validate(build(F.norm_bwd_cpp, dt, layer_norm=True), [dy, x, mean.unsqueeze(1), invstd, w])
+    auto_validate(build(F.norm_bwd_cpp, dt, layer_norm=False), [dy, x, istd, w])
+    auto_validate(build(F.softmax_cpp, dt, log=True), [x])
+    auto_validate(build(F.softmax_bwd_cpp, dt), [dy, sm])
+
+
+def test_executor_cache_and_3d_inputs():
+    fd = build(F.layer_norm_cpp, DataType.BFloat16, ndim=3)
+    w = torch.randn(1024, device="cuda").bfloat16()
+    b = torch.randn(1024, device="cuda").bfloat16()
+    for shape in [(4, 9, 1024), (2, 33, 1024), (4, 9, 1024)]:  # new shapes reuse the same matched segment
+        x = torch.randn(*shape, device="cuda").bfloat16()
+        y, mean, invstd = auto_validate(fd, [x, w, b])
+        assert y.shape == x.shape and mean.shape == shape[:-1] + (1,)
+    with pytest.raises(ValueError):
+        fd.execute([x.float(), w, b])  # dtype differs from the definition

@@ -302,4 +302,5 @@ def test_full_size_properties():
     assert torch.allclose(sums2, 2 * sums1, rtol=1e-5, atol=1e-3)  # exact doubling in bf16 => linear
     assert torch.allclose(sums1[1], dy.float().sum(0), rtol=1e-4, atol=1e-2)
     # dx rows are orthogonal to 1 and to x_hat (projection property of LayerNorm backward)
-    assert dx.float().sum(-1).abs().max().item() < 0.5
+    # (bf16 rounding of 12288 outputs of magnitude ~1-4 leaves a residual of a few units)
+    assert dx.float().sum(-1).abs().max().item() < 4.0
