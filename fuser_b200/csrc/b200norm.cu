@@ -17,9 +17,10 @@
 #include <cstring>
 #include <mutex>
 
+#include <unordered_map>
+
 #include "kernels_generic.cuh"
-#include "kernels_tma_bwd.cuh"
-#include "kernels_tma_fwd.cuh"
+#include "ring_dispatch.cuh"
 
 using namespace b200norm;
 
@@ -116,28 +117,120 @@ struct Plan {
   int tile_rows = 1;
   int contiguous = 0;
   int ch = 0;
+  int nchunks = 0;
   bool cached = false;
   int nparts = 0;          // partial rows produced by the main kernel
   int rows_per_split = 0;  // generic colsum
   int n_launches = 1;
   uint32_t slice_bytes = 0, stream_bytes = 0, stage_bytes = 0;
-  uint32_t off_red = 0, off_cls = 0, off_weight = 0, off_bias = 0, off_ring = 0;
+  uint32_t off_red = 0, off_cls = 0, off_ring = 0;
   uint32_t smem = 0;
   uint64_t ws_bytes = 0;
 };
 
 uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
+// ---------------------------------------------------------------------------
+// kernel tables
+// ---------------------------------------------------------------------------
+template <typename T>
+RingKernel ring_kernel_for(int op, int tpr, int ch, bool cached);
+template <>
+RingKernel ring_kernel_for<float>(int op, int tpr, int ch, bool cached) {
+  return is_norm_bwd(op) ? ring_bwd_kernel_f32(op, tpr, ch, cached) : ring_fwd_kernel_f32(op, tpr, ch);
+}
+template <>
+RingKernel ring_kernel_for<__nv_bfloat16>(int op, int tpr, int ch, bool cached) {
+  return is_norm_bwd(op) ? ring_bwd_kernel_bf16(op, tpr, ch, cached) : ring_fwd_kernel_bf16(op, tpr, ch);
+}
+template <>
+RingKernel ring_kernel_for<__half>(int op, int tpr, int ch, bool cached) {
+  return is_norm_bwd(op) ? ring_bwd_kernel_f16(op, tpr, ch, cached) : ring_fwd_kernel_f16(op, tpr, ch);
+}
+
+// cudaFuncSetAttribute is paid once per (kernel, smem size, cluster class), not per launch.
+int prepare_ring_kernel(RingKernel k, int smem, int cluster) {
+  static std::mutex mu;
+  static std::unordered_map<const void*, std::pair<int, int>> done;  // kernel -> (max smem set, nonportable set)
+  std::lock_guard<std::mutex> lock(mu);
+  auto& st = done[(const void*)k];
+  if (smem > st.first) {
+    cudaError_t err = cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (err != cudaSuccess) return fail(B200NORM_ERR_CUDA + (int)err, "smem attr: %s", cudaGetErrorString(err));
+    st.first = smem;
+  }
+  if (cluster > 8 && !st.second) {
+    cudaError_t err = cudaFuncSetAttribute((const void*)k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (err != cudaSuccess) return fail(B200NORM_ERR_CUDA + (int)err, "cluster attr: %s", cudaGetErrorString(err));
+    st.second = 1;
+  }
+  return B200NORM_OK;
+}
+
+RingKernel ring_kernel_any(int dt, int op, int tpr, int ch, bool cached) {
+  switch (dt) {
+    case B200NORM_DT_F32: return ring_kernel_for<float>(op, tpr, ch, cached);
+    case B200NORM_DT_BF16: return ring_kernel_for<__nv_bfloat16>(op, tpr, ch, cached);
+    case B200NORM_DT_F16: return ring_kernel_for<__half>(op, tpr, ch, cached);
+    default: return nullptr;
+  }
+}
+
+// How many clusters of this shape can be resident at once. Clusters never span GPCs, so
+// the answer is NOT sm_count / C (on B200 a GPC holds 16-20 SMs: e.g. only 72 two-CTA
+// clusters fit 148 SMs). The ring kernels are persistent, so launching more clusters than
+// fit would serialise a second wave. The reference asks the same question before a
+// cluster launch (csrc/runtime/executor.cpp:1329-1340).
+int max_active_clusters(const DeviceInfo& dev, RingKernel k, int block, int smem, int C) {
+  if (C <= 1) return dev.sm_count;
+  if (!dev.has_device || k == nullptr) {
+    return 8 * (18 / C);  // nominal B200: 8 GPCs, >= 18 usable SMs each
+  }
+  static std::mutex mu;
+  static std::unordered_map<uint64_t, int> cache;
+  const uint64_t key = (reinterpret_cast<uint64_t>((const void*)k) << 8) ^ ((uint64_t)block << 40) ^
+                       ((uint64_t)smem << 4) ^ (uint64_t)C;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+  }
+  int n = 0;
+  if (prepare_ring_kernel(k, smem, C) == B200NORM_OK) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(dev.sm_count / C * C));
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = (unsigned)C;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    if (cudaOccupancyMaxActiveClusters(&n, (const void*)k, &cfg) != cudaSuccess) {
+      (void)cudaGetLastError();
+      n = 0;
+    }
+  }
+  if (n <= 0) n = 8 * (18 / C) > 0 ? 8 * (18 / C) : 1;
+  std::lock_guard<std::mutex> lock(mu);
+  cache[key] = n;
+  return n;
+}
+
 constexpr int kConsumerThreads = 512;
-constexpr int kFwdCH = 4;        // chunks per thread kept in registers by the forward kernels
-constexpr int kBwdCacheCH = 2;   // backward, g / xc cached in registers
-constexpr int kBwdCH_RMS = 4;    // backward re-read variant: column accumulators = CH * VEC (x2 for LayerNorm)
-constexpr int kBwdCH_LN = 3;
+constexpr int kFwdMaxCH = 4;       // chunks per thread kept in registers by the forward-type kernels
+constexpr int kBwdCacheCH = 2;     // backward, g / xc cached in registers
+constexpr int kBwdRereadCH_RMS = 4;  // backward re-read variant: column accumulators = CH * VEC (x2 for LayerNorm)
+constexpr int kBwdRereadCH_LN = 3;
 constexpr int kMaxStages = 32;
 const int kTprMenu[] = {32, 64, 128, 256, 512};
 
 // Tuning overrides (like NVFUSER_ENABLE/DISABLE options): B200NORM_TPR, B200NORM_GROUPS,
-// B200NORM_DEPTH (stages per group), B200NORM_TILE_ROWS. Unset = planner's choice.
+// B200NORM_DEPTH (stages per group), B200NORM_TILE_ROWS, B200NORM_CLUSTER, B200NORM_BWD_REREAD.
+// Unset = planner's choice.
 int env_int(const char* name) {
   const char* v = getenv(name);
   return (v != nullptr && *v != 0) ? atoi(v) : 0;
@@ -158,37 +251,45 @@ bool try_ring_plan(const b200norm_desc& d, const DeviceInfo& dev, int C, bool ro
   if (N % C != 0) return false;
   const int64_t slice_cols = N / C;
   if ((slice_cols * es) % 16 != 0) return false;
-  if (slice_cols * es > (int64_t)200 * 1024) return false;
+  if (slice_cols * es > (int64_t)100 * 1024) return false;
   const int nchunks = (int)(slice_cols / vec);
   const int ns = n_streams(d.op);
   const bool bwd = is_norm_bwd(d.op);
   const bool ln_bwd = d.op == B200NORM_OP_LAYERNORM_BWD;
 
-  // threads per row slice: the smallest group that keeps the slice in registers
-  // (forward: kFwdCH chunks per thread; backward: kBwdCacheCH with g/xc cached).
-  // Wider slices: 512 threads, re-reading the stage from shared memory.
+  // Threads per row slice and chunks per thread. Forward-type kernels: the smallest group
+  // that keeps the slice in registers at <= kFwdMaxCH chunks per thread (fewer, fatter
+  // threads = less reduction overhead and more groups per CTA). Backward: <= kBwdCacheCH
+  // with g / xc cached, else the re-read form with more accumulator columns per thread.
+  // Slices wider than 512*4 chunks use the looping form (forward-type only).
   Plan p;
-  int tpr = 0;
-  const int cache_ch = bwd ? kBwdCacheCH : kFwdCH;
-  for (int t : kTprMenu) {
-    if (nchunks <= t * cache_ch) {
-      tpr = t;
-      break;
+  int tpr = 0, ch = 0;
+  bool cached = true;
+  const int forced_tpr = env_int("B200NORM_TPR");
+  auto pick = [&](int max_ch) {
+    for (int t : kTprMenu) {
+      if (forced_tpr != 0 && t != forced_tpr) continue;
+      if (nchunks <= t * max_ch) {
+        tpr = t;
+        ch = (nchunks + t - 1) / t;
+        return true;
+      }
     }
-  }
-  p.cached = tpr != 0;
-  p.ch = cache_ch;
-  if (tpr == 0) {
+    return false;
+  };
+  if (bwd) {
+    const bool force_reread = env_int("B200NORM_BWD_REREAD") != 0;
+    if (force_reread || !pick(kBwdCacheCH)) {
+      cached = false;
+      if (!pick(ln_bwd ? kBwdRereadCH_LN : kBwdRereadCH_RMS)) return false;  // split the row further
+      if (ch < 3) ch = 3;  // only CH 3 / 4 are instantiated for the re-read form
+      if (ch == 4 && ln_bwd) return false;
+    }
+  } else if (!pick(kFwdMaxCH)) {
+    if (forced_tpr != 0 && forced_tpr != 512) return false;
     tpr = 512;
-    if (bwd) {
-      p.ch = ln_bwd ? kBwdCH_LN : kBwdCH_RMS;
-      if (nchunks > tpr * p.ch) return false;  // column accumulators would not fit: split the row further
-    }
-  }
-  if (int t = env_int("B200NORM_TPR")) {
-    bool ok = false;
-    for (int m : kTprMenu) ok = ok || (m == t);
-    if (ok && t >= tpr && (p.cached || t == 512)) tpr = t;
+    ch = 0;
+    cached = false;
   }
   int groups = kConsumerThreads / tpr;
   if (groups > 8) groups = 8;  // named-barrier ids / diminishing returns for warp-sized groups
@@ -199,6 +300,9 @@ bool try_ring_plan(const b200norm_desc& d, const DeviceInfo& dev, int C, bool ro
   p.variant = C > 1 ? B200NORM_VARIANT_CLUSTER : B200NORM_VARIANT_TMA;
   p.cluster = C;
   p.tpr = tpr;
+  p.ch = ch;
+  p.cached = cached;
+  p.nchunks = nchunks;
   p.slice_bytes = (uint32_t)(slice_cols * es);
 
   // rows per tile: aim for >= 8 KB bulk copies when rows are short and contiguous
@@ -215,28 +319,19 @@ bool try_ring_plan(const b200norm_desc& d, const DeviceInfo& dev, int C, bool ro
   }
   p.tile_rows = tile_rows;
   p.contiguous = (C == 1 && rows_contiguous) ? 1 : 0;
+  if (tile_rows == 1) p.contiguous = 1;  // a one-row tile is always one copy per stream
   p.stream_bytes = (uint32_t)tile_rows * p.slice_bytes;
   p.stage_bytes = align_up((uint32_t)ns * p.stream_bytes, 128);
 
-  const bool has_w = (d.flags & B200NORM_F_HAS_WEIGHT) != 0;
-  const bool has_b = (d.flags & B200NORM_F_HAS_BIAS) != 0 && d.op == B200NORM_OP_LAYERNORM_FWD;
-  const uint32_t param_bytes = align_up((uint32_t)slice_cols * 4, 128);  // staged as fp32
-
-  // Ring depth. Stage s is always drained by group (s % groups): stages must be a
-  // multiple of groups, otherwise a group could wait on a stage whose outstanding
-  // phase belongs to another group's tile and alias the mbarrier parity.
+  // Ring depth D (stages per group); the ring is group-major, stage (g*D + s).
   for (;;) {
     uint32_t off = 8u * (kMaxStages + groups);
-    off = align_up(off, 128);
+    off = align_up(off, 2 * kRedSetBytes);  // slot-set pairs are toggled with an XOR
     p.off_red = off;
-    off += (uint32_t)groups * 2 * kMaxWarpsPerGroup * kRedNV * 4;
+    off += (uint32_t)groups * 2 * kRedSetBytes;
     p.off_cls = off;
-    off += (uint32_t)groups * 2 * kMaxCluster * kRedNV * 4;
+    off += (uint32_t)groups * 2 * kClsSetBytes;
     off = align_up(off, 128);
-    p.off_weight = off;
-    if (has_w) off += param_bytes;
-    p.off_bias = off;
-    if (has_b) off += param_bytes;
     p.off_ring = off;
     const int64_t budget = (int64_t)dev.smem_optin - 1024 - off;
     int max_stages = (int)(budget / p.stage_bytes);
@@ -247,7 +342,7 @@ bool try_ring_plan(const b200norm_desc& d, const DeviceInfo& dev, int C, bool ro
       continue;
     }
     if (depth < 2) return false;
-    if (depth > 6) depth = 6;
+    if (depth > 4) depth = 4;  // deeper rings only scatter the DRAM streams (measured: C3 fwd 87% at 6, 93% at 3)
     if (int dd = env_int("B200NORM_DEPTH")) {
       if (dd >= 1 && dd <= max_stages / groups) depth = dd;
     }
@@ -265,7 +360,8 @@ bool try_ring_plan(const b200norm_desc& d, const DeviceInfo& dev, int C, bool ro
   p.smem = p.off_ring + ring_bytes;
 
   const int64_t ntiles = ceil_div64(d.rows, tile_rows);
-  int64_t nclusters = dev.sm_count / C;
+  int64_t nclusters = max_active_clusters(dev, ring_kernel_any(d.io_dtype, d.op, tpr, ch, cached), p.block,
+                                          (int)p.smem, C);
   if (nclusters > ntiles) nclusters = ntiles;
   if (nclusters < 1) nclusters = 1;
   p.grid = (int)(nclusters * C);
@@ -307,8 +403,10 @@ int make_plan(const b200norm_desc& d, bool aligned, bool rows_contiguous, Plan* 
         best = cand;
         ring_ok = true;
       }
-      // prefer the smallest cluster whose slice stays register-resident with >= 3 stages per group
-      const bool good = cand.cached && cand.stages >= 3 * cand.groups;
+      // prefer the smallest cluster that gives a register-resident slice (forward-type) or
+      // per-thread column accumulators (backward) with >= 3 stages per group: a cluster costs
+      // a DSMEM exchange per row and leaves SMs idle (clusters never span GPCs)
+      const bool good = (cand.cached || is_norm_bwd(d.op)) && cand.depth >= 3;
       if (good || forced_c > 0) {
         best = cand;
         break;
@@ -385,39 +483,17 @@ void fill_public_plan(const b200norm_desc& d, const Plan& p, b200norm_plan* out)
   out->algorithmic_bytes = algorithmic_bytes(d);
 }
 
-// ---------------------------------------------------------------------------
-// kernel tables
-// ---------------------------------------------------------------------------
-using RingKernel = void (*)(const RowParams);
-
 template <typename T>
-RingKernel ring_kernel_for(int op, int tpr, bool cached) {
-#define B200_TPR_SWITCH(K, ...)                       \
-  switch (tpr) {                                      \
-    case 32: return K<T, 32, __VA_ARGS__>;            \
-    case 64: return K<T, 64, __VA_ARGS__>;            \
-    case 128: return K<T, 128, __VA_ARGS__>;          \
-    case 256: return K<T, 256, __VA_ARGS__>;          \
-    case 512: return K<T, 512, __VA_ARGS__>;          \
-    default: return nullptr;                          \
+void launch_finalize(const float* partials, int nparts, int K, int N, void* out_a, void* out_b, float* out_f32,
+                     cudaStream_t stream) {
+  if (N % 4 == 0 && (reinterpret_cast<uintptr_t>(partials) & 15u) == 0) {
+    dim3 grid((unsigned)ceil_div64(N, 128), (unsigned)K);
+    finalize_partials_kernel<T, 4><<<grid, dim3(32, kFinY), 0, stream>>>(partials, nparts, K, N, out_a, out_b, out_f32);
+  } else {
+    dim3 grid((unsigned)ceil_div64(N, 32), (unsigned)K);
+    finalize_partials_kernel<T, 1><<<grid, dim3(32, kFinY), 0, stream>>>(partials, nparts, K, N, out_a, out_b, out_f32);
   }
-  switch (op) {
-    case B200NORM_OP_RMSNORM_FWD: B200_TPR_SWITCH(rmsnorm_fwd_tma_kernel, kFwdCH)
-    case B200NORM_OP_LAYERNORM_FWD: B200_TPR_SWITCH(layernorm_fwd_tma_kernel, kFwdCH)
-    case B200NORM_OP_SOFTMAX_FWD: B200_TPR_SWITCH(softmax_fwd_tma_kernel, kFwdCH, false)
-    case B200NORM_OP_LOGSOFTMAX_FWD: B200_TPR_SWITCH(softmax_fwd_tma_kernel, kFwdCH, true)
-    case B200NORM_OP_SOFTMAX_BWD: B200_TPR_SWITCH(softmax_bwd_tma_kernel, kFwdCH, false)
-    case B200NORM_OP_LOGSOFTMAX_BWD: B200_TPR_SWITCH(softmax_bwd_tma_kernel, kFwdCH, true)
-    case B200NORM_OP_LAYERNORM_BWD:
-      if (!cached) return tpr == 512 ? norm_bwd_tma_kernel<T, 512, kBwdCH_LN, true, false> : nullptr;
-      B200_TPR_SWITCH(norm_bwd_tma_kernel, kBwdCacheCH, true, true)
-    case B200NORM_OP_RMSNORM_BWD:
-      if (!cached) return tpr == 512 ? norm_bwd_tma_kernel<T, 512, kBwdCH_RMS, false, false> : nullptr;
-      B200_TPR_SWITCH(norm_bwd_tma_kernel, kBwdCacheCH, false, true)
-    default:
-      return nullptr;
-  }
-#undef B200_TPR_SWITCH
+  g_launches++;
 }
 
 template <typename T>
@@ -448,15 +524,9 @@ int launch_typed(const b200norm_desc& d, const Plan& plan, RowParams& rp, void* 
       dim3 grid((unsigned)ceil_div64(d.cols, 128), (unsigned)plan.nparts);
       generic_colsum_kernel<T, 0><<<grid, 128, 0, stream>>>(rp, plan.rows_per_split);
       g_launches++;
-      dim3 fgrid((unsigned)ceil_div64(d.cols, 32), 1);
-      finalize_partials_kernel<T><<<fgrid, dim3(32, 8), 0, stream>>>(rp.partials, plan.nparts, 1, (int)d.cols, dw,
-                                                                      nullptr, sums_f32);
-      g_launches++;
+      launch_finalize<T>(rp.partials, plan.nparts, 1, (int)d.cols, dw, nullptr, sums_f32, stream);
     } else if (d.op == B200NORM_OP_FINALIZE_PARTIALS) {
-      dim3 fgrid((unsigned)ceil_div64(d.cols, 32), (unsigned)d.rows);
-      finalize_partials_kernel<T><<<fgrid, dim3(32, 8), 0, stream>>>(static_cast<const float*>(rp.in0), 1,
-                                                                      (int)d.rows, (int)d.cols, dw, db, nullptr);
-      g_launches++;
+      launch_finalize<T>(static_cast<const float*>(rp.in0), 1, (int)d.rows, (int)d.cols, dw, db, nullptr, stream);
     } else {
       const bool need_rows = !is_norm_bwd(d.op) || (d.flags & B200NORM_F_OUT_DX);
       if (need_rows) {
@@ -473,10 +543,7 @@ int launch_typed(const b200norm_desc& d, const Plan& plan, RowParams& rp, void* 
           generic_colsum_kernel<T, 2><<<grid, 128, 0, stream>>>(rp, plan.rows_per_split);
         }
         g_launches++;
-        dim3 fgrid((unsigned)ceil_div64(d.cols, 32), (unsigned)K);
-        finalize_partials_kernel<T><<<fgrid, dim3(32, 8), 0, stream>>>(rp.partials, plan.nparts, K, (int)d.cols,
-                                                                        dw, db, sums_f32);
-        g_launches++;
+        launch_finalize<T>(rp.partials, plan.nparts, K, (int)d.cols, dw, db, sums_f32, stream);
       }
     }
     err = cudaGetLastError();
@@ -485,13 +552,12 @@ int launch_typed(const b200norm_desc& d, const Plan& plan, RowParams& rp, void* 
   }
 
   // ---- ring kernels ----
-  RingKernel k = ring_kernel_for<T>(d.op, plan.tpr, plan.cached);
-  if (k == nullptr) return fail(B200NORM_ERR_UNSUPPORTED, "no ring kernel for op %d tpr %d", d.op, plan.tpr);
-  err = cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem);
-  if (err != cudaSuccess) return fail(B200NORM_ERR_CUDA + (int)err, "smem attr: %s", cudaGetErrorString(err));
-  if (plan.cluster > 8) {
-    err = cudaFuncSetAttribute((const void*)k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-    if (err != cudaSuccess) return fail(B200NORM_ERR_CUDA + (int)err, "cluster attr: %s", cudaGetErrorString(err));
+  RingKernel k = ring_kernel_for<T>(d.op, plan.tpr, plan.ch, plan.cached);
+  if (k == nullptr)
+    return fail(B200NORM_ERR_UNSUPPORTED, "no ring kernel for op %d tpr %d ch %d", d.op, plan.tpr, plan.ch);
+  {
+    int rc = prepare_ring_kernel(k, (int)plan.smem, plan.cluster);
+    if (rc != B200NORM_OK) return rc;
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -510,10 +576,7 @@ int launch_typed(const b200norm_desc& d, const Plan& plan, RowParams& rp, void* 
   if (err != cudaSuccess) return fail(B200NORM_ERR_CUDA + (int)err, "ring launch failed: %s", cudaGetErrorString(err));
   g_launches++;
   if (want_cols) {
-    dim3 fgrid((unsigned)ceil_div64(d.cols, 32), (unsigned)K);
-    finalize_partials_kernel<T><<<fgrid, dim3(32, 8), 0, stream>>>(rp.partials, plan.nparts, K, (int)d.cols, dw, db,
-                                                                    sums_f32);
-    g_launches++;
+    launch_finalize<T>(rp.partials, plan.nparts, K, (int)d.cols, dw, db, sums_f32, stream);
     err = cudaGetLastError();
     if (err != cudaSuccess) return fail(B200NORM_ERR_CUDA + (int)err, "finalize launch failed: %s", cudaGetErrorString(err));
   }
@@ -857,10 +920,9 @@ int b200norm_launch(const b200norm_desc* desc, const b200norm_tensor* inputs, in
   rp.slice_bytes = plan.slice_bytes;
   rp.stream_bytes = plan.stream_bytes;
   rp.stage_bytes = plan.stage_bytes;
+  rp.nchunks = plan.nchunks;
   rp.off_red = plan.off_red;
   rp.off_cls = plan.off_cls;
-  rp.off_weight = plan.off_weight;
-  rp.off_bias = plan.off_bias;
   rp.off_ring = plan.off_ring;
   rp.off_acc = plan.off_ring;
 

@@ -348,6 +348,26 @@ __device__ __forceinline__ void warp_allreduce(float (&v)[NV]) {
   }
 }
 
+// Single-MUFU reciprocal / square roots (max relative error ~1 ulp of fp32; subnormal
+// inputs handled). The IEEE-rounded forms cost ~20 instructions each on the per-row
+// critical path; the results here feed values that are rounded to the io dtype or
+// compared under the validator's tolerances (>= 1e-6 relative).
+__device__ __forceinline__ float rsqrt_fast(float x) {
+  float y;
+  asm("rsqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sqrt_fast(float x) {
+  float y;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_fast(float x) {
+  float y;
+  asm("rcp.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // Fast exp for 16-bit outputs (one MUFU.EX2 per element); accurate expf for fp32.
 template <typename T>
 __device__ __forceinline__ float exp_for(float x) {

@@ -1,0 +1,248 @@
+// norm_executor.cpp — see norm_executor.h.
+#include "norm_executor.h"
+
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+
+#include <map>
+#include <mutex>
+#include <sstream>
+
+namespace b200norm {
+
+namespace {
+
+int dtype_id(at::ScalarType t) {
+  switch (t) {
+    case at::kFloat: return B200NORM_DT_F32;
+    case at::kBFloat16: return B200NORM_DT_BF16;
+    case at::kHalf: return B200NORM_DT_F16;
+    default: return -1;
+  }
+}
+
+[[noreturn]] void raise(int code) {
+  std::ostringstream os;
+  os << "b200norm status " << code << ": " << b200norm_last_error();
+  throw NormError(code, os.str());
+}
+[[noreturn]] void raise_msg(int code, const std::string& msg) {
+  std::ostringstream os;
+  os << "b200norm status " << code << ": " << msg;
+  throw NormError(code, os.str());
+}
+
+b200norm_desc make_desc(const SegmentSpec& s, int dt, int64_t rows, int64_t cols) {
+  b200norm_desc d{};
+  d.abi_version = B200NORM_ABI_VERSION;
+  d.op = s.op;
+  d.io_dtype = dt;
+  d.variant = s.variant;
+  d.rows = rows;
+  d.cols = cols;
+  d.eps = s.eps;
+  d.flags = s.flags;
+  d.cluster_size = s.cluster_size;
+  return d;
+}
+
+b200norm_tensor as_arg(const at::Tensor& t) {
+  b200norm_tensor a{};
+  a.data = t.data_ptr();
+  a.dtype = dtype_id(t.scalar_type());
+  a.ndim = (int32_t)t.dim();
+  if (a.ndim > B200NORM_MAX_DIMS) raise_msg(B200NORM_ERR_UNSUPPORTED, "tensor rank > 4 at the kernel boundary");
+  for (int i = 0; i < a.ndim; ++i) {
+    a.sizes[i] = t.size(i);
+    a.strides[i] = t.stride(i);
+  }
+  return a;
+}
+
+// [.., N] -> [M, N] view without a copy (the kernels take any row stride).
+at::Tensor as_rows(const at::Tensor& t, int64_t n) {
+  if (t.dim() == 2 && t.size(1) == n) return t;
+  if (t.numel() == 0) return t.reshape({-1, n});
+  if (!t.is_contiguous())
+    raise_msg(B200NORM_ERR_UNSUPPORTED, "a non-contiguous tensor of rank != 2 is not viewable as [rows, cols]");
+  return t.view({-1, n});
+}
+
+// zero-initialised workspace per (device, stream); the library keeps the header zero
+at::Tensor workspace(size_t nbytes, const at::Device& dev, cudaStream_t stream) {
+  static std::mutex mu;
+  static std::map<std::pair<int, cudaStream_t>, at::Tensor> cache;
+  std::lock_guard<std::mutex> lock(mu);
+  auto key = std::make_pair((int)dev.index(), stream);
+  auto it = cache.find(key);
+  if (it == cache.end() || (size_t)it->second.numel() < nbytes) {
+    size_t n = nbytes < (1u << 20) ? (1u << 20) : nbytes;
+    at::Tensor ws = at::zeros({(int64_t)n}, at::TensorOptions().dtype(at::kByte).device(dev));
+    cache[key] = ws;
+    return ws;
+  }
+  return it->second;
+}
+
+bool is_norm_bwd(int op) { return op == B200NORM_OP_LAYERNORM_BWD || op == B200NORM_OP_RMSNORM_BWD; }
+
+}  // namespace
+
+bool NormExecutor::supported(const SegmentSpec& spec, at::ScalarType io_dtype, int64_t rows, int64_t cols) {
+  const int dt = dtype_id(io_dtype);
+  if (dt < 0) return false;
+  b200norm_desc d = make_desc(spec, dt, rows, cols);
+  return b200norm_query(&d, nullptr) == B200NORM_OK;
+}
+
+void NormExecutor::compile(const SegmentSpec& spec) {
+  if (spec.op < 0 || spec.op >= B200NORM_OP_COUNT_) raise_msg(B200NORM_ERR_UNSUPPORTED, "unknown segment kind");
+  spec_ = spec;
+  compiled_ = true;
+}
+
+std::vector<at::Tensor> NormExecutor::allocateOutputs(const std::vector<at::Tensor>& in, int64_t rows,
+                                                     int64_t cols) const {
+  std::vector<at::Tensor> out;
+  const uint32_t f = spec_.flags;
+  const at::Tensor& first = in.at(0);
+  const auto opts = first.options();
+  const auto f32 = opts.dtype(at::kFloat);
+  auto stat_shape = [&](const at::Tensor& x) {
+    std::vector<int64_t> s(x.sizes().begin(), x.sizes().end());
+    s.back() = 1;
+    return s;
+  };
+  switch (spec_.op) {
+    case B200NORM_OP_LAYERNORM_FWD:
+      out.push_back(at::empty(first.sizes(), opts));
+      if (f & B200NORM_F_OUT_MEAN) out.push_back(at::empty(stat_shape(first), f32));
+      if (f & B200NORM_F_OUT_INVSTD) out.push_back(at::empty(stat_shape(first), f32));
+      break;
+    case B200NORM_OP_RMSNORM_FWD:
+      out.push_back(at::empty(first.sizes(), opts));
+      out.push_back(at::empty(stat_shape(first), f32));
+      break;
+    case B200NORM_OP_SOFTMAX_FWD:
+    case B200NORM_OP_LOGSOFTMAX_FWD:
+      out.push_back(at::empty(first.sizes(), opts));
+      break;
+    case B200NORM_OP_SOFTMAX_BWD:
+    case B200NORM_OP_LOGSOFTMAX_BWD:
+      out.push_back(at::empty(in.at(1).sizes(), opts));
+      break;
+    case B200NORM_OP_LAYERNORM_BWD:
+    case B200NORM_OP_RMSNORM_BWD: {
+      const bool ln = spec_.op == B200NORM_OP_LAYERNORM_BWD;
+      if (f & B200NORM_F_OUT_DX) out.push_back(at::empty(in.at(1).sizes(), opts));
+      const bool want_dw = (f & B200NORM_F_OUT_DW) != 0;
+      const bool want_db = ln && (f & B200NORM_F_OUT_DB) != 0;
+      if (want_dw || want_db) {
+        if (f & B200NORM_F_PARTIALS_F32) {
+          out.push_back(at::empty({ln ? 2 : 1, cols}, f32));
+        } else {
+          if (want_dw) out.push_back(at::empty({cols}, opts));
+          if (want_db) out.push_back(at::empty({cols}, opts));
+        }
+      }
+      break;
+    }
+    case B200NORM_OP_REDUCE_INNER: {
+      std::vector<int64_t> s(first.sizes().begin(), first.sizes().end() - 1);
+      out.push_back(at::empty(s, opts));
+      break;
+    }
+    case B200NORM_OP_REDUCE_OUTER:
+      out.push_back(at::empty({cols}, (f & B200NORM_F_PARTIALS_F32) ? f32 : opts));
+      break;
+    default:
+      raise_msg(B200NORM_ERR_UNSUPPORTED, "allocateOutputs: segment kind not handled");
+  }
+  (void)rows;
+  return out;
+}
+
+std::vector<at::Tensor> NormExecutor::run(const std::vector<at::Tensor>& inputs, std::vector<at::Tensor> outputs) {
+  if (!compiled_) raise_msg(B200NORM_ERR_BAD_ARG, "NormExecutor must be compiled before running");
+  if (inputs.empty()) raise_msg(B200NORM_ERR_BAD_ARG, "no inputs");
+  for (const auto& t : inputs) {
+    if (!t.is_cuda())
+      raise_msg(B200NORM_ERR_NO_DEVICE, "b200norm kernels run on CUDA tensors only (there is no CPU fallback)");
+  }
+  const at::Tensor& lead = inputs[0];
+  const c10::cuda::CUDAGuard guard(lead.device());
+  cudaStream_t stream = at::cuda::getCurrentCUDAStream(lead.device().index()).stream();
+
+  // rows / cols of the segment
+  int64_t cols = 0, rows = 0;
+  int dt = -1;
+  if (spec_.op == B200NORM_OP_FINALIZE_PARTIALS) {
+    // inputs: sums [K, N] fp32; output dtype travels in the first preallocated output
+    if (outputs.empty()) raise_msg(B200NORM_ERR_BAD_ARG, "finalize_partials needs preallocated outputs");
+    rows = lead.size(0);
+    cols = lead.size(1);
+    dt = dtype_id(outputs[0].scalar_type());
+  } else {
+    cols = lead.dim() > 0 ? lead.size(-1) : 1;
+    rows = cols > 0 ? lead.numel() / cols : 0;
+    dt = dtype_id(lead.scalar_type());
+  }
+  if (dt < 0) raise_msg(B200NORM_ERR_UNSUPPORTED, "dtype is not handled by b200norm");
+  b200norm_desc d = make_desc(spec_, dt, rows, cols);
+
+  if (outputs.empty()) outputs = allocateOutputs(inputs, rows, cols);
+
+  // marshal: matrices as [rows, cols] views, vectors flattened
+  const int n_mat_in = (spec_.op == B200NORM_OP_FINALIZE_PARTIALS) ? 0
+                       : (spec_.op == B200NORM_OP_LAYERNORM_BWD || spec_.op == B200NORM_OP_RMSNORM_BWD ||
+                          spec_.op == B200NORM_OP_SOFTMAX_BWD || spec_.op == B200NORM_OP_LOGSOFTMAX_BWD)
+                           ? 2
+                           : 1;
+  std::vector<at::Tensor> keep;  // views must outlive the launch call
+  keep.reserve(inputs.size() + outputs.size());
+  std::vector<b200norm_tensor> in_args, out_args;
+  in_args.reserve(inputs.size());
+  out_args.reserve(outputs.size());
+  for (size_t i = 0; i < inputs.size(); ++i) {
+    keep.push_back((int)i < n_mat_in ? as_rows(inputs[i], cols) : inputs[i].reshape({-1}));
+    in_args.push_back(as_arg(keep.back()));
+  }
+  int n_mat_out = 0;
+  switch (spec_.op) {
+    case B200NORM_OP_LAYERNORM_FWD:
+    case B200NORM_OP_RMSNORM_FWD:
+    case B200NORM_OP_SOFTMAX_FWD:
+    case B200NORM_OP_LOGSOFTMAX_FWD:
+    case B200NORM_OP_SOFTMAX_BWD:
+    case B200NORM_OP_LOGSOFTMAX_BWD:
+      n_mat_out = 1;
+      break;
+    case B200NORM_OP_LAYERNORM_BWD:
+    case B200NORM_OP_RMSNORM_BWD:
+      n_mat_out = (spec_.flags & B200NORM_F_OUT_DX) ? 1 : 0;
+      break;
+    default:
+      n_mat_out = 0;
+  }
+  for (size_t i = 0; i < outputs.size(); ++i) {
+    keep.push_back((int)i < n_mat_out ? as_rows(outputs[i], cols) : outputs[i].view({-1}));
+    out_args.push_back(as_arg(keep.back()));
+  }
+
+  const size_t ws_bytes = b200norm_workspace_bytes(&d);
+  void* ws_ptr = nullptr;
+  size_t ws_n = 0;
+  at::Tensor ws;
+  if (ws_bytes > 0) {
+    ws = workspace(ws_bytes, lead.device(), stream);
+    ws_ptr = ws.data_ptr();
+    ws_n = (size_t)ws.numel();
+  }
+  const int rc = b200norm_launch(&d, in_args.data(), (int)in_args.size(), out_args.data(), (int)out_args.size(),
+                                 ws_ptr, ws_n, (void*)stream);
+  if (rc != B200NORM_OK) raise(rc);
+  (void)is_norm_bwd;
+  return outputs;
+}
+
+}  // namespace b200norm

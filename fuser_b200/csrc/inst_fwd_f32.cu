@@ -1,0 +1,5 @@
+// Instantiations of the forward-type ring kernels for float (see ring_inst_fwd.cuh).
+#include "ring_inst_fwd.cuh"
+namespace b200norm {
+RingKernel ring_fwd_kernel_f32(int op, int tpr, int ch) { return ring_fwd_kernel_for<float>(op, tpr, ch); }
+}  // namespace b200norm

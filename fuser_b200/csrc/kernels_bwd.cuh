@@ -1,0 +1,186 @@
+// kernels_bwd.cuh — LayerNorm / RMSNorm backward on the TMA ring, with the
+// dgamma / dbeta column sums fused in (the InnerOuterPersistent segment).
+//
+// Reference math (csrc/ops/normalization.cpp):
+//   layer_norm_backward :382-436, rms_norm_backward :438-485 (keeps the -sum(g)
+//   term), thunder_rms_norm_backward :487-535 (textbook form, rms statistic).
+//     x_hat = (x - mean) * invstd            g = dy * w
+//     dx    = (invstd / N) * (N*g - sum(g) - x_hat * sum(g*x_hat))
+//     dw    = sum_rows dy * x_hat            db = sum_rows dy
+// Evaluated here as  dx = A*g + B*xc + C  with xc = x - mean and per-row scalars
+//     A = invstd,  B = -invstd^3 * sum(g*xc) / N,  C = -invstd * sum(g) / N
+// (same polynomial, three packed FMAs per two elements).
+//
+// The reference's generated kernel (scheduler/normalization_inner_outer*.cpp)
+// keeps per-CTA partial column sums in registers and finishes them with a grid
+// reduction; we keep per-thread fp32 column accumulators for the CTA's lifetime,
+// combine the consumer groups through shared memory once, write one fp32 partial
+// row per CTA, and finish in finalize_partials_kernel (kernels_generic.cuh).
+#pragma once
+
+#include "ring.cuh"
+
+namespace b200norm {
+
+// LN: true = LayerNorm (mean input, dbeta), false = RMSNorm.
+// Each thread owns chunks c = gtid + j*TPR, j < CH, of the CTA's column slice
+// (the planner guarantees nchunks <= TPR*CH).
+// CACHE: g and xc stay in registers between the reduction pass and the dx pass;
+// otherwise the stage is re-read from shared memory.
+template <typename T, int TPR, int CH, bool LN, bool CACHE>
+__global__ void __launch_bounds__(kMaxBlock, 1) norm_bwd_ring_kernel(const RowParams p) {
+  constexpr int VEC = IO<T>::VEC;
+  constexpr int H = VEC / 2;
+  static_assert(CH > 0, "column accumulators need a fixed chunk ownership");
+  const uint32_t smem0 = smem_u32(smem_raw);
+  ring_setup(p, smem0);
+  Group<TPR> g(p, smem0);
+  Ring<T, TPR> ring(p, smem0, g);
+  ring.prologue();
+
+  const int nchunks = p.nchunks;
+  const bool want_dx = (p.flags & kFlagOutDx) != 0;
+  const bool want_dw = (p.flags & kFlagOutDw) != 0;
+  const bool want_db = LN && (p.flags & kFlagOutDb) != 0;
+  const bool centered = LN || (p.flags & kFlagRmsBwdCentered) != 0;
+  const bool stat_rms = !LN && (p.flags & kFlagStatIsRms) != 0;
+  const size_t col0_bytes = (size_t)g.crank * p.slice_bytes;
+  uint4 wq[CH];
+  load_params_to_regs<T, TPR, CH>(p.weight, col0_bytes, g.gtid, nchunks, 1.0f, wq);
+
+  float2 dw_acc[CH][H];
+  float2 db_acc[LN ? CH : 1][H];
+#pragma unroll
+  for (int j = 0; j < CH; ++j) {
+#pragma unroll
+    for (int k = 0; k < H; ++k) {
+      dw_acc[j][k] = f2(0.f);
+      if constexpr (LN) db_acc[j][k] = f2(0.f);
+    }
+  }
+
+  // per-row statistics are prefetched one row ahead (they sit on the critical path otherwise)
+  float nxt_mean = 0.f, nxt_stat = 0.f;
+  if (ring.more()) {
+    if constexpr (LN) nxt_mean = __ldg(p.stat0 + ring.row0);
+    nxt_stat = __ldg(p.stat1 + ring.row0);
+  }
+
+  uint8_t* out_tile = out_row_ptr<T>(p, ring.row0, g.crank, g.gtid);
+  const size_t out_row_bytes = (size_t)p.out_stride * sizeof(T);
+  const size_t out_tile_bytes = (size_t)ring.row_step * out_row_bytes;
+  for (; ring.more(); ring.advance(), out_tile += out_tile_bytes) {
+    ring.wait();
+    const int nrows = ring.nrows();
+    const uint8_t* dyrow = smem_raw + ring.stage_off + 16u * (uint32_t)g.gtid;
+    uint8_t* dxrow = out_tile;
+    for (int r = 0; r < nrows; ++r, dyrow += p.slice_bytes, dxrow += out_row_bytes) {
+      const uint8_t* xrow = dyrow + p.stream_bytes;
+      const float mean = nxt_mean;
+      const float st = nxt_stat;
+      {
+        int64_t nrow = ring.row0 + r + 1;
+        if (r == nrows - 1) nrow = ring.row0 + ring.row_step;
+        if (nrow < p.rows) {
+          if constexpr (LN) nxt_mean = __ldg(p.stat0 + nrow);
+          nxt_stat = __ldg(p.stat1 + nrow);
+        }
+      }
+      const float invstd = stat_rms ? rcp_fast(st) : st;
+      const float2 nmean = f2(-mean);
+      const float2 is2 = f2(invstd);
+      float2 gv[CACHE ? CH : 1][H];
+      float2 xv[CACHE ? CH : 1][H];
+      float2 s1 = f2(0.f), s2 = f2(0.f);
+      for_each_chunk<TPR, CH>(g.gtid, nchunks, [&](int j, int coff) {
+        float2 dy[H], xc[H], w[H];
+        IO<T>::unpack2(ld_smem_u4(dyrow + 16 * coff), dy);
+        IO<T>::unpack2(ld_smem_u4(xrow + 16 * coff), xc);
+        IO<T>::unpack2(wq[j], w);
+#pragma unroll
+        for (int k = 0; k < H; ++k) {
+          const float2 gg = f2mul(dy[k], w[k]);
+          if constexpr (LN) xc[k] = f2add(xc[k], nmean);
+          s1 = f2add(s1, gg);
+          s2 = f2fma(gg, xc[k], s2);
+          dw_acc[j][k] = f2fma(dy[k], f2mul(xc[k], is2), dw_acc[j][k]);
+          if constexpr (LN) db_acc[j][k] = f2add(db_acc[j][k], dy[k]);
+          if constexpr (CACHE) {
+            gv[j][k] = gg;
+            xv[j][k] = xc[k];
+          }
+        }
+      });
+      if (want_dx) {
+        float s[2] = {s1.x + s1.y, s2.x + s2.y};
+        g.template allreduce<SumOp, 2>(s);
+        if (CACHE && r == nrows - 1) ring.refill();  // g / xc live in registers: the stage is free
+        const float a_n = invstd * p.inv_n;
+        const float2 A = is2;
+        const float2 B = f2(-(a_n * invstd * invstd) * s[1]);
+        const float2 C = f2(centered ? -(a_n * s[0]) : 0.f);
+        for_each_chunk<TPR, CH>(g.gtid, nchunks, [&](int j, int coff) {
+          float2 dx[H];
+          if constexpr (CACHE) {
+#pragma unroll
+            for (int k = 0; k < H; ++k) dx[k] = f2fma(A, gv[j][k], f2fma(B, xv[j][k], C));
+          } else {
+            float2 dy[H], xc[H], w[H];
+            IO<T>::unpack2(ld_smem_u4(dyrow + 16 * coff), dy);
+            IO<T>::unpack2(ld_smem_u4(xrow + 16 * coff), xc);
+            IO<T>::unpack2(wq[j], w);
+#pragma unroll
+            for (int k = 0; k < H; ++k) {
+              if constexpr (LN) xc[k] = f2add(xc[k], nmean);
+              dx[k] = f2fma(A, f2mul(dy[k], w[k]), f2fma(B, xc[k], C));
+            }
+          }
+          st_global_stream(dxrow + 16 * coff, IO<T>::pack2(dx));
+        });
+      }
+    }
+    if (!CACHE || !want_dx) {  // the stage was read until the end of the tile
+      g.sync();
+      ring.refill();
+    }
+  }
+
+  // ---- combine the groups' column accumulators and emit this CTA's partial row ----
+  if (want_dw || want_db) {
+    const int nct = p.groups * TPR;
+    float* acc_w = reinterpret_cast<float*>(smem_raw + p.off_acc);
+    float* acc_b = acc_w + p.cols_cta;
+    named_bar_sync(15, nct);  // every group is done with the ring
+    for (int gi = 0; gi < p.groups; ++gi) {
+      if (g.gid == gi) {
+        for_each_chunk<TPR, CH>(g.gtid, nchunks, [&](int j, int coff) {
+          const int c = g.gtid + coff;
+#pragma unroll
+          for (int k = 0; k < H; ++k) {
+            float2* pw = reinterpret_cast<float2*>(acc_w + c * VEC + 2 * k);
+            float2* pb = reinterpret_cast<float2*>(acc_b + c * VEC + 2 * k);
+            if (gi == 0) {
+              *pw = dw_acc[j][k];
+              if constexpr (LN) *pb = db_acc[j][k];
+            } else {
+              *pw = f2add(*pw, dw_acc[j][k]);
+              if constexpr (LN) *pb = f2add(*pb, db_acc[j][k]);
+            }
+          }
+        });
+      }
+      named_bar_sync(15, nct);
+    }
+    // partials layout: [part][K][N], K = 2 for LN (dw, db), 1 for RMSNorm
+    constexpr int K = LN ? 2 : 1;
+    const int64_t part = blockIdx.x / g.csize;
+    float* dst = p.partials + (size_t)part * K * p.cols + (size_t)g.crank * p.cols_cta;
+    for (int col = threadIdx.x * 4; col < p.cols_cta; col += nct * 4) {
+      *reinterpret_cast<float4*>(dst + col) = *reinterpret_cast<const float4*>(acc_w + col);
+      if constexpr (LN) *reinterpret_cast<float4*>(dst + p.cols + col) = *reinterpret_cast<const float4*>(acc_b + col);
+    }
+  }
+  ring_teardown();
+}
+
+}  // namespace b200norm

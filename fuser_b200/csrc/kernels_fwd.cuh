@@ -1,0 +1,358 @@
+// kernels_fwd.cuh — ring-pipelined kernels without per-column state:
+//   RMSNorm fwd, LayerNorm fwd, softmax fwd/bwd, log-softmax fwd/bwd.
+//
+// Math follows the reference op builders (csrc/ops/normalization.cpp):
+//   rms_norm :352-380, layer_norm :304-342 (Welford -> two-pass: mean, then
+//   sum((x-mean)^2), which is what the segmenter's TranslateApplicableWelford does
+//   for persistent kernels, fusion_segmenter.cpp:2341), softmax :169-189,
+//   softmax_backward :191-210, log_softmax :212-231, log_softmax_backward :233-249.
+// All arithmetic is fp32 (packed FFMA2/FMUL2/FADD2 where two lanes share an op);
+// the only rounding to the io dtype is at the store.
+//
+// Each thread owns chunks c = gtid + j*TPR (j < CH) of the CTA's column slice: the row
+// is read from the shared-memory ring ONCE into registers and every later pass runs on
+// registers (the register-persistent buffer of the reference's inner-persistent
+// schedule). CH == 0 is the looping form for slices wider than 4*TPR chunks: the stage
+// is re-read from shared memory in each pass.
+#pragma once
+
+#include "ring.cuh"
+
+namespace b200norm {
+
+// ---------------------------------------------------------------------------
+// RMSNorm forward: stat = rsqrt(mean(x^2)+eps) (or sqrt(...) with STAT_IS_RMS),
+// y = x * invstd * w.
+// ---------------------------------------------------------------------------
+template <typename T, int TPR, int CH>
+__global__ void __launch_bounds__(kMaxBlock, 1) rmsnorm_fwd_ring_kernel(const RowParams p) {
+  constexpr int VEC = IO<T>::VEC;
+  constexpr int H = VEC / 2;
+  constexpr int NC = CH > 0 ? CH : 1;
+  const uint32_t smem0 = smem_u32(smem_raw);
+  ring_setup(p, smem0);
+  Group<TPR> g(p, smem0);
+  Ring<T, TPR> ring(p, smem0, g);
+  ring.prologue();
+
+  const int nchunks = p.nchunks;
+  const bool stat_rms = (p.flags & kFlagStatIsRms) != 0;
+  const size_t col0_bytes = (size_t)g.crank * p.slice_bytes;
+  uint4 wq[NC];
+  load_params_to_regs<T, TPR, CH>(p.weight, col0_bytes, g.gtid, nchunks, 1.0f, wq);
+  const bool stat_writer = g.gtid == 0 && g.crank == 0 && p.stat1 != nullptr;
+
+  uint8_t* out_tile = out_row_ptr<T>(p, ring.row0, g.crank, g.gtid);
+  const size_t out_row_bytes = (size_t)p.out_stride * sizeof(T);
+  const size_t out_tile_bytes = (size_t)ring.row_step * out_row_bytes;
+  for (; ring.more(); ring.advance(), out_tile += out_tile_bytes) {
+    ring.wait();
+    const int nrows = ring.nrows();
+    const uint8_t* xrow = smem_raw + ring.stage_off + 16u * (uint32_t)g.gtid;
+    uint8_t* yrow = out_tile;
+    for (int r = 0; r < nrows; ++r, xrow += p.slice_bytes, yrow += out_row_bytes) {
+      float2 x[NC][H];
+      float2 acc = f2(0.f);
+      for_each_chunk<TPR, CH>(g.gtid, nchunks, [&](int j, int coff) {
+        float2 t[H];
+        IO<T>::unpack2(ld_smem_u4(xrow + 16 * coff), t);
+#pragma unroll
+        for (int k = 0; k < H; ++k) {
+          acc = f2fma(t[k], t[k], acc);
+          if constexpr (CH > 0) x[j][k] = t[k];
+        }
+      });
+      float ss[1] = {acc.x + acc.y};
+      g.template allreduce<SumOp, 1>(ss);
+      if (CH > 0 && r == nrows - 1) ring.refill();  // registers hold the row: the stage is free
+      const float var_eps = ss[0] * p.inv_n + p.eps;
+      // one MUFU on either path: invstd = rsqrt(v); the rms flavour saves sqrt(v) = v * rsqrt(v)
+      const float invstd = rsqrt_fast(var_eps);
+      const float rms = var_eps * invstd;
+      const float2 scale = f2(invstd);
+      for_each_chunk<TPR, CH>(g.gtid, nchunks, [&](int j, int coff) {
+        float2 y[H], w[H];
+        if constexpr (CH > 0) {
+          IO<T>::unpack2(wq[j], w);
+#pragma unroll
+          for (int k = 0; k < H; ++k) y[k] = f2mul(f2mul(x[j][k], scale), w[k]);
+        } else {
+          IO<T>::unpack2(ld_smem_u4(xrow + 16 * coff), y);
+          IO<T>::unpack2(load_param_chunk<T>(p.weight, col0_bytes, g.gtid + coff, 1.0f), w);
+#pragma unroll
+          for (int k = 0; k < H; ++k) y[k] = f2mul(f2mul(y[k], scale), w[k]);
+        }
+        st_global_stream(yrow + 16 * coff, IO<T>::pack2(y));
+      });
+      if (stat_writer) p.stat1[ring.row0 + r] = stat_rms ? rms : invstd;
+    }
+    if constexpr (CH == 0) {  // looping form: the stage was read until the last pass
+      g.sync();
+      ring.refill();
+    }
+  }
+  ring_teardown();
+}
+
+// ---------------------------------------------------------------------------
+// LayerNorm forward: mean, invstd = rsqrt(M2/N + eps), y = (x-mean)*invstd*w + b.
+// ---------------------------------------------------------------------------
+template <typename T, int TPR, int CH>
+__global__ void __launch_bounds__(kMaxBlock, 1) layernorm_fwd_ring_kernel(const RowParams p) {
+  constexpr int VEC = IO<T>::VEC;
+  constexpr int H = VEC / 2;
+  constexpr int NC = CH > 0 ? CH : 1;
+  const uint32_t smem0 = smem_u32(smem_raw);
+  ring_setup(p, smem0);
+  Group<TPR> g(p, smem0);
+  Ring<T, TPR> ring(p, smem0, g);
+  ring.prologue();
+
+  const int nchunks = p.nchunks;
+  const size_t col0_bytes = (size_t)g.crank * p.slice_bytes;
+  uint4 wq[NC], bq[NC];
+  load_params_to_regs<T, TPR, CH>(p.weight, col0_bytes, g.gtid, nchunks, 1.0f, wq);
+  load_params_to_regs<T, TPR, CH>(p.bias, col0_bytes, g.gtid, nchunks, -0.0f, bq);
+  const bool stat_writer = g.gtid == 0 && g.crank == 0;
+
+  uint8_t* out_tile = out_row_ptr<T>(p, ring.row0, g.crank, g.gtid);
+  const size_t out_row_bytes = (size_t)p.out_stride * sizeof(T);
+  const size_t out_tile_bytes = (size_t)ring.row_step * out_row_bytes;
+  for (; ring.more(); ring.advance(), out_tile += out_tile_bytes) {
+    ring.wait();
+    const int nrows = ring.nrows();
+    const uint8_t* xrow = smem_raw + ring.stage_off + 16u * (uint32_t)g.gtid;
+    uint8_t* yrow = out_tile;
+    for (int r = 0; r < nrows; ++r, xrow += p.slice_bytes, yrow += out_row_bytes) {
+      float2 x[NC][H];
+      float2 acc = f2(0.f);
+      for_each_chunk<TPR, CH>(g.gtid, nchunks, [&](int j, int coff) {
+        float2 t[H];
+        IO<T>::unpack2(ld_smem_u4(xrow + 16 * coff), t);
+#pragma unroll
+        for (int k = 0; k < H; ++k) {
+          acc = f2add(acc, t[k]);
+          if constexpr (CH > 0) x[j][k] = t[k];
+        }
+      });
+      float s[1] = {acc.x + acc.y};
+      g.template allreduce<SumOp, 1>(s);
+      if (CH > 0 && r == nrows - 1) ring.refill();  // registers hold the row: the stage is free
+      const float mean = s[0] * p.inv_n;
+      const float2 nmean = f2(-mean);
+      acc = f2(0.f);
+      for_each_chunk<TPR, CH>(g.gtid, nchunks, [&](int j, int coff) {
+        float2 t[H];
+        if constexpr (CH == 0) IO<T>::unpack2(ld_smem_u4(xrow + 16 * coff), t);
+#pragma unroll
+        for (int k = 0; k < H; ++k) {
+          if constexpr (CH > 0) {
+            x[j][k] = f2add(x[j][k], nmean);  // x now holds x - mean
+            acc = f2fma(x[j][k], x[j][k], acc);
+          } else {
+            const float2 d = f2add(t[k], nmean);
+            acc = f2fma(d, d, acc);
+          }
+        }
+      });
+      float m2[1] = {acc.x + acc.y};
+      g.template allreduce<SumOp, 1>(m2);
+      const float invstd = rsqrt_fast(m2[0] * p.inv_n + p.eps);
+      const float2 is2 = f2(invstd);
+      for_each_chunk<TPR, CH>(g.gtid, nchunks, [&](int j, int coff) {
+        float2 y[H], w[H], b[H];
+        if constexpr (CH > 0) {
+          IO<T>::unpack2(wq[j], w);
+          IO<T>::unpack2(bq[j], b);
+#pragma unroll
+          for (int k = 0; k < H; ++k) y[k] = f2fma(f2mul(x[j][k], is2), w[k], b[k]);
+        } else {
+          IO<T>::unpack2(ld_smem_u4(xrow + 16 * coff), y);
+          IO<T>::unpack2(load_param_chunk<T>(p.weight, col0_bytes, g.gtid + coff, 1.0f), w);
+          IO<T>::unpack2(load_param_chunk<T>(p.bias, col0_bytes, g.gtid + coff, -0.0f), b);
+#pragma unroll
+          for (int k = 0; k < H; ++k) y[k] = f2fma(f2mul(f2add(y[k], nmean), is2), w[k], b[k]);
+        }
+        st_global_stream(yrow + 16 * coff, IO<T>::pack2(y));
+      });
+      if (stat_writer) {
+        if (p.stat0 != nullptr) p.stat0[ring.row0 + r] = mean;
+        if (p.stat1 != nullptr) p.stat1[ring.row0 + r] = invstd;
+      }
+    }
+    if constexpr (CH == 0) {
+      g.sync();
+      ring.refill();
+    }
+  }
+  ring_teardown();
+}
+
+// ---------------------------------------------------------------------------
+// softmax / log-softmax forward. x, then exp(x-max) (or x-max for the log flavour),
+// live in registers — one MUFU per element. The looping form recomputes exp.
+// NaN semantics: max is NaN-propagating (at::amax); any NaN / +inf / all -inf row
+// turns into an all-NaN row exactly as the op-by-op ATen evaluation does.
+// ---------------------------------------------------------------------------
+template <typename T, int TPR, int CH, bool LOG>
+__global__ void __launch_bounds__(kMaxBlock, 1) softmax_fwd_ring_kernel(const RowParams p) {
+  constexpr int VEC = IO<T>::VEC;
+  constexpr int H = VEC / 2;
+  constexpr int NC = CH > 0 ? CH : 1;
+  const uint32_t smem0 = smem_u32(smem_raw);
+  ring_setup(p, smem0);
+  Group<TPR> g(p, smem0);
+  Ring<T, TPR> ring(p, smem0, g);
+  ring.prologue();
+  const int nchunks = p.nchunks;
+
+  uint8_t* out_tile = out_row_ptr<T>(p, ring.row0, g.crank, g.gtid);
+  const size_t out_row_bytes = (size_t)p.out_stride * sizeof(T);
+  const size_t out_tile_bytes = (size_t)ring.row_step * out_row_bytes;
+  for (; ring.more(); ring.advance(), out_tile += out_tile_bytes) {
+    ring.wait();
+    const int nrows = ring.nrows();
+    const uint8_t* xrow = smem_raw + ring.stage_off + 16u * (uint32_t)g.gtid;
+    uint8_t* yrow = out_tile;
+    for (int r = 0; r < nrows; ++r, xrow += p.slice_bytes, yrow += out_row_bytes) {
+      float2 x[NC][H];
+      float m[1] = {-INFINITY};
+      for_each_chunk<TPR, CH>(g.gtid, nchunks, [&](int j, int coff) {
+        float2 t[H];
+        IO<T>::unpack2(ld_smem_u4(xrow + 16 * coff), t);
+#pragma unroll
+        for (int k = 0; k < H; ++k) {
+          m[0] = MaxOp::apply(m[0], MaxOp::apply(t[k].x, t[k].y));
+          if constexpr (CH > 0) x[j][k] = t[k];
+        }
+      });
+      g.template allreduce<MaxOp, 1>(m);
+      if (CH > 0 && r == nrows - 1) ring.refill();  // registers hold the row: the stage is free
+      const float2 nmx = f2(-m[0]);
+      float2 acc = f2(0.f);
+      for_each_chunk<TPR, CH>(g.gtid, nchunks, [&](int j, int coff) {
+        float2 t[H];
+        if constexpr (CH == 0) IO<T>::unpack2(ld_smem_u4(xrow + 16 * coff), t);
+#pragma unroll
+        for (int k = 0; k < H; ++k) {
+          const float2 d = f2add(CH > 0 ? x[j][k] : t[k], nmx);
+          const float2 e = make_float2(exp_for<T>(d.x), exp_for<T>(d.y));
+          acc = f2add(acc, e);
+          if constexpr (CH > 0) x[j][k] = LOG ? d : e;
+        }
+      });
+      float s[1] = {acc.x + acc.y};
+      g.template allreduce<SumOp, 1>(s);
+      const float2 fin = f2(LOG ? -logf(s[0]) : rcp_fast(s[0]));
+      for_each_chunk<TPR, CH>(g.gtid, nchunks, [&](int j, int coff) {
+        float2 y[H];
+        if constexpr (CH > 0) {
+#pragma unroll
+          for (int k = 0; k < H; ++k) y[k] = LOG ? f2add(x[j][k], fin) : f2mul(x[j][k], fin);
+        } else {
+          float2 t[H];
+          IO<T>::unpack2(ld_smem_u4(xrow + 16 * coff), t);
+#pragma unroll
+          for (int k = 0; k < H; ++k) {
+            const float2 d = f2add(t[k], nmx);
+            y[k] = LOG ? f2add(d, fin) : f2mul(make_float2(exp_for<T>(d.x), exp_for<T>(d.y)), fin);
+          }
+        }
+        st_global_stream(yrow + 16 * coff, IO<T>::pack2(y));
+      });
+    }
+    if constexpr (CH == 0) {
+      g.sync();
+      ring.refill();
+    }
+  }
+  ring_teardown();
+}
+
+// ---------------------------------------------------------------------------
+// softmax backward: dx = y*dy - y*sum(y*dy)      (in0 = dy, in1 = y)
+// log-softmax backward: dx = dy - exp(y)*sum(dy)
+// t = y*dy (or dy) and y (or exp(y)) stay in registers.
+// ---------------------------------------------------------------------------
+template <typename T, int TPR, int CH, bool LOG>
+__global__ void __launch_bounds__(kMaxBlock, 1) softmax_bwd_ring_kernel(const RowParams p) {
+  constexpr int VEC = IO<T>::VEC;
+  constexpr int H = VEC / 2;
+  constexpr int NC = CH > 0 ? CH : 1;
+  const uint32_t smem0 = smem_u32(smem_raw);
+  ring_setup(p, smem0);
+  Group<TPR> g(p, smem0);
+  Ring<T, TPR> ring(p, smem0, g);
+  ring.prologue();
+  const int nchunks = p.nchunks;
+  const bool round_sum = (p.flags & kFlagRoundRowsum) != 0;
+
+  uint8_t* out_tile = out_row_ptr<T>(p, ring.row0, g.crank, g.gtid);
+  const size_t out_row_bytes = (size_t)p.out_stride * sizeof(T);
+  const size_t out_tile_bytes = (size_t)ring.row_step * out_row_bytes;
+  for (; ring.more(); ring.advance(), out_tile += out_tile_bytes) {
+    ring.wait();
+    const int nrows = ring.nrows();
+    const uint8_t* dyrow = smem_raw + ring.stage_off + 16u * (uint32_t)g.gtid;
+    uint8_t* dxrow = out_tile;
+    for (int r = 0; r < nrows; ++r, dyrow += p.slice_bytes, dxrow += out_row_bytes) {
+      const uint8_t* yrow = dyrow + p.stream_bytes;
+      float2 a[NC][H];  // y*dy   | dy        (log)
+      float2 b[NC][H];  // y      | exp(y)    (log)
+      float2 acc = f2(0.f);
+      auto load = [&](int coff, float2(&av)[H], float2(&bv)[H]) {
+        float2 dy[H], y[H];
+        IO<T>::unpack2(ld_smem_u4(dyrow + 16 * coff), dy);
+        IO<T>::unpack2(ld_smem_u4(yrow + 16 * coff), y);
+#pragma unroll
+        for (int k = 0; k < H; ++k) {
+          if constexpr (LOG) {
+            av[k] = dy[k];
+            bv[k] = make_float2(expf(y[k].x), expf(y[k].y));
+          } else {
+            av[k] = f2mul(y[k], dy[k]);
+            bv[k] = y[k];
+          }
+        }
+      };
+      for_each_chunk<TPR, CH>(g.gtid, nchunks, [&](int j, int coff) {
+        float2 av[H], bv[H];
+        load(coff, av, bv);
+#pragma unroll
+        for (int k = 0; k < H; ++k) {
+          acc = f2add(acc, av[k]);
+          if constexpr (CH > 0) {
+            a[j][k] = av[k];
+            b[j][k] = bv[k];
+          }
+        }
+      });
+      float s[1] = {acc.x + acc.y};
+      g.template allreduce<SumOp, 1>(s);
+      if (CH > 0 && r == nrows - 1) ring.refill();  // registers hold the row: the stage is free
+      float sum = s[0];
+      if (round_sum) sum = IO<T>::round_trip(sum);
+      const float2 nsum = f2(-sum);
+      for_each_chunk<TPR, CH>(g.gtid, nchunks, [&](int j, int coff) {
+        float2 dx[H];
+        if constexpr (CH > 0) {
+#pragma unroll
+          for (int k = 0; k < H; ++k) dx[k] = f2fma(b[j][k], nsum, a[j][k]);  // a - b*sum
+        } else {
+          float2 av[H], bv[H];
+          load(coff, av, bv);
+#pragma unroll
+          for (int k = 0; k < H; ++k) dx[k] = f2fma(bv[k], nsum, av[k]);
+        }
+        st_global_stream(dxrow + 16 * coff, IO<T>::pack2(dx));
+      });
+    }
+    if constexpr (CH == 0) {
+      g.sync();
+      ring.refill();
+    }
+  }
+  ring_teardown();
+}
+
+}  // namespace b200norm

@@ -10,7 +10,7 @@
 // finishing kernel for fp32 partial column sums.
 #pragma once
 
-#include "kernels_tma_fwd.cuh"
+#include "ring.cuh"
 
 namespace b200norm {
 
@@ -230,34 +230,55 @@ __global__ void __launch_bounds__(128) generic_colsum_kernel(const RowParams p, 
 }
 
 // Finish fp32 partial column sums: out_k[n] = cast(sum_p partials[p][k][n]).
-// block = (32, 8): x walks columns, y splits the partial rows; smem tree over y.
-// With out_f32 != nullptr the fp32 sums are written instead (multi-GPU: the
-// caller allreduces them, then runs this kernel again with nparts = 1).
-template <typename T>
-__global__ void __launch_bounds__(256) finalize_partials_kernel(const float* __restrict__ partials,
-                                                                int nparts, int K, int N,
-                                                                void* out_a, void* out_b,
-                                                                float* out_f32) {
-  __shared__ float sm[8][33];
-  const int col = blockIdx.x * 32 + threadIdx.x;
+// block = (32, 16): x walks float4 column vectors (128 columns per block), y splits the
+// partial rows; smem tree over y. With out_f32 != nullptr the fp32 sums are written
+// instead (multi-GPU: the caller allreduces them, then runs this kernel again with
+// nparts = 1). N must be a multiple of 4 for the vector path; VECN = 1 is the scalar form.
+constexpr int kFinY = 16;
+template <typename T, int VECN>
+__global__ void __launch_bounds__(32 * kFinY) finalize_partials_kernel(const float* __restrict__ partials,
+                                                                       int nparts, int K, int N,
+                                                                       void* out_a, void* out_b,
+                                                                       float* out_f32) {
+  __shared__ float sm[kFinY][32 * VECN + 1];
+  const int col = (blockIdx.x * 32 + threadIdx.x) * VECN;
   const int k = blockIdx.y;
-  float acc = 0.f;
+  float acc[VECN];
+#pragma unroll
+  for (int i = 0; i < VECN; ++i) acc[i] = 0.f;
   if (col < N) {
-    for (int pidx = threadIdx.y; pidx < nparts; pidx += 8) {
-      acc += partials[((size_t)pidx * K + k) * N + col];
+    const float* src = partials + (size_t)k * N + col;
+    const size_t pstride = (size_t)K * N;
+#pragma unroll 4
+    for (int pidx = threadIdx.y; pidx < nparts; pidx += kFinY) {
+      if constexpr (VECN == 4) {
+        const float4 v = __ldcg(reinterpret_cast<const float4*>(src + pidx * pstride));
+        acc[0] += v.x;
+        acc[1] += v.y;
+        acc[2] += v.z;
+        acc[3] += v.w;
+      } else {
+        acc[0] += __ldcg(src + pidx * pstride);
+      }
     }
   }
-  sm[threadIdx.y][threadIdx.x] = acc;
-  __syncthreads();
-  if (threadIdx.y == 0 && col < N) {
-    float t = 0.f;
 #pragma unroll
-    for (int y = 0; y < 8; ++y) t += sm[y][threadIdx.x];
-    if (out_f32 != nullptr) {
-      out_f32[(size_t)k * N + col] = t;
-    } else {
-      T* o = static_cast<T*>(k == 0 ? out_a : out_b);
-      if (o != nullptr) o[col] = IO<T>::from_f32(t);
+  for (int i = 0; i < VECN; ++i) sm[threadIdx.y][threadIdx.x * VECN + i] = acc[i];
+  __syncthreads();
+  // threads (x, y < VECN) finish column col_base + x*VECN + y ... remapped so that stores coalesce
+  const int t = threadIdx.y * 32 + threadIdx.x;
+  if (t < 32 * VECN) {
+    const int c = blockIdx.x * 32 * VECN + t;
+    if (c < N) {
+      float r = 0.f;
+#pragma unroll
+      for (int y = 0; y < kFinY; ++y) r += sm[y][t];
+      if (out_f32 != nullptr) {
+        out_f32[(size_t)k * N + c] = r;
+      } else {
+        T* o = static_cast<T*>(k == 0 ? out_a : out_b);
+        if (o != nullptr) o[c] = IO<T>::from_f32(r);
+      }
     }
   }
 }

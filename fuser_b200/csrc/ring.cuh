@@ -1,0 +1,392 @@
+// ring.cuh — the shared skeleton of every "TMA ring" kernel (sm_100a).
+//
+// One CTA (or one CTA of a cluster) owns a column slice [col0, col0+cols_cta) of a
+// strided sequence of row tiles. The CTA is split into G consumer groups of TPR
+// threads; group g owns D shared-memory stages and walks the tiles
+// cid + (g + k*G)*nclusters, k = 0,1,... Each group keeps its own stages full: its
+// first warp issues 1-D bulk copies (cp.async.bulk, SASS UBLKCP) that complete on a
+// per-stage mbarrier, D tiles ahead, and re-issues into a stage as soon as the whole
+// group has finished reading it. There is no producer warp and no "empty" barrier:
+// a stage is only ever touched by one group, so the refill is ordered by that group's
+// own barrier, and mbarrier phases can never alias.
+// Groups reduce with warp shuffles (+ one named barrier when TPR > 32, + a DSMEM
+// st.async exchange when the row is split over a thread-block cluster).
+//
+// Everything the hot loop needs is a running register (stage offset, barrier address,
+// phase bit, row index): there is no division, modulo or 64-bit multiply per row.
+// Chunk offsets inside a row are compile-time immediates (j*TPR*16 bytes).
+//
+// This replaces, for the matched segments, the loop nest nvFuser's inner persistent
+// schedulers generate (reference: scheduler/normalization_inner_tma.cpp:35-164 for the
+// TMA variant, runtime/warp.cu:30-98 for the cross-warp reduce, runtime/cluster.cu:223-297
+// for the cluster reduce). The structure is ours: bytes in flight are set by
+// G*D*tile bytes, not by occupancy or registers.
+#pragma once
+
+#include "common.cuh"
+
+namespace b200norm {
+
+// Dynamic shared memory of every ring kernel.
+extern __shared__ __align__(128) uint8_t smem_raw[];
+
+constexpr int kMaxWarpsPerGroup = 16;
+constexpr int kMaxCluster = 16;
+constexpr int kRedNV = 4;  // max floats reduced at once
+constexpr int kRedSetBytes = kRedNV * kMaxWarpsPerGroup * 4;  // one slot set: [kRedNV][16 warps]
+constexpr int kClsSetBytes = kRedNV * kMaxCluster * 4;        // one cluster slot set: [16 ranks][kRedNV]
+constexpr int kMaxBlock = 512;  // G * TPR; 128 registers per thread at one CTA per SM
+
+constexpr uint32_t kFlagHasWeight = 1u << 0;
+constexpr uint32_t kFlagHasBias = 1u << 1;
+constexpr uint32_t kFlagStatIsRms = 1u << 2;
+constexpr uint32_t kFlagRmsBwdCentered = 1u << 3;
+constexpr uint32_t kFlagOutDx = 1u << 4;
+constexpr uint32_t kFlagOutDw = 1u << 5;
+constexpr uint32_t kFlagOutDb = 1u << 6;
+constexpr uint32_t kFlagPartialsF32 = 1u << 7;
+constexpr uint32_t kFlagRoundRowsum = 1u << 8;
+constexpr uint32_t kFlagReduceMax = 1u << 9;
+constexpr uint32_t kFlagReduceFmax = 1u << 10;
+constexpr uint32_t kFlagOutMean = 1u << 11;
+constexpr uint32_t kFlagOutInvstd = 1u << 12;
+
+struct RowParams {
+  // streamed operands (row-major, unit inner stride)
+  const void* in0;  // x (forward) | dy (backward)
+  const void* in1;  // -          | x or y (backward)
+  void* out0;       // y (forward) | dx (backward)
+  int64_t in0_stride, in1_stride, out_stride;  // row strides in elements
+  const void* weight;  // [N] io dtype or nullptr
+  const void* bias;    // [N] io dtype or nullptr
+  float* stat0;        // fwd: mean out (LN) ; bwd: mean in (LN)
+  float* stat1;        // fwd: invstd|rms out ; bwd: invstd|rms in
+  float* partials;     // bwd: fp32 [nparts][K][N]
+  int64_t rows;
+  int32_t cols;
+  float eps;
+  float inv_n;
+  float n_f;
+  uint32_t flags;
+  // pipeline geometry (filled by the planner)
+  int32_t groups;      // consumer groups per CTA
+  int32_t depth;       // stages per group (tiles in flight per group)
+  int32_t tile_rows;   // rows per tile
+  int32_t cols_cta;    // columns handled by this CTA (slice width)
+  int32_t nchunks;     // 16-byte chunks per row slice
+  int32_t nstreams;    // 1 or 2 streamed inputs
+  int32_t contiguous;  // tiles are contiguous in memory: one bulk copy per stream
+  uint32_t slice_bytes;   // cols_cta * sizeof(T)
+  uint32_t stream_bytes;  // tile_rows * slice_bytes (bytes of one stream in a stage)
+  uint32_t stage_bytes;   // nstreams * stream_bytes, 128-aligned
+  // shared-memory offsets
+  uint32_t off_red;   // float [groups][2][kRedNV][kMaxWarpsPerGroup]
+  uint32_t off_cls;   // float [groups][2][kMaxCluster][kRedNV]
+  uint32_t off_ring;  // groups*depth stages, group-major: stage (g*depth + s)
+  uint32_t off_acc;   // bwd: cross-group accumulator staging (aliases the ring)
+};
+
+// barrier block at the start of dynamic smem:  full[groups*depth] | clbar[groups]
+
+// ---------------------------------------------------------------------------
+// Consumer-group context: identity of the thread inside its group and the state of
+// the two reduction exchanges (intra-CTA slots, cluster slots).
+// ---------------------------------------------------------------------------
+template <int TPR>
+struct Group {
+  static constexpr int WPG = TPR / 32;
+  int gid;
+  int gtid;
+  int lane;
+  int warp;            // warp index inside the group
+  uint32_t red_off;    // byte offset of this group's current slot set in smem_raw
+  uint32_t cls_off;    // byte offset of this group's cluster slot sets in smem_raw
+  uint32_t cls_addr;   // the same as a shared-window address (for mapa / st.async)
+  uint32_t clbar;
+  uint32_t cl_phase;
+  uint32_t csize;
+  uint32_t crank;
+
+  __device__ __forceinline__ Group(const RowParams& p, uint32_t smem0) {
+    gid = threadIdx.x / TPR;
+    gtid = threadIdx.x % TPR;
+    lane = threadIdx.x & 31;
+    warp = gtid >> 5;
+    red_off = p.off_red + (uint32_t)gid * (2 * kRedSetBytes);
+    cls_off = p.off_cls + (uint32_t)gid * (2 * kClsSetBytes);
+    cls_addr = smem0 + cls_off;
+    clbar = smem0 + 8u * (uint32_t)(p.groups * p.depth + gid);
+    cl_phase = 0;
+    csize = cluster_nctarank();
+    crank = cluster_ctarank();
+  }
+
+  __device__ __forceinline__ void sync() const {
+    if constexpr (TPR == 32) {
+      __syncwarp();
+    } else {
+      named_bar_sync(1 + gid, TPR);
+    }
+  }
+
+  // All-reduce NV floats across the group's TPR threads and, when the row is
+  // split over a cluster, across the peer CTAs' same-numbered groups. Every
+  // thread returns the same bits (fixed combination order). Acts as a barrier
+  // for the group: on return every thread of the group has executed everything
+  // that precedes the call.
+  template <typename Op, int NV>
+  __device__ __forceinline__ void allreduce(float (&v)[NV]) {
+    static_assert(NV <= kRedNV, "too many values");
+    warp_allreduce<Op, NV>(v);
+    if constexpr (TPR > 32) {
+      // double-buffered slot sets: one named barrier per reduction is enough (a set is
+      // rewritten only two reductions later, after every reader passed the next barrier)
+      float* slots = reinterpret_cast<float*>(smem_raw + red_off);
+      if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) slots[i * kMaxWarpsPerGroup + warp] = v[i];
+      }
+      named_bar_sync(1 + gid, TPR);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        if constexpr (WPG == 2) {
+          const float2 t = *reinterpret_cast<const float2*>(slots + i * kMaxWarpsPerGroup);
+          v[i] = Op::apply(t.x, t.y);
+        } else {
+          float4 t = *reinterpret_cast<const float4*>(slots + i * kMaxWarpsPerGroup);
+          float r = Op::apply(Op::apply(t.x, t.y), Op::apply(t.z, t.w));
+#pragma unroll
+          for (int q = 1; q < WPG / 4; ++q) {
+            t = *reinterpret_cast<const float4*>(slots + i * kMaxWarpsPerGroup + 4 * q);
+            r = Op::apply(r, Op::apply(Op::apply(t.x, t.y), Op::apply(t.z, t.w)));
+          }
+          v[i] = r;
+        }
+      }
+      red_off ^= (uint32_t)kRedSetBytes;  // sets are kRedSetBytes-aligned pairs
+    }
+    if (csize > 1) {
+      const uint32_t par = cl_phase & 1u;
+      const uint32_t set = par * kClsSetBytes;
+      if (gtid == 0) mbar_arrive_expect_tx(clbar, csize * NV * 4);
+      if ((uint32_t)gtid < csize) {
+        const uint32_t r = (uint32_t)gtid;
+        const uint32_t rbar = map_to_cta(clbar, r);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          st_async_f32(map_to_cta(cls_addr + set + (crank * kRedNV + i) * 4, r), v[i], rbar);
+        }
+      }
+      mbar_wait(clbar, par);
+      const volatile float* slots = reinterpret_cast<const volatile float*>(smem_raw + cls_off + set);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) v[i] = Op::identity();
+      for (uint32_t r = 0; r < csize; ++r) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) v[i] = Op::apply(v[i], slots[r * kRedNV + i]);
+      }
+      cl_phase += 1u;
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------
+// The group's private ring of D stages. Tile k of group g is the CTA's local tile
+// g + k*G; it lives in stage k % D — tracked as a running (stage, phase) pair.
+// All per-tile bookkeeping is 32-bit counters and running pointers.
+// ---------------------------------------------------------------------------
+template <typename T, int TPR>
+struct Ring {
+  const RowParams& p;
+  const Group<TPR>& g;
+  uint32_t smem0;
+  // consumer cursor
+  uint32_t stage_off;  // smem_raw-relative byte offset of the current stage
+  uint32_t bar;        // shared-window address of the current stage's full barrier
+  uint32_t s;          // stage index in [0, D)
+  uint32_t phase;
+  uint32_t ring_off_g, bar_g;
+  int32_t k;           // current tile (group-local)
+  int32_t ntiles_g;    // tiles this group walks
+  int32_t last_nrows;  // rows of the group's last tile (tile_rows unless it is the ragged global tail)
+  int64_t row0;        // first row of the current tile
+  int64_t row_step;    // rows between consecutive tiles of this group
+  // producer side
+  const uint8_t* base0;
+  const uint8_t* base1;
+
+  __device__ __forceinline__ Ring(const RowParams& p_, uint32_t smem0_, const Group<TPR>& g_)
+      : p(p_), g(g_), smem0(smem0_) {
+    const int64_t ntiles = ceil_div64(p.rows, p.tile_rows);
+    const int64_t nclusters = gridDim.x / g.csize;
+    const int64_t t0 = (int64_t)(blockIdx.x / g.csize) + (int64_t)g.gid * nclusters;
+    const int64_t tstep = (int64_t)p.groups * nclusters;
+    const int64_t n_g = t0 < ntiles ? (ntiles - t0 + tstep - 1) / tstep : 0;
+    ntiles_g = (int32_t)n_g;
+    last_nrows = p.tile_rows;
+    if (n_g > 0 && t0 + (n_g - 1) * tstep == ntiles - 1) {
+      last_nrows = (int32_t)(p.rows - (ntiles - 1) * p.tile_rows);
+    }
+    row0 = t0 * p.tile_rows;
+    row_step = tstep * p.tile_rows;
+    k = 0;
+    s = 0;
+    phase = 0;
+    ring_off_g = p.off_ring + (uint32_t)(g.gid * p.depth) * p.stage_bytes;
+    bar_g = smem0 + 8u * (uint32_t)(g.gid * p.depth);
+    stage_off = ring_off_g;
+    bar = bar_g;
+    const size_t col0_bytes = (size_t)g.crank * p.slice_bytes;
+    base0 = static_cast<const uint8_t*>(p.in0) + col0_bytes;
+    base1 = static_cast<const uint8_t*>(p.in1) + col0_bytes;
+  }
+
+  __device__ __forceinline__ int nrows_of(int32_t kk) const { return kk == ntiles_g - 1 ? last_nrows : p.tile_rows; }
+  __device__ __forceinline__ int nrows() const { return nrows_of(k); }
+
+  // Issue the bulk copies of tile kk (first row r0) into stage (off, b).
+  // Executed by the group's first warp (all 32 lanes, converged).
+  __device__ __forceinline__ void issue(int32_t kk, int64_t r0, uint32_t off, uint32_t b) const {
+    const int nr = nrows_of(kk);
+    const uint32_t bytes = (uint32_t)nr * p.slice_bytes;
+    const uint32_t dst = smem0 + off;
+    const uint64_t policy = l2_policy_evict_first();
+    // No proxy fence is needed for this write-after-read: every reader consumed its loads
+    // (the values fed the reduction) before the group barrier that precedes refill().
+    if (p.contiguous) {
+      if (g.lane == 0) {
+        mbar_arrive_expect_tx(b, bytes * (uint32_t)p.nstreams);
+        bulk_g2s(dst, base0 + (size_t)r0 * p.in0_stride * sizeof(T), bytes, b, policy);
+        if (p.nstreams > 1) {
+          bulk_g2s(dst + p.stream_bytes, base1 + (size_t)r0 * p.in1_stride * sizeof(T), bytes, b, policy);
+        }
+      }
+    } else {
+      if (g.lane == 0) mbar_arrive_expect_tx(b, bytes * (uint32_t)p.nstreams);
+      __syncwarp();
+      for (int r = g.lane; r < nr; r += 32) {
+        bulk_g2s(dst + (uint32_t)r * p.slice_bytes, base0 + (size_t)(r0 + r) * p.in0_stride * sizeof(T),
+                 p.slice_bytes, b, policy);
+        if (p.nstreams > 1) {
+          bulk_g2s(dst + p.stream_bytes + (uint32_t)r * p.slice_bytes,
+                   base1 + (size_t)(r0 + r) * p.in1_stride * sizeof(T), p.slice_bytes, b, policy);
+        }
+      }
+    }
+  }
+
+  // Fill the ring before the first tile.
+  __device__ __forceinline__ void prologue() const {
+    if (g.warp == 0) {
+      int64_t r0 = row0;
+      for (int i = 0; i < p.depth && i < ntiles_g; ++i) {
+        issue(i, r0, ring_off_g + (uint32_t)i * p.stage_bytes, bar_g + 8u * (uint32_t)i);
+        r0 += row_step;
+      }
+    }
+  }
+
+  // Refill the current stage with tile k+D. PRECONDITION: every thread of the group has
+  // finished reading the stage and a group-wide barrier (Group::allreduce or Group::sync)
+  // separates those reads from this call.
+  __device__ __forceinline__ void refill() const {
+    if (g.warp == 0 && k + p.depth < ntiles_g) issue(k + p.depth, row0 + (int64_t)p.depth * row_step, stage_off, bar);
+  }
+
+  __device__ __forceinline__ bool more() const { return k < ntiles_g; }
+  __device__ __forceinline__ void wait() const { mbar_wait(bar, phase); }
+  __device__ __forceinline__ void advance() {
+    ++k;
+    row0 += row_step;
+    ++s;
+    stage_off += p.stage_bytes;
+    bar += 8u;
+    if (s == (uint32_t)p.depth) {
+      s = 0;
+      phase ^= 1u;
+      stage_off = ring_off_g;
+      bar = bar_g;
+    }
+  }
+};
+
+// Barrier setup shared by all ring kernels.
+__device__ __forceinline__ void ring_setup(const RowParams& p, uint32_t smem0) {
+  const int nbars = p.groups * p.depth + p.groups;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < nbars; ++s) mbar_init(smem0 + 8u * (uint32_t)s, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (cluster_nctarank() > 1) {
+    cluster_sync_all();  // peers' mbarriers are initialised before any st.async targets them
+  }
+}
+
+__device__ __forceinline__ void ring_teardown() {
+  if (cluster_nctarank() > 1) {
+    __syncwarp();
+    cluster_sync_all();  // nobody exits while a peer may still st.async into its smem
+  }
+}
+
+// Chunk ownership: thread gtid owns chunks c = gtid + j*TPR, j < CH (CH = ceil(nchunks/TPR),
+// so only the last j needs a bound check). CH == 0 selects the looping ("re-read") form
+// for slices wider than 4*TPR chunks.
+template <int TPR, int CH, typename F>
+__device__ __forceinline__ void for_each_chunk(int gtid, int nchunks, F&& f) {
+  if constexpr (CH > 0) {
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+      if (j < CH - 1 || gtid + j * TPR < nchunks) f(j, j * TPR);
+    }
+  } else {
+    for (int c = 0; gtid + c < nchunks; c += TPR) f(0, c);
+  }
+}
+
+__device__ __forceinline__ uint4 ld_smem_u4(const uint8_t* p) { return *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ void st_global_stream(void* p, const uint4& v) {
+  __stcs(reinterpret_cast<uint4*>(p), v);
+}
+
+// Packed per-column parameters (weight / bias) of the chunks a thread owns, kept in
+// registers for the CTA's lifetime. Absent parameters are replaced by the identity
+// (1.0 for a scale, -0.0 for a shift) so the hot loop has no branches.
+template <typename T>
+__device__ __forceinline__ uint4 splat_chunk(float v) {
+  if constexpr (sizeof(T) == 4) {
+    const uint32_t u = __float_as_uint(v);
+    return make_uint4(u, u, u, u);
+  } else {
+    const uint32_t u = IO<T>::pack2(v, v);
+    return make_uint4(u, u, u, u);
+  }
+}
+template <typename T, int TPR, int CH>
+__device__ __forceinline__ void load_params_to_regs(const void* gp, size_t col0_bytes, int gtid, int nchunks,
+                                                    float identity, uint4 (&q)[CH > 0 ? CH : 1]) {
+  if constexpr (CH > 0) {
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+      q[j] = splat_chunk<T>(identity);
+      if (gp != nullptr && gtid + j * TPR < nchunks) {
+        q[j] = ldg_128_nc(static_cast<const uint8_t*>(gp) + col0_bytes + 16u * (uint32_t)(gtid + j * TPR));
+      }
+    }
+  }
+}
+// Parameter chunk for the looping form: read through the read-only path each time.
+template <typename T>
+__device__ __forceinline__ uint4 load_param_chunk(const void* gp, size_t col0_bytes, int c, float identity) {
+  if (gp == nullptr) return splat_chunk<T>(identity);
+  return ldg_128_nc(static_cast<const uint8_t*>(gp) + col0_bytes + 16u * (uint32_t)c);
+}
+
+template <typename T>
+__device__ __forceinline__ uint8_t* out_row_ptr(const RowParams& p, int64_t row, uint32_t crank, int gtid) {
+  return static_cast<uint8_t*>(p.out0) + ((size_t)row * p.out_stride + (size_t)crank * p.cols_cta) * sizeof(T) +
+         16u * (uint32_t)gtid;
+}
+
+}  // namespace b200norm

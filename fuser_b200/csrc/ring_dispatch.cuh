@@ -1,0 +1,21 @@
+// ring_dispatch.cuh — lookup of ring-kernel instantiations. The instantiations live in
+// one translation unit per (dtype, direction) so the library builds in parallel
+// (inst_fwd_*.cu / inst_bwd_*.cu); this header is the only thing b200norm.cu sees.
+#pragma once
+
+#include "ring.cuh"
+
+namespace b200norm {
+
+using RingKernel = void (*)(const RowParams);
+
+// op: b200norm_op; tpr in {32,64,128,256,512}; ch in {1,2,3,4} or 0 (looping form, tpr 512 only).
+RingKernel ring_fwd_kernel_f32(int op, int tpr, int ch);
+RingKernel ring_fwd_kernel_bf16(int op, int tpr, int ch);
+RingKernel ring_fwd_kernel_f16(int op, int tpr, int ch);
+// norm backward: cached (g / xc in registers, ch in {1,2}) or re-read (ch in {3,4}, tpr 512... any tpr).
+RingKernel ring_bwd_kernel_f32(int op, int tpr, int ch, bool cached);
+RingKernel ring_bwd_kernel_bf16(int op, int tpr, int ch, bool cached);
+RingKernel ring_bwd_kernel_f16(int op, int tpr, int ch, bool cached);
+
+}  // namespace b200norm

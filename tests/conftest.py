@@ -18,4 +18,5 @@ def lib():
     from fuser_b200 import _build, _lib
 
     _build.build()
+    _build.build_host()
     return _lib.load()
