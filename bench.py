@@ -10,12 +10,18 @@ exploration (they are parity-test cases, not the headline bench line).
 
 Metric (same definition as the reference: benchmarks/python/core.py:194-202,
 csrc/fusion_profiler.cpp:786-791): algorithmic IO bytes (the reference's *_iobytes
-formulas) / time. `value` is device-timed with inputs resident in HBM; `e2e` runs the
-same step through the public API from pinned HOST buffers with the H2D / D2H copies
-inside the timed region. `roofline` is the dominant kernel (the backward) against the
-measured copy bandwidth in MEASURED_PEAKS.json. `cpu_baseline` is the ATen oracle on the
-host cores on a bounded row sample. `--impl reference` times the reference's own CPU
-evaluation path (ATen op-by-op, what testValidate runs) with all host threads.
+formulas) / time.
+  value     K steps of the device path (inputs resident in HBM), one CUDA-event pair around
+            the whole region, barrier + synchronize on both sides, max over ranks.
+  roofline  the dominant kernel (the backward) launched back to back K times on rotating
+            inputs, CUDA events on the launching stream -> average launch duration, against
+            the measured copy bandwidth in MEASURED_PEAKS.json.
+  e2e       the same step through the reference-facing API (FusionDefinition.execute) from
+            pinned HOST buffers: H2D of the step's inputs and D2H of its results inside the
+            timed region, double-buffered over three streams.
+  cpu_baseline  the ATen oracle on the host cores on a bounded row sample.
+`--impl reference` times the reference's own CPU evaluation path (ATen op-by-op, what
+testValidate runs) with all host threads.
 """
 from __future__ import annotations
 
@@ -23,7 +29,6 @@ import argparse
 import json
 import os
 import statistics
-import subprocess
 import sys
 import threading
 import time
@@ -43,6 +48,7 @@ WORKLOADS = {
     "c5": ("RMSNorm fwd+bwd bf16 [4096,65536]", 4096, 65536, torch.bfloat16, "rmsnorm_fwd_bwd"),
 }
 EPS = 1e-5
+L2_BYTES = 126 * 1024 * 1024
 
 
 def iobytes(kind: str, m: int, n: int, s: int) -> dict:
@@ -68,154 +74,239 @@ def measured_peak() -> tuple[float, str]:
 
 
 # ---------------------------------------------------------------------------
-# clocks sampling during the timed region
+# clocks sampling during the timed regions (NVML, ~2 ms period)
 # ---------------------------------------------------------------------------
 class ClockSampler:
-    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, index: int):
         self.index = index
-        self.samples: list[list[str]] = []
-        self.proc = None
+        self.sm: list[int] = []
+        self.max_sm = None
+        self.reasons: set[str] = set()
+        self._stop = threading.Event()
+        self._active = threading.Event()
         self.thread = None
+        self.note = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            # CUDA_VISIBLE_DEVICES may remap indices: resolve through the PCI bus id of the torch device
+            bus = torch.cuda.get_device_properties(index).pci_bus_id if hasattr(
+                torch.cuda.get_device_properties(index), "pci_bus_id") else None
+            self.h = None
+            if bus is not None:
+                for i in range(pynvml.nvmlDeviceGetCount()):
+                    h = pynvml.nvmlDeviceGetHandleByIndex(i)
+                    if pynvml.nvmlDeviceGetPciInfo(h).bus == bus:
+                        self.h = h
+                        break
+            if self.h is None:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # noqa: BLE001
+            self.nv = None
+            self.note = f"nvml unavailable: {e}"
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            if self._active.is_set():
+                try:
+                    self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                    for name, bit in self.REASONS.items():
+                        if r & bit:
+                            self.reasons.add(name)
+                except Exception:  # noqa: BLE001
+                    pass
+            time.sleep(0.002)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except Exception:
-            self.proc = None
+        if self.nv is None:
             return
-        def pump():
-            for line in self.proc.stdout:
-                parts = [p.strip() for p in line.split(",")]
-                if len(parts) >= 6:
-                    self.samples.append(parts)
-        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread = threading.Thread(target=self._run, daemon=True)
         self.thread.start()
 
+    def resume(self):
+        self._active.set()
+
+    def pause(self):
+        self._active.clear()
+
     def stop(self) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "nvidia-smi unavailable"}
-        time.sleep(0.06)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for p in self.samples:
-            try:
-                sm.append(float(p[0]))
-                mx.append(float(p[1]))
-            except ValueError:
-                continue
-            for name, v in zip(names, p[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self._stop.set()
+        if self.thread is not None:
+            self.thread.join(timeout=1)
+        out = {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.max_sm,
+               "reasons": sorted(self.reasons), "samples": len(self.sm)}
+        if self.note:
+            out["note"] = self.note
+        return out
 
 
 # ---------------------------------------------------------------------------
-# the hot-path step for each workload, on device tensors, through the public API
+# the hot-path step for each workload, on device tensors, through the public ops API
 # ---------------------------------------------------------------------------
 class Step:
-    def __init__(self, kind, m, n, dtype, device, world, nsets=2):
-        from fuser_b200 import ops
+    def __init__(self, kind, m, n, dtype, device, world, rank):
+        from fuser_b200 import ops, parallel
 
-        self.ops, self.kind, self.m, self.n, self.dtype, self.world = ops, kind, m, n, dtype, world
-        g = torch.Generator(device="cpu").manual_seed(1234 + (torch.distributed.get_rank() if world > 1 else 0))
-        self.host = []
+        self.ops, self.parallel = ops, parallel
+        self.kind, self.m, self.n, self.dtype, self.world, self.device = kind, m, n, dtype, world, device
+        es = torch.empty(0, dtype=dtype).element_size()
+        # rotating input sets so that consecutive steps never find their inputs in L2
+        self.nsets = max(2, int(2.5 * L2_BYTES // (2 * m * n * es)) + 1)
+        g = torch.Generator(device="cpu").manual_seed(1234 + rank)
         self.sets = []
-        for _ in range(nsets):  # rotating input sets: per-step footprint >> L2 (126 MB)
+        for _ in range(self.nsets):
             x = torch.randn(m, n, generator=g, dtype=torch.float32).to(dtype)
             dy = torch.randn(m, n, generator=g, dtype=torch.float32).to(dtype)
-            self.host.append((x.pin_memory(), dy.pin_memory()))
             self.sets.append((x.to(device), dy.to(device)))
-        self.w_host = torch.randn(n, generator=g).to(dtype).pin_memory()
-        self.w = self.w_host.to(device)
-        self.device = device
+        self.w = torch.randn(n, generator=g).to(dtype).to(device)
+        self.reducer = parallel.ColumnSumReducer(device=device) if world > 1 else None
         # saved statistics / forward outputs computed from the inputs (not random)
         self.saved = []
         for x, dy in self.sets:
             if kind == "layernorm_bwd":
                 _, mean, invstd = ops.layer_norm_fwd(x, None, None, EPS)
                 self.saved.append((mean, invstd))
+            elif kind == "rmsnorm_fwd_bwd":
+                self.saved.append(ops.rms_norm_fwd(x, self.w, EPS, stat_is_rms=True)[1])
+            elif kind == "softmax_fwd_bwd":
+                self.saved.append(ops.softmax_fwd(x))
             else:
                 self.saved.append(None)
         torch.cuda.synchronize(device)
 
-    def run(self, i, ev=None):
+    # -- the two halves, separately launchable (roofline loops) -----------------------------
+    def fwd(self, i):
         ops = self.ops
-        x, dy = self.sets[i % len(self.sets)]
-        out = None
-        if ev:
-            ev[0].record()
+        x, _ = self.sets[i % self.nsets]
         if self.kind == "rmsnorm_fwd_bwd":
-            y, rms = ops.rms_norm_fwd(x, self.w, EPS, stat_is_rms=True)
-            if ev:
-                ev[1].record()
-            if self.world > 1:
-                dx, sums = ops.rms_norm_bwd(dy, x, rms, self.w, stat_is_rms=True, centered=False, partials_f32=True)
-                torch.distributed.all_reduce(sums)
-                (dw,) = ops.finalize_partials(sums, self.dtype)
-            else:
-                dx, dw = ops.rms_norm_bwd(dy, x, rms, self.w, stat_is_rms=True, centered=False)
-            out = (y, rms, dx, dw)
-        elif self.kind == "softmax_fwd_bwd":
-            y = ops.softmax_fwd(x)
-            if ev:
-                ev[1].record()
-            dx = ops.softmax_bwd(dy, y)
-            out = (y, dx)
-        elif self.kind == "layernorm_bwd":
-            mean, invstd = self.saved[i % len(self.sets)]
-            if ev:
-                ev[1].record()
-            if self.world > 1:
-                dx, sums = ops.layer_norm_bwd(dy, x, mean, invstd, self.w, partials_f32=True)
-                torch.distributed.all_reduce(sums)
-                dw, db = ops.finalize_partials(sums, self.dtype)
-            else:
-                dx, dw, db = ops.layer_norm_bwd(dy, x, mean, invstd, self.w)
-            out = (dx, dw, db)
-        elif self.kind == "layernorm_fwd":
-            if ev:
-                ev[1].record()
-            out = ops.layer_norm_fwd(x, self.w, self.w, EPS)
-        if ev:
-            ev[2].record()
-        return out
+            return ops.rms_norm_fwd(x, self.w, EPS, stat_is_rms=True)
+        if self.kind == "softmax_fwd_bwd":
+            return (ops.softmax_fwd(x),)
+        if self.kind == "layernorm_fwd":
+            return ops.layer_norm_fwd(x, self.w, self.w, EPS)
+        return None
 
-    def run_e2e(self, i):
-        """Same step from pinned host buffers: H2D of the step's inputs, compute, D2H of the results."""
-        hx, hdy = self.host[i % len(self.host)]
-        dev = self.device
-        x = hx.to(dev, non_blocking=True)
-        dy = hdy.to(dev, non_blocking=True)
-        w = self.w_host.to(dev, non_blocking=True)
-        h2d = hx.nbytes + hdy.nbytes + self.w_host.nbytes
+    def bwd(self, i, fwd_out=None):
         ops = self.ops
+        x, dy = self.sets[i % self.nsets]
+        saved = self.saved[i % self.nsets]
         if self.kind == "rmsnorm_fwd_bwd":
-            y, rms = ops.rms_norm_fwd(x, w, EPS, stat_is_rms=True)
-            dx, dw = ops.rms_norm_bwd(dy, x, rms, w, stat_is_rms=True, centered=False)
-            outs = (y, rms, dx, dw)
-        elif self.kind == "softmax_fwd_bwd":
-            y = ops.softmax_fwd(x)
-            dx = ops.softmax_bwd(dy, y)
-            outs = (y, dx)
-        elif self.kind == "layernorm_bwd":
-            mean, invstd = self.saved[i % len(self.sets)]
-            outs = ops.layer_norm_bwd(dy, x, mean, invstd, w)
+            rms = fwd_out[1] if fwd_out is not None else saved
+            if self.world > 1:
+                return self.parallel.rms_norm_bwd_sharded(dy, x, rms, self.w, self.reducer, stat_is_rms=True)
+            return ops.rms_norm_bwd(dy, x, rms, self.w, stat_is_rms=True, centered=False)
+        if self.kind == "softmax_fwd_bwd":
+            return (ops.softmax_bwd(dy, fwd_out[0] if fwd_out is not None else saved),)
+        if self.kind == "layernorm_bwd":
+            mean, invstd = saved
+            if self.world > 1:
+                return self.parallel.layer_norm_bwd_sharded(dy, x, mean, invstd, self.w, self.reducer)
+            return ops.layer_norm_bwd(dy, x, mean, invstd, self.w)
+        return None
+
+    def run(self, i):
+        f = self.fwd(i)
+        b = self.bwd(i, f)
+        return f, b
+
+    def finish(self):
+        if self.reducer is not None:
+            self.reducer.wait()
+
+
+# ---------------------------------------------------------------------------
+# e2e: host buffers -> FusionDefinition.execute -> host buffers, three streams
+# ---------------------------------------------------------------------------
+class E2E:
+    def __init__(self, kind, m, n, dtype, device, rank):
+        from fuser_b200 import fusions as F
+        from fuser_b200.frontend import FusionDefinition, torch_dtype_to_nvfuser_dtype
+
+        self.kind, self.m, self.n, self.dtype, self.device = kind, m, n, dtype, device
+        nvdt = torch_dtype_to_nvfuser_dtype(dtype)
+
+        def define(fn, *a):
+            with FusionDefinition() as fd:
+                fn(fd, nvdt, *a)
+            return fd
+
+        g = torch.Generator(device="cpu").manual_seed(4321 + rank)
+        self.hx = torch.randn(m, n, generator=g).to(dtype).pin_memory()
+        self.hdy = torch.randn(m, n, generator=g).to(dtype).pin_memory()
+        self.hw = torch.randn(n, generator=g).to(dtype).pin_memory()
+        self.fd_fwd = self.fd_bwd = None
+        if kind == "rmsnorm_fwd_bwd":
+            self.fd_fwd, self.fd_bwd = define(F.rmsnorm_fwd_py, EPS), define(F.rmsnorm_bwd_py)
+        elif kind == "softmax_fwd_bwd":
+            self.fd_fwd, self.fd_bwd = define(F.softmax_fwd_py), define(F.softmax_bwd_py)
+        elif kind == "layernorm_bwd":
+            self.fd_fwd, self.fd_bwd = define(F.layernorm_fwd_py, EPS), define(F.layernorm_bwd_py)
         else:
-            outs = ops.layer_norm_fwd(x, w, w, EPS)
-        res = [o.to("cpu", non_blocking=False) for o in outs if o is not None]
-        d2h = sum(r.nbytes for r in res)
-        return h2d, d2h
+            self.fd_fwd = define(F.layernorm_fwd_py, EPS)
+        self.s_in, self.s_c, self.s_out = (torch.cuda.Stream(device=device) for _ in range(3))
+        # double-buffered device inputs and pinned host outputs
+        self.dbuf = [(torch.empty_like(self.hx, device=device), torch.empty_like(self.hdy, device=device),
+                      torch.empty_like(self.hw, device=device)) for _ in range(2)]
+        self.hout = [None, None]
+        self.ev_in = [torch.cuda.Event() for _ in range(2)]
+        self.ev_c = [torch.cuda.Event() for _ in range(2)]
+        self.ev_out = [torch.cuda.Event() for _ in range(2)]
+        self.h2d = self.d2h = 0
+        self.keep = [None, None]
+
+    def compute(self, x, dy, w):
+        k = self.kind
+        if k == "rmsnorm_fwd_bwd":
+            y, rms = self.fd_fwd.execute([x, w])
+            dx, dw = self.fd_bwd.execute([x, rms, dy, w])
+            return [y, rms, dx, dw]
+        if k == "softmax_fwd_bwd":
+            (y,) = self.fd_fwd.execute([x])
+            (dx,) = self.fd_bwd.execute([y, dy])
+            return [y, dx]
+        if k == "layernorm_bwd":
+            # the config is the backward; the saved statistics come from the forward definition
+            y, mean, invstd = self.fd_fwd.execute([x, w, w])
+            dx, dw, db = self.fd_bwd.execute([x, dy, mean, invstd, w])
+            return [dx, dw, db]
+        return list(self.fd_fwd.execute([x, w, w]))
+
+    def step(self, i):
+        b = i % 2
+        dx_, ddy_, dw_ = self.dbuf[b]
+        with torch.cuda.stream(self.s_in):
+            self.s_in.wait_event(self.ev_c[b])  # the compute that last read this buffer is done
+            dx_.copy_(self.hx, non_blocking=True)
+            ddy_.copy_(self.hdy, non_blocking=True)
+            dw_.copy_(self.hw, non_blocking=True)
+            self.ev_in[b].record(self.s_in)
+        with torch.cuda.stream(self.s_c):
+            self.s_c.wait_event(self.ev_in[b])
+            outs = self.compute(dx_, ddy_, dw_)
+            self.ev_c[b].record(self.s_c)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(self.ev_c[b])
+            self.ev_out[b].synchronize()  # the host buffers of step i-2 have landed
+            if self.hout[b] is None:
+                self.hout[b] = [torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in outs]
+            for h, o in zip(self.hout[b], outs):
+                o.record_stream(self.s_out)
+                h.copy_(o, non_blocking=True)
+            self.ev_out[b].record(self.s_out)
+        self.keep[b] = outs
+        self.h2d = self.hx.nbytes + self.hdy.nbytes + self.hw.nbytes
+        self.d2h = sum(o.nbytes for o in outs)
+
+    def sync(self):
+        for s in (self.s_in, self.s_c, self.s_out):
+            s.synchronize()
 
 
 # ---------------------------------------------------------------------------
@@ -261,8 +352,8 @@ def time_cpu(kind, m, n, dtype, sample_rows, reps, warm=1):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=500)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200norm", choices=["b200norm", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-e2e", action="store_true")
@@ -283,9 +374,10 @@ def main():
         if rank != 0:
             return
         sample_rows = max(64, min(M, (1 << 27) // (N * es)))  # ~128 MB per streamed tensor
-        reps = max(1, args.steps)
-        gbs, sec, cores = time_cpu(kind, M, N, dtype, sample_rows, reps, warm=max(1, args.warmup))
-        sample = f"{sample_rows} of {M} rows x {N} cols {dtype_name}, median of {reps} steps, ATen op-by-op (testValidate path)"
+        reps = max(1, min(args.steps, 20))
+        gbs, sec, cores = time_cpu(kind, M, N, dtype, sample_rows, reps, warm=max(1, min(args.warmup, 3)))
+        sample = (f"{sample_rows} of {M} rows x {N} cols {dtype_name}, median of {reps} steps, ATen op-by-op "
+                  f"(testValidate path), all host threads")
         line = {
             "impl": "reference", "metric": metric, "value": gbs, "unit": "GB/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3 * (M / sample_rows),
@@ -311,75 +403,112 @@ def main():
     rows = M
     scaling = "weak"
     if args.workload == "c4" and world > 1:
-        rows = M // world  # the named multi-GPU config: row-sharded, total work fixed
+        from fuser_b200.parallel import shard_rows
+
+        a, b = shard_rows(M, world, rank)  # the named multi-GPU config: row-sharded, total work fixed
+        rows = b - a
         scaling = "strong"
-    step = Step(kind, rows, N, dtype, device, world)
+    step = Step(kind, rows, N, dtype, device, world, rank)
     byt = iobytes(kind, rows, N, es)
     step_bytes = sum(byt.values())
+    total_bytes = step_bytes * world if scaling == "weak" else sum(iobytes(kind, M, N, es).values())
 
     def barrier():
         if world > 1:
             torch.distributed.barrier()
         torch.cuda.synchronize(device)
 
-    for i in range(args.warmup):
-        step.run(i)
-    barrier()
-
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
-    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-        time.sleep(0.1)
+
+    for i in range(args.warmup):
+        step.run(i)
+    step.finish()
+    barrier()
+
+    # ---- timed region: K steps, one event pair ----
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = L.launch_count()
     barrier()
+    sampler.resume()
+    h0 = time.perf_counter()
     t_start.record()
     for i in range(args.steps):
-        step.run(i, evs[i])
+        step.run(i)
+    step.finish()
     t_end.record()
+    host_enqueue_s = time.perf_counter() - h0
     barrier()
+    sampler.pause()
     launches = L.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else {}
     total_ms = t_start.elapsed_time(t_end)
     tms = torch.tensor([total_ms], device=device)
     if world > 1:
         torch.distributed.all_reduce(tms, op=torch.distributed.ReduceOp.MAX)
     total_ms = float(tms.item())
     ms_per_step = total_ms / args.steps
-    value = step_bytes * world / (ms_per_step * 1e-3) / 1e9
+    value = total_bytes / (ms_per_step * 1e-3) / 1e9
 
-    fwd_ms = statistics.mean(e[0].elapsed_time(e[1]) for e in evs)
-    bwd_ms = statistics.mean(e[1].elapsed_time(e[2]) for e in evs)
+    # ---- roofline: each kernel back to back on rotating inputs, events on the launching stream ----
+    def kernel_loop(fn, n):
+        for i in range(3):
+            fn(i)
+        step.finish()
+        torch.cuda.synchronize(device)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler.resume()
+        a.record()
+        for i in range(n):
+            fn(i)
+        b.record()
+        step.finish()
+        torch.cuda.synchronize(device)
+        sampler.pause()
+        return a.elapsed_time(b) / n
+
+    nk = max(20, min(args.steps, 200))
+    per_kernel = {}
+    if "fwd" in byt:
+        ms = kernel_loop(step.fwd, nk)
+        per_kernel["fwd"] = {"bytes": byt["fwd"], "ms": ms, "gbs": byt["fwd"] / (ms * 1e-3) / 1e9}
+    if "bwd" in byt:
+        ms = kernel_loop(lambda i: step.bwd(i), nk)
+        per_kernel["bwd"] = {"bytes": byt["bwd"], "ms": ms, "gbs": byt["bwd"] / (ms * 1e-3) / 1e9}
     peak, peak_src = measured_peak()
     dom = "bwd" if "bwd" in byt else "fwd"
-    dom_ms = bwd_ms if dom == "bwd" else fwd_ms + bwd_ms
-    achieved = byt[dom] / (dom_ms * 1e-3) / 1e9
+    achieved = per_kernel[dom]["gbs"]
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": f"{kind}:{dom}", "peak_source": peak_src,
-                "per_kernel": {k: {"bytes": byt[k], "ms": (fwd_ms if k == "fwd" else bwd_ms),
-                                   "gbs": byt[k] / ((fwd_ms if k == "fwd" else bwd_ms) * 1e-3) / 1e9} for k in byt
-                               if (fwd_ms if k == "fwd" else bwd_ms) > 0}}
+                "traffic": None, "kernel": f"{kind}:{dom}", "peak_source": peak_src, "launches_timed": nk,
+                "per_kernel": per_kernel,
+                "step_frac_of_peak": (step_bytes / (ms_per_step * 1e-3) / 1e9) / peak}
 
-    # ---------------- e2e: host buffers, copies inside the timed region ----------------
+    # ---- e2e: host buffers, copies inside the timed region ----
     e2e = None
     if not args.no_e2e:
-        n_e2e = max(2, min(args.steps, 5))
-        step.run_e2e(0)
+        e = E2E(kind, rows, N, dtype, device, rank)
+        n_e2e = max(4, min(args.steps, 20))
+        for i in range(2):
+            e.step(i)
+        e.sync()
         barrier()
         t0 = time.perf_counter()
         for i in range(n_e2e):
-            h2d, d2h = step.run_e2e(i)
-        torch.cuda.synchronize(device)
+            e.step(i)
+        e.sync()
         sec = (time.perf_counter() - t0) / n_e2e
         te = torch.tensor([sec], device=device)
         if world > 1:
             torch.distributed.all_reduce(te, op=torch.distributed.ReduceOp.MAX)
         sec = float(te.item())
-        e2e = {"value": step_bytes * world / sec / 1e9, "unit": "GB/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "ms_per_step": sec * 1e3, "steps": n_e2e}
+        e2e = {"value": total_bytes / sec / 1e9, "unit": "GB/s", "h2d_bytes_per_step": e.h2d,
+               "d2h_bytes_per_step": e.d2h, "ms_per_step": sec * 1e3, "steps": n_e2e,
+               "api": "FusionDefinition.execute (fwd + bwd definitions of benchmarks/python), pinned host buffers, "
+                      "H2D / compute / D2H double-buffered on three streams"}
+        del e
+    clocks = sampler.stop() if rank == 0 else {}
 
-    # ---------------- CPU baseline (rank 0, N=1 only) ----------------
+    # ---- CPU baseline (rank 0, N=1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         sample_rows = max(64, min(rows, (1 << 26) // (N * es)))
@@ -388,16 +517,20 @@ def main():
                "sample": f"{sample_rows} of {rows} rows x {N} cols {dtype_name}, median of 5, ATen oracle op-by-op"}
 
     if rank == 0:
+        footprint = step.nsets * 2 * rows * N * es
         line = {
             "metric": metric, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "rows_per_gpu": rows, "cols": N, "io_dtype": dtype_name,
-                       "accumulate": "fp32", "l2": "inputs larger than L2 (2 rotating input sets, 640 MB/step footprint)",
-                       "collective": "nccl allreduce of fp32 dgamma partial sums" if world > 1 else "none",
-                       "rows_per_s": rows * world / (ms_per_step * 1e-3),
+                       "accumulate": "fp32",
+                       "l2": f"inputs larger than L2 ({step.nsets} rotating input sets, {footprint / 1e6:.0f} MB)",
+                       "collective": "nccl allreduce of fp32 dgamma/dbeta partial sums on a side stream"
+                       if world > 1 else "none",
+                       "rows_per_s": (rows * world if scaling == "weak" else M) / (ms_per_step * 1e-3),
                        "pct_of_nominal_8TBs": 100.0 * value / world / 8000.0,
-                       "pct_of_measured_peak": 100.0 * value / world / peak},
+                       "pct_of_measured_peak": 100.0 * value / world / peak,
+                       "host_enqueue_us_per_step": host_enqueue_s / args.steps * 1e6},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)

@@ -514,7 +514,7 @@ RingKernel generic_kernel_for(int op) {
 
 template <typename T>
 int launch_typed(const b200norm_desc& d, const Plan& plan, RowParams& rp, void* dw, void* db, float* sums_f32,
-                 cudaStream_t stream) {
+                 void* ws_header, cudaStream_t stream) {
   const bool want_cols = is_norm_bwd(d.op) && (d.flags & (B200NORM_F_OUT_DW | B200NORM_F_OUT_DB));
   const int K = partial_k(d.op);
   cudaError_t err;
@@ -559,29 +559,86 @@ int launch_typed(const b200norm_desc& d, const Plan& plan, RowParams& rp, void* 
     int rc = prepare_ring_kernel(k, (int)plan.smem, plan.cluster);
     if (rc != B200NORM_OK) return rc;
   }
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3((unsigned)plan.grid);
-  cfg.blockDim = dim3((unsigned)plan.block);
-  cfg.dynamicSmemBytes = plan.smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute attrs[1];
-  attrs[0].id = cudaLaunchAttributeClusterDimension;
-  attrs[0].val.clusterDim.x = (unsigned)plan.cluster;
-  attrs[0].val.clusterDim.y = 1;
-  attrs[0].val.clusterDim.z = 1;
-  cfg.attrs = attrs;
-  cfg.numAttrs = 1;
-  err = cudaLaunchKernelEx(&cfg, k, (const RowParams)rp);
-  if (err != cudaSuccess) return fail(B200NORM_ERR_CUDA + (int)err, "ring launch failed: %s", cudaGetErrorString(err));
-  g_launches++;
-  if (want_cols) {
-    launch_finalize<T>(rp.partials, plan.nparts, K, (int)d.cols, dw, db, sums_f32, stream);
-    err = cudaGetLastError();
-    if (err != cudaSuccess) return fail(B200NORM_ERR_CUDA + (int)err, "finalize launch failed: %s", cudaGetErrorString(err));
+  // Launch attributes: the cluster shape; programmatic dependent launch (the kernel's barrier
+  // setup overlaps its predecessor's tail — every ring kernel calls griddepcontrol.wait before
+  // its first global access); and, for a backward that produces dgamma / dbeta, a cooperative
+  // launch so the grid can finish the column sums itself (the reference's inner-outer kernels
+  // are cooperative for the same reason, executor.cpp:1307-1312). A combination the driver
+  // rejects is remembered per kernel and the launch falls back: no PDL, then no fused finish.
+  static std::mutex mode_mu;
+  static std::unordered_map<const void*, int> bad_modes;  // bit0: cooperative refused, bit1: PDL refused
+  int bad = 0;
+  {
+    std::lock_guard<std::mutex> lock(mode_mu);
+    auto it = bad_modes.find((const void*)k);
+    if (it != bad_modes.end()) bad = it->second;
   }
-  return B200NORM_OK;
+  const bool allow_fused = want_cols && plan.block >= 128 && env_int("B200NORM_NO_FUSED_FINISH") == 0;
+  const bool allow_pdl = env_int("B200NORM_NO_PDL") == 0;
+  for (;;) {
+    const bool fused = allow_fused && !(bad & 1);
+    const bool pdl = allow_pdl && !(bad & 2);
+    rp.fused_finish = fused ? 1 : 0;
+    rp.sync_words = reinterpret_cast<uint32_t*>(ws_header);
+    rp.dw_out = dw;
+    rp.db_out = db;
+    rp.sums_out = sums_f32;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)plan.grid);
+    cfg.blockDim = dim3((unsigned)plan.block);
+    cfg.dynamicSmemBytes = plan.smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attrs[3];
+    int na = 0;
+    attrs[na].id = cudaLaunchAttributeClusterDimension;
+    attrs[na].val.clusterDim.x = (unsigned)plan.cluster;
+    attrs[na].val.clusterDim.y = 1;
+    attrs[na].val.clusterDim.z = 1;
+    ++na;
+    if (fused) {
+      attrs[na].id = cudaLaunchAttributeCooperative;
+      attrs[na].val.cooperative = 1;
+      ++na;
+    }
+    if (pdl) {
+      attrs[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attrs[na].val.programmaticStreamSerializationAllowed = 1;
+      ++na;
+    }
+    cfg.attrs = attrs;
+    cfg.numAttrs = (unsigned)na;
+    err = cudaLaunchKernelEx(&cfg, k, (const RowParams)rp);
+    if (err == cudaSuccess) {
+      g_launches++;
+      if (env_int("B200NORM_DEBUG") > 1)
+        fprintf(stderr, "[b200norm] op %d launched grid %d block %d cluster %d fused=%d pdl=%d\n", d.op, plan.grid,
+                plan.block, plan.cluster, (int)fused, (int)pdl);
+      if (want_cols && !fused) {
+        launch_finalize<T>(rp.partials, plan.nparts, K, (int)d.cols, dw, db, sums_f32, stream);
+        err = cudaGetLastError();
+        if (err != cudaSuccess)
+          return fail(B200NORM_ERR_CUDA + (int)err, "finalize launch failed: %s", cudaGetErrorString(err));
+      }
+      return B200NORM_OK;
+    }
+    (void)cudaGetLastError();
+    if (env_int("B200NORM_DEBUG"))
+      fprintf(stderr, "[b200norm] launch with fused=%d pdl=%d refused: %s\n", (int)fused, (int)pdl,
+              cudaGetErrorString(err));
+    int newbad = bad;
+    if (pdl) {
+      newbad |= 2;
+    } else if (fused) {
+      newbad |= 1;
+    }
+    if (newbad == bad) return fail(B200NORM_ERR_CUDA + (int)err, "ring launch failed: %s", cudaGetErrorString(err));
+    bad = newbad;
+    std::lock_guard<std::mutex> lock(mode_mu);
+    bad_modes[(const void*)k] = bad;
+  }
 }
+
 
 // ---------------------------------------------------------------------------
 // argument checks
@@ -927,9 +984,9 @@ int b200norm_launch(const b200norm_desc* desc, const b200norm_tensor* inputs, in
   rp.off_acc = plan.off_ring;
 
   switch (dt) {
-    case B200NORM_DT_F32: return launch_typed<float>(d, plan, rp, dw, db, sums_f32, stream);
-    case B200NORM_DT_BF16: return launch_typed<__nv_bfloat16>(d, plan, rp, dw, db, sums_f32, stream);
-    case B200NORM_DT_F16: return launch_typed<__half>(d, plan, rp, dw, db, sums_f32, stream);
+    case B200NORM_DT_F32: return launch_typed<float>(d, plan, rp, dw, db, sums_f32, workspace, stream);
+    case B200NORM_DT_BF16: return launch_typed<__nv_bfloat16>(d, plan, rp, dw, db, sums_f32, workspace, stream);
+    case B200NORM_DT_F16: return launch_typed<__half>(d, plan, rp, dw, db, sums_f32, workspace, stream);
     default: return fail(B200NORM_ERR_UNSUPPORTED, "dtype %d", dt);
   }
 }

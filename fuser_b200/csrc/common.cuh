@@ -122,6 +122,29 @@ __device__ __forceinline__ void bulk_wait_read() {
 }
 
 // ----------------------------------------------------------------------------
+// programmatic dependent launch: a kernel launched with the programmatic-stream-
+// serialization attribute may start while its predecessor drains; it must not touch
+// global memory before pdl_wait() (which returns once the predecessor has completed and
+// flushed). Both are no-ops for a normal launch.
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// device-scope acquire load / release add for the in-kernel grid barrier
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t atom_add_release_gpu(uint32_t* p, uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.add.release.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+  return old;
+}
+
+// ----------------------------------------------------------------------------
 // named barriers (bar.sync id, nthreads) for sub-CTA consumer groups
 // ----------------------------------------------------------------------------
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {

@@ -22,6 +22,96 @@
 
 namespace b200norm {
 
+// Sense-reversing grid barrier on two workspace header words {count, generation}. Both are
+// zero before the first launch; count is back to zero when the barrier opens, generation
+// only ever increments, so no departure phase is needed. PRECONDITION: a cooperative launch
+// (all CTAs resident) and a __syncthreads() after the CTA's last global write + __threadfence().
+__device__ __forceinline__ void grid_barrier(uint32_t* words) {
+  if (threadIdx.x == 0) {
+    const uint32_t gen = ld_acquire_gpu(words + 1);  // read before arriving
+    const uint32_t old = atom_add_release_gpu(words, 1u);
+    if (old == gridDim.x - 1) {
+      words[0] = 0u;
+      __threadfence();
+      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(words + 1), "r"(gen + 1u) : "memory");
+    } else {
+      Watchdog wd;
+      while (ld_acquire_gpu(words + 1) == gen) wd.tick();
+    }
+  }
+  __syncthreads();
+}
+
+// After the grid barrier: out[k][n] = sum over the nparts partial rows, in row order.
+// The [K][N] result is cut into chunks of CW float4 columns; CTA b finishes chunks b,
+// b+grid, ... A thread owns one float4 column of the chunk and every RS-th partial row
+// (RS = threads / CW); all its loads are issued before the first add (one L2 round trip),
+// row-splits are combined by shuffles inside a warp and through shared memory across warps.
+template <typename T, int CW>
+__device__ __forceinline__ void finish_columns(const RowParams& p, int K, int F, int nct) {
+  constexpr int kMaxLoads = 10;
+  const int tx = threadIdx.x % CW;
+  const int ty = threadIdx.x / CW;
+  const int RS = nct / CW;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int nwarps = nct >> 5;
+  const int nparts = (int)(gridDim.x / cluster_nctarank());
+  const int fpr = p.cols / 4;  // float4 columns per result row
+  float4* sm = reinterpret_cast<float4*>(smem_raw + p.off_acc);  // [nwarps][CW]
+  const int nchunk = (F + CW - 1) / CW;
+  for (int chunk = blockIdx.x; chunk < nchunk; chunk += gridDim.x) {
+    const int f = chunk * CW + tx;
+    float4 v[kMaxLoads];
+    const bool col_ok = f < F;
+    const int kk = col_ok ? f / fpr : 0;
+    const int c4 = col_ok ? f - kk * fpr : 0;
+    const float4* src = reinterpret_cast<const float4*>(p.partials + (size_t)kk * p.cols) + c4;
+    const size_t pstride4 = (size_t)K * fpr;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int base = 0; base < nparts; base += RS * kMaxLoads) {
+#pragma unroll
+      for (int i = 0; i < kMaxLoads; ++i) {
+        const int pi = base + ty + i * RS;
+        v[i] = (col_ok && pi < nparts) ? __ldcg(src + (size_t)pi * pstride4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int i = 0; i < kMaxLoads; ++i) {
+        a.x += v[i].x;
+        a.y += v[i].y;
+        a.z += v[i].z;
+        a.w += v[i].w;
+      }
+    }
+    // lanes tx, tx+CW, tx+2CW, ... of a warp hold different row-splits of the same column
+#pragma unroll
+    for (int off = CW; off < 32; off <<= 1) {
+      a.x += __shfl_xor_sync(0xffffffffu, a.x, off);
+      a.y += __shfl_xor_sync(0xffffffffu, a.y, off);
+      a.z += __shfl_xor_sync(0xffffffffu, a.z, off);
+      a.w += __shfl_xor_sync(0xffffffffu, a.w, off);
+    }
+    __syncthreads();  // the previous chunk's readers are done with sm
+    if (lane < CW) sm[warp * CW + lane] = a;
+    __syncthreads();
+    if (threadIdx.x < CW * 4) {
+      const float* smf = reinterpret_cast<const float*>(sm);
+      const int e = chunk * CW * 4 + threadIdx.x;  // element index in the flattened [K][N] result
+      if (e < K * p.cols) {
+        float r = 0.f;
+        for (int w = 0; w < nwarps; ++w) r += smf[w * CW * 4 + threadIdx.x];
+        if (p.sums_out != nullptr) {
+          p.sums_out[e] = r;
+        } else {
+          const int k2 = e / p.cols;
+          T* o = static_cast<T*>(k2 == 0 ? p.dw_out : p.db_out);
+          if (o != nullptr) o[e - k2 * p.cols] = IO<T>::from_f32(r);
+        }
+      }
+    }
+  }
+}
+
 // LN: true = LayerNorm (mean input, dbeta), false = RMSNorm.
 // Each thread owns chunks c = gtid + j*TPR, j < CH, of the CTA's column slice
 // (the planner guarantees nchunks <= TPR*CH).
@@ -178,6 +268,20 @@ __global__ void __launch_bounds__(kMaxBlock, 1) norm_bwd_ring_kernel(const RowPa
     for (int col = threadIdx.x * 4; col < p.cols_cta; col += nct * 4) {
       *reinterpret_cast<float4*>(dst + col) = *reinterpret_cast<const float4*>(acc_w + col);
       if constexpr (LN) *reinterpret_cast<float4*>(dst + p.cols + col) = *reinterpret_cast<const float4*>(acc_b + col);
+    }
+    if (p.fused_finish) {
+      // The launch is cooperative (every CTA is resident): one grid barrier, then every CTA
+      // finishes a share of the columns in a fixed order — deterministic, like the reference's
+      // grid reduction (runtime/grid_reduction.cu:201-309 + grid_sync.cu:34-95).
+      __threadfence();
+      __syncthreads();
+      grid_barrier(p.sync_words);
+      const int F = K * (p.cols / 4);  // float4 columns of the [K][N] result
+      if ((F + 7) / 8 <= 2 * (int)gridDim.x) {
+        finish_columns<T, 8>(p, K, F, nct);
+      } else {
+        finish_columns<T, 32>(p, K, F, nct);
+      }
     }
   }
   ring_teardown();

@@ -84,6 +84,12 @@ struct RowParams {
   uint32_t off_cls;   // float [groups][2][kMaxCluster][kRedNV]
   uint32_t off_ring;  // groups*depth stages, group-major: stage (g*depth + s)
   uint32_t off_acc;   // bwd: cross-group accumulator staging (aliases the ring)
+  // backward: in-kernel finish of the column sums (cooperative launch; see kernels_bwd.cuh)
+  int32_t fused_finish;    // 1: the grid is co-resident and finishes dgamma / dbeta itself
+  uint32_t* sync_words;    // two zero-initialised workspace header words, returned to zero
+  void* dw_out;            // io dtype [N] or nullptr
+  void* db_out;            // io dtype [N] or nullptr
+  float* sums_out;         // fp32 [K][N] or nullptr (multi-GPU partial sums, no cast)
 };
 
 // barrier block at the start of dynamic smem:  full[groups*depth] | clbar[groups]
@@ -321,6 +327,11 @@ __device__ __forceinline__ void ring_setup(const RowParams& p, uint32_t smem0) {
   if (cluster_nctarank() > 1) {
     cluster_sync_all();  // peers' mbarriers are initialised before any st.async targets them
   }
+  // Everything above touched only this CTA's shared memory: under a programmatic dependent
+  // launch it overlaps the previous kernel's tail. Let our own successor do the same, then
+  // wait for the predecessor's memory before the first global access.
+  pdl_launch_dependents();
+  pdl_wait();
 }
 
 __device__ __forceinline__ void ring_teardown() {

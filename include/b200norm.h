@@ -23,9 +23,12 @@
  *     synchronises; kernels are enqueued on the stream handed in.
  *   - the workspace must be at least b200norm_workspace_bytes(desc) bytes,
  *     256-byte aligned, and its first B200NORM_WS_HEADER_BYTES bytes must be
- *     ZERO before the first launch that uses it. The library returns the header
- *     to zero at the end of every launch, so one zero-fill at allocation time
- *     is enough (this mirrors nvFuser's zeroed semaphore pool).
+ *     ZERO before the first launch that uses it. After that the header belongs
+ *     to the library (an arrival counter that is back to zero at the end of
+ *     every launch and a barrier generation that only increments), so one
+ *     zero-fill at allocation time is enough (this mirrors nvFuser's zeroed
+ *     semaphore pool). A workspace must not be shared by launches that can run
+ *     concurrently (use one per stream).
  *   - there is NO CPU fallback: on a machine without an sm_100 device the
  *     launch entry points fail with B200NORM_ERR_NO_DEVICE.
  */

@@ -1,0 +1,94 @@
+#!/usr/bin/env python
+"""Time single ops at arbitrary shapes (back-to-back launches, rotating inputs > L2, CUDA events).
+
+    python scripts/kbench.py "ln_bwd:32768x12288:bf16[:ENV=V,ENV=V]" ...
+ops: rms_fwd ln_fwd sm_fwd sm_bwd rms_bwd rms_bwd_dx ln_bwd ln_bwd_dx
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+from bench import measured_peak  # noqa: E402
+from fuser_b200 import ops  # noqa: E402
+
+KEYS = ["B200NORM_TPR", "B200NORM_GROUPS", "B200NORM_DEPTH", "B200NORM_TILE_ROWS", "B200NORM_CLUSTER",
+        "B200NORM_BWD_REREAD", "B200NORM_PAIR"]
+DT = {"bf16": torch.bfloat16, "f32": torch.float32, "f16": torch.float16}
+
+
+def algbytes(op, m, n, s):
+    return {"rms_fwd": s * (2 * m * n + n) + 4 * m, "ln_fwd": s * 2 * (m * n + n) + 8 * m, "sm_fwd": s * 2 * m * n,
+            "sm_bwd": s * 3 * m * n, "rms_bwd": s * (3 * m * n + 2 * n) + 4 * m, "rms_bwd_dx": s * (3 * m * n + 2 * n) + 4 * m,
+            "ln_bwd": s * 3 * (m * n + n) + 8 * m, "ln_bwd_dx": s * 3 * (m * n + n) + 8 * m}[op]
+
+
+def main():
+    peak, _ = measured_peak()
+    dev = torch.device("cuda", 0)
+    cache = {}
+    for spec in sys.argv[1:]:
+        parts = spec.split(":")
+        op, shape, dt = parts[0], parts[1], parts[2]
+        cfg = parts[3] if len(parts) > 3 else ""
+        m, n = (int(v) for v in shape.split("x"))
+        dtype = DT[dt]
+        es = torch.empty(0, dtype=dtype).element_size()
+        for k in KEYS:
+            os.environ.pop(k, None)
+        for kv in filter(None, cfg.split(",")):
+            k, v = kv.split("=")
+            os.environ[k] = v
+        key = (m, n, dt)
+        if key not in cache:
+            cache.clear()
+            torch.cuda.empty_cache()
+            nsets = max(2, int(300e6 // (m * n * es)) + 1)
+            g = torch.Generator(device="cpu").manual_seed(1)
+            xs = [torch.randn(m, n, generator=g).to(dtype).to(dev) for _ in range(nsets)]
+            dys = [torch.randn(m, n, generator=g).to(dtype).to(dev) for _ in range(nsets)]
+            w = torch.randn(n, generator=g).to(dtype).to(dev)
+            cache[key] = (nsets, xs, dys, w, {})
+        nsets, xs, dys, w, aux = cache[key]
+        try:
+            if op in ("rms_bwd", "rms_bwd_dx") and "rms" not in aux:
+                aux["rms"] = [ops.rms_norm_fwd(x, w, 1e-5)[1] for x in xs]
+            if op in ("ln_bwd", "ln_bwd_dx") and "ln" not in aux:
+                aux["ln"] = [ops.layer_norm_fwd(x, None, None, 1e-5)[1:] for x in xs]
+            if op == "sm_bwd" and "sm" not in aux:
+                aux["sm"] = [ops.softmax_fwd(x) for x in xs]
+            fns = {
+                "rms_fwd": lambda i: ops.rms_norm_fwd(xs[i], w, 1e-5),
+                "ln_fwd": lambda i: ops.layer_norm_fwd(xs[i], w, w, 1e-5),
+                "sm_fwd": lambda i: ops.softmax_fwd(xs[i]),
+                "sm_bwd": lambda i: ops.softmax_bwd(dys[i], aux["sm"][i]),
+                "rms_bwd": lambda i: ops.rms_norm_bwd(dys[i], xs[i], aux["rms"][i], w),
+                "rms_bwd_dx": lambda i: ops.rms_norm_bwd(dys[i], xs[i], aux["rms"][i], w, (True, False)),
+                "ln_bwd": lambda i: ops.layer_norm_bwd(dys[i], xs[i], aux["ln"][i][0], aux["ln"][i][1], w),
+                "ln_bwd_dx": lambda i: ops.layer_norm_bwd(dys[i], xs[i], aux["ln"][i][0], aux["ln"][i][1], w,
+                                                          (True, False, False)),
+            }
+            fn = fns[op]
+            for i in range(3):
+                fn(i % nsets)
+            torch.cuda.synchronize()
+            iters = max(10, min(200, int(3e9 // algbytes(op, m, n, es))))
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for i in range(iters):
+                fn(i % nsets)
+            b.record()
+            torch.cuda.synchronize()
+            t = a.elapsed_time(b) / iters * 1e3
+            gbs = algbytes(op, m, n, es) / t / 1e3
+            print(f"{op:10s} {shape:12s} {dt:4s} {cfg or 'default':44s} {t:8.1f}us {gbs:6.0f}GB/s {100 * gbs / peak:5.1f}%",
+                  flush=True)
+        except Exception as e:  # noqa: BLE001
+            print(f"{op:10s} {shape:12s} {dt:4s} {cfg or 'default':44s} FAILED {e}", flush=True)
+            torch.cuda.synchronize()
+
+
+if __name__ == "__main__":
+    main()
