@@ -200,14 +200,18 @@ class Step:
         if self.kind == "rmsnorm_fwd_bwd":
             rms = fwd_out[1] if fwd_out is not None else saved
             if self.world > 1:
-                return self.parallel.rms_norm_bwd_sharded(dy, x, rms, self.w, self.reducer, stat_is_rms=True)
+                prev = self.reducer.pending  # last step's dgamma: its all-reduce had a whole step to finish
+                dx, _ = self.parallel.rms_norm_bwd_sharded(dy, x, rms, self.w, self.reducer, stat_is_rms=True)
+                return dx, (prev.result() if prev is not None else None)
             return ops.rms_norm_bwd(dy, x, rms, self.w, stat_is_rms=True, centered=False)
         if self.kind == "softmax_fwd_bwd":
             return (ops.softmax_bwd(dy, fwd_out[0] if fwd_out is not None else saved),)
         if self.kind == "layernorm_bwd":
             mean, invstd = saved
             if self.world > 1:
-                return self.parallel.layer_norm_bwd_sharded(dy, x, mean, invstd, self.w, self.reducer)
+                prev = self.reducer.pending
+                dx, _ = self.parallel.layer_norm_bwd_sharded(dy, x, mean, invstd, self.w, self.reducer)
+                return dx, (prev.result() if prev is not None else None)
             return ops.layer_norm_bwd(dy, x, mean, invstd, self.w)
         return None
 
@@ -525,7 +529,7 @@ def main():
             "config": {"workload": desc, "rows_per_gpu": rows, "cols": N, "io_dtype": dtype_name,
                        "accumulate": "fp32",
                        "l2": f"inputs larger than L2 ({step.nsets} rotating input sets, {footprint / 1e6:.0f} MB)",
-                       "collective": "nccl allreduce of fp32 dgamma/dbeta partial sums on a side stream"
+                       "collective": "nccl allreduce of fp32 dgamma/dbeta partial sums, async (consumed one step later), cast after the reduce"
                        if world > 1 else "none",
                        "rows_per_s": (rows * world if scaling == "weak" else M) / (ms_per_step * 1e-3),
                        "pct_of_nominal_8TBs": 100.0 * value / world / 8000.0,

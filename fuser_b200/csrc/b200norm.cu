@@ -119,11 +119,12 @@ struct Plan {
   int ch = 0;
   int nchunks = 0;
   bool cached = false;
+  bool psmem = false;      // LayerNorm fwd: weight / bias staged in shared memory as fp32
   int nparts = 0;          // partial rows produced by the main kernel
   int rows_per_split = 0;  // generic colsum
   int n_launches = 1;
   uint32_t slice_bytes = 0, stream_bytes = 0, stage_bytes = 0;
-  uint32_t off_red = 0, off_cls = 0, off_ring = 0;
+  uint32_t off_red = 0, off_cls = 0, off_param = 0, off_ring = 0;
   uint32_t smem = 0;
   uint64_t ws_bytes = 0;
 };
@@ -134,18 +135,18 @@ uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 // kernel tables
 // ---------------------------------------------------------------------------
 template <typename T>
-RingKernel ring_kernel_for(int op, int tpr, int ch, bool cached);
+RingKernel ring_kernel_for(int op, int tpr, int ch, bool cached, bool psmem);
 template <>
-RingKernel ring_kernel_for<float>(int op, int tpr, int ch, bool cached) {
-  return is_norm_bwd(op) ? ring_bwd_kernel_f32(op, tpr, ch, cached) : ring_fwd_kernel_f32(op, tpr, ch);
+RingKernel ring_kernel_for<float>(int op, int tpr, int ch, bool cached, bool psmem) {
+  return is_norm_bwd(op) ? ring_bwd_kernel_f32(op, tpr, ch, cached) : ring_fwd_kernel_f32(op, tpr, ch, psmem);
 }
 template <>
-RingKernel ring_kernel_for<__nv_bfloat16>(int op, int tpr, int ch, bool cached) {
-  return is_norm_bwd(op) ? ring_bwd_kernel_bf16(op, tpr, ch, cached) : ring_fwd_kernel_bf16(op, tpr, ch);
+RingKernel ring_kernel_for<__nv_bfloat16>(int op, int tpr, int ch, bool cached, bool psmem) {
+  return is_norm_bwd(op) ? ring_bwd_kernel_bf16(op, tpr, ch, cached) : ring_fwd_kernel_bf16(op, tpr, ch, psmem);
 }
 template <>
-RingKernel ring_kernel_for<__half>(int op, int tpr, int ch, bool cached) {
-  return is_norm_bwd(op) ? ring_bwd_kernel_f16(op, tpr, ch, cached) : ring_fwd_kernel_f16(op, tpr, ch);
+RingKernel ring_kernel_for<__half>(int op, int tpr, int ch, bool cached, bool psmem) {
+  return is_norm_bwd(op) ? ring_bwd_kernel_f16(op, tpr, ch, cached) : ring_fwd_kernel_f16(op, tpr, ch, psmem);
 }
 
 // cudaFuncSetAttribute is paid once per (kernel, smem size, cluster class), not per launch.
@@ -167,11 +168,11 @@ int prepare_ring_kernel(RingKernel k, int smem, int cluster) {
   return B200NORM_OK;
 }
 
-RingKernel ring_kernel_any(int dt, int op, int tpr, int ch, bool cached) {
+RingKernel ring_kernel_any(int dt, int op, int tpr, int ch, bool cached, bool psmem) {
   switch (dt) {
-    case B200NORM_DT_F32: return ring_kernel_for<float>(op, tpr, ch, cached);
-    case B200NORM_DT_BF16: return ring_kernel_for<__nv_bfloat16>(op, tpr, ch, cached);
-    case B200NORM_DT_F16: return ring_kernel_for<__half>(op, tpr, ch, cached);
+    case B200NORM_DT_F32: return ring_kernel_for<float>(op, tpr, ch, cached, psmem);
+    case B200NORM_DT_BF16: return ring_kernel_for<__nv_bfloat16>(op, tpr, ch, cached, psmem);
+    case B200NORM_DT_F16: return ring_kernel_for<__half>(op, tpr, ch, cached, psmem);
     default: return nullptr;
   }
 }
@@ -221,6 +222,7 @@ int max_active_clusters(const DeviceInfo& dev, RingKernel k, int block, int smem
 }
 
 constexpr int kConsumerThreads = 512;
+constexpr int kFwdWideCH = 6;      // ... for kernels whose only per-chunk state is x (TPR >= 256)
 constexpr int kFwdMaxCH = 4;       // chunks per thread kept in registers by the forward-type kernels
 constexpr int kBwdCacheCH = 2;     // backward, g / xc cached in registers
 constexpr int kBwdRereadCH_RMS = 4;  // backward re-read variant: column accumulators = CH * VEC (x2 for LayerNorm)
@@ -285,6 +287,29 @@ bool try_ring_plan(const b200norm_desc& d, const DeviceInfo& dev, int C, bool ro
       if (ch < 3) ch = 3;  // only CH 3 / 4 are instantiated for the re-read form
       if (ch == 4 && ln_bwd) return false;
     }
+  } else if (d.op == B200NORM_OP_RMSNORM_FWD || d.op == B200NORM_OP_SOFTMAX_FWD) {
+    // x is the only per-chunk register state: up to 6 chunks per thread from TPR 256 on
+    // (N = 12288 bf16 -> two 256-thread groups per CTA instead of one 512-thread group)
+    if (!pick(kFwdMaxCH)) {
+      tpr = 0;
+      for (int t : {256, 512}) {
+        if (forced_tpr != 0 && t != forced_tpr) continue;
+        if (nchunks <= t * kFwdWideCH) {
+          tpr = t;
+          ch = (nchunks + t - 1) / t;
+          break;
+        }
+      }
+      if (tpr == 0) {
+        if (forced_tpr != 0 && forced_tpr != 512) return false;
+        tpr = 512;
+        ch = 0;
+        cached = false;
+      }
+    } else if (tpr == 512 && forced_tpr == 0 && nchunks <= 256 * kFwdWideCH) {
+      tpr = 256;
+      ch = (nchunks + 255) / 256;
+    }
   } else if (!pick(kFwdMaxCH)) {
     if (forced_tpr != 0 && forced_tpr != 512) return false;
     tpr = 512;
@@ -323,6 +348,11 @@ bool try_ring_plan(const b200norm_desc& d, const DeviceInfo& dev, int C, bool ro
   p.stream_bytes = (uint32_t)tile_rows * p.slice_bytes;
   p.stage_bytes = align_up((uint32_t)ns * p.stream_bytes, 128);
 
+  // LayerNorm forward keeps fp32 copies of weight and bias in shared memory when the ring
+  // still gets >= 3 stages per group next to them.
+  bool want_psmem = d.op == B200NORM_OP_LAYERNORM_FWD && ch > 0 && env_int("B200NORM_NO_PSMEM") == 0;
+  const uint32_t param_bytes = align_up(2u * (uint32_t)slice_cols * 4u, 128);
+
   // Ring depth D (stages per group); the ring is group-major, stage (g*D + s).
   for (;;) {
     uint32_t off = 8u * (kMaxStages + groups);
@@ -332,9 +362,15 @@ bool try_ring_plan(const b200norm_desc& d, const DeviceInfo& dev, int C, bool ro
     p.off_cls = off;
     off += (uint32_t)groups * 2 * kClsSetBytes;
     off = align_up(off, 128);
+    p.off_param = off;
+    if (want_psmem) off += param_bytes;
     p.off_ring = off;
     const int64_t budget = (int64_t)dev.smem_optin - 1024 - off;
     int max_stages = (int)(budget / p.stage_bytes);
+    if (want_psmem && max_stages / groups < 3) {
+      want_psmem = false;  // not enough room: parameters stay packed in registers
+      continue;
+    }
     if (max_stages > kMaxStages) max_stages = kMaxStages;
     int depth = max_stages / groups;  // stages per group
     if (depth < 2 && groups > 1) {
@@ -351,6 +387,7 @@ bool try_ring_plan(const b200norm_desc& d, const DeviceInfo& dev, int C, bool ro
     break;
   }
   p.groups = groups;
+  p.psmem = want_psmem;
   p.block = groups * tpr;
   const uint32_t ring_bytes = (uint32_t)p.stages * p.stage_bytes;
   if (bwd) {
@@ -360,7 +397,7 @@ bool try_ring_plan(const b200norm_desc& d, const DeviceInfo& dev, int C, bool ro
   p.smem = p.off_ring + ring_bytes;
 
   const int64_t ntiles = ceil_div64(d.rows, tile_rows);
-  int64_t nclusters = max_active_clusters(dev, ring_kernel_any(d.io_dtype, d.op, tpr, ch, cached), p.block,
+  int64_t nclusters = max_active_clusters(dev, ring_kernel_any(d.io_dtype, d.op, tpr, ch, cached, p.psmem), p.block,
                                           (int)p.smem, C);
   if (nclusters > ntiles) nclusters = ntiles;
   if (nclusters < 1) nclusters = 1;
@@ -552,7 +589,7 @@ int launch_typed(const b200norm_desc& d, const Plan& plan, RowParams& rp, void* 
   }
 
   // ---- ring kernels ----
-  RingKernel k = ring_kernel_for<T>(d.op, plan.tpr, plan.ch, plan.cached);
+  RingKernel k = ring_kernel_for<T>(d.op, plan.tpr, plan.ch, plan.cached, plan.psmem);
   if (k == nullptr)
     return fail(B200NORM_ERR_UNSUPPORTED, "no ring kernel for op %d tpr %d ch %d", d.op, plan.tpr, plan.ch);
   {
@@ -981,6 +1018,7 @@ int b200norm_launch(const b200norm_desc* desc, const b200norm_tensor* inputs, in
   rp.off_red = plan.off_red;
   rp.off_cls = plan.off_cls;
   rp.off_ring = plan.off_ring;
+  rp.off_param = plan.off_param;
   rp.off_acc = plan.off_ring;
 
   switch (dt) {

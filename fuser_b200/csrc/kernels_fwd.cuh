@@ -97,7 +97,11 @@ __global__ void __launch_bounds__(kMaxBlock, 1) rmsnorm_fwd_ring_kernel(const Ro
 // ---------------------------------------------------------------------------
 // LayerNorm forward: mean, invstd = rsqrt(M2/N + eps), y = (x-mean)*invstd*w + b.
 // ---------------------------------------------------------------------------
-template <typename T, int TPR, int CH>
+// PSMEM: weight and bias live in shared memory as fp32 (two LDS.128 per parameter and chunk)
+// instead of packed in registers (16 unpack ops per chunk and 8*CH registers) — LayerNorm is
+// the one forward with two per-column parameters, and unpacking both costs more issue slots
+// than the row math itself.
+template <typename T, int TPR, int CH, bool PSMEM = false>
 __global__ void __launch_bounds__(kMaxBlock, 1) layernorm_fwd_ring_kernel(const RowParams p) {
   constexpr int VEC = IO<T>::VEC;
   constexpr int H = VEC / 2;
@@ -110,9 +114,17 @@ __global__ void __launch_bounds__(kMaxBlock, 1) layernorm_fwd_ring_kernel(const 
 
   const int nchunks = p.nchunks;
   const size_t col0_bytes = (size_t)g.crank * p.slice_bytes;
-  uint4 wq[NC], bq[NC];
-  load_params_to_regs<T, TPR, CH>(p.weight, col0_bytes, g.gtid, nchunks, 1.0f, wq);
-  load_params_to_regs<T, TPR, CH>(p.bias, col0_bytes, g.gtid, nchunks, -0.0f, bq);
+  uint4 wq[PSMEM ? 1 : NC], bq[PSMEM ? 1 : NC];
+  const uint32_t off_w = p.off_param;
+  const uint32_t off_b = p.off_param + (uint32_t)nchunks * (uint32_t)(VEC * 4);
+  if constexpr (PSMEM) {
+    stage_param_smem<T>(p.weight, col0_bytes, off_w, nchunks, 1.0f);
+    stage_param_smem<T>(p.bias, col0_bytes, off_b, nchunks, -0.0f);
+    __syncthreads();
+  } else {
+    load_params_to_regs<T, TPR, CH>(p.weight, col0_bytes, g.gtid, nchunks, 1.0f, wq);
+    load_params_to_regs<T, TPR, CH>(p.bias, col0_bytes, g.gtid, nchunks, -0.0f, bq);
+  }
   const bool stat_writer = g.gtid == 0 && g.crank == 0;
 
   uint8_t* out_tile = out_row_ptr<T>(p, ring.row0, g.crank, g.gtid);
@@ -162,8 +174,13 @@ __global__ void __launch_bounds__(kMaxBlock, 1) layernorm_fwd_ring_kernel(const 
       for_each_chunk<TPR, CH>(g.gtid, nchunks, [&](int j, int coff) {
         float2 y[H], w[H], b[H];
         if constexpr (CH > 0) {
-          IO<T>::unpack2(wq[j], w);
-          IO<T>::unpack2(bq[j], b);
+          if constexpr (PSMEM) {
+            load_param_smem<VEC>(off_w, nchunks, g.gtid + coff, w);
+            load_param_smem<VEC>(off_b, nchunks, g.gtid + coff, b);
+          } else {
+            IO<T>::unpack2(wq[j], w);
+            IO<T>::unpack2(bq[j], b);
+          }
 #pragma unroll
           for (int k = 0; k < H; ++k) y[k] = f2fma(f2mul(x[j][k], is2), w[k], b[k]);
         } else {

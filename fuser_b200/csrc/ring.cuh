@@ -36,6 +36,7 @@ constexpr int kRedNV = 4;  // max floats reduced at once
 constexpr int kRedSetBytes = kRedNV * kMaxWarpsPerGroup * 4;  // one slot set: [kRedNV][16 warps]
 constexpr int kClsSetBytes = kRedNV * kMaxCluster * 4;        // one cluster slot set: [16 ranks][kRedNV]
 constexpr int kMaxBlock = 512;  // G * TPR; 128 registers per thread at one CTA per SM
+// (two CTAs per SM at 64 registers was measured: every kernel spills and loses 10-60 %)
 
 constexpr uint32_t kFlagHasWeight = 1u << 0;
 constexpr uint32_t kFlagHasBias = 1u << 1;
@@ -84,6 +85,7 @@ struct RowParams {
   uint32_t off_cls;   // float [groups][2][kMaxCluster][kRedNV]
   uint32_t off_ring;  // groups*depth stages, group-major: stage (g*depth + s)
   uint32_t off_acc;   // bwd: cross-group accumulator staging (aliases the ring)
+  uint32_t off_param; // LayerNorm fwd: fp32 copies of the weight / bias slices, 16-byte planes
   // backward: in-kernel finish of the column sums (cooperative launch; see kernels_bwd.cuh)
   int32_t fused_finish;    // 1: the grid is co-resident and finishes dgamma / dbeta itself
   uint32_t* sync_words;    // two zero-initialised workspace header words, returned to zero
@@ -392,6 +394,34 @@ template <typename T>
 __device__ __forceinline__ uint4 load_param_chunk(const void* gp, size_t col0_bytes, int c, float identity) {
   if (gp == nullptr) return splat_chunk<T>(identity);
   return ldg_128_nc(static_cast<const uint8_t*>(gp) + col0_bytes + 16u * (uint32_t)c);
+}
+
+// fp32 copies of per-column parameters in shared memory, split in VEC/4 planes of
+// [chunk][4 floats] so that lane l reading chunk (c0 + l) of a plane is conflict-free.
+// Used where two parameters (LayerNorm's weight and bias) would not fit in registers unpacked.
+template <typename T>
+__device__ __forceinline__ void stage_param_smem(const void* gp, size_t col0_bytes, uint32_t off, int nchunks,
+                                                 float identity) {
+  constexpr int VEC = IO<T>::VEC;
+  for (int c = threadIdx.x; c < nchunks; c += blockDim.x) {
+    float2 f[VEC / 2];
+    IO<T>::unpack2(load_param_chunk<T>(gp, col0_bytes, c, identity), f);
+#pragma unroll
+    for (int h = 0; h < VEC / 4; ++h) {
+      *reinterpret_cast<float4*>(smem_raw + off + (uint32_t)h * (uint32_t)nchunks * 16u + 16u * (uint32_t)c) =
+          make_float4(f[2 * h].x, f[2 * h].y, f[2 * h + 1].x, f[2 * h + 1].y);
+    }
+  }
+}
+template <int VEC>
+__device__ __forceinline__ void load_param_smem(uint32_t off, int nchunks, int c, float2 (&w)[VEC / 2]) {
+#pragma unroll
+  for (int h = 0; h < VEC / 4; ++h) {
+    const float4 v =
+        *reinterpret_cast<const float4*>(smem_raw + off + (uint32_t)h * (uint32_t)nchunks * 16u + 16u * (uint32_t)c);
+    w[2 * h] = make_float2(v.x, v.y);
+    w[2 * h + 1] = make_float2(v.z, v.w);
+  }
 }
 
 template <typename T>

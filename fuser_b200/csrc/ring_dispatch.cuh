@@ -10,9 +10,10 @@ namespace b200norm {
 using RingKernel = void (*)(const RowParams);
 
 // op: b200norm_op; tpr in {32,64,128,256,512}; ch in {1,2,3,4} or 0 (looping form, tpr 512 only).
-RingKernel ring_fwd_kernel_f32(int op, int tpr, int ch);
-RingKernel ring_fwd_kernel_bf16(int op, int tpr, int ch);
-RingKernel ring_fwd_kernel_f16(int op, int tpr, int ch);
+// psmem (LayerNorm fwd only): weight / bias staged in shared memory as fp32.
+RingKernel ring_fwd_kernel_f32(int op, int tpr, int ch, bool psmem);
+RingKernel ring_fwd_kernel_bf16(int op, int tpr, int ch, bool psmem);
+RingKernel ring_fwd_kernel_f16(int op, int tpr, int ch, bool psmem);
 // norm backward: cached (g / xc in registers, ch in {1,2}) or re-read (ch in {3,4}, tpr 512... any tpr).
 RingKernel ring_bwd_kernel_f32(int op, int tpr, int ch, bool cached);
 RingKernel ring_bwd_kernel_bf16(int op, int tpr, int ch, bool cached);
