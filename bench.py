@@ -482,8 +482,18 @@ def main():
     peak, peak_src = measured_peak()
     dom = "bwd" if "bwd" in byt else "fwd"
     achieved = per_kernel[dom]["gbs"]
+    # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this
+    # workload (profiles/traffic.json, written by scripts/ncu_summary.py); null when none is committed
+    # or the problem was row-sharded (the capture is of the 1-GPU problem).
+    traffic = traffic_src = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath) and rows == M:
+        ent = json.load(open(tpath)).get(args.workload, {}).get(dom)
+        if ent:
+            traffic, traffic_src = ent["dram_bytes"], f"profiles/{ent['from']}"
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": f"{kind}:{dom}", "peak_source": peak_src, "launches_timed": nk,
+                "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": byt[dom],
+                "kernel": f"{kind}:{dom}", "peak_source": peak_src, "launches_timed": nk,
                 "per_kernel": per_kernel,
                 "step_frac_of_peak": (step_bytes / (ms_per_step * 1e-3) / 1e9) / peak}
 
