@@ -59,6 +59,9 @@ F_REDUCE_MAX = 1 << 9
 F_REDUCE_FMAX = 1 << 10
 F_OUT_MEAN = 1 << 11
 F_OUT_INVSTD = 1 << 12
+F_ADD_RESIDUAL = 1 << 13
+F_OUT_SUM = 1 << 14
+F_ROUND_SUM = 1 << 15
 
 VARIANT_AUTO, VARIANT_GENERIC, VARIANT_TMA, VARIANT_CLUSTER = 0, 1, 2, 3
 
@@ -71,6 +74,7 @@ EXPORTED_SYMBOLS = [
     "b200norm_last_error",
     "b200norm_variant_name",
     "b200norm_device_info",
+    "b200norm_debug_set_timeline",
 ]
 
 
@@ -180,6 +184,8 @@ def load():
     lib.b200norm_variant_name.restype = C.c_char_p
     lib.b200norm_device_info.argtypes = [C.POINTER(C.c_int)] * 5
     lib.b200norm_device_info.restype = C.c_int
+    lib.b200norm_debug_set_timeline.argtypes = [C.c_void_p]
+    lib.b200norm_debug_set_timeline.restype = None
     if lib.b200norm_abi_version() != ABI_VERSION:
         raise ImportError(f"libb200norm ABI {lib.b200norm_abi_version()} != binding {ABI_VERSION}")
     _lib = lib
@@ -229,6 +235,11 @@ def workspace_bytes(desc: Desc) -> int:
 
 def launch_count() -> int:
     return int(load().b200norm_launch_count())
+
+
+def set_timeline(device_ptr) -> None:
+    """Tuning aid: per-CTA %globaltimer marks of every ring kernel go to this device buffer (None = off)."""
+    load().b200norm_debug_set_timeline(C.c_void_p(device_ptr) if device_ptr else None)
 
 
 def device_info() -> dict:

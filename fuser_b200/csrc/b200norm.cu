@@ -28,6 +28,7 @@ namespace {
 
 thread_local char g_err[512] = "";
 std::atomic<uint64_t> g_launches{0};
+std::atomic<unsigned long long*> g_timeline{nullptr};
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -72,6 +73,9 @@ int elem_size(int dt) { return dt == B200NORM_DT_F32 ? 4 : 2; }
 
 bool is_row_op(int op) { return op >= B200NORM_OP_LAYERNORM_FWD && op <= B200NORM_OP_LOGSOFTMAX_BWD; }
 bool is_norm_bwd(int op) { return op == B200NORM_OP_LAYERNORM_BWD || op == B200NORM_OP_RMSNORM_BWD; }
+bool is_add_fwd(const b200norm_desc& d) {
+  return (d.op == B200NORM_OP_LAYERNORM_FWD || d.op == B200NORM_OP_RMSNORM_FWD) && (d.flags & B200NORM_F_ADD_RESIDUAL);
+}
 int n_streams(int op) {
   switch (op) {
     case B200NORM_OP_LAYERNORM_BWD:
@@ -89,9 +93,16 @@ uint64_t algorithmic_bytes(const b200norm_desc& d) {
   // The reference's own *_iobytes formulas (benchmarks/python/test_*_{fwd,bwd}.py).
   const uint64_t s = elem_size(d.io_dtype), M = d.rows, N = d.cols;
   switch (d.op) {
-    case B200NORM_OP_LAYERNORM_FWD: return s * 2 * (M * N + N) + 4 * 2 * M;
+    case B200NORM_OP_LAYERNORM_FWD:
+    case B200NORM_OP_RMSNORM_FWD: {
+      // + the residual read and the sum write of the fused-add variants (every tensor the fusion
+      // reads or writes, as benchmarks/python/core.py:compute_total_iobytes counts them)
+      const uint64_t extra = ((d.flags & B200NORM_F_ADD_RESIDUAL) ? s * M * N : 0) +
+                             ((d.flags & B200NORM_F_ADD_RESIDUAL) && (d.flags & B200NORM_F_OUT_SUM) ? s * M * N : 0);
+      if (d.op == B200NORM_OP_LAYERNORM_FWD) return s * 2 * (M * N + N) + 4 * 2 * M + extra;
+      return s * (2 * M * N + N) + 4 * M + extra;
+    }
     case B200NORM_OP_LAYERNORM_BWD: return s * 3 * (M * N + N) + 4 * 2 * M;
-    case B200NORM_OP_RMSNORM_FWD: return s * (2 * M * N + N) + 4 * M;
     case B200NORM_OP_RMSNORM_BWD: return s * (3 * M * N + 2 * N) + 4 * M;
     case B200NORM_OP_SOFTMAX_FWD:
     case B200NORM_OP_LOGSOFTMAX_FWD: return s * 2 * M * N;
@@ -124,7 +135,7 @@ struct Plan {
   int rows_per_split = 0;  // generic colsum
   int n_launches = 1;
   uint32_t slice_bytes = 0, stream_bytes = 0, stage_bytes = 0;
-  uint32_t off_red = 0, off_cls = 0, off_param = 0, off_ring = 0;
+  uint32_t off_red = 0, off_cls = 0, off_param = 0, off_ring = 0, off_tidx = 0;
   uint32_t smem = 0;
   uint64_t ws_bytes = 0;
 };
@@ -135,17 +146,20 @@ uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 // kernel tables
 // ---------------------------------------------------------------------------
 template <typename T>
-RingKernel ring_kernel_for(int op, int tpr, int ch, bool cached, bool psmem);
+RingKernel ring_kernel_for(int op, int tpr, int ch, bool cached, bool psmem, bool add);
 template <>
-RingKernel ring_kernel_for<float>(int op, int tpr, int ch, bool cached, bool psmem) {
+RingKernel ring_kernel_for<float>(int op, int tpr, int ch, bool cached, bool psmem, bool add) {
+  if (add) return ring_add_kernel_f32(op, tpr, ch, psmem);
   return is_norm_bwd(op) ? ring_bwd_kernel_f32(op, tpr, ch, cached) : ring_fwd_kernel_f32(op, tpr, ch, psmem);
 }
 template <>
-RingKernel ring_kernel_for<__nv_bfloat16>(int op, int tpr, int ch, bool cached, bool psmem) {
+RingKernel ring_kernel_for<__nv_bfloat16>(int op, int tpr, int ch, bool cached, bool psmem, bool add) {
+  if (add) return ring_add_kernel_bf16(op, tpr, ch, psmem);
   return is_norm_bwd(op) ? ring_bwd_kernel_bf16(op, tpr, ch, cached) : ring_fwd_kernel_bf16(op, tpr, ch, psmem);
 }
 template <>
-RingKernel ring_kernel_for<__half>(int op, int tpr, int ch, bool cached, bool psmem) {
+RingKernel ring_kernel_for<__half>(int op, int tpr, int ch, bool cached, bool psmem, bool add) {
+  if (add) return ring_add_kernel_f16(op, tpr, ch, psmem);
   return is_norm_bwd(op) ? ring_bwd_kernel_f16(op, tpr, ch, cached) : ring_fwd_kernel_f16(op, tpr, ch, psmem);
 }
 
@@ -168,11 +182,11 @@ int prepare_ring_kernel(RingKernel k, int smem, int cluster) {
   return B200NORM_OK;
 }
 
-RingKernel ring_kernel_any(int dt, int op, int tpr, int ch, bool cached, bool psmem) {
+RingKernel ring_kernel_any(int dt, int op, int tpr, int ch, bool cached, bool psmem, bool add) {
   switch (dt) {
-    case B200NORM_DT_F32: return ring_kernel_for<float>(op, tpr, ch, cached, psmem);
-    case B200NORM_DT_BF16: return ring_kernel_for<__nv_bfloat16>(op, tpr, ch, cached, psmem);
-    case B200NORM_DT_F16: return ring_kernel_for<__half>(op, tpr, ch, cached, psmem);
+    case B200NORM_DT_F32: return ring_kernel_for<float>(op, tpr, ch, cached, psmem, add);
+    case B200NORM_DT_BF16: return ring_kernel_for<__nv_bfloat16>(op, tpr, ch, cached, psmem, add);
+    case B200NORM_DT_F16: return ring_kernel_for<__half>(op, tpr, ch, cached, psmem, add);
     default: return nullptr;
   }
 }
@@ -255,7 +269,8 @@ bool try_ring_plan(const b200norm_desc& d, const DeviceInfo& dev, int C, bool ro
   if ((slice_cols * es) % 16 != 0) return false;
   if (slice_cols * es > (int64_t)100 * 1024) return false;
   const int nchunks = (int)(slice_cols / vec);
-  const int ns = n_streams(d.op);
+  const bool add = is_add_fwd(d);
+  const int ns = add ? 2 : n_streams(d.op);
   const bool bwd = is_norm_bwd(d.op);
   const bool ln_bwd = d.op == B200NORM_OP_LAYERNORM_BWD;
 
@@ -287,7 +302,7 @@ bool try_ring_plan(const b200norm_desc& d, const DeviceInfo& dev, int C, bool ro
       if (ch < 3) ch = 3;  // only CH 3 / 4 are instantiated for the re-read form
       if (ch == 4 && ln_bwd) return false;
     }
-  } else if (d.op == B200NORM_OP_RMSNORM_FWD || d.op == B200NORM_OP_SOFTMAX_FWD) {
+  } else if ((d.op == B200NORM_OP_RMSNORM_FWD && !add) || d.op == B200NORM_OP_SOFTMAX_FWD) {
     // x is the only per-chunk register state: up to 6 chunks per thread from TPR 256 on
     // (N = 12288 bf16 -> two 256-thread groups per CTA instead of one 512-thread group)
     if (!pick(kFwdMaxCH)) {
@@ -356,6 +371,8 @@ bool try_ring_plan(const b200norm_desc& d, const DeviceInfo& dev, int C, bool ro
   // Ring depth D (stages per group); the ring is group-major, stage (g*D + s).
   for (;;) {
     uint32_t off = 8u * (kMaxStages + groups);
+    p.off_tidx = off;  // dynamic schedule: stage -> tile index
+    off += 4u * kMaxStages;
     off = align_up(off, 2 * kRedSetBytes);  // slot-set pairs are toggled with an XOR
     p.off_red = off;
     off += (uint32_t)groups * 2 * kRedSetBytes;
@@ -397,7 +414,7 @@ bool try_ring_plan(const b200norm_desc& d, const DeviceInfo& dev, int C, bool ro
   p.smem = p.off_ring + ring_bytes;
 
   const int64_t ntiles = ceil_div64(d.rows, tile_rows);
-  int64_t nclusters = max_active_clusters(dev, ring_kernel_any(d.io_dtype, d.op, tpr, ch, cached, p.psmem), p.block,
+  int64_t nclusters = max_active_clusters(dev, ring_kernel_any(d.io_dtype, d.op, tpr, ch, cached, p.psmem, add), p.block,
                                           (int)p.smem, C);
   if (nclusters > ntiles) nclusters = ntiles;
   if (nclusters < 1) nclusters = 1;
@@ -589,7 +606,7 @@ int launch_typed(const b200norm_desc& d, const Plan& plan, RowParams& rp, void* 
   }
 
   // ---- ring kernels ----
-  RingKernel k = ring_kernel_for<T>(d.op, plan.tpr, plan.ch, plan.cached, plan.psmem);
+  RingKernel k = ring_kernel_for<T>(d.op, plan.tpr, plan.ch, plan.cached, plan.psmem, is_add_fwd(d));
   if (k == nullptr)
     return fail(B200NORM_ERR_UNSUPPORTED, "no ring kernel for op %d tpr %d ch %d", d.op, plan.tpr, plan.ch);
   {
@@ -620,6 +637,7 @@ int launch_typed(const b200norm_desc& d, const Plan& plan, RowParams& rp, void* 
     rp.dw_out = dw;
     rp.db_out = db;
     rp.sums_out = sums_f32;
+    rp.timeline = g_timeline.load();
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)plan.grid);
@@ -633,7 +651,14 @@ int launch_typed(const b200norm_desc& d, const Plan& plan, RowParams& rp, void* 
     attrs[na].val.clusterDim.y = 1;
     attrs[na].val.clusterDim.z = 1;
     ++na;
-    if (fused) {
+    // The in-kernel finish needs every CTA resident at its grid barrier. The grid is at most one
+    // CTA per SM (one cluster per cluster slot), so it is co-resident as soon as the SMs are free;
+    // whatever holds an SM when the kernel starts (the stream's predecessor under PDL, an NCCL
+    // kernel on a side stream) finishes without waiting for this kernel, and the successor's CTAs
+    // cannot start before all of ours have. A plain launch therefore cannot deadlock, and unlike a
+    // cooperative launch it overlaps its setup with the predecessor's tail (measured: 77.7 -> 74.2 us
+    // at C2). B200NORM_COOP=1 asks the driver for the formal co-residency guarantee instead.
+    if (fused && env_int("B200NORM_COOP") != 0) {
       attrs[na].id = cudaLaunchAttributeCooperative;
       attrs[na].val.cooperative = 1;
       ++na;
@@ -726,6 +751,8 @@ int b200norm_abi_version(void) { return B200NORM_ABI_VERSION; }
 const char* b200norm_last_error(void) { return g_err; }
 
 uint64_t b200norm_launch_count(void) { return g_launches.load(); }
+
+void b200norm_debug_set_timeline(void* device_buf) { g_timeline.store(static_cast<unsigned long long*>(device_buf)); }
 
 const char* b200norm_variant_name(int variant) {
   switch (variant) {
@@ -830,8 +857,12 @@ int b200norm_launch(const b200norm_desc* desc, const b200norm_tensor* inputs, in
     case B200NORM_OP_LAYERNORM_FWD:
     case B200NORM_OP_RMSNORM_FWD: {
       const bool ln = d.op == B200NORM_OP_LAYERNORM_FWD;
-      NEED_IN(1 + (has_w ? 1 : 0) + ((ln && has_b) ? 1 : 0));
+      const bool add = (d.flags & B200NORM_F_ADD_RESIDUAL) != 0;
+      if (!add && (d.flags & (B200NORM_F_OUT_SUM | B200NORM_F_ROUND_SUM)))
+        return fail(B200NORM_ERR_BAD_ARG, "OUT_SUM / ROUND_SUM need ADD_RESIDUAL");
+      NEED_IN(1 + (add ? 1 : 0) + (has_w ? 1 : 0) + ((ln && has_b) ? 1 : 0));
       CHECK(bind_in_matrix(&rp.in0, &rp.in0_stride, "x"));
+      if (add) CHECK(bind_in_matrix(&rp.in1, &rp.in1_stride, "residual"));
       if (has_w) {
         void* w = nullptr;
         CHECK(bind_vec(inputs[ii++], d.cols, dt, "weight", &w));
@@ -846,6 +877,10 @@ int b200norm_launch(const b200norm_desc* desc, const b200norm_tensor* inputs, in
       }
       NEED_OUT(1);
       CHECK(bind_out_matrix(&rp.out0, &rp.out_stride, "y"));
+      if (add && (d.flags & B200NORM_F_OUT_SUM)) {
+        NEED_OUT(1);
+        CHECK(bind_out_matrix(&rp.out1, &rp.out1_stride, "sum"));
+      }
       if (ln) {
         if (d.flags & B200NORM_F_OUT_MEAN) {
           NEED_OUT(1);
@@ -1009,7 +1044,7 @@ int b200norm_launch(const b200norm_desc* desc, const b200norm_tensor* inputs, in
   rp.depth = plan.depth;
   rp.tile_rows = plan.tile_rows;
   rp.cols_cta = plan.cluster > 0 ? (int32_t)(d.cols / plan.cluster) : (int32_t)d.cols;
-  rp.nstreams = n_streams(d.op);
+  rp.nstreams = is_add_fwd(d) ? 2 : n_streams(d.op);
   rp.contiguous = plan.contiguous;
   rp.slice_bytes = plan.slice_bytes;
   rp.stream_bytes = plan.stream_bytes;
@@ -1020,6 +1055,17 @@ int b200norm_launch(const b200norm_desc* desc, const b200norm_tensor* inputs, in
   rp.off_ring = plan.off_ring;
   rp.off_param = plan.off_param;
   rp.off_acc = plan.off_ring;
+  rp.off_tidx = plan.off_tidx;
+  // Dynamic tile scheduling for the kernels without cross-row state (forward norms, softmax
+  // forward / backward): results are bit-identical whatever SM processes a row. The norm
+  // backward keeps the static split so that its per-CTA dgamma / dbeta partial sums — and with
+  // them the output bits — are the same on every run.
+  if (plan.variant == B200NORM_VARIANT_TMA && plan.cluster == 1 && !is_norm_bwd(d.op) && workspace != nullptr &&
+      workspace_bytes >= B200NORM_WS_HEADER_BYTES && (reinterpret_cast<uintptr_t>(workspace) & 15u) == 0 &&
+      env_int("B200NORM_STATIC") == 0) {
+    rp.dynamic = 1;
+    rp.sched_words = reinterpret_cast<uint32_t*>(workspace) + 2;
+  }
 
   switch (dt) {
     case B200NORM_DT_F32: return launch_typed<float>(d, plan, rp, dw, db, sums_f32, workspace, stream);

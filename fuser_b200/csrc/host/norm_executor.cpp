@@ -116,11 +116,13 @@ std::vector<at::Tensor> NormExecutor::allocateOutputs(const std::vector<at::Tens
   switch (spec_.op) {
     case B200NORM_OP_LAYERNORM_FWD:
       out.push_back(at::empty(first.sizes(), opts));
+      if ((f & B200NORM_F_ADD_RESIDUAL) && (f & B200NORM_F_OUT_SUM)) out.push_back(at::empty(first.sizes(), opts));
       if (f & B200NORM_F_OUT_MEAN) out.push_back(at::empty(stat_shape(first), f32));
       if (f & B200NORM_F_OUT_INVSTD) out.push_back(at::empty(stat_shape(first), f32));
       break;
     case B200NORM_OP_RMSNORM_FWD:
       out.push_back(at::empty(first.sizes(), opts));
+      if ((f & B200NORM_F_ADD_RESIDUAL) && (f & B200NORM_F_OUT_SUM)) out.push_back(at::empty(first.sizes(), opts));
       out.push_back(at::empty(stat_shape(first), f32));
       break;
     case B200NORM_OP_SOFTMAX_FWD:
@@ -193,9 +195,11 @@ std::vector<at::Tensor> NormExecutor::run(const std::vector<at::Tensor>& inputs,
   if (outputs.empty()) outputs = allocateOutputs(inputs, rows, cols);
 
   // marshal: matrices as [rows, cols] views, vectors flattened
+  const bool add_fwd = (spec_.op == B200NORM_OP_LAYERNORM_FWD || spec_.op == B200NORM_OP_RMSNORM_FWD) &&
+                       (spec_.flags & B200NORM_F_ADD_RESIDUAL);
   const int n_mat_in = (spec_.op == B200NORM_OP_FINALIZE_PARTIALS) ? 0
                        : (spec_.op == B200NORM_OP_LAYERNORM_BWD || spec_.op == B200NORM_OP_RMSNORM_BWD ||
-                          spec_.op == B200NORM_OP_SOFTMAX_BWD || spec_.op == B200NORM_OP_LOGSOFTMAX_BWD)
+                          spec_.op == B200NORM_OP_SOFTMAX_BWD || spec_.op == B200NORM_OP_LOGSOFTMAX_BWD || add_fwd)
                            ? 2
                            : 1;
   std::vector<at::Tensor> keep;  // views must outlive the launch call
@@ -211,6 +215,8 @@ std::vector<at::Tensor> NormExecutor::run(const std::vector<at::Tensor>& inputs,
   switch (spec_.op) {
     case B200NORM_OP_LAYERNORM_FWD:
     case B200NORM_OP_RMSNORM_FWD:
+      n_mat_out = (add_fwd && (spec_.flags & B200NORM_F_OUT_SUM)) ? 2 : 1;
+      break;
     case B200NORM_OP_SOFTMAX_FWD:
     case B200NORM_OP_LOGSOFTMAX_FWD:
     case B200NORM_OP_SOFTMAX_BWD:

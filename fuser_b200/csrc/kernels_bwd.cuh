@@ -22,21 +22,22 @@
 
 namespace b200norm {
 
-// Sense-reversing grid barrier on two workspace header words {count, generation}. Both are
-// zero before the first launch; count is back to zero when the barrier opens, generation
-// only ever increments, so no departure phase is needed. PRECONDITION: a cooperative launch
-// (all CTAs resident) and a __syncthreads() after the CTA's last global write + __threadfence().
-__device__ __forceinline__ void grid_barrier(uint32_t* words) {
+// Sense-reversing grid barrier on ONE workspace header word: bit 31 is the sense, the low bits
+// count arrivals. The word is zero before the first launch; the last arriver flips the sense and
+// clears the count with a single atomic add, so the barrier opens one atomic after the last
+// arrival (no separate reset store + fence on the critical path) and the count is zero again
+// afterwards, whatever grid size the next launch uses. PRECONDITION: every CTA of the grid is
+// resident (the grid is at most one CTA per SM; see launch_typed) and a __syncthreads() after the
+// CTA's last global write + __threadfence().
+__device__ __forceinline__ void grid_barrier(uint32_t* word) {
   if (threadIdx.x == 0) {
-    const uint32_t gen = ld_acquire_gpu(words + 1);  // read before arriving
-    const uint32_t old = atom_add_release_gpu(words, 1u);
-    if (old == gridDim.x - 1) {
-      words[0] = 0u;
-      __threadfence();
-      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(words + 1), "r"(gen + 1u) : "memory");
+    const uint32_t old = atom_add_acq_rel_gpu(word, 1u);
+    const uint32_t sense = old & 0x80000000u;
+    if ((old & 0x7fffffffu) == gridDim.x - 1) {
+      atom_add_acq_rel_gpu(word, 0x80000000u - gridDim.x);
     } else {
       Watchdog wd;
-      while (ld_acquire_gpu(words + 1) == gen) wd.tick();
+      while ((ld_acquire_gpu(word) & 0x80000000u) == sense) wd.tick();
     }
   }
   __syncthreads();
@@ -123,7 +124,9 @@ __global__ void __launch_bounds__(kMaxBlock, 1) norm_bwd_ring_kernel(const RowPa
   constexpr int H = VEC / 2;
   static_assert(CH > 0, "column accumulators need a fixed chunk ownership");
   const uint32_t smem0 = smem_u32(smem_raw);
+  tl_mark(p, 0);
   ring_setup(p, smem0);
+  tl_mark(p, 1);
   Group<TPR> g(p, smem0);
   Ring<T, TPR> ring(p, smem0, g);
   ring.prologue();
@@ -161,6 +164,7 @@ __global__ void __launch_bounds__(kMaxBlock, 1) norm_bwd_ring_kernel(const RowPa
   const size_t out_tile_bytes = (size_t)ring.row_step * out_row_bytes;
   for (; ring.more(); ring.advance(), out_tile += out_tile_bytes) {
     ring.wait();
+    if (ring.k == 0) tl_mark(p, 2);
     const int nrows = ring.nrows();
     const uint8_t* dyrow = smem_raw + ring.stage_off + 16u * (uint32_t)g.gtid;
     uint8_t* dxrow = out_tile;
@@ -235,6 +239,7 @@ __global__ void __launch_bounds__(kMaxBlock, 1) norm_bwd_ring_kernel(const RowPa
     }
   }
 
+  tl_mark(p, 3);
   // ---- combine the groups' column accumulators and emit this CTA's partial row ----
   if (want_dw || want_db) {
     const int nct = p.groups * TPR;
@@ -275,7 +280,9 @@ __global__ void __launch_bounds__(kMaxBlock, 1) norm_bwd_ring_kernel(const RowPa
       // grid reduction (runtime/grid_reduction.cu:201-309 + grid_sync.cu:34-95).
       __threadfence();
       __syncthreads();
+      tl_mark(p, 4);
       grid_barrier(p.sync_words);
+      tl_mark(p, 5);
       const int F = K * (p.cols / 4);  // float4 columns of the [K][N] result
       if ((F + 7) / 8 <= 2 * (int)gridDim.x) {
         finish_columns<T, 8>(p, K, F, nct);
@@ -284,7 +291,8 @@ __global__ void __launch_bounds__(kMaxBlock, 1) norm_bwd_ring_kernel(const RowPa
       }
     }
   }
-  ring_teardown();
+  ring_teardown(p);
+  tl_mark(p, 6);
 }
 
 }  // namespace b200norm

@@ -24,13 +24,15 @@ namespace b200norm {
 // RMSNorm forward: stat = rsqrt(mean(x^2)+eps) (or sqrt(...) with STAT_IS_RMS),
 // y = x * invstd * w.
 // ---------------------------------------------------------------------------
-template <typename T, int TPR, int CH>
+template <typename T, int TPR, int CH, bool ADD = false>
 __global__ void __launch_bounds__(kMaxBlock, 1) rmsnorm_fwd_ring_kernel(const RowParams p) {
   constexpr int VEC = IO<T>::VEC;
   constexpr int H = VEC / 2;
   constexpr int NC = CH > 0 ? CH : 1;
   const uint32_t smem0 = smem_u32(smem_raw);
+  tl_mark(p, 0);
   ring_setup(p, smem0);
+  tl_mark(p, 1);
   Group<TPR> g(p, smem0);
   Ring<T, TPR> ring(p, smem0, g);
   ring.prologue();
@@ -41,21 +43,26 @@ __global__ void __launch_bounds__(kMaxBlock, 1) rmsnorm_fwd_ring_kernel(const Ro
   uint4 wq[NC];
   load_params_to_regs<T, TPR, CH>(p.weight, col0_bytes, g.gtid, nchunks, 1.0f, wq);
   const bool stat_writer = g.gtid == 0 && g.crank == 0 && p.stat1 != nullptr;
+  const bool round_sum = ADD && (p.flags & kFlagRoundSum) != 0;
+  const bool out_sum = ADD && p.out1 != nullptr;
 
-  uint8_t* out_tile = out_row_ptr<T>(p, ring.row0, g.crank, g.gtid);
   const size_t out_row_bytes = (size_t)p.out_stride * sizeof(T);
-  const size_t out_tile_bytes = (size_t)ring.row_step * out_row_bytes;
-  for (; ring.more(); ring.advance(), out_tile += out_tile_bytes) {
-    ring.wait();
-    const int nrows = ring.nrows();
+  const size_t sum_row_bytes = (size_t)p.out1_stride * sizeof(T);
+  for (; ring.acquire(); ring.advance()) {
+    if (ring.k == 0) tl_mark(p, 2);
+    const int nrows = ring.cur_nrows;
     const uint8_t* xrow = smem_raw + ring.stage_off + 16u * (uint32_t)g.gtid;
-    uint8_t* yrow = out_tile;
-    for (int r = 0; r < nrows; ++r, xrow += p.slice_bytes, yrow += out_row_bytes) {
+    uint8_t* yrow = out_row_ptr<T>(p, ring.row0, g.crank, g.gtid);
+    uint8_t* srow = out_sum ? out1_row_ptr<T>(p, ring.row0, g.crank, g.gtid) : nullptr;
+    for (int r = 0; r < nrows; ++r, xrow += p.slice_bytes, yrow += out_row_bytes, srow += sum_row_bytes) {
       float2 x[NC][H];
       float2 acc = f2(0.f);
       for_each_chunk<TPR, CH>(g.gtid, nchunks, [&](int j, int coff) {
         float2 t[H];
         IO<T>::unpack2(ld_smem_u4(xrow + 16 * coff), t);
+        if constexpr (ADD) {
+          add_residual_chunk<T, H>(t, xrow + p.stream_bytes + 16 * coff, round_sum, out_sum ? srow + 16 * coff : nullptr);
+        }
 #pragma unroll
         for (int k = 0; k < H; ++k) {
           acc = f2fma(t[k], t[k], acc);
@@ -78,6 +85,7 @@ __global__ void __launch_bounds__(kMaxBlock, 1) rmsnorm_fwd_ring_kernel(const Ro
           for (int k = 0; k < H; ++k) y[k] = f2mul(f2mul(x[j][k], scale), w[k]);
         } else {
           IO<T>::unpack2(ld_smem_u4(xrow + 16 * coff), y);
+          if constexpr (ADD) add_residual_chunk<T, H>(y, xrow + p.stream_bytes + 16 * coff, round_sum, nullptr);
           IO<T>::unpack2(load_param_chunk<T>(p.weight, col0_bytes, g.gtid + coff, 1.0f), w);
 #pragma unroll
           for (int k = 0; k < H; ++k) y[k] = f2mul(f2mul(y[k], scale), w[k]);
@@ -91,7 +99,9 @@ __global__ void __launch_bounds__(kMaxBlock, 1) rmsnorm_fwd_ring_kernel(const Ro
       ring.refill();
     }
   }
-  ring_teardown();
+  tl_mark(p, 3);
+  ring_teardown(p);
+  tl_mark(p, 6);
 }
 
 // ---------------------------------------------------------------------------
@@ -101,13 +111,15 @@ __global__ void __launch_bounds__(kMaxBlock, 1) rmsnorm_fwd_ring_kernel(const Ro
 // instead of packed in registers (16 unpack ops per chunk and 8*CH registers) — LayerNorm is
 // the one forward with two per-column parameters, and unpacking both costs more issue slots
 // than the row math itself.
-template <typename T, int TPR, int CH, bool PSMEM = false>
+template <typename T, int TPR, int CH, bool PSMEM = false, bool ADD = false>
 __global__ void __launch_bounds__(kMaxBlock, 1) layernorm_fwd_ring_kernel(const RowParams p) {
   constexpr int VEC = IO<T>::VEC;
   constexpr int H = VEC / 2;
   constexpr int NC = CH > 0 ? CH : 1;
   const uint32_t smem0 = smem_u32(smem_raw);
+  tl_mark(p, 0);
   ring_setup(p, smem0);
+  tl_mark(p, 1);
   Group<TPR> g(p, smem0);
   Ring<T, TPR> ring(p, smem0, g);
   ring.prologue();
@@ -126,21 +138,26 @@ __global__ void __launch_bounds__(kMaxBlock, 1) layernorm_fwd_ring_kernel(const 
     load_params_to_regs<T, TPR, CH>(p.bias, col0_bytes, g.gtid, nchunks, -0.0f, bq);
   }
   const bool stat_writer = g.gtid == 0 && g.crank == 0;
+  const bool round_sum = ADD && (p.flags & kFlagRoundSum) != 0;
+  const bool out_sum = ADD && p.out1 != nullptr;
 
-  uint8_t* out_tile = out_row_ptr<T>(p, ring.row0, g.crank, g.gtid);
   const size_t out_row_bytes = (size_t)p.out_stride * sizeof(T);
-  const size_t out_tile_bytes = (size_t)ring.row_step * out_row_bytes;
-  for (; ring.more(); ring.advance(), out_tile += out_tile_bytes) {
-    ring.wait();
-    const int nrows = ring.nrows();
+  const size_t sum_row_bytes = (size_t)p.out1_stride * sizeof(T);
+  for (; ring.acquire(); ring.advance()) {
+    if (ring.k == 0) tl_mark(p, 2);
+    const int nrows = ring.cur_nrows;
     const uint8_t* xrow = smem_raw + ring.stage_off + 16u * (uint32_t)g.gtid;
-    uint8_t* yrow = out_tile;
-    for (int r = 0; r < nrows; ++r, xrow += p.slice_bytes, yrow += out_row_bytes) {
+    uint8_t* yrow = out_row_ptr<T>(p, ring.row0, g.crank, g.gtid);
+    uint8_t* srow = out_sum ? out1_row_ptr<T>(p, ring.row0, g.crank, g.gtid) : nullptr;
+    for (int r = 0; r < nrows; ++r, xrow += p.slice_bytes, yrow += out_row_bytes, srow += sum_row_bytes) {
       float2 x[NC][H];
       float2 acc = f2(0.f);
       for_each_chunk<TPR, CH>(g.gtid, nchunks, [&](int j, int coff) {
         float2 t[H];
         IO<T>::unpack2(ld_smem_u4(xrow + 16 * coff), t);
+        if constexpr (ADD) {
+          add_residual_chunk<T, H>(t, xrow + p.stream_bytes + 16 * coff, round_sum, out_sum ? srow + 16 * coff : nullptr);
+        }
 #pragma unroll
         for (int k = 0; k < H; ++k) {
           acc = f2add(acc, t[k]);
@@ -155,7 +172,10 @@ __global__ void __launch_bounds__(kMaxBlock, 1) layernorm_fwd_ring_kernel(const 
       acc = f2(0.f);
       for_each_chunk<TPR, CH>(g.gtid, nchunks, [&](int j, int coff) {
         float2 t[H];
-        if constexpr (CH == 0) IO<T>::unpack2(ld_smem_u4(xrow + 16 * coff), t);
+        if constexpr (CH == 0) {
+          IO<T>::unpack2(ld_smem_u4(xrow + 16 * coff), t);
+          if constexpr (ADD) add_residual_chunk<T, H>(t, xrow + p.stream_bytes + 16 * coff, round_sum, nullptr);
+        }
 #pragma unroll
         for (int k = 0; k < H; ++k) {
           if constexpr (CH > 0) {
@@ -185,6 +205,7 @@ __global__ void __launch_bounds__(kMaxBlock, 1) layernorm_fwd_ring_kernel(const 
           for (int k = 0; k < H; ++k) y[k] = f2fma(f2mul(x[j][k], is2), w[k], b[k]);
         } else {
           IO<T>::unpack2(ld_smem_u4(xrow + 16 * coff), y);
+          if constexpr (ADD) add_residual_chunk<T, H>(y, xrow + p.stream_bytes + 16 * coff, round_sum, nullptr);
           IO<T>::unpack2(load_param_chunk<T>(p.weight, col0_bytes, g.gtid + coff, 1.0f), w);
           IO<T>::unpack2(load_param_chunk<T>(p.bias, col0_bytes, g.gtid + coff, -0.0f), b);
 #pragma unroll
@@ -202,7 +223,9 @@ __global__ void __launch_bounds__(kMaxBlock, 1) layernorm_fwd_ring_kernel(const 
       ring.refill();
     }
   }
-  ring_teardown();
+  tl_mark(p, 3);
+  ring_teardown(p);
+  tl_mark(p, 6);
 }
 
 // ---------------------------------------------------------------------------
@@ -217,20 +240,20 @@ __global__ void __launch_bounds__(kMaxBlock, 1) softmax_fwd_ring_kernel(const Ro
   constexpr int H = VEC / 2;
   constexpr int NC = CH > 0 ? CH : 1;
   const uint32_t smem0 = smem_u32(smem_raw);
+  tl_mark(p, 0);
   ring_setup(p, smem0);
+  tl_mark(p, 1);
   Group<TPR> g(p, smem0);
   Ring<T, TPR> ring(p, smem0, g);
   ring.prologue();
   const int nchunks = p.nchunks;
 
-  uint8_t* out_tile = out_row_ptr<T>(p, ring.row0, g.crank, g.gtid);
   const size_t out_row_bytes = (size_t)p.out_stride * sizeof(T);
-  const size_t out_tile_bytes = (size_t)ring.row_step * out_row_bytes;
-  for (; ring.more(); ring.advance(), out_tile += out_tile_bytes) {
-    ring.wait();
-    const int nrows = ring.nrows();
+  for (; ring.acquire(); ring.advance()) {
+    if (ring.k == 0) tl_mark(p, 2);
+    const int nrows = ring.cur_nrows;
     const uint8_t* xrow = smem_raw + ring.stage_off + 16u * (uint32_t)g.gtid;
-    uint8_t* yrow = out_tile;
+    uint8_t* yrow = out_row_ptr<T>(p, ring.row0, g.crank, g.gtid);
     for (int r = 0; r < nrows; ++r, xrow += p.slice_bytes, yrow += out_row_bytes) {
       float2 x[NC][H];
       float m[1] = {-INFINITY};
@@ -283,7 +306,9 @@ __global__ void __launch_bounds__(kMaxBlock, 1) softmax_fwd_ring_kernel(const Ro
       ring.refill();
     }
   }
-  ring_teardown();
+  tl_mark(p, 3);
+  ring_teardown(p);
+  tl_mark(p, 6);
 }
 
 // ---------------------------------------------------------------------------
@@ -297,21 +322,21 @@ __global__ void __launch_bounds__(kMaxBlock, 1) softmax_bwd_ring_kernel(const Ro
   constexpr int H = VEC / 2;
   constexpr int NC = CH > 0 ? CH : 1;
   const uint32_t smem0 = smem_u32(smem_raw);
+  tl_mark(p, 0);
   ring_setup(p, smem0);
+  tl_mark(p, 1);
   Group<TPR> g(p, smem0);
   Ring<T, TPR> ring(p, smem0, g);
   ring.prologue();
   const int nchunks = p.nchunks;
   const bool round_sum = (p.flags & kFlagRoundRowsum) != 0;
 
-  uint8_t* out_tile = out_row_ptr<T>(p, ring.row0, g.crank, g.gtid);
   const size_t out_row_bytes = (size_t)p.out_stride * sizeof(T);
-  const size_t out_tile_bytes = (size_t)ring.row_step * out_row_bytes;
-  for (; ring.more(); ring.advance(), out_tile += out_tile_bytes) {
-    ring.wait();
-    const int nrows = ring.nrows();
+  for (; ring.acquire(); ring.advance()) {
+    if (ring.k == 0) tl_mark(p, 2);
+    const int nrows = ring.cur_nrows;
     const uint8_t* dyrow = smem_raw + ring.stage_off + 16u * (uint32_t)g.gtid;
-    uint8_t* dxrow = out_tile;
+    uint8_t* dxrow = out_row_ptr<T>(p, ring.row0, g.crank, g.gtid);
     for (int r = 0; r < nrows; ++r, dyrow += p.slice_bytes, dxrow += out_row_bytes) {
       const uint8_t* yrow = dyrow + p.stream_bytes;
       float2 a[NC][H];  // y*dy   | dy        (log)
@@ -369,7 +394,9 @@ __global__ void __launch_bounds__(kMaxBlock, 1) softmax_bwd_ring_kernel(const Ro
       ring.refill();
     }
   }
-  ring_teardown();
+  tl_mark(p, 3);
+  ring_teardown(p);
+  tl_mark(p, 6);
 }
 
 }  // namespace b200norm

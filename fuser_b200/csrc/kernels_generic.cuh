@@ -65,11 +65,27 @@ __global__ void __launch_bounds__(kGenericThreads) generic_row_kernel(const RowP
     const T* a = in0 + row * p.in0_stride;
     const T* b = in1 != nullptr ? in1 + row * p.in1_stride : nullptr;
     T* o = out0 != nullptr ? out0 + row * p.out_stride : nullptr;
+    // fused residual add (forward norms): the normalised value is x + residual, rounded through
+    // the io dtype when the fusion does so; the sum is written out once if requested
+    const bool add_res = (OP == G_RMSNORM_FWD || OP == G_LAYERNORM_FWD) && (p.flags & kFlagAddResidual) != 0;
+    const bool round_sum = (p.flags & kFlagRoundSum) != 0;
+    auto xin = [&](int c) -> float {
+      float x = IO<T>::to_f32(a[c]);
+      if (add_res) {
+        x += IO<T>::to_f32(b[c]);
+        if (round_sum) x = IO<T>::round_trip(x);
+      }
+      return x;
+    };
+    if ((OP == G_RMSNORM_FWD || OP == G_LAYERNORM_FWD) && add_res && p.out1 != nullptr) {
+      T* so = static_cast<T*>(p.out1) + row * p.out1_stride;
+      for (int c = tid; c < N; c += kGenericThreads) so[c] = IO<T>::from_f32(IO<T>::to_f32(a[c]) + IO<T>::to_f32(b[c]));
+    }
 
     if constexpr (OP == G_RMSNORM_FWD) {
       float ss[1] = {0.f};
       for (int c = tid; c < N; c += kGenericThreads) {
-        const float x = IO<T>::to_f32(a[c]);
+        const float x = xin(c);
         ss[0] = fmaf(x, x, ss[0]);
       }
       block_allreduce<SumOp, 1>(ss, red, phase);
@@ -78,25 +94,25 @@ __global__ void __launch_bounds__(kGenericThreads) generic_row_kernel(const RowP
       const float rms = __fsqrt_rn(ve);
       const float scale = (p.flags & kFlagStatIsRms) ? __frcp_rn(rms) : invstd;
       for (int c = tid; c < N; c += kGenericThreads) {
-        float y = IO<T>::to_f32(a[c]) * scale;
+        float y = xin(c) * scale;
         if (wgt != nullptr) y *= IO<T>::to_f32(wgt[c]);
         o[c] = IO<T>::from_f32(y);
       }
       if (tid == 0 && p.stat1 != nullptr) p.stat1[row] = (p.flags & kFlagStatIsRms) ? rms : invstd;
     } else if constexpr (OP == G_LAYERNORM_FWD) {
       float s[1] = {0.f};
-      for (int c = tid; c < N; c += kGenericThreads) s[0] += IO<T>::to_f32(a[c]);
+      for (int c = tid; c < N; c += kGenericThreads) s[0] += xin(c);
       block_allreduce<SumOp, 1>(s, red, phase);
       const float mean = s[0] * p.inv_n;
       float m2[1] = {0.f};
       for (int c = tid; c < N; c += kGenericThreads) {
-        const float d = IO<T>::to_f32(a[c]) - mean;
+        const float d = xin(c) - mean;
         m2[0] = fmaf(d, d, m2[0]);
       }
       block_allreduce<SumOp, 1>(m2, red, phase);
       const float invstd = __frsqrt_rn(m2[0] * p.inv_n + p.eps);
       for (int c = tid; c < N; c += kGenericThreads) {
-        float y = (IO<T>::to_f32(a[c]) - mean) * invstd;
+        float y = (xin(c) - mean) * invstd;
         if (wgt != nullptr) y *= IO<T>::to_f32(wgt[c]);
         if (bia != nullptr) y += IO<T>::to_f32(bia[c]);
         o[c] = IO<T>::from_f32(y);

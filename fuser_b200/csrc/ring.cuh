@@ -51,13 +51,17 @@ constexpr uint32_t kFlagReduceMax = 1u << 9;
 constexpr uint32_t kFlagReduceFmax = 1u << 10;
 constexpr uint32_t kFlagOutMean = 1u << 11;
 constexpr uint32_t kFlagOutInvstd = 1u << 12;
+constexpr uint32_t kFlagAddResidual = 1u << 13;
+constexpr uint32_t kFlagOutSum = 1u << 14;
+constexpr uint32_t kFlagRoundSum = 1u << 15;
 
 struct RowParams {
   // streamed operands (row-major, unit inner stride)
   const void* in0;  // x (forward) | dy (backward)
   const void* in1;  // -          | x or y (backward)
   void* out0;       // y (forward) | dx (backward)
-  int64_t in0_stride, in1_stride, out_stride;  // row strides in elements
+  void* out1;       // forward with a fused residual add: x + residual (nullptr = not requested)
+  int64_t in0_stride, in1_stride, out_stride, out1_stride;  // row strides in elements
   const void* weight;  // [N] io dtype or nullptr
   const void* bias;    // [N] io dtype or nullptr
   float* stat0;        // fwd: mean out (LN) ; bwd: mean in (LN)
@@ -92,7 +96,30 @@ struct RowParams {
   void* dw_out;            // io dtype [N] or nullptr
   void* db_out;            // io dtype [N] or nullptr
   float* sums_out;         // fp32 [K][N] or nullptr (multi-GPU partial sums, no cast)
+  // tuning aid (b200norm_debug_set_timeline): per-CTA %globaltimer marks, 8 slots per CTA; nullptr = off
+  unsigned long long* timeline;
+  // dynamic tile scheduling (forward-type kernels, cluster size 1): after the statically assigned
+  // first `depth` tiles of every group, tiles are drawn from a global counter so that SMs which
+  // stream faster take more rows (per-SM bandwidth differs by up to ~35 % on B200; with a static
+  // split the slowest SM sets the kernel time). sched_words = {next tile, CTAs done}; both are
+  // zero between launches (the last CTA to finish resets them).
+  int32_t dynamic;
+  uint32_t* sched_words;
+  uint32_t off_tidx;  // int32 [groups*depth]: tile index held by each stage (-1 = no more tiles)
 };
+
+// Timeline marks: 0 entry, 1 setup done (after griddepcontrol.wait), 2 first tile landed,
+// 3 row loop done, 4 partial row written, 5 grid barrier passed, 6 exit.
+__device__ __forceinline__ void tl_mark(const RowParams& p, int slot) {
+  if (p.timeline != nullptr && threadIdx.x == 0) {
+    p.timeline[(size_t)blockIdx.x * 8 + slot] = global_timer_ns();
+    if (slot == 0) {
+      uint32_t smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      p.timeline[(size_t)blockIdx.x * 8 + 7] = smid;  // slot 7: the SM this CTA ran on
+    }
+  }
+}
 
 // barrier block at the start of dynamic smem:  full[groups*depth] | clbar[groups]
 
@@ -215,7 +242,14 @@ struct Ring {
   uint32_t phase;
   uint32_t ring_off_g, bar_g;
   int32_t k;           // current tile (group-local)
-  int32_t ntiles_g;    // tiles this group walks
+  int32_t ntiles_g;    // tiles this group walks (static schedule)
+  int32_t cur_nrows;   // rows of the current tile (set by acquire())
+  // dynamic schedule
+  bool dyn;
+  int32_t ntiles_all;  // tiles of the whole problem
+  int32_t dyn_base;    // first tile index handed out by the counter
+  int32_t pending;     // lane 0 of the group's first warp: tile index fetched one refill ahead
+  uint32_t tidx_g;     // smem_raw-relative offset of this group's stage -> tile index table
   int32_t last_nrows;  // rows of the group's last tile (tile_rows unless it is the ragged global tail)
   int64_t row0;        // first row of the current tile
   int64_t row_step;    // rows between consecutive tiles of this group
@@ -240,6 +274,12 @@ struct Ring {
     k = 0;
     s = 0;
     phase = 0;
+    cur_nrows = 0;
+    dyn = p.dynamic != 0;
+    ntiles_all = (int32_t)ntiles;
+    dyn_base = (int32_t)(nclusters * p.groups * p.depth);
+    pending = 0x7fffffff;
+    tidx_g = p.off_tidx + 4u * (uint32_t)(g.gid * p.depth);
     ring_off_g = p.off_ring + (uint32_t)(g.gid * p.depth) * p.stage_bytes;
     bar_g = smem0 + 8u * (uint32_t)(g.gid * p.depth);
     stage_off = ring_off_g;
@@ -255,7 +295,9 @@ struct Ring {
   // Issue the bulk copies of tile kk (first row r0) into stage (off, b).
   // Executed by the group's first warp (all 32 lanes, converged).
   __device__ __forceinline__ void issue(int32_t kk, int64_t r0, uint32_t off, uint32_t b) const {
-    const int nr = nrows_of(kk);
+    issue_rows(nrows_of(kk), r0, off, b);
+  }
+  __device__ __forceinline__ void issue_rows(int nr, int64_t r0, uint32_t off, uint32_t b) const {
     const uint32_t bytes = (uint32_t)nr * p.slice_bytes;
     const uint32_t dst = smem0 + off;
     const uint64_t policy = l2_policy_evict_first();
@@ -284,21 +326,80 @@ struct Ring {
   }
 
   // Fill the ring before the first tile.
-  __device__ __forceinline__ void prologue() const {
+  __device__ __forceinline__ void prologue() {
     if (g.warp == 0) {
-      int64_t r0 = row0;
-      for (int i = 0; i < p.depth && i < ntiles_g; ++i) {
-        issue(i, r0, ring_off_g + (uint32_t)i * p.stage_bytes, bar_g + 8u * (uint32_t)i);
-        r0 += row_step;
+      if (dyn) {
+        // the first `depth` tiles are the static ones; every stage gets a tile index or an end mark
+        int32_t t = (int32_t)(row0 / p.tile_rows);
+        const int32_t tstep = (int32_t)(row_step / p.tile_rows);
+        bool all_valid = true;
+        for (int i = 0; i < p.depth; ++i, t += tstep) {
+          const bool valid = i < ntiles_g;
+          all_valid = all_valid && valid;
+          dyn_issue(valid ? t : -1, ring_off_g + (uint32_t)i * p.stage_bytes, bar_g + 8u * (uint32_t)i,
+                    tidx_g + 4u * (uint32_t)i);
+        }
+        // every fetch is consumed by the next refill (so it has been performed before the CTA's
+        // exit protocol resets the counter); none is issued once the pool is known to be empty
+        if (all_valid && g.lane == 0) pending = dyn_base + (int32_t)atomicAdd(p.sched_words, 1u);
+      } else {
+        int64_t r0 = row0;
+        for (int i = 0; i < p.depth && i < ntiles_g; ++i) {
+          issue(i, r0, ring_off_g + (uint32_t)i * p.stage_bytes, bar_g + 8u * (uint32_t)i);
+          r0 += row_step;
+        }
       }
+    }
+  }
+
+  // dynamic schedule: publish the stage's tile index, then start its copies (or, for the end
+  // mark, complete the stage's phase with a plain arrive). The table write is ordered before the
+  // consumers' read by the release of the arrive and the acquire of their mbarrier wait.
+  __device__ __forceinline__ void dyn_issue(int32_t t, uint32_t off, uint32_t b, uint32_t tidx_off) const {
+    if (g.lane == 0) *reinterpret_cast<volatile int32_t*>(smem_raw + tidx_off) = t;
+    if (t >= 0) {
+      const int64_t r0 = (int64_t)t * p.tile_rows;
+      const int64_t left = p.rows - r0;
+      issue_rows(left < p.tile_rows ? (int)left : p.tile_rows, r0, off, b);
+    } else if (g.lane == 0) {
+      mbar_arrive(b);
     }
   }
 
   // Refill the current stage with tile k+D. PRECONDITION: every thread of the group has
   // finished reading the stage and a group-wide barrier (Group::allreduce or Group::sync)
   // separates those reads from this call.
-  __device__ __forceinline__ void refill() const {
+  __device__ __forceinline__ void refill() {
+    if (dyn) {
+      if (g.warp == 0) {
+        int32_t t = __shfl_sync(0xffffffffu, pending, 0);
+        if (t >= ntiles_all) {
+          t = -1;
+        } else if (g.lane == 0) {
+          pending = dyn_base + (int32_t)atomicAdd(p.sched_words, 1u);
+        }
+        dyn_issue(t, stage_off, bar, tidx_g + 4u * s);
+      }
+      return;
+    }
     if (g.warp == 0 && k + p.depth < ntiles_g) issue(k + p.depth, row0 + (int64_t)p.depth * row_step, stage_off, bar);
+  }
+
+  // Wait for the current stage; false when this group has no more tiles. Sets row0 / cur_nrows.
+  __device__ __forceinline__ bool acquire() {
+    if (dyn) {
+      mbar_wait(bar, phase);
+      const int32_t t = *reinterpret_cast<const volatile int32_t*>(smem_raw + tidx_g + 4u * s);
+      if (t < 0) return false;
+      row0 = (int64_t)t * p.tile_rows;
+      const int64_t left = p.rows - row0;
+      cur_nrows = left < p.tile_rows ? (int32_t)left : p.tile_rows;
+      return true;
+    }
+    if (k >= ntiles_g) return false;
+    mbar_wait(bar, phase);
+    cur_nrows = nrows_of(k);
+    return true;
   }
 
   __device__ __forceinline__ bool more() const { return k < ntiles_g; }
@@ -336,10 +437,22 @@ __device__ __forceinline__ void ring_setup(const RowParams& p, uint32_t smem0) {
   pdl_wait();
 }
 
-__device__ __forceinline__ void ring_teardown() {
+__device__ __forceinline__ void ring_teardown(const RowParams& p) {
   if (cluster_nctarank() > 1) {
     __syncwarp();
     cluster_sync_all();  // nobody exits while a peer may still st.async into its smem
+  }
+  if (p.dynamic) {
+    // exit protocol of the dynamic schedule: the last CTA to get here returns both words to zero.
+    // Every tile fetch of this CTA has returned (its value was consumed) before this barrier.
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const uint32_t old = atomicAdd(p.sched_words + 1, 1u);
+      if (old == gridDim.x - 1) {
+        p.sched_words[0] = 0u;
+        p.sched_words[1] = 0u;
+      }
+    }
   }
 }
 
@@ -422,6 +535,35 @@ __device__ __forceinline__ void load_param_smem(uint32_t off, int nchunks, int c
     w[2 * h] = make_float2(v.x, v.y);
     w[2 * h + 1] = make_float2(v.z, v.w);
   }
+}
+
+// Fused residual add of the forward kernels (the prologue nvFuser's persistent schedulers
+// absorb for `norm(x + residual)`, benchmarks/python/test_rmsnorm_add_fwd.py,
+// test_dropout_layernorm_fwd.py minus the dropout): t = x + r in fp32; when the fusion rounds the
+// sum to the io dtype before normalising (a bf16 `hidden + residual` feeding the norm) the same
+// rounding is applied here; the sum is streamed out once if requested.
+template <typename T, int H>
+__device__ __forceinline__ void add_residual_chunk(float2 (&t)[H], const uint8_t* rchunk, bool round_sum,
+                                                   uint8_t* sum_out /* nullptr = no store */) {
+  float2 r[H];
+  IO<T>::unpack2(ld_smem_u4(rchunk), r);
+#pragma unroll
+  for (int k = 0; k < H; ++k) t[k] = f2add(t[k], r[k]);
+  if constexpr (sizeof(T) == 4) {
+    if (sum_out != nullptr) st_global_stream(sum_out, IO<T>::pack2(t));
+  } else {
+    if (round_sum || sum_out != nullptr) {
+      const uint4 q = IO<T>::pack2(t);
+      if (sum_out != nullptr) st_global_stream(sum_out, q);
+      if (round_sum) IO<T>::unpack2(q, t);
+    }
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ uint8_t* out1_row_ptr(const RowParams& p, int64_t row, uint32_t crank, int gtid) {
+  return static_cast<uint8_t*>(p.out1) + ((size_t)row * p.out1_stride + (size_t)crank * p.cols_cta) * sizeof(T) +
+         16u * (uint32_t)gtid;
 }
 
 template <typename T>

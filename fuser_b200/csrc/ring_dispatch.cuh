@@ -14,6 +14,10 @@ using RingKernel = void (*)(const RowParams);
 RingKernel ring_fwd_kernel_f32(int op, int tpr, int ch, bool psmem);
 RingKernel ring_fwd_kernel_bf16(int op, int tpr, int ch, bool psmem);
 RingKernel ring_fwd_kernel_f16(int op, int tpr, int ch, bool psmem);
+// forward norms with the fused residual add (RMSNORM_FWD / LAYERNORM_FWD only; ch in {1..4} or 0)
+RingKernel ring_add_kernel_f32(int op, int tpr, int ch, bool psmem);
+RingKernel ring_add_kernel_bf16(int op, int tpr, int ch, bool psmem);
+RingKernel ring_add_kernel_f16(int op, int tpr, int ch, bool psmem);
 // norm backward: cached (g / xc in registers, ch in {1,2}) or re-read (ch in {3,4}, tpr 512... any tpr).
 RingKernel ring_bwd_kernel_f32(int op, int tpr, int ch, bool cached);
 RingKernel ring_bwd_kernel_bf16(int op, int tpr, int ch, bool cached);

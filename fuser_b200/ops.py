@@ -66,24 +66,46 @@ def plan_for(op: int, dtype: torch.dtype, rows: int, cols: int, flags: int = 0, 
 # ---------------------------------------------------------------------------
 # forward
 # ---------------------------------------------------------------------------
+def _residual_flags(residual, want_sum, round_sum):
+    if residual is None:
+        if want_sum or round_sum:
+            raise ValueError("want_sum / round_sum need a residual")
+        return 0
+    return L.F_ADD_RESIDUAL | (L.F_OUT_SUM if want_sum else 0) | (L.F_ROUND_SUM if round_sum else 0)
+
+
 def layer_norm_fwd(x, weight=None, bias=None, eps: float = 1e-5, *, want_mean=True, want_invstd=True,
-                   variant=L.VARIANT_AUTO, cluster_size=0):
-    """y, mean[...,1], invstd[...,1] = layer_norm(x) over the last dim."""
+                   residual=None, want_sum=False, round_sum=False, variant=L.VARIANT_AUTO, cluster_size=0):
+    """y, mean[...,1], invstd[...,1] = layer_norm(x) over the last dim.
+
+    With ``residual`` the norm is taken of ``x + residual`` (the fused-add prologue of
+    benchmarks/python/test_dropout_layernorm_fwd.py / test_rmsnorm_add_fwd.py); ``want_sum`` also
+    returns the sum (io dtype) as a 4th value; ``round_sum`` rounds the sum through the io dtype
+    before normalising, as a reduced-precision ``x + residual`` feeding the norm does."""
     flags = (L.F_HAS_WEIGHT if weight is not None else 0) | (L.F_HAS_BIAS if bias is not None else 0)
     flags |= (L.F_OUT_MEAN if want_mean else 0) | (L.F_OUT_INVSTD if want_invstd else 0)
-    ins = [x] + [t for t in (weight, bias) if t is not None]
+    flags |= _residual_flags(residual, want_sum, round_sum)
+    ins = [x] + ([residual] if residual is not None else []) + [t for t in (weight, bias) if t is not None]
     outs = iter(_run(L.OP_LAYERNORM_FWD, flags, eps, variant, cluster_size, ins))
     y = next(outs)
+    s = next(outs) if want_sum else None
     mean = next(outs) if want_mean else None
     invstd = next(outs) if want_invstd else None
-    return y, mean, invstd
+    return (y, mean, invstd, s) if want_sum else (y, mean, invstd)
 
 
-def rms_norm_fwd(x, weight=None, eps: float = 1e-5, *, stat_is_rms=False, variant=L.VARIANT_AUTO, cluster_size=0):
-    """y, stat[...,1] = rms_norm(x); stat = invstd (C++ builder) or rms (Thunder spelling)."""
+def rms_norm_fwd(x, weight=None, eps: float = 1e-5, *, stat_is_rms=False, residual=None, want_sum=False,
+                 round_sum=False, variant=L.VARIANT_AUTO, cluster_size=0):
+    """y, stat[...,1] = rms_norm(x); stat = invstd (C++ builder) or rms (Thunder spelling).
+    ``residual`` / ``want_sum`` / ``round_sum``: as in :func:`layer_norm_fwd` (sum returned 3rd)."""
     flags = (L.F_HAS_WEIGHT if weight is not None else 0) | (L.F_STAT_IS_RMS if stat_is_rms else 0)
-    ins = [x] + ([weight] if weight is not None else [])
-    y, stat = _run(L.OP_RMSNORM_FWD, flags, eps, variant, cluster_size, ins)
+    flags |= _residual_flags(residual, want_sum, round_sum)
+    ins = [x] + ([residual] if residual is not None else []) + ([weight] if weight is not None else [])
+    outs = _run(L.OP_RMSNORM_FWD, flags, eps, variant, cluster_size, ins)
+    if want_sum:
+        y, s, stat = outs
+        return y, stat, s
+    y, stat = outs
     return y, stat
 
 

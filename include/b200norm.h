@@ -111,7 +111,17 @@ enum {
   B200NORM_F_REDUCE_FMAX = 1u << 10,
   /* LayerNorm forward: mean / invstd outputs requested. */
   B200NORM_F_OUT_MEAN = 1u << 11,
-  B200NORM_F_OUT_INVSTD = 1u << 12
+  B200NORM_F_OUT_INVSTD = 1u << 12,
+  /* LayerNorm / RMSNorm forward with a fused residual add — the prologue nvFuser's persistent
+   * schedulers absorb for norm(x + residual) (benchmarks/python/test_rmsnorm_add_fwd.py,
+   * torch_ops.py:76-83; test_dropout_{layernorm,rmsnorm}_fwd.py without the dropout):
+   * ADD_RESIDUAL: a second [M,N] input follows x and the norm is taken of x + residual;
+   * OUT_SUM: x + residual (io dtype) is a second [M,N] output right after y;
+   * ROUND_SUM: the sum is rounded through the io dtype before it is normalised (what a
+   * bf16 `hidden + residual` feeding the norm does); without it the fp32 sum is used. */
+  B200NORM_F_ADD_RESIDUAL = 1u << 13,
+  B200NORM_F_OUT_SUM = 1u << 14,
+  B200NORM_F_ROUND_SUM = 1u << 15
 };
 
 /* desc.variant: 0 lets the library choose (the dispatch rule mirrors the accept
@@ -169,10 +179,11 @@ typedef struct {
 
 /*
  * Tensor order per op (absent optional tensors are simply left out):
- *   LAYERNORM_FWD  in : x[M,N], weight[N]?, bias[N]?        out: y[M,N], mean[M]?, invstd[M]?
+ *   LAYERNORM_FWD  in : x[M,N], residual[M,N]?, weight[N]?, bias[N]?
+ *                  out: y[M,N], sum[M,N]?, mean[M]?, invstd[M]?
  *   LAYERNORM_BWD  in : dy[M,N], x[M,N], mean[M], invstd[M], weight[N]?
  *                  out: dx[M,N]?, dweight[N]?, dbias[N]?
- *   RMSNORM_FWD    in : x[M,N], weight[N]?                   out: y[M,N], stat[M]
+ *   RMSNORM_FWD    in : x[M,N], residual[M,N]?, weight[N]?   out: y[M,N], sum[M,N]?, stat[M]
  *   RMSNORM_BWD    in : dy[M,N], x[M,N], stat[M], weight[N]? out: dx[M,N]?, dweight[N]?
  *   SOFTMAX_FWD / LOGSOFTMAX_FWD   in : x[M,N]               out: y[M,N]
  *   SOFTMAX_BWD / LOGSOFTMAX_BWD   in : dy[M,N], y[M,N]      out: dx[M,N]
@@ -219,6 +230,12 @@ const char* b200norm_variant_name(int variant);
  * *has_device = 0 when no CUDA device is visible. */
 int b200norm_device_info(int* has_device, int* sm_count, int* smem_per_block_optin,
                          int* cc_major, int* cc_minor);
+
+/* Tuning aid (no reference counterpart): while `device_buf` is non-NULL every ring kernel
+ * launched by this process stores per-CTA %globaltimer marks into it (8 x uint64 per CTA:
+ * entry, setup done, first tile landed, row loop done, partial row written, grid barrier
+ * passed, exit). The buffer must hold 8 * grid_x uint64. NULL switches it off. */
+void b200norm_debug_set_timeline(void* device_buf);
 
 #ifdef __cplusplus
 }
