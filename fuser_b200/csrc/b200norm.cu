@@ -372,7 +372,7 @@ bool try_ring_plan(const b200norm_desc& d, const DeviceInfo& dev, int C, bool ro
   for (;;) {
     uint32_t off = 8u * (kMaxStages + groups);
     p.off_tidx = off;  // dynamic schedule: stage -> tile index
-    off += 4u * kMaxStages;
+    off += 4u * kSchedTableInts + 16u;  // + the CTA's "groups that saw the empty pool" counter
     off = align_up(off, 2 * kRedSetBytes);  // slot-set pairs are toggled with an XOR
     p.off_red = off;
     off += (uint32_t)groups * 2 * kRedSetBytes;
@@ -1063,7 +1063,13 @@ int b200norm_launch(const b200norm_desc* desc, const b200norm_tensor* inputs, in
   if (plan.variant == B200NORM_VARIANT_TMA && plan.cluster == 1 && !is_norm_bwd(d.op) && workspace != nullptr &&
       workspace_bytes >= B200NORM_WS_HEADER_BYTES && (reinterpret_cast<uintptr_t>(workspace) & 15u) == 0 &&
       env_int("B200NORM_STATIC") == 0) {
-    rp.dynamic = 1;
+    // Pool size (measured on several B200s, whose per-SM imbalance differs: the static split loses
+    // 5-13 % on the worse ones): the last half of the tiles for two-stream kernels, the last quarter
+    // for RMSNorm / softmax forward; plain LayerNorm forward (two reductions per row, one group per
+    // CTA at wide rows) loses more to the pool tiles' ticket wait than it gains and stays static.
+    const bool ln_plain = d.op == B200NORM_OP_LAYERNORM_FWD && !is_add_fwd(d);
+    rp.dynamic = ln_plain ? 0 : (rp.nstreams > 1 ? 2 : 4);
+    if (int f = env_int("B200NORM_POOL")) rp.dynamic = f > 0 ? f : 4;  // 1 = everything past the first ring fill
     rp.sched_words = reinterpret_cast<uint32_t*>(workspace) + 2;
   }
 

@@ -143,6 +143,22 @@ __device__ __forceinline__ uint32_t atom_add_acq_rel_gpu(uint32_t* p, uint32_t v
   asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
   return old;
 }
+// Ticket counter for the dynamic tile schedule. An integer fetch-add on a warp-uniform address —
+// atomicAdd() or raw atom.add.u32 alike — is rewritten by ptxas into a warp-aggregated atomic
+// (VOTE / elected ATOMG / SHFL of the result), and that SHFL consumes the return value at once:
+// the whole L2 round trip (1-2 us under a saturating stream) lands on the issuing warp and, through
+// the group barrier, on every warp of the group (measured: +20 % per dynamically scheduled tile).
+// Floating-point adds are never aggregated (it would change the rounding), so the counter is kept
+// as an fp32 number: exact up to 2^24 tickets, zero has the all-zero bit pattern, and the
+// destination register stays pending until its first real use.
+__device__ __forceinline__ int32_t ticket_fetch_add(uint32_t* counter, int n) {
+  float old;
+  asm volatile("atom.relaxed.gpu.global.add.f32 %0, [%1], %2;" : "=f"(old) : "l"(counter), "f"((float)n) : "memory");
+  return __float_as_int(old);  // raw bits: convert with ticket_value() at the point of use
+}
+__device__ __forceinline__ int32_t ticket_value(int32_t raw_bits) { return (int32_t)__int_as_float(raw_bits); }
+constexpr int32_t kTicketNone = 0x4b7fffff;  // bits of 16777215.0f: "no ticket" (>= every pool size)
+constexpr int64_t kTicketMax = 1 << 24;
 __device__ __forceinline__ uint32_t atom_add_release_gpu(uint32_t* p, uint32_t v) {
   uint32_t old;
   asm volatile("atom.add.release.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");

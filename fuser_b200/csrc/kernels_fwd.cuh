@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(kMaxBlock, 1) rmsnorm_fwd_ring_kernel(const Ro
   ring_setup(p, smem0);
   tl_mark(p, 1);
   Group<TPR> g(p, smem0);
-  Ring<T, TPR> ring(p, smem0, g);
+  Ring<T, TPR, true> ring(p, smem0, g);
   ring.prologue();
 
   const int nchunks = p.nchunks;
@@ -100,6 +100,7 @@ __global__ void __launch_bounds__(kMaxBlock, 1) rmsnorm_fwd_ring_kernel(const Ro
     }
   }
   tl_mark(p, 3);
+  ring.finish();
   ring_teardown(p);
   tl_mark(p, 6);
 }
@@ -121,7 +122,7 @@ __global__ void __launch_bounds__(kMaxBlock, 1) layernorm_fwd_ring_kernel(const 
   ring_setup(p, smem0);
   tl_mark(p, 1);
   Group<TPR> g(p, smem0);
-  Ring<T, TPR> ring(p, smem0, g);
+  Ring<T, TPR, true> ring(p, smem0, g);
   ring.prologue();
 
   const int nchunks = p.nchunks;
@@ -224,6 +225,7 @@ __global__ void __launch_bounds__(kMaxBlock, 1) layernorm_fwd_ring_kernel(const 
     }
   }
   tl_mark(p, 3);
+  ring.finish();
   ring_teardown(p);
   tl_mark(p, 6);
 }
@@ -244,7 +246,7 @@ __global__ void __launch_bounds__(kMaxBlock, 1) softmax_fwd_ring_kernel(const Ro
   ring_setup(p, smem0);
   tl_mark(p, 1);
   Group<TPR> g(p, smem0);
-  Ring<T, TPR> ring(p, smem0, g);
+  Ring<T, TPR, true> ring(p, smem0, g);
   ring.prologue();
   const int nchunks = p.nchunks;
 
@@ -307,6 +309,7 @@ __global__ void __launch_bounds__(kMaxBlock, 1) softmax_fwd_ring_kernel(const Ro
     }
   }
   tl_mark(p, 3);
+  ring.finish();
   ring_teardown(p);
   tl_mark(p, 6);
 }
@@ -326,7 +329,7 @@ __global__ void __launch_bounds__(kMaxBlock, 1) softmax_bwd_ring_kernel(const Ro
   ring_setup(p, smem0);
   tl_mark(p, 1);
   Group<TPR> g(p, smem0);
-  Ring<T, TPR> ring(p, smem0, g);
+  Ring<T, TPR, true> ring(p, smem0, g);
   ring.prologue();
   const int nchunks = p.nchunks;
   const bool round_sum = (p.flags & kFlagRoundRowsum) != 0;
@@ -395,6 +398,7 @@ __global__ void __launch_bounds__(kMaxBlock, 1) softmax_bwd_ring_kernel(const Ro
     }
   }
   tl_mark(p, 3);
+  ring.finish();
   ring_teardown(p);
   tl_mark(p, 6);
 }

@@ -33,6 +33,7 @@ extern __shared__ __align__(128) uint8_t smem_raw[];
 constexpr int kMaxWarpsPerGroup = 16;
 constexpr int kMaxCluster = 16;
 constexpr int kRedNV = 4;  // max floats reduced at once
+constexpr int kSchedTableInts = 32;  // stage -> tile index table of the dynamic schedule (= max stages)
 constexpr int kRedSetBytes = kRedNV * kMaxWarpsPerGroup * 4;  // one slot set: [kRedNV][16 warps]
 constexpr int kClsSetBytes = kRedNV * kMaxCluster * 4;        // one cluster slot set: [16 ranks][kRedNV]
 constexpr int kMaxBlock = 512;  // G * TPR; 128 registers per thread at one CTA per SM
@@ -98,11 +99,11 @@ struct RowParams {
   float* sums_out;         // fp32 [K][N] or nullptr (multi-GPU partial sums, no cast)
   // tuning aid (b200norm_debug_set_timeline): per-CTA %globaltimer marks, 8 slots per CTA; nullptr = off
   unsigned long long* timeline;
-  // dynamic tile scheduling (forward-type kernels, cluster size 1): after the statically assigned
-  // first `depth` tiles of every group, tiles are drawn from a global counter so that SMs which
-  // stream faster take more rows (per-SM bandwidth differs by up to ~35 % on B200; with a static
-  // split the slowest SM sets the kernel time). sched_words = {next tile, CTAs done}; both are
-  // zero between launches (the last CTA to finish resets them).
+  // dynamic tile scheduling (forward-type kernels, cluster size 1): the last quarter of the tiles
+  // is drawn from a global counter so that SMs which stream faster take more rows (per-SM
+  // bandwidth differs by up to ~35 % on B200; with a static split the slowest SM sets the kernel
+  // time). sched_words = {next pool tile, CTAs done}; both are zero between launches (the last
+  // CTA to finish resets them).
   int32_t dynamic;
   uint32_t* sched_words;
   uint32_t off_tidx;  // int32 [groups*depth]: tile index held by each stage (-1 = no more tiles)
@@ -230,7 +231,7 @@ struct Group {
 // g + k*G; it lives in stage k % D — tracked as a running (stage, phase) pair.
 // All per-tile bookkeeping is 32-bit counters and running pointers.
 // ---------------------------------------------------------------------------
-template <typename T, int TPR>
+template <typename T, int TPR, bool DYN = false>
 struct Ring {
   const RowParams& p;
   const Group<TPR>& g;
@@ -242,17 +243,32 @@ struct Ring {
   uint32_t phase;
   uint32_t ring_off_g, bar_g;
   int32_t k;           // current tile (group-local)
-  int32_t ntiles_g;    // tiles this group walks (static schedule)
+  int32_t ntiles_g;    // tiles this group walks under the static schedule
   int32_t cur_nrows;   // rows of the current tile (set by acquire())
-  // dynamic schedule
+  int32_t last_nrows;  // rows of the group's last static tile (tile_rows unless it is the ragged global tail)
+  int64_t row0;        // first row of the current tile
+  int64_t row_step;    // rows between consecutive static tiles of this group
+  // Hybrid schedule (DYN kernels with p.dynamic set): every group walks ntiles_g statically assigned
+  // tiles with running pointers — the cheap path — and the last 1/p.dynamic of the problem is a
+  // shared pool drawn from a global ticket counter, so SMs that stream faster take more of it and
+  // all CTAs finish together. A pool tile is not free: ptxas makes the warp wait for the ticket's
+  // scoreboard at the next divergent branch (one row later), and under a saturating stream the
+  // atomic sits behind the SM's own streaming stores for longer than that — measured +10 % per
+  // pool tile on one-stream kernels, nothing on two-stream kernels (their rows take twice as long).
+  // Hence a pool of 1/4 (one input stream) or 1/2 (two), chosen in b200norm.cu.
   bool dyn;
   int32_t ntiles_all;  // tiles of the whole problem
-  int32_t dyn_base;    // first tile index handed out by the counter
-  int32_t pending;     // lane 0 of the group's first warp: tile index fetched one refill ahead
+  int32_t dyn_base;    // first tile index of the shared pool
+  int32_t pool_size;   // tiles in the shared pool
+  // Pool slots are fetched a whole ring revolution ahead: under a saturating stream an L2 atomic
+  // takes longer than one tile (fetching one refill ahead cost 20 % per pool tile). Lane s of the
+  // group's first warp owns the fetch for stage s's NEXT refill (raw return value of the atomic:
+  // nothing depends on it until then); the first revolution is one batch fetched in the prologue.
+  int32_t pending;     // lane s: ticket (raw bits, see ticket_fetch_add) for the next refill of stage s
+  int32_t first_base;  // lane 0: first ticket of the prologue batch (depth tickets)
+  int32_t n_dyn;       // pool refills done so far
+  bool saw_empty;      // a fetch of this group has found the pool empty
   uint32_t tidx_g;     // smem_raw-relative offset of this group's stage -> tile index table
-  int32_t last_nrows;  // rows of the group's last tile (tile_rows unless it is the ragged global tail)
-  int64_t row0;        // first row of the current tile
-  int64_t row_step;    // rows between consecutive tiles of this group
   // producer side
   const uint8_t* base0;
   const uint8_t* base1;
@@ -269,17 +285,31 @@ struct Ring {
     if (n_g > 0 && t0 + (n_g - 1) * tstep == ntiles - 1) {
       last_nrows = (int32_t)(p.rows - (ntiles - 1) * p.tile_rows);
     }
+    dyn = false;
+    if constexpr (DYN) {
+      // static tiles per group: all but 1/p.dynamic of the problem (p.dynamic = 1: only the first ring fill)
+      int64_t ks = p.dynamic > 0 ? (ntiles - ntiles / p.dynamic) / tstep : 0;
+      if (p.dynamic == 1 && ntiles >= tstep * p.depth) ks = p.depth;
+      if (p.dynamic != 0 && ks >= p.depth && ntiles < kTicketMax) {
+        dyn = true;
+        ntiles_g = (int32_t)ks;      // all of them full tiles: the ragged tail is in the pool
+        last_nrows = p.tile_rows;
+        ntiles_all = (int32_t)ntiles;
+        dyn_base = (int32_t)(ks * tstep);
+        pool_size = ntiles_all - dyn_base;
+        pending = kTicketNone;
+        first_base = kTicketNone;
+        n_dyn = 0;
+        saw_empty = false;
+        tidx_g = p.off_tidx + 4u * (uint32_t)(g.gid * p.depth);
+      }
+    }
     row0 = t0 * p.tile_rows;
     row_step = tstep * p.tile_rows;
     k = 0;
     s = 0;
     phase = 0;
     cur_nrows = 0;
-    dyn = p.dynamic != 0;
-    ntiles_all = (int32_t)ntiles;
-    dyn_base = (int32_t)(nclusters * p.groups * p.depth);
-    pending = 0x7fffffff;
-    tidx_g = p.off_tidx + 4u * (uint32_t)(g.gid * p.depth);
     ring_off_g = p.off_ring + (uint32_t)(g.gid * p.depth) * p.stage_bytes;
     bar_g = smem0 + 8u * (uint32_t)(g.gid * p.depth);
     stage_off = ring_off_g;
@@ -292,11 +322,8 @@ struct Ring {
   __device__ __forceinline__ int nrows_of(int32_t kk) const { return kk == ntiles_g - 1 ? last_nrows : p.tile_rows; }
   __device__ __forceinline__ int nrows() const { return nrows_of(k); }
 
-  // Issue the bulk copies of tile kk (first row r0) into stage (off, b).
+  // Issue the bulk copies of nr rows starting at row r0 into stage (off, b).
   // Executed by the group's first warp (all 32 lanes, converged).
-  __device__ __forceinline__ void issue(int32_t kk, int64_t r0, uint32_t off, uint32_t b) const {
-    issue_rows(nrows_of(kk), r0, off, b);
-  }
   __device__ __forceinline__ void issue_rows(int nr, int64_t r0, uint32_t off, uint32_t b) const {
     const uint32_t bytes = (uint32_t)nr * p.slice_bytes;
     const uint32_t dst = smem0 + off;
@@ -324,36 +351,28 @@ struct Ring {
       }
     }
   }
+  // static tile kk of this group (first row r0)
+  __device__ __forceinline__ void issue(int32_t kk, int64_t r0, uint32_t off, uint32_t b) const {
+    issue_rows(nrows_of(kk), r0, off, b);
+  }
 
   // Fill the ring before the first tile.
   __device__ __forceinline__ void prologue() {
     if (g.warp == 0) {
-      if (dyn) {
-        // the first `depth` tiles are the static ones; every stage gets a tile index or an end mark
-        int32_t t = (int32_t)(row0 / p.tile_rows);
-        const int32_t tstep = (int32_t)(row_step / p.tile_rows);
-        bool all_valid = true;
-        for (int i = 0; i < p.depth; ++i, t += tstep) {
-          const bool valid = i < ntiles_g;
-          all_valid = all_valid && valid;
-          dyn_issue(valid ? t : -1, ring_off_g + (uint32_t)i * p.stage_bytes, bar_g + 8u * (uint32_t)i,
-                    tidx_g + 4u * (uint32_t)i);
-        }
-        // every fetch is consumed by the next refill (so it has been performed before the CTA's
-        // exit protocol resets the counter); none is issued once the pool is known to be empty
-        if (all_valid && g.lane == 0) pending = dyn_base + (int32_t)atomicAdd(p.sched_words, 1u);
-      } else {
-        int64_t r0 = row0;
-        for (int i = 0; i < p.depth && i < ntiles_g; ++i) {
-          issue(i, r0, ring_off_g + (uint32_t)i * p.stage_bytes, bar_g + 8u * (uint32_t)i);
-          r0 += row_step;
-        }
+      int64_t r0 = row0;
+      for (int i = 0; i < p.depth && i < ntiles_g; ++i) {
+        issue(i, r0, ring_off_g + (uint32_t)i * p.stage_bytes, bar_g + 8u * (uint32_t)i);
+        r0 += row_step;
+      }
+      if constexpr (DYN) {
+        // the slots of the first ring revolution past the static share, as one batch
+        if (dyn && g.lane == 0) first_base = ticket_fetch_add(p.sched_words, p.depth);
       }
     }
   }
 
-  // dynamic schedule: publish the stage's tile index, then start its copies (or, for the end
-  // mark, complete the stage's phase with a plain arrive). The table write is ordered before the
+  // Pool tiles: publish the stage's tile index, then start its copies (or, for the end mark,
+  // complete the stage's phase with a plain arrive). The table write is ordered before the
   // consumers' read by the release of the arrive and the acquire of their mbarrier wait.
   __device__ __forceinline__ void dyn_issue(int32_t t, uint32_t off, uint32_t b, uint32_t tidx_off) const {
     if (g.lane == 0) *reinterpret_cast<volatile int32_t*>(smem_raw + tidx_off) = t;
@@ -366,40 +385,72 @@ struct Ring {
     }
   }
 
-  // Refill the current stage with tile k+D. PRECONDITION: every thread of the group has
-  // finished reading the stage and a group-wide barrier (Group::allreduce or Group::sync)
-  // separates those reads from this call.
+  // Refill the current stage with this group's tile k+D. PRECONDITION: every thread of the
+  // group has finished reading the stage and a group-wide barrier (Group::allreduce or
+  // Group::sync) separates those reads from this call.
   __device__ __forceinline__ void refill() {
-    if (dyn) {
-      if (g.warp == 0) {
-        int32_t t = __shfl_sync(0xffffffffu, pending, 0);
-        if (t >= ntiles_all) {
-          t = -1;
-        } else if (g.lane == 0) {
-          pending = dyn_base + (int32_t)atomicAdd(p.sched_words, 1u);
+    if constexpr (DYN) {
+      if (dyn && k + p.depth >= ntiles_g) {  // past the static share: a pool tile or the end mark
+        if (g.warp == 0) {
+          const int32_t raw = n_dyn < p.depth ? ticket_value(__shfl_sync(0xffffffffu, first_base, 0)) + n_dyn
+                                              : ticket_value(__shfl_sync(0xffffffffu, pending, (int)s));
+          ++n_dyn;
+          int32_t t = -1;
+          if (raw < pool_size) {
+            // slots of one group are fetched microseconds apart and come back in order; a tile must
+            // never be dropped silently if that ever fails to hold
+            if (saw_empty) __trap();
+            t = dyn_base + raw;
+            if (g.lane == (int)s) pending = ticket_fetch_add(p.sched_words, 1);
+          } else {
+            saw_empty = true;
+          }
+          dyn_issue(t, stage_off, bar, tidx_g + 4u * s);
         }
-        dyn_issue(t, stage_off, bar, tidx_g + 4u * s);
+        return;
       }
-      return;
     }
     if (g.warp == 0 && k + p.depth < ntiles_g) issue(k + p.depth, row0 + (int64_t)p.depth * row_step, stage_off, bar);
   }
 
   // Wait for the current stage; false when this group has no more tiles. Sets row0 / cur_nrows.
   __device__ __forceinline__ bool acquire() {
-    if (dyn) {
-      mbar_wait(bar, phase);
-      const int32_t t = *reinterpret_cast<const volatile int32_t*>(smem_raw + tidx_g + 4u * s);
-      if (t < 0) return false;
-      row0 = (int64_t)t * p.tile_rows;
-      const int64_t left = p.rows - row0;
-      cur_nrows = left < p.tile_rows ? (int32_t)left : p.tile_rows;
-      return true;
+    if constexpr (DYN) {
+      if (dyn && k >= ntiles_g) {
+        mbar_wait(bar, phase);
+        const int32_t t = *reinterpret_cast<const volatile int32_t*>(smem_raw + tidx_g + 4u * s);
+        if (t < 0) return false;
+        row0 = (int64_t)t * p.tile_rows;
+        const int64_t left = p.rows - row0;
+        cur_nrows = left < p.tile_rows ? (int32_t)left : p.tile_rows;
+        return true;
+      }
     }
     if (k >= ntiles_g) return false;
     mbar_wait(bar, phase);
     cur_nrows = nrows_of(k);
     return true;
+  }
+
+  // Exit protocol of the dynamic schedule: once every fetch of every group of the CTA has returned
+  // the CTA reports itself done, and the CTA whose report is the grid's last returns both scheduler
+  // words to zero for the next launch.
+  __device__ __forceinline__ void finish() const {
+    if constexpr (DYN) {
+      if (dyn && g.warp == 0) {
+        asm volatile("" ::"r"(pending), "r"(first_base));  // wait for this lane's outstanding fetches
+        __syncwarp();
+        if (g.lane == 0) {
+          uint32_t* cnt = reinterpret_cast<uint32_t*>(smem_raw + p.off_tidx + 4u * kSchedTableInts);
+          if (atomicAdd(cnt, 1u) == (uint32_t)p.groups - 1u) {
+            if (atomicAdd(p.sched_words + 1, 1u) == gridDim.x - 1) {
+              p.sched_words[0] = 0u;
+              p.sched_words[1] = 0u;
+            }
+          }
+        }
+      }
+    }
   }
 
   __device__ __forceinline__ bool more() const { return k < ntiles_g; }
@@ -425,6 +476,7 @@ __device__ __forceinline__ void ring_setup(const RowParams& p, uint32_t smem0) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < nbars; ++s) mbar_init(smem0 + 8u * (uint32_t)s, 1);
     fence_mbar_init();
+    *reinterpret_cast<uint32_t*>(smem_raw + p.off_tidx + 4u * kSchedTableInts) = 0u;  // groups that saw the empty pool
   }
   __syncthreads();
   if (cluster_nctarank() > 1) {
@@ -441,18 +493,6 @@ __device__ __forceinline__ void ring_teardown(const RowParams& p) {
   if (cluster_nctarank() > 1) {
     __syncwarp();
     cluster_sync_all();  // nobody exits while a peer may still st.async into its smem
-  }
-  if (p.dynamic) {
-    // exit protocol of the dynamic schedule: the last CTA to get here returns both words to zero.
-    // Every tile fetch of this CTA has returned (its value was consumed) before this barrier.
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      const uint32_t old = atomicAdd(p.sched_words + 1, 1u);
-      if (old == gridDim.x - 1) {
-        p.sched_words[0] = 0u;
-        p.sched_words[1] = 0u;
-      }
-    }
   }
 }
 

@@ -163,13 +163,15 @@ class FusionDefinition:
             kw["variant"] = L.VARIANT_GENERIC
         res: dict = {}
         want = set(m.outputs)
+        if m.flags & L.F_ADD_RESIDUAL:  # norm(x + residual), optional sum output
+            kw.update(residual=r["r"], want_sum="sum" in want, round_sum=bool(m.flags & L.F_ROUND_SUM))
         if m.op == L.OP_LAYERNORM_FWD:
-            y, mean, invstd = K.layer_norm_fwd(r["x"], r.get("w"), r.get("b"), m.eps, want_mean="mean" in want,
-                                               want_invstd="invstd" in want, **kw)
-            res = {"y": y, "mean": mean, "invstd": invstd}
+            o = K.layer_norm_fwd(r["x"], r.get("w"), r.get("b"), m.eps, want_mean="mean" in want,
+                                 want_invstd="invstd" in want, **kw)
+            res = {"y": o[0], "mean": o[1], "invstd": o[2], "sum": o[3] if len(o) > 3 else None}
         elif m.op == L.OP_RMSNORM_FWD:
-            y, stat = K.rms_norm_fwd(r["x"], r.get("w"), m.eps, stat_is_rms=bool(m.flags & L.F_STAT_IS_RMS), **kw)
-            res = {"y": y, "rms": stat, "invstd": stat}
+            o = K.rms_norm_fwd(r["x"], r.get("w"), m.eps, stat_is_rms=bool(m.flags & L.F_STAT_IS_RMS), **kw)
+            res = {"y": o[0], "rms": o[1], "invstd": o[1], "sum": o[2] if len(o) > 2 else None}
         elif m.op in (L.OP_SOFTMAX_FWD, L.OP_LOGSOFTMAX_FWD):
             res = {"y": K.softmax_fwd(r["x"], log=m.op == L.OP_LOGSOFTMAX_FWD, **kw)}
         elif m.op in (L.OP_SOFTMAX_BWD, L.OP_LOGSOFTMAX_BWD):

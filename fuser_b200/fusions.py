@@ -279,3 +279,66 @@ def softmax_bwd_cpp(fd, dtype, log=False):
         s = fd.ops.broadcast(fd.ops.sum(g, dims=[1]), is_broadcast_dim=[False, True])
         dx = fd.ops.sub(g, fd.ops.mul(yf, s))
     fd.add_output(_down(fd, dx, dtype))
+
+
+# ---- forward norms with a fused residual add ------------------------------
+def add_layernorm_fwd_py(fd, dtype, eps=1e-5):
+    """benchmarks/python/test_dropout_layernorm_fwd.py:18-76 with the dropout removed (p = 0):
+    inputs (input1, input2, weights, bias) → outputs (layernorm(input2 + input1), mean[M], invstd[M,1])."""
+    T2 = fd.define_tensor(shape=[-1, -1], contiguity=[True, True], dtype=dtype, is_cpu=False)
+    T3 = fd.define_tensor(shape=[-1, -1], contiguity=[True, True], dtype=dtype, is_cpu=False)
+    T1 = fd.define_tensor(shape=[-1], contiguity=[True], dtype=dtype, is_cpu=False)
+    T0 = fd.define_tensor(shape=[-1], contiguity=[True], dtype=dtype, is_cpu=False)
+    T0, T1, T2, T3 = (_up(fd, t, dtype) for t in (T0, T1, T2, T3))
+    T16 = fd.ops.add(T3, T2)
+    T17, T18 = fd.ops.var_mean(T16, dims=[1], correction=0, keepdim=False)
+    T22 = fd.ops.broadcast_in_dim(T17, shape=[T2.size(0), 1], broadcast_dims=[0])
+    T26 = fd.ops.broadcast_in_dim(T18, shape=[T2.size(0), 1], broadcast_dims=[0])
+    S27 = fd.define_scalar(eps, dtype=DataType.Double)
+    T29 = fd.ops.rsqrt(fd.ops.add(T22, S27))
+    T34 = fd.ops.sub(T16, fd.ops.broadcast_in_dim(T26, shape=T2.shape(), broadcast_dims=[0, 1]))
+    T39 = fd.ops.mul(T34, fd.ops.broadcast_in_dim(T29, shape=T2.shape(), broadcast_dims=[0, 1]))
+    T45 = fd.ops.mul(T39, fd.ops.broadcast_in_dim(T1, shape=T2.shape(), broadcast_dims=[1]))
+    T51 = fd.ops.add(T45, fd.ops.broadcast_in_dim(T0, shape=T2.shape(), broadcast_dims=[1]))
+    fd.add_output(_down(fd, T51, dtype))
+    fd.add_output(T18)
+    fd.add_output(T29)
+
+
+def add_rmsnorm_fwd_py(fd, dtype, eps=1e-5):
+    """benchmarks/python/test_dropout_rmsnorm_fwd.py:18-82 with the dropout removed:
+    inputs (input1, input2, weights) → outputs (rmsnorm(input2 + input1), rms[M,1])."""
+    T0 = fd.define_tensor(shape=[-1, -1], contiguity=[True, True], dtype=dtype, is_cpu=False)
+    T2 = fd.define_tensor(shape=[-1, -1], contiguity=[True, True], dtype=dtype, is_cpu=False)
+    T1 = fd.define_tensor(shape=[-1], contiguity=[True], dtype=dtype, is_cpu=False)
+    T0, T1, T2 = (_up(fd, t, dtype) for t in (T0, T1, T2))
+    V6 = T0.shape()
+    T15 = fd.ops.add(T2, T0)
+    T17 = fd.ops.pow(T15, fd.define_scalar(2.0, dtype=DataType.Double))
+    T18 = fd.ops.sum(T17, dims=[1], keepdim=False, dtype=DataType.Null)
+    T22 = fd.ops.broadcast_in_dim(T18, shape=[T0.size(0), 1], broadcast_dims=[0])
+    T25 = fd.ops.mul(T22, fd.ops.reciprocal(T0.size(1)))
+    T28 = fd.ops.sqrt(fd.ops.add(T25, fd.define_scalar(eps, dtype=DataType.Double)))
+    T35 = fd.ops.reciprocal(fd.ops.broadcast_in_dim(T28, shape=V6, broadcast_dims=[0, 1]))
+    T36 = fd.ops.mul(T15, T35)
+    T42 = fd.ops.mul(fd.ops.broadcast_in_dim(T1, shape=V6, broadcast_dims=[1]), T36)
+    fd.add_output(_down(fd, T42, dtype))
+    fd.add_output(T28)
+
+
+def rmsnorm_add_thunder(fd, dtype, eps=1e-5):
+    """benchmarks/python/torch_ops.py:76-83 (the op of test_rmsnorm_add_fwd.py) as a per-op trace:
+    every torch op's result is cast back to the io dtype, so the norm sees the *rounded* sum;
+    inputs (hidden, weight, residual) → outputs (weight * normed, hidden + residual)."""
+    H = fd.define_tensor(shape=[-1, -1], contiguity=[True, True], dtype=dtype, is_cpu=False)
+    W = fd.define_tensor(shape=[-1], contiguity=[True], dtype=dtype, is_cpu=False)
+    R = fd.define_tensor(shape=[-1, -1], contiguity=[True, True], dtype=dtype, is_cpu=False)
+    s = _down(fd, fd.ops.add(_up(fd, H, dtype), _up(fd, R, dtype)), dtype)   # hidden_states + residual
+    sf = _up(fd, s, dtype)
+    sq = fd.ops.mul(sf, sf)
+    ms = fd.ops.mul(fd.ops.sum(sq, dims=[1], keepdim=True, dtype=DataType.Null), fd.ops.reciprocal(H.size(1)))
+    inv = fd.ops.rsqrt(fd.ops.add(ms, fd.define_scalar(eps, dtype=DataType.Double)))
+    normed = fd.ops.mul(sf, fd.ops.broadcast_in_dim(inv, shape=H.shape(), broadcast_dims=[0, 1]))
+    y = fd.ops.mul(fd.ops.broadcast_in_dim(_up(fd, W, dtype), shape=H.shape(), broadcast_dims=[1]), normed)
+    fd.add_output(_down(fd, y, dtype))
+    fd.add_output(s)

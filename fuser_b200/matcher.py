@@ -407,6 +407,21 @@ def _has_intermediate_round(fd) -> bool:
     return False
 
 
+def _sum_is_rounded(fd) -> bool:
+    """The residual sum is cast to a reduced-precision dtype and that rounded value feeds further
+    arithmetic (a bf16 ``hidden + residual`` traced ahead of the norm, torch_ops.py:76-83)."""
+    consumed = set()
+    for v in fd._vals:
+        for a in v.args:
+            consumed.add(a.id)
+    for v in fd._vals:
+        if isinstance(v, Tensor) and v.op == "cast" and v.dtype in REDUCED and v.id in consumed:
+            src = v.args[0]
+            if isinstance(src, Tensor) and src.op == "add":
+                return True
+    return False
+
+
 def match_fusion(fd) -> Match:
     """Classify the recorded fusion or raise Unmatchable."""
     if not fd._outputs:
@@ -526,6 +541,50 @@ def match_fusion(fd) -> Match:
                         roles["b"] = I(b)
                     return Match(L.OP_LAYERNORM_FWD, flags, eps, io, roles, names, description="layer_norm")
         raise Unmatchable("single-input fusion is not rms_norm / layer_norm / softmax")
+
+    # ---- forward norms with a fused residual add: two matrix inputs, no statistics ----
+    if n_m == 2 and n_s == 0 and n_v <= 2:
+        x, res = mats[0], mats[1]  # the sum is symmetric: either order is the same segment
+        rflags = L.F_ADD_RESIDUAL | (L.F_ROUND_SUM if _sum_is_rounded(fd) else 0)
+        for eps in eps_list:
+            e = ops._scalar(float(eps))
+
+            def with_sum(build):
+                s_ = ops.add(T(x), T(res))
+                out = build(s_)
+                out["sum"] = s_
+                return out
+
+            if n_v <= 1:
+                w = vecs[0] if n_v == 1 else None
+                names = try_candidate(lambda: with_sum(lambda s_: def_rms_norm_fwd(ops, s_, T(w) if w else None, e)), {})
+                if names and any(nm in ("y", "invstd", "rms") for nm in names):
+                    if "rms" in names and "invstd" in names:
+                        raise Unmatchable("both rms and invstd requested")
+                    flags = rflags | (L.F_HAS_WEIGHT if w else 0) | (L.F_STAT_IS_RMS if "rms" in names else 0)
+                    flags |= L.F_OUT_SUM if "sum" in names else 0
+                    roles = {"x": I(x), "r": I(res)}
+                    if w:
+                        roles["w"] = I(w)
+                    return Match(L.OP_RMSNORM_FWD, flags, eps, io, roles, names, description="rms_norm(x + residual)")
+            combos = [(None, None)]
+            if n_v == 1:
+                combos = [(vecs[0], None)]
+            elif n_v == 2:
+                combos = [(vecs[0], vecs[1]), (vecs[1], vecs[0])]
+            for w, b in combos:
+                names = try_candidate(lambda: with_sum(
+                    lambda s_: def_layer_norm_fwd(ops, s_, T(w) if w else None, T(b) if b else None, e)), {})
+                if names and any(nm in ("y", "mean", "invstd") for nm in names):
+                    flags = rflags | (L.F_HAS_WEIGHT if w else 0) | (L.F_HAS_BIAS if b else 0)
+                    flags |= L.F_OUT_SUM if "sum" in names else 0
+                    roles = {"x": I(x), "r": I(res)}
+                    if w:
+                        roles["w"] = I(w)
+                    if b:
+                        roles["b"] = I(b)
+                    return Match(L.OP_LAYERNORM_FWD, flags, eps, io, roles, names,
+                                 description="layer_norm(x + residual)")
 
     # ---- backward ops: two matrix inputs ----
     if n_m == 2:

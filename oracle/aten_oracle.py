@@ -165,6 +165,49 @@ def rms_norm_fwd_python(x, weight, eps: float):
     return t29.to(io), t15
 
 
+# ---------------------------------------------------------------------------
+# forward norms with a fused residual add
+# ---------------------------------------------------------------------------
+def residual_sum(x, residual, round_sum: bool):
+    """``x + residual`` the way the fused-add fusions evaluate it: both operands cast to Float, one
+    fp32 add (benchmarks/python/test_dropout_layernorm_fwd.py:47-56, T16 = add(T3, T15) with the
+    dropout removed; test_dropout_rmsnorm_fwd.py T15). Returns (value the norm sees, sum in the io
+    dtype). ``round_sum``: the norm sees the sum *after* its cast to the io dtype — what a
+    reduced-precision ``hidden_states + residual`` feeding the norm gives
+    (benchmarks/python/torch_ops.py:76-83 traced through Thunder keeps that cast pair)."""
+    s = _up(x) + _up(residual)
+    s_io = s.to(x.dtype)
+    return (_up(s_io) if round_sum else s), s_io
+
+
+def add_rms_norm_fwd(x, residual, weight, eps: float, round_sum: bool = False, python: bool = False):
+    """rms_norm(x + residual): (y, stat, sum). ``python`` selects the Thunder spelling (rms statistic)."""
+    s, s_io = residual_sum(x, residual, round_sum)
+    if python:
+        w = weight if weight is not None else torch.ones(x.shape[-1], dtype=x.dtype)
+        y, stat = rms_norm_fwd_python(s, w, eps)
+    else:
+        y, stat = rms_norm_fwd(s, weight, eps)
+    return y.to(x.dtype), stat, s_io
+
+
+def add_layer_norm_fwd(x, residual, weight, bias, eps: float, round_sum: bool = False):
+    """layer_norm(x + residual): (y, mean, invstd, sum)."""
+    s, s_io = residual_sum(x, residual, round_sum)
+    y, mean, invstd = layer_norm_fwd(s, weight, bias, eps)
+    return y.to(x.dtype), mean, invstd, s_io
+
+
+def rmsnorm_add_eager(x, weight, residual, eps: float = 1e-5):
+    """benchmarks/python/torch_ops.py:76-83 verbatim (every op in the io dtype, as eager runs it)."""
+    hidden_states = x + residual
+    residual = hidden_states
+    variance = hidden_states.pow(2).mean(-1, keepdim=True)
+    hidden_states = hidden_states * torch.rsqrt(variance + eps)
+    hidden_states = weight * hidden_states
+    return hidden_states, residual
+
+
 def softmax_fwd(x, dim: int = -1):
     """csrc/ops/normalization.cpp:169-189 / benchmarks/python/test_softmax_fwd.py:14-42."""
     io = x.dtype

@@ -2,7 +2,7 @@
 """Time single ops at arbitrary shapes (back-to-back launches, rotating inputs > L2, CUDA events).
 
     python scripts/kbench.py "ln_bwd:32768x12288:bf16[:ENV=V,ENV=V]" ...
-ops: rms_fwd ln_fwd sm_fwd sm_bwd rms_bwd rms_bwd_dx ln_bwd ln_bwd_dx copy (torch copy_, 1 read + 1 write: the
+ops: rms_fwd add_rms_fwd add_ln_fwd ln_fwd sm_fwd sm_bwd rms_bwd rms_bwd_dx ln_bwd ln_bwd_dx copy (torch copy_, 1 read + 1 write: the
 same-size calibration of what the memory system gives a plain streaming kernel)
 """
 import os
@@ -16,12 +16,13 @@ from bench import measured_peak  # noqa: E402
 from fuser_b200 import ops  # noqa: E402
 
 KEYS = ["B200NORM_TPR", "B200NORM_GROUPS", "B200NORM_DEPTH", "B200NORM_TILE_ROWS", "B200NORM_CLUSTER",
-        "B200NORM_BWD_REREAD", "B200NORM_NO_FUSED_FINISH", "B200NORM_NO_PDL", "B200NORM_NO_PSMEM", "B200NORM_COOP", "B200NORM_STATIC"]
+        "B200NORM_BWD_REREAD", "B200NORM_NO_FUSED_FINISH", "B200NORM_NO_PDL", "B200NORM_NO_PSMEM", "B200NORM_COOP", "B200NORM_STATIC", "B200NORM_POOL"]
 DT = {"bf16": torch.bfloat16, "f32": torch.float32, "f16": torch.float16}
 
 
 def algbytes(op, m, n, s):
-    return {"copy": s * 2 * m * n, "rms_fwd": s * (2 * m * n + n) + 4 * m, "ln_fwd": s * 2 * (m * n + n) + 8 * m, "sm_fwd": s * 2 * m * n,
+    return {"add_rms_fwd": s * (4 * m * n + n) + 4 * m, "add_ln_fwd": s * (4 * m * n + 2 * n) + 8 * m,
+            "copy": s * 2 * m * n, "rms_fwd": s * (2 * m * n + n) + 4 * m, "ln_fwd": s * 2 * (m * n + n) + 8 * m, "sm_fwd": s * 2 * m * n,
             "sm_bwd": s * 3 * m * n, "rms_bwd": s * (3 * m * n + 2 * n) + 4 * m, "rms_bwd_dx": s * (3 * m * n + 2 * n) + 4 * m,
             "ln_bwd": s * 3 * (m * n + n) + 8 * m, "ln_bwd_dx": s * 3 * (m * n + n) + 8 * m}[op]
 
@@ -65,6 +66,8 @@ def main():
             fns = {
                 "copy": lambda i: aux["out"].copy_(xs[i]),
                 "rms_fwd": lambda i: ops.rms_norm_fwd(xs[i], w, 1e-5),
+                "add_rms_fwd": lambda i: ops.rms_norm_fwd(xs[i], w, 1e-5, residual=dys[i], want_sum=True),
+                "add_ln_fwd": lambda i: ops.layer_norm_fwd(xs[i], w, w, 1e-5, residual=dys[i], want_sum=True),
                 "ln_fwd": lambda i: ops.layer_norm_fwd(xs[i], w, w, 1e-5),
                 "sm_fwd": lambda i: ops.softmax_fwd(xs[i]),
                 "sm_bwd": lambda i: ops.softmax_bwd(dys[i], aux["sm"][i]),

@@ -149,3 +149,30 @@ def test_reduction_sizes_follow_the_validator():
     rs = fd.reduction_sizes(ins)
     assert rs[1] == 16 and rs[2] == 16 and rs[0] >= 128
     assert get_tolerance(torch.float32, 4096) == pytest.approx((0.00012207, 0.00012207 * 0.01))
+
+
+@pytest.mark.parametrize("dt", DTS, ids=lambda d: d.name)
+def test_fused_residual_add_fusions_are_matched(dt):
+    """norm(x + residual): the dropout_{layernorm,rmsnorm}_fwd definitions without the dropout and
+    the rmsnorm_add op of torch_ops.py."""
+    m = build(F.add_layernorm_fwd_py, dt).segment()
+    assert (m.op, m.outputs, m.eps) == (L.OP_LAYERNORM_FWD, ["y", "mean", "invstd"], 1e-5)
+    assert m.flags & L.F_ADD_RESIDUAL and not (m.flags & (L.F_OUT_SUM | L.F_ROUND_SUM))
+    assert m.roles == {"x": 0, "r": 1, "w": 2, "b": 3}
+    m = build(F.add_rmsnorm_fwd_py, dt).segment()
+    assert (m.op, m.outputs) == (L.OP_RMSNORM_FWD, ["y", "rms"])
+    assert m.flags & L.F_ADD_RESIDUAL and m.flags & L.F_STAT_IS_RMS and not (m.flags & L.F_OUT_SUM)
+    assert m.roles == {"x": 0, "r": 1, "w": 2}
+    m = build(F.rmsnorm_add_thunder, dt).segment()
+    assert (m.op, m.outputs) == (L.OP_RMSNORM_FWD, ["y", "sum"])
+    assert m.flags & L.F_ADD_RESIDUAL and m.flags & L.F_OUT_SUM and m.roles == {"x": 0, "r": 2, "w": 1}
+    assert bool(m.flags & L.F_ROUND_SUM) == (dt is not DataType.Float)
+
+
+def test_add_of_two_matrices_alone_is_not_a_segment():
+    def just_add(fd):
+        a = fd.define_tensor(shape=[-1, -1], dtype=DataType.Float)
+        b = fd.define_tensor(shape=[-1, -1], dtype=DataType.Float)
+        fd.add_output(fd.ops.add(a, b))
+    with pytest.raises(UnsupportedSegment):
+        build(just_add).segment()

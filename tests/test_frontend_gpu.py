@@ -77,3 +77,22 @@ def test_executor_cache_and_3d_inputs():
         assert y.shape == x.shape and mean.shape == shape[:-1] + (1,)
     with pytest.raises(ValueError):
         fd.execute([x.float(), w, b])  # dtype differs from the definition
+
+
+@pytest.mark.parametrize("dt", list(DT), ids=lambda d: d.name)
+@pytest.mark.parametrize("shape", [(64, 768), (33, 4096), (7, 1987), (300, 2048)], ids=lambda s: f"{s[0]}x{s[1]}")
+def test_fused_residual_add_fusions_execute_and_validate(shape, dt):
+    """norm(x + residual) through FusionDefinition, expectation auto-inferred."""
+    m, n = shape
+    td = DT[dt]
+    g = torch.Generator().manual_seed(m * 3 + n)
+    x = torch.randn(m, n, generator=g).to(td).cuda()
+    r = torch.randn(m, n, generator=g).to(td).cuda()
+    w = torch.randn(n, generator=g).to(td).cuda()
+    b = torch.randn(n, generator=g).to(td).cuda()
+    auto_validate(build(F.add_layernorm_fwd_py, dt), [x, r, w, b])
+    auto_validate(build(F.add_rmsnorm_fwd_py, dt), [x, r, w])
+    y, s = auto_validate(build(F.rmsnorm_add_thunder, dt), [x, w, r])
+    ye, se = AO.rmsnorm_add_eager(x.cpu(), w.cpu(), r.cpu())
+    assert torch.equal(s.cpu(), se), "residual stream must be bit-exact"
+    AO.assert_close(y, ye, n, "rmsnorm_add vs eager")
