@@ -1069,6 +1069,10 @@ int b200norm_launch(const b200norm_desc* desc, const b200norm_tensor* inputs, in
     // CTA at wide rows) loses more to the pool tiles' ticket wait than it gains and stays static.
     const bool ln_plain = d.op == B200NORM_OP_LAYERNORM_FWD && !is_add_fwd(d);
     rp.dynamic = ln_plain ? 0 : (rp.nstreams > 1 ? 2 : 4);
+    // short kernels (C2 forward: 28 tiles per group, 47 us) gain nothing: the exit protocol's last
+    // atomic round trip and the few pool tiles cost what the balance wins
+    const int64_t tiles_per_group = ceil_div64(d.rows, plan.tile_rows) / ((int64_t)plan.grid * plan.groups);
+    if (rp.nstreams == 1 && tiles_per_group < 40) rp.dynamic = 0;
     if (int f = env_int("B200NORM_POOL")) rp.dynamic = f > 0 ? f : 4;  // 1 = everything past the first ring fill
     rp.sched_words = reinterpret_cast<uint32_t*>(workspace) + 2;
   }
