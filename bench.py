@@ -151,7 +151,7 @@ class ClockSampler:
 # the hot-path step for each workload, on device tensors, through the public ops API
 # ---------------------------------------------------------------------------
 class Step:
-    def __init__(self, kind, m, n, dtype, device, world, rank):
+    def __init__(self, kind, m, n, dtype, device, world, rank, collective="peer"):
         from fuser_b200 import ops, parallel
 
         self.ops, self.parallel = ops, parallel
@@ -166,7 +166,20 @@ class Step:
             dy = torch.randn(m, n, generator=g, dtype=torch.float32).to(dtype)
             self.sets.append((x.to(device), dy.to(device)))
         self.w = torch.randn(n, generator=g).to(dtype).to(device)
-        self.reducer = parallel.ColumnSumReducer(device=device) if world > 1 else None
+        # dgamma / dbeta across ranks: all-reduced inside the backward kernel over peer memory
+        # (PeerExchange); --collective nccl (or a box without P2P symmetric memory) uses the NCCL
+        # all-reduce of the fp32 partial sums instead
+        self.reducer, self.collective = None, "none"
+        if world > 1:
+            if collective in ("peer", "peer-fused"):
+                try:
+                    self.reducer = parallel.PeerExchange(max_cols=n, device=device, deferred=collective == "peer")
+                    self.collective = collective
+                except Exception as e:  # noqa: BLE001
+                    print(f"[bench] peer exchange unavailable ({e}); falling back to NCCL", file=sys.stderr)
+            if self.reducer is None:
+                self.reducer = parallel.ColumnSumReducer(device=device)
+                self.collective = "nccl"
         # saved statistics / forward outputs computed from the inputs (not random)
         self.saved = []
         for x, dy in self.sets:
@@ -200,8 +213,10 @@ class Step:
         if self.kind == "rmsnorm_fwd_bwd":
             rms = fwd_out[1] if fwd_out is not None else saved
             if self.world > 1:
-                prev = self.reducer.pending  # last step's dgamma: its all-reduce had a whole step to finish
-                dx, _ = self.parallel.rms_norm_bwd_sharded(dy, x, rms, self.w, self.reducer, stat_is_rms=True)
+                prev = self.reducer.pending  # NCCL: last step's dgamma — its all-reduce had a whole step to finish
+                dx, h = self.parallel.rms_norm_bwd_sharded(dy, x, rms, self.w, self.reducer, stat_is_rms=True)
+                if self.collective == "peer-fused":
+                    return dx, h.result()  # reduced inside the kernel: this step's dgamma, final
                 return dx, (prev.result() if prev is not None else None)
             return ops.rms_norm_bwd(dy, x, rms, self.w, stat_is_rms=True, centered=False)
         if self.kind == "softmax_fwd_bwd":
@@ -210,7 +225,9 @@ class Step:
             mean, invstd = saved
             if self.world > 1:
                 prev = self.reducer.pending
-                dx, _ = self.parallel.layer_norm_bwd_sharded(dy, x, mean, invstd, self.w, self.reducer)
+                dx, h = self.parallel.layer_norm_bwd_sharded(dy, x, mean, invstd, self.w, self.reducer)
+                if self.collective == "peer-fused":
+                    return dx, h.result()
                 return dx, (prev.result() if prev is not None else None)
             return ops.layer_norm_bwd(dy, x, mean, invstd, self.w)
         return None
@@ -360,6 +377,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200norm", choices=["b200norm", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--collective", default="peer", choices=["peer", "peer-fused", "nccl"],
+                    help="N > 1, dgamma/dbeta all-reduce: peer = published to peer memory by the backward kernel and "
+                         "combined by a one-CTA kernel a step later; peer-fused = entirely inside the backward kernel; "
+                         "nccl = NCCL all-reduce of the fp32 partial sums")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -412,7 +433,7 @@ def main():
         a, b = shard_rows(M, world, rank)  # the named multi-GPU config: row-sharded, total work fixed
         rows = b - a
         scaling = "strong"
-    step = Step(kind, rows, N, dtype, device, world, rank)
+    step = Step(kind, rows, N, dtype, device, world, rank, args.collective)
     byt = iobytes(kind, rows, N, es)
     step_bytes = sum(byt.values())
     total_bytes = step_bytes * world if scaling == "weak" else sum(iobytes(kind, M, N, es).values())
@@ -539,8 +560,14 @@ def main():
             "config": {"workload": desc, "rows_per_gpu": rows, "cols": N, "io_dtype": dtype_name,
                        "accumulate": "fp32",
                        "l2": f"inputs larger than L2 ({step.nsets} rotating input sets, {footprint / 1e6:.0f} MB)",
-                       "collective": "nccl allreduce of fp32 dgamma/dbeta partial sums, async (consumed one step later), cast after the reduce"
-                       if world > 1 else "none",
+                       "collective": {"none": "none",
+                                      "peer": "fp32 dgamma/dbeta sums published to NVLink peer memory by the backward kernel's "
+                                              "finishing CTAs; a one-CTA combine (P2P loads in rank order, cast) consumes them "
+                                              "one step later; no NCCL",
+                                      "peer-fused": "fp32 dgamma/dbeta sums all-reduced inside the backward kernel over NVLink "
+                                                    "peer memory (P2P stores / loads from the finishing CTAs), cast after the reduce",
+                                      "nccl": "nccl allreduce of fp32 dgamma/dbeta partial sums, async (consumed one step "
+                                              "later), cast after the reduce"}[step.collective],
                        "rows_per_s": (rows * world if scaling == "weak" else M) / (ms_per_step * 1e-3),
                        "pct_of_nominal_8TBs": 100.0 * value / world / 8000.0,
                        "pct_of_measured_peak": 100.0 * value / world / peak,

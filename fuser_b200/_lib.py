@@ -29,7 +29,8 @@ OK, ERR_UNSUPPORTED, ERR_BAD_ARG, ERR_NO_DEVICE, ERR_WORKSPACE, ERR_CUDA = 0, 1,
     OP_REDUCE_INNER,
     OP_REDUCE_OUTER,
     OP_FINALIZE_PARTIALS,
-) = range(11)
+    OP_PEER_COMBINE,
+) = range(12)
 OP_NAMES = [
     "layernorm_fwd",
     "layernorm_bwd",
@@ -42,6 +43,7 @@ OP_NAMES = [
     "reduce_inner",
     "reduce_outer",
     "finalize_partials",
+    "peer_combine",
 ]
 
 DT_F32, DT_BF16, DT_F16 = 0, 1, 2
@@ -62,6 +64,8 @@ F_OUT_INVSTD = 1 << 12
 F_ADD_RESIDUAL = 1 << 13
 F_OUT_SUM = 1 << 14
 F_ROUND_SUM = 1 << 15
+F_PEER_REDUCE = 1 << 16
+F_PEER_PUBLISH = 1 << 17
 
 VARIANT_AUTO, VARIANT_GENERIC, VARIANT_TMA, VARIANT_CLUSTER = 0, 1, 2, 3
 
@@ -74,6 +78,7 @@ EXPORTED_SYMBOLS = [
     "b200norm_last_error",
     "b200norm_variant_name",
     "b200norm_device_info",
+    "b200norm_register_peers",
     "b200norm_debug_set_timeline",
 ]
 
@@ -184,6 +189,8 @@ def load():
     lib.b200norm_variant_name.restype = C.c_char_p
     lib.b200norm_device_info.argtypes = [C.POINTER(C.c_int)] * 5
     lib.b200norm_device_info.restype = C.c_int
+    lib.b200norm_register_peers.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_size_t]
+    lib.b200norm_register_peers.restype = C.c_int
     lib.b200norm_debug_set_timeline.argtypes = [C.c_void_p]
     lib.b200norm_debug_set_timeline.restype = None
     if lib.b200norm_abi_version() != ABI_VERSION:
@@ -235,6 +242,15 @@ def workspace_bytes(desc: Desc) -> int:
 
 def launch_count() -> int:
     return int(load().b200norm_launch_count())
+
+
+def register_peers(world: int, rank: int, ptrs, nbytes: int) -> None:
+    """Register the peer-memory exchange buffers of the row-sharded backward (world = 0: unregister)."""
+    lib = load()
+    arr = (C.c_void_p * max(1, len(ptrs)))(*[C.c_void_p(int(p)) for p in ptrs])
+    rc = lib.b200norm_register_peers(world, rank, arr, nbytes)
+    if rc != 0:
+        raise B200NormError(rc, lib.b200norm_last_error().decode())
 
 
 def set_timeline(device_ptr) -> None:

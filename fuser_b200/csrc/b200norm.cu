@@ -30,6 +30,18 @@ thread_local char g_err[512] = "";
 std::atomic<uint64_t> g_launches{0};
 std::atomic<unsigned long long*> g_timeline{nullptr};
 
+// peer-memory exchange of the row-sharded backward (b200norm_register_peers)
+struct PeerState {
+  std::mutex mu;
+  int world = 0;
+  int rank = 0;
+  void* ptrs[kMaxPeers] = {};
+  size_t bytes = 0;
+  uint32_t epoch = 0;     // publishes so far; identical on every rank because all ranks issue the same sequence
+  uint32_t combined = 0;  // epochs whose sums have been combined (in-kernel or by OP_PEER_COMBINE)
+};
+PeerState g_peers;
+
 int fail(int code, const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -574,7 +586,35 @@ int launch_typed(const b200norm_desc& d, const Plan& plan, RowParams& rp, void* 
   cudaError_t err;
 
   if (plan.variant == B200NORM_VARIANT_GENERIC) {
-    if (d.op == B200NORM_OP_REDUCE_OUTER) {
+    if (want_cols && (d.flags & (B200NORM_F_PEER_REDUCE | B200NORM_F_PEER_PUBLISH)))
+      return fail(B200NORM_ERR_UNSUPPORTED, "peer reduce is only available on the ring kernels (aligned rows)");
+    if (d.op == B200NORM_OP_PEER_COMBINE) {
+      PeerCombineParams q;
+      memset(&q, 0, sizeof(q));
+      {
+        std::lock_guard<std::mutex> lock(g_peers.mu);
+        if (g_peers.world < 1) return fail(B200NORM_ERR_BAD_ARG, "PEER_COMBINE without b200norm_register_peers");
+        if (g_peers.combined >= g_peers.epoch) return fail(B200NORM_ERR_BAD_ARG, "PEER_COMBINE: nothing published");
+        const size_t need = (size_t)kPeerHeaderBytes + 2u * (size_t)d.rows * (size_t)d.cols * 4u;
+        if (need > g_peers.bytes || d.cols % 4 != 0)
+          return fail(B200NORM_ERR_WORKSPACE, "PEER_COMBINE: [%lld,%lld] does not match the exchange buffers",
+                      (long long)d.rows, (long long)d.cols);
+        q.world = g_peers.world;
+        q.rank = g_peers.rank;
+        for (int r = 0; r < g_peers.world; ++r) q.xchg[r] = static_cast<uint8_t*>(g_peers.ptrs[r]);
+        q.epoch = ++g_peers.combined;
+        q.slot_floats = (uint32_t)((g_peers.bytes - kPeerHeaderBytes) / 8 / 4 * 4);
+      }
+      q.K = (int32_t)d.rows;
+      q.N = (int32_t)d.cols;
+      q.out_a = dw;
+      q.out_b = db;
+      int ncta = (int)ceil_div64(d.rows * d.cols / 4, 512);
+      if (ncta > 32) ncta = 32;
+      if (ncta < 1) ncta = 1;
+      peer_combine_kernel<T><<<ncta, 512, 0, stream>>>(q);
+      g_launches++;
+    } else if (d.op == B200NORM_OP_REDUCE_OUTER) {
       dim3 grid((unsigned)ceil_div64(d.cols, 128), (unsigned)plan.nparts);
       generic_colsum_kernel<T, 0><<<grid, 128, 0, stream>>>(rp, plan.rows_per_split);
       g_launches++;
@@ -628,6 +668,29 @@ int launch_typed(const b200norm_desc& d, const Plan& plan, RowParams& rp, void* 
     if (it != bad_modes.end()) bad = it->second;
   }
   const bool allow_fused = want_cols && plan.block >= 128 && env_int("B200NORM_NO_FUSED_FINISH") == 0;
+  const bool peer = want_cols && (d.flags & (B200NORM_F_PEER_REDUCE | B200NORM_F_PEER_PUBLISH)) != 0;
+  const bool deferred = (d.flags & B200NORM_F_PEER_PUBLISH) != 0;
+  if (peer) {
+    // the exchange happens in the in-kernel finish: refuse before anything is enqueued if that path is closed
+    if (!allow_fused || (bad & 1))
+      return fail(B200NORM_ERR_UNSUPPORTED, "peer reduce needs the in-kernel finish (not available for this launch)");
+    std::lock_guard<std::mutex> lock(g_peers.mu);
+    if (g_peers.world < 1) return fail(B200NORM_ERR_BAD_ARG, "PEER_REDUCE without b200norm_register_peers");
+    const size_t need = (size_t)kPeerHeaderBytes + 2u * (size_t)K * (size_t)d.cols * 4u;
+    if (need > g_peers.bytes)
+      return fail(B200NORM_ERR_WORKSPACE, "exchange buffers hold %zu bytes, need %zu", g_peers.bytes, need);
+    if (deferred && g_peers.epoch - g_peers.combined >= 2)
+      return fail(B200NORM_ERR_BAD_ARG, "two publishes are outstanding: launch OP_PEER_COMBINE before the next one");
+    if (!deferred && g_peers.epoch != g_peers.combined)
+      return fail(B200NORM_ERR_BAD_ARG, "PEER_REDUCE with a publish outstanding: launch OP_PEER_COMBINE first");
+    rp.peer_world = g_peers.world;
+    rp.peer_rank = g_peers.rank;
+    rp.peer_deferred = deferred ? 1 : 0;
+    for (int q = 0; q < g_peers.world; ++q) rp.peer_xchg[q] = static_cast<uint8_t*>(g_peers.ptrs[q]);
+    rp.peer_epoch = ++g_peers.epoch;
+    rp.peer_slot_floats = (uint32_t)((g_peers.bytes - kPeerHeaderBytes) / 8 / 4 * 4);
+    if (!deferred) g_peers.combined = g_peers.epoch;
+  }
   const bool allow_pdl = env_int("B200NORM_NO_PDL") == 0;
   for (;;) {
     const bool fused = allow_fused && !(bad & 1);
@@ -694,7 +757,8 @@ int launch_typed(const b200norm_desc& d, const Plan& plan, RowParams& rp, void* 
     } else if (fused) {
       newbad |= 1;
     }
-    if (newbad == bad) return fail(B200NORM_ERR_CUDA + (int)err, "ring launch failed: %s", cudaGetErrorString(err));
+    if (newbad == bad || (peer && (newbad & 1)))
+      return fail(B200NORM_ERR_CUDA + (int)err, "ring launch failed: %s", cudaGetErrorString(err));
     bad = newbad;
     std::lock_guard<std::mutex> lock(mode_mu);
     bad_modes[(const void*)k] = bad;
@@ -751,6 +815,30 @@ int b200norm_abi_version(void) { return B200NORM_ABI_VERSION; }
 const char* b200norm_last_error(void) { return g_err; }
 
 uint64_t b200norm_launch_count(void) { return g_launches.load(); }
+
+int b200norm_register_peers(int world, int rank, void* const* exchange_ptrs, size_t exchange_bytes) {
+  std::lock_guard<std::mutex> lock(g_peers.mu);
+  if (world == 0) {
+    g_peers.world = 0;
+    g_peers.bytes = 0;
+    return B200NORM_OK;
+  }
+  if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world || exchange_ptrs == nullptr)
+    return fail(B200NORM_ERR_BAD_ARG, "register_peers: world %d (1..%d), rank %d", world, kMaxPeers, rank);
+  if (exchange_bytes < (size_t)kPeerHeaderBytes + 32)
+    return fail(B200NORM_ERR_BAD_ARG, "register_peers: exchange buffers too small (%zu bytes)", exchange_bytes);
+  for (int q = 0; q < world; ++q) {
+    if (exchange_ptrs[q] == nullptr || (reinterpret_cast<uintptr_t>(exchange_ptrs[q]) & 255u) != 0)
+      return fail(B200NORM_ERR_BAD_ARG, "register_peers: buffer %d is null or not 256-byte aligned", q);
+  }
+  g_peers.world = world;
+  g_peers.rank = rank;
+  for (int q = 0; q < world; ++q) g_peers.ptrs[q] = exchange_ptrs[q];
+  g_peers.bytes = exchange_bytes;
+  g_peers.epoch = 0;  // the buffers are zero: epochs restart at 1
+  g_peers.combined = 0;
+  return B200NORM_OK;
+}
 
 void b200norm_debug_set_timeline(void* device_buf) { g_timeline.store(static_cast<unsigned long long*>(device_buf)); }
 
@@ -930,7 +1018,11 @@ int b200norm_launch(const b200norm_desc* desc, const b200norm_tensor* inputs, in
       }
       const bool want_dw = (d.flags & B200NORM_F_OUT_DW) != 0;
       const bool want_db = ln && (d.flags & B200NORM_F_OUT_DB) != 0;
-      if (want_dw || want_db) {
+      if ((want_dw || want_db) && (d.flags & B200NORM_F_PEER_PUBLISH)) {
+        if (d.flags & (B200NORM_F_PARTIALS_F32 | B200NORM_F_PEER_REDUCE))
+          return fail(B200NORM_ERR_BAD_ARG, "PEER_PUBLISH excludes PARTIALS_F32 and PEER_REDUCE");
+        // the sums go to the exchange slot only; OP_PEER_COMBINE produces the tensors
+      } else if (want_dw || want_db) {
         if (d.flags & B200NORM_F_PARTIALS_F32) {
           NEED_OUT(1);
           void* s = nullptr;
@@ -986,6 +1078,13 @@ int b200norm_launch(const b200norm_desc* desc, const b200norm_tensor* inputs, in
       } else {
         CHECK(bind_vec(outputs[oi++], d.cols, dt, "result", &dw));
       }
+      break;
+    }
+    case B200NORM_OP_PEER_COMBINE: {
+      if (d.rows < 1 || d.rows > 2) return fail(B200NORM_ERR_BAD_ARG, "peer_combine: rows (K) must be 1 or 2");
+      NEED_OUT((int)d.rows);
+      CHECK(bind_vec(outputs[oi++], d.cols, dt, "out0", &dw));
+      if (d.rows == 2) CHECK(bind_vec(outputs[oi++], d.cols, dt, "out1", &db));
       break;
     }
     case B200NORM_OP_FINALIZE_PARTIALS: {

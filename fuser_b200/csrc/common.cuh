@@ -165,6 +165,24 @@ __device__ __forceinline__ uint32_t atom_add_release_gpu(uint32_t* p, uint32_t v
   return old;
 }
 
+// system-scope release store / acquire load / volatile vector load for the peer-memory exchange
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ld_volatile_f4(const float4* p) {
+  float4 v;
+  asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
+
 // ----------------------------------------------------------------------------
 // named barriers (bar.sync id, nthreads) for sub-CTA consumer groups
 // ----------------------------------------------------------------------------

@@ -139,7 +139,7 @@ std::vector<at::Tensor> NormExecutor::allocateOutputs(const std::vector<at::Tens
       if (f & B200NORM_F_OUT_DX) out.push_back(at::empty(in.at(1).sizes(), opts));
       const bool want_dw = (f & B200NORM_F_OUT_DW) != 0;
       const bool want_db = ln && (f & B200NORM_F_OUT_DB) != 0;
-      if (want_dw || want_db) {
+      if ((want_dw || want_db) && !(f & B200NORM_F_PEER_PUBLISH)) {  // a publish leaves the sums in the exchange slot
         if (f & B200NORM_F_PARTIALS_F32) {
           out.push_back(at::empty({ln ? 2 : 1, cols}, f32));
         } else {
@@ -184,6 +184,12 @@ std::vector<at::Tensor> NormExecutor::run(const std::vector<at::Tensor>& inputs,
     rows = lead.size(0);
     cols = lead.size(1);
     dt = dtype_id(outputs[0].scalar_type());
+  } else if (spec_.op == B200NORM_OP_PEER_COMBINE) {
+    // inputs: any CUDA tensor of the device (the exchange buffer; not passed on); K preallocated outputs [N]
+    if (outputs.empty()) raise_msg(B200NORM_ERR_BAD_ARG, "peer_combine needs preallocated outputs");
+    rows = (int64_t)outputs.size();
+    cols = outputs[0].numel();
+    dt = dtype_id(outputs[0].scalar_type());
   } else {
     cols = lead.dim() > 0 ? lead.size(-1) : 1;
     rows = cols > 0 ? lead.numel() / cols : 0;
@@ -207,7 +213,7 @@ std::vector<at::Tensor> NormExecutor::run(const std::vector<at::Tensor>& inputs,
   std::vector<b200norm_tensor> in_args, out_args;
   in_args.reserve(inputs.size());
   out_args.reserve(outputs.size());
-  for (size_t i = 0; i < inputs.size(); ++i) {
+  for (size_t i = 0; i < inputs.size() && spec_.op != B200NORM_OP_PEER_COMBINE; ++i) {
     keep.push_back((int)i < n_mat_in ? as_rows(inputs[i], cols) : inputs[i].reshape({-1}));
     in_args.push_back(as_arg(keep.back()));
   }

@@ -49,7 +49,7 @@ __device__ __forceinline__ void grid_barrier(uint32_t* word) {
 // (RS = threads / CW); all its loads are issued before the first add (one L2 round trip),
 // row-splits are combined by shuffles inside a warp and through shared memory across warps.
 template <typename T, int CW>
-__device__ __forceinline__ void finish_columns(const RowParams& p, int K, int F, int nct) {
+__device__ __forceinline__ void finish_columns(const RowParams& p, int K, int F, int nct, float* sums_out) {
   constexpr int kMaxLoads = 10;
   const int tx = threadIdx.x % CW;
   const int ty = threadIdx.x / CW;
@@ -101,13 +101,112 @@ __device__ __forceinline__ void finish_columns(const RowParams& p, int K, int F,
       if (e < K * p.cols) {
         float r = 0.f;
         for (int w = 0; w < nwarps; ++w) r += smf[w * CW * 4 + threadIdx.x];
-        if (p.sums_out != nullptr) {
-          p.sums_out[e] = r;
+        if (sums_out != nullptr) {
+          sums_out[e] = r;
         } else {
           const int k2 = e / p.cols;
           T* o = static_cast<T*>(k2 == 0 ? p.dw_out : p.db_out);
           if (o != nullptr) o[e - k2 * p.cols] = IO<T>::from_f32(r);
         }
+      }
+    }
+  }
+}
+
+// The all-reduce of the column sums, inside the backward kernel (row-sharded backward on the GPUs
+// of one box; reference mechanism: lowerToAllreduce + postAllreduce, host_ir/lower_to_communication.cpp
+// :266-284, multidevice/post_communication.cpp:288-313 — a separate NCCL kernel there).
+// On entry this rank's [K][N] fp32 sums are being written to its exchange slot by all CTAs.
+//   1. grid barrier: the slot is complete; one CTA publishes the launch epoch into every rank's
+//      flag word for this rank (st.release.sys over NVLink);
+//   2. every CTA waits until all ranks' flags in ITS OWN memory carry the epoch (local polling);
+//   3. every rank adds the P slots in rank order — the same order everywhere, so all ranks get
+//      the same bits — and casts once, as on a single GPU.
+// Two slots alternate between launches: a rank may run one launch ahead of a peer that is still
+// reading, never two (its next epoch flag is only published after it finished reading).
+template <typename T>
+__device__ __forceinline__ void peer_allreduce_columns(const RowParams& p, int K, int nct) {
+  const int P = p.peer_world;
+  const uint32_t epoch = p.peer_epoch;
+  // The slot is local memory: device-scope visibility (this rank's L2, which is also what the peers'
+  // NVLink reads go through) is enough for the writers; the system-scope release is the flag store.
+  // (A system-scope fence by every thread here cost several microseconds per launch.)
+  __threadfence();
+  __syncthreads();
+  grid_barrier(p.sync_words);
+  if (blockIdx.x == 0 && (int)threadIdx.x < P) {
+    st_release_sys(reinterpret_cast<uint32_t*>(p.peer_xchg[threadIdx.x]) + p.peer_rank, epoch);
+  }
+  if ((int)threadIdx.x < P) {
+    const uint32_t* flag = reinterpret_cast<const uint32_t*>(p.peer_xchg[p.peer_rank]) + threadIdx.x;
+    Watchdog wd;
+    while ((int32_t)(ld_acquire_sys(flag) - epoch) < 0) wd.tick();
+  }
+  __syncthreads();
+  const int total4 = K * p.cols / 4;
+  const size_t slot = (size_t)(epoch & 1u) * p.peer_slot_floats;
+  for (int i = blockIdx.x * nct + threadIdx.x; i < total4; i += gridDim.x * nct) {
+    float4 a = ld_volatile_f4(reinterpret_cast<const float4*>(
+                                  reinterpret_cast<const float*>(p.peer_xchg[0] + kPeerHeaderBytes) + slot) + i);
+    for (int q = 1; q < P; ++q) {
+      const float4 v = ld_volatile_f4(reinterpret_cast<const float4*>(
+                                          reinterpret_cast<const float*>(p.peer_xchg[q] + kPeerHeaderBytes) + slot) + i);
+      a.x += v.x;
+      a.y += v.y;
+      a.z += v.z;
+      a.w += v.w;
+    }
+    const int e = i * 4;
+    const int k2 = e / p.cols;
+    const int c = e - k2 * p.cols;
+    if (p.sums_out != nullptr) {
+      *reinterpret_cast<float4*>(p.sums_out + e) = a;
+    } else {
+      T* o = static_cast<T*>(k2 == 0 ? p.dw_out : p.db_out);
+      if (o != nullptr) {
+        o[c] = IO<T>::from_f32(a.x);
+        o[c + 1] = IO<T>::from_f32(a.y);
+        o[c + 2] = IO<T>::from_f32(a.z);
+        o[c + 3] = IO<T>::from_f32(a.w);
+      }
+    }
+  }
+  // tell the peers their slots of this epoch have been read (only a later PEER_PUBLISH looks at it)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t old = atom_add_acq_rel_gpu(p.sync_words + 1, 1u);
+    if (old == gridDim.x - 1) {
+      p.sync_words[1] = 0u;
+      for (int q = 0; q < P; ++q) {
+        st_release_sys(reinterpret_cast<uint32_t*>(p.peer_xchg[q] + kPeerConsumedOffset) + p.peer_rank, epoch);
+      }
+    }
+  }
+}
+
+// Deferred flavour (B200NORM_F_PEER_PUBLISH): nobody waits for a peer inside the backward.
+// Before the slot is overwritten every peer must have consumed what it held two publishes ago
+// (normally true long since); after the slot is written the last CTA to get there tells every peer.
+__device__ __forceinline__ void peer_wait_consumed(const RowParams& p) {
+  if (p.peer_epoch > 2u) {
+    if ((int)threadIdx.x < p.peer_world) {
+      const uint32_t* flag =
+          reinterpret_cast<const uint32_t*>(p.peer_xchg[p.peer_rank] + kPeerConsumedOffset) + threadIdx.x;
+      Watchdog wd;
+      while ((int32_t)(ld_acquire_sys(flag) - (p.peer_epoch - 2u)) < 0) wd.tick();
+    }
+    __syncthreads();
+  }
+}
+__device__ __forceinline__ void peer_publish(const RowParams& p) {
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t old = atom_add_acq_rel_gpu(p.sync_words + 1, 1u);
+    if (old == gridDim.x - 1) {
+      p.sync_words[1] = 0u;  // next used by the next launch
+      for (int q = 0; q < p.peer_world; ++q) {
+        st_release_sys(reinterpret_cast<uint32_t*>(p.peer_xchg[q]) + p.peer_rank, p.peer_epoch);
       }
     }
   }
@@ -284,10 +383,24 @@ __global__ void __launch_bounds__(kMaxBlock, 1) norm_bwd_ring_kernel(const RowPa
       grid_barrier(p.sync_words);
       tl_mark(p, 5);
       const int F = K * (p.cols / 4);  // float4 columns of the [K][N] result
+      // several GPUs: this rank's sums go to its exchange slot instead of being cast
+      float* sums_dst = p.sums_out;
+      if (p.peer_world > 0) {
+        sums_dst = reinterpret_cast<float*>(p.peer_xchg[p.peer_rank] + kPeerHeaderBytes) +
+                   (size_t)(p.peer_epoch & 1u) * p.peer_slot_floats;
+        if (p.peer_deferred) peer_wait_consumed(p);  // the slot's previous content (two publishes ago) was read
+      }
       if ((F + 7) / 8 <= 2 * (int)gridDim.x) {
-        finish_columns<T, 8>(p, K, F, nct);
+        finish_columns<T, 8>(p, K, F, nct, sums_dst);
       } else {
-        finish_columns<T, 32>(p, K, F, nct);
+        finish_columns<T, 32>(p, K, F, nct, sums_dst);
+      }
+      if (p.peer_world > 0) {
+        if (p.peer_deferred) {
+          peer_publish(p);
+        } else {
+          peer_allreduce_columns<T>(p, K, nct);
+        }
       }
     }
   }

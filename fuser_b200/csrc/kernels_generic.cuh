@@ -299,4 +299,65 @@ __global__ void __launch_bounds__(32 * kFinY) finalize_partials_kernel(const flo
   }
 }
 
+// OP_PEER_COMBINE: finish a published epoch. A few CTAs (one remote load per thread and peer — the
+// loads are latency bound): wait until every rank's "published" flag in this rank's header carries
+// the epoch (normally long true), add the P slots in rank order (the same order on every rank:
+// identical bits everywhere), cast once; the last CTA to finish tells every peer that its slot has
+// been consumed (counter in this rank's header, word 32).
+struct PeerCombineParams {
+  int32_t world, rank, K, N;
+  uint32_t epoch;
+  uint32_t slot_floats;
+  uint8_t* xchg[kMaxPeers];
+  void* out_a;
+  void* out_b;
+};
+template <typename T>
+__global__ void __launch_bounds__(512) peer_combine_kernel(const PeerCombineParams q) {
+  if ((int)threadIdx.x < q.world) {
+    const uint32_t* flag = reinterpret_cast<const uint32_t*>(q.xchg[q.rank]) + threadIdx.x;
+    Watchdog wd;
+    while ((int32_t)(ld_acquire_sys(flag) - q.epoch) < 0) wd.tick();
+  }
+  __syncthreads();
+  const size_t slot = (size_t)(q.epoch & 1u) * q.slot_floats;
+  const int total = q.K * q.N;
+  if (q.N % 4 == 0) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total / 4; i += gridDim.x * blockDim.x) {
+      float4 a = ld_volatile_f4(reinterpret_cast<const float4*>(
+                                    reinterpret_cast<const float*>(q.xchg[0] + kPeerHeaderBytes) + slot) + i);
+      for (int r = 1; r < q.world; ++r) {
+        const float4 v = ld_volatile_f4(reinterpret_cast<const float4*>(
+                                            reinterpret_cast<const float*>(q.xchg[r] + kPeerHeaderBytes) + slot) + i);
+        a.x += v.x;
+        a.y += v.y;
+        a.z += v.z;
+        a.w += v.w;
+      }
+      const int e = i * 4;
+      const int k2 = e / q.N;
+      const int c = e - k2 * q.N;
+      T* o = static_cast<T*>(k2 == 0 ? q.out_a : q.out_b);
+      if (o != nullptr) {
+        o[c] = IO<T>::from_f32(a.x);
+        o[c + 1] = IO<T>::from_f32(a.y);
+        o[c + 2] = IO<T>::from_f32(a.z);
+        o[c + 3] = IO<T>::from_f32(a.w);
+      }
+    }
+  }
+  __syncthreads();
+  __shared__ uint32_t last;
+  if (threadIdx.x == 0) {
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(q.xchg[q.rank] + 128);
+    const uint32_t old = atom_add_acq_rel_gpu(cnt, 1u);
+    last = old == gridDim.x - 1 ? 1u : 0u;
+    if (last) *cnt = 0u;
+  }
+  __syncthreads();
+  if (last && (int)threadIdx.x < q.world) {
+    st_release_sys(reinterpret_cast<uint32_t*>(q.xchg[threadIdx.x] + kPeerConsumedOffset) + q.rank, q.epoch);
+  }
+}
+
 }  // namespace b200norm

@@ -33,6 +33,9 @@ extern __shared__ __align__(128) uint8_t smem_raw[];
 constexpr int kMaxWarpsPerGroup = 16;
 constexpr int kMaxCluster = 16;
 constexpr int kRedNV = 4;  // max floats reduced at once
+constexpr int kMaxPeers = 8;         // GPUs of one box
+constexpr int kPeerHeaderBytes = 256;  // uint32 published[16] | uint32 consumed[16] | pad
+constexpr int kPeerConsumedOffset = 64;
 constexpr int kSchedTableInts = 32;  // stage -> tile index table of the dynamic schedule (= max stages)
 constexpr int kRedSetBytes = kRedNV * kMaxWarpsPerGroup * 4;  // one slot set: [kRedNV][16 warps]
 constexpr int kClsSetBytes = kRedNV * kMaxCluster * 4;        // one cluster slot set: [16 ranks][kRedNV]
@@ -97,6 +100,17 @@ struct RowParams {
   void* dw_out;            // io dtype [N] or nullptr
   void* db_out;            // io dtype [N] or nullptr
   float* sums_out;         // fp32 [K][N] or nullptr (multi-GPU partial sums, no cast)
+  // Row-sharded backward over several GPUs of one box (B200NORM_F_PEER_REDUCE): the finishing CTAs
+  // exchange the fp32 column sums through peer memory (NVLink / NVSwitch P2P) and every rank
+  // produces the cast dgamma / dbeta itself — the all-reduce is part of this kernel.
+  // peer_xchg[q] = rank q's exchange buffer: 16 uint32 epoch flags (one per source rank), padded to
+  // kPeerHeaderBytes, then two [K][N] fp32 slots used alternately by consecutive launches.
+  int32_t peer_world;  // 0 = single GPU
+  int32_t peer_rank;
+  int32_t peer_deferred;  // 1: publish only (B200NORM_F_PEER_PUBLISH); the combine is a later launch
+  uint32_t peer_epoch;  // launch sequence number, identical on every rank, starts at 1
+  uint32_t peer_slot_floats;  // distance between the two slots (half of the buffer past the header)
+  uint8_t* peer_xchg[kMaxPeers];
   // tuning aid (b200norm_debug_set_timeline): per-CTA %globaltimer marks, 8 slots per CTA; nullptr = off
   unsigned long long* timeline;
   // dynamic tile scheduling (forward-type kernels, cluster size 1): the last quarter of the tiles

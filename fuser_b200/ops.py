@@ -123,7 +123,9 @@ def softmax_bwd(dy, y, *, log=False, round_rowsum=False, variant=L.VARIANT_AUTO,
     return dx
 
 
-def _norm_bwd(op, dy, x, stats, weight, flags, output_mask, partials_f32, variant, cluster_size):
+def _norm_bwd(op, dy, x, stats, weight, flags, output_mask, partials_f32, variant, cluster_size, peer_reduce=False):
+    """``peer_reduce``: False | True ("fused": all-reduced inside this kernel) | "publish" (the sums are
+    only published to the peers; :func:`peer_combine` produces the tensors later)."""
     ln = op == L.OP_LAYERNORM_BWD
     want_dx, want_dw = bool(output_mask[0]), bool(output_mask[1]) and weight is not None
     want_db = ln and len(output_mask) > 2 and bool(output_mask[2])
@@ -131,11 +133,16 @@ def _norm_bwd(op, dy, x, stats, weight, flags, output_mask, partials_f32, varian
     flags |= (L.F_OUT_DX if want_dx else 0) | (L.F_OUT_DW if want_dw else 0) | (L.F_OUT_DB if want_db else 0)
     if partials_f32 and (want_dw or want_db):
         flags |= L.F_PARTIALS_F32
+    publish = peer_reduce == "publish" and (want_dw or want_db)
+    if publish:
+        flags |= L.F_PEER_PUBLISH
+    elif peer_reduce and (want_dw or want_db):
+        flags |= L.F_PEER_REDUCE
     ins = [dy, x] + list(stats) + ([weight] if weight is not None else [])
     outs = iter(_run(op, flags, 0.0, variant, cluster_size, ins))
     dx = next(outs) if want_dx else None
     dw = db = sums = None
-    if want_dw or want_db:
+    if (want_dw or want_db) and not publish:
         if partials_f32:
             sums = next(outs)
         else:
@@ -147,18 +154,28 @@ def _norm_bwd(op, dy, x, stats, weight, flags, output_mask, partials_f32, varian
 
 
 def layer_norm_bwd(dy, x, mean, invstd, weight=None, output_mask=(True, True, True), *, partials_f32=False,
-                   variant=L.VARIANT_AUTO, cluster_size=0):
-    """dx, dweight, dbias (or dx, fp32 sums[2,N] with ``partials_f32``)."""
+                   peer_reduce=False, variant=L.VARIANT_AUTO, cluster_size=0):
+    """dx, dweight, dbias (or dx, fp32 sums[2,N] with ``partials_f32``). ``peer_reduce``: the rows are
+    one rank's shard and the kernel all-reduces dweight / dbias over the registered peer buffers
+    (``fuser_b200.parallel.PeerExchange``); every rank gets the full gradients."""
     return _norm_bwd(L.OP_LAYERNORM_BWD, dy, x, [mean, invstd], weight, 0, output_mask, partials_f32, variant,
-                     cluster_size)
+                     cluster_size, peer_reduce)
 
 
 def rms_norm_bwd(dy, x, stat, weight=None, output_mask=(True, True), *, stat_is_rms=False, centered=False,
-                 partials_f32=False, variant=L.VARIANT_AUTO, cluster_size=0):
+                 partials_f32=False, peer_reduce=False, variant=L.VARIANT_AUTO, cluster_size=0):
     """dx, dweight. ``centered`` keeps the -sum(g) term of the C++ rms_norm_backward builder."""
     flags = (L.F_STAT_IS_RMS if stat_is_rms else 0) | (L.F_RMS_BWD_CENTERED if centered else 0)
     return _norm_bwd(L.OP_RMSNORM_BWD, dy, x, [stat], weight, flags, output_mask, partials_f32, variant,
-                     cluster_size)
+                     cluster_size, peer_reduce)
+
+
+def peer_combine(k: int, n: int, dtype: torch.dtype, anchor: torch.Tensor):
+    """Finish the oldest outstanding publish (``peer_reduce="publish"``): K tensors [N] in ``dtype`` holding
+    the sums over all ranks. ``anchor`` is any tensor on the device (the exchange buffer)."""
+    outs = [torch.empty((n,), dtype=dtype, device=anchor.device) for _ in range(k)]
+    _run(L.OP_PEER_COMBINE, 0, 0.0, L.VARIANT_AUTO, 0, [anchor], outs)
+    return outs
 
 
 def finalize_partials(sums: torch.Tensor, dtype: torch.dtype):

@@ -74,6 +74,7 @@ typedef enum {
   B200NORM_OP_REDUCE_INNER = 8, /* [M,N] -> [M]   sum / max / amax            */
   B200NORM_OP_REDUCE_OUTER = 9, /* [M,N] -> [N]   sum (the dgamma/dbeta shape) */
   B200NORM_OP_FINALIZE_PARTIALS = 10, /* fp32 [K,N] sums -> io dtype (after allreduce) */
+  B200NORM_OP_PEER_COMBINE = 11, /* finish the oldest outstanding PEER_PUBLISH: K tensors [N] io dtype */
   B200NORM_OP_COUNT_
 } b200norm_op;
 
@@ -121,7 +122,23 @@ enum {
    * bf16 `hidden + residual` feeding the norm does); without it the fp32 sum is used. */
   B200NORM_F_ADD_RESIDUAL = 1u << 13,
   B200NORM_F_OUT_SUM = 1u << 14,
-  B200NORM_F_ROUND_SUM = 1u << 15
+  B200NORM_F_ROUND_SUM = 1u << 15,
+  /* LayerNorm / RMSNorm backward, rows sharded over the GPUs of one box: the kernel itself
+   * all-reduces the fp32 dgamma / dbeta sums through the peer-memory exchange buffers registered
+   * with b200norm_register_peers (NVLink / NVSwitch P2P loads and stores from the finishing CTAs)
+   * and writes the cast result on every rank — no separate collective. Replaces the reference's
+   * Communication(Allreduce) node (csrc/host_ir/lower_to_communication.cpp:266-284,
+   * csrc/multidevice/post_communication.cpp:288-313). Every rank must issue the same sequence of
+   * PEER_REDUCE launches; the launch fails with B200NORM_ERR_UNSUPPORTED when the shape cannot
+   * take the fused path (the caller then all-reduces the PARTIALS_F32 sums with NCCL). */
+  B200NORM_F_PEER_REDUCE = 1u << 16,
+  /* The same exchange split in two so that ranks never wait for each other inside the backward:
+   * the backward only PUBLISHES its fp32 sums (slot write + one flag store per peer from the last
+   * finishing CTA; it produces no dweight / dbias tensors), and a later OP_PEER_COMBINE launch — one
+   * CTA, typically a step later, when every peer's flag has long arrived — adds the ranks' slots in
+   * rank order and casts. Publishes and combines pair up in order; at most two publishes may be
+   * outstanding (two slots), the third waits in-kernel for the peers' "consumed" flags. */
+  B200NORM_F_PEER_PUBLISH = 1u << 17
 };
 
 /* desc.variant: 0 lets the library choose (the dispatch rule mirrors the accept
@@ -190,6 +207,7 @@ typedef struct {
  *   REDUCE_INNER   in : x[M,N]                               out: r[M]   (io dtype)
  *   REDUCE_OUTER   in : x[M,N]                               out: r[N]   (io dtype, or fp32 with PARTIALS_F32)
  *   FINALIZE_PARTIALS in: p[K,N] fp32 (rows=K)               out: K tensors [N] io dtype
+ *   PEER_COMBINE   in : -  (rows=K, cols=N)                  out: K tensors [N] io dtype
  * Per-row statistics are always fp32; [M] and [M,1] are both accepted.
  */
 
@@ -230,6 +248,16 @@ const char* b200norm_variant_name(int variant);
  * *has_device = 0 when no CUDA device is visible. */
 int b200norm_device_info(int* has_device, int* sm_count, int* smem_per_block_optin,
                          int* cc_major, int* cc_minor);
+
+/* Registers this process's view of the peer-memory exchange buffers for B200NORM_F_PEER_REDUCE:
+ * `exchange_ptrs[q]` is a device pointer, valid on the current device, to rank q's buffer
+ * (`exchange_ptrs[rank]` is this rank's own); every buffer holds `exchange_bytes` bytes, is
+ * 256-byte aligned and ZERO when registered (256 bytes of epoch flags, then two fp32 [K,N] slots:
+ * exchange_bytes >= 256 + 2*K*N*4 for every launch that uses it). world <= 8 (one box); world = 0
+ * unregisters. The buffers stay owned by the caller (e.g. torch symmetric memory) and must
+ * outlive every launch that uses them. Reference counterpart: the IPC / symmetric-memory handles
+ * of csrc/multidevice/ipc_handle.cpp, symmetric_tensor.cpp. */
+int b200norm_register_peers(int world, int rank, void* const* exchange_ptrs, size_t exchange_bytes);
 
 /* Tuning aid (no reference counterpart): while `device_buf` is non-NULL every ring kernel
  * launched by this process stores per-CTA %globaltimer marks into it (8 x uint64 per CTA:
