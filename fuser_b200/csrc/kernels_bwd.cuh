@@ -7,9 +7,9 @@
 //     x_hat = (x - mean) * invstd            g = dy * w
 //     dx    = (invstd / N) * (N*g - sum(g) - x_hat * sum(g*x_hat))
 //     dw    = sum_rows dy * x_hat            db = sum_rows dy
-// Evaluated here as  dx = A*g + B*xc + C  with xc = x - mean and per-row scalars
-//     A = invstd,  B = -invstd^3 * sum(g*xc) / N,  C = -invstd * sum(g) / N
-// (same polynomial, three packed FMAs per two elements).
+// Evaluated here as  dx = A*g + B*x_hat + C  with per-row scalars
+//     A = invstd,  B = -invstd * sum(g*x_hat) / N,  C = -invstd * sum(g) / N
+// (same polynomial, two packed FMAs and one multiply per two elements).
 //
 // The reference's generated kernel (scheduler/normalization_inner_outer*.cpp)
 // keeps per-CTA partial column sums in registers and finishes them with a grid
@@ -282,50 +282,75 @@ __global__ void __launch_bounds__(kMaxBlock, 1) norm_bwd_ring_kernel(const RowPa
       const float invstd = stat_rms ? rcp_fast(st) : st;
       const float2 nmean = f2(-mean);
       const float2 is2 = f2(invstd);
+      // x_hat = (x - mean) * invstd. With 16-bit inputs it is one FMA, x*invstd + (-mean*invstd): the
+      // pre-rounded product costs at most |mean|/std fp32 ulps of x_hat, far below the resolution of
+      // the 16-bit data it was computed from; fp32 inputs keep the subtract-then-scale form.
+      constexpr bool FMA_XHAT = LN && sizeof(T) == 2;
+      const float nmi_s = -mean * invstd;
+      const float2 nmi = f2(nmi_s);
+      auto x_hat = [&](float2 xv_) -> float2 {
+        if constexpr (FMA_XHAT) {
+          return f2fma(xv_, is2, nmi);
+        } else if constexpr (LN) {
+          return f2mul(f2add(xv_, nmean), is2);
+        } else {
+          return f2mul(xv_, is2);
+        }
+      };
       float2 gv[CACHE ? CH : 1][H];
       float2 xv[CACHE ? CH : 1][H];
       float2 s1 = f2(0.f), s2 = f2(0.f);
       for_each_chunk<TPR, CH>(g.gtid, nchunks, [&](int j, int coff) {
-        float2 dy[H], xc[H], w[H];
+        float2 dy[H], x[H], w[H];
         IO<T>::unpack2(ld_smem_u4(dyrow + 16 * coff), dy);
-        IO<T>::unpack2(ld_smem_u4(xrow + 16 * coff), xc);
+        IO<T>::unpack2(ld_smem_u4(xrow + 16 * coff), x);
         IO<T>::unpack2(wq[j], w);
 #pragma unroll
         for (int k = 0; k < H; ++k) {
           const float2 gg = f2mul(dy[k], w[k]);
-          if constexpr (LN) xc[k] = f2add(xc[k], nmean);
+          const float2 xh = x_hat(x[k]);
           s1 = f2add(s1, gg);
-          s2 = f2fma(gg, xc[k], s2);
-          dw_acc[j][k] = f2fma(dy[k], f2mul(xc[k], is2), dw_acc[j][k]);
+          s2 = f2fma(gg, xh, s2);
+          dw_acc[j][k] = f2fma(dy[k], xh, dw_acc[j][k]);
           if constexpr (LN) db_acc[j][k] = f2add(db_acc[j][k], dy[k]);
           if constexpr (CACHE) {
             gv[j][k] = gg;
-            xv[j][k] = xc[k];
+            xv[j][k] = xh;
           }
         }
       });
       if (want_dx) {
-        float s[2] = {s1.x + s1.y, s2.x + s2.y};
+        float s[2] = {s1.x + s1.y, s2.x + s2.y};  // sum(g), sum(g * x_hat)
         g.template allreduce<SumOp, 2>(s);
-        if (CACHE && r == nrows - 1) ring.refill();  // g / xc live in registers: the stage is free
+        if (CACHE && r == nrows - 1) ring.refill();  // g / x_hat live in registers: the stage is free
+        // dx = invstd * g - (invstd/N) * sum(g x_hat) * x_hat - (invstd/N) * sum(g)  =  A g + B x_hat + C
         const float a_n = invstd * p.inv_n;
+        const float b_s = -(a_n * s[1]);
+        const float c_s = centered ? -(a_n * s[0]) : 0.f;
         const float2 A = is2;
-        const float2 B = f2(-(a_n * invstd * invstd) * s[1]);
-        const float2 C = f2(centered ? -(a_n * s[0]) : 0.f);
+        const float2 B = f2(b_s);
+        const float2 C = f2(c_s);
+        // re-read form: B x_hat + C folded onto x itself where x_hat is affine in x with exact-enough
+        // coefficients (16-bit LayerNorm, RMSNorm): (B invstd) x + (B (-mean invstd) + C)
+        const float2 Bx = f2(b_s * invstd);
+        const float2 Cx = f2(LN ? fmaf(b_s, nmi_s, c_s) : c_s);
         for_each_chunk<TPR, CH>(g.gtid, nchunks, [&](int j, int coff) {
           float2 dx[H];
           if constexpr (CACHE) {
 #pragma unroll
             for (int k = 0; k < H; ++k) dx[k] = f2fma(A, gv[j][k], f2fma(B, xv[j][k], C));
           } else {
-            float2 dy[H], xc[H], w[H];
+            float2 dy[H], x[H], w[H];
             IO<T>::unpack2(ld_smem_u4(dyrow + 16 * coff), dy);
-            IO<T>::unpack2(ld_smem_u4(xrow + 16 * coff), xc);
+            IO<T>::unpack2(ld_smem_u4(xrow + 16 * coff), x);
             IO<T>::unpack2(wq[j], w);
 #pragma unroll
             for (int k = 0; k < H; ++k) {
-              if constexpr (LN) xc[k] = f2add(xc[k], nmean);
-              dx[k] = f2fma(A, f2mul(dy[k], w[k]), f2fma(B, xc[k], C));
+              if constexpr (FMA_XHAT || !LN) {
+                dx[k] = f2fma(A, f2mul(dy[k], w[k]), f2fma(Bx, x[k], Cx));
+              } else {
+                dx[k] = f2fma(A, f2mul(dy[k], w[k]), f2fma(B, x_hat(x[k]), C));
+              }
             }
           }
           st_global_stream(dxrow + 16 * coff, IO<T>::pack2(dx));
