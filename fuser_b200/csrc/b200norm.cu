@@ -366,6 +366,16 @@ bool try_ring_plan(const b200norm_desc& d, const DeviceInfo& dev, int C, bool ro
     // do not starve the grid: keep at least a few tiles per consumer group per SM
     while (tile_rows > 1 && ceil_div64(d.rows, tile_rows) < (int64_t)dev.sm_count * groups * 2) tile_rows /= 2;
   }
+  // 16-bit norm backward with rows of 8 KB and more: two rows per tile when the ring still gets
+  // three stages per group. The per-tile work (barrier wait, refill, pointer rebuild) is a large
+  // share of these instruction-bound kernels: measured +12-15 % at N = 4096 and 8192 bf16
+  // (C2 backward 80 -> 70 us); fp32 rows (memory bound already) and N = 12288 (only two stages
+  // would fit) stay at one row.
+  if (bwd && es == 2 && C == 1 && rows_contiguous && tile_rows == 1) {
+    const uint32_t stage2 = align_up((uint32_t)ns * 2u * p.slice_bytes, 128);
+    const int64_t budget = (int64_t)dev.smem_optin - 4096;
+    if (budget / stage2 / groups >= 3 && ceil_div64(d.rows, 2) >= (int64_t)dev.sm_count * groups * 2) tile_rows = 2;
+  }
   if (int tr = env_int("B200NORM_TILE_ROWS")) {
     if (C == 1 && rows_contiguous && tr >= 1 && tr <= 64) tile_rows = tr;
   }
