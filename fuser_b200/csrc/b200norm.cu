@@ -387,7 +387,11 @@ bool try_ring_plan(const b200norm_desc& d, const DeviceInfo& dev, int C, bool ro
 
   // LayerNorm forward keeps fp32 copies of weight and bias in shared memory when the ring
   // still gets >= 3 stages per group next to them.
-  bool want_psmem = d.op == B200NORM_OP_LAYERNORM_FWD && ch > 0 && env_int("B200NORM_NO_PSMEM") == 0;
+  // (16-bit io only: fp32 parameters need no unpacking, and staging them costs a tiny kernel like
+  // C1 16 % — 16.4 vs 14.1 us; not beyond 8192 columns: at N = 12288 the 96 KB of staged parameters
+  // and their four LDS per chunk cost 10 % — 378 vs 342 us)
+  bool want_psmem = d.op == B200NORM_OP_LAYERNORM_FWD && ch > 0 && es == 2 && slice_cols <= 8192 &&
+                    env_int("B200NORM_NO_PSMEM") == 0;
   const uint32_t param_bytes = align_up(2u * (uint32_t)slice_cols * 4u, 128);
 
   // Ring depth D (stages per group); the ring is group-major, stage (g*D + s).
@@ -1174,10 +1178,10 @@ int b200norm_launch(const b200norm_desc* desc, const b200norm_tensor* inputs, in
       env_int("B200NORM_STATIC") == 0) {
     // Pool size (measured on several B200s, whose per-SM imbalance differs: the static split loses
     // 5-13 % on the worse ones): the last half of the tiles for two-stream kernels, the last quarter
-    // for RMSNorm / softmax forward; plain LayerNorm forward (two reductions per row, one group per
-    // CTA at wide rows) loses more to the pool tiles' ticket wait than it gains and stays static.
-    const bool ln_plain = d.op == B200NORM_OP_LAYERNORM_FWD && !is_add_fwd(d);
-    rp.dynamic = ln_plain ? 0 : (rp.nstreams > 1 ? 2 : 4);
+    // for RMSNorm / softmax forward; LayerNorm forward (two reductions per row, one group per CTA
+    // at wide rows) loses more to the pool tiles' ticket wait than it gains and stays static.
+    const bool ln_fwd = d.op == B200NORM_OP_LAYERNORM_FWD;  // plain or with the residual add (112 vs 102 us)
+    rp.dynamic = ln_fwd ? 0 : (rp.nstreams > 1 ? 2 : 4);
     // short kernels (C2 forward: 28 tiles per group, 47 us) gain nothing: the exit protocol's last
     // atomic round trip and the few pool tiles cost what the balance wins
     const int64_t tiles_per_group = ceil_div64(d.rows, plan.tile_rows) / ((int64_t)plan.grid * plan.groups);
