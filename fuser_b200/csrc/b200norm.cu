@@ -143,11 +143,12 @@ struct Plan {
   int nchunks = 0;
   bool cached = false;
   bool psmem = false;      // LayerNorm fwd: weight / bias staged in shared memory as fp32
+  bool pipe = false;       // backward, re-read form: split-phase reductions pipelined across rows
   int nparts = 0;          // partial rows produced by the main kernel
   int rows_per_split = 0;  // generic colsum
   int n_launches = 1;
   uint32_t slice_bytes = 0, stream_bytes = 0, stage_bytes = 0;
-  uint32_t off_red = 0, off_cls = 0, off_param = 0, off_ring = 0, off_tidx = 0;
+  uint32_t off_red = 0, off_cls = 0, off_param = 0, off_ring = 0, off_tidx = 0, off_pipe = 0;
   uint32_t smem = 0;
   uint64_t ws_bytes = 0;
 };
@@ -157,21 +158,25 @@ uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 // ---------------------------------------------------------------------------
 // kernel tables
 // ---------------------------------------------------------------------------
+// `psmem` doubles as the pipelined-backward selector for the norm backward (it has no other meaning there)
 template <typename T>
 RingKernel ring_kernel_for(int op, int tpr, int ch, bool cached, bool psmem, bool add);
 template <>
 RingKernel ring_kernel_for<float>(int op, int tpr, int ch, bool cached, bool psmem, bool add) {
   if (add) return ring_add_kernel_f32(op, tpr, ch, psmem);
+  if (is_norm_bwd(op) && !cached && psmem) return ring_bwd_pipe_kernel_f32(op, tpr, ch);
   return is_norm_bwd(op) ? ring_bwd_kernel_f32(op, tpr, ch, cached) : ring_fwd_kernel_f32(op, tpr, ch, psmem);
 }
 template <>
 RingKernel ring_kernel_for<__nv_bfloat16>(int op, int tpr, int ch, bool cached, bool psmem, bool add) {
   if (add) return ring_add_kernel_bf16(op, tpr, ch, psmem);
+  if (is_norm_bwd(op) && !cached && psmem) return ring_bwd_pipe_kernel_bf16(op, tpr, ch);
   return is_norm_bwd(op) ? ring_bwd_kernel_bf16(op, tpr, ch, cached) : ring_fwd_kernel_bf16(op, tpr, ch, psmem);
 }
 template <>
 RingKernel ring_kernel_for<__half>(int op, int tpr, int ch, bool cached, bool psmem, bool add) {
   if (add) return ring_add_kernel_f16(op, tpr, ch, psmem);
+  if (is_norm_bwd(op) && !cached && psmem) return ring_bwd_pipe_kernel_f16(op, tpr, ch);
   return is_norm_bwd(op) ? ring_bwd_kernel_f16(op, tpr, ch, cached) : ring_fwd_kernel_f16(op, tpr, ch, psmem);
 }
 
@@ -399,6 +404,8 @@ bool try_ring_plan(const b200norm_desc& d, const DeviceInfo& dev, int C, bool ro
     uint32_t off = 8u * (kMaxStages + groups);
     p.off_tidx = off;  // dynamic schedule: stage -> tile index
     off += 4u * kSchedTableInts + 16u;  // + the CTA's "groups that saw the empty pool" counter
+    p.off_pipe = off;  // pipelined backward: red[2G] | free[G*D] | clusterB[G] mbarriers
+    off += 8u * (uint32_t)(kMaxStages + 3 * groups);
     off = align_up(off, 2 * kRedSetBytes);  // slot-set pairs are toggled with an XOR
     p.off_red = off;
     off += (uint32_t)groups * 2 * kRedSetBytes;
@@ -431,6 +438,14 @@ bool try_ring_plan(const b200norm_desc& d, const DeviceInfo& dev, int C, bool ro
   }
   p.groups = groups;
   p.psmem = want_psmem;
+  // re-read backward: the pipelined kernel (one row per tile, at least two warps per group) where it
+  // was measured faster — rows split over a cluster (the DSMEM exchange overlaps the next row's
+  // first pass: C5 335 -> 320 us) and fp32 rows ([16384,8192] 273 -> 248 us); the 16-bit
+  // single-CTA case is bound by instruction issue, not by the reduction latency, and loses 4 %
+  // (C4 420 -> 440 us), so it keeps the plain kernel. B200NORM_PIPE=1 / B200NORM_NO_PIPE=1 force it.
+  p.pipe = bwd && !cached && tile_rows == 1 && tpr >= 64 && env_int("B200NORM_NO_PIPE") == 0 &&
+           (C > 1 || es == 4 || env_int("B200NORM_PIPE") != 0);
+  if (p.pipe) p.psmem = true;  // kernel-table selector, see ring_kernel_for
   p.block = groups * tpr;
   const uint32_t ring_bytes = (uint32_t)p.stages * p.stage_bytes;
   if (bwd) {
@@ -1169,6 +1184,7 @@ int b200norm_launch(const b200norm_desc* desc, const b200norm_tensor* inputs, in
   rp.off_param = plan.off_param;
   rp.off_acc = plan.off_ring;
   rp.off_tidx = plan.off_tidx;
+  rp.off_pipe = plan.off_pipe;
   // Dynamic tile scheduling for the kernels without cross-row state (forward norms, softmax
   // forward / backward): results are bit-identical whatever SM processes a row. The norm
   // backward keeps the static split so that its per-CTA dgamma / dbeta partial sums — and with

@@ -212,6 +212,84 @@ __device__ __forceinline__ void peer_publish(const RowParams& p) {
   }
 }
 
+// After the row loop: combine the groups' column accumulators, emit this CTA's partial row and —
+// with the in-kernel finish — reduce the partial rows (and, on several GPUs, the ranks' sums).
+template <typename T, int TPR, int CH, bool LN>
+__device__ __forceinline__ void bwd_epilogue(const RowParams& p, const Group<TPR>& g,
+                                             float2 (&dw_acc)[CH][IO<T>::VEC / 2],
+                                             float2 (&db_acc)[LN ? CH : 1][IO<T>::VEC / 2], bool want_dw,
+                                             bool want_db) {
+  constexpr int VEC = IO<T>::VEC;
+  constexpr int H = VEC / 2;
+  tl_mark(p, 3);
+  const int nchunks = p.nchunks;
+  // ---- combine the groups' column accumulators and emit this CTA's partial row ----
+  if (want_dw || want_db) {
+    const int nct = p.groups * TPR;
+    float* acc_w = reinterpret_cast<float*>(smem_raw + p.off_acc);
+    float* acc_b = acc_w + p.cols_cta;
+    named_bar_sync(15, nct);  // every group is done with the ring
+    for (int gi = 0; gi < p.groups; ++gi) {
+      if (g.gid == gi) {
+        for_each_chunk<TPR, CH>(g.gtid, nchunks, [&](int j, int coff) {
+          const int c = g.gtid + coff;
+#pragma unroll
+          for (int k = 0; k < H; ++k) {
+            float2* pw = reinterpret_cast<float2*>(acc_w + c * VEC + 2 * k);
+            float2* pb = reinterpret_cast<float2*>(acc_b + c * VEC + 2 * k);
+            if (gi == 0) {
+              *pw = dw_acc[j][k];
+              if constexpr (LN) *pb = db_acc[j][k];
+            } else {
+              *pw = f2add(*pw, dw_acc[j][k]);
+              if constexpr (LN) *pb = f2add(*pb, db_acc[j][k]);
+            }
+          }
+        });
+      }
+      named_bar_sync(15, nct);
+    }
+    // partials layout: [part][K][N], K = 2 for LN (dw, db), 1 for RMSNorm
+    constexpr int K = LN ? 2 : 1;
+    const int64_t part = blockIdx.x / g.csize;
+    float* dst = p.partials + (size_t)part * K * p.cols + (size_t)g.crank * p.cols_cta;
+    for (int col = threadIdx.x * 4; col < p.cols_cta; col += nct * 4) {
+      *reinterpret_cast<float4*>(dst + col) = *reinterpret_cast<const float4*>(acc_w + col);
+      if constexpr (LN) *reinterpret_cast<float4*>(dst + p.cols + col) = *reinterpret_cast<const float4*>(acc_b + col);
+    }
+    if (p.fused_finish) {
+      // The launch is cooperative (every CTA is resident): one grid barrier, then every CTA
+      // finishes a share of the columns in a fixed order — deterministic, like the reference's
+      // grid reduction (runtime/grid_reduction.cu:201-309 + grid_sync.cu:34-95).
+      __threadfence();
+      __syncthreads();
+      tl_mark(p, 4);
+      grid_barrier(p.sync_words);
+      tl_mark(p, 5);
+      const int F = K * (p.cols / 4);  // float4 columns of the [K][N] result
+      // several GPUs: this rank's sums go to its exchange slot instead of being cast
+      float* sums_dst = p.sums_out;
+      if (p.peer_world > 0) {
+        sums_dst = reinterpret_cast<float*>(p.peer_xchg[p.peer_rank] + kPeerHeaderBytes) +
+                   (size_t)(p.peer_epoch & 1u) * p.peer_slot_floats;
+        if (p.peer_deferred) peer_wait_consumed(p);  // the slot's previous content (two publishes ago) was read
+      }
+      if ((F + 7) / 8 <= 2 * (int)gridDim.x) {
+        finish_columns<T, 8>(p, K, F, nct, sums_dst);
+      } else {
+        finish_columns<T, 32>(p, K, F, nct, sums_dst);
+      }
+      if (p.peer_world > 0) {
+        if (p.peer_deferred) {
+          peer_publish(p);
+        } else {
+          peer_allreduce_columns<T>(p, K, nct);
+        }
+      }
+    }
+  }
+}
+
 // LN: true = LayerNorm (mean input, dbeta), false = RMSNorm.
 // Each thread owns chunks c = gtid + j*TPR, j < CH, of the CTA's column slice
 // (the planner guarantees nchunks <= TPR*CH).
@@ -363,72 +441,252 @@ __global__ void __launch_bounds__(kMaxBlock, 1) norm_bwd_ring_kernel(const RowPa
     }
   }
 
-  tl_mark(p, 3);
-  // ---- combine the groups' column accumulators and emit this CTA's partial row ----
-  if (want_dw || want_db) {
-    const int nct = p.groups * TPR;
-    float* acc_w = reinterpret_cast<float*>(smem_raw + p.off_acc);
-    float* acc_b = acc_w + p.cols_cta;
-    named_bar_sync(15, nct);  // every group is done with the ring
-    for (int gi = 0; gi < p.groups; ++gi) {
-      if (g.gid == gi) {
-        for_each_chunk<TPR, CH>(g.gtid, nchunks, [&](int j, int coff) {
-          const int c = g.gtid + coff;
+  bwd_epilogue<T, TPR, CH, LN>(p, g, dw_acc, db_acc, want_dw, want_db);
+  ring_teardown(p);
+  tl_mark(p, 6);
+}
+
+
+// ---------------------------------------------------------------------------
+// Pipelined re-read backward (rows too wide for the cached form: one or two 512-thread groups per
+// CTA, e.g. C4 LayerNorm N = 12288, C5 RMSNorm N = 65536 over a cluster of 4).
+// With a single group per CTA nothing overlaps a row's reduction: every warp waits at the group
+// barrier (and, in a cluster, for the DSMEM exchange) between the two passes. Here the reduction is
+// split-phase and software-pipelined across rows:
+//     iteration k:  collect1(k)   totals of row k inside the CTA (posted an iteration ago: no wait);
+//                                 cluster: send them to the peers
+//                   pass1(k+1)    first pass of the NEXT row (sums, dgamma / dbeta accumulation), post
+//                   collect2(k)   cluster: the peers' totals have had a whole pass to arrive
+//                   pass2(k)      dx of row k
+//                   release       the row's stage; the first warp refills it when every warp has let go
+// post / collect use mbarriers (arrive is non-blocking, the wait only needs the other warps'
+// arrivals — a named barrier would need their waits too). Slot sets, reduction barriers and cluster
+// barriers alternate between even and odd rows; a warp can be at most one row ahead of another.
+// One row per tile (the planner guarantees it for these shapes).
+// ---------------------------------------------------------------------------
+template <typename T, int TPR, int CH, bool LN>
+__global__ void __launch_bounds__(kMaxBlock, 1) norm_bwd_pipe_kernel(const RowParams p) {
+  constexpr int VEC = IO<T>::VEC;
+  constexpr int H = VEC / 2;
+  constexpr int WPG = TPR / 32;
+  static_assert(CH > 0 && TPR >= 64, "pipelined backward: fixed chunk ownership, more than one warp per group");
+  const uint32_t smem0 = smem_u32(smem_raw);
+  tl_mark(p, 0);
+  if (threadIdx.x == 0) {
+    const int n_red = 2 * p.groups, n_free = p.groups * p.depth;
+    for (int i = 0; i < n_red + n_free; ++i) mbar_init(smem0 + p.off_pipe + 8u * (uint32_t)i, WPG);
+    for (int i = 0; i < p.groups; ++i) mbar_init(smem0 + p.off_pipe + 8u * (uint32_t)(n_red + n_free + i), 1);
+  }
+  ring_setup(p, smem0);  // fences the barrier inits, syncs the CTA (and the cluster)
+  tl_mark(p, 1);
+  Group<TPR> g(p, smem0);
+  Ring<T, TPR> ring(p, smem0, g);
+  ring.prologue();
+
+  const int nchunks = p.nchunks;
+  const bool want_dx = (p.flags & kFlagOutDx) != 0;
+  const bool want_dw = (p.flags & kFlagOutDw) != 0;
+  const bool want_db = LN && (p.flags & kFlagOutDb) != 0;
+  const bool centered = LN || (p.flags & kFlagRmsBwdCentered) != 0;
+  const bool stat_rms = !LN && (p.flags & kFlagStatIsRms) != 0;
+  const size_t col0_bytes = (size_t)g.crank * p.slice_bytes;
+  uint4 wq[CH];
+  load_params_to_regs<T, TPR, CH>(p.weight, col0_bytes, g.gtid, nchunks, 1.0f, wq);
+
+  float2 dw_acc[CH][H];
+  float2 db_acc[LN ? CH : 1][H];
 #pragma unroll
-          for (int k = 0; k < H; ++k) {
-            float2* pw = reinterpret_cast<float2*>(acc_w + c * VEC + 2 * k);
-            float2* pb = reinterpret_cast<float2*>(acc_b + c * VEC + 2 * k);
-            if (gi == 0) {
-              *pw = dw_acc[j][k];
-              if constexpr (LN) *pb = db_acc[j][k];
-            } else {
-              *pw = f2add(*pw, dw_acc[j][k]);
-              if constexpr (LN) *pb = f2add(*pb, db_acc[j][k]);
-            }
-          }
-        });
-      }
-      named_bar_sync(15, nct);
+  for (int j = 0; j < CH; ++j) {
+#pragma unroll
+    for (int k = 0; k < H; ++k) {
+      dw_acc[j][k] = f2(0.f);
+      if constexpr (LN) db_acc[j][k] = f2(0.f);
     }
-    // partials layout: [part][K][N], K = 2 for LN (dw, db), 1 for RMSNorm
-    constexpr int K = LN ? 2 : 1;
-    const int64_t part = blockIdx.x / g.csize;
-    float* dst = p.partials + (size_t)part * K * p.cols + (size_t)g.crank * p.cols_cta;
-    for (int col = threadIdx.x * 4; col < p.cols_cta; col += nct * 4) {
-      *reinterpret_cast<float4*>(dst + col) = *reinterpret_cast<const float4*>(acc_w + col);
-      if constexpr (LN) *reinterpret_cast<float4*>(dst + p.cols + col) = *reinterpret_cast<const float4*>(acc_b + col);
+  }
+
+  // barriers and slot sets of this group
+  const uint32_t red_bar = smem0 + p.off_pipe + 8u * (uint32_t)(2 * g.gid);
+  const uint32_t free_bar = smem0 + p.off_pipe + 8u * (uint32_t)(2 * p.groups + g.gid * p.depth);
+  const uint32_t cl_bar_even = g.clbar;
+  const uint32_t cl_bar_odd = smem0 + p.off_pipe + 8u * (uint32_t)(2 * p.groups + p.groups * p.depth + g.gid);
+  float* red_slots = reinterpret_cast<float*>(smem_raw + p.off_red + (uint32_t)g.gid * (2 * kRedSetBytes));
+  const uint32_t cls_off = p.off_cls + (uint32_t)g.gid * (2 * kClsSetBytes);
+
+  const int n = ring.ntiles_g;
+  const int64_t row_first = ring.row0, row_step = ring.row_step;
+  auto stat_of = [&](int64_t k, float& mean, float& st) {
+    const int64_t row = row_first + k * row_step;
+    mean = 0.f;
+    st = 0.f;
+    if (k < n) {
+      if constexpr (LN) mean = __ldg(p.stat0 + row);
+      st = __ldg(p.stat1 + row);
     }
-    if (p.fused_finish) {
-      // The launch is cooperative (every CTA is resident): one grid barrier, then every CTA
-      // finishes a share of the columns in a fixed order — deterministic, like the reference's
-      // grid reduction (runtime/grid_reduction.cu:201-309 + grid_sync.cu:34-95).
-      __threadfence();
-      __syncthreads();
-      tl_mark(p, 4);
-      grid_barrier(p.sync_words);
-      tl_mark(p, 5);
-      const int F = K * (p.cols / 4);  // float4 columns of the [K][N] result
-      // several GPUs: this rank's sums go to its exchange slot instead of being cast
-      float* sums_dst = p.sums_out;
-      if (p.peer_world > 0) {
-        sums_dst = reinterpret_cast<float*>(p.peer_xchg[p.peer_rank] + kPeerHeaderBytes) +
-                   (size_t)(p.peer_epoch & 1u) * p.peer_slot_floats;
-        if (p.peer_deferred) peer_wait_consumed(p);  // the slot's previous content (two publishes ago) was read
-      }
-      if ((F + 7) / 8 <= 2 * (int)gridDim.x) {
-        finish_columns<T, 8>(p, K, F, nct, sums_dst);
-      } else {
-        finish_columns<T, 32>(p, K, F, nct, sums_dst);
-      }
-      if (p.peer_world > 0) {
-        if (p.peer_deferred) {
-          peer_publish(p);
+  };
+  // row statistics: A = row k (second pass), B = row k+1 (first pass), C = row k+2 (in flight)
+  float mean_a, st_a, mean_b, st_b, mean_c, st_c;
+  stat_of(0, mean_b, st_b);
+  stat_of(1, mean_c, st_c);
+
+  // two cursors over the ring: c1 = first pass (one row ahead), c2 = second pass
+  uint32_t c1_off = ring.ring_off_g, c1_bar = ring.bar_g, c1_s = 0, c1_phase = 0;
+  uint32_t c2_off = ring.ring_off_g, c2_bar = ring.bar_g, c2_s = 0, c2_phase = 0;
+  auto advance = [&](uint32_t& off, uint32_t& bar, uint32_t& s, uint32_t& phase) {
+    ++s;
+    off += p.stage_bytes;
+    bar += 8u;
+    if (s == (uint32_t)p.depth) {
+      s = 0;
+      phase ^= 1u;
+      off = ring.ring_off_g;
+      bar = ring.bar_g;
+    }
+  };
+
+  // first pass of one row + post of its partial sums
+  auto pass1_post = [&](int j_row, float mean, float st) {
+    mbar_wait(c1_bar, c1_phase);
+    const uint8_t* dyrow = smem_raw + c1_off + 16u * (uint32_t)g.gtid;
+    const uint8_t* xrow = dyrow + p.stream_bytes;
+    const float invstd = stat_rms ? rcp_fast(st) : st;
+    constexpr bool FMA_XHAT = LN && sizeof(T) == 2;
+    const float2 is2 = f2(invstd), nmean = f2(-mean), nmi = f2(-mean * invstd);
+    float2 s1 = f2(0.f), s2 = f2(0.f);
+    for_each_chunk<TPR, CH>(g.gtid, nchunks, [&](int j, int coff) {
+      float2 dy[H], x[H], w[H];
+      IO<T>::unpack2(ld_smem_u4(dyrow + 16 * coff), dy);
+      IO<T>::unpack2(ld_smem_u4(xrow + 16 * coff), x);
+      IO<T>::unpack2(wq[j], w);
+#pragma unroll
+      for (int k = 0; k < H; ++k) {
+        const float2 gg = f2mul(dy[k], w[k]);
+        float2 xh;
+        if constexpr (FMA_XHAT) {
+          xh = f2fma(x[k], is2, nmi);
+        } else if constexpr (LN) {
+          xh = f2mul(f2add(x[k], nmean), is2);
         } else {
-          peer_allreduce_columns<T>(p, K, nct);
+          xh = f2mul(x[k], is2);
+        }
+        s1 = f2add(s1, gg);
+        s2 = f2fma(gg, xh, s2);
+        dw_acc[j][k] = f2fma(dy[k], xh, dw_acc[j][k]);
+        if constexpr (LN) db_acc[j][k] = f2add(db_acc[j][k], dy[k]);
+      }
+    });
+    float v[2] = {s1.x + s1.y, s2.x + s2.y};
+    warp_allreduce<SumOp, 2>(v);
+    if (g.lane == 0) {
+      float* set = red_slots + (j_row & 1) * (kRedSetBytes / 4);
+      set[g.warp] = v[0];
+      set[kMaxWarpsPerGroup + g.warp] = v[1];
+      mbar_arrive(red_bar + 8u * (uint32_t)(j_row & 1));  // release: the slots are visible to whoever sees the phase
+    }
+    advance(c1_off, c1_bar, c1_s, c1_phase);
+  };
+
+  if (n > 0) pass1_post(0, mean_b, st_b);
+  mean_a = mean_b;
+  st_a = st_b;
+  mean_b = mean_c;
+  st_b = st_c;
+  stat_of(2, mean_c, st_c);
+
+  for (int k = 0; k < n; ++k) {
+    if (k == 0) tl_mark(p, 2);
+    const uint32_t par = (uint32_t)(k & 1), ph = (uint32_t)((k >> 1) & 1);
+    const uint32_t cl_bar = par ? cl_bar_odd : cl_bar_even;
+    // ---- collect1(k): totals inside the CTA (fixed order: every thread gets the same bits) ----
+    mbar_wait(red_bar + 8u * par, ph);
+    float tot[2];
+    {
+      const float* set = red_slots + par * (kRedSetBytes / 4);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        float r = 0.f;
+#pragma unroll
+        for (int w4 = 0; w4 < (WPG + 3) / 4; ++w4) {
+          const float4 t = *reinterpret_cast<const float4*>(set + i * kMaxWarpsPerGroup + 4 * w4);
+          if constexpr (WPG >= 4) {
+            r += (t.x + t.y) + (t.z + t.w);
+          } else {
+            r += t.x + t.y;  // WPG == 2
+          }
+        }
+        tot[i] = r;
+      }
+    }
+    if (g.csize > 1) {
+      const uint32_t set = par * kClsSetBytes;
+      if (g.gtid == 0) mbar_arrive_expect_tx(cl_bar, g.csize * 2 * 4);
+      if ((uint32_t)g.gtid < g.csize) {
+        const uint32_t r = (uint32_t)g.gtid;
+        const uint32_t rbar = map_to_cta(cl_bar, r);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          st_async_f32(map_to_cta(smem0 + cls_off + set + (g.crank * kRedNV + i) * 4, r), tot[i], rbar);
         }
       }
     }
+    // ---- first pass of the next row ----
+    if (k + 1 < n) pass1_post(k + 1, mean_b, st_b);
+    // ---- collect2(k): the peers' totals ----
+    if (g.csize > 1) {
+      mbar_wait(cl_bar, ph);
+      const volatile float* slots = reinterpret_cast<const volatile float*>(smem_raw + cls_off + par * kClsSetBytes);
+      tot[0] = 0.f;
+      tot[1] = 0.f;
+      for (uint32_t r = 0; r < g.csize; ++r) {
+        tot[0] += slots[r * kRedNV + 0];
+        tot[1] += slots[r * kRedNV + 1];
+      }
+    }
+    // ---- second pass of row k ----
+    if (want_dx) {
+      const float invstd = stat_rms ? rcp_fast(st_a) : st_a;
+      constexpr bool FMA_XHAT = LN && sizeof(T) == 2;
+      const float nmi_s = -mean_a * invstd;
+      const float a_n = invstd * p.inv_n;
+      const float b_s = -(a_n * tot[1]);
+      const float c_s = centered ? -(a_n * tot[0]) : 0.f;
+      const float2 A = f2(invstd), B = f2(b_s), C = f2(c_s), is2 = f2(invstd), nmean = f2(-mean_a);
+      const float2 Bx = f2(b_s * invstd);
+      const float2 Cx = f2(LN ? fmaf(b_s, nmi_s, c_s) : c_s);
+      const uint8_t* dyrow = smem_raw + c2_off + 16u * (uint32_t)g.gtid;
+      const uint8_t* xrow = dyrow + p.stream_bytes;
+      uint8_t* dxrow = out_row_ptr<T>(p, row_first + (int64_t)k * row_step, g.crank, g.gtid);
+      for_each_chunk<TPR, CH>(g.gtid, nchunks, [&](int j, int coff) {
+        float2 dy[H], x[H], w[H], dx[H];
+        IO<T>::unpack2(ld_smem_u4(dyrow + 16 * coff), dy);
+        IO<T>::unpack2(ld_smem_u4(xrow + 16 * coff), x);
+        IO<T>::unpack2(wq[j], w);
+#pragma unroll
+        for (int q = 0; q < H; ++q) {
+          if constexpr (FMA_XHAT || !LN) {
+            dx[q] = f2fma(A, f2mul(dy[q], w[q]), f2fma(Bx, x[q], Cx));
+          } else {
+            dx[q] = f2fma(A, f2mul(dy[q], w[q]), f2fma(B, f2mul(f2add(x[q], nmean), is2), C));
+          }
+        }
+        st_global_stream(dxrow + 16 * coff, IO<T>::pack2(dx));
+      });
+    }
+    // ---- release the stage; the first warp refills it once every warp has let go ----
+    __syncwarp();
+    if (g.lane == 0) mbar_arrive(free_bar + 8u * c2_s);
+    if (g.warp == 0) {
+      mbar_wait(free_bar + 8u * c2_s, c2_phase);
+      if (k + p.depth < n) ring.issue_rows(1, row_first + (int64_t)(k + p.depth) * row_step, c2_off, c2_bar);
+    }
+    advance(c2_off, c2_bar, c2_s, c2_phase);
+    mean_a = mean_b;
+    st_a = st_b;
+    mean_b = mean_c;
+    st_b = st_c;
+    stat_of((int64_t)k + 3, mean_c, st_c);
   }
+
+  bwd_epilogue<T, TPR, CH, LN>(p, g, dw_acc, db_acc, want_dw, want_db);
   ring_teardown(p);
   tl_mark(p, 6);
 }

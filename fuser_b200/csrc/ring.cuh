@@ -121,6 +121,7 @@ struct RowParams {
   int32_t dynamic;
   uint32_t* sched_words;
   uint32_t off_tidx;  // int32 [groups*depth]: tile index held by each stage (-1 = no more tiles)
+  uint32_t off_pipe;  // pipelined backward: mbarriers red[2*groups] | free[groups*depth] | clusterB[groups]
 };
 
 // Timeline marks: 0 entry, 1 setup done (after griddepcontrol.wait), 2 first tile landed,
