@@ -165,18 +165,21 @@ template <>
 RingKernel ring_kernel_for<float>(int op, int tpr, int ch, bool cached, bool psmem, bool add) {
   if (add) return ring_add_kernel_f32(op, tpr, ch, psmem);
   if (is_norm_bwd(op) && !cached && psmem) return ring_bwd_pipe_kernel_f32(op, tpr, ch);
+  if (op == B200NORM_OP_RMSNORM_FWD && psmem) return ring_fwd_pipe_kernel_f32(op, tpr, ch);
   return is_norm_bwd(op) ? ring_bwd_kernel_f32(op, tpr, ch, cached) : ring_fwd_kernel_f32(op, tpr, ch, psmem);
 }
 template <>
 RingKernel ring_kernel_for<__nv_bfloat16>(int op, int tpr, int ch, bool cached, bool psmem, bool add) {
   if (add) return ring_add_kernel_bf16(op, tpr, ch, psmem);
   if (is_norm_bwd(op) && !cached && psmem) return ring_bwd_pipe_kernel_bf16(op, tpr, ch);
+  if (op == B200NORM_OP_RMSNORM_FWD && psmem) return ring_fwd_pipe_kernel_bf16(op, tpr, ch);
   return is_norm_bwd(op) ? ring_bwd_kernel_bf16(op, tpr, ch, cached) : ring_fwd_kernel_bf16(op, tpr, ch, psmem);
 }
 template <>
 RingKernel ring_kernel_for<__half>(int op, int tpr, int ch, bool cached, bool psmem, bool add) {
   if (add) return ring_add_kernel_f16(op, tpr, ch, psmem);
   if (is_norm_bwd(op) && !cached && psmem) return ring_bwd_pipe_kernel_f16(op, tpr, ch);
+  if (op == B200NORM_OP_RMSNORM_FWD && psmem) return ring_fwd_pipe_kernel_f16(op, tpr, ch);
   return is_norm_bwd(op) ? ring_bwd_kernel_f16(op, tpr, ch, cached) : ring_fwd_kernel_f16(op, tpr, ch, psmem);
 }
 
@@ -445,6 +448,12 @@ bool try_ring_plan(const b200norm_desc& d, const DeviceInfo& dev, int C, bool ro
   // (C4 420 -> 440 us), so it keeps the plain kernel. B200NORM_PIPE=1 / B200NORM_NO_PIPE=1 force it.
   p.pipe = bwd && !cached && tile_rows == 1 && tpr >= 64 && env_int("B200NORM_NO_PIPE") == 0 &&
            (C > 1 || es == 4 || env_int("B200NORM_PIPE") != 0);
+  // RMSNorm forward over a cluster: the same pipeline (the row is read twice from its stage instead
+  // of being held in registers, so the next row's sum of squares overlaps the DSMEM exchange)
+  if (d.op == B200NORM_OP_RMSNORM_FWD && !add && (C > 1 || env_int("B200NORM_PIPE") != 0) && ch > 0 &&
+      tile_rows == 1 && tpr >= 64 && (ch <= 4 || tpr >= 256) && env_int("B200NORM_NO_PIPE") == 0) {
+    p.pipe = true;
+  }
   if (p.pipe) p.psmem = true;  // kernel-table selector, see ring_kernel_for
   p.block = groups * tpr;
   const uint32_t ring_bytes = (uint32_t)p.stages * p.stage_bytes;

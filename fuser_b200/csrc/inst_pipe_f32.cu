@@ -2,4 +2,5 @@
 #include "ring_inst_pipe.cuh"
 namespace b200norm {
 RingKernel ring_bwd_pipe_kernel_f32(int op, int tpr, int ch) { return ring_bwd_pipe_kernel_for<float>(op, tpr, ch); }
+RingKernel ring_fwd_pipe_kernel_f32(int op, int tpr, int ch) { return ring_fwd_pipe_kernel_for<float>(op, tpr, ch); }
 }  // namespace b200norm

@@ -403,4 +403,143 @@ __global__ void __launch_bounds__(kMaxBlock, 1) softmax_bwd_ring_kernel(const Ro
   tl_mark(p, 6);
 }
 
+
+// ---------------------------------------------------------------------------
+// RMSNorm forward, pipelined (rows split over a thread-block cluster, e.g. C5 N = 65536 over 4
+// CTAs): the register-resident kernel above waits for the DSMEM exchange of every row between its
+// two passes with nothing else to do (one group per CTA). Here the row stays in the shared-memory
+// stage and is read twice, which frees the registers to run the NEXT row's sum of squares while
+// the exchange of the current row is in flight — the same split-phase pipeline as
+// norm_bwd_pipe_kernel (kernels_bwd.cuh), with one reduced value per row.
+// ---------------------------------------------------------------------------
+template <typename T, int TPR, int CH>
+__global__ void __launch_bounds__(kMaxBlock, 1) rmsnorm_fwd_pipe_kernel(const RowParams p) {
+  constexpr int VEC = IO<T>::VEC;
+  constexpr int H = VEC / 2;
+  constexpr int WPG = TPR / 32;
+  static_assert(CH > 0 && TPR >= 64, "pipelined forward: fixed chunk ownership, more than one warp per group");
+  const uint32_t smem0 = smem_u32(smem_raw);
+  tl_mark(p, 0);
+  if (threadIdx.x == 0) {
+    const int n_red = 2 * p.groups, n_free = p.groups * p.depth;
+    for (int i = 0; i < n_red + n_free; ++i) mbar_init(smem0 + p.off_pipe + 8u * (uint32_t)i, WPG);
+    for (int i = 0; i < p.groups; ++i) mbar_init(smem0 + p.off_pipe + 8u * (uint32_t)(n_red + n_free + i), 1);
+  }
+  ring_setup(p, smem0);
+  tl_mark(p, 1);
+  Group<TPR> g(p, smem0);
+  Ring<T, TPR> ring(p, smem0, g);
+  ring.prologue();
+
+  const int nchunks = p.nchunks;
+  const bool stat_rms = (p.flags & kFlagStatIsRms) != 0;
+  const size_t col0_bytes = (size_t)g.crank * p.slice_bytes;
+  uint4 wq[CH];
+  load_params_to_regs<T, TPR, CH>(p.weight, col0_bytes, g.gtid, nchunks, 1.0f, wq);
+  const bool stat_writer = g.gtid == 0 && g.crank == 0 && p.stat1 != nullptr;
+
+  const uint32_t red_bar = smem0 + p.off_pipe + 8u * (uint32_t)(2 * g.gid);
+  const uint32_t free_bar = smem0 + p.off_pipe + 8u * (uint32_t)(2 * p.groups + g.gid * p.depth);
+  const uint32_t cl_bar_even = g.clbar;
+  const uint32_t cl_bar_odd = smem0 + p.off_pipe + 8u * (uint32_t)(2 * p.groups + p.groups * p.depth + g.gid);
+  float* red_slots = reinterpret_cast<float*>(smem_raw + p.off_red + (uint32_t)g.gid * (2 * kRedSetBytes));
+  const uint32_t cls_off = p.off_cls + (uint32_t)g.gid * (2 * kClsSetBytes);
+
+  const int n = ring.ntiles_g;
+  const int64_t row_first = ring.row0, row_step = ring.row_step;
+  uint32_t c1_off = ring.ring_off_g, c1_bar = ring.bar_g, c1_s = 0, c1_phase = 0;
+  uint32_t c2_off = ring.ring_off_g, c2_bar = ring.bar_g, c2_s = 0, c2_phase = 0;
+  auto advance = [&](uint32_t& off, uint32_t& bar, uint32_t& s, uint32_t& phase) {
+    ++s;
+    off += p.stage_bytes;
+    bar += 8u;
+    if (s == (uint32_t)p.depth) {
+      s = 0;
+      phase ^= 1u;
+      off = ring.ring_off_g;
+      bar = ring.bar_g;
+    }
+  };
+  auto pass1_post = [&](int j_row) {
+    mbar_wait(c1_bar, c1_phase);
+    const uint8_t* xrow = smem_raw + c1_off + 16u * (uint32_t)g.gtid;
+    float2 acc = f2(0.f);
+    for_each_chunk<TPR, CH>(g.gtid, nchunks, [&](int, int coff) {
+      float2 t[H];
+      IO<T>::unpack2(ld_smem_u4(xrow + 16 * coff), t);
+#pragma unroll
+      for (int k = 0; k < H; ++k) acc = f2fma(t[k], t[k], acc);
+    });
+    float v[1] = {acc.x + acc.y};
+    warp_allreduce<SumOp, 1>(v);
+    if (g.lane == 0) {
+      red_slots[(j_row & 1) * (kRedSetBytes / 4) + g.warp] = v[0];
+      mbar_arrive(red_bar + 8u * (uint32_t)(j_row & 1));
+    }
+    advance(c1_off, c1_bar, c1_s, c1_phase);
+  };
+
+  if (n > 0) pass1_post(0);
+  for (int k = 0; k < n; ++k) {
+    if (k == 0) tl_mark(p, 2);
+    const uint32_t par = (uint32_t)(k & 1), ph = (uint32_t)((k >> 1) & 1);
+    const uint32_t cl_bar = par ? cl_bar_odd : cl_bar_even;
+    mbar_wait(red_bar + 8u * par, ph);
+    float tot = 0.f;
+    {
+      const float* set = red_slots + par * (kRedSetBytes / 4);
+#pragma unroll
+      for (int w4 = 0; w4 < (WPG + 3) / 4; ++w4) {
+        const float4 t = *reinterpret_cast<const float4*>(set + 4 * w4);
+        if constexpr (WPG >= 4) {
+          tot += (t.x + t.y) + (t.z + t.w);
+        } else {
+          tot += t.x + t.y;
+        }
+      }
+    }
+    if (g.csize > 1) {
+      if (g.gtid == 0) mbar_arrive_expect_tx(cl_bar, g.csize * 4);
+      if ((uint32_t)g.gtid < g.csize) {
+        const uint32_t r = (uint32_t)g.gtid;
+        st_async_f32(map_to_cta(smem0 + cls_off + par * kClsSetBytes + (g.crank * kRedNV) * 4, r), tot,
+                     map_to_cta(cl_bar, r));
+      }
+    }
+    if (k + 1 < n) pass1_post(k + 1);
+    if (g.csize > 1) {
+      mbar_wait(cl_bar, ph);
+      const volatile float* slots = reinterpret_cast<const volatile float*>(smem_raw + cls_off + par * kClsSetBytes);
+      tot = 0.f;
+      for (uint32_t r = 0; r < g.csize; ++r) tot += slots[r * kRedNV];
+    }
+    const float var_eps = tot * p.inv_n + p.eps;
+    const float invstd = rsqrt_fast(var_eps);
+    const float rms = var_eps * invstd;
+    const float2 scale = f2(invstd);
+    const int64_t row = row_first + (int64_t)k * row_step;
+    const uint8_t* xrow = smem_raw + c2_off + 16u * (uint32_t)g.gtid;
+    uint8_t* yrow = out_row_ptr<T>(p, row, g.crank, g.gtid);
+    for_each_chunk<TPR, CH>(g.gtid, nchunks, [&](int j, int coff) {
+      float2 y[H], w[H];
+      IO<T>::unpack2(ld_smem_u4(xrow + 16 * coff), y);
+      IO<T>::unpack2(wq[j], w);
+#pragma unroll
+      for (int q = 0; q < H; ++q) y[q] = f2mul(f2mul(y[q], scale), w[q]);
+      st_global_stream(yrow + 16 * coff, IO<T>::pack2(y));
+    });
+    if (stat_writer) p.stat1[row] = stat_rms ? rms : invstd;
+    __syncwarp();
+    if (g.lane == 0) mbar_arrive(free_bar + 8u * c2_s);
+    if (g.warp == 0) {
+      mbar_wait(free_bar + 8u * c2_s, c2_phase);
+      if (k + p.depth < n) ring.issue_rows(1, row_first + (int64_t)(k + p.depth) * row_step, c2_off, c2_bar);
+    }
+    advance(c2_off, c2_bar, c2_s, c2_phase);
+  }
+  tl_mark(p, 3);
+  ring_teardown(p);
+  tl_mark(p, 6);
+}
+
 }  // namespace b200norm

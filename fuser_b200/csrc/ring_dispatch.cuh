@@ -26,5 +26,9 @@ RingKernel ring_bwd_kernel_f16(int op, int tpr, int ch, bool cached);
 RingKernel ring_bwd_pipe_kernel_f32(int op, int tpr, int ch);
 RingKernel ring_bwd_pipe_kernel_bf16(int op, int tpr, int ch);
 RingKernel ring_bwd_pipe_kernel_f16(int op, int tpr, int ch);
+// pipelined RMSNorm forward (cluster rows)
+RingKernel ring_fwd_pipe_kernel_f32(int op, int tpr, int ch);
+RingKernel ring_fwd_pipe_kernel_bf16(int op, int tpr, int ch);
+RingKernel ring_fwd_pipe_kernel_f16(int op, int tpr, int ch);
 
 }  // namespace b200norm

@@ -3,6 +3,7 @@
 
 #include "../../include/b200norm.h"
 #include "kernels_bwd.cuh"
+#include "kernels_fwd.cuh"
 #include "ring_dispatch.cuh"
 
 namespace b200norm {
@@ -24,6 +25,30 @@ RingKernel ring_bwd_pipe_kernel_for(int op, int tpr, int ch) {
     default: return nullptr;
   }
 #undef B200_PIPE_CASE
+}
+
+// RMSNorm forward, pipelined (cluster rows): ch in {1..4} (tpr 64 / 128), {1..6} (tpr 256 / 512)
+template <typename T>
+RingKernel ring_fwd_pipe_kernel_for(int op, int tpr, int ch) {
+  if (op != B200NORM_OP_RMSNORM_FWD) return nullptr;
+#define B200_FPIPE_CH(TPR, MAXCH)                                              \
+  switch (ch) {                                                               \
+    case 1: return rmsnorm_fwd_pipe_kernel<T, TPR, 1>;                        \
+    case 2: return rmsnorm_fwd_pipe_kernel<T, TPR, 2>;                        \
+    case 3: return rmsnorm_fwd_pipe_kernel<T, TPR, 3>;                        \
+    case 4: return rmsnorm_fwd_pipe_kernel<T, TPR, 4>;                        \
+    case 5: if (MAXCH >= 5) return rmsnorm_fwd_pipe_kernel<T, TPR, (MAXCH >= 5 ? 5 : 1)>; return nullptr; \
+    case 6: if (MAXCH >= 6) return rmsnorm_fwd_pipe_kernel<T, TPR, (MAXCH >= 6 ? 6 : 1)>; return nullptr; \
+    default: return nullptr;                                                  \
+  }
+  switch (tpr) {
+    case 64: B200_FPIPE_CH(64, 4)
+    case 128: B200_FPIPE_CH(128, 4)
+    case 256: B200_FPIPE_CH(256, 6)
+    case 512: B200_FPIPE_CH(512, 6)
+    default: return nullptr;
+  }
+#undef B200_FPIPE_CH
 }
 
 }  // namespace b200norm
