@@ -341,7 +341,12 @@ bool try_ring_plan(const b200norm_desc& d, const DeviceInfo& dev, int C, bool ro
         ch = 0;
         cached = false;
       }
-    } else if (tpr == 512 && forced_tpr == 0 && nchunks <= 256 * kFwdWideCH) {
+    } else if (tpr == 512 && forced_tpr == 0 && nchunks <= 256 * kFwdWideCH &&
+               !(d.op == B200NORM_OP_RMSNORM_FWD && es == 2 && (nchunks + 255) / 256 == 6 &&
+                 env_int("B200NORM_NO_PIPE") == 0)) {
+      // (16-bit RMSNorm forward at six chunks per thread — N = 12288 — keeps the single 512-thread
+      // group: its pipelined kernel beats two 256-thread groups there, 252 vs 275 us; at five chunks
+      // (N = 10240: 109 vs 123 us) and at N = 16384 (162 vs 178 us) the register-resident kernels win)
       tpr = 256;
       ch = (nchunks + 255) / 256;
     }
@@ -450,7 +455,11 @@ bool try_ring_plan(const b200norm_desc& d, const DeviceInfo& dev, int C, bool ro
            (C > 1 || es == 4 || env_int("B200NORM_PIPE") != 0);
   // RMSNorm forward over a cluster: the same pipeline (the row is read twice from its stage instead
   // of being held in registers, so the next row's sum of squares overlaps the DSMEM exchange)
-  if (d.op == B200NORM_OP_RMSNORM_FWD && !add && (C > 1 || env_int("B200NORM_PIPE") != 0) && ch > 0 &&
+  // ... and for rows wide enough to need one 512-thread group per CTA; with several groups per
+  // CTA the groups already overlap each other and the second smem pass only costs (N = 8192: 85 vs 95 us).
+  // (16-bit only: the fp32 single-group kernel is at the roofline already, 163 vs 182 us at N = 8192)
+  if (d.op == B200NORM_OP_RMSNORM_FWD && !add &&
+      (C > 1 || (tpr == 512 && es == 2 && ch == 3 && (nchunks + 255) / 256 == 6) || env_int("B200NORM_PIPE") != 0) && ch > 0 &&
       tile_rows == 1 && tpr >= 64 && (ch <= 4 || tpr >= 256) && env_int("B200NORM_NO_PIPE") == 0) {
     p.pipe = true;
   }
