@@ -87,3 +87,39 @@ def test_dynamic_every_row_written_once():
                 os.environ.pop("B200NORM_STATIC", None)
         assert torch.equal(y, ref), f"launch {it} differs"
         assert torch.isfinite(st).all()
+
+
+def test_cuda_graph_replay_of_the_c2_step():
+    """The forward + backward step captured in a CUDA graph and replayed: the in-kernel state
+    (grid-barrier word, tile-pool tickets, done counter) must return to its rest value after every
+    launch, so replays reproduce the eager results bit for bit."""
+    m, n = 16384, 4096
+    x, dy, w, _ = make_inputs(m, n, torch.bfloat16, seed=11)
+    xd, dyd, wd = x.cuda(), dy.cuda(), w.cuda()
+    big = torch.randn(40000, 512, device="cuda", dtype=torch.bfloat16)  # a pool-scheduled forward as well
+    y0, r0 = ops.rms_norm_fwd(xd, wd, 1e-5, stat_is_rms=True)
+    dx0, dw0 = ops.rms_norm_bwd(dyd, xd, r0, wd, stat_is_rms=True)
+    s0 = ops.softmax_fwd(big)
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):  # warm-up on the capture stream: workspace, kernel attributes
+            y, r = ops.rms_norm_fwd(xd, wd, 1e-5, stat_is_rms=True)
+            ops.rms_norm_bwd(dyd, xd, r, wd, stat_is_rms=True)
+            ops.softmax_fwd(big)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        y, r = ops.rms_norm_fwd(xd, wd, 1e-5, stat_is_rms=True)
+        dx, dw = ops.rms_norm_bwd(dyd, xd, r, wd, stat_is_rms=True)
+        s = ops.softmax_fwd(big)
+    for it in range(3):
+        for t in (y, r, dx, dw, s):
+            t.zero_()
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(y, y0) and torch.equal(r, r0), f"replay {it}: forward differs"
+        assert torch.equal(dx, dx0) and torch.equal(dw, dw0), f"replay {it}: backward differs"
+        assert torch.equal(s, s0), f"replay {it}: softmax differs"
