@@ -66,6 +66,7 @@ F_OUT_SUM = 1 << 14
 F_ROUND_SUM = 1 << 15
 F_PEER_REDUCE = 1 << 16
 F_PEER_PUBLISH = 1 << 17
+F_OUTER = 1 << 18
 
 VARIANT_AUTO, VARIANT_GENERIC, VARIANT_TMA, VARIANT_CLUSTER = 0, 1, 2, 3
 

@@ -20,6 +20,7 @@
 #include <unordered_map>
 
 #include "kernels_generic.cuh"
+#include "outer.cuh"
 #include "ring_dispatch.cuh"
 
 using namespace b200norm;
@@ -85,6 +86,8 @@ int elem_size(int dt) { return dt == B200NORM_DT_F32 ? 4 : 2; }
 
 bool is_row_op(int op) { return op >= B200NORM_OP_LAYERNORM_FWD && op <= B200NORM_OP_LOGSOFTMAX_BWD; }
 bool is_norm_bwd(int op) { return op == B200NORM_OP_LAYERNORM_BWD || op == B200NORM_OP_RMSNORM_BWD; }
+bool is_softmax_op(int op) { return op >= B200NORM_OP_SOFTMAX_FWD && op <= B200NORM_OP_LOGSOFTMAX_BWD; }
+bool is_outer(const b200norm_desc& d) { return (d.flags & B200NORM_F_OUTER) != 0; }
 bool is_add_fwd(const b200norm_desc& d) {
   return (d.op == B200NORM_OP_LAYERNORM_FWD || d.op == B200NORM_OP_RMSNORM_FWD) && (d.flags & B200NORM_F_ADD_RESIDUAL);
 }
@@ -563,6 +566,22 @@ int make_plan(const b200norm_desc& d, bool aligned, bool rows_contiguous, Plan* 
   return B200NORM_OK;
 }
 
+OuterArgs outer_args_from(const b200norm_desc& d) {
+  const DeviceInfo& dev = device_info();
+  OuterArgs a;
+  a.bwd = (d.op == B200NORM_OP_SOFTMAX_BWD || d.op == B200NORM_OP_LOGSOFTMAX_BWD) ? 1 : 0;
+  a.log = (d.op == B200NORM_OP_LOGSOFTMAX_FWD || d.op == B200NORM_OP_LOGSOFTMAX_BWD) ? 1 : 0;
+  a.dtype = d.io_dtype;
+  a.M = d.rows;
+  a.N = d.cols;
+  a.round_sum = (d.flags & B200NORM_F_ROUND_ROWSUM) ? 1 : 0;
+  a.cluster_forced = d.cluster_size != 0 ? d.cluster_size : env_int("B200NORM_CLUSTER");
+  a.has_device = dev.has_device;
+  a.sm_count = dev.sm_count;
+  a.smem_optin = dev.smem_optin;
+  return a;
+}
+
 int check_desc(const b200norm_desc* d) {
   if (d == nullptr) return fail(B200NORM_ERR_BAD_ARG, "null desc");
   if (d->abi_version != B200NORM_ABI_VERSION)
@@ -576,6 +595,8 @@ int check_desc(const b200norm_desc* d) {
       d->cluster_size != 8 && d->cluster_size != 16)
     return fail(B200NORM_ERR_BAD_ARG, "cluster_size must be 0,1,2,4,8,16");
   if (d->variant < 0 || d->variant > B200NORM_VARIANT_CLUSTER) return fail(B200NORM_ERR_BAD_ARG, "bad variant");
+  if ((d->flags & B200NORM_F_OUTER) && !is_softmax_op(d->op))
+    return fail(B200NORM_ERR_UNSUPPORTED, "B200NORM_F_OUTER applies to the softmax / log-softmax ops only");
   if ((d->flags & B200NORM_F_OUT_DW) && !(d->flags & B200NORM_F_HAS_WEIGHT) && is_norm_bwd(d->op))
     return fail(B200NORM_ERR_BAD_ARG, "dweight requested without a weight (the builders return none)");
   return B200NORM_OK;
@@ -912,6 +933,32 @@ int b200norm_device_info(int* has_device, int* sm_count, int* smem_per_block_opt
 int b200norm_query(const b200norm_desc* desc, b200norm_plan* plan) {
   int rc = check_desc(desc);
   if (rc != B200NORM_OK) return rc;
+  if (is_outer(*desc)) {
+    if (desc->variant == B200NORM_VARIANT_GENERIC)
+      return fail(B200NORM_ERR_UNSUPPORTED, "the outer-persistent ops have no generic kernel family");
+    if (plan != nullptr) memset(plan, 0, sizeof(*plan));
+    if (desc->rows == 0 || desc->cols == 0) {
+      if (plan != nullptr) plan->workspace_bytes = B200NORM_WS_HEADER_BYTES;
+      return B200NORM_OK;
+    }
+    OuterPlan op;
+    char msg[256] = "";
+    if (!outer_make_plan(outer_args_from(*desc), &op, msg, sizeof(msg))) return fail(B200NORM_ERR_UNSUPPORTED, "%s", msg);
+    if (plan != nullptr) {
+      plan->variant = op.cluster > 1 ? B200NORM_VARIANT_CLUSTER : B200NORM_VARIANT_TMA;
+      plan->cluster_size = op.cluster;
+      plan->grid_x = op.grid;
+      plan->block_x = op.block;
+      plan->threads_per_row = op.slab_bytes / 16;  // threads across one slab row
+      plan->stages = op.depth;
+      plan->tile_rows = op.rows_cta;
+      plan->smem_bytes = (int32_t)op.smem;
+      plan->n_launches = 1;
+      plan->workspace_bytes = B200NORM_WS_HEADER_BYTES;
+      plan->algorithmic_bytes = algorithmic_bytes(*desc);
+    }
+    return B200NORM_OK;
+  }
   Plan p;
   // rows are assumed 16-byte aligned and contiguous at query time; the launch
   // re-plans with the real pointers (the workspace bound covers both outcomes).
@@ -1159,6 +1206,25 @@ int b200norm_launch(const b200norm_desc* desc, const b200norm_tensor* inputs, in
       if (outputs[o].data != nullptr && outputs[o].data == inputs[i].data)
         return fail(B200NORM_ERR_UNSUPPORTED, "output %d aliases input %d", o, i);
     }
+  }
+
+  if (is_outer(d)) {
+    // outer-persistent softmax family (outer.cu): its own planner and launch
+    if (d.rows == 0 || d.cols == 0) return B200NORM_OK;
+    if (d.variant == B200NORM_VARIANT_GENERIC)
+      return fail(B200NORM_ERR_UNSUPPORTED, "the outer-persistent ops have no generic kernel family");
+    OuterArgs a = outer_args_from(d);
+    a.in0 = rp.in0;
+    a.in1 = rp.in1;
+    a.out = rp.out0;
+    a.in0_stride = rp.in0_stride;
+    a.in1_stride = rp.in1_stride;
+    a.out_stride = rp.out_stride;
+    char msg[256] = "";
+    rc = outer_launch(a, stream_v, msg, sizeof(msg));
+    if (rc != B200NORM_OK) return fail(rc, "%s", msg);
+    g_launches++;
+    return B200NORM_OK;
   }
 
   Plan plan;

@@ -62,6 +62,12 @@ b200norm_tensor as_arg(const at::Tensor& t) {
 // [.., N] -> [M, N] view without a copy (the kernels take any row stride).
 at::Tensor as_rows(const at::Tensor& t, int64_t n) {
   if (t.dim() == 2 && t.size(1) == n) return t;
+  if (t.dim() >= 2 && n > 0 && t.size(0) * n == t.numel() && t.size(-1) != n) {
+    // outer ops: [M, d1, d2, ..] -> [M, d1*d2*..]
+    if (!t.is_contiguous())
+      raise_msg(B200NORM_ERR_UNSUPPORTED, "a non-contiguous tensor of rank > 2 is not viewable as [rows, cols]");
+    return t.view({t.size(0), n});
+  }
   if (t.numel() == 0) return t.reshape({-1, n});
   if (!t.is_contiguous())
     raise_msg(B200NORM_ERR_UNSUPPORTED, "a non-contiguous tensor of rank != 2 is not viewable as [rows, cols]");
@@ -190,6 +196,14 @@ std::vector<at::Tensor> NormExecutor::run(const std::vector<at::Tensor>& inputs,
     rows = (int64_t)outputs.size();
     cols = outputs[0].numel();
     dt = dtype_id(outputs[0].scalar_type());
+  } else if (spec_.flags & B200NORM_F_OUTER) {
+    // outer-persistent ops: the reduction runs over dim 0; everything behind it is the iteration domain
+    if (lead.dim() < 2) raise_msg(B200NORM_ERR_UNSUPPORTED, "an outer reduction needs a tensor of rank >= 2");
+    rows = lead.size(0);
+    cols = rows > 0 ? lead.numel() / rows : 0;
+    if (rows == 0)
+      for (int64_t i = 1, c = 1; i < lead.dim(); ++i) cols = (c *= lead.size(i));
+    dt = dtype_id(lead.scalar_type());
   } else {
     cols = lead.dim() > 0 ? lead.size(-1) : 1;
     rows = cols > 0 ? lead.numel() / cols : 0;

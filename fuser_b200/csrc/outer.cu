@@ -1,0 +1,650 @@
+// outer.cu — outer-persistent softmax / log-softmax, forward and backward (sm_100a).
+//
+// Reduction over dim 0 of a row-major [M, N] matrix: every column is an independent problem, but a
+// column is strided in memory, so the unit of work is a *slab*: W bytes (64-512) of every row. The
+// reference keeps such a slab persistent in registers across a cooperative grid and reduces through
+// global memory (scheduler/normalization_outer.cpp:451-683, runtime/grid_reduction.cu:905-1066,
+// runtime/fused_welford_impl_outer.cu). Here:
+//
+//   * a slab is held in SHARED memory — of one CTA when M*W fits, else of a thread-block cluster
+//     whose CTAs split the rows (rank q holds rows [q*Rc, (q+1)*Rc)) and exchange their per-column
+//     partial results through DSMEM (st.shared::cluster + barrier.cluster), never through HBM;
+//   * a slab tile is fetched with 2-D TMA box loads (cp.async.bulk.tensor.2d, <= 256 rows per box)
+//     that complete on an mbarrier; two tiles per CTA: the next slab streams in while the current
+//     one is reduced and written out. Out-of-range rows / columns are zero-filled by the TMA unit
+//     and masked by index;
+//   * the grid is persistent (clusters walk the slabs round-robin) and sized from the occupancy
+//     API: small tiles run two CTAs per SM so that one CTA's barrier latency hides behind the
+//     other's passes;
+//   * a thread owns one 16-byte column chunk and every (256 / LC)-th row of it: consecutive threads
+//     read consecutive 16-byte words of the tile (conflict-free), per-column partials are combined
+//     with xor-shuffles inside a warp, through shared memory across the 8 warps, and across the
+//     cluster in rank order — a fixed order, so results are deterministic;
+//   * arithmetic is fp32 with the same element formulas as the inner kernels (kernels_fwd.cuh):
+//     NaN-propagating max, exp(x - max), e * rcp(sum) (softmax) or (x - max) - log(sum) (log-softmax);
+//     backward dx = y*dy - y*sum(y*dy) or dy - exp(y)*sum(dy) (csrc/ops/normalization.cpp:169-249).
+//     HBM traffic is the algorithmic minimum: every input element is read once, every output written once.
+#include "outer.cuh"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <unordered_map>
+
+#include "../../include/b200norm.h"
+#include "common.cuh"
+
+namespace b200norm {
+
+extern __shared__ __align__(128) uint8_t outer_smem[];
+
+constexpr int kOuterThreads = 256;
+constexpr int kOuterWarps = kOuterThreads / 32;
+
+struct OuterParams {
+  void* out;
+  int64_t out_stride;  // elements
+  int32_t M, N;
+  int32_t rows_cta;    // Rc: rows of a slab held by one CTA (nboxes * box_rows)
+  int32_t box_rows, nboxes;
+  int32_t slab_cols;   // SC = W / sizeof(T)
+  int32_t lc_shift;    // log2(LC), LC = W / 16 chunks per slab row
+  int32_t nslabs;
+  int32_t cluster;     // C
+  int32_t depth;       // 1 or 2 tiles
+  int32_t round_sum;
+  uint32_t slab_bytes; // W
+  uint32_t tile_bytes; // Rc * W (one stream)
+  uint32_t stage_bytes;  // nstreams * tile_bytes
+  uint32_t off_wpart, off_cls, off_fin, off_tiles;
+};
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int32_t c0, int32_t c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float4 lds_f4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+// Column reduction context: combine the per-thread partials v[VEC] (thread's 16-byte column chunk)
+// over every row of the slab: lanes of a warp that share the chunk, the CTA's warps, the cluster's CTAs.
+struct ColCtx {
+  uint32_t smem0;
+  int tid, lane, warp, c, LC, SC;
+  uint32_t C, crank;
+  uint32_t set;  // cluster slot set, alternates per exchange
+  float* wpart;  // [kOuterWarps][SC]
+  float* cls;    // [2][C][SC]
+  float* fin;    // [SC]
+  uint32_t off_cls;
+};
+
+template <typename Op, int VEC>
+__device__ __forceinline__ void col_reduce(float (&v)[VEC], ColCtx& x) {
+  for (int off = 16; off >= x.LC; off >>= 1) {
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) v[k] = Op::apply(v[k], __shfl_xor_sync(0xffffffffu, v[k], off));
+  }
+  if (x.lane < x.LC) {  // lane == chunk index for these lanes
+    float* dst = x.wpart + x.warp * x.SC + x.c * VEC;
+#pragma unroll
+    for (int k = 0; k < VEC; k += 4) *reinterpret_cast<float4*>(dst + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+  }
+  __syncthreads();
+  if (x.tid < x.SC) {
+    float a = x.wpart[x.tid];
+#pragma unroll
+    for (int w = 1; w < kOuterWarps; ++w) a = Op::apply(a, x.wpart[w * x.SC + x.tid]);
+    if (x.C > 1) {
+      const uint32_t local = x.smem0 + x.off_cls + ((x.set * x.C + x.crank) * (uint32_t)x.SC + (uint32_t)x.tid) * 4u;
+      for (uint32_t q = 0; q < x.C; ++q) st_cluster_f32(map_to_cta(local, q), a);
+    } else {
+      x.fin[x.tid] = a;
+    }
+  }
+  if (x.C > 1) {
+    cluster_sync_all();
+    if (x.tid < x.SC) {
+      const float* s = x.cls + (size_t)x.set * x.C * x.SC + x.tid;
+      float a = s[0];
+      for (uint32_t q = 1; q < x.C; ++q) a = Op::apply(a, s[q * x.SC]);
+      x.fin[x.tid] = a;
+    }
+    x.set ^= 1u;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < VEC; k += 4) {
+    const float4 t = lds_f4(x.fin + x.c * VEC + k);
+    v[k] = t.x;
+    v[k + 1] = t.y;
+    v[k + 2] = t.z;
+    v[k + 3] = t.w;
+  }
+}
+
+template <typename T, bool BWD, bool LOG>
+__global__ void __launch_bounds__(kOuterThreads, 2)
+outer_softmax_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
+                     const OuterParams p) {
+  constexpr int VEC = IO<T>::VEC;
+  constexpr uint32_t kStep = kOuterThreads * 16;  // bytes between a thread's consecutive chunks
+  const uint32_t smem0 = smem_u32(outer_smem);
+  const int tid = threadIdx.x;
+
+  ColCtx cx;
+  cx.smem0 = smem0;
+  cx.tid = tid;
+  cx.lane = tid & 31;
+  cx.warp = tid >> 5;
+  cx.LC = 1 << p.lc_shift;
+  cx.SC = p.slab_cols;
+  cx.c = tid & (cx.LC - 1);
+  cx.C = (uint32_t)p.cluster;
+  cx.crank = cx.C > 1 ? cluster_ctarank() : 0u;
+  cx.set = 0;
+  cx.wpart = reinterpret_cast<float*>(outer_smem + p.off_wpart);
+  cx.cls = reinterpret_cast<float*>(outer_smem + p.off_cls);
+  cx.fin = reinterpret_cast<float*>(outer_smem + p.off_fin);
+  cx.off_cls = p.off_cls;
+
+  const int r0 = tid >> p.lc_shift;
+  const int rstep = kOuterThreads >> p.lc_shift;
+  const int cid = (int)(blockIdx.x / cx.C);
+  const int nclusters = (int)(gridDim.x / cx.C);
+  const int row_base = (int)cx.crank * p.rows_cta;
+  int rows_valid = p.M - row_base;
+  if (rows_valid > p.rows_cta) rows_valid = p.rows_cta;
+  if (rows_valid < 0) rows_valid = 0;
+  // chunks of this thread: rows r0 + j*rstep < rows_valid
+  const int nj = rows_valid > r0 ? (rows_valid - r0 + rstep - 1) / rstep : 0;
+
+  const uint32_t bar0 = smem0;  // full[2]
+  if (tid == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (cx.C > 1) cluster_sync_all();  // every CTA of the cluster is resident before any DSMEM store
+  pdl_wait();
+
+  auto issue = [&](int slab, uint32_t buf) {
+    const uint32_t bar = bar0 + 8u * buf;
+    mbar_arrive_expect_tx(bar, p.stage_bytes);
+    uint32_t dst = smem0 + p.off_tiles + buf * p.stage_bytes;
+    const int32_t col = slab * p.slab_cols;
+    const uint32_t box_bytes = (uint32_t)p.box_rows * p.slab_bytes;
+    for (int b = 0; b < p.nboxes; ++b) tma_load_2d(dst + (uint32_t)b * box_bytes, &map0, col, row_base + b * p.box_rows, bar);
+    if constexpr (BWD) {
+      dst += p.tile_bytes;
+      for (int b = 0; b < p.nboxes; ++b) tma_load_2d(dst + (uint32_t)b * box_bytes, &map1, col, row_base + b * p.box_rows, bar);
+    }
+  };
+
+  int slab = cid;
+  if (slab < p.nslabs && tid == 0) issue(slab, 0);
+  const size_t out_row_bytes = (size_t)p.out_stride * sizeof(T);
+  const size_t out_step = out_row_bytes * (size_t)rstep;
+  for (int it = 0; slab < p.nslabs; slab += nclusters, ++it) {
+    const uint32_t buf = p.depth == 2 ? (uint32_t)(it & 1) : 0u;
+    const uint32_t phase = p.depth == 2 ? (uint32_t)((it >> 1) & 1) : (uint32_t)(it & 1);
+    const int next = slab + nclusters;
+    // the other tile was released by the __syncthreads that ended the previous iteration
+    if (p.depth == 2 && next < p.nslabs && tid == 0) issue(next, buf ^ 1u);
+    mbar_wait(bar0 + 8u * buf, phase);
+
+    const uint8_t* t0 = outer_smem + p.off_tiles + buf * p.stage_bytes + (uint32_t)tid * 16u;
+    const int col = slab * p.slab_cols + cx.c * VEC;
+    const bool col_ok = col < p.N;
+    uint8_t* o = static_cast<uint8_t*>(p.out) + (size_t)(row_base + r0) * out_row_bytes + (size_t)col * sizeof(T);
+
+    if constexpr (!BWD) {
+      float m[VEC];
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) m[k] = -INFINITY;
+#pragma unroll 4
+      for (int j = 0; j < nj; ++j) {
+        float x[VEC];
+        IO<T>::unpack(*reinterpret_cast<const uint4*>(t0 + (uint32_t)j * kStep), x);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) m[k] = MaxOp::apply(m[k], x[k]);
+      }
+      col_reduce<MaxOp, VEC>(m, cx);
+      float s[VEC];
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) s[k] = 0.f;
+#pragma unroll 4
+      for (int j = 0; j < nj; ++j) {
+        float x[VEC];
+        IO<T>::unpack(*reinterpret_cast<const uint4*>(t0 + (uint32_t)j * kStep), x);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) s[k] += exp_for<T>(x[k] - m[k]);
+      }
+      col_reduce<SumOp, VEC>(s, cx);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) s[k] = LOG ? -logf(s[k]) : rcp_fast(s[k]);
+      if (col_ok) {
+#pragma unroll 4
+        for (int j = 0; j < nj; ++j) {
+          float x[VEC];
+          IO<T>::unpack(*reinterpret_cast<const uint4*>(t0 + (uint32_t)j * kStep), x);
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) {
+            const float d = x[k] - m[k];
+            x[k] = LOG ? d + s[k] : exp_for<T>(d) * s[k];
+          }
+          stg_128_stream(o + (size_t)j * out_step, IO<T>::pack(x));
+        }
+      }
+    } else {
+      const uint8_t* t1 = t0 + p.tile_bytes;  // y
+      float s[VEC];
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) s[k] = 0.f;
+#pragma unroll 4
+      for (int j = 0; j < nj; ++j) {
+        float dy[VEC], y[VEC];
+        IO<T>::unpack(*reinterpret_cast<const uint4*>(t0 + (uint32_t)j * kStep), dy);
+        if constexpr (LOG) {
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) s[k] += dy[k];
+        } else {
+          IO<T>::unpack(*reinterpret_cast<const uint4*>(t1 + (uint32_t)j * kStep), y);
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) s[k] += y[k] * dy[k];
+        }
+      }
+      col_reduce<SumOp, VEC>(s, cx);
+      if (p.round_sum) {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) s[k] = IO<T>::round_trip(s[k]);
+      }
+      if (col_ok) {
+#pragma unroll 4
+        for (int j = 0; j < nj; ++j) {
+          float dy[VEC], y[VEC];
+          IO<T>::unpack(*reinterpret_cast<const uint4*>(t0 + (uint32_t)j * kStep), dy);
+          IO<T>::unpack(*reinterpret_cast<const uint4*>(t1 + (uint32_t)j * kStep), y);
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) {
+            if constexpr (LOG) {
+              dy[k] = fmaf(expf(y[k]), -s[k], dy[k]);
+            } else {
+              dy[k] = fmaf(y[k], -s[k], y[k] * dy[k]);
+            }
+          }
+          stg_128_stream(o + (size_t)j * out_step, IO<T>::pack(dy));
+        }
+      }
+    }
+    __syncthreads();  // every thread is done with tile `buf` (and with fin / wpart)
+    if (p.depth == 1 && next < p.nslabs && tid == 0) issue(next, 0);
+  }
+  pdl_launch_dependents();
+  if (cx.C > 1) cluster_sync_all();  // no CTA leaves while a peer may still store into its slots
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+namespace {
+
+int set_err(char* err, size_t n, int code, const char* fmt, ...) {
+  if (err != nullptr && n > 0) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(err, n, fmt, ap);
+    va_end(ap);
+  }
+  return code;
+}
+
+int env_int_outer(const char* name) {
+  const char* v = getenv(name);
+  return (v != nullptr && *v != 0) ? atoi(v) : 0;
+}
+
+using OuterKernel = void (*)(const CUtensorMap, const CUtensorMap, const OuterParams);
+
+template <typename T>
+OuterKernel outer_kernel_typed(bool bwd, bool log) {
+  if (bwd) return log ? outer_softmax_kernel<T, true, true> : outer_softmax_kernel<T, true, false>;
+  return log ? outer_softmax_kernel<T, false, true> : outer_softmax_kernel<T, false, false>;
+}
+OuterKernel outer_kernel_for(int dt, bool bwd, bool log) {
+  switch (dt) {
+    case B200NORM_DT_F32: return outer_kernel_typed<float>(bwd, log);
+    case B200NORM_DT_BF16: return outer_kernel_typed<__nv_bfloat16>(bwd, log);
+    case B200NORM_DT_F16: return outer_kernel_typed<__half>(bwd, log);
+    default: return nullptr;
+  }
+}
+
+uint32_t up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
+
+constexpr int kSmemPerSm = 233472;  // 228 KB per SM on sm_100; each resident CTA reserves 1 KB
+
+struct Geometry {
+  int rows_cta, box_rows, nboxes;
+  uint32_t tile, stage, overhead;
+};
+
+Geometry geometry(const OuterArgs& a, int W, int C) {
+  const int es = a.dtype == B200NORM_DT_F32 ? 4 : 2;
+  const int ns = a.bwd ? 2 : 1;
+  Geometry g;
+  int64_t rc = (a.M + C - 1) / C;
+  if (rc <= 256) {
+    rc = (rc + 7) / 8 * 8;
+    g.box_rows = (int)rc;
+  } else {
+    rc = (rc + 127) / 128 * 128;
+    g.box_rows = 128;
+  }
+  g.rows_cta = (int)rc;
+  g.nboxes = g.rows_cta / g.box_rows;
+  g.tile = (uint32_t)g.rows_cta * (uint32_t)W;
+  g.stage = (uint32_t)ns * g.tile;
+  const uint32_t sc = (uint32_t)(W / es);
+  g.overhead = up(128 + kOuterWarps * sc * 4 + (C > 1 ? 2u * (uint32_t)C * sc * 4 : 0u) + sc * 4, 128);
+  return g;
+}
+
+}  // namespace
+
+bool outer_make_plan(const OuterArgs& a, OuterPlan* plan, char* err, size_t errlen) {
+  const int es = a.dtype == B200NORM_DT_F32 ? 4 : 2;
+  if (a.M < 1 || a.N < 1) {
+    set_err(err, errlen, 0, "outer softmax: empty problem");
+    return false;
+  }
+  if ((a.N * es) % 16 != 0) {
+    set_err(err, errlen, 0, "outer softmax: N * sizeof(T) = %lld is not a multiple of 16", (long long)(a.N * es));
+    return false;
+  }
+  if (a.M > (int64_t)1 << 24 || a.N > 0x7fffffffLL) {
+    set_err(err, errlen, 0, "outer softmax: extents out of range");
+    return false;
+  }
+  const int64_t row_bytes = a.N * es;
+  // widest slab that still gives every SM a couple of slabs
+  int wpref = 128;
+  for (int w : {512, 256}) {
+    if ((row_bytes + w - 1) / w >= 2 * (int64_t)a.sm_count) {
+      wpref = w;
+      break;
+    }
+  }
+  const int forced_w = env_int_outer("B200NORM_OUTER_W");
+  const int forced_depth = env_int_outer("B200NORM_OUTER_DEPTH");
+  const int64_t limit2 = kSmemPerSm / 2 - 1024;  // two CTAs per SM
+  const int64_t limit1 = a.smem_optin;
+  struct Tier {
+    int depth;
+    int64_t limit;
+  };
+  const Tier tiers[] = {{2, limit2}, {2, limit1}, {1, limit1}};
+  static const int cs[] = {1, 2, 4, 8, 16};
+  int W = 0, C = 0, depth = 0;
+  for (const Tier& t : tiers) {
+    if (forced_depth != 0 && t.depth != forced_depth) continue;
+    for (int w : {512, 256, 128, 64}) {
+      if (forced_w != 0 ? w != forced_w : w > wpref) continue;
+      for (int c : cs) {
+        if (a.cluster_forced != 0 && c != a.cluster_forced) continue;
+        const Geometry g = geometry(a, w, c);
+        if ((int64_t)g.overhead + (int64_t)t.depth * g.stage <= t.limit) {
+          W = w;
+          C = c;
+          depth = t.depth;
+          break;
+        }
+      }
+      if (W != 0) break;
+    }
+    if (W != 0) break;
+  }
+  if (W == 0) {
+    set_err(err, errlen, 0,
+            "outer softmax: M = %lld does not fit the shared memory of a 16-CTA cluster (the reference segments "
+            "such fusions too)",
+            (long long)a.M);
+    return false;
+  }
+  int64_t nslabs = (row_bytes + W - 1) / W;
+  // few slabs: split the rows over more CTAs so that more SMs stream
+  while (a.cluster_forced == 0 && C < 16 && nslabs * C < a.sm_count && (a.M + 2 * C - 1) / (2 * C) >= 32) C *= 2;
+  const Geometry g = geometry(a, W, C);
+  OuterPlan p;
+  p.cluster = C;
+  p.block = kOuterThreads;
+  p.slab_bytes = W;
+  p.rows_cta = g.rows_cta;
+  p.box_rows = g.box_rows;
+  p.depth = depth;
+  p.tile_bytes = g.tile;
+  p.stage_bytes = g.stage;
+  const uint32_t sc = (uint32_t)(W / es);
+  uint32_t off = 128;
+  p.off_wpart = off;
+  off += kOuterWarps * sc * 4;
+  p.off_cls = off;
+  if (C > 1) off += 2u * (uint32_t)C * sc * 4;
+  p.off_fin = off;
+  off += sc * 4;
+  off = up(off, 128);
+  p.off_tiles = off;
+  p.smem = off + (uint32_t)depth * g.stage;
+  p.nslabs = (int)nslabs;
+  int per_sm = (int)(kSmemPerSm / ((int64_t)p.smem + 1024));
+  if (per_sm > 2) per_sm = 2;  // __launch_bounds__(256, 2)
+  if (per_sm < 1) per_sm = 1;
+  p.ctas_per_sm = per_sm;
+  int64_t nclusters = C > 1 ? (int64_t)8 * (18 / C) * per_sm : (int64_t)a.sm_count * per_sm;  // nominal; refined at launch
+  if (nclusters < 1) nclusters = 1;
+  if (nclusters > nslabs) nclusters = nslabs;
+  p.grid = (int)(nclusters * C);
+  *plan = p;
+  return true;
+}
+
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult st;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &st) == cudaSuccess &&
+        st == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    } else {
+      (void)cudaGetLastError();
+    }
+  });
+  return fn;
+}
+
+bool make_map(CUtensorMap* map, const OuterArgs& a, const void* base, int64_t row_stride, int W, int box_rows) {
+  const int es = a.dtype == B200NORM_DT_F32 ? 4 : 2;
+  const CUtensorMapDataType dt = a.dtype == B200NORM_DT_F32    ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                 : a.dtype == B200NORM_DT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                                               : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  const cuuint64_t dims[2] = {(cuuint64_t)a.N, (cuuint64_t)a.M};
+  const cuuint64_t strides[1] = {(cuuint64_t)((a.M > 1 ? row_stride : a.N) * es)};
+  const cuuint32_t box[2] = {(cuuint32_t)(W / es), (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  EncodeTiledFn fn = encode_fn();
+  if (fn == nullptr) return false;
+  return fn(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) ==
+         CUDA_SUCCESS;
+}
+
+// resident clusters (C > 1) or CTAs (C == 1) of this launch shape on the current device
+int resident_units(OuterKernel k, int smem, int C, int sm_count) {
+  static std::mutex mu;
+  static std::unordered_map<uint64_t, int> cache;
+  const uint64_t key = (reinterpret_cast<uint64_t>((const void*)k) << 6) ^ ((uint64_t)smem << 8) ^ (uint64_t)C;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+  }
+  int n = 0;
+  if (C > 1) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(sm_count / C * C * 2));
+    cfg.blockDim = dim3(kOuterThreads);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = (unsigned)C;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    if (cudaOccupancyMaxActiveClusters(&n, (const void*)k, &cfg) != cudaSuccess) {
+      (void)cudaGetLastError();
+      n = 0;
+    }
+    if (n <= 0) n = 8 * (18 / C) > 0 ? 8 * (18 / C) : 1;
+  } else {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k, kOuterThreads, (size_t)smem) != cudaSuccess) {
+      (void)cudaGetLastError();
+      per_sm = 0;
+    }
+    if (per_sm < 1) per_sm = 1;
+    n = per_sm * sm_count;
+  }
+  std::lock_guard<std::mutex> lock(mu);
+  cache[key] = n;
+  return n;
+}
+
+}  // namespace
+
+int outer_launch(const OuterArgs& a, void* stream_v, char* err, size_t errlen) {
+  OuterPlan pl;
+  if (!outer_make_plan(a, &pl, err, errlen)) return B200NORM_ERR_UNSUPPORTED;
+  const int es = a.dtype == B200NORM_DT_F32 ? 4 : 2;
+  auto aligned = [&](const void* ptr, int64_t stride) {
+    return (reinterpret_cast<uintptr_t>(ptr) & 15u) == 0 && (a.M <= 1 || (stride * es) % 16 == 0);
+  };
+  if (!aligned(a.in0, a.in0_stride) || !aligned(a.out, a.out_stride) || (a.bwd && !aligned(a.in1, a.in1_stride)))
+    return set_err(err, errlen, B200NORM_ERR_UNSUPPORTED, "outer softmax: operands must be 16-byte aligned (base and row stride)");
+
+  OuterKernel k = outer_kernel_for(a.dtype, a.bwd != 0, a.log != 0);
+  if (k == nullptr) return set_err(err, errlen, B200NORM_ERR_UNSUPPORTED, "outer softmax: dtype %d", a.dtype);
+  {
+    static std::mutex mu;
+    static std::unordered_map<const void*, std::pair<int, int>> done;
+    std::lock_guard<std::mutex> lock(mu);
+    auto& st = done[(const void*)k];
+    if ((int)pl.smem > st.first) {
+      cudaError_t e = cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+      if (e != cudaSuccess) return set_err(err, errlen, B200NORM_ERR_CUDA + (int)e, "outer smem attr: %s", cudaGetErrorString(e));
+      st.first = (int)pl.smem;
+    }
+    if (pl.cluster > 8 && !st.second) {
+      cudaError_t e = cudaFuncSetAttribute((const void*)k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      if (e != cudaSuccess) return set_err(err, errlen, B200NORM_ERR_CUDA + (int)e, "outer cluster attr: %s", cudaGetErrorString(e));
+      st.second = 1;
+    }
+  }
+  int64_t units = resident_units(k, (int)pl.smem, pl.cluster, a.sm_count);
+  if (int g = env_int_outer("B200NORM_OUTER_UNITS")) units = g;
+  if (units > pl.nslabs) units = pl.nslabs;
+  if (units < 1) units = 1;
+
+  CUtensorMap map0, map1;
+  memset(&map0, 0, sizeof(map0));
+  memset(&map1, 0, sizeof(map1));
+  if (!make_map(&map0, a, a.in0, a.in0_stride, pl.slab_bytes, pl.box_rows))
+    return set_err(err, errlen, B200NORM_ERR_CUDA, "outer softmax: cuTensorMapEncodeTiled failed for input 0");
+  if (a.bwd) {
+    if (!make_map(&map1, a, a.in1, a.in1_stride, pl.slab_bytes, pl.box_rows))
+      return set_err(err, errlen, B200NORM_ERR_CUDA, "outer softmax: cuTensorMapEncodeTiled failed for input 1");
+  } else {
+    map1 = map0;
+  }
+
+  OuterParams p;
+  memset(&p, 0, sizeof(p));
+  p.out = a.out;
+  p.out_stride = a.M > 1 ? a.out_stride : a.N;
+  p.M = (int32_t)a.M;
+  p.N = (int32_t)a.N;
+  p.rows_cta = pl.rows_cta;
+  p.box_rows = pl.box_rows;
+  p.nboxes = pl.rows_cta / pl.box_rows;
+  p.slab_cols = pl.slab_bytes / es;
+  int lc = pl.slab_bytes / 16, sh = 0;
+  while ((1 << sh) < lc) ++sh;
+  p.lc_shift = sh;
+  p.nslabs = pl.nslabs;
+  p.cluster = pl.cluster;
+  p.depth = pl.depth;
+  p.round_sum = a.round_sum;
+  p.slab_bytes = (uint32_t)pl.slab_bytes;
+  p.tile_bytes = pl.tile_bytes;
+  p.stage_bytes = pl.stage_bytes;
+  p.off_wpart = pl.off_wpart;
+  p.off_cls = pl.off_cls;
+  p.off_fin = pl.off_fin;
+  p.off_tiles = pl.off_tiles;
+
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(units * pl.cluster));
+  cfg.blockDim = dim3(kOuterThreads);
+  cfg.dynamicSmemBytes = pl.smem;
+  cfg.stream = static_cast<cudaStream_t>(stream_v);
+  cudaLaunchAttribute attrs[2];
+  int na = 0;
+  attrs[na].id = cudaLaunchAttributeClusterDimension;
+  attrs[na].val.clusterDim.x = (unsigned)pl.cluster;
+  attrs[na].val.clusterDim.y = 1;
+  attrs[na].val.clusterDim.z = 1;
+  ++na;
+  if (env_int_outer("B200NORM_NO_PDL") == 0) {
+    attrs[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attrs[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attrs;
+  cfg.numAttrs = (unsigned)na;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, k, map0, map1, p);
+  if (e != cudaSuccess && na == 2) {  // retry without programmatic serialization
+    (void)cudaGetLastError();
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, k, map0, map1, p);
+  }
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    return set_err(err, errlen, B200NORM_ERR_CUDA + (int)e, "outer softmax launch failed: %s", cudaGetErrorString(e));
+  }
+  if (env_int_outer("B200NORM_DEBUG") > 1)
+    fprintf(stderr, "[b200norm] outer softmax bwd=%d log=%d W=%d C=%d Rc=%d depth=%d grid=%d smem=%u\n", a.bwd, a.log,
+            pl.slab_bytes, pl.cluster, pl.rows_cta, pl.depth, (int)(units * pl.cluster), pl.smem);
+  return B200NORM_OK;
+}
+
+}  // namespace b200norm

@@ -1,0 +1,57 @@
+// outer.cuh — host interface of the outer-persistent kernels (outer.cu): softmax / log-softmax
+// forward and backward with the reduction over dim 0 of a row-major [M, N] matrix.
+//
+// These are the segments nvFuser's OuterPersistentKernelScheduler takes
+// (reference: scheduler/normalization_outer.cpp:451-683; device side
+// runtime/fused_welford_impl_outer.cu:222-438, runtime/grid_reduction.cu:905-1066; benchmark
+// definitions benchmarks/python/test_softmax_{fwd,bwd}.py with reduction_axis = 0, pytest mark
+// `outer_persistent`). The design here is not the reference's register-persistent grid reduction:
+// a column slab lives in the shared memory of one CTA or of a thread-block cluster split along M
+// (2-D TMA tile loads, DSMEM exchange of the per-column partials) — see outer.cu.
+#pragma once
+
+#include <stddef.h>
+#include <stdint.h>
+
+namespace b200norm {
+
+struct OuterArgs {
+  int bwd = 0;        // 0: forward (in0 = x), 1: backward (in0 = dy, in1 = y)
+  int log = 0;        // log-softmax flavour
+  int dtype = 0;      // b200norm_dtype
+  int64_t M = 0;      // reduced extent (rows)
+  int64_t N = 0;      // iteration extent (columns, unit stride)
+  const void* in0 = nullptr;
+  const void* in1 = nullptr;
+  void* out = nullptr;
+  int64_t in0_stride = 0, in1_stride = 0, out_stride = 0;  // row strides in elements
+  int round_sum = 0;       // backward: round the column sum through the io dtype (B200NORM_F_ROUND_ROWSUM)
+  int cluster_forced = 0;  // 0 = planner's choice, else 1,2,4,8,16
+  int has_device = 0;
+  int sm_count = 148;
+  int smem_optin = 232448;
+};
+
+struct OuterPlan {
+  int cluster = 1;       // CTAs per column slab (split along M)
+  int grid = 1;          // CTAs launched (persistent: clusters walk the slabs round-robin)
+  int block = 256;
+  int slab_bytes = 0;    // W: bytes of one row segment of a slab
+  int rows_cta = 0;      // rows of the slab held by one CTA
+  int box_rows = 0;      // rows per TMA box (<= 256)
+  int depth = 0;         // slab tiles in flight per CTA (1 or 2)
+  int ctas_per_sm = 1;
+  uint32_t tile_bytes = 0, stage_bytes = 0;
+  uint32_t off_wpart = 0, off_cls = 0, off_fin = 0, off_tiles = 0;
+  uint32_t smem = 0;
+  int nslabs = 0;
+};
+
+// Pure host logic (works without a device: nominal B200 numbers). Returns false with a message when
+// no persistent plan exists (the reference segments such fusions as well).
+bool outer_make_plan(const OuterArgs& a, OuterPlan* plan, char* err, size_t errlen);
+
+// Enqueue on `stream`. Returns 0, or a b200norm status code with the message in err.
+int outer_launch(const OuterArgs& a, void* stream, char* err, size_t errlen);
+
+}  // namespace b200norm

@@ -173,10 +173,11 @@ class FusionDefinition:
             o = K.rms_norm_fwd(r["x"], r.get("w"), m.eps, stat_is_rms=bool(m.flags & L.F_STAT_IS_RMS), **kw)
             res = {"y": o[0], "rms": o[1], "invstd": o[1], "sum": o[2] if len(o) > 2 else None}
         elif m.op in (L.OP_SOFTMAX_FWD, L.OP_LOGSOFTMAX_FWD):
-            res = {"y": K.softmax_fwd(r["x"], log=m.op == L.OP_LOGSOFTMAX_FWD, **kw)}
+            res = {"y": K.softmax_fwd(r["x"], log=m.op == L.OP_LOGSOFTMAX_FWD, dim=0 if m.flags & L.F_OUTER else -1, **kw)}
         elif m.op in (L.OP_SOFTMAX_BWD, L.OP_LOGSOFTMAX_BWD):
             res = {"dx": K.softmax_bwd(r["dy"], r["y"], log=m.op == L.OP_LOGSOFTMAX_BWD,
-                                       round_rowsum=bool(m.flags & L.F_ROUND_ROWSUM), **kw)}
+                                       round_rowsum=bool(m.flags & L.F_ROUND_ROWSUM),
+                                       dim=0 if m.flags & L.F_OUTER else -1, **kw)}
         elif m.op == L.OP_LAYERNORM_BWD:
             mask = ("dx" in want, "dw" in want, "db" in want)
             dx, dw, db = K.layer_norm_bwd(r["dy"], r["x"], r["mean"], r["stat"], r.get("w"), mask, **kw)

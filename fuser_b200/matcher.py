@@ -319,18 +319,18 @@ def def_rms_norm_fwd(ops, x, w, eps):
     return {"y": y, "invstd": invstd, "rms": ops.sqrt(var_eps)}
 
 
-def def_softmax_fwd(ops, x, log):
-    """normalization.cpp:169-189 / :212-231"""
-    last = [x.ndim - 1]
+def def_softmax_fwd(ops, x, log, axis=-1):
+    """normalization.cpp:169-189 / :212-231 (axis 0: the outer-persistent case)"""
+    last = [axis % x.ndim]
     d = ops.sub(x, ops.max(x, dims=last, keepdim=True))
     e = ops.exp(d)
     s = ops.sum(e, dims=last, keepdim=True)
     return {"y": ops.sub(d, ops.log(s)) if log else ops.mul(e, ops.reciprocal(s))}
 
 
-def def_softmax_bwd(ops, dy, y, log):
-    """normalization.cpp:191-210 / :233-249"""
-    last = [y.ndim - 1]
+def def_softmax_bwd(ops, dy, y, log, axis=-1):
+    """normalization.cpp:191-210 / :233-249 (axis 0: the outer-persistent case)"""
+    last = [axis % y.ndim]
     if log:
         return {"dx": ops.sub(dy, ops.mul(ops.exp(y), ops.sum(dy, dims=last, keepdim=True)))}
     g = ops.mul(dy, y)
@@ -504,11 +504,13 @@ def match_fusion(fd) -> Match:
     if n_m == 1 and n_s == 0:
         x = mats[0]
         if n_v == 0:
-            for log in (False, True):
-                names = try_candidate(lambda: def_softmax_fwd(ops, T(x), log), {})
-                if names:
-                    return Match(L.OP_LOGSOFTMAX_FWD if log else L.OP_SOFTMAX_FWD, 0, 0.0, io, {"x": I(x)}, names,
-                                 description="log_softmax" if log else "softmax")
+            for axis in (-1, 0):  # inner-persistent | outer-persistent (reduction over dim 0)
+                for log in (False, True):
+                    names = try_candidate(lambda: def_softmax_fwd(ops, T(x), log, axis), {})
+                    if names:
+                        return Match(L.OP_LOGSOFTMAX_FWD if log else L.OP_SOFTMAX_FWD, L.F_OUTER if axis == 0 else 0,
+                                     0.0, io, {"x": I(x)}, names,
+                                     description=("log_softmax" if log else "softmax") + (" over dim 0" if axis == 0 else ""))
         for eps in eps_list:
             e = ops._scalar(float(eps))
             # RMSNorm: 0 or 1 vectors
@@ -591,13 +593,15 @@ def match_fusion(fd) -> Match:
         round_sum = _has_intermediate_round(fd)
         for a, b_ in ((mats[0], mats[1]), (mats[1], mats[0])):
             if n_s == 0 and n_v == 0:
-                for log in (False, True):
-                    names = try_candidate(lambda: def_softmax_bwd(ops, T(a), T(b_), log), {})
-                    if names:
-                        flags = L.F_ROUND_ROWSUM if (round_sum and not log) else 0
-                        return Match(L.OP_LOGSOFTMAX_BWD if log else L.OP_SOFTMAX_BWD, flags, 0.0, io,
-                                     {"dy": I(a), "y": I(b_)}, names,
-                                     description="log_softmax_backward" if log else "softmax_backward")
+                for axis in (-1, 0):
+                    for log in (False, True):
+                        names = try_candidate(lambda: def_softmax_bwd(ops, T(a), T(b_), log, axis), {})
+                        if names:
+                            flags = (L.F_ROUND_ROWSUM if (round_sum and not log) else 0) | (L.F_OUTER if axis == 0 else 0)
+                            return Match(L.OP_LOGSOFTMAX_BWD if log else L.OP_SOFTMAX_BWD, flags, 0.0, io,
+                                         {"dy": I(a), "y": I(b_)}, names,
+                                         description=("log_softmax_backward" if log else "softmax_backward") +
+                                         (" over dim 0" if axis == 0 else ""))
             w = vecs[0] if n_v == 1 else None
             if n_v > 1:
                 continue

@@ -109,16 +109,30 @@ def rms_norm_fwd(x, weight=None, eps: float = 1e-5, *, stat_is_rms=False, residu
     return y, stat
 
 
-def softmax_fwd(x, *, log=False, variant=L.VARIANT_AUTO, cluster_size=0):
-    (y,) = _run(L.OP_LOGSOFTMAX_FWD if log else L.OP_SOFTMAX_FWD, 0, 0.0, variant, cluster_size, [x])
+def _softmax_axis_flags(t, dim: int) -> int:
+    """dim = -1 / last: the inner-persistent kernels; dim = 0 of a tensor of rank >= 2: the
+    outer-persistent kernels (``F_OUTER``, the reduction_axis = 0 case of
+    benchmarks/python/test_softmax_{fwd,bwd}.py). Other axes are not on this path."""
+    nd = t.dim()
+    d = dim + nd if dim < 0 else dim
+    if d == nd - 1:
+        return 0
+    if d == 0:
+        return L.F_OUTER
+    raise L.UnsupportedSegment(L.ERR_UNSUPPORTED, f"softmax over axis {dim} of a rank-{nd} tensor is not handled")
+
+
+def softmax_fwd(x, *, log=False, dim: int = -1, variant=L.VARIANT_AUTO, cluster_size=0):
+    flags = _softmax_axis_flags(x, dim)
+    (y,) = _run(L.OP_LOGSOFTMAX_FWD if log else L.OP_SOFTMAX_FWD, flags, 0.0, variant, cluster_size, [x])
     return y
 
 
 # ---------------------------------------------------------------------------
 # backward
 # ---------------------------------------------------------------------------
-def softmax_bwd(dy, y, *, log=False, round_rowsum=False, variant=L.VARIANT_AUTO, cluster_size=0):
-    flags = L.F_ROUND_ROWSUM if round_rowsum else 0
+def softmax_bwd(dy, y, *, log=False, round_rowsum=False, dim: int = -1, variant=L.VARIANT_AUTO, cluster_size=0):
+    flags = (L.F_ROUND_ROWSUM if round_rowsum else 0) | _softmax_axis_flags(y, dim)
     (dx,) = _run(L.OP_LOGSOFTMAX_BWD if log else L.OP_SOFTMAX_BWD, flags, 0.0, variant, cluster_size, [dy, y])
     return dx
 

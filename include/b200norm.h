@@ -138,7 +138,17 @@ enum {
    * CTA, typically a step later, when every peer's flag has long arrived — adds the ranks' slots in
    * rank order and casts. Publishes and combines pair up in order; at most two publishes may be
    * outstanding (two slots), the third waits in-kernel for the peers' "consumed" flags. */
-  B200NORM_F_PEER_PUBLISH = 1u << 17
+  B200NORM_F_PEER_PUBLISH = 1u << 17,
+  /* SOFTMAX_* / LOGSOFTMAX_* only: the reduction runs over dim 0 (the ROWS) of the row-major [M,N]
+   * matrix instead of dim 1 — the segments nvFuser's OuterPersistent scheduler takes
+   * (scheduler/normalization_outer.cpp:451-683; benchmarks/python/test_softmax_{fwd,bwd}.py with
+   * reduction_axis = 0, pytest mark outer_persistent). desc.rows = M is then the reduced extent and
+   * desc.cols = N the iteration extent; tensors keep the same [M,N] layout and order as the inner
+   * ops. Runs on the outer-persistent kernels (a column slab resident in the shared memory of a CTA
+   * or of a cluster split along M); requires 16-byte aligned operands and N * sizeof(T) % 16 == 0,
+   * and M small enough for a 16-CTA cluster (else B200NORM_ERR_UNSUPPORTED: the caller falls through,
+   * as the reference segments such fusions). */
+  B200NORM_F_OUTER = 1u << 18
 };
 
 /* desc.variant: 0 lets the library choose (the dispatch rule mirrors the accept
@@ -204,6 +214,7 @@ typedef struct {
  *   RMSNORM_BWD    in : dy[M,N], x[M,N], stat[M], weight[N]? out: dx[M,N]?, dweight[N]?
  *   SOFTMAX_FWD / LOGSOFTMAX_FWD   in : x[M,N]               out: y[M,N]
  *   SOFTMAX_BWD / LOGSOFTMAX_BWD   in : dy[M,N], y[M,N]      out: dx[M,N]
+ *       (with B200NORM_F_OUTER the four softmax ops reduce over M instead of N; same tensors)
  *   REDUCE_INNER   in : x[M,N]                               out: r[M]   (io dtype)
  *   REDUCE_OUTER   in : x[M,N]                               out: r[N]   (io dtype, or fp32 with PARTIALS_F32)
  *   FINALIZE_PARTIALS in: p[K,N] fp32 (rows=K)               out: K tensors [N] io dtype

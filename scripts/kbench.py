@@ -2,7 +2,7 @@
 """Time single ops at arbitrary shapes (back-to-back launches, rotating inputs > L2, CUDA events).
 
     python scripts/kbench.py "ln_bwd:32768x12288:bf16[:ENV=V,ENV=V]" ...
-ops: rms_fwd add_rms_fwd add_ln_fwd ln_fwd sm_fwd sm_bwd rms_bwd rms_bwd_dx ln_bwd ln_bwd_dx copy (torch copy_, 1 read + 1 write: the
+ops: osm_fwd osm_bwd (softmax over dim 0: the outer-persistent kernels) rms_fwd add_rms_fwd add_ln_fwd ln_fwd sm_fwd sm_bwd rms_bwd rms_bwd_dx ln_bwd ln_bwd_dx copy (torch copy_, 1 read + 1 write: the
 same-size calibration of what the memory system gives a plain streaming kernel)
 """
 import os
@@ -16,13 +16,14 @@ from bench import measured_peak  # noqa: E402
 from fuser_b200 import ops  # noqa: E402
 
 KEYS = ["B200NORM_TPR", "B200NORM_GROUPS", "B200NORM_DEPTH", "B200NORM_TILE_ROWS", "B200NORM_CLUSTER",
-        "B200NORM_BWD_REREAD", "B200NORM_NO_FUSED_FINISH", "B200NORM_NO_PDL", "B200NORM_NO_PSMEM", "B200NORM_COOP", "B200NORM_STATIC", "B200NORM_POOL", "B200NORM_NO_PIPE", "B200NORM_PIPE"]
+        "B200NORM_BWD_REREAD", "B200NORM_NO_FUSED_FINISH", "B200NORM_NO_PDL", "B200NORM_NO_PSMEM", "B200NORM_COOP", "B200NORM_STATIC", "B200NORM_POOL", "B200NORM_NO_PIPE", "B200NORM_PIPE",
+        "B200NORM_OUTER_W", "B200NORM_OUTER_DEPTH", "B200NORM_OUTER_UNITS"]
 DT = {"bf16": torch.bfloat16, "f32": torch.float32, "f16": torch.float16}
 
 
 def algbytes(op, m, n, s):
     return {"add_rms_fwd": s * (4 * m * n + n) + 4 * m, "add_ln_fwd": s * (4 * m * n + 2 * n) + 8 * m,
-            "copy": s * 2 * m * n, "rms_fwd": s * (2 * m * n + n) + 4 * m, "ln_fwd": s * 2 * (m * n + n) + 8 * m, "sm_fwd": s * 2 * m * n,
+            "copy": s * 2 * m * n, "rms_fwd": s * (2 * m * n + n) + 4 * m, "ln_fwd": s * 2 * (m * n + n) + 8 * m, "sm_fwd": s * 2 * m * n, "osm_fwd": s * 2 * m * n, "osm_bwd": s * 3 * m * n,
             "sm_bwd": s * 3 * m * n, "rms_bwd": s * (3 * m * n + 2 * n) + 4 * m, "rms_bwd_dx": s * (3 * m * n + 2 * n) + 4 * m,
             "ln_bwd": s * 3 * (m * n + n) + 8 * m, "ln_bwd_dx": s * 3 * (m * n + n) + 8 * m}[op]
 
@@ -61,6 +62,8 @@ def main():
                 aux["ln"] = [ops.layer_norm_fwd(x, None, None, 1e-5)[1:] for x in xs]
             if op == "sm_bwd" and "sm" not in aux:
                 aux["sm"] = [ops.softmax_fwd(x) for x in xs]
+            if op == "osm_bwd" and "osm" not in aux:
+                aux["osm"] = [torch.softmax(x.float(), 0).to(dtype) for x in xs]
             if op == "copy" and "out" not in aux:
                 aux["out"] = torch.empty_like(xs[0])
             fns = {
@@ -70,6 +73,8 @@ def main():
                 "add_ln_fwd": lambda i: ops.layer_norm_fwd(xs[i], w, w, 1e-5, residual=dys[i], want_sum=True),
                 "ln_fwd": lambda i: ops.layer_norm_fwd(xs[i], w, w, 1e-5),
                 "sm_fwd": lambda i: ops.softmax_fwd(xs[i]),
+                "osm_fwd": lambda i: ops.softmax_fwd(xs[i], dim=0),
+                "osm_bwd": lambda i: ops.softmax_bwd(dys[i], aux["osm"][i], dim=0),
                 "sm_bwd": lambda i: ops.softmax_bwd(dys[i], aux["sm"][i]),
                 "rms_bwd": lambda i: ops.rms_norm_bwd(dys[i], xs[i], aux["rms"][i], w),
                 "rms_bwd_dx": lambda i: ops.rms_norm_bwd(dys[i], xs[i], aux["rms"][i], w, (True, False)),

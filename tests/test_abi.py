@@ -119,3 +119,42 @@ def test_no_cpu_fallback(lib):
 
     with pytest.raises(L.B200NormError):
         ops.rms_norm_fwd(x, None, 1e-5)
+
+
+def _outer_plan(op, dt, m, n, cluster=0):
+    d = L.make_desc(op, dt, m, n, 0.0, L.F_OUTER, L.VARIANT_AUTO, cluster)
+    return L.query(d).as_dict()
+
+
+def test_outer_persistent_planner():
+    """Dispatch rules of the outer-persistent softmax family (pure host logic, nominal B200): one CTA
+    per column slab while M * W fits its shared memory twice over, then a cluster split along M; the
+    extent a 16-CTA cluster cannot hold is declined (the reference segments such fusions,
+    scheduler/normalization_outer.cpp:451-683 canSchedule)."""
+    # small reduced extent: one CTA per slab, two tiles in flight, wide slabs when N gives enough of them
+    p = _outer_plan(L.OP_SOFTMAX_FWD, L.DT_BF16, 16, 4 * 73728)
+    assert p["variant"] == "tma" and p["cluster_size"] == 1 and p["stages"] == 2 and p["threads_per_row"] == 32
+    # the reference's outer_persistent benchmark rows {512, 2048, 8192, 16384} at N = 4096 bf16
+    p = _outer_plan(L.OP_SOFTMAX_FWD, L.DT_BF16, 512, 4096)
+    assert p["cluster_size"] * p["tile_rows"] >= 512 and p["stages"] == 2 and p["block"] == 256
+    p = _outer_plan(L.OP_SOFTMAX_FWD, L.DT_BF16, 2048, 4096)
+    assert p["variant"] == "cluster" and p["cluster_size"] * p["tile_rows"] >= 2048 and p["stages"] == 2
+    p = _outer_plan(L.OP_SOFTMAX_FWD, L.DT_BF16, 8192, 4096)
+    assert p["variant"] == "cluster" and p["cluster_size"] == 16 and p["tile_rows"] == 512 and p["stages"] == 2
+    assert p["grid"] % 16 == 0 and p["smem_bytes"] <= 232448 // 2  # two CTAs per SM
+    p = _outer_plan(L.OP_SOFTMAX_BWD, L.DT_BF16, 8192, 4096)  # two streams: narrower slabs or one tile
+    assert p["cluster_size"] == 16 and p["smem_bytes"] <= 232448
+    p = _outer_plan(L.OP_SOFTMAX_FWD, L.DT_BF16, 16384, 4096)
+    assert p["cluster_size"] == 16 and p["tile_rows"] == 1024 and p["smem_bytes"] <= 232448
+    assert p["algorithmic_bytes"] == 2 * 2 * 16384 * 4096
+    # forced cluster sizes are honoured
+    for c in (1, 2, 4, 8, 16):
+        assert _outer_plan(L.OP_SOFTMAX_FWD, L.DT_F32, 777, 384, c)["cluster_size"] == c
+    # declined: rows that are not a multiple of 16 bytes, extents beyond a 16-CTA cluster, other ops
+    for m, n in ((32, 100), (1 << 18, 4096)):
+        with pytest.raises(L.UnsupportedSegment):
+            _outer_plan(L.OP_SOFTMAX_FWD, L.DT_BF16, m, n)
+    with pytest.raises(L.UnsupportedSegment):
+        _outer_plan(L.OP_RMSNORM_FWD, L.DT_BF16, 512, 4096)
+    # empty problems plan to nothing
+    assert _outer_plan(L.OP_SOFTMAX_FWD, L.DT_BF16, 0, 4096)["grid"] == 0

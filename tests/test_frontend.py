@@ -94,9 +94,14 @@ def test_equivalent_respellings_match_and_near_misses_do_not():
     with pytest.raises(UnsupportedSegment):
         build(unsafe_softmax).segment()
 
-    # near miss 3: reduction over the outer axis (an OuterPersistent segment)
+    # near miss 3: softmax over the middle axis of a rank-3 tensor (neither inner nor outer persistent)
+    def middle_axis(fd):
+        x = fd.define_tensor(shape=[-1, -1, -1], dtype=DataType.Float)
+        d = fd.ops.sub(x, fd.ops.max(x, dims=[1], keepdim=True))
+        e = fd.ops.exp(d)
+        fd.add_output(fd.ops.mul(e, fd.ops.reciprocal(fd.ops.sum(e, dims=[1], keepdim=True))))
     with pytest.raises(UnsupportedSegment):
-        build(F.softmax_fwd_py, DataType.Float, reduction_axis=0).segment()
+        build(middle_axis).segment()
 
     # near miss 4: a pointwise fusion is somebody else's segment
     def pointwise(fd):
@@ -176,3 +181,27 @@ def test_add_of_two_matrices_alone_is_not_a_segment():
         fd.add_output(fd.ops.add(a, b))
     with pytest.raises(UnsupportedSegment):
         build(just_add).segment()
+
+
+@pytest.mark.parametrize("dt", [DataType.Float, DataType.BFloat16])
+def test_outer_persistent_softmax_matches(dt):
+    """reduction_axis = 0 of the reference's softmax benchmarks (pytest mark outer_persistent,
+    benchmarks/python/test_softmax_{fwd,bwd}.py): matched as the same ops with F_OUTER; the evaluated
+    fusion agrees with eager softmax over dim 0."""
+    import torch
+    from oracle import fusion_eval
+
+    fd = build(F.softmax_fwd_py, dt, reduction_axis=0)
+    m = fd.segment()
+    assert m.op == L.OP_SOFTMAX_FWD and m.flags & L.F_OUTER and m.outputs == ["y"]
+    td = torch.float32 if dt == DataType.Float else torch.bfloat16
+    x = torch.randn(37, 24).to(td)
+    (y,) = fusion_eval.evaluate(fd, [x])
+    assert torch.allclose(y.float(), torch.softmax(x.float(), 0), atol=1e-2 if td == torch.bfloat16 else 1e-6)
+    fd = build(F.softmax_bwd_py, dt, reduction_axis=0)
+    m = fd.segment()
+    assert m.op == L.OP_SOFTMAX_BWD and m.flags & L.F_OUTER
+    assert bool(m.flags & L.F_ROUND_ROWSUM) == (dt != DataType.Float)
+    # the inner spellings keep matching without the flag
+    assert not build(F.softmax_fwd_py, dt).segment().flags & L.F_OUTER
+    assert not build(F.softmax_bwd_py, dt).segment().flags & L.F_OUTER

@@ -1,0 +1,200 @@
+"""GPU parity tests of the outer-persistent kernels (softmax / log-softmax over dim 0, forward and
+backward; B200NORM_F_OUTER): the segments nvFuser's OuterPersistent scheduler takes
+(scheduler/normalization_outer.cpp:451-683; benchmarks/python/test_softmax_{fwd,bwd}.py with
+reduction_axis = 0). Called through the C ABI (ops -> C++ NormExecutor -> b200norm_launch) and
+compared with (a) the ATen oracle under the validator's tolerances and (b) the fp64 C oracle
+(through a transpose: a column of the matrix is a row of its transpose) with a tight ulp bound.
+Shapes cover one CTA per slab, every cluster size (rows split along M with the DSMEM exchange),
+ragged row counts, slabs cut by the matrix edge, strided rows and the NaN / Inf semantics.
+"""
+import pytest
+import torch
+
+from fuser_b200 import _lib as L
+from fuser_b200 import fusions as F
+from fuser_b200 import ops
+from fuser_b200.frontend import FusionDefinition
+from fuser_b200.ir import DataType
+from oracle import aten_oracle as AO
+from oracle import c_oracle as CO
+from tests.util import make_inputs, ulp_err
+
+pytestmark = pytest.mark.gpu
+
+DTYPES = [torch.bfloat16, torch.float32, torch.float16]
+TIGHT = {torch.bfloat16: 1.01, torch.float16: 1.01, torch.float32: 64.0}
+# (M = reduced extent, N = iteration extent)
+SHAPES = [(1, 64), (5, 8), (16, 768), (33, 1000), (216, 96), (512, 2048), (600, 136), (2048, 264), (4100, 512)]
+
+
+def check(actual, aten_expected, exact, red_size, what, floor):
+    torch.cuda.synchronize()
+    AO.assert_close(actual, aten_expected, red_size, what)
+    u = ulp_err(actual.cpu(), exact, floor=floor)
+    assert u <= TIGHT[actual.dtype], f"{what}: {u:.2f} ulp vs fp64"
+
+
+def c_softmax_fwd(x, log=False):
+    return CO.softmax_fwd(x.t().contiguous(), log=log).t()
+
+
+def c_softmax_bwd(dy, y, log=False):
+    return CO.softmax_bwd(dy.t().contiguous(), y.t().contiguous(), log=log).t()
+
+
+def run_all(x, dy, dt, m, what, **kw):
+    xd, dyd = x.cuda(), dy.cuda()
+    y = ops.softmax_fwd(xd, dim=0, **kw)
+    assert y.shape == x.shape and y.dtype == dt
+    check(y, AO.softmax_fwd(x, dim=0), c_softmax_fwd(x), m * m, what + " softmax y", 1e-6 if dt != torch.float32 else 1e-3)
+    y = ops.softmax_fwd(xd, log=True, dim=0, **kw)
+    check(y, AO.log_softmax_fwd(x, dim=0), c_softmax_fwd(x, log=True), m * m, what + " log_softmax y", 1.0)
+    sm = AO.softmax_fwd(x, dim=0)
+    lsm = AO.log_softmax_fwd(x, dim=0)
+    dx = ops.softmax_bwd(dyd, sm.cuda(), dim=0, **kw)
+    check(dx, AO.softmax_bwd(dy, sm, dim=0), c_softmax_bwd(dy, sm), m, what + " softmax dx", 1e-3 if dt != torch.float32 else 1e-1)
+    dx = ops.softmax_bwd(dyd, sm.cuda(), round_rowsum=True, dim=0, **kw)
+    torch.cuda.synchronize()
+    AO.assert_close(dx, AO.softmax_bwd_python(sm, dy, dim=0), m, what + " softmax(py) dx")
+    dx = ops.softmax_bwd(dyd, lsm.cuda(), log=True, dim=0, **kw)
+    check(dx, AO.log_softmax_bwd(dy, lsm, dim=0), c_softmax_bwd(dy, lsm, log=True), m, what + " log_softmax dx", 1.0)
+
+
+@pytest.mark.parametrize("dt", DTYPES, ids=["bf16", "f32", "f16"])
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: f"{s[0]}x{s[1]}")
+def test_outer_softmax(shape, dt):
+    m, n = shape
+    x, dy, _, _ = make_inputs(m, n, dt, seed=m * 13 + n)
+    run_all(x, dy, dt, m, f"[{m},{n}]")
+
+
+@pytest.mark.parametrize("cluster", [1, 2, 4, 8, 16])
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float32], ids=["bf16", "f32"])
+@pytest.mark.parametrize("shape", [(40, 256), (777, 384), (3000, 1024)], ids=lambda s: f"{s[0]}x{s[1]}")
+def test_outer_cluster_split(shape, dt, cluster):
+    """Rows of a slab split over a thread-block cluster; the per-column partials cross the cluster
+    through DSMEM (reference mechanism: the grid reduction of runtime/grid_reduction.cu:905-1066)."""
+    m, n = shape
+    try:
+        plan = ops.plan_for(L.OP_SOFTMAX_BWD, dt, m, n, flags=L.F_OUTER, cluster_size=cluster)
+    except L.UnsupportedSegment:
+        pytest.skip(f"M = {m} does not fit a cluster of {cluster}")
+    assert plan["cluster_size"] == cluster
+    x, dy, _, _ = make_inputs(m, n, dt, seed=cluster)
+    run_all(x, dy, dt, m, f"[{m},{n}] C={cluster}", cluster_size=cluster)
+
+
+def test_outer_large_m_two_deep_and_single_tile():
+    """M = 8192 (16-CTA cluster, two tiles in flight) and M = 16384 (64-byte slabs or one tile)."""
+    dt = torch.bfloat16
+    for m, n in ((8192, 1024), (16384, 512)):
+        x, dy, _, _ = make_inputs(m, n, dt, seed=m)
+        xd = x.cuda()
+        y = ops.softmax_fwd(xd, dim=0)
+        torch.cuda.synchronize()
+        AO.assert_close(y, AO.softmax_fwd(x, dim=0), m * m, f"softmax [{m},{n}]")
+        assert ulp_err(y.cpu(), c_softmax_fwd(x), floor=1e-6) <= TIGHT[dt]
+        dx = ops.softmax_bwd(dy.cuda(), y, dim=0)
+        torch.cuda.synchronize()
+        AO.assert_close(dx, AO.softmax_bwd(dy, y.cpu(), dim=0), m, f"softmax dx [{m},{n}]")
+        assert ulp_err(dx.cpu(), c_softmax_bwd(dy, y.cpu()), floor=1e-3) <= TIGHT[dt]
+
+
+def test_outer_edge_cases():
+    dt = torch.bfloat16
+    # empty reduction / iteration domains
+    for shape in ((0, 256), (16, 0)):
+        x = torch.empty(*shape, dtype=dt, device="cuda")
+        assert ops.softmax_fwd(x, dim=0).shape == shape
+        assert ops.softmax_bwd(x, x, dim=0).shape == shape
+    # strided rows (a column block of a wider matrix) in, contiguous out
+    big = torch.randn(300, 1024, dtype=torch.float32).to(dt)
+    view = big.cuda()[:, 128:640]
+    y = ops.softmax_fwd(view, dim=0)
+    torch.cuda.synchronize()
+    AO.assert_close(y, AO.softmax_fwd(big[:, 128:640], dim=0), 300 * 300, "strided rows")
+    # 3-D input: [M, a, b] reduces over dim 0 with [a*b] independent columns
+    x3 = torch.randn(64, 6, 40).to(dt)
+    y3 = ops.softmax_fwd(x3.cuda(), dim=0)
+    torch.cuda.synchronize()
+    assert y3.shape == x3.shape
+    AO.assert_close(y3, AO.softmax_fwd(x3, dim=0), 64 * 64, "3-D outer softmax")
+    # NaN / Inf columns: the whole column turns NaN exactly as the op-by-op ATen evaluation does
+    xs = torch.randn(96, 64).to(dt)
+    xs[7, 1] = float("nan")
+    xs[:, 2] = float("-inf")
+    xs[5, 3] = float("inf")
+    y = ops.softmax_fwd(xs.cuda(), dim=0)
+    torch.cuda.synchronize()
+    AO.assert_close(y, AO.softmax_fwd(xs, dim=0), 96 * 96, "softmax with NaN/Inf columns")
+    assert torch.isnan(y[:, 1:4]).all() and not torch.isnan(y[:, 0]).any() and not torch.isnan(y[:, 4:]).any()
+    # shapes the persistent kernels decline: misaligned rows, reduced extent beyond a 16-CTA cluster
+    with pytest.raises(L.UnsupportedSegment):
+        ops.softmax_fwd(torch.randn(32, 100).to(dt).cuda(), dim=0)  # 200 bytes per row
+    with pytest.raises(L.UnsupportedSegment):
+        ops.softmax_fwd(torch.empty(1 << 18, 8, dtype=dt, device="cuda"), dim=0)
+    with pytest.raises(L.UnsupportedSegment):
+        ops.softmax_fwd(torch.randn(8, 8, 8).to(dt).cuda(), dim=1)
+
+
+def test_outer_deterministic_and_graph_replay():
+    """Same bits on every run, also when replayed from a CUDA graph (mbarrier phases and cluster
+    slot sets start from rest in every launch)."""
+    dt = torch.bfloat16
+    x = torch.randn(1024, 2048).to(dt).cuda()
+    ref = ops.softmax_fwd(x, dim=0).clone()
+    for _ in range(3):
+        assert torch.equal(ops.softmax_fwd(x, dim=0), ref)
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):  # warm-up on the capture stream: workspace, kernel attributes
+            ops.softmax_fwd(x, dim=0)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        out = ops.softmax_fwd(x, dim=0)
+    for it in range(3):
+        out.zero_()
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out, ref), f"replay {it} differs"
+
+
+@pytest.mark.parametrize("dt", [DataType.BFloat16, DataType.Float], ids=["bf16", "f32"])
+def test_outer_frontend_fusions(dt):
+    """The reference's outer_persistent benchmark definitions, recorded through FusionDefinition,
+    matched, executed and validated against the node-by-node ATen evaluation (testValidate)."""
+    from oracle import fusion_eval
+
+    td = torch.bfloat16 if dt == DataType.BFloat16 else torch.float32
+    m, n = 512, 1536
+    x = torch.randn(m, n).to(td).cuda()
+    dy = torch.randn(m, n).to(td).cuda()
+    with FusionDefinition() as fd:
+        F.softmax_fwd_py(fd, dt, reduction_axis=0)
+    assert fd.segment().flags & L.F_OUTER
+    (y,) = fd.validate([x], fusion_eval.evaluate(fd, [x.cpu()]))
+    AO.assert_close(y, torch.softmax(x.float(), 0).to(td).cpu(), m * m, "outer softmax vs eager")
+    with FusionDefinition() as fd:
+        F.softmax_bwd_py(fd, dt, reduction_axis=0)
+    assert fd.segment().flags & L.F_OUTER
+    fd.validate([y, dy], fusion_eval.evaluate(fd, [y.cpu(), dy.cpu()]))
+
+
+def test_outer_full_size_properties():
+    """The reference's outer_persistent benchmark shape class ([8192, N] / [2048, N], bf16):
+    columns of the softmax sum to 1, dx sums to 0 over every column, elementwise agreement with eager."""
+    dt = torch.bfloat16
+    for m, n in ((8192, 4096), (2048, 16384)):
+        x = torch.randn(m, n, device="cuda").to(dt)
+        sm = ops.softmax_fwd(x, dim=0)
+        assert (sm.float().sum(0) - 1).abs().max().item() < 2e-2
+        ref = torch.softmax(x.float(), 0)
+        assert (sm.float() - ref).abs().max().item() <= 2.0 ** -8 * ref.max().item() + 1e-6
+        dy = torch.randn(m, n, device="cuda").to(dt)
+        dx = ops.softmax_bwd(dy, sm, dim=0)
+        scale = (sm.float() * dy.float()).abs().sum(0)
+        assert (dx.float().sum(0).abs() / scale).max().item() < 2e-2
