@@ -8,14 +8,14 @@
 //
 //   * a slab is held in SHARED memory — of one CTA when M*W fits, else of a thread-block cluster
 //     whose CTAs split the rows (rank q holds rows [q*Rc, (q+1)*Rc)) and exchange their per-column
-//     partial results through DSMEM (st.shared::cluster + barrier.cluster), never through HBM;
+//     partial results through DSMEM (st.async completing on the peer's mbarrier), never through HBM;
 //   * a slab tile is fetched with 2-D TMA box loads (cp.async.bulk.tensor.2d, <= 256 rows per box)
 //     that complete on an mbarrier; two tiles per CTA: the next slab streams in while the current
 //     one is reduced and written out. Out-of-range rows / columns are zero-filled by the TMA unit
 //     and masked by index;
 //   * the grid is persistent (clusters walk the slabs round-robin) and sized from the occupancy
-//     API: small tiles run two CTAs per SM so that one CTA's barrier latency hides behind the
-//     other's passes;
+//     API: small tiles run two or three CTAs per SM so that one CTA's barrier latency hides behind
+//     the others' passes;
 //   * a thread owns one 16-byte column chunk and every (256 / LC)-th row of it: consecutive threads
 //     read consecutive 16-byte words of the tile (conflict-free), per-column partials are combined
 //     with xor-shuffles inside a warp, through shared memory across the 8 warps, and across the
@@ -75,16 +75,63 @@ __device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
 }
 __device__ __forceinline__ float4 lds_f4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
+// packed 16-bit NaN-propagating max (exact: no rounding is involved), one instruction per two elements
+template <typename T>
+struct Max2;
+template <>
+struct Max2<__nv_bfloat16> {
+  static constexpr uint32_t kNegInf = 0xff80ff80u;
+  __device__ __forceinline__ static uint32_t apply(uint32_t a, uint32_t b) {
+    uint32_t r;
+    asm("max.NaN.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+  }
+};
+template <>
+struct Max2<__half> {
+  static constexpr uint32_t kNegInf = 0xfc00fc00u;
+  __device__ __forceinline__ static uint32_t apply(uint32_t a, uint32_t b) {
+    uint32_t r;
+    asm("max.NaN.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+  }
+};
+
+constexpr float kLog2e = 1.4426950408889634f;
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// exp(x - m) for a pair: 16-bit io -> ex2(x*log2e - m*log2e), one FFMA2 + two MUFU (nml = -m*log2e);
+// fp32 io -> accurate expf(x - m) (nm = -m)
+template <typename T>
+__device__ __forceinline__ float2 exp_shift(float2 x, float2 nm, float2 nml) {
+  if constexpr (sizeof(T) == 4) {
+    const float2 d = f2add(x, nm);
+    return make_float2(expf(d.x), expf(d.y));
+  } else {
+    const float2 t = f2fma(x, f2(kLog2e), nml);
+    return make_float2(ex2_fast(t.x), ex2_fast(t.y));
+  }
+}
+
 // Column reduction context: combine the per-thread partials v[VEC] (thread's 16-byte column chunk)
 // over every row of the slab: lanes of a warp that share the chunk, the CTA's warps, the cluster's CTAs.
+// The cluster step is an all-to-all of SC floats per CTA with st.async: every value lands in the
+// peer's slot set and completes 4 tx-bytes on the PEER's mbarrier, which the peer armed with
+// expect_tx(C * SC * 4). No barrier.cluster and no fence in the loop: a release fence here would also
+// wait for the CTA's outstanding global stores of the previous slab (measured: MEMBAR was the top
+// stall, and a 16-CTA cluster ran 4x slower than one CTA).
 struct ColCtx {
   uint32_t smem0;
   int tid, lane, warp, c, LC, SC;
   uint32_t C, crank;
-  uint32_t set;  // cluster slot set, alternates per exchange
-  float* wpart;  // [kOuterWarps][SC]
-  float* cls;    // [2][C][SC]
-  float* fin;    // [SC]
+  uint32_t nx;       // cluster exchanges done so far: set = nx & 1, parity = (nx >> 1) & 1
+  uint32_t xbar;     // mbarrier pair of the exchange (shared::cta address)
+  float* wpart;      // [kOuterWarps][SC]
+  float* cls;        // [2][C][SC]
+  float* fin;        // [SC]
   uint32_t off_cls;
 };
 
@@ -105,22 +152,19 @@ __device__ __forceinline__ void col_reduce(float (&v)[VEC], ColCtx& x) {
 #pragma unroll
     for (int w = 1; w < kOuterWarps; ++w) a = Op::apply(a, x.wpart[w * x.SC + x.tid]);
     if (x.C > 1) {
-      const uint32_t local = x.smem0 + x.off_cls + ((x.set * x.C + x.crank) * (uint32_t)x.SC + (uint32_t)x.tid) * 4u;
-      for (uint32_t q = 0; q < x.C; ++q) st_cluster_f32(map_to_cta(local, q), a);
-    } else {
-      x.fin[x.tid] = a;
-    }
-  }
-  if (x.C > 1) {
-    cluster_sync_all();
-    if (x.tid < x.SC) {
-      const float* s = x.cls + (size_t)x.set * x.C * x.SC + x.tid;
-      float a = s[0];
+      const uint32_t set = x.nx & 1u, parity = (x.nx >> 1) & 1u;
+      const uint32_t bar = x.xbar + 8u * set;
+      if (x.tid == 0) mbar_arrive_expect_tx(bar, x.C * (uint32_t)x.SC * 4u);
+      const uint32_t local = x.smem0 + x.off_cls + ((set * x.C + x.crank) * (uint32_t)x.SC + (uint32_t)x.tid) * 4u;
+      for (uint32_t q = 0; q < x.C; ++q) st_async_f32(map_to_cta(local, q), a, map_to_cta(bar, q));
+      mbar_wait(bar, parity);
+      const volatile float* s = x.cls + (size_t)set * x.C * x.SC + x.tid;
+      a = s[0];
       for (uint32_t q = 1; q < x.C; ++q) a = Op::apply(a, s[q * x.SC]);
-      x.fin[x.tid] = a;
     }
-    x.set ^= 1u;
+    x.fin[x.tid] = a;
   }
+  if (x.C > 1) ++x.nx;
   __syncthreads();
 #pragma unroll
   for (int k = 0; k < VEC; k += 4) {
@@ -133,10 +177,11 @@ __device__ __forceinline__ void col_reduce(float (&v)[VEC], ColCtx& x) {
 }
 
 template <typename T, bool BWD, bool LOG>
-__global__ void __launch_bounds__(kOuterThreads, 2)
+__global__ void __launch_bounds__(kOuterThreads, 3)
 outer_softmax_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
                      const OuterParams p) {
   constexpr int VEC = IO<T>::VEC;
+  constexpr int H = VEC / 2;
   constexpr uint32_t kStep = kOuterThreads * 16;  // bytes between a thread's consecutive chunks
   const uint32_t smem0 = smem_u32(outer_smem);
   const int tid = threadIdx.x;
@@ -151,7 +196,8 @@ outer_softmax_kernel(const __grid_constant__ CUtensorMap map0, const __grid_cons
   cx.c = tid & (cx.LC - 1);
   cx.C = (uint32_t)p.cluster;
   cx.crank = cx.C > 1 ? cluster_ctarank() : 0u;
-  cx.set = 0;
+  cx.nx = 0;
+  cx.xbar = smem0 + 16;
   cx.wpart = reinterpret_cast<float*>(outer_smem + p.off_wpart);
   cx.cls = reinterpret_cast<float*>(outer_smem + p.off_cls);
   cx.fin = reinterpret_cast<float*>(outer_smem + p.off_fin);
@@ -168,14 +214,16 @@ outer_softmax_kernel(const __grid_constant__ CUtensorMap map0, const __grid_cons
   // chunks of this thread: rows r0 + j*rstep < rows_valid
   const int nj = rows_valid > r0 ? (rows_valid - r0 + rstep - 1) / rstep : 0;
 
-  const uint32_t bar0 = smem0;  // full[2]
+  const uint32_t bar0 = smem0;  // full[2] | exchange[2]
   if (tid == 0) {
     mbar_init(bar0, 1);
     mbar_init(bar0 + 8, 1);
+    mbar_init(bar0 + 16, 1);
+    mbar_init(bar0 + 24, 1);
     fence_mbar_init();
   }
   __syncthreads();
-  if (cx.C > 1) cluster_sync_all();  // every CTA of the cluster is resident before any DSMEM store
+  if (cx.C > 1) cluster_sync_all();  // every CTA of the cluster is resident, its barriers initialised
   pdl_wait();
 
   auto issue = [&](int slab, uint32_t buf) {
@@ -210,80 +258,119 @@ outer_softmax_kernel(const __grid_constant__ CUtensorMap map0, const __grid_cons
 
     if constexpr (!BWD) {
       float m[VEC];
-#pragma unroll
-      for (int k = 0; k < VEC; ++k) m[k] = -INFINITY;
+      if constexpr (sizeof(T) == 2) {
+        uint4 mx = make_uint4(Max2<T>::kNegInf, Max2<T>::kNegInf, Max2<T>::kNegInf, Max2<T>::kNegInf);
 #pragma unroll 4
-      for (int j = 0; j < nj; ++j) {
-        float x[VEC];
-        IO<T>::unpack(*reinterpret_cast<const uint4*>(t0 + (uint32_t)j * kStep), x);
+        for (int j = 0; j < nj; ++j) {
+          const uint4 v = *reinterpret_cast<const uint4*>(t0 + (uint32_t)j * kStep);
+          mx.x = Max2<T>::apply(mx.x, v.x);
+          mx.y = Max2<T>::apply(mx.y, v.y);
+          mx.z = Max2<T>::apply(mx.z, v.z);
+          mx.w = Max2<T>::apply(mx.w, v.w);
+        }
+        IO<T>::unpack(mx, m);
+      } else {
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) m[k] = MaxOp::apply(m[k], x[k]);
-      }
-      col_reduce<MaxOp, VEC>(m, cx);
-      float s[VEC];
-#pragma unroll
-      for (int k = 0; k < VEC; ++k) s[k] = 0.f;
-#pragma unroll 4
-      for (int j = 0; j < nj; ++j) {
-        float x[VEC];
-        IO<T>::unpack(*reinterpret_cast<const uint4*>(t0 + (uint32_t)j * kStep), x);
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) s[k] += exp_for<T>(x[k] - m[k]);
-      }
-      col_reduce<SumOp, VEC>(s, cx);
-#pragma unroll
-      for (int k = 0; k < VEC; ++k) s[k] = LOG ? -logf(s[k]) : rcp_fast(s[k]);
-      if (col_ok) {
+        for (int k = 0; k < VEC; ++k) m[k] = -INFINITY;
 #pragma unroll 4
         for (int j = 0; j < nj; ++j) {
           float x[VEC];
           IO<T>::unpack(*reinterpret_cast<const uint4*>(t0 + (uint32_t)j * kStep), x);
 #pragma unroll
-          for (int k = 0; k < VEC; ++k) {
-            const float d = x[k] - m[k];
-            x[k] = LOG ? d + s[k] : exp_for<T>(d) * s[k];
+          for (int k = 0; k < VEC; ++k) m[k] = MaxOp::apply(m[k], x[k]);
+        }
+      }
+      col_reduce<MaxOp, VEC>(m, cx);
+      float2 nm[H], nml[H], s2[H];
+#pragma unroll
+      for (int k = 0; k < H; ++k) {
+        nm[k] = make_float2(-m[2 * k], -m[2 * k + 1]);
+        nml[k] = make_float2(-m[2 * k] * kLog2e, -m[2 * k + 1] * kLog2e);
+        s2[k] = f2(0.f);
+      }
+#pragma unroll 2
+      for (int j = 0; j < nj; ++j) {
+        float2 x[H];
+        IO<T>::unpack2(*reinterpret_cast<const uint4*>(t0 + (uint32_t)j * kStep), x);
+#pragma unroll
+        for (int k = 0; k < H; ++k) s2[k] = f2add(s2[k], exp_shift<T>(x[k], nm[k], nml[k]));
+      }
+      float s[VEC];
+#pragma unroll
+      for (int k = 0; k < H; ++k) {
+        s[2 * k] = s2[k].x;
+        s[2 * k + 1] = s2[k].y;
+      }
+      col_reduce<SumOp, VEC>(s, cx);
+      float2 fin[H];
+#pragma unroll
+      for (int k = 0; k < H; ++k)
+        fin[k] = LOG ? make_float2(-logf(s[2 * k]), -logf(s[2 * k + 1])) : make_float2(rcp_fast(s[2 * k]), rcp_fast(s[2 * k + 1]));
+      if (col_ok) {
+#pragma unroll 2
+        for (int j = 0; j < nj; ++j) {
+          float2 x[H];
+          IO<T>::unpack2(*reinterpret_cast<const uint4*>(t0 + (uint32_t)j * kStep), x);
+#pragma unroll
+          for (int k = 0; k < H; ++k) {
+            if constexpr (LOG) {
+              x[k] = f2add(f2add(x[k], nm[k]), fin[k]);
+            } else {
+              x[k] = f2mul(exp_shift<T>(x[k], nm[k], nml[k]), fin[k]);
+            }
           }
-          stg_128_stream(o + (size_t)j * out_step, IO<T>::pack(x));
+          stg_128_stream(o + (size_t)j * out_step, IO<T>::pack2(x));
         }
       }
     } else {
       const uint8_t* t1 = t0 + p.tile_bytes;  // y
-      float s[VEC];
+      float2 s2[H];
 #pragma unroll
-      for (int k = 0; k < VEC; ++k) s[k] = 0.f;
+      for (int k = 0; k < H; ++k) s2[k] = f2(0.f);
 #pragma unroll 4
       for (int j = 0; j < nj; ++j) {
-        float dy[VEC], y[VEC];
-        IO<T>::unpack(*reinterpret_cast<const uint4*>(t0 + (uint32_t)j * kStep), dy);
+        float2 dy[H], y[H];
+        IO<T>::unpack2(*reinterpret_cast<const uint4*>(t0 + (uint32_t)j * kStep), dy);
         if constexpr (LOG) {
 #pragma unroll
-          for (int k = 0; k < VEC; ++k) s[k] += dy[k];
+          for (int k = 0; k < H; ++k) s2[k] = f2add(s2[k], dy[k]);
         } else {
-          IO<T>::unpack(*reinterpret_cast<const uint4*>(t1 + (uint32_t)j * kStep), y);
+          IO<T>::unpack2(*reinterpret_cast<const uint4*>(t1 + (uint32_t)j * kStep), y);
 #pragma unroll
-          for (int k = 0; k < VEC; ++k) s[k] += y[k] * dy[k];
+          for (int k = 0; k < H; ++k) s2[k] = f2fma(y[k], dy[k], s2[k]);
         }
       }
-      col_reduce<SumOp, VEC>(s, cx);
-      if (p.round_sum) {
+      float s[VEC];
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) s[k] = IO<T>::round_trip(s[k]);
+      for (int k = 0; k < H; ++k) {
+        s[2 * k] = s2[k].x;
+        s[2 * k + 1] = s2[k].y;
+      }
+      col_reduce<SumOp, VEC>(s, cx);
+      float2 ns[H];
+#pragma unroll
+      for (int k = 0; k < H; ++k) {
+        if (p.round_sum) {
+          s[2 * k] = IO<T>::round_trip(s[2 * k]);
+          s[2 * k + 1] = IO<T>::round_trip(s[2 * k + 1]);
+        }
+        ns[k] = make_float2(-s[2 * k], -s[2 * k + 1]);
       }
       if (col_ok) {
-#pragma unroll 4
+#pragma unroll 2
         for (int j = 0; j < nj; ++j) {
-          float dy[VEC], y[VEC];
-          IO<T>::unpack(*reinterpret_cast<const uint4*>(t0 + (uint32_t)j * kStep), dy);
-          IO<T>::unpack(*reinterpret_cast<const uint4*>(t1 + (uint32_t)j * kStep), y);
+          float2 dy[H], y[H];
+          IO<T>::unpack2(*reinterpret_cast<const uint4*>(t0 + (uint32_t)j * kStep), dy);
+          IO<T>::unpack2(*reinterpret_cast<const uint4*>(t1 + (uint32_t)j * kStep), y);
 #pragma unroll
-          for (int k = 0; k < VEC; ++k) {
+          for (int k = 0; k < H; ++k) {
             if constexpr (LOG) {
-              dy[k] = fmaf(expf(y[k]), -s[k], dy[k]);
+              dy[k] = f2fma(make_float2(expf(y[k].x), expf(y[k].y)), ns[k], dy[k]);
             } else {
-              dy[k] = fmaf(y[k], -s[k], y[k] * dy[k]);
+              dy[k] = f2fma(y[k], ns[k], f2mul(y[k], dy[k]));
             }
           }
-          stg_128_stream(o + (size_t)j * out_step, IO<T>::pack(dy));
+          stg_128_stream(o + (size_t)j * out_step, IO<T>::pack2(dy));
         }
       }
     }
@@ -447,7 +534,7 @@ bool outer_make_plan(const OuterArgs& a, OuterPlan* plan, char* err, size_t errl
   p.smem = off + (uint32_t)depth * g.stage;
   p.nslabs = (int)nslabs;
   int per_sm = (int)(kSmemPerSm / ((int64_t)p.smem + 1024));
-  if (per_sm > 2) per_sm = 2;  // __launch_bounds__(256, 2)
+  if (per_sm > 3) per_sm = 3;  // __launch_bounds__(256, 3)
   if (per_sm < 1) per_sm = 1;
   p.ctas_per_sm = per_sm;
   int64_t nclusters = C > 1 ? (int64_t)8 * (18 / C) * per_sm : (int64_t)a.sm_count * per_sm;  // nominal; refined at launch
