@@ -260,9 +260,10 @@ outer_softmax_kernel(const __grid_constant__ CUtensorMap map0, const __grid_cons
       float m[VEC];
       if constexpr (sizeof(T) == 2) {
         uint4 mx = make_uint4(Max2<T>::kNegInf, Max2<T>::kNegInf, Max2<T>::kNegInf, Max2<T>::kNegInf);
+        const uint8_t* t = t0;
 #pragma unroll 4
-        for (int j = 0; j < nj; ++j) {
-          const uint4 v = *reinterpret_cast<const uint4*>(t0 + (uint32_t)j * kStep);
+        for (int j = 0; j < nj; ++j, t += kStep) {
+          const uint4 v = *reinterpret_cast<const uint4*>(t);
           mx.x = Max2<T>::apply(mx.x, v.x);
           mx.y = Max2<T>::apply(mx.y, v.y);
           mx.z = Max2<T>::apply(mx.z, v.z);
@@ -272,10 +273,11 @@ outer_softmax_kernel(const __grid_constant__ CUtensorMap map0, const __grid_cons
       } else {
 #pragma unroll
         for (int k = 0; k < VEC; ++k) m[k] = -INFINITY;
+        const uint8_t* t = t0;
 #pragma unroll 4
-        for (int j = 0; j < nj; ++j) {
+        for (int j = 0; j < nj; ++j, t += kStep) {
           float x[VEC];
-          IO<T>::unpack(*reinterpret_cast<const uint4*>(t0 + (uint32_t)j * kStep), x);
+          IO<T>::unpack(*reinterpret_cast<const uint4*>(t), x);
 #pragma unroll
           for (int k = 0; k < VEC; ++k) m[k] = MaxOp::apply(m[k], x[k]);
         }
@@ -288,12 +290,15 @@ outer_softmax_kernel(const __grid_constant__ CUtensorMap map0, const __grid_cons
         nml[k] = make_float2(-m[2 * k] * kLog2e, -m[2 * k + 1] * kLog2e);
         s2[k] = f2(0.f);
       }
+      {
+        const uint8_t* t = t0;
 #pragma unroll 2
-      for (int j = 0; j < nj; ++j) {
-        float2 x[H];
-        IO<T>::unpack2(*reinterpret_cast<const uint4*>(t0 + (uint32_t)j * kStep), x);
+        for (int j = 0; j < nj; ++j, t += kStep) {
+          float2 x[H];
+          IO<T>::unpack2(*reinterpret_cast<const uint4*>(t), x);
 #pragma unroll
-        for (int k = 0; k < H; ++k) s2[k] = f2add(s2[k], exp_shift<T>(x[k], nm[k], nml[k]));
+          for (int k = 0; k < H; ++k) s2[k] = f2add(s2[k], exp_shift<T>(x[k], nm[k], nml[k]));
+        }
       }
       float s[VEC];
 #pragma unroll
@@ -307,10 +312,11 @@ outer_softmax_kernel(const __grid_constant__ CUtensorMap map0, const __grid_cons
       for (int k = 0; k < H; ++k)
         fin[k] = LOG ? make_float2(-logf(s[2 * k]), -logf(s[2 * k + 1])) : make_float2(rcp_fast(s[2 * k]), rcp_fast(s[2 * k + 1]));
       if (col_ok) {
+        const uint8_t* t = t0;
 #pragma unroll 2
-        for (int j = 0; j < nj; ++j) {
+        for (int j = 0; j < nj; ++j, t += kStep, o += out_step) {
           float2 x[H];
-          IO<T>::unpack2(*reinterpret_cast<const uint4*>(t0 + (uint32_t)j * kStep), x);
+          IO<T>::unpack2(*reinterpret_cast<const uint4*>(t), x);
 #pragma unroll
           for (int k = 0; k < H; ++k) {
             if constexpr (LOG) {
@@ -319,23 +325,23 @@ outer_softmax_kernel(const __grid_constant__ CUtensorMap map0, const __grid_cons
               x[k] = f2mul(exp_shift<T>(x[k], nm[k], nml[k]), fin[k]);
             }
           }
-          stg_128_stream(o + (size_t)j * out_step, IO<T>::pack2(x));
+          stg_128_stream(o, IO<T>::pack2(x));
         }
       }
     } else {
-      const uint8_t* t1 = t0 + p.tile_bytes;  // y
       float2 s2[H];
 #pragma unroll
       for (int k = 0; k < H; ++k) s2[k] = f2(0.f);
+      const uint8_t* t = t0;
 #pragma unroll 4
-      for (int j = 0; j < nj; ++j) {
+      for (int j = 0; j < nj; ++j, t += kStep) {
         float2 dy[H], y[H];
-        IO<T>::unpack2(*reinterpret_cast<const uint4*>(t0 + (uint32_t)j * kStep), dy);
+        IO<T>::unpack2(*reinterpret_cast<const uint4*>(t), dy);
         if constexpr (LOG) {
 #pragma unroll
           for (int k = 0; k < H; ++k) s2[k] = f2add(s2[k], dy[k]);
         } else {
-          IO<T>::unpack2(*reinterpret_cast<const uint4*>(t1 + (uint32_t)j * kStep), y);
+          IO<T>::unpack2(*reinterpret_cast<const uint4*>(t + p.tile_bytes), y);
 #pragma unroll
           for (int k = 0; k < H; ++k) s2[k] = f2fma(y[k], dy[k], s2[k]);
         }
@@ -357,11 +363,12 @@ outer_softmax_kernel(const __grid_constant__ CUtensorMap map0, const __grid_cons
         ns[k] = make_float2(-s[2 * k], -s[2 * k + 1]);
       }
       if (col_ok) {
+        t = t0;
 #pragma unroll 2
-        for (int j = 0; j < nj; ++j) {
+        for (int j = 0; j < nj; ++j, t += kStep, o += out_step) {
           float2 dy[H], y[H];
-          IO<T>::unpack2(*reinterpret_cast<const uint4*>(t0 + (uint32_t)j * kStep), dy);
-          IO<T>::unpack2(*reinterpret_cast<const uint4*>(t1 + (uint32_t)j * kStep), y);
+          IO<T>::unpack2(*reinterpret_cast<const uint4*>(t), dy);
+          IO<T>::unpack2(*reinterpret_cast<const uint4*>(t + p.tile_bytes), y);
 #pragma unroll
           for (int k = 0; k < H; ++k) {
             if constexpr (LOG) {
@@ -370,7 +377,7 @@ outer_softmax_kernel(const __grid_constant__ CUtensorMap map0, const __grid_cons
               dy[k] = f2fma(y[k], ns[k], f2mul(y[k], dy[k]));
             }
           }
-          stg_128_stream(o + (size_t)j * out_step, IO<T>::pack2(dy));
+          stg_128_stream(o, IO<T>::pack2(dy));
         }
       }
     }
@@ -474,21 +481,28 @@ bool outer_make_plan(const OuterArgs& a, OuterPlan* plan, char* err, size_t errl
   }
   const int forced_w = env_int_outer("B200NORM_OUTER_W");
   const int forced_depth = env_int_outer("B200NORM_OUTER_DEPTH");
-  const int64_t limit2 = kSmemPerSm / 2 - 1024;  // two CTAs per SM
+  // Tile policy (measured, profiles/r01j_outer_sweep.txt): the per-slab fixed cost (two column reductions, the
+  // cluster exchange, barrier latency) is amortised by tiles of ~64 KB, and load / compute overlap comes from
+  // THREE co-resident CTAs per SM with one tile each rather than from two half-size tiles per CTA; clusters are
+  // kept as small as the extent allows (every doubling adds exchange traffic and lock-step waiting). Order of
+  // preference: one tile at three CTAs per SM, two tiles at two / one CTA per SM, one tile at one CTA per SM;
+  // inside a tier the smallest cluster, then the widest slab that fits.
+  const int64_t limit3 = kSmemPerSm / 3 - 1024;
+  const int64_t limit2 = kSmemPerSm / 2 - 1024;
   const int64_t limit1 = a.smem_optin;
   struct Tier {
     int depth;
     int64_t limit;
   };
-  const Tier tiers[] = {{2, limit2}, {2, limit1}, {1, limit1}};
+  const Tier tiers[] = {{1, limit3}, {2, limit2}, {2, limit1}, {1, limit1}};
   static const int cs[] = {1, 2, 4, 8, 16};
   int W = 0, C = 0, depth = 0;
   for (const Tier& t : tiers) {
     if (forced_depth != 0 && t.depth != forced_depth) continue;
-    for (int w : {512, 256, 128, 64}) {
-      if (forced_w != 0 ? w != forced_w : w > wpref) continue;
-      for (int c : cs) {
-        if (a.cluster_forced != 0 && c != a.cluster_forced) continue;
+    for (int c : cs) {
+      if (a.cluster_forced != 0 && c != a.cluster_forced) continue;
+      for (int w : {512, 256, 128, 64}) {
+        if (forced_w != 0 ? w != forced_w : w > wpref) continue;
         const Geometry g = geometry(a, w, c);
         if ((int64_t)g.overhead + (int64_t)t.depth * g.stage <= t.limit) {
           W = w;
