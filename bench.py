@@ -46,6 +46,10 @@ WORKLOADS = {
     "c3": ("softmax fwd+bwd bf16 [65536,8192]", 65536, 8192, torch.bfloat16, "softmax_fwd_bwd"),
     "c4": ("LayerNorm bwd bf16 [32768,12288]", 32768, 12288, torch.bfloat16, "layernorm_bwd"),
     "c5": ("RMSNorm fwd+bwd bf16 [4096,65536]", 4096, 65536, torch.bfloat16, "rmsnorm_fwd_bwd"),
+    # SURVEY section 8f rank 2 (not a BASELINE.json config): the reference's outer_persistent benchmark,
+    # softmax over dim 0 (benchmarks/python/test_softmax_{fwd,bwd}.py, reduction_axis = 0)
+    "o1": ("softmax over dim 0 fwd+bwd bf16 [8192,18432] (outer-persistent)", 8192, 18432, torch.bfloat16,
+           "softmax_outer_fwd_bwd"),
 }
 EPS = 1e-5
 L2_BYTES = 126 * 1024 * 1024
@@ -55,7 +59,7 @@ def iobytes(kind: str, m: int, n: int, s: int) -> dict:
     """The reference's IO-byte accounting per op (benchmarks/python/test_*_{fwd,bwd}.py)."""
     if kind == "rmsnorm_fwd_bwd":
         return {"fwd": s * (2 * m * n + n) + 4 * m, "bwd": s * (3 * m * n + 2 * n) + 4 * m}
-    if kind == "softmax_fwd_bwd":
+    if kind in ("softmax_fwd_bwd", "softmax_outer_fwd_bwd"):
         return {"fwd": s * 2 * m * n, "bwd": s * 3 * m * n}
     if kind == "layernorm_bwd":
         return {"bwd": s * 3 * (m * n + n) + 4 * 2 * m}
@@ -190,6 +194,8 @@ class Step:
                 self.saved.append(ops.rms_norm_fwd(x, self.w, EPS, stat_is_rms=True)[1])
             elif kind == "softmax_fwd_bwd":
                 self.saved.append(ops.softmax_fwd(x))
+            elif kind == "softmax_outer_fwd_bwd":
+                self.saved.append(ops.softmax_fwd(x, dim=0))
             else:
                 self.saved.append(None)
         torch.cuda.synchronize(device)
@@ -202,6 +208,8 @@ class Step:
             return ops.rms_norm_fwd(x, self.w, EPS, stat_is_rms=True)
         if self.kind == "softmax_fwd_bwd":
             return (ops.softmax_fwd(x),)
+        if self.kind == "softmax_outer_fwd_bwd":
+            return (ops.softmax_fwd(x, dim=0),)
         if self.kind == "layernorm_fwd":
             return ops.layer_norm_fwd(x, self.w, self.w, EPS)
         return None
@@ -221,6 +229,8 @@ class Step:
             return ops.rms_norm_bwd(dy, x, rms, self.w, stat_is_rms=True, centered=False)
         if self.kind == "softmax_fwd_bwd":
             return (ops.softmax_bwd(dy, fwd_out[0] if fwd_out is not None else saved),)
+        if self.kind == "softmax_outer_fwd_bwd":
+            return (ops.softmax_bwd(dy, fwd_out[0] if fwd_out is not None else saved, dim=0),)
         if self.kind == "layernorm_bwd":
             mean, invstd = saved
             if self.world > 1:
@@ -267,6 +277,8 @@ class E2E:
             self.fd_fwd, self.fd_bwd = define(F.rmsnorm_fwd_py, EPS), define(F.rmsnorm_bwd_py)
         elif kind == "softmax_fwd_bwd":
             self.fd_fwd, self.fd_bwd = define(F.softmax_fwd_py), define(F.softmax_bwd_py)
+        elif kind == "softmax_outer_fwd_bwd":
+            self.fd_fwd, self.fd_bwd = define(F.softmax_fwd_py, 0), define(F.softmax_bwd_py, 0)
         elif kind == "layernorm_bwd":
             self.fd_fwd, self.fd_bwd = define(F.layernorm_fwd_py, EPS), define(F.layernorm_bwd_py)
         else:
@@ -288,7 +300,7 @@ class E2E:
             y, rms = self.fd_fwd.execute([x, w])
             dx, dw = self.fd_bwd.execute([x, rms, dy, w])
             return [y, rms, dx, dw]
-        if k == "softmax_fwd_bwd":
+        if k in ("softmax_fwd_bwd", "softmax_outer_fwd_bwd"):
             (y,) = self.fd_fwd.execute([x])
             (dx,) = self.fd_bwd.execute([y, dy])
             return [y, dx]
@@ -343,6 +355,9 @@ def cpu_step_fn(kind, dtype):
         if kind == "softmax_fwd_bwd":
             y = AO.softmax_fwd(x)
             return AO.softmax_bwd_python(y, dy)
+        if kind == "softmax_outer_fwd_bwd":
+            y = AO.softmax_fwd(x, dim=0)
+            return AO.softmax_bwd_python(y, dy, dim=0)
         if kind == "layernorm_bwd":
             _, mean, invstd = AO.layer_norm_fwd(x, None, None, EPS)
             return AO.layer_norm_bwd_python(x, dy, mean.view(-1), invstd, w)

@@ -58,6 +58,8 @@ struct OuterParams {
   int32_t cluster;     // C
   int32_t depth;       // 1 or 2 tiles
   int32_t round_sum;
+  int32_t plain_stores;       // 1: default-policy st.global instead of the streaming (evict-first) form
+  int32_t debug_skip_reduce;  // tuning aid (B200NORM_OUTER_SKIP_REDUCE): wrong results, timing only
   uint32_t slab_bytes; // W
   uint32_t tile_bytes; // Rc * W (one stream)
   uint32_t stage_bytes;  // nstreams * tile_bytes
@@ -282,7 +284,7 @@ outer_softmax_kernel(const __grid_constant__ CUtensorMap map0, const __grid_cons
           for (int k = 0; k < VEC; ++k) m[k] = MaxOp::apply(m[k], x[k]);
         }
       }
-      col_reduce<MaxOp, VEC>(m, cx);
+      if (!p.debug_skip_reduce) col_reduce<MaxOp, VEC>(m, cx);
       float2 nm[H], nml[H], s2[H];
 #pragma unroll
       for (int k = 0; k < H; ++k) {
@@ -306,7 +308,7 @@ outer_softmax_kernel(const __grid_constant__ CUtensorMap map0, const __grid_cons
         s[2 * k] = s2[k].x;
         s[2 * k + 1] = s2[k].y;
       }
-      col_reduce<SumOp, VEC>(s, cx);
+      if (!p.debug_skip_reduce) col_reduce<SumOp, VEC>(s, cx);
       float2 fin[H];
 #pragma unroll
       for (int k = 0; k < H; ++k)
@@ -325,7 +327,11 @@ outer_softmax_kernel(const __grid_constant__ CUtensorMap map0, const __grid_cons
               x[k] = f2mul(exp_shift<T>(x[k], nm[k], nml[k]), fin[k]);
             }
           }
-          stg_128_stream(o, IO<T>::pack2(x));
+          if (p.plain_stores) {
+            *reinterpret_cast<uint4*>(o) = IO<T>::pack2(x);
+          } else {
+            stg_128_stream(o, IO<T>::pack2(x));
+          }
         }
       }
     } else {
@@ -352,7 +358,7 @@ outer_softmax_kernel(const __grid_constant__ CUtensorMap map0, const __grid_cons
         s[2 * k] = s2[k].x;
         s[2 * k + 1] = s2[k].y;
       }
-      col_reduce<SumOp, VEC>(s, cx);
+      if (!p.debug_skip_reduce) col_reduce<SumOp, VEC>(s, cx);
       float2 ns[H];
 #pragma unroll
       for (int k = 0; k < H; ++k) {
@@ -377,7 +383,11 @@ outer_softmax_kernel(const __grid_constant__ CUtensorMap map0, const __grid_cons
               dy[k] = f2fma(y[k], ns[k], f2mul(y[k], dy[k]));
             }
           }
-          stg_128_stream(o, IO<T>::pack2(dy));
+          if (p.plain_stores) {
+            *reinterpret_cast<uint4*>(o) = IO<T>::pack2(dy);
+          } else {
+            stg_128_stream(o, IO<T>::pack2(dy));
+          }
         }
       }
     }
@@ -487,7 +497,9 @@ bool outer_make_plan(const OuterArgs& a, OuterPlan* plan, char* err, size_t errl
   // kept as small as the extent allows (every doubling adds exchange traffic and lock-step waiting). Order of
   // preference: one tile at three CTAs per SM, two tiles at two / one CTA per SM, one tile at one CTA per SM;
   // inside a tier the smallest cluster, then the widest slab that fits.
-  const int64_t limit3 = kSmemPerSm / 3 - 1024;
+  int target_per_sm = env_int_outer("B200NORM_OUTER_PER_SM");  // tuning: 1..3 CTAs per SM for the first tier
+  if (target_per_sm < 1 || target_per_sm > 3) target_per_sm = 3;
+  const int64_t limit3 = kSmemPerSm / target_per_sm - 1024;
   const int64_t limit2 = kSmemPerSm / 2 - 1024;
   const int64_t limit1 = a.smem_optin;
   struct Tier {
@@ -704,6 +716,8 @@ int outer_launch(const OuterArgs& a, void* stream_v, char* err, size_t errlen) {
   p.cluster = pl.cluster;
   p.depth = pl.depth;
   p.round_sum = a.round_sum;
+  p.debug_skip_reduce = env_int_outer("B200NORM_OUTER_SKIP_REDUCE");
+  p.plain_stores = env_int_outer("B200NORM_OUTER_PLAIN_ST");
   p.slab_bytes = (uint32_t)pl.slab_bytes;
   p.tile_bytes = pl.tile_bytes;
   p.stage_bytes = pl.stage_bytes;

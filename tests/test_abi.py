@@ -127,26 +127,32 @@ def _outer_plan(op, dt, m, n, cluster=0):
 
 
 def test_outer_persistent_planner():
-    """Dispatch rules of the outer-persistent softmax family (pure host logic, nominal B200): one CTA
-    per column slab while M * W fits its shared memory twice over, then a cluster split along M; the
-    extent a 16-CTA cluster cannot hold is declined (the reference segments such fusions,
-    scheduler/normalization_outer.cpp:451-683 canSchedule)."""
-    # small reduced extent: one CTA per slab, two tiles in flight, wide slabs when N gives enough of them
+    """Dispatch rules of the outer-persistent softmax family (pure host logic, nominal B200): one tile of
+    up to ~72 KB per CTA at three CTAs per SM, one CTA per column slab while M * W fits that tile, then the
+    smallest cluster split along M that does; the extent a 16-CTA cluster cannot hold is declined (the
+    reference segments such fusions, scheduler/normalization_outer.cpp:451-683 canSchedule)."""
+    per_cta = 233472 // 3 - 1024
+    # small reduced extent: one CTA per slab, the widest slab when N gives enough of them
     p = _outer_plan(L.OP_SOFTMAX_FWD, L.DT_BF16, 16, 4 * 73728)
-    assert p["variant"] == "tma" and p["cluster_size"] == 1 and p["stages"] == 2 and p["threads_per_row"] == 32
-    # the reference's outer_persistent benchmark rows {512, 2048, 8192, 16384} at N = 4096 bf16
-    p = _outer_plan(L.OP_SOFTMAX_FWD, L.DT_BF16, 512, 4096)
-    assert p["cluster_size"] * p["tile_rows"] >= 512 and p["stages"] == 2 and p["block"] == 256
-    p = _outer_plan(L.OP_SOFTMAX_FWD, L.DT_BF16, 2048, 4096)
-    assert p["variant"] == "cluster" and p["cluster_size"] * p["tile_rows"] >= 2048 and p["stages"] == 2
-    p = _outer_plan(L.OP_SOFTMAX_FWD, L.DT_BF16, 8192, 4096)
-    assert p["variant"] == "cluster" and p["cluster_size"] == 16 and p["tile_rows"] == 512 and p["stages"] == 2
-    assert p["grid"] % 16 == 0 and p["smem_bytes"] <= 232448 // 2  # two CTAs per SM
-    p = _outer_plan(L.OP_SOFTMAX_BWD, L.DT_BF16, 8192, 4096)  # two streams: narrower slabs or one tile
+    assert p["variant"] == "tma" and p["cluster_size"] == 1 and p["stages"] == 1 and p["threads_per_row"] == 32
+    p = _outer_plan(L.OP_SOFTMAX_FWD, L.DT_BF16, 512, 65536)
+    assert p["variant"] == "tma" and p["cluster_size"] == 1 and p["tile_rows"] == 512 and p["smem_bytes"] <= per_cta
+    # the reference's outer_persistent benchmark rows {2048, 8192, 16384}: the smallest cluster that fits
+    p = _outer_plan(L.OP_SOFTMAX_FWD, L.DT_BF16, 2048, 16384)
+    assert p["variant"] == "cluster" and p["cluster_size"] == 2 and p["tile_rows"] == 1024 and p["smem_bytes"] <= per_cta
+    p = _outer_plan(L.OP_SOFTMAX_FWD, L.DT_BF16, 8192, 18432)
+    assert p["cluster_size"] == 8 and p["tile_rows"] == 1024 and p["block"] == 256 and p["smem_bytes"] <= per_cta
+    assert p["grid"] % 8 == 0
+    p = _outer_plan(L.OP_SOFTMAX_BWD, L.DT_BF16, 8192, 18432)  # two streams: half the rows per CTA
+    assert p["cluster_size"] == 16 and p["tile_rows"] == 512 and p["smem_bytes"] <= per_cta
+    p = _outer_plan(L.OP_SOFTMAX_FWD, L.DT_BF16, 16384, 8192)
+    assert p["cluster_size"] == 16 and p["tile_rows"] == 1024 and p["smem_bytes"] <= per_cta
+    assert p["algorithmic_bytes"] == 2 * 2 * 16384 * 8192
+    p = _outer_plan(L.OP_SOFTMAX_BWD, L.DT_BF16, 16384, 8192)  # beyond three per SM: one CTA per SM
     assert p["cluster_size"] == 16 and p["smem_bytes"] <= 232448
-    p = _outer_plan(L.OP_SOFTMAX_FWD, L.DT_BF16, 16384, 4096)
-    assert p["cluster_size"] == 16 and p["tile_rows"] == 1024 and p["smem_bytes"] <= 232448
-    assert p["algorithmic_bytes"] == 2 * 2 * 16384 * 4096
+    # few slabs: the rows are split further so that more SMs stream
+    p = _outer_plan(L.OP_SOFTMAX_FWD, L.DT_BF16, 512, 4096)
+    assert p["cluster_size"] * (4096 * 2 // (16 * p["threads_per_row"])) >= 148
     # forced cluster sizes are honoured
     for c in (1, 2, 4, 8, 16):
         assert _outer_plan(L.OP_SOFTMAX_FWD, L.DT_F32, 777, 384, c)["cluster_size"] == c
