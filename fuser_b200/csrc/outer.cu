@@ -58,6 +58,7 @@ struct OuterParams {
   int32_t cluster;     // C
   int32_t depth;       // 1 or 2 tiles
   int32_t round_sum;
+  int32_t two_exchanges;      // tuning (B200NORM_OUTER_TWO_EXCH=1): forward exchanges max and sum separately
   int32_t plain_stores;       // 1: default-policy st.global instead of the streaming (evict-first) form
   int32_t debug_skip_reduce;  // tuning aid (B200NORM_OUTER_SKIP_REDUCE): wrong results, timing only
   uint32_t slab_bytes; // W
@@ -143,7 +144,7 @@ struct ColCtx {
   uint32_t off_cls;
 };
 
-template <typename Op, int VEC>
+template <typename Op, int VEC, bool kCluster = true>
 __device__ __forceinline__ void col_reduce(float (&v)[VEC], ColCtx& x) {
   for (int off = 16; off >= x.LC; off >>= 1) {
 #pragma unroll
@@ -169,7 +170,7 @@ __device__ __forceinline__ void col_reduce(float (&v)[VEC], ColCtx& x) {
       a.z = Op::apply(a.z, b.z);
       a.w = Op::apply(a.w, b.w);
     }
-    if (x.C > 1) {
+    if (kCluster && x.C > 1) {
       const uint32_t set = x.nx & 1u, parity = (x.nx >> 1) & 1u;
       const uint32_t bar = x.xbar + 8u * set;
       if (x.tid == 0) mbar_arrive_expect_tx(bar, x.C * (uint32_t)x.SC * 4u);
@@ -191,7 +192,7 @@ __device__ __forceinline__ void col_reduce(float (&v)[VEC], ColCtx& x) {
     }
     *reinterpret_cast<float4*>(x.fin + c4) = a;
   }
-  if (x.C > 1) ++x.nx;
+  if (kCluster && x.C > 1) ++x.nx;
   __syncthreads();
 #pragma unroll
   for (int k = 0; k < VEC; k += 4) {
@@ -200,6 +201,90 @@ __device__ __forceinline__ void col_reduce(float (&v)[VEC], ColCtx& x) {
     v[k + 1] = t.y;
     v[k + 2] = t.z;
     v[k + 3] = t.w;
+  }
+}
+
+// Softmax forward over a cluster: ONE exchange per slab instead of two. Every CTA reduces its own rows
+// completely — max (local col_reduce, result in fin), then the sum of exp(x - CTA max) — and the cluster
+// exchanges (max, sum) PAIRS: M = max_q m_q, S = sum_q s_q * exp(m_q - M). The cluster is a lock-step on
+// its slowest tile load, so meeting once instead of twice is what this buys. A CTA whose rows are all
+// -inf (or that holds no rows) contributes (m = -inf, s = 0): its sum was taken against 0 instead of
+// -inf by the caller, and its factor is exp(-inf - M) = 0, or 1 when M is -inf too (then S = 0 and the
+// last pass turns the column into NaN through x - M, as the op-by-op evaluation does). NaN and +inf
+// propagate through max / expf.
+// in: m = CTA max of the thread's columns (as left in fin by the local max reduce), s = thread's partial sums;
+// out: m = cluster max, s = cluster sum relative to it.
+__device__ __forceinline__ float pair_factor(float mq, float M) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"((mq - M) * 1.4426950408889634f));
+  return mq == M ? 1.f : e;
+}
+
+template <int VEC>
+__device__ __forceinline__ void col_reduce_softmax_pair(float (&m)[VEC], float (&v)[VEC], ColCtx& x) {
+  for (int off = 16; off >= x.LC; off >>= 1) {
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) v[k] += __shfl_xor_sync(0xffffffffu, v[k], off);
+  }
+  if (x.lane < x.LC) {
+    float* dst = x.wpart + x.warp * x.SC + x.c * VEC;
+#pragma unroll
+    for (int k = 0; k < VEC; k += 4) *reinterpret_cast<float4*>(dst + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+  }
+  __syncthreads();  // also: every thread has read the CTA max out of fin
+  if (x.tid < (x.SC >> 2)) {
+    const int c4 = x.tid << 2;
+    float4 a = lds_f4(x.wpart + c4);
+#pragma unroll
+    for (int w = 1; w < kOuterWarps; ++w) {
+      const float4 b = lds_f4(x.wpart + w * x.SC + c4);
+      a.x += b.x;
+      a.y += b.y;
+      a.z += b.z;
+      a.w += b.w;
+    }
+    const float4 mc = lds_f4(x.fin + c4);
+    const uint32_t set = x.nx & 1u, parity = (x.nx >> 1) & 1u;
+    const uint32_t bar = x.xbar + 8u * set;
+    if (x.tid == 0) mbar_arrive_expect_tx(bar, x.C * (uint32_t)x.SC * 8u);
+    // slot layout of this exchange: [set][rank][max | sum][SC]
+    const uint32_t local = x.smem0 + x.off_cls + (((set * x.C + x.crank) * 2u) * (uint32_t)x.SC + (uint32_t)c4) * 4u;
+    for (uint32_t q = 0; q < x.C; ++q) {
+      const uint32_t rbar = map_to_cta(bar, q);
+      st_async_f32x4(map_to_cta(local, q), mc, rbar);
+      st_async_f32x4(map_to_cta(local + (uint32_t)x.SC * 4u, q), a, rbar);
+    }
+  }
+  // one column per thread for the combine (the factors cost an exp each: spread over SC threads, not SC / 4)
+  if (x.tid < x.SC) {
+    const uint32_t set = x.nx & 1u, parity = (x.nx >> 1) & 1u;
+    mbar_wait(x.xbar + 8u * set, parity);
+    const volatile float* base = x.cls + (size_t)set * x.C * 2 * x.SC + x.tid;
+    float M = base[0];
+    for (uint32_t q = 1; q < x.C; ++q) M = MaxOp::apply(M, base[(size_t)q * 2 * x.SC]);
+    float S = 0.f;
+    for (uint32_t q = 0; q < x.C; ++q) {
+      const float mq = base[(size_t)q * 2 * x.SC];
+      const float sq = base[(size_t)q * 2 * x.SC + x.SC];
+      S = fmaf(sq, pair_factor(mq, M), S);
+    }
+    x.fin[x.tid] = M;
+    x.fin[x.SC + x.tid] = S;
+  }
+  ++x.nx;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < VEC; k += 4) {
+    const float4 t = lds_f4(x.fin + x.c * VEC + k);
+    const float4 u = lds_f4(x.fin + x.SC + x.c * VEC + k);
+    m[k] = t.x;
+    m[k + 1] = t.y;
+    m[k + 2] = t.z;
+    m[k + 3] = t.w;
+    v[k] = u.x;
+    v[k + 1] = u.y;
+    v[k + 2] = u.z;
+    v[k + 3] = u.w;
   }
 }
 
@@ -309,12 +394,24 @@ outer_softmax_kernel(const __grid_constant__ CUtensorMap map0, const __grid_cons
           for (int k = 0; k < VEC; ++k) m[k] = MaxOp::apply(m[k], x[k]);
         }
       }
-      if (!p.debug_skip_reduce) col_reduce<MaxOp, VEC>(m, cx);
+      // a cluster meets once per slab: the max stays CTA-local here and (max, sum) pairs are exchanged
+      // after the second pass (col_reduce_softmax_pair)
+      const bool pair = cx.C > 1 && !p.two_exchanges;
+      if (!p.debug_skip_reduce) {
+        if (pair) {
+          col_reduce<MaxOp, VEC, false>(m, cx);
+        } else {
+          col_reduce<MaxOp, VEC>(m, cx);
+        }
+      }
       float2 nm[H], nml[H], s2[H];
 #pragma unroll
       for (int k = 0; k < H; ++k) {
-        nm[k] = make_float2(-m[2 * k], -m[2 * k + 1]);
-        nml[k] = make_float2(-m[2 * k] * kLog2e, -m[2 * k + 1] * kLog2e);
+        // a CTA with nothing but -inf takes its sum against 0 (= 0) instead of producing inf - inf
+        const float ma = (pair && m[2 * k] == -INFINITY) ? 0.f : m[2 * k];
+        const float mb = (pair && m[2 * k + 1] == -INFINITY) ? 0.f : m[2 * k + 1];
+        nm[k] = make_float2(-ma, -mb);
+        nml[k] = make_float2(-ma * kLog2e, -mb * kLog2e);
         s2[k] = f2(0.f);
       }
       {
@@ -333,7 +430,18 @@ outer_softmax_kernel(const __grid_constant__ CUtensorMap map0, const __grid_cons
         s[2 * k] = s2[k].x;
         s[2 * k + 1] = s2[k].y;
       }
-      if (!p.debug_skip_reduce) col_reduce<SumOp, VEC>(s, cx);
+      if (!p.debug_skip_reduce) {
+        if (pair) {
+          col_reduce_softmax_pair<VEC>(m, s, cx);
+#pragma unroll
+          for (int k = 0; k < H; ++k) {  // from here on: the cluster max
+            nm[k] = make_float2(-m[2 * k], -m[2 * k + 1]);
+            nml[k] = make_float2(-m[2 * k] * kLog2e, -m[2 * k + 1] * kLog2e);
+          }
+        } else {
+          col_reduce<SumOp, VEC>(s, cx);
+        }
+      }
       float2 fin[H];
 #pragma unroll
       for (int k = 0; k < H; ++k)
@@ -485,7 +593,7 @@ Geometry geometry(const OuterArgs& a, int W, int C) {
   g.tile = (uint32_t)g.rows_cta * (uint32_t)W;
   g.stage = (uint32_t)ns * g.tile;
   const uint32_t sc = (uint32_t)(W / es);
-  g.overhead = up(128 + kOuterWarps * sc * 4 + (C > 1 ? 2u * (uint32_t)C * sc * 4 : 0u) + sc * 4, 128);
+  g.overhead = up(128 + kOuterWarps * sc * 4 + (C > 1 ? 4u * (uint32_t)C * sc * 4 : 0u) + 2 * sc * 4, 128);
   return g;
 }
 
@@ -577,9 +685,9 @@ bool outer_make_plan(const OuterArgs& a, OuterPlan* plan, char* err, size_t errl
   p.off_wpart = off;
   off += kOuterWarps * sc * 4;
   p.off_cls = off;
-  if (C > 1) off += 2u * (uint32_t)C * sc * 4;
+  if (C > 1) off += 4u * (uint32_t)C * sc * 4;  // two slot sets of [C][max | sum][SC]
   p.off_fin = off;
-  off += sc * 4;
+  off += 2 * sc * 4;
   off = up(off, 128);
   p.off_tiles = off;
   p.smem = off + (uint32_t)depth * g.stage;
@@ -743,6 +851,7 @@ int outer_launch(const OuterArgs& a, void* stream_v, char* err, size_t errlen) {
   p.round_sum = a.round_sum;
   p.debug_skip_reduce = env_int_outer("B200NORM_OUTER_SKIP_REDUCE");
   p.plain_stores = env_int_outer("B200NORM_OUTER_PLAIN_ST");
+  p.two_exchanges = env_int_outer("B200NORM_OUTER_TWO_EXCH");
   p.slab_bytes = (uint32_t)pl.slab_bytes;
   p.tile_bytes = pl.tile_bytes;
   p.stage_bytes = pl.stage_bytes;

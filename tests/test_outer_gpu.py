@@ -128,6 +128,22 @@ def test_outer_edge_cases():
     torch.cuda.synchronize()
     AO.assert_close(y, AO.softmax_fwd(xs, dim=0), 96 * 96, "softmax with NaN/Inf columns")
     assert torch.isnan(y[:, 1:4]).all() and not torch.isnan(y[:, 0]).any() and not torch.isnan(y[:, 4:]).any()
+    # the same through a cluster split (the forward exchanges (max, sum) pairs): one CTA's rows all -inf
+    # in a column that is finite elsewhere must NOT poison the column; NaN / +inf / all -inf still do
+    for cluster in (2, 4, 8):
+        xs = torch.randn(96, 64).to(dt)
+        xs[7, 1] = float("nan")
+        xs[:, 2] = float("-inf")
+        xs[5, 3] = float("inf")
+        xs[: 96 // cluster, 5] = float("-inf")  # exactly the rows of cluster rank 0
+        xs[40:, 6] = float("-inf")
+        for log in (False, True):
+            y = ops.softmax_fwd(xs.cuda(), dim=0, log=log, cluster_size=cluster)
+            torch.cuda.synchronize()
+            ref = AO.log_softmax_fwd(xs, dim=0) if log else AO.softmax_fwd(xs, dim=0)
+            AO.assert_close(y, ref, 96 * 96, f"NaN/Inf columns, cluster {cluster}, log={log}")
+            assert torch.isnan(y[:, 1:4]).all() and not torch.isnan(y[:, 0]).any()
+            assert not torch.isnan(y[:, 4:]).any(), f"cluster {cluster}: -inf rows poisoned a finite column"
     # shapes the persistent kernels decline: misaligned rows, reduced extent beyond a 16-CTA cluster
     with pytest.raises(L.UnsupportedSegment):
         ops.softmax_fwd(torch.randn(32, 100).to(dt).cuda(), dim=0)  # 200 bytes per row
