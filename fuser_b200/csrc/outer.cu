@@ -268,15 +268,16 @@ __device__ __forceinline__ void col_reduce_softmax_pair(float (&m)[VEC], float (
       const float sq = base[(size_t)q * 2 * x.SC + x.SC];
       S = fmaf(sq, pair_factor(mq, M), S);
     }
-    x.fin[x.tid] = M;
-    x.fin[x.SC + x.tid] = S;
+    // results go to their own planes: plane 0 (the CTA max read by the senders above) is left alone
+    x.fin[x.SC + x.tid] = M;
+    x.fin[2 * x.SC + x.tid] = S;
   }
   ++x.nx;
   __syncthreads();
 #pragma unroll
   for (int k = 0; k < VEC; k += 4) {
-    const float4 t = lds_f4(x.fin + x.c * VEC + k);
-    const float4 u = lds_f4(x.fin + x.SC + x.c * VEC + k);
+    const float4 t = lds_f4(x.fin + x.SC + x.c * VEC + k);
+    const float4 u = lds_f4(x.fin + 2 * x.SC + x.c * VEC + k);
     m[k] = t.x;
     m[k + 1] = t.y;
     m[k + 2] = t.z;
@@ -593,7 +594,7 @@ Geometry geometry(const OuterArgs& a, int W, int C) {
   g.tile = (uint32_t)g.rows_cta * (uint32_t)W;
   g.stage = (uint32_t)ns * g.tile;
   const uint32_t sc = (uint32_t)(W / es);
-  g.overhead = up(128 + kOuterWarps * sc * 4 + (C > 1 ? 4u * (uint32_t)C * sc * 4 : 0u) + 2 * sc * 4, 128);
+  g.overhead = up(128 + kOuterWarps * sc * 4 + (C > 1 ? 4u * (uint32_t)C * sc * 4 : 0u) + 3 * sc * 4, 128);
   return g;
 }
 
@@ -687,7 +688,7 @@ bool outer_make_plan(const OuterArgs& a, OuterPlan* plan, char* err, size_t errl
   p.off_cls = off;
   if (C > 1) off += 4u * (uint32_t)C * sc * 4;  // two slot sets of [C][max | sum][SC]
   p.off_fin = off;
-  off += 2 * sc * 4;
+  off += 3 * sc * 4;
   off = up(off, 128);
   p.off_tiles = off;
   p.smem = off + (uint32_t)depth * g.stage;
