@@ -114,6 +114,7 @@ uint64_t algorithmic_bytes(const b200norm_desc& d) {
       // reads or writes, as benchmarks/python/core.py:compute_total_iobytes counts them)
       const uint64_t extra = ((d.flags & B200NORM_F_ADD_RESIDUAL) ? s * M * N : 0) +
                              ((d.flags & B200NORM_F_ADD_RESIDUAL) && (d.flags & B200NORM_F_OUT_SUM) ? s * M * N : 0);
+      if (d.op == B200NORM_OP_LAYERNORM_FWD && (d.flags & B200NORM_F_OUTER)) return s * 2 * (M * N + N) + 4 * 2 * N;
       if (d.op == B200NORM_OP_LAYERNORM_FWD) return s * 2 * (M * N + N) + 4 * 2 * M + extra;
       return s * (2 * M * N + N) + 4 * M + extra;
     }
@@ -574,6 +575,8 @@ OuterArgs outer_args_from(const b200norm_desc& d) {
   a.dtype = d.io_dtype;
   a.M = d.rows;
   a.N = d.cols;
+  a.norm = d.op == B200NORM_OP_LAYERNORM_FWD ? 1 : 0;
+  a.eps = d.eps;
   a.round_sum = (d.flags & B200NORM_F_ROUND_ROWSUM) ? 1 : 0;
   a.cluster_forced = d.cluster_size != 0 ? d.cluster_size : env_int("B200NORM_CLUSTER");
   a.has_device = dev.has_device;
@@ -595,8 +598,10 @@ int check_desc(const b200norm_desc* d) {
       d->cluster_size != 8 && d->cluster_size != 16)
     return fail(B200NORM_ERR_BAD_ARG, "cluster_size must be 0,1,2,4,8,16");
   if (d->variant < 0 || d->variant > B200NORM_VARIANT_CLUSTER) return fail(B200NORM_ERR_BAD_ARG, "bad variant");
-  if ((d->flags & B200NORM_F_OUTER) && !is_softmax_op(d->op))
-    return fail(B200NORM_ERR_UNSUPPORTED, "B200NORM_F_OUTER applies to the softmax / log-softmax ops only");
+  if ((d->flags & B200NORM_F_OUTER) && !is_softmax_op(d->op) && d->op != B200NORM_OP_LAYERNORM_FWD)
+    return fail(B200NORM_ERR_UNSUPPORTED, "B200NORM_F_OUTER applies to softmax / log-softmax and to the LayerNorm-type forward");
+  if ((d->flags & B200NORM_F_OUTER) && (d->flags & B200NORM_F_ADD_RESIDUAL))
+    return fail(B200NORM_ERR_UNSUPPORTED, "the outer normalization has no fused residual add");
   if ((d->flags & B200NORM_F_OUT_DW) && !(d->flags & B200NORM_F_HAS_WEIGHT) && is_norm_bwd(d->op))
     return fail(B200NORM_ERR_BAD_ARG, "dweight requested without a weight (the builders return none)");
   return B200NORM_OK;
@@ -1064,16 +1069,17 @@ int b200norm_launch(const b200norm_desc* desc, const b200norm_tensor* inputs, in
         CHECK(bind_out_matrix(&rp.out1, &rp.out1_stride, "sum"));
       }
       if (ln) {
+        const int64_t nstat = is_outer(d) ? d.cols : d.rows;  // statistics per column when the reduction runs over dim 0
         if (d.flags & B200NORM_F_OUT_MEAN) {
           NEED_OUT(1);
           void* m = nullptr;
-          CHECK(bind_vec(outputs[oi++], d.rows, B200NORM_DT_F32, "mean", &m));
+          CHECK(bind_vec(outputs[oi++], nstat, B200NORM_DT_F32, "mean", &m));
           rp.stat0 = static_cast<float*>(m);
         }
         if (d.flags & B200NORM_F_OUT_INVSTD) {
           NEED_OUT(1);
           void* m = nullptr;
-          CHECK(bind_vec(outputs[oi++], d.rows, B200NORM_DT_F32, "invstd", &m));
+          CHECK(bind_vec(outputs[oi++], nstat, B200NORM_DT_F32, "invstd", &m));
           rp.stat1 = static_cast<float*>(m);
         }
       } else {
@@ -1220,6 +1226,10 @@ int b200norm_launch(const b200norm_desc* desc, const b200norm_tensor* inputs, in
     a.in0_stride = rp.in0_stride;
     a.in1_stride = rp.in1_stride;
     a.out_stride = rp.out_stride;
+    a.weight = rp.weight;
+    a.bias = rp.bias;
+    a.mean_out = rp.stat0;
+    a.invstd_out = rp.stat1;
     char msg[256] = "";
     rc = outer_launch(a, stream_v, msg, sizeof(msg));
     if (rc != B200NORM_OK) return fail(rc, "%s", msg);

@@ -115,6 +115,7 @@ std::vector<at::Tensor> NormExecutor::allocateOutputs(const std::vector<at::Tens
   const auto opts = first.options();
   const auto f32 = opts.dtype(at::kFloat);
   auto stat_shape = [&](const at::Tensor& x) {
+    if (f & B200NORM_F_OUTER) return std::vector<int64_t>{cols};  // one statistic per column (keepdim = false)
     std::vector<int64_t> s(x.sizes().begin(), x.sizes().end());
     s.back() = 1;
     return s;
@@ -196,8 +197,9 @@ std::vector<at::Tensor> NormExecutor::run(const std::vector<at::Tensor>& inputs,
     rows = (int64_t)outputs.size();
     cols = outputs[0].numel();
     dt = dtype_id(outputs[0].scalar_type());
-  } else if (spec_.flags & B200NORM_F_OUTER) {
-    // outer-persistent ops: the reduction runs over dim 0; everything behind it is the iteration domain
+  } else if ((spec_.flags & B200NORM_F_OUTER) && spec_.op != B200NORM_OP_LAYERNORM_FWD) {
+    // outer-persistent softmax: the reduction runs over dim 0; everything behind it is the iteration domain
+    // (the outer normalization reduces every axis but the last: the [.., C] -> [rows, C] view below)
     if (lead.dim() < 2) raise_msg(B200NORM_ERR_UNSUPPORTED, "an outer reduction needs a tensor of rank >= 2");
     rows = lead.size(0);
     cols = rows > 0 ? lead.numel() / rows : 0;

@@ -58,6 +58,13 @@ struct OuterParams {
   int32_t cluster;     // C
   int32_t depth;       // 1 or 2 tiles
   int32_t round_sum;
+  // outer normalization (statistics over dim 0, affine per column)
+  const void* weight;   // [N] io dtype or nullptr
+  const void* bias;     // [N] io dtype or nullptr
+  float* mean_out;      // [N] fp32 or nullptr
+  float* invstd_out;    // [N] fp32 or nullptr
+  float inv_m;          // 1 / M
+  float eps;
   int32_t two_exchanges;      // tuning (B200NORM_OUTER_TWO_EXCH=1): forward exchanges max and sum separately
   int32_t plain_stores;       // 1: default-policy st.global instead of the streaming (evict-first) form
   int32_t debug_skip_reduce;  // tuning aid (B200NORM_OUTER_SKIP_REDUCE): wrong results, timing only
@@ -244,7 +251,7 @@ __device__ __forceinline__ void col_reduce_softmax_pair(float (&m)[VEC], float (
       a.w += b.w;
     }
     const float4 mc = lds_f4(x.fin + c4);
-    const uint32_t set = x.nx & 1u, parity = (x.nx >> 1) & 1u;
+    const uint32_t set = x.nx & 1u;
     const uint32_t bar = x.xbar + 8u * set;
     if (x.tid == 0) mbar_arrive_expect_tx(bar, x.C * (uint32_t)x.SC * 8u);
     // slot layout of this exchange: [set][rank][max | sum][SC]
@@ -289,10 +296,17 @@ __device__ __forceinline__ void col_reduce_softmax_pair(float (&m)[VEC], float (
   }
 }
 
-template <typename T, bool BWD, bool LOG>
+// KIND: 0 softmax fwd, 1 log-softmax fwd, 2 softmax bwd, 3 log-softmax bwd, 4 normalization fwd
+// (mean / variance over dim 0, y = (x - mean) * invstd * weight[col] + bias[col]: the batch-norm-shaped
+// segment of benchmarks/python/normalization.py:13-95 with channels last, statistics by the two-pass form the
+// reference's persistent kernels use after TranslateApplicableWelford, fusion_segmenter.cpp:2341)
+template <typename T, int KIND>
 __global__ void __launch_bounds__(kOuterThreads, 3)
 outer_softmax_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
                      const OuterParams p) {
+  constexpr bool BWD = KIND == 2 || KIND == 3;
+  constexpr bool LOG = KIND == 1 || KIND == 3;
+  constexpr bool NORM = KIND == 4;
   constexpr int VEC = IO<T>::VEC;
   constexpr int H = VEC / 2;
   constexpr uint32_t kStep = kOuterThreads * 16;  // bytes between a thread's consecutive chunks
@@ -369,7 +383,100 @@ outer_softmax_kernel(const __grid_constant__ CUtensorMap map0, const __grid_cons
     const bool col_ok = col < p.N;
     uint8_t* o = static_cast<uint8_t*>(p.out) + (size_t)(row_base + r0) * out_row_bytes + (size_t)col * sizeof(T);
 
-    if constexpr (!BWD) {
+    if constexpr (NORM) {
+      // pass A: column sums -> mean
+      float s[VEC];
+      {
+        float2 s2[H];
+#pragma unroll
+        for (int k = 0; k < H; ++k) s2[k] = f2(0.f);
+        const uint8_t* t = t0;
+#pragma unroll 4
+        for (int j = 0; j < nj; ++j, t += kStep) {
+          float2 x[H];
+          IO<T>::unpack2(*reinterpret_cast<const uint4*>(t), x);
+#pragma unroll
+          for (int k = 0; k < H; ++k) s2[k] = f2add(s2[k], x[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < H; ++k) {
+          s[2 * k] = s2[k].x;
+          s[2 * k + 1] = s2[k].y;
+        }
+      }
+      col_reduce<SumOp, VEC>(s, cx);
+      float2 nmean[H];
+#pragma unroll
+      for (int k = 0; k < H; ++k) nmean[k] = make_float2(-s[2 * k] * p.inv_m, -s[2 * k + 1] * p.inv_m);
+      // pass B: centred sums of squares -> invstd
+      float q[VEC];
+      {
+        float2 q2[H];
+#pragma unroll
+        for (int k = 0; k < H; ++k) q2[k] = f2(0.f);
+        const uint8_t* t = t0;
+#pragma unroll 4
+        for (int j = 0; j < nj; ++j, t += kStep) {
+          float2 x[H];
+          IO<T>::unpack2(*reinterpret_cast<const uint4*>(t), x);
+#pragma unroll
+          for (int k = 0; k < H; ++k) {
+            const float2 d = f2add(x[k], nmean[k]);
+            q2[k] = f2fma(d, d, q2[k]);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < H; ++k) {
+          q[2 * k] = q2[k].x;
+          q[2 * k + 1] = q2[k].y;
+        }
+      }
+      col_reduce<SumOp, VEC>(q, cx);
+      float2 scale[H], shift[H];
+      float istd[VEC];
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) istd[k] = rsqrt_fast(fmaf(q[k], p.inv_m, p.eps));
+      if (col_ok) {
+        float2 w[H], b[H];
+        if (p.weight != nullptr) {
+          IO<T>::unpack2(ldg_128_nc(static_cast<const uint8_t*>(p.weight) + (size_t)col * sizeof(T)), w);
+        } else {
+#pragma unroll
+          for (int k = 0; k < H; ++k) w[k] = f2(1.f);
+        }
+        if (p.bias != nullptr) {
+          IO<T>::unpack2(ldg_128_nc(static_cast<const uint8_t*>(p.bias) + (size_t)col * sizeof(T)), b);
+        } else {
+#pragma unroll
+          for (int k = 0; k < H; ++k) b[k] = f2(0.f);
+        }
+#pragma unroll
+        for (int k = 0; k < H; ++k) {
+          scale[k] = f2mul(make_float2(istd[2 * k], istd[2 * k + 1]), w[k]);
+          shift[k] = b[k];
+        }
+        // per-column statistics: written once, by the threads that own row 0 of cluster rank 0
+        if (cx.crank == 0 && r0 == 0) {
+#pragma unroll
+          for (int k = 0; k < VEC; k += 4) {
+            if (p.mean_out != nullptr)
+              *reinterpret_cast<float4*>(p.mean_out + col + k) =
+                  make_float4(-nmean[k / 2].x, -nmean[k / 2].y, -nmean[k / 2 + 1].x, -nmean[k / 2 + 1].y);
+            if (p.invstd_out != nullptr)
+              *reinterpret_cast<float4*>(p.invstd_out + col + k) = make_float4(istd[k], istd[k + 1], istd[k + 2], istd[k + 3]);
+          }
+        }
+        const uint8_t* t = t0;
+#pragma unroll 2
+        for (int j = 0; j < nj; ++j, t += kStep, o += out_step) {
+          float2 x[H];
+          IO<T>::unpack2(*reinterpret_cast<const uint4*>(t), x);
+#pragma unroll
+          for (int k = 0; k < H; ++k) x[k] = f2fma(f2add(x[k], nmean[k]), scale[k], shift[k]);
+          stg_128_stream(o, IO<T>::pack2(x));
+        }
+      }
+    } else if constexpr (!BWD) {
       float m[VEC];
       if constexpr (sizeof(T) == 2) {
         uint4 mx = make_uint4(Max2<T>::kNegInf, Max2<T>::kNegInf, Max2<T>::kNegInf, Max2<T>::kNegInf);
@@ -555,15 +662,21 @@ int env_int_outer(const char* name) {
 using OuterKernel = void (*)(const CUtensorMap, const CUtensorMap, const OuterParams);
 
 template <typename T>
-OuterKernel outer_kernel_typed(bool bwd, bool log) {
-  if (bwd) return log ? outer_softmax_kernel<T, true, true> : outer_softmax_kernel<T, true, false>;
-  return log ? outer_softmax_kernel<T, false, true> : outer_softmax_kernel<T, false, false>;
+OuterKernel outer_kernel_typed(int kind) {
+  switch (kind) {
+    case 0: return outer_softmax_kernel<T, 0>;
+    case 1: return outer_softmax_kernel<T, 1>;
+    case 2: return outer_softmax_kernel<T, 2>;
+    case 3: return outer_softmax_kernel<T, 3>;
+    case 4: return outer_softmax_kernel<T, 4>;
+    default: return nullptr;
+  }
 }
-OuterKernel outer_kernel_for(int dt, bool bwd, bool log) {
+OuterKernel outer_kernel_for(int dt, int kind) {
   switch (dt) {
-    case B200NORM_DT_F32: return outer_kernel_typed<float>(bwd, log);
-    case B200NORM_DT_BF16: return outer_kernel_typed<__nv_bfloat16>(bwd, log);
-    case B200NORM_DT_F16: return outer_kernel_typed<__half>(bwd, log);
+    case B200NORM_DT_F32: return outer_kernel_typed<float>(kind);
+    case B200NORM_DT_BF16: return outer_kernel_typed<__nv_bfloat16>(kind);
+    case B200NORM_DT_F16: return outer_kernel_typed<__half>(kind);
     default: return nullptr;
   }
 }
@@ -603,15 +716,15 @@ Geometry geometry(const OuterArgs& a, int W, int C) {
 bool outer_make_plan(const OuterArgs& a, OuterPlan* plan, char* err, size_t errlen) {
   const int es = a.dtype == B200NORM_DT_F32 ? 4 : 2;
   if (a.M < 1 || a.N < 1) {
-    set_err(err, errlen, 0, "outer softmax: empty problem");
+    set_err(err, errlen, 0, "outer-persistent: empty problem");
     return false;
   }
   if ((a.N * es) % 16 != 0) {
-    set_err(err, errlen, 0, "outer softmax: N * sizeof(T) = %lld is not a multiple of 16", (long long)(a.N * es));
+    set_err(err, errlen, 0, "outer-persistent: N * sizeof(T) = %lld is not a multiple of 16", (long long)(a.N * es));
     return false;
   }
   if (a.M > (int64_t)1 << 24 || a.N > 0x7fffffffLL) {
-    set_err(err, errlen, 0, "outer softmax: extents out of range");
+    set_err(err, errlen, 0, "outer-persistent: extents out of range");
     return false;
   }
   const int64_t row_bytes = a.N * es;
@@ -663,7 +776,7 @@ bool outer_make_plan(const OuterArgs& a, OuterPlan* plan, char* err, size_t errl
   }
   if (W == 0) {
     set_err(err, errlen, 0,
-            "outer softmax: M = %lld does not fit the shared memory of a 16-CTA cluster (the reference segments "
+            "outer-persistent: M = %lld does not fit the shared memory of a 16-CTA cluster (the reference segments "
             "such fusions too)",
             (long long)a.M);
     return false;
@@ -795,11 +908,14 @@ int outer_launch(const OuterArgs& a, void* stream_v, char* err, size_t errlen) {
   auto aligned = [&](const void* ptr, int64_t stride) {
     return (reinterpret_cast<uintptr_t>(ptr) & 15u) == 0 && (a.M <= 1 || (stride * es) % 16 == 0);
   };
+  auto aligned_vec = [](const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15u) == 0; };
+  if (a.norm && (!aligned_vec(a.weight) || !aligned_vec(a.bias) || !aligned_vec(a.mean_out) || !aligned_vec(a.invstd_out)))
+    return set_err(err, errlen, B200NORM_ERR_UNSUPPORTED, "outer norm: weight / bias / statistics must be 16-byte aligned");
   if (!aligned(a.in0, a.in0_stride) || !aligned(a.out, a.out_stride) || (a.bwd && !aligned(a.in1, a.in1_stride)))
-    return set_err(err, errlen, B200NORM_ERR_UNSUPPORTED, "outer softmax: operands must be 16-byte aligned (base and row stride)");
+    return set_err(err, errlen, B200NORM_ERR_UNSUPPORTED, "outer-persistent: operands must be 16-byte aligned (base and row stride)");
 
-  OuterKernel k = outer_kernel_for(a.dtype, a.bwd != 0, a.log != 0);
-  if (k == nullptr) return set_err(err, errlen, B200NORM_ERR_UNSUPPORTED, "outer softmax: dtype %d", a.dtype);
+  OuterKernel k = outer_kernel_for(a.dtype, a.norm ? 4 : (a.bwd ? 2 : 0) + (a.log ? 1 : 0));
+  if (k == nullptr) return set_err(err, errlen, B200NORM_ERR_UNSUPPORTED, "outer-persistent: dtype %d", a.dtype);
   {
     static std::mutex mu;
     static std::unordered_map<const void*, std::pair<int, int>> done;
@@ -825,10 +941,10 @@ int outer_launch(const OuterArgs& a, void* stream_v, char* err, size_t errlen) {
   memset(&map0, 0, sizeof(map0));
   memset(&map1, 0, sizeof(map1));
   if (!make_map(&map0, a, a.in0, a.in0_stride, pl.slab_bytes, pl.box_rows))
-    return set_err(err, errlen, B200NORM_ERR_CUDA, "outer softmax: cuTensorMapEncodeTiled failed for input 0");
+    return set_err(err, errlen, B200NORM_ERR_CUDA, "outer-persistent: cuTensorMapEncodeTiled failed for input 0");
   if (a.bwd) {
     if (!make_map(&map1, a, a.in1, a.in1_stride, pl.slab_bytes, pl.box_rows))
-      return set_err(err, errlen, B200NORM_ERR_CUDA, "outer softmax: cuTensorMapEncodeTiled failed for input 1");
+      return set_err(err, errlen, B200NORM_ERR_CUDA, "outer-persistent: cuTensorMapEncodeTiled failed for input 1");
   } else {
     map1 = map0;
   }
@@ -850,6 +966,12 @@ int outer_launch(const OuterArgs& a, void* stream_v, char* err, size_t errlen) {
   p.cluster = pl.cluster;
   p.depth = pl.depth;
   p.round_sum = a.round_sum;
+  p.weight = a.weight;
+  p.bias = a.bias;
+  p.mean_out = a.mean_out;
+  p.invstd_out = a.invstd_out;
+  p.inv_m = (float)(1.0 / (double)a.M);
+  p.eps = (float)a.eps;
   p.debug_skip_reduce = env_int_outer("B200NORM_OUTER_SKIP_REDUCE");
   p.plain_stores = env_int_outer("B200NORM_OUTER_PLAIN_ST");
   p.two_exchanges = env_int_outer("B200NORM_OUTER_TWO_EXCH");

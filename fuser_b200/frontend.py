@@ -165,7 +165,11 @@ class FusionDefinition:
         want = set(m.outputs)
         if m.flags & L.F_ADD_RESIDUAL:  # norm(x + residual), optional sum output
             kw.update(residual=r["r"], want_sum="sum" in want, round_sum=bool(m.flags & L.F_ROUND_SUM))
-        if m.op == L.OP_LAYERNORM_FWD:
+        if m.op == L.OP_LAYERNORM_FWD and m.flags & L.F_OUTER:
+            o = K.outer_norm_fwd(r["x"], r.get("w"), r.get("b"), m.eps, want_mean="mean" in want,
+                                 want_invstd="invstd" in want, **kw)
+            res = {"y": o[0], "mean": o[1], "invstd": o[2]}
+        elif m.op == L.OP_LAYERNORM_FWD:
             o = K.layer_norm_fwd(r["x"], r.get("w"), r.get("b"), m.eps, want_mean="mean" in want,
                                  want_invstd="invstd" in want, **kw)
             res = {"y": o[0], "mean": o[1], "invstd": o[2], "sum": o[3] if len(o) > 3 else None}

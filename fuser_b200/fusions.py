@@ -189,6 +189,32 @@ def softmax_bwd_py(fd, dtype, reduction_axis=1):
     fd.add_output(T19)
 
 
+def batchnorm_fwd_py(fd, dtype, num_dims=4, eps=1e-5, momentum=0.01):
+    """benchmarks/python/normalization.py:13-95 for norm = "batch_norm", channels_last = True: training
+    statistics over every axis but the last, per-channel affine; the running statistics are fusion inputs
+    whose updates are computed but never added as outputs (dead code, exactly as in the reference)."""
+    cdim = num_dims - 1
+    mask = [i != cdim for i in range(num_dims)]
+    axes = [i for i in range(num_dims) if i != cdim]
+    x = fd.define_tensor(shape=[-1] * num_dims, contiguity=[True] * num_dims, dtype=dtype, is_cpu=False)
+    weight = fd.define_tensor(shape=[-1], contiguity=[True], dtype=dtype, is_cpu=False)
+    bias = fd.define_tensor(shape=[-1], contiguity=[True], dtype=dtype, is_cpu=False)
+    running_mean = fd.define_tensor(shape=[-1], contiguity=[True], dtype=DataType.Float, is_cpu=False)
+    running_var = fd.define_tensor(shape=[-1], contiguity=[True], dtype=DataType.Float, is_cpu=False)
+    x, weight, bias = _up(fd, x, dtype), _up(fd, weight, dtype), _up(fd, bias, dtype)
+    var, mean = fd.ops.var_mean(x, dims=axes, correction=0, keepdim=False)
+    invstd = fd.ops.rsqrt(fd.ops.add(var, fd.define_scalar(eps, dtype=DataType.Double)))
+    x_norm = fd.ops.mul(fd.ops.sub(x, fd.ops.broadcast(mean, mask)), fd.ops.broadcast(invstd, mask))
+    out = fd.ops.add(fd.ops.mul(x_norm, fd.ops.broadcast(weight, mask)), fd.ops.broadcast(bias, mask))
+    rev = fd.define_scalar(1 - momentum, dtype=DataType.Double)
+    mom = fd.define_scalar(momentum, dtype=DataType.Double)
+    fd.ops.add(fd.ops.mul(mom, mean), fd.ops.mul(rev, running_mean))  # updated_mean: not an output
+    fd.ops.add(fd.ops.mul(mom, var), fd.ops.mul(rev, running_var))    # updated_var: not an output
+    fd.add_output(_down(fd, out, dtype))
+    fd.add_output(mean)
+    fd.add_output(invstd)
+
+
 # ---- C++ builder spellings (csrc/ops/normalization.cpp) ----------------------------------------
 def layer_norm_cpp(fd, dtype, eps=1e-5, ndim=2, weight=True, bias=True):
     """layer_norm :304-342 via Welford; outputs (y, mean[..,1], invstd[..,1])"""

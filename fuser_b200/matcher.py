@@ -307,6 +307,20 @@ def def_layer_norm_fwd(ops, x, w, b, eps):
     return {"y": y, "mean": mean, "invstd": invstd}
 
 
+def def_outer_norm_fwd(ops, x, w, b, eps):
+    """benchmarks/python/normalization.py:13-95 (batch norm, training, channels last): statistics over every
+    axis but the last, affine per channel — an OuterPersistent segment."""
+    outer = list(range(x.ndim - 1))
+    var, mean = ops.var_mean(x, dims=outer, correction=0, keepdim=False)
+    invstd = ops.rsqrt(ops.add(var, eps))
+    y = ops.mul(ops.sub(x, _bcast_last(ops, mean, x)), _bcast_last(ops, invstd, x))
+    if w is not None:
+        y = ops.mul(y, _bcast_last(ops, w, x))
+    if b is not None:
+        y = ops.add(y, _bcast_last(ops, b, x))
+    return {"y": y, "mean": mean, "invstd": invstd}
+
+
 def def_rms_norm_fwd(ops, x, w, eps):
     """normalization.cpp:352-380 (+ the rms statistic of benchmarks/python/test_rmsnorm_fwd.py:26-45)"""
     last = [x.ndim - 1]
@@ -375,7 +389,17 @@ class Match:
 
 
 def _tensor_inputs(fd):
-    return [(i, v) for i, v in enumerate(fd._inputs) if isinstance(v, Tensor)]
+    """Tensor inputs that reach an output. An input whose consumers are all dead code (the running statistics of
+    benchmarks/python/normalization.py, whose updates are never added as outputs) is not part of the segment —
+    the reference's dead-code removal drops those expressions before segmentation."""
+    live, stack = set(), list(fd._outputs)
+    while stack:
+        v = stack.pop()
+        if v.id in live:
+            continue
+        live.add(v.id)
+        stack.extend(a for a in v.args if isinstance(a, Val))
+    return [(i, v) for i, v in enumerate(fd._inputs) if isinstance(v, Tensor) and v.id in live]
 
 
 def _eps_candidates(fd) -> list[float]:
@@ -542,6 +566,18 @@ def match_fusion(fd) -> Match:
                     if b:
                         roles["b"] = I(b)
                     return Match(L.OP_LAYERNORM_FWD, flags, eps, io, roles, names, description="layer_norm")
+                # statistics over the outer axes, affine per column: the batch-norm-shaped forward
+                names = try_candidate(
+                    lambda: def_outer_norm_fwd(ops, T(x), T(w) if w else None, T(b) if b else None, e), {})
+                if names and "y" in names:
+                    flags = L.F_OUTER | (L.F_HAS_WEIGHT if w else 0) | (L.F_HAS_BIAS if b else 0)
+                    roles = {"x": I(x)}
+                    if w:
+                        roles["w"] = I(w)
+                    if b:
+                        roles["b"] = I(b)
+                    return Match(L.OP_LAYERNORM_FWD, flags, eps, io, roles, names,
+                                 description="batch_norm forward (statistics over the outer axes, channels last)")
         raise Unmatchable("single-input fusion is not rms_norm / layer_norm / softmax")
 
     # ---- forward norms with a fused residual add: two matrix inputs, no statistics ----

@@ -122,6 +122,22 @@ def _softmax_axis_flags(t, dim: int) -> int:
     raise L.UnsupportedSegment(L.ERR_UNSUPPORTED, f"softmax over axis {dim} of a rank-{nd} tensor is not handled")
 
 
+def outer_norm_fwd(x, weight=None, bias=None, eps: float = 1e-5, *, want_mean=True, want_invstd=True,
+                   variant=L.VARIANT_AUTO, cluster_size=0):
+    """y, mean[N], invstd[N]: normalization with the statistics taken over dim 0 (everything behind it is the
+    iteration domain) and a per-column affine — the batch-norm-shaped forward in training mode with channels
+    last (benchmarks/python/normalization.py:13-95 viewed as [N*H*W, C]; an OuterPersistent segment in the
+    reference, scheduler/normalization_outer.cpp:451-683). Biased variance, invstd = rsqrt(var + eps)."""
+    flags = L.F_OUTER | (L.F_HAS_WEIGHT if weight is not None else 0) | (L.F_HAS_BIAS if bias is not None else 0)
+    flags |= (L.F_OUT_MEAN if want_mean else 0) | (L.F_OUT_INVSTD if want_invstd else 0)
+    ins = [x] + [t for t in (weight, bias) if t is not None]
+    outs = iter(_run(L.OP_LAYERNORM_FWD, flags, eps, variant, cluster_size, ins))
+    y = next(outs)
+    mean = next(outs) if want_mean else None
+    invstd = next(outs) if want_invstd else None
+    return y, mean, invstd
+
+
 def softmax_fwd(x, *, log=False, dim: int = -1, variant=L.VARIANT_AUTO, cluster_size=0):
     flags = _softmax_axis_flags(x, dim)
     (y,) = _run(L.OP_LOGSOFTMAX_FWD if log else L.OP_SOFTMAX_FWD, flags, 0.0, variant, cluster_size, [x])

@@ -139,7 +139,7 @@ enum {
    * rank order and casts. Publishes and combines pair up in order; at most two publishes may be
    * outstanding (two slots), the third waits in-kernel for the peers' "consumed" flags. */
   B200NORM_F_PEER_PUBLISH = 1u << 17,
-  /* SOFTMAX_* / LOGSOFTMAX_* only: the reduction runs over dim 0 (the ROWS) of the row-major [M,N]
+  /* SOFTMAX_* / LOGSOFTMAX_* and LAYERNORM_FWD: the reduction runs over dim 0 (the ROWS) of the row-major [M,N]
    * matrix instead of dim 1 — the segments nvFuser's OuterPersistent scheduler takes
    * (scheduler/normalization_outer.cpp:451-683; benchmarks/python/test_softmax_{fwd,bwd}.py with
    * reduction_axis = 0, pytest mark outer_persistent). desc.rows = M is then the reduced extent and
@@ -147,7 +147,11 @@ enum {
    * ops. Runs on the outer-persistent kernels (a column slab resident in the shared memory of a CTA
    * or of a cluster split along M); requires 16-byte aligned operands and N * sizeof(T) % 16 == 0,
    * and M small enough for a 16-CTA cluster (else B200NORM_ERR_UNSUPPORTED: the caller falls through,
-   * as the reference segments such fusions). */
+   * as the reference segments such fusions).
+   * LAYERNORM_FWD | OUTER is the batch-norm-shaped forward (training statistics, channels last:
+   * benchmarks/python/normalization.py:13-95 viewed as [N*H*W, C]): mean / biased variance per COLUMN
+   * over the M rows, y = (x - mean) * rsqrt(var + eps) * weight[col] + bias[col]; the mean / invstd
+   * outputs are fp32 [N]. No fused residual add. */
   B200NORM_F_OUTER = 1u << 18
 };
 

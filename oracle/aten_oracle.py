@@ -123,6 +123,24 @@ def layer_norm_fwd(x, weight, bias, eps: float):
     return y.to(io), mean_bcast, invstd
 
 
+def outer_norm_fwd(x, weight, bias, eps: float):
+    """Batch-norm-shaped forward, training statistics, channels last
+    (benchmarks/python/normalization.py:13-95 with channels_last=True, evaluated per Expr): var_mean over
+    every axis but the last (correction 0), invstd = rsqrt(var + eps), y = (x - mean) * invstd * w + b.
+    Returns y (io dtype), mean [C], invstd [C] (fp32)."""
+    io = x.dtype
+    xf = _up(x)
+    axes = list(range(xf.dim() - 1))
+    var, mean = torch.var_mean(xf, dim=axes, correction=0, keepdim=False)
+    invstd = torch.rsqrt(var + eps)
+    y = (xf - mean) * invstd
+    if weight is not None:
+        y = y * _up(weight)
+    if bias is not None:
+        y = y + _up(bias)
+    return y.to(io), mean, invstd
+
+
 def layer_norm_fwd_python(x, weight, bias, eps: float):
     """benchmarks/python/test_layernorm_fwd.py:14-54 (var_mean, correction=0)."""
     io = x.dtype

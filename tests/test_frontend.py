@@ -205,3 +205,33 @@ def test_outer_persistent_softmax_matches(dt):
     # the inner spellings keep matching without the flag
     assert not build(F.softmax_fwd_py, dt).segment().flags & L.F_OUTER
     assert not build(F.softmax_bwd_py, dt).segment().flags & L.F_OUTER
+
+
+@pytest.mark.parametrize("dt", [DataType.Float, DataType.BFloat16])
+@pytest.mark.parametrize("nd", [2, 4])
+def test_batchnorm_fwd_matches_as_outer_norm(dt, nd):
+    """benchmarks/python/normalization.py (batch norm, training, channels last): matched as the LayerNorm-type
+    forward with F_OUTER; the running-statistics inputs only feed dead code and are not part of the segment."""
+    import torch
+    from oracle import aten_oracle as AO
+    from oracle import fusion_eval
+
+    fd = build(F.batchnorm_fwd_py, dt, num_dims=nd)
+    m = fd.segment()
+    assert m.op == L.OP_LAYERNORM_FWD and m.flags & L.F_OUTER and m.flags & L.F_HAS_WEIGHT and m.flags & L.F_HAS_BIAS
+    assert m.outputs == ["y", "mean", "invstd"] and m.roles == {"x": 0, "w": 1, "b": 2} and m.eps == 1e-5
+    td = torch.float32 if dt == DataType.Float else torch.bfloat16
+    shape = [6, 5, 4, 16][4 - nd:]
+    x, w, b = torch.randn(*shape).to(td), torch.randn(16).to(td), torch.randn(16).to(td)
+    outs = fusion_eval.evaluate(fd, [x, w, b, torch.zeros(16), torch.ones(16)])
+    for got, want in zip(outs, AO.outer_norm_fwd(x, w, b, 1e-5)):
+        assert torch.equal(got, want)
+    # the oracle against the explicit ATen reference (training-mode native_batch_norm on the NCHW view)
+    if nd == 4:
+        yn, mn, inn = torch.native_batch_norm(x.float().permute(0, 3, 1, 2), w.float(), b.float(), None, None, True,
+                                               0.1, 1e-5)
+        ye, me, ie = AO.outer_norm_fwd(x, w, b, 1e-5)
+        assert torch.allclose(ye.float(), yn.permute(0, 2, 3, 1).to(td).float(), atol=2e-2 if td == torch.bfloat16 else 1e-5)
+        assert torch.allclose(me, mn, atol=1e-6) and torch.allclose(ie, inn, rtol=1e-5)
+    # the inner LayerNorm spelling is untouched
+    assert not build(F.layernorm_fwd_py, dt).segment().flags & L.F_OUTER

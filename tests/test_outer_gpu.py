@@ -214,3 +214,82 @@ def test_outer_full_size_properties():
         dx = ops.softmax_bwd(dy, sm, dim=0)
         scale = (sm.float() * dy.float()).abs().sum(0)
         assert (dx.float().sum(0).abs() / scale).max().item() < 2e-2
+
+
+def c_outer_norm_fwd(x, w, b, eps):
+    """fp64: statistics from the C oracle on the transpose (a column is a row of it), affine applied here."""
+    yh, mean, invstd = CO.layer_norm_fwd(x.t().contiguous(), None, None, eps)
+    y = yh.t()
+    if w is not None:
+        y = y * w.double()
+    if b is not None:
+        y = y + b.double()
+    return y, mean.view(-1), invstd.view(-1)
+
+
+@pytest.mark.parametrize("dt", DTYPES, ids=["bf16", "f32", "f16"])
+@pytest.mark.parametrize("shape", [(1, 64), (16, 768), (33, 1000), (216, 96), (512, 2048), (600, 136), (4100, 512)],
+                         ids=lambda s: f"{s[0]}x{s[1]}")
+def test_outer_norm_fwd(shape, dt):
+    """Normalization over dim 0 with a per-column affine (batch-norm-shaped forward, channels last)."""
+    m, n = shape
+    x, _, w, b = make_inputs(m, n, dt, seed=m * 17 + n)
+    eps = 1e-5
+    for ww, bb in ((w, b), (w, None), (None, None)):
+        y, mean, invstd = ops.outer_norm_fwd(x.cuda(), None if ww is None else ww.cuda(), None if bb is None else bb.cuda(), eps)
+        assert y.shape == (m, n) and mean.shape == (n,) and invstd.shape == (n,) and mean.dtype == torch.float32
+        ye, me, ie = AO.outer_norm_fwd(x, ww, bb, eps)
+        yc, mc, ic = c_outer_norm_fwd(x, ww, bb, eps)
+        fl = 1.0 if dt == torch.float32 else 1e-2
+        check(y, ye, yc, m, "outer norm y", fl)
+        check(mean, me, mc, m, "outer norm mean", 1.0)  # a sum with cancellation: absolute accuracy, as for the inner mean
+        check(invstd, ie, ic, m, "outer norm invstd", 1e-3)
+
+
+@pytest.mark.parametrize("cluster", [1, 2, 4, 8, 16])
+def test_outer_norm_cluster_split_and_batchnorm_pin(cluster):
+    """Every cluster size; the oracle itself is pinned to at::native_batch_norm (training statistics) on the
+    NHWC view, the explicit ATen reference the reference's batch-norm tests call."""
+    dt = torch.bfloat16
+    nb, h, wd, c = 6, 8, 16, 384  # [N,H,W,C] channels last -> [768, 384]
+    g = torch.Generator().manual_seed(cluster)
+    x4 = torch.randn(nb, h, wd, c, generator=g).to(dt)
+    w = torch.randn(c, generator=g).to(dt)
+    b = torch.randn(c, generator=g).to(dt)
+    eps = 1e-5
+    ye, me, ie = AO.outer_norm_fwd(x4, w, b, eps)
+    yn, mn, inn = torch.native_batch_norm(x4.float().permute(0, 3, 1, 2), w.float(), b.float(), None, None, True, 0.1, eps)
+    assert torch.allclose(ye.float(), yn.permute(0, 2, 3, 1).to(dt).float(), atol=2e-2, rtol=2e-2)
+    assert torch.allclose(me, mn, atol=1e-5) and torch.allclose(ie, inn, rtol=1e-4)
+    y, mean, invstd = ops.outer_norm_fwd(x4.cuda(), w.cuda(), b.cuda(), eps, cluster_size=cluster)
+    torch.cuda.synchronize()
+    assert y.shape == x4.shape
+    m = nb * h * wd
+    AO.assert_close(y, ye, m, f"outer norm 4-D, cluster {cluster}")
+    AO.assert_close(mean, me, m, "mean")
+    AO.assert_close(invstd, ie, m, "invstd")
+    yc, mc, ic = c_outer_norm_fwd(x4.view(m, c), w, b, eps)
+    assert ulp_err(y.view(m, c).cpu(), yc, floor=1e-2) <= TIGHT[dt]
+    assert ulp_err(mean.cpu(), mc, floor=1.0) <= 64 and ulp_err(invstd.cpu(), ic, floor=1e-3) <= 64
+
+
+@pytest.mark.parametrize("dt", [DataType.BFloat16, DataType.Float], ids=["bf16", "f32"])
+def test_batchnorm_fwd_frontend(dt):
+    """The reference's batch-norm forward definition (benchmarks/python/normalization.py, channels last) through
+    FusionDefinition: matched, executed on the outer-persistent kernel, validated against the node-by-node ATen
+    evaluation under the validator's tolerances; the unused running statistics are accepted as inputs."""
+    from oracle import fusion_eval
+
+    td = torch.bfloat16 if dt == DataType.BFloat16 else torch.float32
+    nb, h, wd, c = 8, 14, 14, 256
+    x = torch.randn(nb, h, wd, c).to(td).cuda()
+    w, b = torch.randn(c).to(td).cuda(), torch.randn(c).to(td).cuda()
+    rm, rv = torch.zeros(c, device="cuda"), torch.ones(c, device="cuda")
+    with FusionDefinition() as fd:
+        F.batchnorm_fwd_py(fd, dt, num_dims=4)
+    assert fd.segment().flags & L.F_OUTER
+    ins = [x, w, b, rm, rv]
+    y, mean, invstd = fd.validate(ins, fusion_eval.evaluate(fd, [t.cpu() for t in ins]))
+    assert y.shape == x.shape and mean.shape == (c,) and invstd.shape == (c,)
+    yn = torch.nn.functional.batch_norm(x.float().permute(0, 3, 1, 2), None, None, w.float(), b.float(), True, 0.1, 1e-5)
+    AO.assert_close(y, yn.permute(0, 2, 3, 1).to(td).cpu(), nb * h * wd, "batch norm vs eager")
