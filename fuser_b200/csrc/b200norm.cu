@@ -118,7 +118,9 @@ uint64_t algorithmic_bytes(const b200norm_desc& d) {
       if (d.op == B200NORM_OP_LAYERNORM_FWD) return s * 2 * (M * N + N) + 4 * 2 * M + extra;
       return s * (2 * M * N + N) + 4 * M + extra;
     }
-    case B200NORM_OP_LAYERNORM_BWD: return s * 3 * (M * N + N) + 4 * 2 * M;
+    case B200NORM_OP_LAYERNORM_BWD:
+      if (d.flags & B200NORM_F_OUTER) return s * 3 * (M * N + N) + 4 * 2 * N;
+      return s * 3 * (M * N + N) + 4 * 2 * M;
     case B200NORM_OP_RMSNORM_BWD: return s * (3 * M * N + 2 * N) + 4 * M;
     case B200NORM_OP_SOFTMAX_FWD:
     case B200NORM_OP_LOGSOFTMAX_FWD: return s * 2 * M * N;
@@ -570,12 +572,12 @@ int make_plan(const b200norm_desc& d, bool aligned, bool rows_contiguous, Plan* 
 OuterArgs outer_args_from(const b200norm_desc& d) {
   const DeviceInfo& dev = device_info();
   OuterArgs a;
-  a.bwd = (d.op == B200NORM_OP_SOFTMAX_BWD || d.op == B200NORM_OP_LOGSOFTMAX_BWD) ? 1 : 0;
+  a.bwd = (d.op == B200NORM_OP_SOFTMAX_BWD || d.op == B200NORM_OP_LOGSOFTMAX_BWD || d.op == B200NORM_OP_LAYERNORM_BWD) ? 1 : 0;
   a.log = (d.op == B200NORM_OP_LOGSOFTMAX_FWD || d.op == B200NORM_OP_LOGSOFTMAX_BWD) ? 1 : 0;
   a.dtype = d.io_dtype;
   a.M = d.rows;
   a.N = d.cols;
-  a.norm = d.op == B200NORM_OP_LAYERNORM_FWD ? 1 : 0;
+  a.norm = (d.op == B200NORM_OP_LAYERNORM_FWD || d.op == B200NORM_OP_LAYERNORM_BWD) ? 1 : 0;
   a.eps = d.eps;
   a.round_sum = (d.flags & B200NORM_F_ROUND_ROWSUM) ? 1 : 0;
   a.cluster_forced = d.cluster_size != 0 ? d.cluster_size : env_int("B200NORM_CLUSTER");
@@ -598,8 +600,12 @@ int check_desc(const b200norm_desc* d) {
       d->cluster_size != 8 && d->cluster_size != 16)
     return fail(B200NORM_ERR_BAD_ARG, "cluster_size must be 0,1,2,4,8,16");
   if (d->variant < 0 || d->variant > B200NORM_VARIANT_CLUSTER) return fail(B200NORM_ERR_BAD_ARG, "bad variant");
-  if ((d->flags & B200NORM_F_OUTER) && !is_softmax_op(d->op) && d->op != B200NORM_OP_LAYERNORM_FWD)
-    return fail(B200NORM_ERR_UNSUPPORTED, "B200NORM_F_OUTER applies to softmax / log-softmax and to the LayerNorm-type forward");
+  if ((d->flags & B200NORM_F_OUTER) && !is_softmax_op(d->op) && d->op != B200NORM_OP_LAYERNORM_FWD &&
+      d->op != B200NORM_OP_LAYERNORM_BWD)
+    return fail(B200NORM_ERR_UNSUPPORTED, "B200NORM_F_OUTER applies to softmax / log-softmax and to the LayerNorm-type ops");
+  if ((d->flags & B200NORM_F_OUTER) &&
+      (d->flags & (B200NORM_F_PARTIALS_F32 | B200NORM_F_PEER_REDUCE | B200NORM_F_PEER_PUBLISH)))
+    return fail(B200NORM_ERR_UNSUPPORTED, "the outer normalization backward produces dweight / dbias directly (no partial sums)");
   if ((d->flags & B200NORM_F_OUTER) && (d->flags & B200NORM_F_ADD_RESIDUAL))
     return fail(B200NORM_ERR_UNSUPPORTED, "the outer normalization has no fused residual add");
   if ((d->flags & B200NORM_F_OUT_DW) && !(d->flags & B200NORM_F_HAS_WEIGHT) && is_norm_bwd(d->op))
@@ -1096,14 +1102,15 @@ int b200norm_launch(const b200norm_desc* desc, const b200norm_tensor* inputs, in
       NEED_IN(2 + (ln ? 2 : 1) + (has_w ? 1 : 0));
       CHECK(bind_in_matrix(&rp.in0, &rp.in0_stride, "dy"));
       CHECK(bind_in_matrix(&rp.in1, &rp.in1_stride, "x"));
+      const int64_t nstat = is_outer(d) ? d.cols : d.rows;  // saved statistics per column when the reduction ran over dim 0
       if (ln) {
         void* m = nullptr;
-        CHECK(bind_vec(inputs[ii++], d.rows, B200NORM_DT_F32, "mean", &m));
+        CHECK(bind_vec(inputs[ii++], nstat, B200NORM_DT_F32, "mean", &m));
         rp.stat0 = static_cast<float*>(m);
       }
       {
         void* m = nullptr;
-        CHECK(bind_vec(inputs[ii++], d.rows, B200NORM_DT_F32, ln ? "invstd" : "stat", &m));
+        CHECK(bind_vec(inputs[ii++], nstat, B200NORM_DT_F32, ln ? "invstd" : "stat", &m));
         rp.stat1 = static_cast<float*>(m);
       }
       if (has_w) {
@@ -1228,8 +1235,15 @@ int b200norm_launch(const b200norm_desc* desc, const b200norm_tensor* inputs, in
     a.out_stride = rp.out_stride;
     a.weight = rp.weight;
     a.bias = rp.bias;
-    a.mean_out = rp.stat0;
-    a.invstd_out = rp.stat1;
+    if (d.op == B200NORM_OP_LAYERNORM_BWD) {
+      a.mean_in = rp.stat0;
+      a.invstd_in = rp.stat1;
+      a.dw_out = dw;
+      a.db_out = db;
+    } else {
+      a.mean_out = rp.stat0;
+      a.invstd_out = rp.stat1;
+    }
     char msg[256] = "";
     rc = outer_launch(a, stream_v, msg, sizeof(msg));
     if (rc != B200NORM_OK) return fail(rc, "%s", msg);

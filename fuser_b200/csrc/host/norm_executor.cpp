@@ -197,7 +197,8 @@ std::vector<at::Tensor> NormExecutor::run(const std::vector<at::Tensor>& inputs,
     rows = (int64_t)outputs.size();
     cols = outputs[0].numel();
     dt = dtype_id(outputs[0].scalar_type());
-  } else if ((spec_.flags & B200NORM_F_OUTER) && spec_.op != B200NORM_OP_LAYERNORM_FWD) {
+  } else if ((spec_.flags & B200NORM_F_OUTER) && spec_.op != B200NORM_OP_LAYERNORM_FWD &&
+             spec_.op != B200NORM_OP_LAYERNORM_BWD) {
     // outer-persistent softmax: the reduction runs over dim 0; everything behind it is the iteration domain
     // (the outer normalization reduces every axis but the last: the [.., C] -> [rows, C] view below)
     if (lead.dim() < 2) raise_msg(B200NORM_ERR_UNSUPPORTED, "an outer reduction needs a tensor of rank >= 2");

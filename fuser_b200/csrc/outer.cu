@@ -63,9 +63,14 @@ struct OuterParams {
   const void* bias;     // [N] io dtype or nullptr
   float* mean_out;      // [N] fp32 or nullptr
   float* invstd_out;    // [N] fp32 or nullptr
+  const float* mean_in;    // normalization backward: saved statistics [N] fp32
+  const float* invstd_in;
+  void* dw_out;            // [N] io dtype or nullptr
+  void* db_out;            // [N] io dtype or nullptr
   float inv_m;          // 1 / M
   float eps;
   int32_t two_exchanges;      // tuning (B200NORM_OUTER_TWO_EXCH=1): forward exchanges max and sum separately
+  int32_t l2_prefetch;        // 1: prefetch the next slab's boxes into L2 at the start of an iteration
   int32_t plain_stores;       // 1: default-policy st.global instead of the streaming (evict-first) form
   int32_t debug_skip_reduce;  // tuning aid (B200NORM_OUTER_SKIP_REDUCE): wrong results, timing only
   uint32_t slab_bytes; // W
@@ -79,6 +84,10 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
       ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
       : "memory");
+}
+// L2 prefetch of a box (no shared memory, no completion to wait for)
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
   asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
@@ -211,6 +220,78 @@ __device__ __forceinline__ void col_reduce(float (&v)[VEC], ColCtx& x) {
   }
 }
 
+// Two sums per column in one go (the normalization backward's grad_sum and dot_p): one pair of local barriers and
+// ONE cluster exchange instead of two. Planes: wpart [warps][2][SC], slots [set][rank][2][SC], fin planes 0 and 1.
+template <int VEC>
+__device__ __forceinline__ void col_reduce_sum2(float (&u)[VEC], float (&v)[VEC], ColCtx& x) {
+  for (int off = 16; off >= x.LC; off >>= 1) {
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      u[k] += __shfl_xor_sync(0xffffffffu, u[k], off);
+      v[k] += __shfl_xor_sync(0xffffffffu, v[k], off);
+    }
+  }
+  if (x.lane < x.LC) {
+    float* dst = x.wpart + x.warp * 2 * x.SC + x.c * VEC;
+#pragma unroll
+    for (int k = 0; k < VEC; k += 4) {
+      *reinterpret_cast<float4*>(dst + k) = make_float4(u[k], u[k + 1], u[k + 2], u[k + 3]);
+      *reinterpret_cast<float4*>(dst + x.SC + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+    }
+  }
+  __syncthreads();
+  if (x.tid < (x.SC >> 1)) {  // SC / 4 threads per plane
+    const int plane = x.tid >= (x.SC >> 2) ? 1 : 0;
+    const int c4 = (x.tid - plane * (x.SC >> 2)) << 2;
+    const float* src = x.wpart + plane * x.SC + c4;
+    float4 a = lds_f4(src);
+#pragma unroll
+    for (int w = 1; w < kOuterWarps; ++w) {
+      const float4 b = lds_f4(src + w * 2 * x.SC);
+      a.x += b.x;
+      a.y += b.y;
+      a.z += b.z;
+      a.w += b.w;
+    }
+    if (x.C > 1) {
+      const uint32_t set = x.nx & 1u, parity = (x.nx >> 1) & 1u;
+      const uint32_t bar = x.xbar + 8u * set;
+      if (x.tid == 0) mbar_arrive_expect_tx(bar, x.C * (uint32_t)x.SC * 8u);
+      const uint32_t local =
+          x.smem0 + x.off_cls + ((((set * x.C + x.crank) * 2u) + (uint32_t)plane) * (uint32_t)x.SC + (uint32_t)c4) * 4u;
+      for (uint32_t q = 0; q < x.C; ++q) st_async_f32x4(map_to_cta(local, q), a, map_to_cta(bar, q));
+      mbar_wait(bar, parity);
+      const volatile float* base = x.cls + ((size_t)set * x.C * 2 + plane) * x.SC + c4;
+      a.x = base[0];
+      a.y = base[1];
+      a.z = base[2];
+      a.w = base[3];
+      for (uint32_t q = 1; q < x.C; ++q) {
+        a.x += base[(size_t)q * 2 * x.SC];
+        a.y += base[(size_t)q * 2 * x.SC + 1];
+        a.z += base[(size_t)q * 2 * x.SC + 2];
+        a.w += base[(size_t)q * 2 * x.SC + 3];
+      }
+    }
+    *reinterpret_cast<float4*>(x.fin + plane * x.SC + c4) = a;
+  }
+  if (x.C > 1) ++x.nx;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < VEC; k += 4) {
+    const float4 t = lds_f4(x.fin + x.c * VEC + k);
+    const float4 w = lds_f4(x.fin + x.SC + x.c * VEC + k);
+    u[k] = t.x;
+    u[k + 1] = t.y;
+    u[k + 2] = t.z;
+    u[k + 3] = t.w;
+    v[k] = w.x;
+    v[k + 1] = w.y;
+    v[k + 2] = w.z;
+    v[k + 3] = w.w;
+  }
+}
+
 // Softmax forward over a cluster: ONE exchange per slab instead of two. Every CTA reduces its own rows
 // completely — max (local col_reduce, result in fin), then the sum of exp(x - CTA max) — and the cluster
 // exchanges (max, sum) PAIRS: M = max_q m_q, S = sum_q s_q * exp(m_q - M). The cluster is a lock-step on
@@ -296,7 +377,10 @@ __device__ __forceinline__ void col_reduce_softmax_pair(float (&m)[VEC], float (
   }
 }
 
-// KIND: 0 softmax fwd, 1 log-softmax fwd, 2 softmax bwd, 3 log-softmax bwd, 4 normalization fwd
+// KIND: 0 softmax fwd, 1 log-softmax fwd, 2 softmax bwd, 3 log-softmax bwd, 4 normalization fwd,
+// 5 normalization bwd (in0 = dy, in1 = x; benchmarks/python/normalization.py:98-190: grad_sum = sum(dy),
+// dot_p = sum(dy * (x - mean)) over dim 0; dx = (dy - dot_p/M * invstd^2 * (x - mean) - grad_sum/M) * w * invstd;
+// dweight = dot_p * invstd; dbias = grad_sum)
 // (mean / variance over dim 0, y = (x - mean) * invstd * weight[col] + bias[col]: the batch-norm-shaped
 // segment of benchmarks/python/normalization.py:13-95 with channels last, statistics by the two-pass form the
 // reference's persistent kernels use after TranslateApplicableWelford, fusion_segmenter.cpp:2341)
@@ -304,9 +388,10 @@ template <typename T, int KIND>
 __global__ void __launch_bounds__(kOuterThreads, 3)
 outer_softmax_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
                      const OuterParams p) {
-  constexpr bool BWD = KIND == 2 || KIND == 3;
+  constexpr bool BWD = KIND == 2 || KIND == 3 || KIND == 5;  // two streamed inputs
   constexpr bool LOG = KIND == 1 || KIND == 3;
   constexpr bool NORM = KIND == 4;
+  constexpr bool NORM_BWD = KIND == 5;
   constexpr int VEC = IO<T>::VEC;
   constexpr int H = VEC / 2;
   constexpr uint32_t kStep = kOuterThreads * 16;  // bytes between a thread's consecutive chunks
@@ -376,14 +461,127 @@ outer_softmax_kernel(const __grid_constant__ CUtensorMap map0, const __grid_cons
     const int next = slab + nclusters;
     // the other tile was released by the __syncthreads that ended the previous iteration
     if (p.depth == 2 && next < p.nslabs && tid == 0) issue(next, buf ^ 1u);
-    mbar_wait(bar0 + 8u * buf, phase);
-
+    // Experiment (B200NORM_OUTER_L2PF=1, off by default): with one tile per CTA the next slab cannot land in
+    // shared memory before this one is done, but it can be pulled into L2 now (444 CTAs x 64 KB = 28 MB ahead).
+    // Measured neutral (+-2 %) to -8 %: the tile wait is not what limits these kernels.
+    if (p.depth == 1 && p.l2_prefetch && next < p.nslabs && tid == 0) {
+      const int32_t ncol = next * p.slab_cols;
+      for (int b = 0; b < p.nboxes; ++b) {
+        tma_prefetch_2d(&map0, ncol, row_base + b * p.box_rows);
+        if constexpr (BWD) tma_prefetch_2d(&map1, ncol, row_base + b * p.box_rows);
+      }
+    }
     const uint8_t* t0 = outer_smem + p.off_tiles + buf * p.stage_bytes + (uint32_t)tid * 16u;
     const int col = slab * p.slab_cols + cx.c * VEC;
     const bool col_ok = col < p.N;
     uint8_t* o = static_cast<uint8_t*>(p.out) + (size_t)(row_base + r0) * out_row_bytes + (size_t)col * sizeof(T);
+    // per-column parameters of the normalization ops: requested BEFORE the wait for the tile, so that their
+    // global-memory latency hides behind it (after the wait it sat on every slab's critical path)
+    uint4 wq = make_uint4(0, 0, 0, 0), bq = wq;
+    float4 mq[VEC / 4], iq[VEC / 4];
+    if constexpr (NORM || NORM_BWD) {
+      if (col_ok && p.weight != nullptr) wq = ldg_128_nc(static_cast<const uint8_t*>(p.weight) + (size_t)col * sizeof(T));
+      if (NORM && col_ok && p.bias != nullptr) bq = ldg_128_nc(static_cast<const uint8_t*>(p.bias) + (size_t)col * sizeof(T));
+    }
+    if constexpr (NORM_BWD) {
+#pragma unroll
+      for (int k = 0; k < VEC / 4; ++k) {
+        mq[k] = iq[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (col_ok) {
+          mq[k] = *reinterpret_cast<const float4*>(p.mean_in + col + 4 * k);
+          iq[k] = *reinterpret_cast<const float4*>(p.invstd_in + col + 4 * k);
+        }
+      }
+    }
+    mbar_wait(bar0 + 8u * buf, phase);
 
-    if constexpr (NORM) {
+    if constexpr (NORM_BWD) {
+      float2 nmean[H];
+      float istd[VEC];
+      {
+        float mv[VEC];
+#pragma unroll
+        for (int k = 0; k < VEC; k += 4) {
+          const float4 a = mq[k / 4], b = iq[k / 4];
+          mv[k] = a.x; mv[k + 1] = a.y; mv[k + 2] = a.z; mv[k + 3] = a.w;
+          istd[k] = b.x; istd[k + 1] = b.y; istd[k + 2] = b.z; istd[k + 3] = b.w;
+        }
+#pragma unroll
+        for (int k = 0; k < H; ++k) nmean[k] = make_float2(-mv[2 * k], -mv[2 * k + 1]);
+      }
+      // pass A: grad_sum and dot_p
+      float gs[VEC], dp[VEC];
+      {
+        float2 g2[H], d2[H];
+#pragma unroll
+        for (int k = 0; k < H; ++k) g2[k] = d2[k] = f2(0.f);
+        const uint8_t* t = t0;
+#pragma unroll 4
+        for (int j = 0; j < nj; ++j, t += kStep) {
+          float2 dy[H], x[H];
+          IO<T>::unpack2(*reinterpret_cast<const uint4*>(t), dy);
+          IO<T>::unpack2(*reinterpret_cast<const uint4*>(t + p.tile_bytes), x);
+#pragma unroll
+          for (int k = 0; k < H; ++k) {
+            g2[k] = f2add(g2[k], dy[k]);
+            d2[k] = f2fma(dy[k], f2add(x[k], nmean[k]), d2[k]);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < H; ++k) {
+          gs[2 * k] = g2[k].x; gs[2 * k + 1] = g2[k].y;
+          dp[2 * k] = d2[k].x; dp[2 * k + 1] = d2[k].y;
+        }
+      }
+      col_reduce_sum2<VEC>(gs, dp, cx);
+      if (col_ok) {
+        float2 w[H], nps[H], ngm[H], gsc[H];
+        if (p.weight != nullptr) {
+          IO<T>::unpack2(wq, w);
+        } else {
+#pragma unroll
+          for (int k = 0; k < H; ++k) w[k] = f2(1.f);
+        }
+#pragma unroll
+        for (int k = 0; k < H; ++k) {
+          const float2 is2 = make_float2(istd[2 * k], istd[2 * k + 1]);
+          const float2 dpn = make_float2(dp[2 * k] * p.inv_m, dp[2 * k + 1] * p.inv_m);
+          nps[k] = f2mul(f2mul(dpn, f2mul(is2, is2)), f2(-1.f));            // -(dot_p / M) * invstd^2
+          ngm[k] = make_float2(-gs[2 * k] * p.inv_m, -gs[2 * k + 1] * p.inv_m);  // -grad_sum / M
+          gsc[k] = f2mul(w[k], is2);                                         // weight * invstd
+        }
+        if (cx.crank == 0 && r0 == 0) {
+          if (p.dw_out != nullptr) {
+            float2 dw[H];
+#pragma unroll
+            for (int k = 0; k < H; ++k) dw[k] = make_float2(dp[2 * k] * istd[2 * k], dp[2 * k + 1] * istd[2 * k + 1]);
+            *reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.dw_out) + (size_t)col * sizeof(T)) = IO<T>::pack2(dw);
+          }
+          if (p.db_out != nullptr) {
+            float2 db[H];
+#pragma unroll
+            for (int k = 0; k < H; ++k) db[k] = make_float2(gs[2 * k], gs[2 * k + 1]);
+            *reinterpret_cast<uint4*>(static_cast<uint8_t*>(p.db_out) + (size_t)col * sizeof(T)) = IO<T>::pack2(db);
+          }
+        }
+        if (p.out != nullptr) {
+          const uint8_t* t = t0;
+#pragma unroll 2
+          for (int j = 0; j < nj; ++j, t += kStep, o += out_step) {
+            float2 dy[H], x[H];
+            IO<T>::unpack2(*reinterpret_cast<const uint4*>(t), dy);
+            IO<T>::unpack2(*reinterpret_cast<const uint4*>(t + p.tile_bytes), x);
+#pragma unroll
+            for (int k = 0; k < H; ++k) {
+              // ((dy - proj) - grad_mean) * grad_scale, proj = proj_scale * (x - mean)
+              const float2 xc = f2add(x[k], nmean[k]);
+              dy[k] = f2mul(f2add(f2fma(nps[k], xc, dy[k]), ngm[k]), gsc[k]);
+            }
+            stg_128_stream(o, IO<T>::pack2(dy));
+          }
+        }
+      }
+    } else if constexpr (NORM) {
       // pass A: column sums -> mean
       float s[VEC];
       {
@@ -439,13 +637,13 @@ outer_softmax_kernel(const __grid_constant__ CUtensorMap map0, const __grid_cons
       if (col_ok) {
         float2 w[H], b[H];
         if (p.weight != nullptr) {
-          IO<T>::unpack2(ldg_128_nc(static_cast<const uint8_t*>(p.weight) + (size_t)col * sizeof(T)), w);
+          IO<T>::unpack2(wq, w);
         } else {
 #pragma unroll
           for (int k = 0; k < H; ++k) w[k] = f2(1.f);
         }
         if (p.bias != nullptr) {
-          IO<T>::unpack2(ldg_128_nc(static_cast<const uint8_t*>(p.bias) + (size_t)col * sizeof(T)), b);
+          IO<T>::unpack2(bq, b);
         } else {
 #pragma unroll
           for (int k = 0; k < H; ++k) b[k] = f2(0.f);
@@ -669,6 +867,7 @@ OuterKernel outer_kernel_typed(int kind) {
     case 2: return outer_softmax_kernel<T, 2>;
     case 3: return outer_softmax_kernel<T, 3>;
     case 4: return outer_softmax_kernel<T, 4>;
+    case 5: return outer_softmax_kernel<T, 5>;
     default: return nullptr;
   }
 }
@@ -707,7 +906,7 @@ Geometry geometry(const OuterArgs& a, int W, int C) {
   g.tile = (uint32_t)g.rows_cta * (uint32_t)W;
   g.stage = (uint32_t)ns * g.tile;
   const uint32_t sc = (uint32_t)(W / es);
-  g.overhead = up(128 + kOuterWarps * sc * 4 + (C > 1 ? 4u * (uint32_t)C * sc * 4 : 0u) + 3 * sc * 4, 128);
+  g.overhead = up(128 + 2 * kOuterWarps * sc * 4 + (C > 1 ? 4u * (uint32_t)C * sc * 4 : 0u) + 3 * sc * 4, 128);
   return g;
 }
 
@@ -797,7 +996,7 @@ bool outer_make_plan(const OuterArgs& a, OuterPlan* plan, char* err, size_t errl
   const uint32_t sc = (uint32_t)(W / es);
   uint32_t off = 128;
   p.off_wpart = off;
-  off += kOuterWarps * sc * 4;
+  off += 2 * kOuterWarps * sc * 4;  // two planes (col_reduce_sum2)
   p.off_cls = off;
   if (C > 1) off += 4u * (uint32_t)C * sc * 4;  // two slot sets of [C][max | sum][SC]
   p.off_fin = off;
@@ -909,12 +1108,13 @@ int outer_launch(const OuterArgs& a, void* stream_v, char* err, size_t errlen) {
     return (reinterpret_cast<uintptr_t>(ptr) & 15u) == 0 && (a.M <= 1 || (stride * es) % 16 == 0);
   };
   auto aligned_vec = [](const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15u) == 0; };
-  if (a.norm && (!aligned_vec(a.weight) || !aligned_vec(a.bias) || !aligned_vec(a.mean_out) || !aligned_vec(a.invstd_out)))
+  if (a.norm && (!aligned_vec(a.weight) || !aligned_vec(a.bias) || !aligned_vec(a.mean_out) || !aligned_vec(a.invstd_out) ||
+                 !aligned_vec(a.mean_in) || !aligned_vec(a.invstd_in) || !aligned_vec(a.dw_out) || !aligned_vec(a.db_out)))
     return set_err(err, errlen, B200NORM_ERR_UNSUPPORTED, "outer norm: weight / bias / statistics must be 16-byte aligned");
-  if (!aligned(a.in0, a.in0_stride) || !aligned(a.out, a.out_stride) || (a.bwd && !aligned(a.in1, a.in1_stride)))
+  if (!aligned(a.in0, a.in0_stride) || (a.out != nullptr && !aligned(a.out, a.out_stride)) || (a.bwd && !aligned(a.in1, a.in1_stride)))
     return set_err(err, errlen, B200NORM_ERR_UNSUPPORTED, "outer-persistent: operands must be 16-byte aligned (base and row stride)");
 
-  OuterKernel k = outer_kernel_for(a.dtype, a.norm ? 4 : (a.bwd ? 2 : 0) + (a.log ? 1 : 0));
+  OuterKernel k = outer_kernel_for(a.dtype, a.norm ? (a.bwd ? 5 : 4) : (a.bwd ? 2 : 0) + (a.log ? 1 : 0));
   if (k == nullptr) return set_err(err, errlen, B200NORM_ERR_UNSUPPORTED, "outer-persistent: dtype %d", a.dtype);
   {
     static std::mutex mu;
@@ -970,10 +1170,15 @@ int outer_launch(const OuterArgs& a, void* stream_v, char* err, size_t errlen) {
   p.bias = a.bias;
   p.mean_out = a.mean_out;
   p.invstd_out = a.invstd_out;
+  p.mean_in = a.mean_in;
+  p.invstd_in = a.invstd_in;
+  p.dw_out = a.dw_out;
+  p.db_out = a.db_out;
   p.inv_m = (float)(1.0 / (double)a.M);
   p.eps = (float)a.eps;
   p.debug_skip_reduce = env_int_outer("B200NORM_OUTER_SKIP_REDUCE");
   p.plain_stores = env_int_outer("B200NORM_OUTER_PLAIN_ST");
+  p.l2_prefetch = env_int_outer("B200NORM_OUTER_L2PF") != 0;  // measured neutral to -8 %: off by default
   p.two_exchanges = env_int_outer("B200NORM_OUTER_TWO_EXCH");
   p.slab_bytes = (uint32_t)pl.slab_bytes;
   p.tile_bytes = pl.tile_bytes;

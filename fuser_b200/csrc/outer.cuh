@@ -25,11 +25,16 @@ struct OuterArgs {
   const void* in1 = nullptr;
   void* out = nullptr;
   int64_t in0_stride = 0, in1_stride = 0, out_stride = 0;  // row strides in elements
-  int norm = 0;       // 1: normalization forward (statistics over dim 0, affine per column); bwd = log = 0
+  int norm = 0;       // 1: normalization (statistics over dim 0, affine per column): forward, or backward with bwd = 1
+                      // (in0 = dy, in1 = x, saved statistics in, dx / dweight / dbias out)
   const void* weight = nullptr;  // [N] io dtype
   const void* bias = nullptr;    // [N] io dtype
   float* mean_out = nullptr;     // [N] fp32
   float* invstd_out = nullptr;   // [N] fp32
+  const float* mean_in = nullptr;    // backward: saved mean [N] fp32
+  const float* invstd_in = nullptr;  // backward: saved invstd [N] fp32
+  void* dw_out = nullptr;            // backward: [N] io dtype
+  void* db_out = nullptr;            // backward: [N] io dtype
   double eps = 0.0;
   int round_sum = 0;       // backward: round the column sum through the io dtype (B200NORM_F_ROUND_ROWSUM)
   int cluster_forced = 0;  // 0 = planner's choice, else 1,2,4,8,16

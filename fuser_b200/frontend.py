@@ -182,6 +182,10 @@ class FusionDefinition:
             res = {"dx": K.softmax_bwd(r["dy"], r["y"], log=m.op == L.OP_LOGSOFTMAX_BWD,
                                        round_rowsum=bool(m.flags & L.F_ROUND_ROWSUM),
                                        dim=0 if m.flags & L.F_OUTER else -1, **kw)}
+        elif m.op == L.OP_LAYERNORM_BWD and m.flags & L.F_OUTER:
+            mask = ("dx" in want, "dw" in want, "db" in want)
+            dx, dw, db = K.outer_norm_bwd(r["dy"], r["x"], r["mean"], r["stat"], r.get("w"), mask, **kw)
+            res = {"dx": dx, "dw": dw, "db": db}
         elif m.op == L.OP_LAYERNORM_BWD:
             mask = ("dx" in want, "dw" in want, "db" in want)
             dx, dw, db = K.layer_norm_bwd(r["dy"], r["x"], r["mean"], r["stat"], r.get("w"), mask, **kw)

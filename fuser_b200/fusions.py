@@ -215,6 +215,38 @@ def batchnorm_fwd_py(fd, dtype, num_dims=4, eps=1e-5, momentum=0.01):
     fd.add_output(invstd)
 
 
+def batchnorm_bwd_py(fd, dtype, num_dims=4):
+    """benchmarks/python/normalization.py:98-190 for norm = "batch_norm", channels_last = True; inputs
+    (input, grad, weight, running_mean, running_var, mean, invstd) — the running statistics are unused."""
+    from functools import reduce
+
+    cdim = num_dims - 1
+    mask = [i != cdim for i in range(num_dims)]
+    axes = [i for i in range(num_dims) if i != cdim]
+    x = fd.define_tensor(shape=[-1] * num_dims, contiguity=[True] * num_dims, dtype=dtype, is_cpu=False)
+    grad = fd.define_tensor(shape=[-1] * num_dims, contiguity=[True] * num_dims, dtype=dtype, is_cpu=False)
+    weight = fd.define_tensor(shape=[-1], contiguity=[True], dtype=dtype, is_cpu=False)
+    fd.define_tensor(shape=[-1], contiguity=[True], dtype=DataType.Float, is_cpu=False)  # running_mean
+    fd.define_tensor(shape=[-1], contiguity=[True], dtype=DataType.Float, is_cpu=False)  # running_var
+    mean = fd.define_tensor(shape=[-1], contiguity=[True], dtype=DataType.Float, is_cpu=False)
+    invstd = fd.define_tensor(shape=[-1], contiguity=[True], dtype=DataType.Float, is_cpu=False)
+    x, grad, weight = _up(fd, x, dtype), _up(fd, grad, dtype), _up(fd, weight, dtype)
+    norm = fd.ops.reciprocal(reduce(fd.ops.mul, [x.size(ax) for ax in axes], 1))
+    mean_b = fd.ops.broadcast(mean, mask)
+    grad_sum = fd.ops.sum(grad, dims=axes, keepdim=False)
+    x_sub_mean = fd.ops.sub(x, mean_b)
+    dot_p = fd.ops.sum(fd.ops.mul(grad, x_sub_mean), dims=axes, keepdim=False)
+    grad_mean = fd.ops.broadcast(fd.ops.mul(grad_sum, norm), mask)
+    proj_scale = fd.ops.broadcast(fd.ops.mul(fd.ops.mul(dot_p, norm), fd.ops.mul(invstd, invstd)), mask)
+    grad_scale = fd.ops.mul(fd.ops.broadcast(weight, mask), fd.ops.broadcast(invstd, mask))
+    proj = fd.ops.mul(proj_scale, x_sub_mean)
+    grad_input = fd.ops.mul(fd.ops.sub(fd.ops.sub(grad, proj), grad_mean), grad_scale)
+    grad_weight = fd.ops.mul(dot_p, invstd)
+    fd.add_output(_down(fd, grad_input, dtype))
+    fd.add_output(_down(fd, grad_weight, dtype))
+    fd.add_output(_down(fd, grad_sum, dtype))
+
+
 # ---- C++ builder spellings (csrc/ops/normalization.cpp) ----------------------------------------
 def layer_norm_cpp(fd, dtype, eps=1e-5, ndim=2, weight=True, bias=True):
     """layer_norm :304-342 via Welford; outputs (y, mean[..,1], invstd[..,1])"""

@@ -321,6 +321,25 @@ def def_outer_norm_fwd(ops, x, w, b, eps):
     return {"y": y, "mean": mean, "invstd": invstd}
 
 
+def def_outer_norm_bwd(ops, dy, x, mean, invstd, w):
+    """benchmarks/python/normalization.py:98-190 (batch norm backward, training, channels last)."""
+    outer = list(range(x.ndim - 1))
+    num = x.size(0)
+    for ax in outer[1:]:
+        num = ops.mul(num, x.size(ax))
+    norm = ops.reciprocal(num)
+    xc = ops.sub(x, _bcast_last(ops, mean, x))
+    grad_sum = ops.sum(dy, dims=outer, keepdim=False)
+    dot_p = ops.sum(ops.mul(dy, xc), dims=outer, keepdim=False)
+    grad_mean = _bcast_last(ops, ops.mul(grad_sum, norm), x)
+    proj_scale = _bcast_last(ops, ops.mul(ops.mul(dot_p, norm), ops.mul(invstd, invstd)), x)
+    grad_scale = _bcast_last(ops, invstd, x)
+    if w is not None:
+        grad_scale = ops.mul(_bcast_last(ops, w, x), grad_scale)
+    dx = ops.mul(ops.sub(ops.sub(dy, ops.mul(proj_scale, xc)), grad_mean), grad_scale)
+    return {"dx": dx, "dw": ops.mul(dot_p, invstd), "db": grad_sum}
+
+
 def def_rms_norm_fwd(ops, x, w, eps):
     """normalization.cpp:352-380 (+ the rms statistic of benchmarks/python/test_rmsnorm_fwd.py:26-45)"""
     last = [x.ndim - 1]
@@ -473,10 +492,15 @@ def match_fusion(fd) -> Match:
         raise Unmatchable("square symbolic shapes: rows and cols were unified")
     mats = [(i, t) for i, t in mats if t.ndim == nd and tuple(cls(d) for d in t.dims) == row_cls + (col_cls,)]
     vecs = [(i, t) for i, t in tin if t.ndim == 1 and cls(t.dims[0]) == col_cls]
+    io0 = mats[0][1].dtype
+    # fp32 per-COLUMN statistics next to reduced-precision activations (saved mean / invstd of the outer
+    # normalization backward); with fp32 io they cannot be told from weights here and stay in `vecs`
+    cstats = [(i, t) for i, t in vecs if t.dtype == DataType.Float and io0 != DataType.Float]
+    vecs = [(i, t) for i, t in vecs if (i, t) not in cstats]
     stats = [(i, t) for i, t in tin
              if (t.ndim == nd - 1 and tuple(cls(d) for d in t.dims) == row_cls)
              or (t.ndim == nd and t.dims[-1] is None and tuple(cls(d) for d in t.dims[:-1]) == row_cls)]
-    used = {i for i, _ in mats} | {i for i, _ in vecs} | {i for i, _ in stats}
+    used = {i for i, _ in mats} | {i for i, _ in vecs} | {i for i, _ in stats} | {i for i, _ in cstats}
     if len(used) != len(tin):
         raise Unmatchable("an input is neither [rows, cols], [cols] nor a per-row statistic")
     io = mats[0][1].dtype
@@ -623,6 +647,27 @@ def match_fusion(fd) -> Match:
                         roles["b"] = I(b)
                     return Match(L.OP_LAYERNORM_FWD, flags, eps, io, roles, names,
                                  description="layer_norm(x + residual)")
+
+    # ---- outer normalization backward: two matrices + per-column mean, invstd (+ weight) ----
+    pool = vecs + cstats
+    if n_m == 2 and n_s == 0 and len(pool) in (2, 3):
+        for a, b_ in ((mats[0], mats[1]), (mats[1], mats[0])):
+            for perm in itertools.permutations(pool):
+                mean, st = perm[0], perm[1]
+                w = perm[2] if len(perm) == 3 else None
+                if mean[1].dtype != DataType.Float or st[1].dtype != DataType.Float or (w and w[1].dtype != io):
+                    continue
+                names = try_candidate(
+                    lambda: def_outer_norm_bwd(ops, T(a), T(b_), mean[1], st[1], T(w) if w else None), {})
+                if names and "dx" in names:
+                    flags = L.F_OUTER | (L.F_HAS_WEIGHT if w else 0)
+                    roles = {"dy": I(a), "x": I(b_), "mean": I(mean), "stat": I(st)}
+                    if w:
+                        roles["w"] = I(w)
+                    return Match(L.OP_LAYERNORM_BWD, flags, 0.0, io, roles, names,
+                                 description="batch_norm backward (statistics over the outer axes, channels last)")
+    if cstats:
+        raise Unmatchable("per-column fp32 statistics outside an outer normalization backward")
 
     # ---- backward ops: two matrix inputs ----
     if n_m == 2:

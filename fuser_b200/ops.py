@@ -138,6 +138,21 @@ def outer_norm_fwd(x, weight=None, bias=None, eps: float = 1e-5, *, want_mean=Tr
     return y, mean, invstd
 
 
+def outer_norm_bwd(dy, x, mean, invstd, weight=None, output_mask=(True, True, True), *, variant=L.VARIANT_AUTO,
+                   cluster_size=0):
+    """dx, dweight[N], dbias[N] of :func:`outer_norm_fwd` (batch-norm backward in training mode, channels last:
+    benchmarks/python/normalization.py:98-190). ``mean`` / ``invstd`` are the saved fp32 [N] statistics."""
+    want_dx, want_dw, want_db = bool(output_mask[0]), bool(output_mask[1]) and weight is not None, bool(output_mask[2])
+    flags = L.F_OUTER | (L.F_HAS_WEIGHT if weight is not None else 0)
+    flags |= (L.F_OUT_DX if want_dx else 0) | (L.F_OUT_DW if want_dw else 0) | (L.F_OUT_DB if want_db else 0)
+    ins = [dy, x, mean, invstd] + ([weight] if weight is not None else [])
+    outs = iter(_run(L.OP_LAYERNORM_BWD, flags, 0.0, variant, cluster_size, ins))
+    dx = next(outs) if want_dx else None
+    dw = next(outs) if want_dw else None
+    db = next(outs) if want_db else None
+    return dx, dw, db
+
+
 def softmax_fwd(x, *, log=False, dim: int = -1, variant=L.VARIANT_AUTO, cluster_size=0):
     flags = _softmax_axis_flags(x, dim)
     (y,) = _run(L.OP_LOGSOFTMAX_FWD if log else L.OP_SOFTMAX_FWD, flags, 0.0, variant, cluster_size, [x])

@@ -139,7 +139,7 @@ enum {
    * rank order and casts. Publishes and combines pair up in order; at most two publishes may be
    * outstanding (two slots), the third waits in-kernel for the peers' "consumed" flags. */
   B200NORM_F_PEER_PUBLISH = 1u << 17,
-  /* SOFTMAX_* / LOGSOFTMAX_* and LAYERNORM_FWD: the reduction runs over dim 0 (the ROWS) of the row-major [M,N]
+  /* SOFTMAX_* / LOGSOFTMAX_* and LAYERNORM_FWD / LAYERNORM_BWD: the reduction runs over dim 0 (the ROWS) of the row-major [M,N]
    * matrix instead of dim 1 — the segments nvFuser's OuterPersistent scheduler takes
    * (scheduler/normalization_outer.cpp:451-683; benchmarks/python/test_softmax_{fwd,bwd}.py with
    * reduction_axis = 0, pytest mark outer_persistent). desc.rows = M is then the reduced extent and
@@ -151,7 +151,10 @@ enum {
    * LAYERNORM_FWD | OUTER is the batch-norm-shaped forward (training statistics, channels last:
    * benchmarks/python/normalization.py:13-95 viewed as [N*H*W, C]): mean / biased variance per COLUMN
    * over the M rows, y = (x - mean) * rsqrt(var + eps) * weight[col] + bias[col]; the mean / invstd
-   * outputs are fp32 [N]. No fused residual add. */
+   * outputs are fp32 [N]. No fused residual add.
+   * LAYERNORM_BWD | OUTER is its backward (benchmarks/python/normalization.py:98-190): in dy[M,N], x[M,N],
+   * mean[N], invstd[N] (fp32), weight[N]?; out dx[M,N]?, dweight[N]?, dbias[N]? (io dtype) — column sums taken
+   * inside the kernel (no partial-sum / peer flags). */
   B200NORM_F_OUTER = 1u << 18
 };
 

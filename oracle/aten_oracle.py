@@ -141,6 +141,27 @@ def outer_norm_fwd(x, weight, bias, eps: float):
     return y.to(io), mean, invstd
 
 
+def outer_norm_bwd(dy, x, mean, invstd, weight):
+    """benchmarks/python/normalization.py:98-190 (batch norm backward, training, channels last), per Expr.
+    Returns dx, dweight, dbias in the io dtype."""
+    io = x.dtype
+    xf, gf = _up(x), _up(dy)
+    axes = list(range(xf.dim() - 1))
+    num = 1
+    for ax in axes:
+        num *= xf.shape[ax]
+    norm = 1.0 / float(num)
+    grad_sum = torch.sum(gf, dim=axes)
+    x_sub_mean = xf - mean
+    dot_p = torch.sum(gf * x_sub_mean, dim=axes)
+    grad_mean = grad_sum * norm
+    proj_scale = (dot_p * norm) * (invstd * invstd)
+    grad_scale = (_up(weight) if weight is not None else 1.0) * invstd
+    dx = ((gf - proj_scale * x_sub_mean) - grad_mean) * grad_scale
+    dw = dot_p * invstd
+    return dx.to(io), dw.to(io), grad_sum.to(io)
+
+
 def layer_norm_fwd_python(x, weight, bias, eps: float):
     """benchmarks/python/test_layernorm_fwd.py:14-54 (var_mean, correction=0)."""
     io = x.dtype

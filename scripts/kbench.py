@@ -2,7 +2,7 @@
 """Time single ops at arbitrary shapes (back-to-back launches, rotating inputs > L2, CUDA events).
 
     python scripts/kbench.py "ln_bwd:32768x12288:bf16[:ENV=V,ENV=V]" ...
-ops: osm_fwd osm_bwd onorm_fwd (softmax / batch-norm-shaped normalization over dim 0: the outer-persistent kernels) rms_fwd add_rms_fwd add_ln_fwd ln_fwd sm_fwd sm_bwd rms_bwd rms_bwd_dx ln_bwd ln_bwd_dx copy (torch copy_, 1 read + 1 write: the
+ops: osm_fwd osm_bwd onorm_fwd onorm_bwd (softmax / batch-norm-shaped normalization over dim 0: the outer-persistent kernels) rms_fwd add_rms_fwd add_ln_fwd ln_fwd sm_fwd sm_bwd rms_bwd rms_bwd_dx ln_bwd ln_bwd_dx copy (torch copy_, 1 read + 1 write: the
 same-size calibration of what the memory system gives a plain streaming kernel)
 """
 import os
@@ -17,13 +17,13 @@ from fuser_b200 import ops  # noqa: E402
 
 KEYS = ["B200NORM_TPR", "B200NORM_GROUPS", "B200NORM_DEPTH", "B200NORM_TILE_ROWS", "B200NORM_CLUSTER",
         "B200NORM_BWD_REREAD", "B200NORM_NO_FUSED_FINISH", "B200NORM_NO_PDL", "B200NORM_NO_PSMEM", "B200NORM_COOP", "B200NORM_STATIC", "B200NORM_POOL", "B200NORM_NO_PIPE", "B200NORM_PIPE",
-        "B200NORM_OUTER_W", "B200NORM_OUTER_DEPTH", "B200NORM_OUTER_UNITS", "B200NORM_OUTER_PER_SM", "B200NORM_OUTER_SKIP_REDUCE", "B200NORM_OUTER_PLAIN_ST", "B200NORM_OUTER_TWO_EXCH"]
+        "B200NORM_OUTER_W", "B200NORM_OUTER_DEPTH", "B200NORM_OUTER_UNITS", "B200NORM_OUTER_PER_SM", "B200NORM_OUTER_SKIP_REDUCE", "B200NORM_OUTER_PLAIN_ST", "B200NORM_OUTER_TWO_EXCH", "B200NORM_OUTER_L2PF"]
 DT = {"bf16": torch.bfloat16, "f32": torch.float32, "f16": torch.float16}
 
 
 def algbytes(op, m, n, s):
     return {"add_rms_fwd": s * (4 * m * n + n) + 4 * m, "add_ln_fwd": s * (4 * m * n + 2 * n) + 8 * m,
-            "copy": s * 2 * m * n, "rms_fwd": s * (2 * m * n + n) + 4 * m, "ln_fwd": s * 2 * (m * n + n) + 8 * m, "sm_fwd": s * 2 * m * n, "osm_fwd": s * 2 * m * n, "onorm_fwd": s * 2 * (m * n + n) + 8 * n, "osm_bwd": s * 3 * m * n,
+            "copy": s * 2 * m * n, "rms_fwd": s * (2 * m * n + n) + 4 * m, "ln_fwd": s * 2 * (m * n + n) + 8 * m, "sm_fwd": s * 2 * m * n, "osm_fwd": s * 2 * m * n, "onorm_fwd": s * 2 * (m * n + n) + 8 * n, "onorm_bwd": s * 3 * (m * n + n) + 8 * n, "osm_bwd": s * 3 * m * n,
             "sm_bwd": s * 3 * m * n, "rms_bwd": s * (3 * m * n + 2 * n) + 4 * m, "rms_bwd_dx": s * (3 * m * n + 2 * n) + 4 * m,
             "ln_bwd": s * 3 * (m * n + n) + 8 * m, "ln_bwd_dx": s * 3 * (m * n + n) + 8 * m}[op]
 
@@ -64,6 +64,8 @@ def main():
                 aux["sm"] = [ops.softmax_fwd(x) for x in xs]
             if op == "osm_bwd" and "osm" not in aux:
                 aux["osm"] = [torch.softmax(x.float(), 0).to(dtype) for x in xs]
+            if op == "onorm_bwd" and "onorm" not in aux:
+                aux["onorm"] = [ops.outer_norm_fwd(x, w, w, 1e-5)[1:] for x in xs]
             if op == "copy" and "out" not in aux:
                 aux["out"] = torch.empty_like(xs[0])
             fns = {
@@ -75,6 +77,7 @@ def main():
                 "sm_fwd": lambda i: ops.softmax_fwd(xs[i]),
                 "osm_fwd": lambda i: ops.softmax_fwd(xs[i], dim=0),
                 "onorm_fwd": lambda i: ops.outer_norm_fwd(xs[i], w, w, 1e-5),
+                "onorm_bwd": lambda i: ops.outer_norm_bwd(dys[i], xs[i], aux["onorm"][i][0], aux["onorm"][i][1], w),
                 "osm_bwd": lambda i: ops.softmax_bwd(dys[i], aux["osm"][i], dim=0),
                 "sm_bwd": lambda i: ops.softmax_bwd(dys[i], aux["sm"][i]),
                 "rms_bwd": lambda i: ops.rms_norm_bwd(dys[i], xs[i], aux["rms"][i], w),

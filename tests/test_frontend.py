@@ -235,3 +235,30 @@ def test_batchnorm_fwd_matches_as_outer_norm(dt, nd):
         assert torch.allclose(me, mn, atol=1e-6) and torch.allclose(ie, inn, rtol=1e-5)
     # the inner LayerNorm spelling is untouched
     assert not build(F.layernorm_fwd_py, dt).segment().flags & L.F_OUTER
+
+
+@pytest.mark.parametrize("dt", [DataType.Float, DataType.BFloat16])
+def test_batchnorm_bwd_matches_as_outer_norm(dt):
+    """benchmarks/python/normalization.py:98-190: weight, mean and invstd are all [C] vectors (all Float with fp32
+    io) — the roles come out of the normal-form comparison, the running statistics are dropped as dead inputs."""
+    import torch
+    from oracle import aten_oracle as AO
+    from oracle import fusion_eval
+
+    fd = build(F.batchnorm_bwd_py, dt, num_dims=4)
+    m = fd.segment()
+    assert m.op == L.OP_LAYERNORM_BWD and m.flags & L.F_OUTER and m.flags & L.F_HAS_WEIGHT
+    assert m.roles == {"dy": 1, "x": 0, "mean": 5, "stat": 6, "w": 2} and m.outputs == ["dx", "dw", "db"]
+    td = torch.float32 if dt == DataType.Float else torch.bfloat16
+    x, dy, w = torch.randn(3, 4, 5, 16).to(td), torch.randn(3, 4, 5, 16).to(td), torch.randn(16).to(td)
+    _, mean, invstd = AO.outer_norm_fwd(x, w, None, 1e-5)
+    outs = fusion_eval.evaluate(fd, [x, dy, w, torch.zeros(16), torch.ones(16), mean, invstd])
+    for got, want in zip(outs, AO.outer_norm_bwd(dy, x, mean, invstd, w)):
+        assert torch.equal(got, want)
+    r = torch.ops.aten.native_batch_norm_backward(dy.float().permute(0, 3, 1, 2), x.float().permute(0, 3, 1, 2), w.float(),
+                                                   None, None, mean, invstd, True, 1e-5, [True, True, True])
+    tol = dict(atol=3e-2, rtol=3e-2) if td == torch.bfloat16 else dict(atol=1e-5, rtol=1e-5)
+    assert torch.allclose(outs[0].float(), r[0].permute(0, 2, 3, 1), **tol)
+    assert torch.allclose(outs[1].float(), r[1], atol=0.2 if td == torch.bfloat16 else 1e-4, rtol=3e-2)
+    # the inner backward spellings keep their classification
+    assert not build(F.layernorm_bwd_py, dt).segment().flags & L.F_OUTER

@@ -293,3 +293,67 @@ def test_batchnorm_fwd_frontend(dt):
     assert y.shape == x.shape and mean.shape == (c,) and invstd.shape == (c,)
     yn = torch.nn.functional.batch_norm(x.float().permute(0, 3, 1, 2), None, None, w.float(), b.float(), True, 0.1, 1e-5)
     AO.assert_close(y, yn.permute(0, 2, 3, 1).to(td).cpu(), nb * h * wd, "batch norm vs eager")
+
+
+@pytest.mark.parametrize("dt", DTYPES, ids=["bf16", "f32", "f16"])
+@pytest.mark.parametrize("shape", [(1, 64), (16, 768), (33, 1000), (216, 96), (512, 2048), (600, 136), (4100, 512)],
+                         ids=lambda s: f"{s[0]}x{s[1]}")
+def test_outer_norm_bwd(shape, dt):
+    """Backward of the outer normalization (batch-norm backward, training, channels last): dx + dweight + dbias."""
+    m, n = shape
+    x, dy, w, _ = make_inputs(m, n, dt, seed=m * 19 + n)
+    _, mean, invstd = AO.outer_norm_fwd(x, w, None, 1e-5)
+    dx, dw, db = ops.outer_norm_bwd(dy.cuda(), x.cuda(), mean.cuda(), invstd.cuda(), w.cuda())
+    assert dx.shape == (m, n) and dw.shape == (n,) and db.shape == (n,) and dw.dtype == dt
+    dxe, dwe, dbe = AO.outer_norm_bwd(dy, x, mean, invstd, w)
+    dxc, dwc, dbc = AO.outer_norm_bwd(dy.double(), x.double(), mean.double(), invstd.double(), w.double())
+    check(dx, dxe, dxc, m, "outer norm dx", 1.0 if dt == torch.float32 else 1e-1)
+    check(dw, dwe, dwc, m, "outer norm dw", max(1.0, m ** 0.5))
+    check(db, dbe, dbc, m, "outer norm db", max(1.0, m ** 0.5))
+    # output masks
+    dx2, dw2, db2 = ops.outer_norm_bwd(dy.cuda(), x.cuda(), mean.cuda(), invstd.cuda(), w.cuda(), (True, False, False))
+    assert dw2 is None and db2 is None and torch.equal(dx2, dx)
+
+
+@pytest.mark.parametrize("cluster", [1, 2, 4, 8, 16])
+def test_outer_norm_bwd_cluster_split(cluster):
+    dt = torch.bfloat16
+    m, n = 777, 384
+    x, dy, w, _ = make_inputs(m, n, dt, seed=cluster + 100)
+    _, mean, invstd = AO.outer_norm_fwd(x, w, None, 1e-5)
+    try:
+        ops.plan_for(L.OP_LAYERNORM_BWD, dt, m, n, flags=L.F_OUTER | L.F_HAS_WEIGHT | L.F_OUT_DX, cluster_size=cluster)
+    except L.UnsupportedSegment:
+        pytest.skip(f"M = {m} does not fit a cluster of {cluster}")
+    dx, dw, db = ops.outer_norm_bwd(dy.cuda(), x.cuda(), mean.cuda(), invstd.cuda(), w.cuda(), cluster_size=cluster)
+    dxe, dwe, dbe = AO.outer_norm_bwd(dy, x, mean, invstd, w)
+    dxc, dwc, dbc = AO.outer_norm_bwd(dy.double(), x.double(), mean.double(), invstd.double(), w.double())
+    check(dx, dxe, dxc, m, f"dx C={cluster}", 1e-1)
+    check(dw, dwe, dwc, m, f"dw C={cluster}", m ** 0.5)
+    check(db, dbe, dbc, m, f"db C={cluster}", m ** 0.5)
+
+
+@pytest.mark.parametrize("dt", [DataType.BFloat16, DataType.Float], ids=["bf16", "f32"])
+def test_batchnorm_bwd_frontend(dt):
+    """The reference's batch-norm backward definition through FusionDefinition (7 inputs, two of them unused),
+    validated against the node-by-node ATen evaluation and against at::native_batch_norm_backward."""
+    from oracle import fusion_eval
+
+    td = torch.bfloat16 if dt == DataType.BFloat16 else torch.float32
+    nb, h, wd, c = 8, 14, 14, 256
+    x = torch.randn(nb, h, wd, c).to(td)
+    dy = torch.randn(nb, h, wd, c).to(td)
+    w = torch.randn(c).to(td)
+    _, mean, invstd = AO.outer_norm_fwd(x, w, None, 1e-5)
+    ins = [x, dy, w, torch.zeros(c), torch.ones(c), mean, invstd]
+    with FusionDefinition() as fd:
+        F.batchnorm_bwd_py(fd, dt, num_dims=4)
+    assert fd.segment().op == L.OP_LAYERNORM_BWD and fd.segment().flags & L.F_OUTER
+    dx, dw, db = fd.validate([t.cuda() for t in ins], fusion_eval.evaluate(fd, ins))
+    assert dx.shape == x.shape and dw.shape == (c,) and db.shape == (c,)
+    r = torch.ops.aten.native_batch_norm_backward(dy.float().permute(0, 3, 1, 2), x.float().permute(0, 3, 1, 2), w.float(),
+                                                   None, None, mean, invstd, True, 1e-5, [True, True, True])
+    m = nb * h * wd
+    AO.assert_close(dx, r[0].permute(0, 2, 3, 1).to(td), m, "dx vs native_batch_norm_backward")
+    AO.assert_close(dw, r[1].to(td), m, "dweight")
+    AO.assert_close(db, r[2].to(td), m, "dbias")
