@@ -3,8 +3,9 @@
  *
  * This is the drop-in boundary for the ONE hot path this repository implements:
  * the LayerNorm / RMSNorm / softmax forward+backward segments that nvFuser's
- * InnerPersistent / InnerOuterPersistent / Reduction schedulers would otherwise
- * lower to NVRTC-generated code.
+ * InnerPersistent / InnerOuterPersistent / OuterPersistent / Reduction schedulers
+ * would otherwise lower to NVRTC-generated code (OuterPersistent: softmax and the
+ * batch-norm-shaped normalization over dim 0, B200NORM_F_OUTER).
  *
  * Reference interfaces each entry point replaces (paths under the reference tree):
  *   - ExecutorDispatch::{makeExecutor,compile,isCompiled,run}
