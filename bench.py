@@ -50,6 +50,10 @@ WORKLOADS = {
     # softmax over dim 0 (benchmarks/python/test_softmax_{fwd,bwd}.py, reduction_axis = 0)
     "o1": ("softmax over dim 0 fwd+bwd bf16 [8192,18432] (outer-persistent)", 8192, 18432, torch.bfloat16,
            "softmax_outer_fwd_bwd"),
+    # batch-norm-shaped normalization over dim 0, training statistics, channels last
+    # (benchmarks/python/normalization.py, test_batchnorm_{fwd,bwd}.py viewed as [N*H*W, C])
+    "o2": ("batch norm fwd+bwd bf16 [8192,18432] (statistics over dim 0, outer-persistent)", 8192, 18432, torch.bfloat16,
+           "outer_norm_fwd_bwd"),
 }
 EPS = 1e-5
 L2_BYTES = 126 * 1024 * 1024
@@ -61,6 +65,8 @@ def iobytes(kind: str, m: int, n: int, s: int) -> dict:
         return {"fwd": s * (2 * m * n + n) + 4 * m, "bwd": s * (3 * m * n + 2 * n) + 4 * m}
     if kind in ("softmax_fwd_bwd", "softmax_outer_fwd_bwd"):
         return {"fwd": s * 2 * m * n, "bwd": s * 3 * m * n}
+    if kind == "outer_norm_fwd_bwd":
+        return {"fwd": s * 2 * (m * n + n) + 4 * 2 * n, "bwd": s * 3 * (m * n + n) + 4 * 2 * n}
     if kind == "layernorm_bwd":
         return {"bwd": s * 3 * (m * n + n) + 4 * 2 * m}
     if kind == "layernorm_fwd":
@@ -196,6 +202,8 @@ class Step:
                 self.saved.append(ops.softmax_fwd(x))
             elif kind == "softmax_outer_fwd_bwd":
                 self.saved.append(ops.softmax_fwd(x, dim=0))
+            elif kind == "outer_norm_fwd_bwd":
+                self.saved.append(ops.outer_norm_fwd(x, self.w, self.w, EPS)[1:])
             else:
                 self.saved.append(None)
         torch.cuda.synchronize(device)
@@ -210,6 +218,8 @@ class Step:
             return (ops.softmax_fwd(x),)
         if self.kind == "softmax_outer_fwd_bwd":
             return (ops.softmax_fwd(x, dim=0),)
+        if self.kind == "outer_norm_fwd_bwd":
+            return ops.outer_norm_fwd(x, self.w, self.w, EPS)
         if self.kind == "layernorm_fwd":
             return ops.layer_norm_fwd(x, self.w, self.w, EPS)
         return None
@@ -231,6 +241,9 @@ class Step:
             return (ops.softmax_bwd(dy, fwd_out[0] if fwd_out is not None else saved),)
         if self.kind == "softmax_outer_fwd_bwd":
             return (ops.softmax_bwd(dy, fwd_out[0] if fwd_out is not None else saved, dim=0),)
+        if self.kind == "outer_norm_fwd_bwd":
+            mean, invstd = (fwd_out[1], fwd_out[2]) if fwd_out is not None else saved
+            return ops.outer_norm_bwd(dy, x, mean, invstd, self.w)
         if self.kind == "layernorm_bwd":
             mean, invstd = saved
             if self.world > 1:
@@ -279,6 +292,11 @@ class E2E:
             self.fd_fwd, self.fd_bwd = define(F.softmax_fwd_py), define(F.softmax_bwd_py)
         elif kind == "softmax_outer_fwd_bwd":
             self.fd_fwd, self.fd_bwd = define(F.softmax_fwd_py, 0), define(F.softmax_bwd_py, 0)
+        elif kind == "outer_norm_fwd_bwd":
+            self.fd_fwd, self.fd_bwd = define(F.batchnorm_fwd_py, 2, EPS), define(F.batchnorm_bwd_py, 2)
+            # the running statistics of the reference's definitions: inputs that only feed dead code
+            self.rm = torch.zeros(n, device=device)
+            self.rv = torch.ones(n, device=device)
         elif kind == "layernorm_bwd":
             self.fd_fwd, self.fd_bwd = define(F.layernorm_fwd_py, EPS), define(F.layernorm_bwd_py)
         else:
@@ -304,6 +322,10 @@ class E2E:
             (y,) = self.fd_fwd.execute([x])
             (dx,) = self.fd_bwd.execute([y, dy])
             return [y, dx]
+        if k == "outer_norm_fwd_bwd":
+            y, mean, invstd = self.fd_fwd.execute([x, w, w, self.rm, self.rv])
+            dx, dw, db = self.fd_bwd.execute([x, dy, w, self.rm, self.rv, mean, invstd])
+            return [y, mean, invstd, dx, dw, db]
         if k == "layernorm_bwd":
             # the config is the backward; the saved statistics come from the forward definition
             y, mean, invstd = self.fd_fwd.execute([x, w, w])
@@ -358,6 +380,9 @@ def cpu_step_fn(kind, dtype):
         if kind == "softmax_outer_fwd_bwd":
             y = AO.softmax_fwd(x, dim=0)
             return AO.softmax_bwd_python(y, dy, dim=0)
+        if kind == "outer_norm_fwd_bwd":
+            y, mean, invstd = AO.outer_norm_fwd(x, w, w, EPS)
+            return AO.outer_norm_bwd(dy, x, mean, invstd, w)
         if kind == "layernorm_bwd":
             _, mean, invstd = AO.layer_norm_fwd(x, None, None, EPS)
             return AO.layer_norm_bwd_python(x, dy, mean.view(-1), invstd, w)
