@@ -33,7 +33,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
+#include <tuple>
 #include <unordered_map>
 
 #include "../../include/b200norm.h"
@@ -1058,8 +1060,8 @@ bool make_map(CUtensorMap* map, const OuterArgs& a, const void* base, int64_t ro
 // resident clusters (C > 1) or CTAs (C == 1) of this launch shape on the current device
 int resident_units(OuterKernel k, int smem, int C, int sm_count) {
   static std::mutex mu;
-  static std::unordered_map<uint64_t, int> cache;
-  const uint64_t key = (reinterpret_cast<uint64_t>((const void*)k) << 6) ^ ((uint64_t)smem << 8) ^ (uint64_t)C;
+  static std::map<std::tuple<const void*, int, int>, int> cache;
+  const auto key = std::make_tuple((const void*)k, smem, C);
   {
     std::lock_guard<std::mutex> lock(mu);
     auto it = cache.find(key);

@@ -313,6 +313,8 @@ def test_outer_norm_bwd(shape, dt):
     # output masks
     dx2, dw2, db2 = ops.outer_norm_bwd(dy.cuda(), x.cuda(), mean.cuda(), invstd.cuda(), w.cuda(), (True, False, False))
     assert dw2 is None and db2 is None and torch.equal(dx2, dx)
+    dx3, dw3, db3 = ops.outer_norm_bwd(dy.cuda(), x.cuda(), mean.cuda(), invstd.cuda(), w.cuda(), (False, True, True))
+    assert dx3 is None and torch.equal(dw3, dw) and torch.equal(db3, db)
 
 
 @pytest.mark.parametrize("cluster", [1, 2, 4, 8, 16])
