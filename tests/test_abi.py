@@ -164,3 +164,25 @@ def test_outer_persistent_planner():
         _outer_plan(L.OP_RMSNORM_FWD, L.DT_BF16, 512, 4096)
     # empty problems plan to nothing
     assert _outer_plan(L.OP_SOFTMAX_FWD, L.DT_BF16, 0, 4096)["grid"] == 0
+
+
+def test_outer_normalization_descs():
+    """LAYERNORM_FWD / LAYERNORM_BWD with F_OUTER (batch-norm-shaped, statistics per column): planned on the
+    outer-persistent family; per-column statistics in the byte count; flag combinations that make no sense
+    are refused before any device work."""
+    f_fwd = L.F_OUTER | L.F_HAS_WEIGHT | L.F_HAS_BIAS | L.F_OUT_MEAN | L.F_OUT_INVSTD
+    p = L.query(L.make_desc(L.OP_LAYERNORM_FWD, L.DT_BF16, 8192, 18432, 1e-5, f_fwd, L.VARIANT_AUTO, 0)).as_dict()
+    assert p["variant"] == "cluster" and p["cluster_size"] == 8 and p["block"] == 256 and p["n_launches"] == 1
+    assert p["algorithmic_bytes"] == 2 * 2 * (8192 * 18432 + 18432) + 8 * 18432
+    f_bwd = L.F_OUTER | L.F_HAS_WEIGHT | L.F_OUT_DX | L.F_OUT_DW | L.F_OUT_DB
+    p = L.query(L.make_desc(L.OP_LAYERNORM_BWD, L.DT_BF16, 8192, 18432, 0.0, f_bwd, L.VARIANT_AUTO, 0)).as_dict()
+    assert p["cluster_size"] == 16 and p["n_launches"] == 1  # two streams: half the rows per CTA; sums finished in-kernel
+    assert p["algorithmic_bytes"] == 2 * 3 * (8192 * 18432 + 18432) + 8 * 18432
+    for bad in (f_fwd | L.F_ADD_RESIDUAL, ):
+        with pytest.raises(L.UnsupportedSegment):
+            L.query(L.make_desc(L.OP_LAYERNORM_FWD, L.DT_BF16, 512, 4096, 1e-5, bad, L.VARIANT_AUTO, 0))
+    for bad in (f_bwd | L.F_PARTIALS_F32, f_bwd | L.F_PEER_REDUCE):
+        with pytest.raises(L.UnsupportedSegment):
+            L.query(L.make_desc(L.OP_LAYERNORM_BWD, L.DT_BF16, 512, 4096, 0.0, bad, L.VARIANT_AUTO, 0))
+    with pytest.raises(L.UnsupportedSegment):  # ResNet-size N*H*W: beyond a 16-CTA cluster, the caller falls through
+        L.query(L.make_desc(L.OP_LAYERNORM_FWD, L.DT_BF16, 100352, 256, 1e-5, f_fwd, L.VARIANT_AUTO, 0))
