@@ -581,6 +581,8 @@ OuterArgs outer_args_from(const b200norm_desc& d) {
   a.eps = d.eps;
   a.round_sum = (d.flags & B200NORM_F_ROUND_ROWSUM) ? 1 : 0;
   a.cluster_forced = d.cluster_size != 0 ? d.cluster_size : env_int("B200NORM_CLUSTER");
+  a.force_generic = d.variant == B200NORM_VARIANT_GENERIC ? 1 : 0;
+  a.force_persistent = (d.variant == B200NORM_VARIANT_TMA || d.variant == B200NORM_VARIANT_CLUSTER) ? 1 : 0;
   a.has_device = dev.has_device;
   a.sm_count = dev.sm_count;
   a.smem_optin = dev.smem_optin;
@@ -945,27 +947,42 @@ int b200norm_query(const b200norm_desc* desc, b200norm_plan* plan) {
   int rc = check_desc(desc);
   if (rc != B200NORM_OK) return rc;
   if (is_outer(*desc)) {
-    if (desc->variant == B200NORM_VARIANT_GENERIC)
-      return fail(B200NORM_ERR_UNSUPPORTED, "the outer-persistent ops have no generic kernel family");
     if (plan != nullptr) memset(plan, 0, sizeof(*plan));
+    const OuterArgs oa = outer_args_from(*desc);
+    const uint64_t ws = outer_generic_workspace_bytes(oa);  // covers a launch-time fall-back to the generic family
     if (desc->rows == 0 || desc->cols == 0) {
-      if (plan != nullptr) plan->workspace_bytes = B200NORM_WS_HEADER_BYTES;
+      if (plan != nullptr) plan->workspace_bytes = ws;
       return B200NORM_OK;
     }
     OuterPlan op;
     char msg[256] = "";
-    if (!outer_make_plan(outer_args_from(*desc), &op, msg, sizeof(msg))) return fail(B200NORM_ERR_UNSUPPORTED, "%s", msg);
+    const bool persistent = !oa.force_generic && outer_make_plan(oa, &op, msg, sizeof(msg));
+    if (!persistent && (desc->variant == B200NORM_VARIANT_TMA || desc->variant == B200NORM_VARIANT_CLUSTER))
+      return fail(B200NORM_ERR_UNSUPPORTED, "requested kernel family cannot run this outer segment: %s", msg);
     if (plan != nullptr) {
-      plan->variant = op.cluster > 1 ? B200NORM_VARIANT_CLUSTER : B200NORM_VARIANT_TMA;
-      plan->cluster_size = op.cluster;
-      plan->grid_x = op.grid;
-      plan->block_x = op.block;
-      plan->threads_per_row = op.slab_bytes / 16;  // threads across one slab row
-      plan->stages = op.depth;
-      plan->tile_rows = op.rows_cta;
-      plan->smem_bytes = (int32_t)op.smem;
-      plan->n_launches = 1;
-      plan->workspace_bytes = B200NORM_WS_HEADER_BYTES;
+      if (persistent) {
+        plan->variant = op.cluster > 1 ? B200NORM_VARIANT_CLUSTER : B200NORM_VARIANT_TMA;
+        plan->cluster_size = op.cluster;
+        plan->grid_x = op.grid;
+        plan->block_x = op.block;
+        plan->threads_per_row = op.slab_bytes / 16;  // threads across one slab row
+        plan->stages = op.depth;
+        plan->tile_rows = op.rows_cta;
+        plan->smem_bytes = (int32_t)op.smem;
+        plan->n_launches = 1;
+      } else {
+        // shape-agnostic family (outer_generic.cuh): statistics / merge / apply kernels over (column blocks x row splits)
+        int gx = 1, ns = 1, rps = 1;
+        outer_generic_plan(oa, &gx, &ns, &rps);
+        plan->variant = B200NORM_VARIANT_GENERIC;
+        plan->cluster_size = 1;
+        plan->grid_x = gx * ns;
+        plan->block_x = 128;
+        plan->threads_per_row = 1;
+        plan->tile_rows = rps;
+        plan->n_launches = 3;
+      }
+      plan->workspace_bytes = ws;
       plan->algorithmic_bytes = algorithmic_bytes(*desc);
     }
     return B200NORM_OK;
@@ -1224,9 +1241,9 @@ int b200norm_launch(const b200norm_desc* desc, const b200norm_tensor* inputs, in
   if (is_outer(d)) {
     // outer-persistent softmax family (outer.cu): its own planner and launch
     if (d.rows == 0 || d.cols == 0) return B200NORM_OK;
-    if (d.variant == B200NORM_VARIANT_GENERIC)
-      return fail(B200NORM_ERR_UNSUPPORTED, "the outer-persistent ops have no generic kernel family");
     OuterArgs a = outer_args_from(d);
+    a.workspace = workspace;
+    a.workspace_bytes = workspace_bytes;
     a.in0 = rp.in0;
     a.in1 = rp.in1;
     a.out = rp.out0;
@@ -1247,7 +1264,7 @@ int b200norm_launch(const b200norm_desc* desc, const b200norm_tensor* inputs, in
     char msg[256] = "";
     rc = outer_launch(a, stream_v, msg, sizeof(msg));
     if (rc != B200NORM_OK) return fail(rc, "%s", msg);
-    g_launches++;
+    g_launches += (uint64_t)outer_last_launches();
     return B200NORM_OK;
   }
 

@@ -40,6 +40,7 @@
 
 #include "../../include/b200norm.h"
 #include "common.cuh"
+#include "outer_generic.cuh"
 
 namespace b200norm {
 
@@ -1102,21 +1103,124 @@ int resident_units(OuterKernel k, int smem, int C, int sm_count) {
 
 }  // namespace
 
+namespace {
+thread_local int g_outer_last_launches = 0;
+}
+int outer_last_launches() { return g_outer_last_launches; }
+
+void outer_generic_plan(const OuterArgs& a, int* grid_x, int* nsplit, int* rows_per_split) {
+  const int64_t ncb = (a.N + kOuterGenThreads - 1) / kOuterGenThreads;
+  int64_t want = (16 * (int64_t)a.sm_count + ncb - 1) / ncb;  // ~16 CTAs of 128 threads per SM in total
+  if (want > (a.M + 31) / 32) want = (a.M + 31) / 32;           // at least 32 rows per split
+  if (want > kOuterGenMaxSplits) want = kOuterGenMaxSplits;
+  if (want > a.M) want = a.M;
+  if (want < 1) want = 1;
+  const int64_t rps = (a.M + want - 1) / want;
+  *rows_per_split = (int)(rps < 1 ? 1 : rps);
+  *nsplit = (int)((a.M + *rows_per_split - 1) / *rows_per_split);
+  if (*nsplit < 1) *nsplit = 1;
+  *grid_x = (int)ncb;
+}
+
+size_t outer_generic_workspace_bytes(const OuterArgs& a) {
+  if (a.M <= 0 || a.N <= 0) return B200NORM_WS_HEADER_BYTES;
+  int gx = 1, ns = 1, rps = 1;
+  outer_generic_plan(a, &gx, &ns, &rps);
+  return (size_t)B200NORM_WS_HEADER_BYTES + ((size_t)ns + 1u) * 2u * (size_t)a.N * 4u;  // partials + merged values
+}
+
+namespace {
+
+template <typename T, int KIND>
+void launch_outer_generic_kind(const OuterGenParams& p, dim3 grid, cudaStream_t stream) {
+  outer_generic_stats<T, KIND><<<grid, kOuterGenThreads, 0, stream>>>(p);
+  outer_generic_merge<T, KIND><<<dim3(grid.x), kOuterGenThreads, 0, stream>>>(p);
+  outer_generic_apply<T, KIND><<<grid, kOuterGenThreads, 0, stream>>>(p);
+}
+template <typename T>
+void launch_outer_generic_typed(int kind, const OuterGenParams& p, dim3 grid, cudaStream_t stream) {
+  switch (kind) {
+    case 0: launch_outer_generic_kind<T, 0>(p, grid, stream); break;
+    case 1: launch_outer_generic_kind<T, 1>(p, grid, stream); break;
+    case 2: launch_outer_generic_kind<T, 2>(p, grid, stream); break;
+    case 3: launch_outer_generic_kind<T, 3>(p, grid, stream); break;
+    case 4: launch_outer_generic_kind<T, 4>(p, grid, stream); break;
+    default: launch_outer_generic_kind<T, 5>(p, grid, stream); break;
+  }
+}
+
+int outer_generic_launch(const OuterArgs& a, int kind, void* stream_v, char* err, size_t errlen) {
+  const size_t need = outer_generic_workspace_bytes(a);
+  if (a.workspace == nullptr || a.workspace_bytes < need)
+    return set_err(err, errlen, B200NORM_ERR_WORKSPACE, "outer generic family: workspace %zu bytes, need %zu", a.workspace_bytes, need);
+  if ((reinterpret_cast<uintptr_t>(a.workspace) & 255u) != 0)
+    return set_err(err, errlen, B200NORM_ERR_WORKSPACE, "workspace must be 256-byte aligned");
+  if (a.M > 0x7fffffffLL || a.N > 0x7fffffffLL) return set_err(err, errlen, B200NORM_ERR_UNSUPPORTED, "outer generic family: extents exceed int32");
+  OuterGenParams p;
+  memset(&p, 0, sizeof(p));
+  p.in0 = a.in0;
+  p.in1 = a.in1;
+  p.out = a.out;
+  p.s0 = a.M > 1 ? a.in0_stride : a.N;
+  p.s1 = a.M > 1 ? a.in1_stride : a.N;
+  p.so = a.M > 1 ? a.out_stride : a.N;
+  p.M = (int32_t)a.M;
+  p.N = (int32_t)a.N;
+  int gx = 1, ns = 1, rps = 1;
+  outer_generic_plan(a, &gx, &ns, &rps);
+  p.nsplit = ns;
+  p.rows_per_split = rps;
+  p.part = reinterpret_cast<float*>(static_cast<uint8_t*>(a.workspace) + B200NORM_WS_HEADER_BYTES);
+  p.weight = a.weight;
+  p.bias = a.bias;
+  p.mean_out = a.mean_out;
+  p.invstd_out = a.invstd_out;
+  p.mean_in = a.mean_in;
+  p.invstd_in = a.invstd_in;
+  p.dw_out = a.dw_out;
+  p.db_out = a.db_out;
+  p.inv_m = (float)(1.0 / (double)a.M);
+  p.eps = (float)a.eps;
+  p.round_sum = a.round_sum;
+  const dim3 grid((unsigned)gx, (unsigned)ns);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  switch (a.dtype) {
+    case B200NORM_DT_F32: launch_outer_generic_typed<float>(kind, p, grid, stream); break;
+    case B200NORM_DT_BF16: launch_outer_generic_typed<__nv_bfloat16>(kind, p, grid, stream); break;
+    case B200NORM_DT_F16: launch_outer_generic_typed<__half>(kind, p, grid, stream); break;
+    default: return set_err(err, errlen, B200NORM_ERR_UNSUPPORTED, "outer generic family: dtype %d", a.dtype);
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_err(err, errlen, B200NORM_ERR_CUDA + (int)e, "outer generic launch failed: %s", cudaGetErrorString(e));
+  return B200NORM_OK;
+}
+
+}  // namespace
+
 int outer_launch(const OuterArgs& a, void* stream_v, char* err, size_t errlen) {
-  OuterPlan pl;
-  if (!outer_make_plan(a, &pl, err, errlen)) return B200NORM_ERR_UNSUPPORTED;
+  const int kind = a.norm ? (a.bwd ? 5 : 4) : (a.bwd ? 2 : 0) + (a.log ? 1 : 0);
   const int es = a.dtype == B200NORM_DT_F32 ? 4 : 2;
   auto aligned = [&](const void* ptr, int64_t stride) {
     return (reinterpret_cast<uintptr_t>(ptr) & 15u) == 0 && (a.M <= 1 || (stride * es) % 16 == 0);
   };
   auto aligned_vec = [](const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15u) == 0; };
-  if (a.norm && (!aligned_vec(a.weight) || !aligned_vec(a.bias) || !aligned_vec(a.mean_out) || !aligned_vec(a.invstd_out) ||
-                 !aligned_vec(a.mean_in) || !aligned_vec(a.invstd_in) || !aligned_vec(a.dw_out) || !aligned_vec(a.db_out)))
-    return set_err(err, errlen, B200NORM_ERR_UNSUPPORTED, "outer norm: weight / bias / statistics must be 16-byte aligned");
-  if (!aligned(a.in0, a.in0_stride) || (a.out != nullptr && !aligned(a.out, a.out_stride)) || (a.bwd && !aligned(a.in1, a.in1_stride)))
-    return set_err(err, errlen, B200NORM_ERR_UNSUPPORTED, "outer-persistent: operands must be 16-byte aligned (base and row stride)");
+  OuterPlan pl;
+  char why[160] = "";
+  bool persistent = !a.force_generic && outer_make_plan(a, &pl, why, sizeof(why));
+  if (persistent && a.norm &&
+      (!aligned_vec(a.weight) || !aligned_vec(a.bias) || !aligned_vec(a.mean_out) || !aligned_vec(a.invstd_out) ||
+       !aligned_vec(a.mean_in) || !aligned_vec(a.invstd_in) || !aligned_vec(a.dw_out) || !aligned_vec(a.db_out)))
+    persistent = false;
+  if (persistent && (!aligned(a.in0, a.in0_stride) || (a.out != nullptr && !aligned(a.out, a.out_stride)) ||
+                     (a.bwd && !aligned(a.in1, a.in1_stride))))
+    persistent = false;
+  // whatever the persistent kernels cannot take goes to the shape-agnostic family (two kernels, matrix read twice)
+  g_outer_last_launches = persistent ? 1 : 3;
+  if (!persistent && a.force_persistent)
+    return set_err(err, errlen, B200NORM_ERR_UNSUPPORTED, "requested kernel family cannot run this outer segment: %s", why);
+  if (!persistent) return outer_generic_launch(a, kind, stream_v, err, errlen);
 
-  OuterKernel k = outer_kernel_for(a.dtype, a.norm ? (a.bwd ? 5 : 4) : (a.bwd ? 2 : 0) + (a.log ? 1 : 0));
+  OuterKernel k = outer_kernel_for(a.dtype, kind);
   if (k == nullptr) return set_err(err, errlen, B200NORM_ERR_UNSUPPORTED, "outer-persistent: dtype %d", a.dtype);
   {
     static std::mutex mu;

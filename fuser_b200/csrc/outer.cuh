@@ -38,6 +38,10 @@ struct OuterArgs {
   double eps = 0.0;
   int round_sum = 0;       // backward: round the column sum through the io dtype (B200NORM_F_ROUND_ROWSUM)
   int cluster_forced = 0;  // 0 = planner's choice, else 1,2,4,8,16
+  int force_generic = 0;   // 1: the shape-agnostic family (outer_generic.cuh: stats / merge / apply) whatever the shape
+  int force_persistent = 0;  // 1: a persistent family was requested: no fall-back
+  void* workspace = nullptr;  // caller's workspace (generic family: fp32 partials behind the 256-byte header)
+  size_t workspace_bytes = 0;
   int has_device = 0;
   int sm_count = 148;
   int smem_optin = 232448;
@@ -62,7 +66,17 @@ struct OuterPlan {
 // no persistent plan exists (the reference segments such fusions as well).
 bool outer_make_plan(const OuterArgs& a, OuterPlan* plan, char* err, size_t errlen);
 
-// Enqueue on `stream`. Returns 0, or a b200norm status code with the message in err.
+// Workspace the shape-agnostic family needs for this problem (header included).
+size_t outer_generic_workspace_bytes(const OuterArgs& a);
+
+// Plan of the shape-agnostic family: CTAs per launch and row splits.
+void outer_generic_plan(const OuterArgs& a, int* grid_x, int* nsplit, int* rows_per_split);
+
+// Enqueue on `stream`. Returns 0, or a b200norm status code with the message in err. Falls back to the
+// shape-agnostic family when no persistent plan exists or the operands are not 16-byte aligned.
 int outer_launch(const OuterArgs& a, void* stream, char* err, size_t errlen);
+
+// Kernels the last outer_launch of this thread enqueued (1 persistent, 3 shape-agnostic).
+int outer_last_launches();
 
 }  // namespace b200norm

@@ -146,9 +146,10 @@ enum {
    * reduction_axis = 0, pytest mark outer_persistent). desc.rows = M is then the reduced extent and
    * desc.cols = N the iteration extent; tensors keep the same [M,N] layout and order as the inner
    * ops. Runs on the outer-persistent kernels (a column slab resident in the shared memory of a CTA
-   * or of a cluster split along M); requires 16-byte aligned operands and N * sizeof(T) % 16 == 0,
-   * and M small enough for a 16-CTA cluster (else B200NORM_ERR_UNSUPPORTED: the caller falls through,
-   * as the reference segments such fusions).
+   * or of a cluster split along M) when the operands are 16-byte aligned, N * sizeof(T) % 16 == 0 and M is
+   * small enough for a 16-CTA cluster; anything else (and B200NORM_VARIANT_GENERIC) runs on the shape-agnostic
+   * three-kernel family (statistics / merge / apply, fp32 partials in the workspace), the split the reference
+   * makes when it segments such fusions. A forced TMA / CLUSTER variant refuses instead of falling back.
    * LAYERNORM_FWD | OUTER is the batch-norm-shaped forward (training statistics, channels last:
    * benchmarks/python/normalization.py:13-95 viewed as [N*H*W, C]): mean / biased variance per COLUMN
    * over the M rows, y = (x - mean) * rsqrt(var + eps) * weight[col] + bias[col]; the mean / invstd

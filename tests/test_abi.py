@@ -156,11 +156,18 @@ def test_outer_persistent_planner():
     # forced cluster sizes are honoured
     for c in (1, 2, 4, 8, 16):
         assert _outer_plan(L.OP_SOFTMAX_FWD, L.DT_F32, 777, 384, c)["cluster_size"] == c
-    # declined: rows that are not a multiple of 16 bytes, extents beyond a 16-CTA cluster, other ops
+    # rows that are not a multiple of 16 bytes, extents beyond a 16-CTA cluster: the shape-agnostic family
+    # (statistics kernel + apply kernel; the reference segments such fusions the same way)
     for m, n in ((32, 100), (1 << 18, 4096)):
-        with pytest.raises(L.UnsupportedSegment):
-            _outer_plan(L.OP_SOFTMAX_FWD, L.DT_BF16, m, n)
-    with pytest.raises(L.UnsupportedSegment):
+        p = _outer_plan(L.OP_SOFTMAX_FWD, L.DT_BF16, m, n)
+        assert p["variant"] == "generic" and p["n_launches"] == 3 and p["block"] == 128
+        assert p["workspace_bytes"] >= 256 + 2 * 4 * n
+    d = L.make_desc(L.OP_SOFTMAX_FWD, L.DT_BF16, 1 << 18, 4096, 0.0, L.F_OUTER, L.VARIANT_CLUSTER, 0)
+    with pytest.raises(L.UnsupportedSegment):  # a forced persistent family still refuses
+        L.query(d)
+    assert L.query(L.make_desc(L.OP_SOFTMAX_FWD, L.DT_BF16, 512, 4096, 0.0, L.F_OUTER, L.VARIANT_GENERIC, 0)).as_dict()[
+        "variant"] == "generic"
+    with pytest.raises(L.UnsupportedSegment):  # other ops have no outer flavour
         _outer_plan(L.OP_RMSNORM_FWD, L.DT_BF16, 512, 4096)
     # empty problems plan to nothing
     assert _outer_plan(L.OP_SOFTMAX_FWD, L.DT_BF16, 0, 4096)["grid"] == 0
@@ -184,5 +191,6 @@ def test_outer_normalization_descs():
     for bad in (f_bwd | L.F_PARTIALS_F32, f_bwd | L.F_PEER_REDUCE):
         with pytest.raises(L.UnsupportedSegment):
             L.query(L.make_desc(L.OP_LAYERNORM_BWD, L.DT_BF16, 512, 4096, 0.0, bad, L.VARIANT_AUTO, 0))
-    with pytest.raises(L.UnsupportedSegment):  # ResNet-size N*H*W: beyond a 16-CTA cluster, the caller falls through
-        L.query(L.make_desc(L.OP_LAYERNORM_FWD, L.DT_BF16, 100352, 256, 1e-5, f_fwd, L.VARIANT_AUTO, 0))
+    # ResNet-size N*H*W: beyond a 16-CTA cluster -> the shape-agnostic family, many row splits for few columns
+    p = L.query(L.make_desc(L.OP_LAYERNORM_FWD, L.DT_BF16, 100352, 256, 1e-5, f_fwd, L.VARIANT_AUTO, 0)).as_dict()
+    assert p["variant"] == "generic" and p["n_launches"] == 3 and p["grid"] % 2 == 0 and p["grid"] >= 2 * 256

@@ -144,11 +144,15 @@ def test_outer_edge_cases():
             AO.assert_close(y, ref, 96 * 96, f"NaN/Inf columns, cluster {cluster}, log={log}")
             assert torch.isnan(y[:, 1:4]).all() and not torch.isnan(y[:, 0]).any()
             assert not torch.isnan(y[:, 4:]).any(), f"cluster {cluster}: -inf rows poisoned a finite column"
-    # shapes the persistent kernels decline: misaligned rows, reduced extent beyond a 16-CTA cluster
+    # shapes the persistent kernels cannot take (rows that are not a multiple of 16 bytes, a reduced extent
+    # beyond a 16-CTA cluster) run on the shape-agnostic family; a forced persistent family refuses them
+    xo = torch.randn(32, 100).to(dt)  # 200 bytes per row
+    assert ops.plan_for(L.OP_SOFTMAX_FWD, dt, 32, 100, flags=L.F_OUTER)["variant"] == "generic"
+    AO.assert_close(ops.softmax_fwd(xo.cuda(), dim=0), AO.softmax_fwd(xo, dim=0), 32 * 32, "odd row bytes")
+    xl = torch.randn(1 << 18, 8).to(dt)
+    AO.assert_close(ops.softmax_fwd(xl.cuda(), dim=0), AO.softmax_fwd(xl, dim=0), (1 << 18) ** 2, "M = 2^18")
     with pytest.raises(L.UnsupportedSegment):
-        ops.softmax_fwd(torch.randn(32, 100).to(dt).cuda(), dim=0)  # 200 bytes per row
-    with pytest.raises(L.UnsupportedSegment):
-        ops.softmax_fwd(torch.empty(1 << 18, 8, dtype=dt, device="cuda"), dim=0)
+        ops.softmax_fwd(xl.cuda(), dim=0, variant=L.VARIANT_CLUSTER)
     with pytest.raises(L.UnsupportedSegment):
         ops.softmax_fwd(torch.randn(8, 8, 8).to(dt).cuda(), dim=1)
 
@@ -359,3 +363,64 @@ def test_batchnorm_bwd_frontend(dt):
     AO.assert_close(dx, r[0].permute(0, 2, 3, 1).to(td), m, "dx vs native_batch_norm_backward")
     AO.assert_close(dw, r[1].to(td), m, "dweight")
     AO.assert_close(db, r[2].to(td), m, "dbias")
+
+
+GENERIC_SHAPES = [(1, 3), (7, 1), (33, 1987), (216, 96), (600, 130), (2048, 264), (5000, 37)]
+
+
+@pytest.mark.parametrize("dt", DTYPES, ids=["bf16", "f32", "f16"])
+@pytest.mark.parametrize("shape", GENERIC_SHAPES, ids=lambda s: f"{s[0]}x{s[1]}")
+def test_outer_generic_family(shape, dt):
+    """The shape-agnostic two-kernel family (outer_generic.cuh: single-pass partials per row split — online
+    softmax, Welford — merged in split order, then an apply pass): every outer op at shapes no vectorised path
+    takes (N = 3, 1987, 37 ...), forced with VARIANT_GENERIC, against both oracles."""
+    m, n = shape
+    x, dy, w, b = make_inputs(m, n, dt, seed=m * 23 + n)
+    assert ops.plan_for(L.OP_SOFTMAX_FWD, dt, m, n, flags=L.F_OUTER, variant=L.VARIANT_GENERIC)["variant"] == "generic"
+    run_all(x, dy, dt, m, f"generic [{m},{n}]", variant=L.VARIANT_GENERIC)
+    eps = 1e-5
+    y, mean, invstd = ops.outer_norm_fwd(x.cuda(), w.cuda(), b.cuda(), eps, variant=L.VARIANT_GENERIC)
+    ye, me, ie = AO.outer_norm_fwd(x, w, b, eps)
+    yc, mc, ic = c_outer_norm_fwd(x, w, b, eps)
+    check(y, ye, yc, m, "generic outer norm y", 1.0 if dt == torch.float32 else 1e-2)
+    check(mean, me, mc, m, "generic outer norm mean", 1.0)
+    check(invstd, ie, ic, m, "generic outer norm invstd", 1e-3)
+    dx, dw, db = ops.outer_norm_bwd(dy.cuda(), x.cuda(), me.cuda(), ie.cuda(), w.cuda(), variant=L.VARIANT_GENERIC)
+    dxe, dwe, dbe = AO.outer_norm_bwd(dy, x, me, ie, w)
+    dxc, dwc, dbc = AO.outer_norm_bwd(dy.double(), x.double(), me.double(), ie.double(), w.double())
+    check(dx, dxe, dxc, m, "generic outer norm dx", 1.0 if dt == torch.float32 else 1e-1)
+    check(dw, dwe, dwc, m, "generic outer norm dw", max(1.0, m ** 0.5))
+    check(db, dbe, dbc, m, "generic outer norm db", max(1.0, m ** 0.5))
+
+
+def test_outer_generic_semantics_and_resnet_shape():
+    """NaN / +-inf columns through the online softmax of the generic family (a leading -inf run, a -inf-only row
+    split, +inf, NaN), and a ResNet-size batch norm ([32*56*56, 64]: far beyond a 16-CTA cluster) through the
+    default dispatch."""
+    dt = torch.bfloat16
+    xs = torch.randn(300, 40).to(dt)
+    xs[7, 1] = float("nan")
+    xs[:, 2] = float("-inf")
+    xs[5, 3] = float("inf")
+    xs[:150, 5] = float("-inf")
+    xs[100:, 6] = float("-inf")
+    for log in (False, True):
+        y = ops.softmax_fwd(xs.cuda(), dim=0, log=log, variant=L.VARIANT_GENERIC)
+        torch.cuda.synchronize()
+        ref = AO.log_softmax_fwd(xs, dim=0) if log else AO.softmax_fwd(xs, dim=0)
+        AO.assert_close(y, ref, 300 * 300, f"generic NaN/Inf columns log={log}")
+        assert torch.isnan(y[:, 1:4]).all() and not torch.isnan(y[:, 0]).any() and not torch.isnan(y[:, 4:]).any()
+    m, c = 32 * 56 * 56, 64
+    x = torch.randn(32, 56, 56, c).to(dt)
+    w, b = torch.randn(c).to(dt), torch.randn(c).to(dt)
+    assert ops.plan_for(L.OP_LAYERNORM_FWD, dt, m, c, flags=L.F_OUTER | L.F_HAS_WEIGHT | L.F_HAS_BIAS)["variant"] == "generic"
+    y, mean, invstd = ops.outer_norm_fwd(x.cuda(), w.cuda(), b.cuda(), 1e-5)
+    ye, me, ie = AO.outer_norm_fwd(x, w, b, 1e-5)
+    AO.assert_close(y, ye, m, "ResNet-size batch norm y")
+    assert torch.allclose(mean.cpu(), me, atol=1e-5) and torch.allclose(invstd.cpu(), ie, rtol=1e-4)
+    dy = torch.randn(32, 56, 56, c).to(dt)
+    dx, dw, db = ops.outer_norm_bwd(dy.cuda(), x.cuda(), me.cuda(), ie.cuda(), w.cuda())
+    dxe, dwe, dbe = AO.outer_norm_bwd(dy, x, me, ie, w)
+    AO.assert_close(dx, dxe, m, "ResNet-size batch norm dx")
+    AO.assert_close(dw, dwe, m, "dweight")
+    AO.assert_close(db, dbe, m, "dbias")
