@@ -13,7 +13,7 @@ import torch
 
 from oracle import aten_oracle as AO
 from oracle import c_oracle as CO
-from tests.util import golden_files, load_golden, make_inputs, ulp_err
+from tests.util import golden_files, load_golden, make_inputs, outer_golden_files, ulp_err
 
 
 def test_tolerance_rule_worked_examples():
@@ -146,3 +146,25 @@ def test_nan_and_inf_semantics():
     assert torch.isnan(y[:3]).all() and torch.isnan(yc[:3]).all()
     assert torch.allclose(y[3].double(), yc[3])
     assert math.isnan(CO.reduce_inner(x, "max")[0].item()) and CO.reduce_inner(x, "fmax")[0].item() == 3.0
+
+
+@pytest.mark.parametrize("path", outer_golden_files(), ids=lambda p: p.split("/")[-1][:-4])
+def test_outer_oracle_matches_golden(path):
+    """The oracle's outer (dim 0) ops against fixtures made by ATen's native kernels: _softmax / _log_softmax
+    (+ backward data) over dim 0, native_batch_norm(_backward) in training mode on [M, C]
+    (tests/golden/make_golden_outer.py)."""
+    dt, m, n, g = load_golden(path)
+    eps = g["eps"]
+    x, dy, w, b = g["x"], g["dy"], g["w"], g["b"]
+    AO.assert_close(AO.softmax_fwd(x, dim=0), g["osm_y"], m * m, "outer softmax y")
+    AO.assert_close(AO.log_softmax_fwd(x, dim=0), g["olsm_y"], m * m, "outer log_softmax y")
+    AO.assert_close(AO.softmax_bwd(dy, g["osm_y"], dim=0), g["osm_dx"], m, "outer softmax dx")
+    AO.assert_close(AO.log_softmax_bwd(dy, g["olsm_y"], dim=0), g["olsm_dx"], m, "outer log_softmax dx")
+    y, mean, invstd = AO.outer_norm_fwd(x, w, b, eps)
+    AO.assert_close(y, g["bn_y"], m, "batch norm y")
+    AO.assert_close(mean, g["bn_mean"], m, "batch norm mean")
+    AO.assert_close(invstd, g["bn_invstd"], m, "batch norm invstd")
+    dx, dw, db = AO.outer_norm_bwd(dy, x, g["bn_mean"], g["bn_invstd"], w)
+    AO.assert_close(dx, g["bn_dx"], m, "batch norm dx")
+    AO.assert_close(dw, g["bn_dw"], m, "batch norm dweight")
+    AO.assert_close(db, g["bn_db"], m, "batch norm dbias")

@@ -17,7 +17,7 @@ from fuser_b200.frontend import FusionDefinition
 from fuser_b200.ir import DataType
 from oracle import aten_oracle as AO
 from oracle import c_oracle as CO
-from tests.util import make_inputs, ulp_err
+from tests.util import load_golden, make_inputs, outer_golden_files, ulp_err
 
 pytestmark = pytest.mark.gpu
 
@@ -424,3 +424,25 @@ def test_outer_generic_semantics_and_resnet_shape():
     AO.assert_close(dx, dxe, m, "ResNet-size batch norm dx")
     AO.assert_close(dw, dwe, m, "dweight")
     AO.assert_close(db, dbe, m, "dbias")
+
+
+@pytest.mark.parametrize("variant", [L.VARIANT_AUTO, L.VARIANT_GENERIC], ids=["auto", "generic"])
+@pytest.mark.parametrize("path", outer_golden_files(), ids=lambda p: p.split("/")[-1][:-4])
+def test_outer_golden_fixtures(path, variant):
+    """The committed ATen-native fixtures of the outer ops (tests/golden/make_golden_outer.py) replayed against
+    the CUDA kernels — persistent and shape-agnostic families."""
+    dt, m, n, g = load_golden(path)
+    x, dy, w, b = (g[k].cuda() for k in ("x", "dy", "w", "b"))
+    kw = dict(variant=variant)
+    AO.assert_close(ops.softmax_fwd(x, dim=0, **kw), g["osm_y"], m * m, "outer softmax y")
+    AO.assert_close(ops.softmax_fwd(x, dim=0, log=True, **kw), g["olsm_y"], m * m, "outer log_softmax y")
+    AO.assert_close(ops.softmax_bwd(dy, g["osm_y"].cuda(), dim=0, **kw), g["osm_dx"], m, "outer softmax dx")
+    AO.assert_close(ops.softmax_bwd(dy, g["olsm_y"].cuda(), dim=0, log=True, **kw), g["olsm_dx"], m, "outer log_softmax dx")
+    y, mean, invstd = ops.outer_norm_fwd(x, w, b, g["eps"], **kw)
+    AO.assert_close(y, g["bn_y"], m, "batch norm y")
+    AO.assert_close(mean, g["bn_mean"], m, "batch norm mean")
+    AO.assert_close(invstd, g["bn_invstd"], m, "batch norm invstd")
+    dx, dw, db = ops.outer_norm_bwd(dy, x, g["bn_mean"].cuda(), g["bn_invstd"].cuda(), w, **kw)
+    AO.assert_close(dx, g["bn_dx"], m, "batch norm dx")
+    AO.assert_close(dw, g["bn_dw"], m, "batch norm dweight")
+    AO.assert_close(db, g["bn_db"], m, "batch norm dbias")

@@ -13,6 +13,11 @@ def golden_files():
     return sorted(glob.glob(os.path.join(GOLDEN_DIR, "norm_*.npz")))
 
 
+def outer_golden_files():
+    """Fixtures of the outer (dim 0) ops: tests/golden/make_golden_outer.py."""
+    return sorted(glob.glob(os.path.join(GOLDEN_DIR, "outer_*.npz")))
+
+
 def load_golden(path):
     name = os.path.basename(path)[: -len(".npz")]
     _, dt_name, shape = name.split("_")
