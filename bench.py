@@ -391,6 +391,88 @@ def cpu_step_fn(kind, dtype):
     return fn
 
 
+def validate_step(step, kind, world, device):
+    """One step checked against the ATen oracle with the validator's tolerances before anything is timed
+    (the reference's benchmarks call fd.validate first: benchmarks/python/test_layernorm_fwd.py:90-95).
+    y / dx rows are independent: above 2^26 elements a row sample is compared (first / middle / last blocks
+    and random rows); dgamma / dbeta are compared over ALL rows (summed over the ranks when row-sharded)."""
+    from oracle import aten_oracle as AO
+
+    x, dy = step.sets[0]
+    w = step.w
+    m, n = x.shape
+    f, b = step.run(0)
+    pend = step.reducer.pending if step.reducer is not None else None  # nccl / deferred peer: this step's handle
+    step.finish()
+    torch.cuda.synchronize(device)
+    sharded_cols = None
+    if world > 1 and kind in ("rmsnorm_fwd_bwd", "layernorm_bwd"):
+        sharded_cols = b[1] if step.collective == "peer-fused" else pend.result()
+    if m * n > (1 << 26):
+        g = torch.Generator().manual_seed(5)
+        rows = torch.unique(torch.cat([torch.arange(0, 64), torch.arange(m // 2, m // 2 + 64), torch.arange(m - 64, m),
+                                       torch.randint(0, m, (64,), generator=g)]))
+    else:
+        rows = torch.arange(m)
+    rd = rows.to(device)
+    xs, dys, wc = x[rd].cpu(), dy[rd].cpu(), w.cpu()
+    checked = []
+
+    def close(actual, expected, red, what):
+        AO.assert_close(actual, expected, red, what)
+        checked.append(what)
+
+    def col_sums(name, actual, local_f32):
+        """column sums: the oracle's fp32 sums of this rank's rows, added over the ranks, cast once."""
+        t = local_f32.to(device)
+        if world > 1:
+            torch.distributed.all_reduce(t)
+        close(actual, t.to(actual.dtype).cpu(), m * world, name)
+
+    if kind == "rmsnorm_fwd_bwd":
+        y, rms = f
+        dx, dw = b[0], b[1]
+        ye, rmse = AO.rms_norm_fwd_python(xs, wc, EPS)
+        close(y[rd], ye, n, "y")
+        close(rms[rd], rmse, n, "rms")
+        dxe, _ = AO.rms_norm_bwd_python(xs, rms[rd].cpu(), dys, wc)
+        close(dx[rd], dxe, n, "dx")
+        if sharded_cols is not None:
+            dw = sharded_cols[0]
+        col_sums("dgamma", dw, (dy.cpu().float() * (x.cpu().float() / rms.cpu())).sum(0))
+    elif kind in ("softmax_fwd_bwd", "softmax_outer_fwd_bwd"):
+        dim = 0 if kind == "softmax_outer_fwd_bwd" else -1
+        (y,), (dx,) = f, b
+        if dim == 0:
+            close(y, AO.softmax_fwd(x.cpu(), dim=0), m * m, "y")
+            close(dx, AO.softmax_bwd(dy.cpu(), y.cpu(), dim=0), m, "dx")
+        else:
+            close(y[rd], AO.softmax_fwd(xs), n * n, "y")
+            close(dx[rd], AO.softmax_bwd(dys, y[rd].cpu()), n, "dx")
+    elif kind == "outer_norm_fwd_bwd":
+        ye, me, ie = AO.outer_norm_fwd(x.cpu(), wc, wc, EPS)
+        close(f[0], ye, m, "y")
+        close(f[1], me, m, "mean")
+        close(f[2], ie, m, "invstd")
+        for name, a, e in zip(("dx", "dgamma", "dbeta"), b, AO.outer_norm_bwd(dy.cpu(), x.cpu(), f[1].cpu(), f[2].cpu(), wc)):
+            close(a, e, m, name)
+    elif kind == "layernorm_bwd":
+        mean, invstd = step.saved[0]
+        dx, cols = b[0], b[1:]
+        if sharded_cols is not None:
+            cols = sharded_cols
+        dxe, _, _ = AO.layer_norm_bwd(dys, xs, mean[rd].cpu(), invstd[rd].cpu(), wc)
+        close(dx[rd], dxe, n, "dx")
+        xc, dyc = x.cpu().float(), dy.cpu().float()
+        col_sums("dgamma", cols[0], (dyc * ((xc - mean.cpu()) * invstd.cpu())).sum(0))
+        col_sums("dbeta", cols[1], dyc.sum(0))
+    else:  # layernorm_fwd
+        for name, a, e in zip(("y", "mean", "invstd"), f, AO.layer_norm_fwd(x.cpu(), wc, wc, EPS)):
+            close(a, e, n, name)
+    return {"oracle": "ATen op-by-op on the host (oracle/aten_oracle.py), validator tolerances", "outputs": checked,
+            "rows_compared": int(rows.numel()), "rows": int(m)}
+
+
 def time_cpu(kind, m, n, dtype, sample_rows, reps, warm=1):
     torch.set_num_threads(os.cpu_count() or 1)
     g = torch.Generator().manual_seed(7)
@@ -424,6 +506,7 @@ def main():
                          "fp32 partial sums, consumed a step later")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-validate", action="store_true", help="skip the oracle check of one step before timing")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200norm" else args.warmup
 
@@ -487,6 +570,11 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+
+    # ---- one step against the oracle before anything is timed (every rank checks its own rows) ----
+    validation = None
+    if not args.no_validate:
+        validation = validate_step(step, kind, world, device)
 
     for i in range(args.warmup):
         step.run(i)
@@ -613,6 +701,7 @@ def main():
                        "pct_of_nominal_8TBs": 100.0 * value / world / 8000.0,
                        "pct_of_measured_peak": 100.0 * value / world / peak,
                        "host_enqueue_us_per_step": host_enqueue_s / args.steps * 1e6},
+            "validated": validation is not None, "validation": validation,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)

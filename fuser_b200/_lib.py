@@ -69,6 +69,7 @@ F_PEER_PUBLISH = 1 << 17
 F_OUTER = 1 << 18
 
 VARIANT_AUTO, VARIANT_GENERIC, VARIANT_TMA, VARIANT_CLUSTER = 0, 1, 2, 3
+FORM_CACHED, FORM_PIPE, FORM_PSMEM, FORM_FUSED_FINISH = 1, 2, 4, 8
 
 EXPORTED_SYMBOLS = [
     "b200norm_abi_version",
@@ -120,7 +121,9 @@ class Plan(C.Structure):
         ("tile_rows", C.c_int32),
         ("smem_bytes", C.c_int32),
         ("n_launches", C.c_int32),
-        ("reserved", C.c_int32 * 3),
+        ("form", C.c_int32),
+        ("groups", C.c_int32),
+        ("chunks", C.c_int32),
         ("workspace_bytes", C.c_uint64),
         ("algorithmic_bytes", C.c_uint64),
     ]
@@ -136,6 +139,11 @@ class Plan(C.Structure):
             "tile_rows": self.tile_rows,
             "smem_bytes": self.smem_bytes,
             "n_launches": self.n_launches,
+            "cached": bool(self.form & FORM_CACHED),
+            "pipe": bool(self.form & FORM_PIPE),
+            "psmem": bool(self.form & FORM_PSMEM),
+            "groups": self.groups,
+            "chunks": self.chunks,
             "workspace_bytes": int(self.workspace_bytes),
             "algorithmic_bytes": int(self.algorithmic_bytes),
         }

@@ -626,6 +626,11 @@ void fill_public_plan(const b200norm_desc& d, const Plan& p, b200norm_plan* out)
   out->tile_rows = p.tile_rows;
   out->smem_bytes = (int32_t)p.smem;
   out->n_launches = p.n_launches;
+  // `psmem` doubles as the pipelined-kernel selector (see ring_kernel_for)
+  out->form = (p.cached ? B200NORM_FORM_CACHED : 0) | (p.pipe ? B200NORM_FORM_PIPE : 0) |
+              ((p.psmem && !p.pipe) ? B200NORM_FORM_PSMEM : 0);
+  out->groups = p.groups;
+  out->chunks = p.ch;
   out->workspace_bytes = p.ws_bytes;
   out->algorithmic_bytes = algorithmic_bytes(d);
 }

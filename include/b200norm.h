@@ -183,6 +183,14 @@ typedef struct {
   int32_t reserved[4];
 } b200norm_desc;
 
+/* plan.form */
+enum {
+  B200NORM_FORM_CACHED = 1,   /* the row (or g / x_hat) stays in registers between the passes   */
+  B200NORM_FORM_PIPE = 2,     /* split-phase reductions pipelined across rows (mbarrier based)  */
+  B200NORM_FORM_PSMEM = 4,    /* per-column parameters staged in shared memory as fp32          */
+  B200NORM_FORM_FUSED_FINISH = 8 /* dweight / dbias finished inside the backward (grid barrier)   */
+};
+
 /* Tensor argument: same fields as CutlassCompiledKernel::TensorArg
  * (cutlass_compiled_kernel.h:69-74) with the arrays held inline. Strides are in
  * elements. The innermost stride must be 1 (or the extent 1). */
@@ -208,7 +216,9 @@ typedef struct {
   int32_t tile_rows;     /* rows per bulk copy                               */
   int32_t smem_bytes;    /* dynamic shared memory per CTA                    */
   int32_t n_launches;    /* kernels enqueued per b200norm_launch             */
-  int32_t reserved[3];
+  int32_t form;          /* B200NORM_FORM_* bits: which flavour of the ring kernel */
+  int32_t groups;        /* consumer groups per CTA (each with its own ring)  */
+  int32_t chunks;        /* 16-byte chunks per thread (0 = looping form)      */
   uint64_t workspace_bytes;
   uint64_t algorithmic_bytes; /* the reference's *_iobytes for this desc      */
 } b200norm_plan;

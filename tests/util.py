@@ -62,3 +62,36 @@ def make_inputs(m, n, dtype, seed=0, device="cpu"):
     w = torch.randn(n, generator=g).to(dtype)
     b = torch.randn(n, generator=g).to(dtype)
     return [t.to(device) for t in (x, dy, w, b)]
+
+
+def sample_rows(m: int, block: int = 64, n_random: int = 64, seed: int = 0) -> torch.Tensor:
+    """Row indices for an oracle comparison at sizes the CPU oracle cannot take whole: the first, middle and
+    last `block` rows (first ring fill, steady state, ragged tail / pool tiles of the dynamic schedule) plus
+    `n_random` rows spread over the matrix. Every row is independent for y / dx, so a row sample is an exact
+    check of those rows."""
+    if m <= 3 * block + n_random:
+        return torch.arange(m)
+    g = torch.Generator().manual_seed(seed)
+    mid = m // 2
+    idx = torch.cat([torch.arange(0, block), torch.arange(mid, mid + block), torch.arange(m - block, m),
+                     torch.randint(0, m, (n_random,), generator=g)])
+    return torch.unique(idx)
+
+
+def col_sums_fp64(dy: torch.Tensor, x: torch.Tensor, mean, invstd, block: int = 2048):
+    """fp64 column sums of the norm backward over ALL rows, in row blocks (bounded memory):
+    dw = sum_rows dy * (x - mean) * invstd, db = sum_rows dy. CPU tensors; mean may be None (RMSNorm)."""
+    m, n = x.shape
+    dw = torch.zeros(n, dtype=torch.float64)
+    db = torch.zeros(n, dtype=torch.float64)
+    inv = invstd.reshape(m, 1).double()
+    mu = mean.reshape(m, 1).double() if mean is not None else None
+    for a in range(0, m, block):
+        b = min(m, a + block)
+        dyb = dy[a:b].double()
+        xb = x[a:b].double()
+        if mu is not None:
+            xb = xb - mu[a:b]
+        dw += (dyb * (xb * inv[a:b])).sum(0)
+        db += dyb.sum(0)
+    return dw, db
