@@ -81,6 +81,7 @@ EXPORTED_SYMBOLS = [
     "b200norm_variant_name",
     "b200norm_device_info",
     "b200norm_register_peers",
+    "b200norm_peer_exchange_bytes",
     "b200norm_debug_set_timeline",
 ]
 
@@ -200,6 +201,8 @@ def load():
     lib.b200norm_device_info.restype = C.c_int
     lib.b200norm_register_peers.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_size_t]
     lib.b200norm_register_peers.restype = C.c_int
+    lib.b200norm_peer_exchange_bytes.argtypes = [C.c_int, C.c_int64]
+    lib.b200norm_peer_exchange_bytes.restype = C.c_size_t
     lib.b200norm_debug_set_timeline.argtypes = [C.c_void_p]
     lib.b200norm_debug_set_timeline.restype = None
     if lib.b200norm_abi_version() != ABI_VERSION:
@@ -260,6 +263,14 @@ def register_peers(world: int, rank: int, ptrs, nbytes: int) -> None:
     rc = lib.b200norm_register_peers(world, rank, arr, nbytes)
     if rc != 0:
         raise B200NormError(rc, lib.b200norm_last_error().decode())
+
+
+def peer_exchange_bytes(world: int, max_floats: int) -> int:
+    """Size of one peer exchange buffer for segments of up to ``max_floats`` = K*N column sums."""
+    n = int(load().b200norm_peer_exchange_bytes(world, max_floats))
+    if n == 0:
+        raise B200NormError(ERR_BAD_ARG, f"peer_exchange_bytes({world}, {max_floats})")
+    return n
 
 
 def set_timeline(device_ptr) -> None:

@@ -9,6 +9,7 @@
 #include "../../include/b200norm.h"
 
 #include <cuda_runtime.h>
+#include <unistd.h>  // environ
 
 #include <atomic>
 #include <cstdarg>
@@ -33,15 +34,18 @@ std::atomic<unsigned long long*> g_timeline{nullptr};
 
 // peer-memory exchange of the row-sharded backward (b200norm_register_peers)
 struct PeerState {
-  std::mutex mu;
   int world = 0;
   int rank = 0;
   void* ptrs[kMaxPeers] = {};
   size_t bytes = 0;
-  uint32_t epoch = 0;     // publishes so far; identical on every rank because all ranks issue the same sequence
-  uint32_t combined = 0;  // epochs whose sums have been combined (in-kernel or by OP_PEER_COMBINE)
+  uint32_t cap_floats = 0;    // K*N capacity of one slot
+  uint32_t ll_off = 0;        // byte offset of the LL region (behind the header and the two publish slots)
+  uint32_t ll_parity_bytes = 0;  // bytes of one parity of the LL region: world * cap_floats * 8
+  uint32_t ll_epoch = 0;      // fused (PEER_REDUCE) launches so far; identical on every rank (same launch sequence)
+  uint32_t epoch = 0;         // publishes so far (PEER_PUBLISH)
+  uint32_t combined = 0;      // publishes whose sums have been combined by OP_PEER_COMBINE
+  uint64_t timeout_ns = 0;    // in-kernel wait for a peer: 0 = for ever
 };
-PeerState g_peers;
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -59,27 +63,102 @@ struct DeviceInfo {
   int cc_minor = 0;
 };
 
-const DeviceInfo& device_info() {
-  static DeviceInfo info;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    int n = 0;
-    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
-      (void)cudaGetLastError();
-      return;
-    }
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) {
-      (void)cudaGetLastError();
-      return;
-    }
-    info.has_device = 1;
-    cudaDeviceGetAttribute(&info.sm_count, cudaDevAttrMultiProcessorCount, dev);
-    cudaDeviceGetAttribute(&info.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    cudaDeviceGetAttribute(&info.cc_major, cudaDevAttrComputeCapabilityMajor, dev);
-    cudaDeviceGetAttribute(&info.cc_minor, cudaDevAttrComputeCapabilityMinor, dev);
+// Everything the library remembers is per DEVICE: function attributes and occupancy answers belong to a
+// device context, one process may drive several devices (NormExecutor launches under a device guard), and the
+// peer exchange buffers are registered for the device that was current at registration.
+struct DeviceCtx {
+  int ordinal = -1;
+  DeviceInfo info;
+  std::mutex mu;  // guards the maps below
+  std::unordered_map<const void*, std::pair<int, int>> attr_done;  // kernel -> (max smem set, nonportable cluster set)
+  std::unordered_map<uint64_t, int> cluster_cache;                 // (kernel, block, smem, C) -> resident clusters
+  std::unordered_map<const void*, int> bad_modes;                  // kernel -> bit0: fused finish refused, bit1: PDL refused
+  // Kernels that spin on an in-kernel grid barrier need their whole grid resident. On ONE stream that holds by
+  // construction (see launch_typed); two such kernels on two streams could each get a part of the SMs and wait
+  // for ever. They are therefore serialised across streams: a barrier kernel launched on another stream than the
+  // previous one first waits for everything enqueued on that stream so far.
+  std::mutex barrier_mu;
+  cudaStream_t barrier_stream = nullptr;
+  bool barrier_seen = false;
+  cudaEvent_t barrier_event = nullptr;
+  std::mutex peer_mu;  // held across a PEER launch: epochs advance in launch order and only on success
+  PeerState peers;
+};
+
+constexpr int kMaxDevices = 64;
+
+DeviceCtx& device_ctx() {
+  static DeviceCtx nominal;  // no device: plans for a nominal B200
+  static DeviceCtx table[kMaxDevices];
+  static std::once_flag once[kMaxDevices];
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    (void)cudaGetLastError();
+    return nominal;
+  }
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) {
+    (void)cudaGetLastError();
+    return nominal;
+  }
+  std::call_once(once[dev], [dev] {
+    DeviceCtx& c = table[dev];
+    c.ordinal = dev;
+    c.info.has_device = 1;
+    cudaDeviceGetAttribute(&c.info.sm_count, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&c.info.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    cudaDeviceGetAttribute(&c.info.cc_major, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&c.info.cc_minor, cudaDevAttrComputeCapabilityMinor, dev);
   });
-  return info;
+  return table[dev];
+}
+
+const DeviceInfo& device_info() { return device_ctx().info; }
+
+// Tuning overrides (like NVFUSER_ENABLE / NVFUSER_DISABLE options), all unset in production:
+// B200NORM_TPR, _GROUPS, _DEPTH (stages per group), _TILE_ROWS, _CLUSTER, _BWD_REREAD, _PIPE, _NO_PIPE, _NO_PSMEM,
+// _NO_FUSED_FINISH, _NO_PDL, _COOP, _STATIC, _POOL, _DEBUG, _PEER_TIMEOUT_S. They are read with ONE scan of the
+// environment per query / launch (ten getenv calls were ten scans).
+struct Knobs {
+  int tpr = 0, groups = 0, depth = 0, tile_rows = 0, cluster = 0, bwd_reread = 0, pipe = 0, no_pipe = 0, no_psmem = 0;
+  int no_fused_finish = 0, no_pdl = 0, coop = 0, static_sched = 0, pool = 0, debug = 0, peer_timeout_s = -1;
+  int ln_pipe = 0, no_ln_pipe = 0, no_guard = 0;
+  bool any = false;
+  uint64_t hash = 0;  // of the planner-relevant values (plan cache key)
+};
+
+Knobs read_knobs() {
+  Knobs k;
+  static const struct { const char* name; int Knobs::*field; } table[] = {
+      {"TPR", &Knobs::tpr}, {"GROUPS", &Knobs::groups}, {"DEPTH", &Knobs::depth}, {"TILE_ROWS", &Knobs::tile_rows},
+      {"CLUSTER", &Knobs::cluster}, {"BWD_REREAD", &Knobs::bwd_reread}, {"PIPE", &Knobs::pipe}, {"NO_PIPE", &Knobs::no_pipe},
+      {"NO_PSMEM", &Knobs::no_psmem}, {"NO_FUSED_FINISH", &Knobs::no_fused_finish}, {"NO_PDL", &Knobs::no_pdl},
+      {"COOP", &Knobs::coop}, {"STATIC", &Knobs::static_sched}, {"POOL", &Knobs::pool}, {"DEBUG", &Knobs::debug},
+      {"PEER_TIMEOUT_S", &Knobs::peer_timeout_s}, {"LN_PIPE", &Knobs::ln_pipe}, {"NO_LN_PIPE", &Knobs::no_ln_pipe},
+      {"NO_GUARD", &Knobs::no_guard}};
+  if (::environ == nullptr) return k;
+  for (char** e = ::environ; *e != nullptr; ++e) {
+    if (strncmp(*e, "B200NORM_", 9) != 0) continue;
+    const char* name = *e + 9;
+    const char* eq = strchr(name, '=');
+    if (eq == nullptr || eq[1] == 0) continue;
+    for (const auto& t : table) {
+      const size_t len = strlen(t.name);
+      if ((size_t)(eq - name) == len && strncmp(name, t.name, len) == 0) {
+        k.*(t.field) = atoi(eq + 1);
+        k.any = true;
+        break;
+      }
+    }
+  }
+  if (k.any) {
+    const int vals[] = {k.tpr, k.groups, k.depth, k.tile_rows, k.cluster, k.bwd_reread, k.pipe, k.no_pipe, k.no_psmem,
+                        k.ln_pipe, k.no_ln_pipe};
+    uint64_t h = 1469598103934665603ull;
+    for (int v : vals) h = (h ^ (uint64_t)(uint32_t)v) * 1099511628211ull;
+    k.hash = h | 1ull;
+  }
+  return k;
 }
 
 int elem_size(int dt) { return dt == B200NORM_DT_F32 ? 4 : 2; }
@@ -189,12 +268,10 @@ RingKernel ring_kernel_for<__half>(int op, int tpr, int ch, bool cached, bool ps
   return is_norm_bwd(op) ? ring_bwd_kernel_f16(op, tpr, ch, cached) : ring_fwd_kernel_f16(op, tpr, ch, psmem);
 }
 
-// cudaFuncSetAttribute is paid once per (kernel, smem size, cluster class), not per launch.
-int prepare_ring_kernel(RingKernel k, int smem, int cluster) {
-  static std::mutex mu;
-  static std::unordered_map<const void*, std::pair<int, int>> done;  // kernel -> (max smem set, nonportable set)
-  std::lock_guard<std::mutex> lock(mu);
-  auto& st = done[(const void*)k];
+// cudaFuncSetAttribute is paid once per (device, kernel, smem size, cluster class), not per launch.
+int prepare_ring_kernel(DeviceCtx& ctx, RingKernel k, int smem, int cluster) {
+  std::lock_guard<std::mutex> lock(ctx.mu);
+  auto& st = ctx.attr_done[(const void*)k];
   if (smem > st.first) {
     cudaError_t err = cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (err != cudaSuccess) return fail(B200NORM_ERR_CUDA + (int)err, "smem attr: %s", cudaGetErrorString(err));
@@ -222,22 +299,21 @@ RingKernel ring_kernel_any(int dt, int op, int tpr, int ch, bool cached, bool ps
 // clusters fit 148 SMs). The ring kernels are persistent, so launching more clusters than
 // fit would serialise a second wave. The reference asks the same question before a
 // cluster launch (csrc/runtime/executor.cpp:1329-1340).
-int max_active_clusters(const DeviceInfo& dev, RingKernel k, int block, int smem, int C) {
+int max_active_clusters(DeviceCtx& ctx, RingKernel k, int block, int smem, int C) {
+  const DeviceInfo& dev = ctx.info;
   if (C <= 1) return dev.sm_count;
   if (!dev.has_device || k == nullptr) {
     return 8 * (18 / C);  // nominal B200: 8 GPCs, >= 18 usable SMs each
   }
-  static std::mutex mu;
-  static std::unordered_map<uint64_t, int> cache;
   const uint64_t key = (reinterpret_cast<uint64_t>((const void*)k) << 8) ^ ((uint64_t)block << 40) ^
                        ((uint64_t)smem << 4) ^ (uint64_t)C;
   {
-    std::lock_guard<std::mutex> lock(mu);
-    auto it = cache.find(key);
-    if (it != cache.end()) return it->second;
+    std::lock_guard<std::mutex> lock(ctx.mu);
+    auto it = ctx.cluster_cache.find(key);
+    if (it != ctx.cluster_cache.end()) return it->second;
   }
   int n = 0;
-  if (prepare_ring_kernel(k, smem, C) == B200NORM_OK) {
+  if (prepare_ring_kernel(ctx, k, smem, C) == B200NORM_OK) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)(dev.sm_count / C * C));
@@ -256,8 +332,8 @@ int max_active_clusters(const DeviceInfo& dev, RingKernel k, int block, int smem
     }
   }
   if (n <= 0) n = 8 * (18 / C) > 0 ? 8 * (18 / C) : 1;
-  std::lock_guard<std::mutex> lock(mu);
-  cache[key] = n;
+  std::lock_guard<std::mutex> lock(ctx.mu);
+  ctx.cluster_cache[key] = n;
   return n;
 }
 
@@ -270,14 +346,6 @@ constexpr int kBwdRereadCH_LN = 3;
 constexpr int kMaxStages = 32;
 const int kTprMenu[] = {32, 64, 128, 256, 512};
 
-// Tuning overrides (like NVFUSER_ENABLE/DISABLE options): B200NORM_TPR, B200NORM_GROUPS,
-// B200NORM_DEPTH (stages per group), B200NORM_TILE_ROWS, B200NORM_CLUSTER, B200NORM_BWD_REREAD.
-// Unset = planner's choice.
-int env_int(const char* name) {
-  const char* v = getenv(name);
-  return (v != nullptr && *v != 0) ? atoi(v) : 0;
-}
-
 int generic_nsplit(int64_t rows) {
   int64_t n = rows / 64;
   if (n < 1) n = 1;
@@ -286,7 +354,8 @@ int generic_nsplit(int64_t rows) {
 }
 
 // Try to build a ring plan with cluster size C. Returns false if infeasible.
-bool try_ring_plan(const b200norm_desc& d, const DeviceInfo& dev, int C, bool rows_contiguous, Plan* out) {
+bool try_ring_plan(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, int C, bool rows_contiguous, Plan* out) {
+  const DeviceInfo& dev = ctx.info;
   const int es = elem_size(d.io_dtype);
   const int vec = 16 / es;
   const int64_t N = d.cols;
@@ -308,7 +377,7 @@ bool try_ring_plan(const b200norm_desc& d, const DeviceInfo& dev, int C, bool ro
   Plan p;
   int tpr = 0, ch = 0;
   bool cached = true;
-  const int forced_tpr = env_int("B200NORM_TPR");
+  const int forced_tpr = kn.tpr;
   auto pick = [&](int max_ch) {
     for (int t : kTprMenu) {
       if (forced_tpr != 0 && t != forced_tpr) continue;
@@ -321,7 +390,7 @@ bool try_ring_plan(const b200norm_desc& d, const DeviceInfo& dev, int C, bool ro
     return false;
   };
   if (bwd) {
-    const bool force_reread = env_int("B200NORM_BWD_REREAD") != 0;
+    const bool force_reread = kn.bwd_reread != 0;
     if (force_reread || !pick(kBwdCacheCH)) {
       cached = false;
       if (!pick(ln_bwd ? kBwdRereadCH_LN : kBwdRereadCH_RMS)) return false;  // split the row further
@@ -349,7 +418,7 @@ bool try_ring_plan(const b200norm_desc& d, const DeviceInfo& dev, int C, bool ro
       }
     } else if (tpr == 512 && forced_tpr == 0 && nchunks <= 256 * kFwdWideCH &&
                !(d.op == B200NORM_OP_RMSNORM_FWD && es == 2 && (nchunks + 255) / 256 == 6 &&
-                 env_int("B200NORM_NO_PIPE") == 0)) {
+                 kn.no_pipe == 0)) {
       // (16-bit RMSNorm forward at six chunks per thread — N = 12288 — keeps the single 512-thread
       // group: its pipelined kernel beats two 256-thread groups there, 252 vs 275 us; at five chunks
       // (N = 10240: 109 vs 123 us) and at N = 16384 (162 vs 178 us) the register-resident kernels win)
@@ -364,7 +433,7 @@ bool try_ring_plan(const b200norm_desc& d, const DeviceInfo& dev, int C, bool ro
   }
   int groups = kConsumerThreads / tpr;
   if (groups > 8) groups = 8;  // named-barrier ids / diminishing returns for warp-sized groups
-  if (int gmax = env_int("B200NORM_GROUPS")) {
+  if (int gmax = kn.groups) {
     if (gmax >= 1 && gmax < groups) groups = gmax;
   }
 
@@ -395,7 +464,7 @@ bool try_ring_plan(const b200norm_desc& d, const DeviceInfo& dev, int C, bool ro
     const int64_t budget = (int64_t)dev.smem_optin - 4096;
     if (budget / stage2 / groups >= 3 && ceil_div64(d.rows, 2) >= (int64_t)dev.sm_count * groups * 2) tile_rows = 2;
   }
-  if (int tr = env_int("B200NORM_TILE_ROWS")) {
+  if (int tr = kn.tile_rows) {
     if (C == 1 && rows_contiguous && tr >= 1 && tr <= 64) tile_rows = tr;
   }
   p.tile_rows = tile_rows;
@@ -410,7 +479,7 @@ bool try_ring_plan(const b200norm_desc& d, const DeviceInfo& dev, int C, bool ro
   // C1 16 % — 16.4 vs 14.1 us; not beyond 8192 columns: at N = 12288 the 96 KB of staged parameters
   // and their four LDS per chunk cost 10 % — 378 vs 342 us)
   bool want_psmem = d.op == B200NORM_OP_LAYERNORM_FWD && ch > 0 && es == 2 && slice_cols <= 8192 &&
-                    env_int("B200NORM_NO_PSMEM") == 0;
+                    kn.no_psmem == 0;
   const uint32_t param_bytes = align_up(2u * (uint32_t)slice_cols * 4u, 128);
 
   // Ring depth D (stages per group); the ring is group-major, stage (g*D + s).
@@ -443,7 +512,7 @@ bool try_ring_plan(const b200norm_desc& d, const DeviceInfo& dev, int C, bool ro
     }
     if (depth < 2) return false;
     if (depth > 4) depth = 4;  // deeper rings only scatter the DRAM streams (measured: C3 fwd 87% at 6, 93% at 3)
-    if (int dd = env_int("B200NORM_DEPTH")) {
+    if (int dd = kn.depth) {
       if (dd >= 1 && dd <= max_stages / groups) depth = dd;
     }
     p.stages = depth * groups;
@@ -457,16 +526,16 @@ bool try_ring_plan(const b200norm_desc& d, const DeviceInfo& dev, int C, bool ro
   // first pass: C5 335 -> 320 us) and fp32 rows ([16384,8192] 273 -> 248 us); the 16-bit
   // single-CTA case is bound by instruction issue, not by the reduction latency, and loses 4 %
   // (C4 420 -> 440 us), so it keeps the plain kernel. B200NORM_PIPE=1 / B200NORM_NO_PIPE=1 force it.
-  p.pipe = bwd && !cached && tile_rows == 1 && tpr >= 64 && env_int("B200NORM_NO_PIPE") == 0 &&
-           (C > 1 || es == 4 || env_int("B200NORM_PIPE") != 0);
+  p.pipe = bwd && !cached && tile_rows == 1 && tpr >= 64 && kn.no_pipe == 0 &&
+           (C > 1 || es == 4 || kn.pipe != 0);
   // RMSNorm forward over a cluster: the same pipeline (the row is read twice from its stage instead
   // of being held in registers, so the next row's sum of squares overlaps the DSMEM exchange)
   // ... and for rows wide enough to need one 512-thread group per CTA; with several groups per
   // CTA the groups already overlap each other and the second smem pass only costs (N = 8192: 85 vs 95 us).
   // (16-bit only: the fp32 single-group kernel is at the roofline already, 163 vs 182 us at N = 8192)
   if (d.op == B200NORM_OP_RMSNORM_FWD && !add &&
-      (C > 1 || (tpr == 512 && es == 2 && ch == 3 && (nchunks + 255) / 256 == 6) || env_int("B200NORM_PIPE") != 0) && ch > 0 &&
-      tile_rows == 1 && tpr >= 64 && (ch <= 4 || tpr >= 256) && env_int("B200NORM_NO_PIPE") == 0) {
+      (C > 1 || (tpr == 512 && es == 2 && ch == 3 && (nchunks + 255) / 256 == 6) || kn.pipe != 0) && ch > 0 &&
+      tile_rows == 1 && tpr >= 64 && (ch <= 4 || tpr >= 256) && kn.no_pipe == 0) {
     p.pipe = true;
   }
   if (p.pipe) p.psmem = true;  // kernel-table selector, see ring_kernel_for
@@ -479,7 +548,7 @@ bool try_ring_plan(const b200norm_desc& d, const DeviceInfo& dev, int C, bool ro
   p.smem = p.off_ring + ring_bytes;
 
   const int64_t ntiles = ceil_div64(d.rows, tile_rows);
-  int64_t nclusters = max_active_clusters(dev, ring_kernel_any(d.io_dtype, d.op, tpr, ch, cached, p.psmem, add), p.block,
+  int64_t nclusters = max_active_clusters(ctx, ring_kernel_any(d.io_dtype, d.op, tpr, ch, cached, p.psmem, add), p.block,
                                           (int)p.smem, C);
   if (nclusters > ntiles) nclusters = ntiles;
   if (nclusters < 1) nclusters = 1;
@@ -491,8 +560,8 @@ bool try_ring_plan(const b200norm_desc& d, const DeviceInfo& dev, int C, bool ro
   return true;
 }
 
-int make_plan(const b200norm_desc& d, bool aligned, bool rows_contiguous, Plan* out) {
-  const DeviceInfo& dev = device_info();
+int make_plan_uncached(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, bool aligned, bool rows_contiguous, Plan* out) {
+  const DeviceInfo& dev = ctx.info;
   Plan p;
   const bool bwd = is_norm_bwd(d.op);
   const bool want_cols = bwd && (d.flags & (B200NORM_F_OUT_DW | B200NORM_F_OUT_DB));
@@ -509,7 +578,7 @@ int make_plan(const b200norm_desc& d, bool aligned, bool rows_contiguous, Plan* 
 
   bool ring_ok = false;
   if (is_row_op(d.op) && aligned && d.variant != B200NORM_VARIANT_GENERIC && d.rows > 0 && d.cols > 0) {
-    const int forced_c = d.cluster_size != 0 ? d.cluster_size : env_int("B200NORM_CLUSTER");
+    const int forced_c = d.cluster_size != 0 ? d.cluster_size : kn.cluster;
     static const int cs[] = {1, 2, 4, 8, 16};
     Plan best;
     for (int C : cs) {
@@ -517,7 +586,7 @@ int make_plan(const b200norm_desc& d, bool aligned, bool rows_contiguous, Plan* 
       if (forced_c == 0 && d.variant == B200NORM_VARIANT_TMA && C != 1) continue;
       if (forced_c == 0 && d.variant == B200NORM_VARIANT_CLUSTER && C == 1) continue;
       Plan cand;
-      if (!try_ring_plan(d, dev, C, rows_contiguous, &cand)) continue;
+      if (!try_ring_plan(d, ctx, kn, C, rows_contiguous, &cand)) continue;
       if (!ring_ok) {
         best = cand;
         ring_ok = true;
@@ -569,6 +638,60 @@ int make_plan(const b200norm_desc& d, bool aligned, bool rows_contiguous, Plan* 
   return B200NORM_OK;
 }
 
+// The plan of a (desc, alignment, device, knobs) tuple never changes: the executor asks twice per launch
+// (workspace size, then the launch itself), so the answer is cached (the role of
+// KernelExecutor::executor_entry_lookup_, csrc/runtime/executor.cpp:1055-1077).
+struct PlanKey {
+  int32_t op, dt, variant, cluster, dev;
+  uint32_t flags;
+  int64_t rows, cols;
+  uint64_t knobs;
+  int32_t aligned, contiguous;
+  bool operator==(const PlanKey& o) const { return memcmp(this, &o, sizeof(PlanKey)) == 0; }
+};
+struct PlanKeyHash {
+  size_t operator()(const PlanKey& k) const {
+    const uint64_t* w = reinterpret_cast<const uint64_t*>(&k);
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < sizeof(PlanKey) / 8; ++i) h = (h ^ w[i]) * 1099511628211ull;
+    return (size_t)h;
+  }
+};
+static_assert(sizeof(PlanKey) % 8 == 0, "PlanKey is hashed as 64-bit words");
+
+int make_plan(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, bool aligned, bool rows_contiguous, Plan* out) {
+  static std::mutex mu;
+  static std::unordered_map<PlanKey, Plan, PlanKeyHash> cache;
+  PlanKey key;
+  memset(&key, 0, sizeof(key));
+  key.op = d.op;
+  key.dt = d.io_dtype;
+  key.variant = d.variant;
+  key.cluster = d.cluster_size;
+  key.dev = ctx.ordinal;
+  key.flags = d.flags;
+  key.rows = d.rows;
+  key.cols = d.cols;
+  key.knobs = kn.hash;
+  key.aligned = aligned ? 1 : 0;
+  key.contiguous = rows_contiguous ? 1 : 0;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      *out = it->second;
+      return B200NORM_OK;
+    }
+  }
+  const int rc = make_plan_uncached(d, ctx, kn, aligned, rows_contiguous, out);
+  if (rc == B200NORM_OK) {
+    std::lock_guard<std::mutex> lock(mu);
+    if (cache.size() > 4096) cache.clear();
+    cache[key] = *out;
+  }
+  return rc;
+}
+
 OuterArgs outer_args_from(const b200norm_desc& d) {
   const DeviceInfo& dev = device_info();
   OuterArgs a;
@@ -580,7 +703,7 @@ OuterArgs outer_args_from(const b200norm_desc& d) {
   a.norm = (d.op == B200NORM_OP_LAYERNORM_FWD || d.op == B200NORM_OP_LAYERNORM_BWD) ? 1 : 0;
   a.eps = d.eps;
   a.round_sum = (d.flags & B200NORM_F_ROUND_ROWSUM) ? 1 : 0;
-  a.cluster_forced = d.cluster_size != 0 ? d.cluster_size : env_int("B200NORM_CLUSTER");
+  a.cluster_forced = d.cluster_size != 0 ? d.cluster_size : read_knobs().cluster;
   a.force_generic = d.variant == B200NORM_VARIANT_GENERIC ? 1 : 0;
   a.force_persistent = (d.variant == B200NORM_VARIANT_TMA || d.variant == B200NORM_VARIANT_CLUSTER) ? 1 : 0;
   a.has_device = dev.has_device;
@@ -635,6 +758,28 @@ void fill_public_plan(const b200norm_desc& d, const Plan& p, b200norm_plan* out)
   out->algorithmic_bytes = algorithmic_bytes(d);
 }
 
+// See launch_typed: serialise kernels with an in-kernel grid barrier across the streams of this process.
+// Free on a single stream (nothing is recorded or waited for); on a stream switch the new stream waits for
+// everything enqueued so far on the previous one. Skipped while either stream is being captured into a CUDA
+// graph (an event of one capture must not leak into another stream): graphs replayed concurrently on several
+// streams need B200NORM_COOP=1.
+void barrier_guard(DeviceCtx& ctx, cudaStream_t stream) {
+  std::lock_guard<std::mutex> lock(ctx.barrier_mu);
+  if (ctx.barrier_seen && ctx.barrier_stream != stream) {
+    cudaStreamCaptureStatus c0 = cudaStreamCaptureStatusNone, c1 = cudaStreamCaptureStatusNone;
+    const bool ok0 = cudaStreamIsCapturing(ctx.barrier_stream, &c0) == cudaSuccess;
+    const bool ok1 = cudaStreamIsCapturing(stream, &c1) == cudaSuccess;
+    if (ok0 && ok1 && c0 == cudaStreamCaptureStatusNone && c1 == cudaStreamCaptureStatusNone) {
+      if (ctx.barrier_event == nullptr) cudaEventCreateWithFlags(&ctx.barrier_event, cudaEventDisableTiming);
+      if (ctx.barrier_event != nullptr && cudaEventRecord(ctx.barrier_event, ctx.barrier_stream) == cudaSuccess)
+        cudaStreamWaitEvent(stream, ctx.barrier_event, 0);
+    }
+    (void)cudaGetLastError();  // a destroyed predecessor stream has nothing left to wait for
+  }
+  ctx.barrier_stream = stream;
+  ctx.barrier_seen = true;
+}
+
 template <typename T>
 void launch_finalize(const float* partials, int nparts, int K, int N, void* out_a, void* out_b, float* out_f32,
                      cudaStream_t stream) {
@@ -665,8 +810,8 @@ RingKernel generic_kernel_for(int op) {
 }
 
 template <typename T>
-int launch_typed(const b200norm_desc& d, const Plan& plan, RowParams& rp, void* dw, void* db, float* sums_f32,
-                 void* ws_header, cudaStream_t stream) {
+int launch_typed(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, const Plan& plan, RowParams& rp, void* dw,
+                 void* db, float* sums_f32, void* ws_header, cudaStream_t stream) {
   const bool want_cols = is_norm_bwd(d.op) && (d.flags & (B200NORM_F_OUT_DW | B200NORM_F_OUT_DB));
   const int K = partial_k(d.op);
   cudaError_t err;
@@ -677,20 +822,19 @@ int launch_typed(const b200norm_desc& d, const Plan& plan, RowParams& rp, void* 
     if (d.op == B200NORM_OP_PEER_COMBINE) {
       PeerCombineParams q;
       memset(&q, 0, sizeof(q));
-      {
-        std::lock_guard<std::mutex> lock(g_peers.mu);
-        if (g_peers.world < 1) return fail(B200NORM_ERR_BAD_ARG, "PEER_COMBINE without b200norm_register_peers");
-        if (g_peers.combined >= g_peers.epoch) return fail(B200NORM_ERR_BAD_ARG, "PEER_COMBINE: nothing published");
-        const size_t need = (size_t)kPeerHeaderBytes + 2u * (size_t)d.rows * (size_t)d.cols * 4u;
-        if (need > g_peers.bytes || d.cols % 4 != 0)
-          return fail(B200NORM_ERR_WORKSPACE, "PEER_COMBINE: [%lld,%lld] does not match the exchange buffers",
-                      (long long)d.rows, (long long)d.cols);
-        q.world = g_peers.world;
-        q.rank = g_peers.rank;
-        for (int r = 0; r < g_peers.world; ++r) q.xchg[r] = static_cast<uint8_t*>(g_peers.ptrs[r]);
-        q.epoch = ++g_peers.combined;
-        q.slot_floats = (uint32_t)((g_peers.bytes - kPeerHeaderBytes) / 8 / 4 * 4);
-      }
+      std::lock_guard<std::mutex> plock(ctx.peer_mu);  // held across the launch: combines pair up with publishes in order
+      PeerState& ps = ctx.peers;
+      if (ps.world < 1) return fail(B200NORM_ERR_BAD_ARG, "PEER_COMBINE without b200norm_register_peers");
+      if (ps.combined >= ps.epoch) return fail(B200NORM_ERR_BAD_ARG, "PEER_COMBINE: nothing published");
+      if ((uint64_t)d.rows * (uint64_t)d.cols > ps.cap_floats || d.cols % 4 != 0)
+        return fail(B200NORM_ERR_WORKSPACE, "PEER_COMBINE: [%lld,%lld] does not match the exchange buffers",
+                    (long long)d.rows, (long long)d.cols);
+      q.world = ps.world;
+      q.rank = ps.rank;
+      for (int r = 0; r < ps.world; ++r) q.xchg[r] = static_cast<uint8_t*>(ps.ptrs[r]);
+      q.epoch = ps.combined + 1;
+      q.slot_floats = ps.cap_floats;
+      q.timeout_ns = ps.timeout_ns;
       q.K = (int32_t)d.rows;
       q.N = (int32_t)d.cols;
       q.out_a = dw;
@@ -699,7 +843,11 @@ int launch_typed(const b200norm_desc& d, const Plan& plan, RowParams& rp, void* 
       if (ncta > 32) ncta = 32;
       if (ncta < 1) ncta = 1;
       peer_combine_kernel<T><<<ncta, 512, 0, stream>>>(q);
+      err = cudaGetLastError();
+      if (err != cudaSuccess) return fail(B200NORM_ERR_CUDA + (int)err, "launch failed: %s", cudaGetErrorString(err));
+      ps.combined += 1;  // only a combine that was enqueued counts
       g_launches++;
+      return B200NORM_OK;
     } else if (d.op == B200NORM_OP_REDUCE_OUTER) {
       dim3 grid((unsigned)ceil_div64(d.cols, 128), (unsigned)plan.nparts);
       generic_colsum_kernel<T, 0><<<grid, 128, 0, stream>>>(rp, plan.rows_per_split);
@@ -736,48 +884,50 @@ int launch_typed(const b200norm_desc& d, const Plan& plan, RowParams& rp, void* 
   if (k == nullptr)
     return fail(B200NORM_ERR_UNSUPPORTED, "no ring kernel for op %d tpr %d ch %d", d.op, plan.tpr, plan.ch);
   {
-    int rc = prepare_ring_kernel(k, (int)plan.smem, plan.cluster);
+    int rc = prepare_ring_kernel(ctx, k, (int)plan.smem, plan.cluster);
     if (rc != B200NORM_OK) return rc;
   }
   // Launch attributes: the cluster shape; programmatic dependent launch (the kernel's barrier
   // setup overlaps its predecessor's tail — every ring kernel calls griddepcontrol.wait before
-  // its first global access); and, for a backward that produces dgamma / dbeta, a cooperative
-  // launch so the grid can finish the column sums itself (the reference's inner-outer kernels
-  // are cooperative for the same reason, executor.cpp:1307-1312). A combination the driver
-  // rejects is remembered per kernel and the launch falls back: no PDL, then no fused finish.
-  static std::mutex mode_mu;
-  static std::unordered_map<const void*, int> bad_modes;  // bit0: cooperative refused, bit1: PDL refused
+  // its first global access); and, for a backward that produces dgamma / dbeta, the in-kernel finish
+  // of the column sums behind a grid barrier (the reference's inner-outer kernels are cooperative
+  // for the same reason, executor.cpp:1307-1312). A combination the driver rejects falls back — no PDL,
+  // then no fused finish — and is remembered per (device, kernel) once the fallback has SUCCEEDED
+  // (an error that the fallback does not cure is not a launch-mode refusal and is reported as it is).
   int bad = 0;
   {
-    std::lock_guard<std::mutex> lock(mode_mu);
-    auto it = bad_modes.find((const void*)k);
-    if (it != bad_modes.end()) bad = it->second;
+    std::lock_guard<std::mutex> lock(ctx.mu);
+    auto it = ctx.bad_modes.find((const void*)k);
+    if (it != ctx.bad_modes.end()) bad = it->second;
   }
-  const bool allow_fused = want_cols && plan.block >= 128 && env_int("B200NORM_NO_FUSED_FINISH") == 0;
+  const int bad0 = bad;
+  const bool allow_fused = want_cols && plan.block >= 128 && kn.no_fused_finish == 0;
   const bool peer = want_cols && (d.flags & (B200NORM_F_PEER_REDUCE | B200NORM_F_PEER_PUBLISH)) != 0;
   const bool deferred = (d.flags & B200NORM_F_PEER_PUBLISH) != 0;
+  std::unique_lock<std::mutex> plock(ctx.peer_mu, std::defer_lock);
+  PeerState& ps = ctx.peers;
   if (peer) {
     // the exchange happens in the in-kernel finish: refuse before anything is enqueued if that path is closed
     if (!allow_fused || (bad & 1))
       return fail(B200NORM_ERR_UNSUPPORTED, "peer reduce needs the in-kernel finish (not available for this launch)");
-    std::lock_guard<std::mutex> lock(g_peers.mu);
-    if (g_peers.world < 1) return fail(B200NORM_ERR_BAD_ARG, "PEER_REDUCE without b200norm_register_peers");
-    const size_t need = (size_t)kPeerHeaderBytes + 2u * (size_t)K * (size_t)d.cols * 4u;
-    if (need > g_peers.bytes)
-      return fail(B200NORM_ERR_WORKSPACE, "exchange buffers hold %zu bytes, need %zu", g_peers.bytes, need);
-    if (deferred && g_peers.epoch - g_peers.combined >= 2)
+    plock.lock();  // held until the launch has been enqueued: epochs advance in launch order, and only on success
+    if (ps.world < 1) return fail(B200NORM_ERR_BAD_ARG, "PEER_REDUCE without b200norm_register_peers");
+    if ((uint64_t)K * (uint64_t)d.cols > ps.cap_floats)
+      return fail(B200NORM_ERR_WORKSPACE, "exchange buffers hold %u floats per slot, need %llu", ps.cap_floats,
+                  (unsigned long long)K * (unsigned long long)d.cols);
+    if (deferred && ps.epoch - ps.combined >= 2)
       return fail(B200NORM_ERR_BAD_ARG, "two publishes are outstanding: launch OP_PEER_COMBINE before the next one");
-    if (!deferred && g_peers.epoch != g_peers.combined)
-      return fail(B200NORM_ERR_BAD_ARG, "PEER_REDUCE with a publish outstanding: launch OP_PEER_COMBINE first");
-    rp.peer_world = g_peers.world;
-    rp.peer_rank = g_peers.rank;
+    rp.peer_world = ps.world;
+    rp.peer_rank = ps.rank;
     rp.peer_deferred = deferred ? 1 : 0;
-    for (int q = 0; q < g_peers.world; ++q) rp.peer_xchg[q] = static_cast<uint8_t*>(g_peers.ptrs[q]);
-    rp.peer_epoch = ++g_peers.epoch;
-    rp.peer_slot_floats = (uint32_t)((g_peers.bytes - kPeerHeaderBytes) / 8 / 4 * 4);
-    if (!deferred) g_peers.combined = g_peers.epoch;
+    for (int q = 0; q < ps.world; ++q) rp.peer_xchg[q] = static_cast<uint8_t*>(ps.ptrs[q]);
+    rp.peer_epoch = deferred ? ps.epoch + 1 : ps.ll_epoch + 1;  // committed below, after a successful launch
+    rp.peer_slot_floats = ps.cap_floats;
+    rp.peer_ll_off = ps.ll_off;
+    rp.peer_ll_parity_bytes = ps.ll_parity_bytes;
+    rp.peer_timeout_ns = ps.timeout_ns;
   }
-  const bool allow_pdl = env_int("B200NORM_NO_PDL") == 0;
+  const bool allow_pdl = kn.no_pdl == 0;
   for (;;) {
     const bool fused = allow_fused && !(bad & 1);
     const bool pdl = allow_pdl && !(bad & 2);
@@ -800,14 +950,17 @@ int launch_typed(const b200norm_desc& d, const Plan& plan, RowParams& rp, void* 
     attrs[na].val.clusterDim.y = 1;
     attrs[na].val.clusterDim.z = 1;
     ++na;
-    // The in-kernel finish needs every CTA resident at its grid barrier. The grid is at most one
-    // CTA per SM (one cluster per cluster slot), so it is co-resident as soon as the SMs are free;
-    // whatever holds an SM when the kernel starts (the stream's predecessor under PDL, an NCCL
-    // kernel on a side stream) finishes without waiting for this kernel, and the successor's CTAs
-    // cannot start before all of ours have. A plain launch therefore cannot deadlock, and unlike a
-    // cooperative launch it overlaps its setup with the predecessor's tail (measured: 77.7 -> 74.2 us
-    // at C2). B200NORM_COOP=1 asks the driver for the formal co-residency guarantee instead.
-    if (fused && env_int("B200NORM_COOP") != 0) {
+    // The in-kernel finish needs every CTA resident at its grid barrier. The grid is at most one CTA per SM
+    // (one cluster per cluster slot), so on ONE stream it is co-resident as soon as the SMs are free: whatever
+    // holds an SM when the kernel starts (the stream's predecessor under PDL, an NCCL kernel on a side stream)
+    // finishes without waiting for this kernel, and the successor's CTAs cannot start before all of ours have.
+    // Unlike a cooperative launch, the plain launch overlaps its setup with the predecessor's tail (measured:
+    // 77.7 -> 74.2 us at C2). Two barrier kernels on two STREAMS could each get part of the SMs and spin for ever
+    // (or until the watchdog traps): barrier_guard() serialises them across the streams of this process.
+    // B200NORM_COOP=1 asks the driver for the formal co-residency guarantee instead (other processes under MPS).
+    const bool coop = fused && kn.coop != 0;
+    if (fused && !coop && kn.no_guard == 0) barrier_guard(ctx, stream);
+    if (coop) {
       attrs[na].id = cudaLaunchAttributeCooperative;
       attrs[na].val.cooperative = 1;
       ++na;
@@ -822,7 +975,19 @@ int launch_typed(const b200norm_desc& d, const Plan& plan, RowParams& rp, void* 
     err = cudaLaunchKernelEx(&cfg, k, (const RowParams)rp);
     if (err == cudaSuccess) {
       g_launches++;
-      if (env_int("B200NORM_DEBUG") > 1)
+      if (peer) {  // the launch is in the stream: its epoch is taken
+        if (deferred) {
+          ps.epoch += 1;
+        } else {
+          ps.ll_epoch += 1;
+        }
+        plock.unlock();
+      }
+      if (bad != bad0) {  // the fallback cured it: remember the refused mode for this (device, kernel)
+        std::lock_guard<std::mutex> lock(ctx.mu);
+        ctx.bad_modes[(const void*)k] = bad;
+      }
+      if (kn.debug > 1)
         fprintf(stderr, "[b200norm] op %d launched grid %d block %d cluster %d fused=%d pdl=%d\n", d.op, plan.grid,
                 plan.block, plan.cluster, (int)fused, (int)pdl);
       if (want_cols && !fused) {
@@ -834,7 +999,7 @@ int launch_typed(const b200norm_desc& d, const Plan& plan, RowParams& rp, void* 
       return B200NORM_OK;
     }
     (void)cudaGetLastError();
-    if (env_int("B200NORM_DEBUG"))
+    if (kn.debug)
       fprintf(stderr, "[b200norm] launch with fused=%d pdl=%d refused: %s\n", (int)fused, (int)pdl,
               cudaGetErrorString(err));
     int newbad = bad;
@@ -846,8 +1011,6 @@ int launch_typed(const b200norm_desc& d, const Plan& plan, RowParams& rp, void* 
     if (newbad == bad || (peer && (newbad & 1)))
       return fail(B200NORM_ERR_CUDA + (int)err, "ring launch failed: %s", cudaGetErrorString(err));
     bad = newbad;
-    std::lock_guard<std::mutex> lock(mode_mu);
-    bad_modes[(const void*)k] = bad;
   }
 }
 
@@ -903,27 +1066,45 @@ const char* b200norm_last_error(void) { return g_err; }
 uint64_t b200norm_launch_count(void) { return g_launches.load(); }
 
 int b200norm_register_peers(int world, int rank, void* const* exchange_ptrs, size_t exchange_bytes) {
-  std::lock_guard<std::mutex> lock(g_peers.mu);
+  DeviceCtx& ctx = device_ctx();
+  std::lock_guard<std::mutex> lock(ctx.peer_mu);
+  PeerState& ps = ctx.peers;
   if (world == 0) {
-    g_peers.world = 0;
-    g_peers.bytes = 0;
+    ps = PeerState();
     return B200NORM_OK;
   }
   if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world || exchange_ptrs == nullptr)
     return fail(B200NORM_ERR_BAD_ARG, "register_peers: world %d (1..%d), rank %d", world, kMaxPeers, rank);
-  if (exchange_bytes < (size_t)kPeerHeaderBytes + 32)
+  // layout: header | two publish slots of cap floats | LL region: 2 parities x world x cap (value, epoch) pairs
+  const size_t per_float = 2 * 4 + 2 * (size_t)world * 8;
+  const size_t cap = exchange_bytes > (size_t)kPeerHeaderBytes ? (exchange_bytes - kPeerHeaderBytes) / per_float / 4 * 4 : 0;
+  if (cap < 4)
     return fail(B200NORM_ERR_BAD_ARG, "register_peers: exchange buffers too small (%zu bytes)", exchange_bytes);
   for (int q = 0; q < world; ++q) {
     if (exchange_ptrs[q] == nullptr || (reinterpret_cast<uintptr_t>(exchange_ptrs[q]) & 255u) != 0)
       return fail(B200NORM_ERR_BAD_ARG, "register_peers: buffer %d is null or not 256-byte aligned", q);
   }
-  g_peers.world = world;
-  g_peers.rank = rank;
-  for (int q = 0; q < world; ++q) g_peers.ptrs[q] = exchange_ptrs[q];
-  g_peers.bytes = exchange_bytes;
-  g_peers.epoch = 0;  // the buffers are zero: epochs restart at 1
-  g_peers.combined = 0;
+  ps = PeerState();
+  ps.world = world;
+  ps.rank = rank;
+  for (int q = 0; q < world; ++q) ps.ptrs[q] = exchange_ptrs[q];
+  ps.bytes = exchange_bytes;
+  ps.cap_floats = (uint32_t)(cap > 0x3fffffffu ? 0x3ffffffcu : cap);
+  ps.ll_off = (uint32_t)(kPeerHeaderBytes + 2 * (size_t)ps.cap_floats * 4);
+  ps.ll_parity_bytes = (uint32_t)((size_t)world * ps.cap_floats * 8);
+  // Waiting for a PEER is not an error for minutes (first iteration, evaluation or checkpoint on another rank,
+  // a data-loader stall): the in-kernel waits for peers get ten minutes by default, B200NORM_PEER_TIMEOUT_S
+  // changes that (0 = wait for ever, like the NCCL kernel this replaces).
+  const Knobs kn = read_knobs();
+  const int tmo = kn.peer_timeout_s >= 0 ? kn.peer_timeout_s : 600;
+  ps.timeout_ns = (uint64_t)tmo * 1000000000ull;
   return B200NORM_OK;
+}
+
+size_t b200norm_peer_exchange_bytes(int world, int64_t max_floats) {
+  if (world < 1 || world > kMaxPeers || max_floats < 1) return 0;
+  const size_t cap = ((size_t)max_floats + 3) / 4 * 4;
+  return (size_t)kPeerHeaderBytes + cap * (2 * 4 + 2 * (size_t)world * 8);
 }
 
 void b200norm_debug_set_timeline(void* device_buf) { g_timeline.store(static_cast<unsigned long long*>(device_buf)); }
@@ -995,7 +1176,7 @@ int b200norm_query(const b200norm_desc* desc, b200norm_plan* plan) {
   Plan p;
   // rows are assumed 16-byte aligned and contiguous at query time; the launch
   // re-plans with the real pointers (the workspace bound covers both outcomes).
-  rc = make_plan(*desc, /*aligned=*/true, /*rows_contiguous=*/true, &p);
+  rc = make_plan(*desc, device_ctx(), read_knobs(), /*aligned=*/true, /*rows_contiguous=*/true, &p);
   if (rc != B200NORM_OK) return rc;
   if (plan != nullptr) fill_public_plan(*desc, p, plan);
   return B200NORM_OK;
@@ -1013,7 +1194,9 @@ int b200norm_launch(const b200norm_desc* desc, const b200norm_tensor* inputs, in
   int rc = check_desc(desc);
   if (rc != B200NORM_OK) return rc;
   const b200norm_desc& d = *desc;
-  const DeviceInfo& dev = device_info();
+  DeviceCtx& ctx = device_ctx();
+  const DeviceInfo& dev = ctx.info;
+  const Knobs kn = read_knobs();
   if (!dev.has_device) return fail(B200NORM_ERR_NO_DEVICE, "no CUDA device visible (there is no CPU fallback)");
   if (dev.cc_major != 10)
     return fail(B200NORM_ERR_NO_DEVICE, "device is sm_%d%d; this library contains sm_100a code only", dev.cc_major,
@@ -1274,7 +1457,7 @@ int b200norm_launch(const b200norm_desc* desc, const b200norm_tensor* inputs, in
   }
 
   Plan plan;
-  rc = make_plan(d, aligned, rows_contiguous, &plan);
+  rc = make_plan(d, ctx, kn, aligned, rows_contiguous, &plan);
   if (rc != B200NORM_OK) return rc;
 
   if (d.rows == 0 || d.cols == 0) {
@@ -1321,7 +1504,7 @@ int b200norm_launch(const b200norm_desc* desc, const b200norm_tensor* inputs, in
   // them the output bits — are the same on every run.
   if (plan.variant == B200NORM_VARIANT_TMA && plan.cluster == 1 && !is_norm_bwd(d.op) && workspace != nullptr &&
       workspace_bytes >= B200NORM_WS_HEADER_BYTES && (reinterpret_cast<uintptr_t>(workspace) & 15u) == 0 &&
-      env_int("B200NORM_STATIC") == 0) {
+      kn.static_sched == 0) {
     // Pool size (measured on several B200s, whose per-SM imbalance differs: the static split loses
     // 5-13 % on the worse ones): the last half of the tiles for two-stream kernels, the last quarter
     // for RMSNorm / softmax forward; LayerNorm forward (two reductions per row, one group per CTA
@@ -1332,14 +1515,14 @@ int b200norm_launch(const b200norm_desc* desc, const b200norm_tensor* inputs, in
     // atomic round trip and the few pool tiles cost what the balance wins
     const int64_t tiles_per_group = ceil_div64(d.rows, plan.tile_rows) / ((int64_t)plan.grid * plan.groups);
     if (rp.nstreams == 1 && tiles_per_group < 40) rp.dynamic = 0;
-    if (int f = env_int("B200NORM_POOL")) rp.dynamic = f > 0 ? f : 4;  // 1 = everything past the first ring fill
+    if (int f = kn.pool) rp.dynamic = f > 0 ? f : 4;  // 1 = everything past the first ring fill
     rp.sched_words = reinterpret_cast<uint32_t*>(workspace) + 2;
   }
 
   switch (dt) {
-    case B200NORM_DT_F32: return launch_typed<float>(d, plan, rp, dw, db, sums_f32, workspace, stream);
-    case B200NORM_DT_BF16: return launch_typed<__nv_bfloat16>(d, plan, rp, dw, db, sums_f32, workspace, stream);
-    case B200NORM_DT_F16: return launch_typed<__half>(d, plan, rp, dw, db, sums_f32, workspace, stream);
+    case B200NORM_DT_F32: return launch_typed<float>(d, ctx, kn, plan, rp, dw, db, sums_f32, workspace, stream);
+    case B200NORM_DT_BF16: return launch_typed<__nv_bfloat16>(d, ctx, kn, plan, rp, dw, db, sums_f32, workspace, stream);
+    case B200NORM_DT_F16: return launch_typed<__half>(d, ctx, kn, plan, rp, dw, db, sums_f32, workspace, stream);
     default: return fail(B200NORM_ERR_UNSUPPORTED, "dtype %d", dt);
   }
 }

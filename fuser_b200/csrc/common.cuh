@@ -29,17 +29,21 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
   return t;
 }
 
-// A spin that can never hang the device: after ~4 s of waiting the kernel traps
-// (the launch then surfaces cudaErrorLaunchFailed instead of wedging the box).
+// A spin that can never hang the device: after `limit_ns` of waiting (default ~4 s: everything it guards
+// inside ONE GPU completes in microseconds) the kernel traps — the launch then surfaces cudaErrorLaunchFailed
+// instead of wedging the box. Waits for ANOTHER GPU take their limit from the peer registration (minutes by
+// default, 0 = wait for ever): rank skew of seconds is normal there.
 struct Watchdog {
   uint32_t spins = 0;
   uint64_t t0 = 0;
+  uint64_t limit_ns;
+  __device__ __forceinline__ explicit Watchdog(uint64_t limit = 4000000000ull) : limit_ns(limit) {}
   __device__ __forceinline__ void tick() {
-    if ((++spins & 0x3fffu) == 0) {
+    if ((++spins & 0x3fffu) == 0 && limit_ns != 0) {
       uint64_t now = global_timer_ns();
       if (t0 == 0) {
         t0 = now;
-      } else if (now - t0 > 4000000000ull) {
+      } else if (now - t0 > limit_ns) {
         __trap();
       }
     }
@@ -181,6 +185,19 @@ __device__ __forceinline__ float4 ld_volatile_f4(const float4* p) {
                : "l"(p)
                : "memory");
   return v;
+}
+
+// "LL" words of the fused peer all-reduce: one 64-bit store carries a value and the launch epoch that makes it
+// valid, so the receiver polls the data itself — no flag, no fence, one NVLink one-way latency (a scalar
+// 64-bit access is single-copy atomic in the PTX memory model; NCCL's LL protocol rests on the same property).
+__device__ __forceinline__ void st_ll(uint64_t* p, float v, uint32_t epoch) {
+  const uint64_t w = ((uint64_t)epoch << 32) | (uint64_t)__float_as_uint(v);
+  asm volatile("st.relaxed.sys.global.b64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+}
+__device__ __forceinline__ uint64_t ld_ll(const uint64_t* p) {
+  uint64_t w;
+  asm volatile("ld.relaxed.sys.global.b64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+  return w;
 }
 
 // ----------------------------------------------------------------------------

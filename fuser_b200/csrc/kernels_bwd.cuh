@@ -48,7 +48,9 @@ __device__ __forceinline__ void grid_barrier(uint32_t* word) {
 // b+grid, ... A thread owns one float4 column of the chunk and every RS-th partial row
 // (RS = threads / CW); all its loads are issued before the first add (one L2 round trip),
 // row-splits are combined by shuffles inside a warp and through shared memory across warps.
-template <typename T, int CW>
+// PUSH (several GPUs, fused flavour): instead of writing a local result, every finished sum goes to EVERY rank's
+// receive area as a (value, epoch) word — see peer_collect_columns.
+template <typename T, int CW, bool PUSH>
 __device__ __forceinline__ void finish_columns(const RowParams& p, int K, int F, int nct, float* sums_out) {
   constexpr int kMaxLoads = 10;
   const int tx = threadIdx.x % CW;
@@ -101,7 +103,14 @@ __device__ __forceinline__ void finish_columns(const RowParams& p, int K, int F,
       if (e < K * p.cols) {
         float r = 0.f;
         for (int w = 0; w < nwarps; ++w) r += smf[w * CW * 4 + threadIdx.x];
-        if (sums_out != nullptr) {
+        if constexpr (PUSH) {
+          const size_t off = (size_t)p.peer_ll_off + (size_t)(p.peer_epoch & 1u) * p.peer_ll_parity_bytes +
+                             ((size_t)p.peer_rank * p.peer_slot_floats + (size_t)e) * 8;
+#pragma unroll
+          for (int q = 0; q < kMaxPeers; ++q) {
+            if (q < p.peer_world) st_ll(reinterpret_cast<uint64_t*>(p.peer_xchg[q] + off), r, p.peer_epoch);
+          }
+        } else if (sums_out != nullptr) {
           sums_out[e] = r;
         } else {
           const int k2 = e / p.cols;
@@ -115,70 +124,57 @@ __device__ __forceinline__ void finish_columns(const RowParams& p, int K, int F,
 
 // The all-reduce of the column sums, inside the backward kernel (row-sharded backward on the GPUs
 // of one box; reference mechanism: lowerToAllreduce + postAllreduce, host_ir/lower_to_communication.cpp
-// :266-284, multidevice/post_communication.cpp:288-313 — a separate NCCL kernel there).
-// On entry this rank's [K][N] fp32 sums are being written to its exchange slot by all CTAs.
-//   1. grid barrier: the slot is complete; one CTA publishes the launch epoch into every rank's
-//      flag word for this rank (st.release.sys over NVLink);
-//   2. every CTA waits until all ranks' flags in ITS OWN memory carry the epoch (local polling);
-//   3. every rank adds the P slots in rank order — the same order everywhere, so all ranks get
-//      the same bits — and casts once, as on a single GPU.
-// Two slots alternate between launches: a rank may run one launch ahead of a peer that is still
-// reading, never two (its next epoch flag is only published after it finished reading).
-template <typename T>
-__device__ __forceinline__ void peer_allreduce_columns(const RowParams& p, int K, int nct) {
+// :266-284, multidevice/post_communication.cpp:288-313 — a separate NCCL kernel there; its NVLink-native
+// one-shot reduce: runtime/multicast_reduce.cu:13-40, csrc/multidevice/cuda_p2p.cpp:828-918).
+// One-shot, push based, no flags and no second grid barrier:
+//   1. finish_columns<PUSH>: the CTA that finishes a chunk of this rank's [K][N] sums stores every sum into the
+//      receive area of EVERY rank (its own included) as a 64-bit (value, launch epoch) word — remote stores over
+//      NVLink are posted, nobody waits for a round trip;
+//   2. the same CTA then polls, in its OWN memory, the words of its chunks from all P source ranks (all P loads
+//      of an element are issued before the first is examined), adds them in rank order — the same order on
+//      every rank, so all ranks get the same bits — and casts once, as on a single GPU.
+// The epoch makes a word valid: what the slot held before (two launches ago, the parities alternate) carries an
+// older epoch. A rank can be at most one launch ahead of a peer that is still reading: it only gets to launch
+// e+2 after collecting everybody's sums of e+1, which a peer sends after it has finished reading e.
+template <typename T, int CW>
+__device__ __forceinline__ void peer_collect_columns(const RowParams& p, int K, int F) {
   const int P = p.peer_world;
   const uint32_t epoch = p.peer_epoch;
-  // The slot is local memory: device-scope visibility (this rank's L2, which is also what the peers'
-  // NVLink reads go through) is enough for the writers; the system-scope release is the flag store.
-  // (A system-scope fence by every thread here cost several microseconds per launch.)
-  __threadfence();
-  __syncthreads();
-  grid_barrier(p.sync_words);
-  if (blockIdx.x == 0 && (int)threadIdx.x < P) {
-    st_release_sys(reinterpret_cast<uint32_t*>(p.peer_xchg[threadIdx.x]) + p.peer_rank, epoch);
-  }
-  if ((int)threadIdx.x < P) {
-    const uint32_t* flag = reinterpret_cast<const uint32_t*>(p.peer_xchg[p.peer_rank]) + threadIdx.x;
-    Watchdog wd;
-    while ((int32_t)(ld_acquire_sys(flag) - epoch) < 0) wd.tick();
-  }
-  __syncthreads();
-  const int total4 = K * p.cols / 4;
-  const size_t slot = (size_t)(epoch & 1u) * p.peer_slot_floats;
-  for (int i = blockIdx.x * nct + threadIdx.x; i < total4; i += gridDim.x * nct) {
-    float4 a = ld_volatile_f4(reinterpret_cast<const float4*>(
-                                  reinterpret_cast<const float*>(p.peer_xchg[0] + kPeerHeaderBytes) + slot) + i);
-    for (int q = 1; q < P; ++q) {
-      const float4 v = ld_volatile_f4(reinterpret_cast<const float4*>(
-                                          reinterpret_cast<const float*>(p.peer_xchg[q] + kPeerHeaderBytes) + slot) + i);
-      a.x += v.x;
-      a.y += v.y;
-      a.z += v.z;
-      a.w += v.w;
-    }
-    const int e = i * 4;
-    const int k2 = e / p.cols;
-    const int c = e - k2 * p.cols;
-    if (p.sums_out != nullptr) {
-      *reinterpret_cast<float4*>(p.sums_out + e) = a;
-    } else {
-      T* o = static_cast<T*>(k2 == 0 ? p.dw_out : p.db_out);
-      if (o != nullptr) {
-        o[c] = IO<T>::from_f32(a.x);
-        o[c + 1] = IO<T>::from_f32(a.y);
-        o[c + 2] = IO<T>::from_f32(a.z);
-        o[c + 3] = IO<T>::from_f32(a.w);
+  const int total = K * p.cols;
+  const uint8_t* base = p.peer_xchg[p.peer_rank] + p.peer_ll_off + (size_t)(epoch & 1u) * p.peer_ll_parity_bytes;
+  const size_t rank_stride = (size_t)p.peer_slot_floats * 8;
+  const int nchunk = (F + CW - 1) / CW;
+  if ((int)threadIdx.x < CW * 4) {
+    for (int chunk = blockIdx.x; chunk < nchunk; chunk += gridDim.x) {
+      const int e = chunk * CW * 4 + threadIdx.x;
+      if (e >= total) continue;
+      const uint64_t* src = reinterpret_cast<const uint64_t*>(base) + e;
+      uint64_t w[kMaxPeers];
+      Watchdog wd(p.peer_timeout_ns);
+      for (;;) {
+        bool ready = true;
+#pragma unroll
+        for (int q = 0; q < kMaxPeers; ++q) {
+          if (q < P) w[q] = ld_ll(reinterpret_cast<const uint64_t*>(reinterpret_cast<const uint8_t*>(src) + q * rank_stride));
+        }
+#pragma unroll
+        for (int q = 0; q < kMaxPeers; ++q) {
+          if (q < P) ready = ready && (uint32_t)(w[q] >> 32) == epoch;
+        }
+        if (ready) break;
+        wd.tick();
       }
-    }
-  }
-  // tell the peers their slots of this epoch have been read (only a later PEER_PUBLISH looks at it)
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const uint32_t old = atom_add_acq_rel_gpu(p.sync_words + 1, 1u);
-    if (old == gridDim.x - 1) {
-      p.sync_words[1] = 0u;
-      for (int q = 0; q < P; ++q) {
-        st_release_sys(reinterpret_cast<uint32_t*>(p.peer_xchg[q] + kPeerConsumedOffset) + p.peer_rank, epoch);
+      float a = __uint_as_float((uint32_t)w[0]);
+#pragma unroll
+      for (int q = 1; q < kMaxPeers; ++q) {
+        if (q < P) a += __uint_as_float((uint32_t)w[q]);
+      }
+      if (p.sums_out != nullptr) {
+        p.sums_out[e] = a;
+      } else {
+        const int k2 = e / p.cols;
+        T* o = static_cast<T*>(k2 == 0 ? p.dw_out : p.db_out);
+        if (o != nullptr) o[e - k2 * p.cols] = IO<T>::from_f32(a);
       }
     }
   }
@@ -192,7 +188,7 @@ __device__ __forceinline__ void peer_wait_consumed(const RowParams& p) {
     if ((int)threadIdx.x < p.peer_world) {
       const uint32_t* flag =
           reinterpret_cast<const uint32_t*>(p.peer_xchg[p.peer_rank] + kPeerConsumedOffset) + threadIdx.x;
-      Watchdog wd;
+      Watchdog wd(p.peer_timeout_ns);
       while ((int32_t)(ld_acquire_sys(flag) - (p.peer_epoch - 2u)) < 0) wd.tick();
     }
     __syncthreads();
@@ -267,24 +263,37 @@ __device__ __forceinline__ void bwd_epilogue(const RowParams& p, const Group<TPR
       grid_barrier(p.sync_words);
       tl_mark(p, 5);
       const int F = K * (p.cols / 4);  // float4 columns of the [K][N] result
-      // several GPUs: this rank's sums go to its exchange slot instead of being cast
+      // several GPUs: this rank's sums go to the peers (fused flavour: pushed to every rank's receive area;
+      // deferred flavour: written to this rank's publish slot) instead of being cast
+      const bool push = p.peer_world > 0 && !p.peer_deferred;
       float* sums_dst = p.sums_out;
-      if (p.peer_world > 0) {
+      if (p.peer_world > 0 && p.peer_deferred) {
         sums_dst = reinterpret_cast<float*>(p.peer_xchg[p.peer_rank] + kPeerHeaderBytes) +
                    (size_t)(p.peer_epoch & 1u) * p.peer_slot_floats;
-        if (p.peer_deferred) peer_wait_consumed(p);  // the slot's previous content (two publishes ago) was read
+        peer_wait_consumed(p);  // the slot's previous content (two publishes ago) was read
       }
-      if ((F + 7) / 8 <= 2 * (int)gridDim.x) {
-        finish_columns<T, 8>(p, K, F, nct, sums_dst);
-      } else {
-        finish_columns<T, 32>(p, K, F, nct, sums_dst);
-      }
-      if (p.peer_world > 0) {
-        if (p.peer_deferred) {
-          peer_publish(p);
+      const bool narrow = (F + 7) / 8 <= 2 * (int)gridDim.x;
+      if (push) {
+        if (narrow) {
+          finish_columns<T, 8, true>(p, K, F, nct, nullptr);
         } else {
-          peer_allreduce_columns<T>(p, K, nct);
+          finish_columns<T, 32, true>(p, K, F, nct, nullptr);
         }
+        tl_mark(p, 8);
+        if (narrow) {
+          peer_collect_columns<T, 8>(p, K, F);
+        } else {
+          peer_collect_columns<T, 32>(p, K, F);
+        }
+        tl_mark(p, 9);
+      } else {
+        if (narrow) {
+          finish_columns<T, 8, false>(p, K, F, nct, sums_dst);
+        } else {
+          finish_columns<T, 32, false>(p, K, F, nct, sums_dst);
+        }
+        tl_mark(p, 8);
+        if (p.peer_world > 0) peer_publish(p);
       }
     }
   }

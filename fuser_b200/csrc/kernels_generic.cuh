@@ -308,6 +308,7 @@ struct PeerCombineParams {
   int32_t world, rank, K, N;
   uint32_t epoch;
   uint32_t slot_floats;
+  uint64_t timeout_ns;  // limit of the wait for the peers' flags (0 = for ever)
   uint8_t* xchg[kMaxPeers];
   void* out_a;
   void* out_b;
@@ -316,7 +317,7 @@ template <typename T>
 __global__ void __launch_bounds__(512) peer_combine_kernel(const PeerCombineParams q) {
   if ((int)threadIdx.x < q.world) {
     const uint32_t* flag = reinterpret_cast<const uint32_t*>(q.xchg[q.rank]) + threadIdx.x;
-    Watchdog wd;
+    Watchdog wd(q.timeout_ns);
     while ((int32_t)(ld_acquire_sys(flag) - q.epoch) < 0) wd.tick();
   }
   __syncthreads();

@@ -1061,8 +1061,10 @@ bool make_map(CUtensorMap* map, const OuterArgs& a, const void* base, int64_t ro
 // resident clusters (C > 1) or CTAs (C == 1) of this launch shape on the current device
 int resident_units(OuterKernel k, int smem, int C, int sm_count) {
   static std::mutex mu;
-  static std::map<std::tuple<const void*, int, int>, int> cache;
-  const auto key = std::make_tuple((const void*)k, smem, C);
+  static std::map<std::tuple<int, const void*, int, int>, int> cache;  // per device: occupancy belongs to a device context
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) (void)cudaGetLastError();
+  const auto key = std::make_tuple(dev, (const void*)k, smem, C);
   {
     std::lock_guard<std::mutex> lock(mu);
     auto it = cache.find(key);
@@ -1224,9 +1226,11 @@ int outer_launch(const OuterArgs& a, void* stream_v, char* err, size_t errlen) {
   if (k == nullptr) return set_err(err, errlen, B200NORM_ERR_UNSUPPORTED, "outer-persistent: dtype %d", a.dtype);
   {
     static std::mutex mu;
-    static std::unordered_map<const void*, std::pair<int, int>> done;
+    static std::map<std::pair<int, const void*>, std::pair<int, int>> done;  // function attributes are per device
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) (void)cudaGetLastError();
     std::lock_guard<std::mutex> lock(mu);
-    auto& st = done[(const void*)k];
+    auto& st = done[std::make_pair(dev, (const void*)k)];
     if ((int)pl.smem > st.first) {
       cudaError_t e = cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
       if (e != cudaSuccess) return set_err(err, errlen, B200NORM_ERR_CUDA + (int)e, "outer smem attr: %s", cudaGetErrorString(e));

@@ -109,9 +109,13 @@ struct RowParams {
   int32_t peer_rank;
   int32_t peer_deferred;  // 1: publish only (B200NORM_F_PEER_PUBLISH); the combine is a later launch
   uint32_t peer_epoch;  // launch sequence number, identical on every rank, starts at 1
-  uint32_t peer_slot_floats;  // distance between the two slots (half of the buffer past the header)
+  uint32_t peer_slot_floats;  // capacity of one slot in floats: distance between the two publish slots, and between
+                              // the per-source-rank areas of the fused flavour's receive region
+  uint32_t peer_ll_off;           // fused flavour: byte offset of the (value, epoch) receive region in every buffer
+  uint32_t peer_ll_parity_bytes;  // ... and bytes of one of its two parities (world * peer_slot_floats * 8)
+  uint64_t peer_timeout_ns;       // limit of an in-kernel wait for a peer (0 = for ever)
   uint8_t* peer_xchg[kMaxPeers];
-  // tuning aid (b200norm_debug_set_timeline): per-CTA %globaltimer marks, 8 slots per CTA; nullptr = off
+  // tuning aid (b200norm_debug_set_timeline): per-CTA %globaltimer marks, kTimelineSlots per CTA; nullptr = off
   unsigned long long* timeline;
   // dynamic tile scheduling (forward-type kernels, cluster size 1): the last quarter of the tiles
   // is drawn from a global counter so that SMs which stream faster take more rows (per-SM
@@ -125,14 +129,16 @@ struct RowParams {
 };
 
 // Timeline marks: 0 entry, 1 setup done (after griddepcontrol.wait), 2 first tile landed,
-// 3 row loop done, 4 partial row written, 5 grid barrier passed, 6 exit.
+// 3 row loop done, 4 partial row written, 5 grid barrier passed, 6 exit, 7 (the SM id), 8 column sums
+// finished (and pushed to the peers), 9 peers' sums collected.
+constexpr int kTimelineSlots = 12;
 __device__ __forceinline__ void tl_mark(const RowParams& p, int slot) {
   if (p.timeline != nullptr && threadIdx.x == 0) {
-    p.timeline[(size_t)blockIdx.x * 8 + slot] = global_timer_ns();
+    p.timeline[(size_t)blockIdx.x * kTimelineSlots + slot] = global_timer_ns();
     if (slot == 0) {
       uint32_t smid;
       asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-      p.timeline[(size_t)blockIdx.x * 8 + 7] = smid;  // slot 7: the SM this CTA ran on
+      p.timeline[(size_t)blockIdx.x * kTimelineSlots + 7] = smid;  // slot 7: the SM this CTA ran on
     }
   }
 }

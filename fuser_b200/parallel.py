@@ -121,8 +121,9 @@ class PeerExchange:
 
     Two flavours (``deferred``):
       * False (``B200NORM_F_PEER_REDUCE``): everything inside the backward kernel, gradients final
-        when it returns — but the ranks meet inside the kernel every step, so any skew between them
-        is paid at once (measured at 2 GPUs: +15 us per step at C2);
+        when it returns: the finishing CTAs push their sums into every rank's receive area (one 64-bit
+        (value, epoch) store per sum and peer) and collect the peers' from their own memory — but the
+        ranks meet inside the kernel every step, so any skew between them is paid at once;
       * True (``B200NORM_F_PEER_PUBLISH`` + ``OP_PEER_COMBINE``, the default): the backward only
         publishes; ``result()`` of the returned handle launches a one-CTA combine, typically a step
         later when every peer's flag has long arrived, so no rank ever waits for another.
@@ -130,7 +131,8 @@ class PeerExchange:
     The buffers are torch symmetric memory (``torch.distributed._symmetric_memory``: CUDA VMM
     allocations exported to the other ranks of the box — the role of the reference's
     csrc/multidevice/symmetric_tensor.cpp / ipc_handle.cpp). ``max_cols`` bounds N of the segments
-    that will use it (2 slots x 2 sums x N fp32). Construction is collective over ``group``.
+    that will use it (``b200norm_peer_exchange_bytes``: the publish slots plus, for the fused flavour, a
+    receive area of two parities x world x 2N (value, epoch) words). Construction is collective over ``group``.
     """
 
     HEADER = 256
@@ -150,7 +152,7 @@ class PeerExchange:
         if self.world > 8:
             raise ValueError("peer exchange covers the GPUs of one box (world <= 8)")
         self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
-        self.nbytes = self.HEADER + 2 * 2 * int(max_cols) * 4
+        self.nbytes = L.peer_exchange_bytes(self.world, 2 * int(max_cols))  # K <= 2 sums per column
         self.buf = symm.empty(self.nbytes, dtype=torch.uint8, device=self.device)
         self.buf.zero_()
         self.handle = symm.rendezvous(self.buf, self.group)

@@ -29,7 +29,10 @@
  *     every launch and a barrier generation that only increments), so one
  *     zero-fill at allocation time is enough (this mirrors nvFuser's zeroed
  *     semaphore pool). A workspace must not be shared by launches that can run
- *     concurrently (use one per stream).
+ *     concurrently (use one per stream). The backward kernels that finish dweight / dbias behind an
+ *     in-kernel grid barrier are serialised across the streams of one process by the library (a launch
+ *     on another stream than the previous such launch first waits for that stream); across PROCESSES
+ *     sharing a device (MPS) set B200NORM_COOP=1 to make them cooperative launches.
  *   - there is NO CPU fallback: on a machine without an sm_100 device the
  *     launch entry points fail with B200NORM_ERR_NO_DEVICE.
  */
@@ -279,20 +282,27 @@ const char* b200norm_variant_name(int variant);
 int b200norm_device_info(int* has_device, int* sm_count, int* smem_per_block_optin,
                          int* cc_major, int* cc_minor);
 
-/* Registers this process's view of the peer-memory exchange buffers for B200NORM_F_PEER_REDUCE:
- * `exchange_ptrs[q]` is a device pointer, valid on the current device, to rank q's buffer
- * (`exchange_ptrs[rank]` is this rank's own); every buffer holds `exchange_bytes` bytes, is
- * 256-byte aligned and ZERO when registered (256 bytes of epoch flags, then two fp32 [K,N] slots:
- * exchange_bytes >= 256 + 2*K*N*4 for every launch that uses it). world <= 8 (one box); world = 0
- * unregisters. The buffers stay owned by the caller (e.g. torch symmetric memory) and must
- * outlive every launch that uses them. Reference counterpart: the IPC / symmetric-memory handles
- * of csrc/multidevice/ipc_handle.cpp, symmetric_tensor.cpp. */
+/* Registers, for the CURRENT device, this process's view of the peer-memory exchange buffers of
+ * B200NORM_F_PEER_REDUCE / PEER_PUBLISH: `exchange_ptrs[q]` is a device pointer, valid on the current device,
+ * to rank q's buffer (`exchange_ptrs[rank]` is this rank's own); every buffer holds `exchange_bytes` bytes, is
+ * 256-byte aligned and ZERO when registered. Size it with b200norm_peer_exchange_bytes(world, K*N) for the
+ * largest K*N (K = 2 LayerNorm, 1 RMSNorm) that will use it. Layout: 256 bytes of flags | two fp32 [K,N] slots
+ * of the publish / combine flavour | the fused flavour's receive area: two parities x world x K*N (value, epoch)
+ * 8-byte words, written by the PEERS with remote stores. world <= 8 (one box); world = 0 unregisters. The
+ * buffers stay owned by the caller (e.g. torch symmetric memory) and must outlive every launch that uses them.
+ * In-kernel waits for a peer time out after B200NORM_PEER_TIMEOUT_S seconds (environment, read here; default
+ * 600, 0 = never) with a trap, i.e. a sticky launch failure. Reference counterpart: the IPC / symmetric-memory
+ * handles of csrc/multidevice/ipc_handle.cpp, symmetric_tensor.cpp. */
 int b200norm_register_peers(int world, int rank, void* const* exchange_ptrs, size_t exchange_bytes);
 
+/* Bytes of one exchange buffer for `world` ranks and segments of up to `max_floats` = K*N column sums (0 on bad arguments). */
+size_t b200norm_peer_exchange_bytes(int world, int64_t max_floats);
+
 /* Tuning aid (no reference counterpart): while `device_buf` is non-NULL every ring kernel
- * launched by this process stores per-CTA %globaltimer marks into it (8 x uint64 per CTA:
+ * launched by this process stores per-CTA %globaltimer marks into it (12 x uint64 per CTA:
  * entry, setup done, first tile landed, row loop done, partial row written, grid barrier
- * passed, exit). The buffer must hold 8 * grid_x uint64. NULL switches it off. */
+ * passed, exit, SM id, column sums finished, peers' sums collected, 2 spare). The buffer must
+ * hold 12 * grid_x uint64. NULL switches it off. */
 void b200norm_debug_set_timeline(void* device_buf);
 
 #ifdef __cplusplus

@@ -6,7 +6,8 @@
 Launches the op three times back to back (the middle and last launches are instrumented) and prints,
 for every mark, min / median / max over the CTAs in microseconds relative to the first CTA's entry,
 plus the gap between launch 2's last exit and launch 3's marks (what PDL overlaps).
-marks: 0 entry, 1 setup done, 2 first tile landed, 3 row loop done, 4 partial written, 5 grid barrier passed, 6 exit
+marks: 0 entry, 1 setup done, 2 first tile landed, 3 row loop done, 4 partial written, 5 grid barrier passed, 6 exit,
+8 column sums finished (pushed to the peers), 9 peers' sums collected
 """
 import os
 import sys
@@ -21,7 +22,8 @@ from fuser_b200 import ops  # noqa: E402
 KEYS = ["B200NORM_TPR", "B200NORM_GROUPS", "B200NORM_DEPTH", "B200NORM_TILE_ROWS", "B200NORM_CLUSTER",
         "B200NORM_BWD_REREAD", "B200NORM_NO_FUSED_FINISH", "B200NORM_NO_PDL", "B200NORM_NO_PSMEM", "B200NORM_COOP", "B200NORM_STATIC", "B200NORM_POOL", "B200NORM_NO_PIPE", "B200NORM_PIPE"]
 DT = {"bf16": torch.bfloat16, "f32": torch.float32, "f16": torch.float16}
-NAMES = ["entry", "setup", "first", "loop", "partial", "gbar", "exit"]
+NAMES = ["entry", "setup", "first", "loop", "partial", "gbar", "exit", None, "finish", "collect"]
+SLOTS = 12
 
 
 def main():
@@ -61,7 +63,7 @@ def main():
         for i in range(3):
             fn(i)
         torch.cuda.synchronize()
-        bufs = [torch.zeros(2048 * 8, dtype=torch.int64, device=dev) for _ in range(2)]
+        bufs = [torch.zeros(2048 * SLOTS, dtype=torch.int64, device=dev) for _ in range(2)]
         torch.cuda.synchronize()
         fn(0)
         L.set_timeline(bufs[0].data_ptr())
@@ -70,7 +72,7 @@ def main():
         fn(2)
         L.set_timeline(None)
         torch.cuda.synchronize()
-        tl = [b.cpu().view(-1, 8) for b in bufs]
+        tl = [b.cpu().view(-1, SLOTS) for b in bufs]
         nct = int((tl[1][:, 0] != 0).sum())
         print(f"== {spec}: {nct} CTAs")
         t0 = int(tl[0][:nct, 0].min())
@@ -78,6 +80,8 @@ def main():
             t = t[:nct]
             print(f" launch {li + 2}:")
             for sidx, name in enumerate(NAMES):
+                if name is None:
+                    continue
                 col = t[:, sidx]
                 if int(col.max()) == 0:
                     continue

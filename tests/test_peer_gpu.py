@@ -27,7 +27,7 @@ def test_peer_reduce_world_of_one(shape, dt):
     _, rstd = ops.rms_norm_fwd(xd, wd, 1e-5)
     ref_ln = ops.layer_norm_bwd(dyd, xd, mean, invstd, wd)
     ref_rms = ops.rms_norm_bwd(dyd, xd, rstd, wd)
-    nbytes = 256 + 2 * 2 * n * 4
+    nbytes = L.peer_exchange_bytes(1, 2 * n)
     buf = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
     L.register_peers(1, 0, [buf.data_ptr()], nbytes)
     try:
@@ -37,7 +37,10 @@ def test_peer_reduce_world_of_one(shape, dt):
             got = ops.rms_norm_bwd(dyd, xd, rstd, wd, peer_reduce=True)
             assert all(torch.equal(a, b) for a, b in zip(got, ref_rms))
         torch.cuda.synchronize()
-        assert int(buf[:4].view(torch.int32).item()) == 6, "six launches must have published epochs 1..6"
+        # the receive area (behind the header and the two publish slots) carries (value, epoch) words: the
+        # sixth launch wrote its first sum with epoch 6 into parity 0
+        ll_off = 256 + 2 * (2 * n) * 4
+        assert int(buf[ll_off + 4:ll_off + 8].view(torch.int32).item()) == 6, "six fused launches: epochs 1..6"
         # publish now / combine later, two publishes in flight
         for _ in range(2):
             dx1, none_w, none_b = ops.layer_norm_bwd(dyd, xd, mean, invstd, wd, peer_reduce="publish")
