@@ -492,6 +492,57 @@ def time_cpu(kind, m, n, dtype, sample_rows, reps, warm=1):
     return nbytes / sec / 1e9, sec, torch.get_num_threads()
 
 
+def c4_strong_record(args, device, world, rank, collective, barrier):
+    """BASELINE configs[3]: LayerNorm backward bf16 [32768,12288], rows sharded over the ranks, dgamma / dbeta
+    all-reduced; total work fixed. Timed like the main line (K launches, one event pair, max over ranks); rank 0
+    then times the UNSHARDED problem alone (the other ranks idle) so the record carries its own 1-GPU time."""
+    from fuser_b200.parallel import shard_rows
+
+    _, M, N, dtype, kind = WORKLOADS["c4"]
+    a, b = shard_rows(M, world, rank)
+    total_bytes = sum(iobytes(kind, M, N, 2).values())
+    st = Step(kind, b - a, N, dtype, device, world, rank, collective)
+    nk = max(20, min(args.steps, 100))
+    for i in range(5):
+        st.bwd(i)
+    st.finish()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(nk):
+        st.bwd(i)
+    st.finish()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1) / nk], device=device)
+    torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms = float(t.item())
+    used = st.collective
+    if st.reducer is not None and hasattr(st.reducer, "close"):
+        st.reducer.close()
+    del st
+    torch.cuda.empty_cache()
+    one = None
+    if rank == 0:
+        s1 = Step(kind, M, N, dtype, device, 1, 0)
+        for i in range(3):
+            s1.bwd(i)
+        torch.cuda.synchronize(device)
+        e0.record()
+        for i in range(20):
+            s1.bwd(i)
+        e1.record()
+        torch.cuda.synchronize(device)
+        one = e0.elapsed_time(e1) / 20
+        del s1
+        torch.cuda.empty_cache()
+    barrier()
+    return {"workload": WORKLOADS["c4"][0] + f", rows sharded over {world} GPUs", "scaling": "strong", "n_gpus": world,
+            "value": total_bytes / (ms * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": ms, "launches_timed": nk,
+            "one_gpu_ms": one, "speedup_vs_one_gpu": (one / ms) if one else None,
+            "efficiency": (one / ms / world) if one else None, "collective": used}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -506,6 +557,7 @@ def main():
                          "fp32 partial sums, consumed a step later")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-c4", action="store_true", help="N > 1: skip the C4 strong-scaling sub-record")
     ap.add_argument("--no-validate", action="store_true", help="skip the oracle check of one step before timing")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200norm" else args.warmup
@@ -642,7 +694,9 @@ def main():
         if ent:
             traffic, traffic_src = ent["dram_bytes"], f"profiles/{ent['from']}"
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": byt[dom],
+                "traffic": traffic, "traffic_source": traffic_src,
+                "traffic_note": "a constant read from the committed ncu --set full capture named in traffic_source, "
+                                "not measured in this run", "algorithmic_bytes": byt[dom],
                 "kernel": f"{kind}:{dom}", "peak_source": peak_src, "launches_timed": nk,
                 "per_kernel": per_kernel,
                 "step_frac_of_peak": (step_bytes / (ms_per_step * 1e-3) / 1e9) / peak}
@@ -670,6 +724,11 @@ def main():
                "api": "FusionDefinition.execute (fwd + bwd definitions of benchmarks/python), pinned host buffers, "
                       "H2D / compute / D2H double-buffered on three streams"}
         del e
+    # ---- N > 1: the north-star multi-GPU config (C4, LayerNorm backward [32768,12288] row-sharded, STRONG
+    # scaling) as a sub-record of the default line, with its own 1-GPU time measured in the same run ----
+    c4_strong = None
+    if world > 1 and args.workload == "c2" and not args.no_c4:
+        c4_strong = c4_strong_record(args, device, world, rank, step.collective, barrier)
     clocks = sampler.stop() if rank == 0 else {}
 
     # ---- CPU baseline (rank 0, N=1 only) ----
@@ -686,23 +745,28 @@ def main():
             "metric": metric, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            # `config` names the workload and nothing else, so that this line and the reference arm's compare equal
             "config": {"workload": desc, "rows_per_gpu": rows, "cols": N, "io_dtype": dtype_name,
-                       "accumulate": "fp32",
-                       "l2": f"inputs larger than L2 ({step.nsets} rotating input sets, {footprint / 1e6:.0f} MB)",
-                       "collective": {"none": "none",
-                                      "peer": "fp32 dgamma/dbeta sums published to NVLink peer memory by the backward kernel's "
-                                              "finishing CTAs; a one-CTA combine (P2P loads in rank order, cast) consumes them "
-                                              "one step later; no NCCL",
-                                      "peer-fused": "fp32 dgamma/dbeta sums all-reduced inside the backward kernel over NVLink "
-                                                    "peer memory (P2P stores / loads from the finishing CTAs), cast after the reduce",
-                                      "nccl": "nccl allreduce of fp32 dgamma/dbeta partial sums, async (consumed one step "
-                                              "later), cast after the reduce"}[step.collective],
-                       "rows_per_s": (rows * world if scaling == "weak" else M) / (ms_per_step * 1e-3),
-                       "pct_of_nominal_8TBs": 100.0 * value / world / 8000.0,
-                       "pct_of_measured_peak": 100.0 * value / world / peak,
-                       "host_enqueue_us_per_step": host_enqueue_s / args.steps * 1e6},
+                       "l2": "inputs larger than L2"},
+            "details": {"accumulate": "fp32",
+                        "value_api": "fuser_b200.ops -> C++ NormExecutor -> C ABI (device tensors); e2e goes through "
+                                     "FusionDefinition.execute",
+                        "l2": f"{step.nsets} rotating input sets, {footprint / 1e6:.0f} MB",
+                        "collective": {"none": "none",
+                                       "peer": "fp32 dgamma/dbeta sums published to NVLink peer memory by the backward kernel's "
+                                               "finishing CTAs; a small combine kernel (P2P loads in rank order, cast) consumes "
+                                               "them one step later; no NCCL",
+                                       "peer-fused": "fp32 dgamma/dbeta sums all-reduced inside the backward kernel over NVLink "
+                                                     "peer memory: one-shot push of (value, epoch) words into every rank's "
+                                                     "receive area, collected locally in rank order, cast after the reduce",
+                                       "nccl": "nccl allreduce of fp32 dgamma/dbeta partial sums, async (consumed one step "
+                                               "later), cast after the reduce"}[step.collective],
+                        "rows_per_s": (rows * world if scaling == "weak" else M) / (ms_per_step * 1e-3),
+                        "pct_of_nominal_8TBs": 100.0 * value / world / 8000.0,
+                        "pct_of_measured_peak": 100.0 * value / world / peak,
+                        "host_enqueue_us_per_step": host_enqueue_s / args.steps * 1e6},
             "validated": validation is not None, "validation": validation,
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "c4_strong": c4_strong, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
