@@ -243,30 +243,22 @@ uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 // ---------------------------------------------------------------------------
 // kernel tables
 // ---------------------------------------------------------------------------
-// `psmem` doubles as the pipelined-backward selector for the norm backward (it has no other meaning there)
+// pipe: the split-phase pipelined flavours (norm backward re-read form, RMSNorm / LayerNorm forward)
+#define B200_RING_KERNEL_FOR(T, SUF)                                                                         \
+  template <>                                                                                                \
+  RingKernel ring_kernel_for<T>(int op, int tpr, int ch, bool cached, bool psmem, bool add, bool pipe) {      \
+    if (pipe && op == B200NORM_OP_LAYERNORM_FWD) return ring_ln_pipe_kernel_##SUF(tpr, ch, add);             \
+    if (add) return ring_add_kernel_##SUF(op, tpr, ch, psmem);                                               \
+    if (is_norm_bwd(op) && !cached && pipe) return ring_bwd_pipe_kernel_##SUF(op, tpr, ch);                  \
+    if (op == B200NORM_OP_RMSNORM_FWD && pipe) return ring_fwd_pipe_kernel_##SUF(op, tpr, ch);               \
+    return is_norm_bwd(op) ? ring_bwd_kernel_##SUF(op, tpr, ch, cached) : ring_fwd_kernel_##SUF(op, tpr, ch, psmem); \
+  }
 template <typename T>
-RingKernel ring_kernel_for(int op, int tpr, int ch, bool cached, bool psmem, bool add);
-template <>
-RingKernel ring_kernel_for<float>(int op, int tpr, int ch, bool cached, bool psmem, bool add) {
-  if (add) return ring_add_kernel_f32(op, tpr, ch, psmem);
-  if (is_norm_bwd(op) && !cached && psmem) return ring_bwd_pipe_kernel_f32(op, tpr, ch);
-  if (op == B200NORM_OP_RMSNORM_FWD && psmem) return ring_fwd_pipe_kernel_f32(op, tpr, ch);
-  return is_norm_bwd(op) ? ring_bwd_kernel_f32(op, tpr, ch, cached) : ring_fwd_kernel_f32(op, tpr, ch, psmem);
-}
-template <>
-RingKernel ring_kernel_for<__nv_bfloat16>(int op, int tpr, int ch, bool cached, bool psmem, bool add) {
-  if (add) return ring_add_kernel_bf16(op, tpr, ch, psmem);
-  if (is_norm_bwd(op) && !cached && psmem) return ring_bwd_pipe_kernel_bf16(op, tpr, ch);
-  if (op == B200NORM_OP_RMSNORM_FWD && psmem) return ring_fwd_pipe_kernel_bf16(op, tpr, ch);
-  return is_norm_bwd(op) ? ring_bwd_kernel_bf16(op, tpr, ch, cached) : ring_fwd_kernel_bf16(op, tpr, ch, psmem);
-}
-template <>
-RingKernel ring_kernel_for<__half>(int op, int tpr, int ch, bool cached, bool psmem, bool add) {
-  if (add) return ring_add_kernel_f16(op, tpr, ch, psmem);
-  if (is_norm_bwd(op) && !cached && psmem) return ring_bwd_pipe_kernel_f16(op, tpr, ch);
-  if (op == B200NORM_OP_RMSNORM_FWD && psmem) return ring_fwd_pipe_kernel_f16(op, tpr, ch);
-  return is_norm_bwd(op) ? ring_bwd_kernel_f16(op, tpr, ch, cached) : ring_fwd_kernel_f16(op, tpr, ch, psmem);
-}
+RingKernel ring_kernel_for(int op, int tpr, int ch, bool cached, bool psmem, bool add, bool pipe);
+B200_RING_KERNEL_FOR(float, f32)
+B200_RING_KERNEL_FOR(__nv_bfloat16, bf16)
+B200_RING_KERNEL_FOR(__half, f16)
+#undef B200_RING_KERNEL_FOR
 
 // cudaFuncSetAttribute is paid once per (device, kernel, smem size, cluster class), not per launch.
 int prepare_ring_kernel(DeviceCtx& ctx, RingKernel k, int smem, int cluster) {
@@ -285,11 +277,11 @@ int prepare_ring_kernel(DeviceCtx& ctx, RingKernel k, int smem, int cluster) {
   return B200NORM_OK;
 }
 
-RingKernel ring_kernel_any(int dt, int op, int tpr, int ch, bool cached, bool psmem, bool add) {
+RingKernel ring_kernel_any(int dt, int op, int tpr, int ch, bool cached, bool psmem, bool add, bool pipe) {
   switch (dt) {
-    case B200NORM_DT_F32: return ring_kernel_for<float>(op, tpr, ch, cached, psmem, add);
-    case B200NORM_DT_BF16: return ring_kernel_for<__nv_bfloat16>(op, tpr, ch, cached, psmem, add);
-    case B200NORM_DT_F16: return ring_kernel_for<__half>(op, tpr, ch, cached, psmem, add);
+    case B200NORM_DT_F32: return ring_kernel_for<float>(op, tpr, ch, cached, psmem, add, pipe);
+    case B200NORM_DT_BF16: return ring_kernel_for<__nv_bfloat16>(op, tpr, ch, cached, psmem, add, pipe);
+    case B200NORM_DT_F16: return ring_kernel_for<__half>(op, tpr, ch, cached, psmem, add, pipe);
     default: return nullptr;
   }
 }
@@ -478,8 +470,16 @@ bool try_ring_plan(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, int 
   // (16-bit io only: fp32 parameters need no unpacking, and staging them costs a tiny kernel like
   // C1 16 % — 16.4 vs 14.1 us; not beyond 8192 columns: at N = 12288 the 96 KB of staged parameters
   // and their four LDS per chunk cost 10 % — 378 vs 342 us)
+  // LayerNorm forward with one reduction round per row (Welford pairs merged with Chan's formula), pipelined
+  // across rows (kernels_ln_pipe.cuh): where nothing else overlaps the reduction — one consumer group per CTA
+  // (N > 8192 at 16 bits) or rows split over a cluster. Needs equal element counts per thread and one row per
+  // tile; the residual-add flavour is instantiated from 256 threads per row on. B200NORM_LN_PIPE=1 forces it
+  // wherever it can run, B200NORM_NO_LN_PIPE=1 switches it off.
+  const bool ln_pipe = d.op == B200NORM_OP_LAYERNORM_FWD && ch > 0 && nchunks == tpr * ch && tile_rows == 1 &&
+                       tpr >= 64 && (!add || tpr >= 256) && kn.no_ln_pipe == 0 &&
+                       (C > 1 || groups == 1 || kn.ln_pipe != 0);
   bool want_psmem = d.op == B200NORM_OP_LAYERNORM_FWD && ch > 0 && es == 2 && slice_cols <= 8192 &&
-                    kn.no_psmem == 0;
+                    kn.no_psmem == 0 && !ln_pipe;
   const uint32_t param_bytes = align_up(2u * (uint32_t)slice_cols * 4u, 128);
 
   // Ring depth D (stages per group); the ring is group-major, stage (g*D + s).
@@ -533,12 +533,12 @@ bool try_ring_plan(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, int 
   // ... and for rows wide enough to need one 512-thread group per CTA; with several groups per
   // CTA the groups already overlap each other and the second smem pass only costs (N = 8192: 85 vs 95 us).
   // (16-bit only: the fp32 single-group kernel is at the roofline already, 163 vs 182 us at N = 8192)
+  if (ln_pipe) p.pipe = true;
   if (d.op == B200NORM_OP_RMSNORM_FWD && !add &&
       (C > 1 || (tpr == 512 && es == 2 && ch == 3 && (nchunks + 255) / 256 == 6) || kn.pipe != 0) && ch > 0 &&
       tile_rows == 1 && tpr >= 64 && (ch <= 4 || tpr >= 256) && kn.no_pipe == 0) {
     p.pipe = true;
   }
-  if (p.pipe) p.psmem = true;  // kernel-table selector, see ring_kernel_for
   p.block = groups * tpr;
   const uint32_t ring_bytes = (uint32_t)p.stages * p.stage_bytes;
   if (bwd) {
@@ -548,7 +548,7 @@ bool try_ring_plan(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, int 
   p.smem = p.off_ring + ring_bytes;
 
   const int64_t ntiles = ceil_div64(d.rows, tile_rows);
-  int64_t nclusters = max_active_clusters(ctx, ring_kernel_any(d.io_dtype, d.op, tpr, ch, cached, p.psmem, add), p.block,
+  int64_t nclusters = max_active_clusters(ctx, ring_kernel_any(d.io_dtype, d.op, tpr, ch, cached, p.psmem, add, p.pipe), p.block,
                                           (int)p.smem, C);
   if (nclusters > ntiles) nclusters = ntiles;
   if (nclusters < 1) nclusters = 1;
@@ -749,9 +749,8 @@ void fill_public_plan(const b200norm_desc& d, const Plan& p, b200norm_plan* out)
   out->tile_rows = p.tile_rows;
   out->smem_bytes = (int32_t)p.smem;
   out->n_launches = p.n_launches;
-  // `psmem` doubles as the pipelined-kernel selector (see ring_kernel_for)
   out->form = (p.cached ? B200NORM_FORM_CACHED : 0) | (p.pipe ? B200NORM_FORM_PIPE : 0) |
-              ((p.psmem && !p.pipe) ? B200NORM_FORM_PSMEM : 0);
+              (p.psmem ? B200NORM_FORM_PSMEM : 0);
   out->groups = p.groups;
   out->chunks = p.ch;
   out->workspace_bytes = p.ws_bytes;
@@ -880,7 +879,7 @@ int launch_typed(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, const 
   }
 
   // ---- ring kernels ----
-  RingKernel k = ring_kernel_for<T>(d.op, plan.tpr, plan.ch, plan.cached, plan.psmem, is_add_fwd(d));
+  RingKernel k = ring_kernel_for<T>(d.op, plan.tpr, plan.ch, plan.cached, plan.psmem, is_add_fwd(d), plan.pipe);
   if (k == nullptr)
     return fail(B200NORM_ERR_UNSUPPORTED, "no ring kernel for op %d tpr %d ch %d", d.op, plan.tpr, plan.ch);
   {

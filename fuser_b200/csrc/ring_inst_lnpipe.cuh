@@ -1,0 +1,37 @@
+// ring_inst_lnpipe.cuh — instantiation table of the pipelined one-round LayerNorm forward for one dtype.
+#pragma once
+
+#include "../../include/b200norm.h"
+#include "kernels_ln_pipe.cuh"
+#include "ring_dispatch.cuh"
+
+namespace b200norm {
+
+template <typename T>
+RingKernel ring_ln_pipe_kernel_for(int tpr, int ch, bool add) {
+#define B200_LNPIPE_CH(TPR, ADD)                                      \
+  switch (ch) {                                                       \
+    case 1: return layernorm_fwd_pipe_kernel<T, TPR, 1, ADD>;         \
+    case 2: return layernorm_fwd_pipe_kernel<T, TPR, 2, ADD>;         \
+    case 3: return layernorm_fwd_pipe_kernel<T, TPR, 3, ADD>;         \
+    case 4: return layernorm_fwd_pipe_kernel<T, TPR, 4, ADD>;         \
+    default: return nullptr;                                          \
+  }
+  if (add) {
+    switch (tpr) {
+      case 256: B200_LNPIPE_CH(256, true)
+      case 512: B200_LNPIPE_CH(512, true)
+      default: return nullptr;
+    }
+  }
+  switch (tpr) {
+    case 64: B200_LNPIPE_CH(64, false)
+    case 128: B200_LNPIPE_CH(128, false)
+    case 256: B200_LNPIPE_CH(256, false)
+    case 512: B200_LNPIPE_CH(512, false)
+    default: return nullptr;
+  }
+#undef B200_LNPIPE_CH
+}
+
+}  // namespace b200norm

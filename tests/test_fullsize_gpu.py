@@ -251,3 +251,62 @@ def test_fp32_pipelined_backward_steady_state():
     _rms_bwd_small(m, n, torch.float32, 90, {"variant": "tma", "pipe": True, "cached": False}, centered=False)
     _ln_bwd(m, 6144, torch.float32, 91, {"variant": "tma", "pipe": True, "cached": False, "chunks": 3}, sample=False)
     _ln_bwd(m, n, torch.float32, 92, {"variant": "cluster", "cluster_size": 2, "cached": True}, sample=False)
+
+
+# ---------------------------------------------------------------------------------------------------
+# LayerNorm forward: the pipelined one-round kernel (Welford pairs + Chan merge) in its steady state
+# ---------------------------------------------------------------------------------------------------
+def _ln_fwd(m, n, dt, seed, expect, residual=False, shift=0.0):
+    flags = L.F_HAS_WEIGHT | L.F_HAS_BIAS | L.F_OUT_MEAN | L.F_OUT_INVSTD
+    if residual:
+        flags |= L.F_ADD_RESIDUAL | L.F_OUT_SUM
+    plan = ops.plan_for(L.OP_LAYERNORM_FWD, dt, m, n, flags, EPS)
+    for k, v in expect.items():
+        assert plan[k] == v, f"plan {k}: {plan[k]} (expected {v}) {plan}"
+    x = gpu_randn(m, n, dt, seed)
+    if shift:
+        x = (x.float() * 0.5 + shift).to(dt)  # |mean| >> std: where a one-pass E[x^2] - mean^2 would lose the variance
+    w = gpu_randn(1, n, dt, seed + 1).view(n)
+    b = gpu_randn(1, n, dt, seed + 2).view(n)
+    xc, wc, bc = x.cpu(), w.cpu(), b.cpu()
+    fl = 1.0 if dt == torch.float32 else 1e-2
+    if residual:
+        r = gpu_randn(m, n, dt, seed + 3)
+        y, mean, invstd, s = ops.layer_norm_fwd(x, w, b, EPS, residual=r, want_sum=True, round_sum=dt != torch.float32)
+        se = AO.residual_sum(xc, r.cpu(), dt != torch.float32)
+        assert torch.equal(s.cpu(), se.to(dt)), "x + residual must be bit-exact"
+        ye, me, ie = AO.add_layer_norm_fwd(xc, r.cpu(), wc, bc, EPS, round_sum=dt != torch.float32)
+        y64, m64, i64 = CO.layer_norm_fwd(se, wc, bc, EPS)
+    else:
+        y, mean, invstd = ops.layer_norm_fwd(x, w, b, EPS)
+        ye, me, ie = AO.layer_norm_fwd(xc, wc, bc, EPS)
+        y64, m64, i64 = CO.layer_norm_fwd(xc, wc, bc, EPS)
+    torch.cuda.synchronize()
+    check(y, ye, y64, n, "ln y", fl)
+    check(mean, me, m64, n, "ln mean", 1.0)
+    check(invstd, ie, i64, n, "ln invstd", 1e-3)
+    return plan
+
+
+def test_layernorm_fwd_pipelined_steady_state(monkeypatch):
+    pipe1 = {"variant": "tma", "cluster_size": 1, "pipe": True, "groups": 1}
+    _ln_fwd(1500, 12288, torch.bfloat16, 100, dict(pipe1, chunks=3))   # the [32768,12288] kernel, ~10 rows per CTA
+    _ln_fwd(1500, 12288, torch.float16, 101, dict(pipe1, chunks=3))
+    _ln_fwd(1500, 12288, torch.bfloat16, 102, dict(pipe1, chunks=3), shift=20.0)
+    _ln_fwd(1500, 16384, torch.bfloat16, 103, dict(pipe1, chunks=4))   # packed parameters
+    _ln_fwd(3000, 8192, torch.float32, 104, dict(pipe1, chunks=4))
+    _ln_fwd(3000, 8192, torch.float32, 105, dict(pipe1, chunks=4), shift=100.0)
+    _ln_fwd(1500, 12288, torch.bfloat16, 106, dict(pipe1, chunks=3), residual=True)
+    _ln_fwd(1000, 8192, torch.float32, 107, dict(pipe1, chunks=4), residual=True)
+    plan = _ln_fwd(700, 65536, torch.bfloat16, 108, {"variant": "cluster", "cluster_size": 4, "pipe": True})
+    assert 700 / (plan["grid"] // 4) > plan["stages"]
+    _ln_fwd(300, 131072, torch.bfloat16, 109, {"variant": "cluster", "pipe": True})
+    # forced onto multi-group shapes (every threads-per-row class of the table)
+    monkeypatch.setenv("B200NORM_LN_PIPE", "1")
+    for m, n, dt in [(3001, 4096, torch.bfloat16), (3001, 4096, torch.float32), (2000, 2048, torch.bfloat16),
+                     (2000, 1024, torch.float32), (2000, 8192, torch.bfloat16), (2000, 3072, torch.float16)]:
+        plan = _ln_fwd(m, n, dt, 110 + n, {"variant": "tma", "pipe": True})
+        assert plan["groups"] > 1
+    monkeypatch.delenv("B200NORM_LN_PIPE")
+    monkeypatch.setenv("B200NORM_NO_LN_PIPE", "1")
+    _ln_fwd(1500, 12288, torch.bfloat16, 100, {"variant": "tma", "pipe": False})
