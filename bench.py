@@ -270,7 +270,7 @@ class Step:
 # ---------------------------------------------------------------------------
 class E2E:
     def __init__(self, kind, m, n, dtype, device, rank):
-        from fuser_b200 import fusions as F
+        from tests import fusions as F
         from fuser_b200.frontend import FusionDefinition, torch_dtype_to_nvfuser_dtype
 
         self.kind, self.m, self.n, self.dtype, self.device = kind, m, n, dtype, device

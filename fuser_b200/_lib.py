@@ -67,6 +67,7 @@ F_ROUND_SUM = 1 << 15
 F_PEER_REDUCE = 1 << 16
 F_PEER_PUBLISH = 1 << 17
 F_OUTER = 1 << 18
+F_RMS_BWD_HALF_PROJ = 1 << 19
 
 VARIANT_AUTO, VARIANT_GENERIC, VARIANT_TMA, VARIANT_CLUSTER = 0, 1, 2, 3
 FORM_CACHED, FORM_PIPE, FORM_PSMEM, FORM_FUSED_FINISH = 1, 2, 4, 8

@@ -418,10 +418,17 @@ bool try_ring_plan(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, int 
       ch = (nchunks + 255) / 256;
     }
   } else if (!pick(kFwdMaxCH)) {
-    if (forced_tpr != 0 && forced_tpr != 512) return false;
-    tpr = 512;
-    ch = 0;
-    cached = false;
+    if (d.op == B200NORM_OP_LAYERNORM_FWD && !add && forced_tpr == 256 && nchunks <= 256 * kFwdWideCH &&
+        nchunks % 256 == 0 && kn.no_ln_pipe == 0) {
+      // tuning: two 256-thread groups of the pipelined one-round kernel (rows of 5 / 6 chunks per thread)
+      tpr = 256;
+      ch = nchunks / 256;
+    } else {
+      if (forced_tpr != 0 && forced_tpr != 512) return false;
+      tpr = 512;
+      ch = 0;
+      cached = false;
+    }
   }
   int groups = kConsumerThreads / tpr;
   if (groups > 8) groups = 8;  // named-barrier ids / diminishing returns for warp-sized groups
@@ -477,7 +484,7 @@ bool try_ring_plan(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, int 
   // wherever it can run, B200NORM_NO_LN_PIPE=1 switches it off.
   const bool ln_pipe = d.op == B200NORM_OP_LAYERNORM_FWD && ch > 0 && nchunks == tpr * ch && tile_rows == 1 &&
                        tpr >= 64 && (!add || tpr >= 256) && kn.no_ln_pipe == 0 &&
-                       (C > 1 || groups == 1 || kn.ln_pipe != 0);
+                       (C > 1 || groups == 1 || ch > kFwdMaxCH || kn.ln_pipe != 0);
   bool want_psmem = d.op == B200NORM_OP_LAYERNORM_FWD && ch > 0 && es == 2 && slice_cols <= 8192 &&
                     kn.no_psmem == 0 && !ln_pipe;
   const uint32_t param_bytes = align_up(2u * (uint32_t)slice_cols * 4u, 128);
@@ -733,6 +740,9 @@ int check_desc(const b200norm_desc* d) {
     return fail(B200NORM_ERR_UNSUPPORTED, "the outer normalization backward produces dweight / dbias directly (no partial sums)");
   if ((d->flags & B200NORM_F_OUTER) && (d->flags & B200NORM_F_ADD_RESIDUAL))
     return fail(B200NORM_ERR_UNSUPPORTED, "the outer normalization has no fused residual add");
+  if ((d->flags & B200NORM_F_RMS_BWD_HALF_PROJ) &&
+      (d->op != B200NORM_OP_RMSNORM_BWD || (d->flags & B200NORM_F_RMS_BWD_CENTERED)))
+    return fail(B200NORM_ERR_BAD_ARG, "RMS_BWD_HALF_PROJ is the thunder_rms_norm_backward spelling: RMSNORM_BWD, not centred");
   if ((d->flags & B200NORM_F_OUT_DW) && !(d->flags & B200NORM_F_HAS_WEIGHT) && is_norm_bwd(d->op))
     return fail(B200NORM_ERR_BAD_ARG, "dweight requested without a weight (the builders return none)");
   return B200NORM_OK;
@@ -1214,6 +1224,7 @@ int b200norm_launch(const b200norm_desc* desc, const b200norm_tensor* inputs, in
   rp.eps = (float)d.eps;
   rp.inv_n = d.cols > 0 ? (float)(1.0 / (double)d.cols) : 0.f;
   rp.n_f = (float)d.cols;
+  rp.proj_scale = (d.flags & B200NORM_F_RMS_BWD_HALF_PROJ) ? 0.5f : 1.0f;
   rp.flags = d.flags;
   void* dw = nullptr;
   void* db = nullptr;

@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(kMaxBlock, 1) norm_bwd_ring_kernel(const RowPa
         if (CACHE && r == nrows - 1) ring.refill();  // g / x_hat live in registers: the stage is free
         // dx = invstd * g - (invstd/N) * sum(g x_hat) * x_hat - (invstd/N) * sum(g)  =  A g + B x_hat + C
         const float a_n = invstd * p.inv_n;
-        const float b_s = -(a_n * s[1]);
+        const float b_s = -(a_n * s[1]) * p.proj_scale;
         const float c_s = centered ? -(a_n * s[0]) : 0.f;
         const float2 A = is2;
         const float2 B = f2(b_s);
@@ -656,7 +656,7 @@ __global__ void __launch_bounds__(kMaxBlock, 1) norm_bwd_pipe_kernel(const RowPa
       constexpr bool FMA_XHAT = LN && sizeof(T) == 2;
       const float nmi_s = -mean_a * invstd;
       const float a_n = invstd * p.inv_n;
-      const float b_s = -(a_n * tot[1]);
+      const float b_s = -(a_n * tot[1]) * p.proj_scale;
       const float c_s = centered ? -(a_n * tot[0]) : 0.f;
       const float2 A = f2(invstd), B = f2(b_s), C = f2(c_s), is2 = f2(invstd), nmean = f2(-mean_a);
       const float2 Bx = f2(b_s * invstd);

@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(kGenericThreads) generic_row_kernel(const RowP
         const float xh = (IO<T>::to_f32(b[c]) - mean) * invstd;
         float gg = IO<T>::to_f32(a[c]);
         if (wgt != nullptr) gg *= IO<T>::to_f32(wgt[c]);
-        o[c] = IO<T>::from_f32(aa * ((p.n_f * gg - s1) - xh * s[1]));
+        o[c] = IO<T>::from_f32(aa * ((p.n_f * gg - s1) - xh * (s[1] * p.proj_scale)));
       }
     } else if constexpr (OP == G_REDUCE_INNER) {
       // sum / amax / fmax over the row -> stat1-less: result goes to out0[row] (io dtype)

@@ -79,6 +79,9 @@ __global__ void __launch_bounds__(kMaxBlock, 1) layernorm_fwd_pipe_kernel(const 
 
   const int n = ring.ntiles_g;
   const int64_t row_first = ring.row0, row_step = ring.row_step;
+  uint8_t* yrow = out_row_ptr<T>(p, row_first, g.crank, g.gtid);  // running pointers: no 64-bit multiply per row
+  const size_t y_step = (size_t)row_step * (size_t)p.out_stride * sizeof(T);
+  int64_t row = row_first;
   uint32_t c1_off = ring.ring_off_g, c1_bar = ring.bar_g, c1_s = 0, c1_phase = 0;
   uint32_t c2_off = ring.ring_off_g, c2_bar = ring.bar_g, c2_s = 0, c2_phase = 0;
   auto advance = [&](uint32_t& off, uint32_t& bar, uint32_t& s, uint32_t& phase) {
@@ -160,22 +163,7 @@ __global__ void __launch_bounds__(kMaxBlock, 1) layernorm_fwd_pipe_kernel(const 
     float mean, m2;
     {
       const float* set = red_slots + par * (kRedSetBytes / 4);
-      float ms[WPG];
-      float sm = 0.f, s2 = 0.f;
-#pragma unroll
-      for (int w = 0; w < WPG; ++w) {
-        ms[w] = set[w];
-        sm += ms[w];
-        s2 += set[kMaxWarpsPerGroup + w];
-      }
-      mean = sm * (1.0f / WPG);
-      float dev = 0.f;
-#pragma unroll
-      for (int w = 0; w < WPG; ++w) {
-        const float d = ms[w] - mean;
-        dev = fmaf(d, d, dev);
-      }
-      m2 = fmaf(dev, kWarpN, s2);
+      welford_combine_equal<WPG>(set, set + kMaxWarpsPerGroup, kWarpN, mean, m2);
     }
     if (g.csize > 1) {
       const uint32_t set = par * kClsSetBytes;
@@ -207,9 +195,7 @@ __global__ void __launch_bounds__(kMaxBlock, 1) layernorm_fwd_pipe_kernel(const 
     }
     const float invstd = rsqrt_fast(m2 * p.inv_n + p.eps);
     // ---- second pass of row k: y = (x - mean) * invstd * w + b ----
-    const int64_t row = row_first + (int64_t)k * row_step;
     const uint8_t* xrow = smem_raw + c2_off + 16u * (uint32_t)g.gtid;
-    uint8_t* yrow = out_row_ptr<T>(p, row, g.crank, g.gtid);
     const float2 is2 = f2(invstd), nmean = f2(-mean), nmi = f2(-mean * invstd);
 #pragma unroll
     for (int j = 0; j < CH; ++j) {
@@ -251,6 +237,8 @@ __global__ void __launch_bounds__(kMaxBlock, 1) layernorm_fwd_pipe_kernel(const 
       if (k + p.depth < n) ring.issue_rows(1, row_first + (int64_t)(k + p.depth) * row_step, c2_off, c2_bar);
     }
     advance(c2_off, c2_bar, c2_s, c2_phase);
+    yrow += y_step;
+    row += row_step;
   }
   tl_mark(p, 3);
   ring_teardown(p);

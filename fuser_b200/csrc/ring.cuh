@@ -76,6 +76,7 @@ struct RowParams {
   float eps;
   float inv_n;
   float n_f;
+  float proj_scale;  // norm backward: factor on the projection term (1, or 1/2 for B200NORM_F_RMS_BWD_HALF_PROJ)
   uint32_t flags;
   // pipeline geometry (filled by the planner)
   int32_t groups;      // consumer groups per CTA
@@ -144,6 +145,43 @@ __device__ __forceinline__ void tl_mark(const RowParams& p, int slot) {
 }
 
 // barrier block at the start of dynamic smem:  full[groups*depth] | clbar[groups]
+
+// Welford pairs of M equal-count partial sets, stored as means[M] | m2s[M] (16-byte aligned when M >= 4), combined
+// in closed form: mean = avg(mean_i), M2 = sum(M2_i) + n_each * sum((mean_i - mean)^2). Fixed order: every
+// caller gets the same bits. Vector loads and packed adds: this runs once per row in every thread.
+template <int M>
+__device__ __forceinline__ void welford_combine_equal(const float* means, const float* m2s, float n_each, float& mean,
+                                                      float& m2) {
+  static_assert(M == 2 || M == 4 || M == 8 || M == 16, "partial sets: 2, 4, 8 or 16");
+  if constexpr (M == 2) {
+    const float2 a = *reinterpret_cast<const float2*>(means);
+    const float2 b = *reinterpret_cast<const float2*>(m2s);
+    mean = (a.x + a.y) * 0.5f;
+    const float d = a.x - a.y;
+    m2 = fmaf(d * d, 0.5f * n_each, b.x + b.y);
+  } else {
+    float2 mv[M / 2];
+    float2 sm = f2(0.f), s2 = f2(0.f);
+#pragma unroll
+    for (int q = 0; q < M / 4; ++q) {
+      const float4 a = *reinterpret_cast<const float4*>(means + 4 * q);
+      const float4 b = *reinterpret_cast<const float4*>(m2s + 4 * q);
+      mv[2 * q] = make_float2(a.x, a.y);
+      mv[2 * q + 1] = make_float2(a.z, a.w);
+      sm = f2add(sm, f2add(mv[2 * q], mv[2 * q + 1]));
+      s2 = f2add(s2, f2add(make_float2(b.x, b.y), make_float2(b.z, b.w)));
+    }
+    mean = (sm.x + sm.y) * (1.0f / M);
+    const float2 nm = f2(-mean);
+    float2 dev = f2(0.f);
+#pragma unroll
+    for (int q = 0; q < M / 2; ++q) {
+      const float2 d = f2add(mv[q], nm);
+      dev = f2fma(d, d, dev);
+    }
+    m2 = fmaf(dev.x + dev.y, n_each, s2.x + s2.y);
+  }
+}
 
 // ---------------------------------------------------------------------------
 // Consumer-group context: identity of the thread inside its group and the state of

@@ -194,7 +194,8 @@ class FusionDefinition:
             mask = ("dx" in want, "dw" in want)
             dx, dw = K.rms_norm_bwd(r["dy"], r["x"], r["stat"], r.get("w"), mask,
                                     stat_is_rms=bool(m.flags & L.F_STAT_IS_RMS),
-                                    centered=bool(m.flags & L.F_RMS_BWD_CENTERED), **kw)
+                                    centered=bool(m.flags & L.F_RMS_BWD_CENTERED),
+                                    half_projection=bool(m.flags & L.F_RMS_BWD_HALF_PROJ), **kw)
             res = {"dx": dx, "dw": dw}
         outs = []
         for node, role in zip(self._outputs, m.outputs):

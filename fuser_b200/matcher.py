@@ -42,6 +42,11 @@ class Poly:
 
     __slots__ = ("terms",)
 
+    # A term disappears only when its contributions CANCEL (|c| <= _CANCEL * sum |contribution|), never because
+    # it is small next to the polynomial's other terms: an epsilon of 1e-12 next to a variance is a term like
+    # any other, and two fusions that differ in it are different segments.
+    _CANCEL = 1e-12
+
     def __init__(self, terms: Optional[dict] = None):
         self.terms: dict[tuple, float] = terms or {}
 
@@ -56,11 +61,18 @@ class Poly:
 
     # -- helpers
     def clean(self) -> "Poly":
-        if not self.terms:
-            return self
-        mx = max(abs(c) for c in self.terms.values())
-        self.terms = {k: c for k, c in self.terms.items() if abs(c) > 1e-9 * max(mx, 1e-300) and c == c}
+        self.terms = {k: c for k, c in self.terms.items() if c != 0.0 and c == c}
         return self
+
+    @staticmethod
+    def _accumulate(pairs) -> "Poly":
+        """Sum (key, coefficient) contributions; a key whose contributions cancel is dropped."""
+        t: dict = {}
+        mag: dict = {}
+        for k, c in pairs:
+            t[k] = t.get(k, 0.0) + c
+            mag[k] = mag.get(k, 0.0) + abs(c)
+        return Poly({k: c for k, c in t.items() if c == c and abs(c) > Poly._CANCEL * mag[k]})
 
     def key(self) -> tuple:
         return tuple(sorted((k, _round(c)) for k, c in self.terms.items()))
@@ -70,10 +82,7 @@ class Poly:
 
     # -- arithmetic
     def __add__(self, o: "Poly") -> "Poly":
-        t = dict(self.terms)
-        for k, c in o.terms.items():
-            t[k] = t.get(k, 0.0) + c
-        return Poly(t).clean()
+        return Poly._accumulate(itertools.chain(self.terms.items(), o.terms.items()))
 
     def scale(self, c: float) -> "Poly":
         return Poly({k: v * c for k, v in self.terms.items()}).clean()
@@ -92,12 +101,8 @@ class Poly:
         return tuple(sorted(((atom, e) for atom, e in d.items() if e != 0), key=repr))
 
     def __mul__(self, o: "Poly") -> "Poly":
-        t: dict = {}
-        for ka, ca in self.terms.items():
-            for kb, cb in o.terms.items():
-                k = Poly._mul_keys(ka, kb)
-                t[k] = t.get(k, 0.0) + ca * cb
-        return Poly(t).clean()
+        return Poly._accumulate((Poly._mul_keys(ka, kb), ca * cb)
+                                for ka, ca in self.terms.items() for kb, cb in o.terms.items())
 
     def pow(self, e: Fraction) -> "Poly":
         if e == 1:
@@ -370,9 +375,10 @@ def def_softmax_bwd(ops, dy, y, log, axis=-1):
     return {"dx": ops.sub(g, ops.mul(y, ops.sum(g, dims=last, keepdim=True)))}
 
 
-def def_norm_bwd(ops, dy, x, mean, stat, w, stat_is_rms, centered):
-    """normalization.cpp:382-436 (LayerNorm), :438-485 (RMSNorm, centred), :487-535 / the Python
-    trace benchmarks/python/test_rmsnorm_bwd.py:20-76 (RMSNorm, textbook)."""
+def def_norm_bwd(ops, dy, x, mean, stat, w, stat_is_rms, centered, half_projection=False):
+    """normalization.cpp:382-436 (LayerNorm), :438-485 (RMSNorm, centred), the Python trace
+    benchmarks/python/test_rmsnorm_bwd.py:20-76 (RMSNorm, textbook) and :487-535 (thunder_rms_norm_backward
+    as the C++ builder writes it: the projection term carries a factor 1/2)."""
     last = [x.ndim - 1]
     outer = list(range(x.ndim - 1))
     st = _bcast_rows(ops, stat, x)
@@ -384,7 +390,10 @@ def def_norm_bwd(ops, dy, x, mean, stat, w, stat_is_rms, centered):
     inner = ops.mul(n, g)
     if centered:
         inner = ops.sub(inner, ops.sum(g, dims=last, keepdim=True))
-    inner = ops.sub(inner, ops.mul(xh, ops.sum(ops.mul(g, xh), dims=last, keepdim=True)))
+    proj = ops.mul(xh, ops.sum(ops.mul(g, xh), dims=last, keepdim=True))
+    if half_projection:
+        proj = ops.mul(proj, 0.5)
+    inner = ops.sub(inner, proj)
     dx = ops.mul(ops.mul(ops.reciprocal(n), invstd), inner)
     out = {"dx": dx, "db": ops.sum(dy, dims=outer)}
     out["dw"] = ops.sum(ops.mul(dy, xh), dims=outer)
@@ -687,19 +696,21 @@ def match_fusion(fd) -> Match:
             if n_v > 1:
                 continue
             if n_s == 1:  # RMSNorm backward
-                for stat_is_rms in (False, True):
-                    for centered in (False, True):
+                for stat_is_rms, centered, half in ((False, False, False), (False, True, False), (True, False, False),
+                                                    (True, True, False), (True, False, True), (False, False, True)):
                         names = try_candidate(
                             lambda: def_norm_bwd(ops, T(a), T(b_), None, T(stats[0]), T(w) if w else None,
-                                                 stat_is_rms, centered), {})
+                                                 stat_is_rms, centered, half), {})
                         if names and "db" not in names:
                             flags = (L.F_HAS_WEIGHT if w else 0) | (L.F_STAT_IS_RMS if stat_is_rms else 0)
                             flags |= L.F_RMS_BWD_CENTERED if centered else 0
+                            flags |= L.F_RMS_BWD_HALF_PROJ if half else 0
                             roles = {"dy": I(a), "x": I(b_), "stat": I(stats[0])}
                             if w:
                                 roles["w"] = I(w)
                             return Match(L.OP_RMSNORM_BWD, flags, 0.0, io, roles, names,
-                                         description="rms_norm_backward")
+                                         description="thunder_rms_norm_backward (halved projection)" if half
+                                         else "rms_norm_backward")
             if n_s == 2:  # LayerNorm backward
                 for mean, st in ((stats[0], stats[1]), (stats[1], stats[0])):
                     names = try_candidate(

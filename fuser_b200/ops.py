@@ -208,9 +208,12 @@ def layer_norm_bwd(dy, x, mean, invstd, weight=None, output_mask=(True, True, Tr
 
 
 def rms_norm_bwd(dy, x, stat, weight=None, output_mask=(True, True), *, stat_is_rms=False, centered=False,
-                 partials_f32=False, peer_reduce=False, variant=L.VARIANT_AUTO, cluster_size=0):
-    """dx, dweight. ``centered`` keeps the -sum(g) term of the C++ rms_norm_backward builder."""
+                 half_projection=False, partials_f32=False, peer_reduce=False, variant=L.VARIANT_AUTO, cluster_size=0):
+    """dx, dweight. ``centered`` keeps the -sum(g) term of the C++ rms_norm_backward builder;
+    ``half_projection`` is thunder_rms_norm_backward as written (normalization.cpp:487-535: the projection
+    term carries a factor 1/2)."""
     flags = (L.F_STAT_IS_RMS if stat_is_rms else 0) | (L.F_RMS_BWD_CENTERED if centered else 0)
+    flags |= L.F_RMS_BWD_HALF_PROJ if half_projection else 0
     return _norm_bwd(L.OP_RMSNORM_BWD, dy, x, [stat], weight, flags, output_mask, partials_f32, variant,
                      cluster_size, peer_reduce)
 

@@ -160,7 +160,13 @@ enum {
    * LAYERNORM_BWD | OUTER is its backward (benchmarks/python/normalization.py:98-190): in dy[M,N], x[M,N],
    * mean[N], invstd[N] (fp32), weight[N]?; out dx[M,N]?, dweight[N]?, dbias[N]? (io dtype) — column sums taken
    * inside the kernel (no partial-sum / peer flags). */
-  B200NORM_F_OUTER = 1u << 18
+  B200NORM_F_OUTER = 1u << 18,
+  /* RMSNORM_BWD: the projection term carries a factor 1/2 — thunder_rms_norm_backward as the C++ builder
+   * writes it (csrc/ops/normalization.cpp:487-535: inv_rms_mul2 = 1 / (2 rms) scales x * sum(-g x / rms^2) / N),
+   * used by tests/cpp/test_combined_inner_outer_reduction.cpp:1197:
+   *   dx = g / rms - x * sum(g x) / (2 N rms^3)      (the textbook form has no 2)
+   * dweight is unaffected. Parity is with the fusion as written, so the spelling is a segment kind. */
+  B200NORM_F_RMS_BWD_HALF_PROJ = 1u << 19
 };
 
 /* desc.variant: 0 lets the library choose (the dispatch rule mirrors the accept

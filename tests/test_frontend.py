@@ -110,20 +110,37 @@ def test_equivalent_respellings_match_and_near_misses_do_not():
     with pytest.raises(UnsupportedSegment):
         build(pointwise).segment()
 
-    # near miss 5: the C++ thunder_rms_norm_backward text halves the projection term
-    # (csrc/ops/normalization.cpp:487-535); it is not the textbook backward and no kernel computes it
-    def thunder_cpp(fd):
-        dy = fd.define_tensor(shape=[-1, -1], dtype=DataType.Float)
+
+
+def test_thunder_rms_norm_backward_as_written():
+    """csrc/ops/normalization.cpp:487-535: the C++ builder's dx carries 1 / (2 rms) on the projection term. The
+    fusion as written is its own segment kind (B200NORM_F_RMS_BWD_HALF_PROJ), distinct from the textbook form."""
+    for dt in (DataType.Float, DataType.BFloat16):
+        for weight in (True, False):
+            m = build(lambda fd: F.thunder_rms_norm_bwd_cpp(fd, dt, weight)).segment()
+            assert m.op == L.OP_RMSNORM_BWD
+            assert m.flags & L.F_RMS_BWD_HALF_PROJ and m.flags & L.F_STAT_IS_RMS and not m.flags & L.F_RMS_BWD_CENTERED
+            assert bool(m.flags & L.F_HAS_WEIGHT) == weight
+            assert m.outputs == (["dx", "dw"] if weight else ["dx"])
+    m = build(lambda fd: F.rmsnorm_bwd_py(fd, DataType.BFloat16)).segment()  # the Python trace compensates with * 2
+    assert not m.flags & L.F_RMS_BWD_HALF_PROJ
+
+
+def test_epsilon_is_part_of_the_match():
+    """A tiny epsilon (BERT-style 1e-12) must neither vanish from the normal form nor be replaced by another
+    small constant of the fusion."""
+    def ln(fd, eps, scale):
         x = fd.define_tensor(shape=[-1, -1], dtype=DataType.Float)
-        rms = fd.define_tensor(shape=[-1, 1], dtype=DataType.Float)
-        w = fd.define_tensor(shape=[-1], dtype=DataType.Float)
-        gw = fd.ops.mul(dy, fd.ops.broadcast(w, is_broadcast_dim=[True, False]))
-        t = fd.ops.mul(fd.ops.mul(fd.ops.neg(gw), x), fd.ops.reciprocal(fd.ops.mul(rms, rms)))
-        inner = fd.ops.broadcast(fd.ops.sum(t, dims=[1]), is_broadcast_dim=[False, True])
-        k = fd.ops.mul(fd.ops.reciprocal(fd.ops.mul(rms, 2.0)), fd.ops.reciprocal(x.size(1)))
-        fd.add_output(fd.ops.add(fd.ops.mul(inner, fd.ops.mul(x, k)), fd.ops.mul(gw, fd.ops.reciprocal(rms))))
-    with pytest.raises(UnsupportedSegment):
-        build(thunder_cpp).segment()
+        var, mean = fd.ops.var_mean(x, dims=[1], correction=0, keepdim=True)
+        y = fd.ops.mul(fd.ops.sub(x, mean), fd.ops.rsqrt(fd.ops.add(var, eps)))
+        if scale is not None:  # another constant below one elsewhere in the fusion
+            y = fd.ops.mul(fd.ops.add(y, scale), 1.0)
+        fd.add_output(y)
+    for eps in (1e-12, 1e-5, 0.25):
+        m = build(lambda fd: ln(fd, eps, None)).segment()
+        assert m.op == L.OP_LAYERNORM_FWD and m.eps == eps
+    with pytest.raises(UnsupportedSegment):  # y + 0.5 is not a layer norm, whatever epsilon is tried
+        build(lambda fd: ln(fd, 1e-12, 0.5)).segment()
 
 
 def test_api_surface_and_errors():

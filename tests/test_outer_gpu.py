@@ -11,7 +11,7 @@ import pytest
 import torch
 
 from fuser_b200 import _lib as L
-from fuser_b200 import fusions as F
+from tests import fusions as F
 from fuser_b200 import ops
 from fuser_b200.frontend import FusionDefinition
 from fuser_b200.ir import DataType
