@@ -68,6 +68,9 @@ F_PEER_REDUCE = 1 << 16
 F_PEER_PUBLISH = 1 << 17
 F_OUTER = 1 << 18
 F_RMS_BWD_HALF_PROJ = 1 << 19
+F_NO_Y = 1 << 20
+F_STAT_VAR = 1 << 21
+F_STAT_M2 = 1 << 22
 
 VARIANT_AUTO, VARIANT_GENERIC, VARIANT_TMA, VARIANT_CLUSTER = 0, 1, 2, 3
 FORM_CACHED, FORM_PIPE, FORM_PSMEM, FORM_FUSED_FINISH = 1, 2, 4, 8
@@ -227,7 +230,7 @@ def _raise(code: int):
     raise B200NormError(code, msg)
 
 
-def make_desc(op, io_dtype, rows, cols, eps=0.0, flags=0, variant=VARIANT_AUTO, cluster_size=0) -> Desc:
+def make_desc(op, io_dtype, rows, cols, eps=0.0, flags=0, variant=VARIANT_AUTO, cluster_size=0, correction=0) -> Desc:
     d = Desc()
     d.abi_version = ABI_VERSION
     d.op = op
@@ -238,6 +241,7 @@ def make_desc(op, io_dtype, rows, cols, eps=0.0, flags=0, variant=VARIANT_AUTO, 
     d.eps = eps
     d.flags = flags
     d.cluster_size = cluster_size
+    d.reserved[0] = correction
     return d
 
 

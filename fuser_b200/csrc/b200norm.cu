@@ -163,7 +163,16 @@ Knobs read_knobs() {
 
 int elem_size(int dt) { return dt == B200NORM_DT_F32 ? 4 : 2; }
 
-bool is_row_op(int op) { return op >= B200NORM_OP_LAYERNORM_FWD && op <= B200NORM_OP_LOGSOFTMAX_BWD; }
+bool is_row_op(int op) {  // ops with a TMA-ring kernel family
+  return (op >= B200NORM_OP_LAYERNORM_FWD && op <= B200NORM_OP_LOGSOFTMAX_BWD) || op == B200NORM_OP_REDUCE_INNER ||
+         op == B200NORM_OP_REDUCE_OUTER;
+}
+// ops that keep per-thread column accumulators and finish fp32 column sums (dgamma / dbeta, plain column sums)
+bool has_column_sums(const b200norm_desc& d) {
+  if (d.op == B200NORM_OP_REDUCE_OUTER) return true;
+  return (d.op == B200NORM_OP_LAYERNORM_BWD || d.op == B200NORM_OP_RMSNORM_BWD) &&
+         (d.flags & (B200NORM_F_OUT_DW | B200NORM_F_OUT_DB)) != 0;
+}
 bool is_norm_bwd(int op) { return op == B200NORM_OP_LAYERNORM_BWD || op == B200NORM_OP_RMSNORM_BWD; }
 bool is_softmax_op(int op) { return op >= B200NORM_OP_SOFTMAX_FWD && op <= B200NORM_OP_LOGSOFTMAX_BWD; }
 bool is_outer(const b200norm_desc& d) { return (d.flags & B200NORM_F_OUTER) != 0; }
@@ -193,6 +202,11 @@ uint64_t algorithmic_bytes(const b200norm_desc& d) {
       // reads or writes, as benchmarks/python/core.py:compute_total_iobytes counts them)
       const uint64_t extra = ((d.flags & B200NORM_F_ADD_RESIDUAL) ? s * M * N : 0) +
                              ((d.flags & B200NORM_F_ADD_RESIDUAL) && (d.flags & B200NORM_F_OUT_SUM) ? s * M * N : 0);
+      if (d.op == B200NORM_OP_LAYERNORM_FWD && (d.flags & B200NORM_F_NO_Y)) {
+        // var_mean / welford: the input once, one fp32 value per requested statistic and row
+        const uint64_t nstat = ((d.flags & B200NORM_F_OUT_MEAN) ? 1 : 0) + ((d.flags & B200NORM_F_OUT_INVSTD) ? 1 : 0);
+        return s * M * N + 4 * nstat * M;
+      }
       if (d.op == B200NORM_OP_LAYERNORM_FWD && (d.flags & B200NORM_F_OUTER)) return s * 2 * (M * N + N) + 4 * 2 * N;
       if (d.op == B200NORM_OP_LAYERNORM_FWD) return s * 2 * (M * N + N) + 4 * 2 * M + extra;
       return s * (2 * M * N + N) + 4 * M + extra;
@@ -247,6 +261,8 @@ uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 #define B200_RING_KERNEL_FOR(T, SUF)                                                                         \
   template <>                                                                                                \
   RingKernel ring_kernel_for<T>(int op, int tpr, int ch, bool cached, bool psmem, bool add, bool pipe) {      \
+    if (op == B200NORM_OP_REDUCE_INNER) return ring_reduce_inner_kernel_##SUF(tpr, ch);                      \
+    if (op == B200NORM_OP_REDUCE_OUTER) return ring_colsum_kernel_##SUF(tpr, ch);                            \
     if (pipe && op == B200NORM_OP_LAYERNORM_FWD) return ring_ln_pipe_kernel_##SUF(tpr, ch, add);             \
     if (add) return ring_add_kernel_##SUF(op, tpr, ch, psmem);                                               \
     if (is_norm_bwd(op) && !cached && pipe) return ring_bwd_pipe_kernel_##SUF(op, tpr, ch);                  \
@@ -360,6 +376,7 @@ bool try_ring_plan(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, int 
   const int ns = add ? 2 : n_streams(d.op);
   const bool bwd = is_norm_bwd(d.op);
   const bool ln_bwd = d.op == B200NORM_OP_LAYERNORM_BWD;
+  const bool colsum = d.op == B200NORM_OP_REDUCE_OUTER;  // per-thread column accumulators, no per-row reduction
 
   // Threads per row slice and chunks per thread. Forward-type kernels: the smallest group
   // that keeps the slice in registers at <= kFwdMaxCH chunks per thread (fewer, fatter
@@ -381,7 +398,9 @@ bool try_ring_plan(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, int 
     }
     return false;
   };
-  if (bwd) {
+  if (colsum) {
+    if (!pick(kFwdMaxCH)) return false;  // CH * VEC accumulators per thread; wider rows are split over a cluster
+  } else if (bwd) {
     const bool force_reread = kn.bwd_reread != 0;
     if (force_reread || !pick(kBwdCacheCH)) {
       cached = false;
@@ -548,7 +567,7 @@ bool try_ring_plan(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, int 
   }
   p.block = groups * tpr;
   const uint32_t ring_bytes = (uint32_t)p.stages * p.stage_bytes;
-  if (bwd) {
+  if (bwd || colsum) {
     const uint32_t acc_bytes = (uint32_t)partial_k(d.op) * (uint32_t)slice_cols * 4;
     if (acc_bytes > ring_bytes) return false;
   }
@@ -562,7 +581,7 @@ bool try_ring_plan(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, int 
   p.grid = (int)(nclusters * C);
   p.nparts = (int)nclusters;
   p.n_launches = 1;
-  if (bwd && (d.flags & (B200NORM_F_OUT_DW | B200NORM_F_OUT_DB))) p.n_launches = 2;
+  if (has_column_sums(d)) p.n_launches = 2;
   *out = p;
   return true;
 }
@@ -571,7 +590,7 @@ int make_plan_uncached(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, 
   const DeviceInfo& dev = ctx.info;
   Plan p;
   const bool bwd = is_norm_bwd(d.op);
-  const bool want_cols = bwd && (d.flags & (B200NORM_F_OUT_DW | B200NORM_F_OUT_DB));
+  const bool want_cols = has_column_sums(d);
 
   // workspace: large enough for whichever family ends up running
   uint64_t ws = B200NORM_WS_HEADER_BYTES;
@@ -579,8 +598,6 @@ int make_plan_uncached(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, 
     int maxparts = generic_nsplit(d.rows);
     if (dev.sm_count > maxparts) maxparts = dev.sm_count;
     ws += (uint64_t)maxparts * partial_k(d.op) * d.cols * 4;
-  } else if (d.op == B200NORM_OP_REDUCE_OUTER) {
-    ws += (uint64_t)generic_nsplit(d.rows) * d.cols * 4;
   }
 
   bool ring_ok = false;
@@ -601,7 +618,7 @@ int make_plan_uncached(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, 
       // prefer the smallest cluster that gives a register-resident slice (forward-type) or
       // per-thread column accumulators (backward) with >= 3 stages per group: a cluster costs
       // a DSMEM exchange per row and leaves SMs idle (clusters never span GPCs)
-      const bool good = (cand.cached || is_norm_bwd(d.op)) && cand.depth >= 3;
+      const bool good = (cand.cached || is_norm_bwd(d.op) || d.op == B200NORM_OP_REDUCE_INNER) && cand.depth >= 3;
       if (good || forced_c > 0) {
         best = cand;
         break;
@@ -624,7 +641,7 @@ int make_plan_uncached(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, 
     if (g < 1) g = 1;
     p.grid = (int)g;
     p.n_launches = 1;
-    if (want_cols) {
+    if (want_cols && bwd) {
       p.nparts = generic_nsplit(d.rows);
       p.rows_per_split = (int)ceil_div64(d.rows, p.nparts);
       p.n_launches = 3;
@@ -740,6 +757,18 @@ int check_desc(const b200norm_desc* d) {
     return fail(B200NORM_ERR_UNSUPPORTED, "the outer normalization backward produces dweight / dbias directly (no partial sums)");
   if ((d->flags & B200NORM_F_OUTER) && (d->flags & B200NORM_F_ADD_RESIDUAL))
     return fail(B200NORM_ERR_UNSUPPORTED, "the outer normalization has no fused residual add");
+  if (d->flags & (B200NORM_F_NO_Y | B200NORM_F_STAT_VAR | B200NORM_F_STAT_M2)) {
+    if (d->op != B200NORM_OP_LAYERNORM_FWD || (d->flags & B200NORM_F_OUTER))
+      return fail(B200NORM_ERR_UNSUPPORTED, "NO_Y / STAT_VAR / STAT_M2 apply to LAYERNORM_FWD over the last axis");
+    if ((d->flags & B200NORM_F_STAT_VAR) && (d->flags & B200NORM_F_STAT_M2))
+      return fail(B200NORM_ERR_BAD_ARG, "STAT_VAR and STAT_M2 exclude each other");
+    if ((d->flags & B200NORM_F_NO_Y) &&
+        (d->flags & (B200NORM_F_HAS_WEIGHT | B200NORM_F_HAS_BIAS | B200NORM_F_ADD_RESIDUAL)))
+      return fail(B200NORM_ERR_BAD_ARG, "a statistics-only segment has no weight, bias or residual");
+    if ((d->flags & B200NORM_F_NO_Y) && !(d->flags & (B200NORM_F_OUT_MEAN | B200NORM_F_OUT_INVSTD)))
+      return fail(B200NORM_ERR_BAD_ARG, "NO_Y without a requested statistic has no output");
+    if (d->reserved[0] < 0) return fail(B200NORM_ERR_BAD_ARG, "correction must be non-negative");
+  }
   if ((d->flags & B200NORM_F_RMS_BWD_HALF_PROJ) &&
       (d->op != B200NORM_OP_RMSNORM_BWD || (d->flags & B200NORM_F_RMS_BWD_CENTERED)))
     return fail(B200NORM_ERR_BAD_ARG, "RMS_BWD_HALF_PROJ is the thunder_rms_norm_backward spelling: RMSNORM_BWD, not centred");
@@ -821,7 +850,7 @@ RingKernel generic_kernel_for(int op) {
 template <typename T>
 int launch_typed(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, const Plan& plan, RowParams& rp, void* dw,
                  void* db, float* sums_f32, void* ws_header, cudaStream_t stream) {
-  const bool want_cols = is_norm_bwd(d.op) && (d.flags & (B200NORM_F_OUT_DW | B200NORM_F_OUT_DB));
+  const bool want_cols = has_column_sums(d);
   const int K = partial_k(d.op);
   cudaError_t err;
 
@@ -872,7 +901,7 @@ int launch_typed(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, const 
         k<<<plan.grid, kGenericThreads, 0, stream>>>(rp);
         g_launches++;
       }
-      if (want_cols) {
+      if (want_cols && is_norm_bwd(d.op)) {
         dim3 grid((unsigned)ceil_div64(d.cols, 128), (unsigned)plan.nparts);
         if (d.op == B200NORM_OP_LAYERNORM_BWD) {
           generic_colsum_kernel<T, 1><<<grid, 128, 0, stream>>>(rp, plan.rows_per_split);
@@ -1225,6 +1254,10 @@ int b200norm_launch(const b200norm_desc* desc, const b200norm_tensor* inputs, in
   rp.inv_n = d.cols > 0 ? (float)(1.0 / (double)d.cols) : 0.f;
   rp.n_f = (float)d.cols;
   rp.proj_scale = (d.flags & B200NORM_F_RMS_BWD_HALF_PROJ) ? 0.5f : 1.0f;
+  {
+    const double denom = (double)d.cols - (double)d.reserved[0];  // var = M2 / max(N - correction, 0), as at::var_mean
+    rp.var_scale = (float)(1.0 / (denom > 0.0 ? denom : 0.0));
+  }
   rp.flags = d.flags;
   void* dw = nullptr;
   void* db = nullptr;
@@ -1283,8 +1316,11 @@ int b200norm_launch(const b200norm_desc* desc, const b200norm_tensor* inputs, in
         rp.bias = b;
         if (!is_aligned16(b)) aligned = false;
       }
-      NEED_OUT(1);
-      CHECK(bind_out_matrix(&rp.out0, &rp.out_stride, "y"));
+      const bool no_y = ln && (d.flags & B200NORM_F_NO_Y) != 0;
+      if (!no_y) {
+        NEED_OUT(1);
+        CHECK(bind_out_matrix(&rp.out0, &rp.out_stride, "y"));
+      }
       if (add && (d.flags & B200NORM_F_OUT_SUM)) {
         NEED_OUT(1);
         CHECK(bind_out_matrix(&rp.out1, &rp.out1_stride, "sum"));
@@ -1512,7 +1548,8 @@ int b200norm_launch(const b200norm_desc* desc, const b200norm_tensor* inputs, in
   // forward / backward): results are bit-identical whatever SM processes a row. The norm
   // backward keeps the static split so that its per-CTA dgamma / dbeta partial sums — and with
   // them the output bits — are the same on every run.
-  if (plan.variant == B200NORM_VARIANT_TMA && plan.cluster == 1 && !is_norm_bwd(d.op) && workspace != nullptr &&
+  if (plan.variant == B200NORM_VARIANT_TMA && plan.cluster == 1 && !is_norm_bwd(d.op) &&
+      d.op != B200NORM_OP_REDUCE_OUTER && workspace != nullptr &&
       workspace_bytes >= B200NORM_WS_HEADER_BYTES && (reinterpret_cast<uintptr_t>(workspace) & 15u) == 0 &&
       kn.static_sched == 0) {
     // Pool size (measured on several B200s, whose per-SM imbalance differs: the static split loses

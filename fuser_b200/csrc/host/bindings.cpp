@@ -23,22 +23,24 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   });
 
   py::class_<SegmentSpec>(m, "SegmentSpec")
-      .def(py::init([](int op, uint32_t flags, double eps, int variant, int cluster_size) {
+      .def(py::init([](int op, uint32_t flags, double eps, int variant, int cluster_size, int correction) {
              SegmentSpec s;
              s.op = op;
              s.flags = flags;
              s.eps = eps;
              s.variant = variant;
              s.cluster_size = cluster_size;
+             s.correction = correction;
              return s;
            }),
            py::arg("op"), py::arg("flags") = 0, py::arg("eps") = 0.0, py::arg("variant") = 0,
-           py::arg("cluster_size") = 0)
+           py::arg("cluster_size") = 0, py::arg("correction") = 0)
       .def_readwrite("op", &SegmentSpec::op)
       .def_readwrite("flags", &SegmentSpec::flags)
       .def_readwrite("eps", &SegmentSpec::eps)
       .def_readwrite("variant", &SegmentSpec::variant)
-      .def_readwrite("cluster_size", &SegmentSpec::cluster_size);
+      .def_readwrite("cluster_size", &SegmentSpec::cluster_size)
+      .def_readwrite("correction", &SegmentSpec::correction);
 
   py::class_<NormExecutor>(m, "NormExecutor")
       .def(py::init<int64_t, int64_t, int64_t, int64_t>(), py::arg("fusion_id") = 0, py::arg("concrete_id") = 0,

@@ -43,6 +43,7 @@ b200norm_desc make_desc(const SegmentSpec& s, int dt, int64_t rows, int64_t cols
   d.eps = s.eps;
   d.flags = s.flags;
   d.cluster_size = s.cluster_size;
+  d.reserved[0] = s.correction;
   return d;
 }
 
@@ -122,7 +123,7 @@ std::vector<at::Tensor> NormExecutor::allocateOutputs(const std::vector<at::Tens
   };
   switch (spec_.op) {
     case B200NORM_OP_LAYERNORM_FWD:
-      out.push_back(at::empty(first.sizes(), opts));
+      if (!(f & B200NORM_F_NO_Y)) out.push_back(at::empty(first.sizes(), opts));
       if ((f & B200NORM_F_ADD_RESIDUAL) && (f & B200NORM_F_OUT_SUM)) out.push_back(at::empty(first.sizes(), opts));
       if (f & B200NORM_F_OUT_MEAN) out.push_back(at::empty(stat_shape(first), f32));
       if (f & B200NORM_F_OUT_INVSTD) out.push_back(at::empty(stat_shape(first), f32));
@@ -239,6 +240,7 @@ std::vector<at::Tensor> NormExecutor::run(const std::vector<at::Tensor>& inputs,
     case B200NORM_OP_LAYERNORM_FWD:
     case B200NORM_OP_RMSNORM_FWD:
       n_mat_out = (add_fwd && (spec_.flags & B200NORM_F_OUT_SUM)) ? 2 : 1;
+      if (spec_.op == B200NORM_OP_LAYERNORM_FWD && (spec_.flags & B200NORM_F_NO_Y)) n_mat_out = 0;
       break;
     case B200NORM_OP_SOFTMAX_FWD:
     case B200NORM_OP_LOGSOFTMAX_FWD:

@@ -33,6 +33,7 @@ struct SegmentSpec {
   double eps = 0.0;
   int32_t variant = 0;     // b200norm_variant (0 = planner's choice)
   int32_t cluster_size = 0;
+  int32_t correction = 0;  // var_mean's correction (B200NORM_F_STAT_VAR), travels in desc.reserved[0]
 };
 
 class NormExecutor {

@@ -139,6 +139,7 @@ __global__ void __launch_bounds__(kMaxBlock, 1) layernorm_fwd_ring_kernel(const 
     load_params_to_regs<T, TPR, CH>(p.bias, col0_bytes, g.gtid, nchunks, -0.0f, bq);
   }
   const bool stat_writer = g.gtid == 0 && g.crank == 0;
+  const bool no_y = (p.flags & kFlagNoY) != 0;  // stand-alone var_mean / welford: statistics only
   const bool round_sum = ADD && (p.flags & kFlagRoundSum) != 0;
   const bool out_sum = ADD && p.out1 != nullptr;
 
@@ -192,7 +193,7 @@ __global__ void __launch_bounds__(kMaxBlock, 1) layernorm_fwd_ring_kernel(const 
       g.template allreduce<SumOp, 1>(m2);
       const float invstd = rsqrt_fast(m2[0] * p.inv_n + p.eps);
       const float2 is2 = f2(invstd);
-      for_each_chunk<TPR, CH>(g.gtid, nchunks, [&](int j, int coff) {
+      if (!no_y) for_each_chunk<TPR, CH>(g.gtid, nchunks, [&](int j, int coff) {
         float2 y[H], w[H], b[H];
         if constexpr (CH > 0) {
           if constexpr (PSMEM) {
@@ -216,7 +217,7 @@ __global__ void __launch_bounds__(kMaxBlock, 1) layernorm_fwd_ring_kernel(const 
       });
       if (stat_writer) {
         if (p.stat0 != nullptr) p.stat0[ring.row0 + r] = mean;
-        if (p.stat1 != nullptr) p.stat1[ring.row0 + r] = invstd;
+        if (p.stat1 != nullptr) p.stat1[ring.row0 + r] = ln_second_stat(p, m2[0], invstd);
       }
     }
     if constexpr (CH == 0) {

@@ -111,15 +111,17 @@ __global__ void __launch_bounds__(kGenericThreads) generic_row_kernel(const RowP
       }
       block_allreduce<SumOp, 1>(m2, red, phase);
       const float invstd = __frsqrt_rn(m2[0] * p.inv_n + p.eps);
-      for (int c = tid; c < N; c += kGenericThreads) {
-        float y = (xin(c) - mean) * invstd;
-        if (wgt != nullptr) y *= IO<T>::to_f32(wgt[c]);
-        if (bia != nullptr) y += IO<T>::to_f32(bia[c]);
-        o[c] = IO<T>::from_f32(y);
+      if (o != nullptr) {  // absent for a stand-alone var_mean / welford segment (kFlagNoY)
+        for (int c = tid; c < N; c += kGenericThreads) {
+          float y = (xin(c) - mean) * invstd;
+          if (wgt != nullptr) y *= IO<T>::to_f32(wgt[c]);
+          if (bia != nullptr) y += IO<T>::to_f32(bia[c]);
+          o[c] = IO<T>::from_f32(y);
+        }
       }
       if (tid == 0) {
         if (p.stat0 != nullptr) p.stat0[row] = mean;
-        if (p.stat1 != nullptr) p.stat1[row] = invstd;
+        if (p.stat1 != nullptr) p.stat1[row] = ln_second_stat(p, m2[0], invstd);
       }
     } else if constexpr (OP == G_SOFTMAX_FWD || OP == G_LOGSOFTMAX_FWD) {
       constexpr bool LOG = OP == G_LOGSOFTMAX_FWD;

@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(kMaxBlock, 1) layernorm_fwd_pipe_kernel(const 
     load_params_to_regs<T, TPR, CH>(p.bias, col0_bytes, g.gtid, p.nchunks, -0.0f, bq);
   }
   const bool stat_writer = g.gtid == 0 && g.crank == 0;
+  const bool no_y = (p.flags & kFlagNoY) != 0;  // stand-alone var_mean / welford: statistics only
   const bool round_sum = ADD && (p.flags & kFlagRoundSum) != 0;
   const bool out_sum = ADD && p.out1 != nullptr;
 
@@ -199,6 +200,7 @@ __global__ void __launch_bounds__(kMaxBlock, 1) layernorm_fwd_pipe_kernel(const 
     const float2 is2 = f2(invstd), nmean = f2(-mean), nmi = f2(-mean * invstd);
 #pragma unroll
     for (int j = 0; j < CH; ++j) {
+      if (no_y) break;
       float2 y[H], w[H], b[H];
       IO<T>::unpack2(ld_smem_u4(xrow + 16 * j * TPR), y);
       if constexpr (ADD) add_residual_chunk<T, H>(y, xrow + p.stream_bytes + 16 * j * TPR, round_sum, nullptr);
@@ -227,7 +229,7 @@ __global__ void __launch_bounds__(kMaxBlock, 1) layernorm_fwd_pipe_kernel(const 
     }
     if (stat_writer) {
       if (p.stat0 != nullptr) p.stat0[row] = mean;
-      if (p.stat1 != nullptr) p.stat1[row] = invstd;
+      if (p.stat1 != nullptr) p.stat1[row] = ln_second_stat(p, m2, invstd);
     }
     // ---- release the stage; the first warp refills it once every warp has let go ----
     __syncwarp();

@@ -58,6 +58,9 @@ constexpr uint32_t kFlagOutInvstd = 1u << 12;
 constexpr uint32_t kFlagAddResidual = 1u << 13;
 constexpr uint32_t kFlagOutSum = 1u << 14;
 constexpr uint32_t kFlagRoundSum = 1u << 15;
+constexpr uint32_t kFlagNoY = 1u << 20;
+constexpr uint32_t kFlagStatVar = 1u << 21;
+constexpr uint32_t kFlagStatM2 = 1u << 22;
 
 struct RowParams {
   // streamed operands (row-major, unit inner stride)
@@ -76,6 +79,7 @@ struct RowParams {
   float eps;
   float inv_n;
   float n_f;
+  float var_scale;   // LayerNorm forward with kFlagStatVar: 1 / max(N - correction, 0)
   float proj_scale;  // norm backward: factor on the projection term (1, or 1/2 for B200NORM_F_RMS_BWD_HALF_PROJ)
   uint32_t flags;
   // pipeline geometry (filled by the planner)
@@ -573,6 +577,14 @@ __device__ __forceinline__ void for_each_chunk(int gtid, int nchunks, F&& f) {
 __device__ __forceinline__ uint4 ld_smem_u4(const uint8_t* p) { return *reinterpret_cast<const uint4*>(p); }
 __device__ __forceinline__ void st_global_stream(void* p, const uint4& v) {
   __stcs(reinterpret_cast<uint4*>(p), v);
+}
+
+// LayerNorm forward: what is stored as the second statistic (invstd, or the variance / M2 of a stand-alone
+// var_mean / welford segment).
+__device__ __forceinline__ float ln_second_stat(const RowParams& p, float m2, float invstd) {
+  if (p.flags & kFlagStatVar) return m2 * p.var_scale;
+  if (p.flags & kFlagStatM2) return m2;
+  return invstd;
 }
 
 // Packed per-column parameters (weight / bias) of the chunks a thread owns, kept in

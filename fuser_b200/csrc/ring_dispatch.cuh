@@ -36,4 +36,13 @@ RingKernel ring_ln_pipe_kernel_f32(int tpr, int ch, bool add);
 RingKernel ring_ln_pipe_kernel_bf16(int tpr, int ch, bool add);
 RingKernel ring_ln_pipe_kernel_f16(int tpr, int ch, bool add);
 
+// plain reductions on the ring (kernels_reduce.cuh): inner sum / max / fmax (ch 1..4 or 0 with tpr 512) and the
+// column sum over the rows (ch 1..4)
+RingKernel ring_reduce_inner_kernel_f32(int tpr, int ch);
+RingKernel ring_reduce_inner_kernel_bf16(int tpr, int ch);
+RingKernel ring_reduce_inner_kernel_f16(int tpr, int ch);
+RingKernel ring_colsum_kernel_f32(int tpr, int ch);
+RingKernel ring_colsum_kernel_bf16(int tpr, int ch);
+RingKernel ring_colsum_kernel_f16(int tpr, int ch);
+
 }  // namespace b200norm

@@ -134,7 +134,7 @@ class FusionDefinition:
 
     def _check_output_dtypes(self, m: Match):
         for node, role in zip(self._outputs, m.outputs):
-            want = DataType.Float if role in ("mean", "invstd", "rms") else m.io_dtype
+            want = DataType.Float if role in ("mean", "invstd", "rms", "var", "m2") else m.io_dtype
             if node.dtype != want:
                 raise Unmatchable(f"output '{role}' has dtype {node.dtype.name}; the kernels produce {want.name}")
 
@@ -165,7 +165,18 @@ class FusionDefinition:
         want = set(m.outputs)
         if m.flags & L.F_ADD_RESIDUAL:  # norm(x + residual), optional sum output
             kw.update(residual=r["r"], want_sum="sum" in want, round_sum=bool(m.flags & L.F_ROUND_SUM))
-        if m.op == L.OP_LAYERNORM_FWD and m.flags & L.F_OUTER:
+        if m.op == L.OP_LAYERNORM_FWD and m.flags & L.F_NO_Y:  # stand-alone var_mean / welford
+            if m.flags & L.F_STAT_M2:
+                avg, m2 = K.welford(r["x"], **kw)
+                res = {"mean": avg, "m2": m2}
+            else:
+                var, mean = K.var_mean(r["x"], m.correction, want_var="var" in want, want_mean="mean" in want, **kw)
+                res = {"var": var, "mean": mean}
+        elif m.op == L.OP_REDUCE_INNER:
+            res = {"r": K.reduce_inner(r["x"], "max" if m.flags & L.F_REDUCE_MAX else "sum", **kw)}
+        elif m.op == L.OP_REDUCE_OUTER:
+            res = {"r": K.reduce_outer(r["x"], **kw)}
+        elif m.op == L.OP_LAYERNORM_FWD and m.flags & L.F_OUTER:
             o = K.outer_norm_fwd(r["x"], r.get("w"), r.get("b"), m.eps, want_mean="mean" in want,
                                  want_invstd="invstd" in want, **kw)
             res = {"y": o[0], "mean": o[1], "invstd": o[2]}
@@ -200,7 +211,7 @@ class FusionDefinition:
         outs = []
         for node, role in zip(self._outputs, m.outputs):
             t = res[role]
-            if role in ("mean", "invstd", "rms") and node.ndim == t.dim() - 1:
+            if role in ("mean", "invstd", "rms", "var", "m2") and node.ndim == t.dim() - 1:
                 t = t.squeeze(-1)
             outs.append(t)
         return outs

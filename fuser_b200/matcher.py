@@ -357,6 +357,20 @@ def def_rms_norm_fwd(ops, x, w, eps):
     return {"y": y, "invstd": invstd, "rms": ops.sqrt(var_eps)}
 
 
+def def_reduce(ops, x, kind, inner):
+    """plain reductions (scheduler/reduction.cpp:198-360): sum / max over the last axis, sum over all the others"""
+    dims = [x.ndim - 1] if inner else list(range(x.ndim - 1))
+    return {"r": (ops.sum if kind == "sum" else ops.max)(x, dims=dims, keepdim=False)}
+
+
+def def_var_mean(ops, x, correction):
+    """variance_mean / Welford over the last axis (normalization.cpp:93-158, python_direct/ops.cpp:1824-1863)"""
+    last = [x.ndim - 1]
+    var, mean = ops.var_mean(x, dims=last, correction=correction, keepdim=False)
+    _, m2, _ = ops.welford(x, dims=last)
+    return {"var": var, "mean": mean, "m2": m2}
+
+
 def def_softmax_fwd(ops, x, log, axis=-1):
     """normalization.cpp:169-189 / :212-231 (axis 0: the outer-persistent case)"""
     last = [axis % x.ndim]
@@ -412,6 +426,7 @@ class Match:
     roles: dict                # role -> index into fusion inputs (x, dy, y, w, b, mean, stat)
     outputs: list              # per fusion output: role name (y, mean, invstd, rms, dx, dw, db)
     norm_ndim: int = 1
+    correction: int = 0        # var_mean (F_STAT_VAR)
     description: str = ""
     notes: list = field(default_factory=list)
 
@@ -568,6 +583,24 @@ def match_fusion(fd) -> Match:
                         return Match(L.OP_LOGSOFTMAX_FWD if log else L.OP_SOFTMAX_FWD, L.F_OUTER if axis == 0 else 0,
                                      0.0, io, {"x": I(x)}, names,
                                      description=("log_softmax" if log else "softmax") + (" over dim 0" if axis == 0 else ""))
+            # plain reductions and stand-alone statistics (Reduction segments / variance_mean, Welford)
+            for kind, inner in (("sum", True), ("max", True), ("sum", False)):
+                names = try_candidate(lambda: def_reduce(ops, T(x), kind, inner), {})
+                if names:
+                    if inner:
+                        return Match(L.OP_REDUCE_INNER, L.F_REDUCE_MAX if kind == "max" else 0, 0.0, io, {"x": I(x)}, names,
+                                     description=f"{kind} over the last axis")
+                    return Match(L.OP_REDUCE_OUTER, 0, 0.0, io, {"x": I(x)}, names, description="sum over the outer axes")
+            corrections = sorted({int(v.attrs.get("correction", 0)) for v in fd._vals
+                                  if isinstance(v, Tensor) and v.op == "var"} | {0})
+            for corr in corrections:
+                names = try_candidate(lambda: def_var_mean(ops, T(x), corr), {})
+                if names:
+                    if "var" in names and "m2" in names:
+                        raise Unmatchable("both the variance and the sum of squared deviations requested")
+                    flags = L.F_NO_Y | (L.F_STAT_M2 if "m2" in names else L.F_STAT_VAR)
+                    return Match(L.OP_LAYERNORM_FWD, flags, 0.0, io, {"x": I(x)}, names, correction=corr,
+                                 description="welford" if "m2" in names else f"var_mean (correction {corr})")
         for eps in eps_list:
             e = ops._scalar(float(eps))
             # RMSNorm: 0 or 1 vectors

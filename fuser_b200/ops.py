@@ -46,20 +46,20 @@ def _dtype_id(t: torch.Tensor) -> int:
 
 
 def _run(op: int, flags: int, eps: float, variant: int, cluster_size: int, ins: Sequence[torch.Tensor],
-         outs: Sequence[torch.Tensor] = ()):
+         outs: Sequence[torch.Tensor] = (), correction: int = 0):
     """Hand the segment to the C++ NormExecutor (csrc/host/norm_executor.cpp): it allocates
     the outputs, sizes the workspace and launches on the current stream."""
     if variant == L.VARIANT_AUTO:
         variant = _forced_variant
     if cluster_size == 0:
         cluster_size = _forced_cluster
-    return H.run(op, flags, float(eps), variant, cluster_size, ins, outs)
+    return H.run(op, flags, float(eps), variant, cluster_size, ins, outs, correction)
 
 
 def plan_for(op: int, dtype: torch.dtype, rows: int, cols: int, flags: int = 0, eps: float = 0.0,
-             variant: int = L.VARIANT_AUTO, cluster_size: int = 0) -> dict:
+             variant: int = L.VARIANT_AUTO, cluster_size: int = 0, correction: int = 0) -> dict:
     """Dispatch decision for a segment (no launch): the launch_param dump of this library."""
-    d = L.make_desc(op, _DT[dtype], rows, cols, eps, flags, variant, cluster_size)
+    d = L.make_desc(op, _DT[dtype], rows, cols, eps, flags, variant, cluster_size, correction)
     return L.query(d).as_dict()
 
 
@@ -232,6 +232,30 @@ def finalize_partials(sums: torch.Tensor, dtype: torch.dtype):
     outs = [torch.empty((n,), dtype=dtype, device=sums.device) for _ in range(k)]
     _run(L.OP_FINALIZE_PARTIALS, 0, 0.0, L.VARIANT_AUTO, 0, [sums], outs)
     return outs
+
+
+# ---------------------------------------------------------------------------
+# stand-alone statistics (variance_mean / Welford, csrc/ops/normalization.cpp:93-158)
+# ---------------------------------------------------------------------------
+def var_mean(x, correction: int = 1, *, want_var=True, want_mean=True, variant=L.VARIANT_AUTO, cluster_size=0):
+    """var[...,1], mean[...,1] over the last axis (fp32), var = M2 / max(N - correction, 0) as ops.var_mean
+    (python/python_direct/ops.cpp:1824-1835; at::var_mean semantics). Runs on the LayerNorm forward kernels
+    without their output pass (``F_NO_Y``)."""
+    if correction < 0:
+        raise ValueError(f"correction must be non-negative, but got {correction}")
+    flags = L.F_NO_Y | L.F_STAT_VAR | (L.F_OUT_MEAN if want_mean else 0) | (L.F_OUT_INVSTD if want_var else 0)
+    outs = iter(_run(L.OP_LAYERNORM_FWD, flags, 0.0, variant, cluster_size, [x], correction=int(correction)))
+    mean = next(outs) if want_mean else None
+    var = next(outs) if want_var else None
+    return var, mean
+
+
+def welford(x, *, variant=L.VARIANT_AUTO, cluster_size=0):
+    """avg[...,1], var_sum[...,1] (= M2, the sum of squared deviations) over the last axis, fp32 — the tensor
+    outputs of ops.welford (python/python_direct/ops.cpp:1857-1863); the count is the extent itself."""
+    flags = L.F_NO_Y | L.F_STAT_M2 | L.F_OUT_MEAN | L.F_OUT_INVSTD
+    avg, m2 = _run(L.OP_LAYERNORM_FWD, flags, 0.0, variant, cluster_size, [x])
+    return avg, m2
 
 
 # ---------------------------------------------------------------------------

@@ -166,7 +166,16 @@ enum {
    * used by tests/cpp/test_combined_inner_outer_reduction.cpp:1197:
    *   dx = g / rms - x * sum(g x) / (2 N rms^3)      (the textbook form has no 2)
    * dweight is unaffected. Parity is with the fusion as written, so the spelling is a segment kind. */
-  B200NORM_F_RMS_BWD_HALF_PROJ = 1u << 19
+  B200NORM_F_RMS_BWD_HALF_PROJ = 1u << 19,
+  /* LAYERNORM_FWD as a stand-alone statistics segment — ops.var_mean / ops.welford over the last axis
+   * (csrc/ops/normalization.cpp:93-158, python/python_direct/ops.cpp:1824-1863; device side of the reference:
+   * runtime/welford.cu:52-221): NO_Y: there is no y output (and no weight / bias); the statistics requested with
+   * OUT_MEAN / OUT_INVSTD are the only outputs. STAT_VAR: the second statistic is the variance
+   * M2 / max(N - correction, 0) with the integer correction in desc.reserved[0] (var_mean); STAT_M2: it is
+   * M2 = sum((x - mean)^2) itself (welford's var_sum). Without either it stays invstd = rsqrt(M2 / N + eps). */
+  B200NORM_F_NO_Y = 1u << 20,
+  B200NORM_F_STAT_VAR = 1u << 21,
+  B200NORM_F_STAT_M2 = 1u << 22
 };
 
 /* desc.variant: 0 lets the library choose (the dispatch rule mirrors the accept
@@ -235,7 +244,7 @@ typedef struct {
 /*
  * Tensor order per op (absent optional tensors are simply left out):
  *   LAYERNORM_FWD  in : x[M,N], residual[M,N]?, weight[N]?, bias[N]?
- *                  out: y[M,N], sum[M,N]?, mean[M]?, invstd[M]?
+ *                  out: y[M,N] (absent with NO_Y), sum[M,N]?, mean[M]?, invstd | var | M2 [M]?
  *   LAYERNORM_BWD  in : dy[M,N], x[M,N], mean[M], invstd[M], weight[N]?
  *                  out: dx[M,N]?, dweight[N]?, dbias[N]?
  *   RMSNORM_FWD    in : x[M,N], residual[M,N]?, weight[N]?   out: y[M,N], sum[M,N]?, stat[M]

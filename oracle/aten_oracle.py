@@ -443,3 +443,37 @@ def ulp_bound(dtype: torch.dtype) -> float:
 
 
 __all__ = [n for n in dir() if not n.startswith("_")] + ["math"]
+
+
+# ---------------------------------------------------------------------------
+# plain reductions and stand-alone statistics (ReductionOp / WelfordOp::evaluate,
+# csrc/ir/internal_nodes.cpp:1726-1778, :2058-2083)
+# ---------------------------------------------------------------------------
+def reduce_inner(x, kind: str = "sum"):
+    """sum / max over the last axis as the evaluator computes them: at::sum in fp32 (the fusions cast reduced
+    precision up first) or at::amax (NaN-propagating), cast back to the io dtype."""
+    xf = _up(x)
+    r = torch.sum(xf, dim=[-1]) if kind == "sum" else torch.amax(xf, dim=[-1])
+    return r.to(x.dtype)
+
+
+def reduce_outer(x):
+    """sum over every axis but the last."""
+    xf = _up(x)
+    return torch.sum(xf, dim=list(range(xf.dim() - 1))).to(x.dtype)
+
+
+def var_mean(x, correction: int = 1):
+    """ops.var_mean over the last axis -> (var, mean), fp32 (variance_mean, csrc/ops/normalization.cpp:93-158:
+    Welford, var = M2 / max(N - correction, 0))."""
+    xf = _up(x)
+    var, mean = torch.var_mean(xf, dim=[-1], correction=correction, keepdim=False)
+    return var, mean
+
+
+def welford(x):
+    """ops.welford over the last axis -> (avg, var_sum): WelfordOp::evaluate is at::var_mean(unbiased=False),
+    var_sum = var * N (internal_nodes.cpp:2058-2083)."""
+    xf = _up(x)
+    var, mean = torch.var_mean(xf, dim=[-1], unbiased=False, keepdim=False)
+    return mean, var * xf.shape[-1]

@@ -15,7 +15,7 @@ import torch  # noqa: E402
 from bench import measured_peak  # noqa: E402
 from fuser_b200 import ops  # noqa: E402
 
-KEYS = ["B200NORM_TPR", "B200NORM_GROUPS", "B200NORM_DEPTH", "B200NORM_TILE_ROWS", "B200NORM_CLUSTER",
+KEYS = ["B200NORM_LN_PIPE", "B200NORM_NO_LN_PIPE", "B200NORM_TPR", "B200NORM_GROUPS", "B200NORM_DEPTH", "B200NORM_TILE_ROWS", "B200NORM_CLUSTER",
         "B200NORM_BWD_REREAD", "B200NORM_NO_FUSED_FINISH", "B200NORM_NO_PDL", "B200NORM_NO_PSMEM", "B200NORM_COOP", "B200NORM_STATIC", "B200NORM_POOL", "B200NORM_NO_PIPE", "B200NORM_PIPE",
         "B200NORM_OUTER_W", "B200NORM_OUTER_DEPTH", "B200NORM_OUTER_UNITS", "B200NORM_OUTER_PER_SM", "B200NORM_OUTER_SKIP_REDUCE", "B200NORM_OUTER_PLAIN_ST", "B200NORM_OUTER_TWO_EXCH", "B200NORM_OUTER_L2PF"]
 DT = {"bf16": torch.bfloat16, "f32": torch.float32, "f16": torch.float16}
@@ -23,7 +23,8 @@ DT = {"bf16": torch.bfloat16, "f32": torch.float32, "f16": torch.float16}
 
 def algbytes(op, m, n, s):
     return {"add_rms_fwd": s * (4 * m * n + n) + 4 * m, "add_ln_fwd": s * (4 * m * n + 2 * n) + 8 * m,
-            "copy": s * 2 * m * n, "rms_fwd": s * (2 * m * n + n) + 4 * m, "ln_fwd": s * 2 * (m * n + n) + 8 * m, "sm_fwd": s * 2 * m * n, "osm_fwd": s * 2 * m * n, "onorm_fwd": s * 2 * (m * n + n) + 8 * n, "onorm_bwd": s * 3 * (m * n + n) + 8 * n, "osm_bwd": s * 3 * m * n,
+            "copy": s * 2 * m * n, "red_sum": s * (m * n + m), "red_max": s * (m * n + m), "colsum": s * (m * n + n),
+            "var_mean": s * m * n + 8 * m, "rms_fwd": s * (2 * m * n + n) + 4 * m, "ln_fwd": s * 2 * (m * n + n) + 8 * m, "sm_fwd": s * 2 * m * n, "osm_fwd": s * 2 * m * n, "onorm_fwd": s * 2 * (m * n + n) + 8 * n, "onorm_bwd": s * 3 * (m * n + n) + 8 * n, "osm_bwd": s * 3 * m * n,
             "sm_bwd": s * 3 * m * n, "rms_bwd": s * (3 * m * n + 2 * n) + 4 * m, "rms_bwd_dx": s * (3 * m * n + 2 * n) + 4 * m,
             "ln_bwd": s * 3 * (m * n + n) + 8 * m, "ln_bwd_dx": s * 3 * (m * n + n) + 8 * m}[op]
 
@@ -70,6 +71,10 @@ def main():
                 aux["out"] = torch.empty_like(xs[0])
             fns = {
                 "copy": lambda i: aux["out"].copy_(xs[i]),
+                "red_sum": lambda i: ops.reduce_inner(xs[i], "sum"),
+                "red_max": lambda i: ops.reduce_inner(xs[i], "max"),
+                "colsum": lambda i: ops.reduce_outer(xs[i]),
+                "var_mean": lambda i: ops.var_mean(xs[i], 1),
                 "rms_fwd": lambda i: ops.rms_norm_fwd(xs[i], w, 1e-5),
                 "add_rms_fwd": lambda i: ops.rms_norm_fwd(xs[i], w, 1e-5, residual=dys[i], want_sum=True),
                 "add_ln_fwd": lambda i: ops.layer_norm_fwd(xs[i], w, w, 1e-5, residual=dys[i], want_sum=True),

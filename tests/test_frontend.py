@@ -126,6 +126,55 @@ def test_thunder_rms_norm_backward_as_written():
     assert not m.flags & L.F_RMS_BWD_HALF_PROJ
 
 
+def test_reduction_and_statistics_segments():
+    """Plain Reduction segments (scheduler/reduction.cpp) and stand-alone variance_mean / Welford
+    (csrc/ops/normalization.cpp:93-158) are routed to their kernels; near misses are refused."""
+    def red(kind, dims, dt=DataType.BFloat16, nd=2):
+        def f(fd):
+            x = fd.define_tensor(shape=[-1] * nd, dtype=dt)
+            xf = fd.ops.cast(x, DataType.Float) if dt != DataType.Float else x
+            r = (fd.ops.sum if kind == "sum" else fd.ops.max)(xf, dims=dims)
+            fd.add_output(fd.ops.cast(r, dt) if dt != DataType.Float else r)
+        return f
+    for dt in DTS:
+        m = build(red("sum", [1], dt)).segment()
+        assert (m.op, m.flags, m.outputs) == (L.OP_REDUCE_INNER, 0, ["r"])
+        m = build(red("max", [-1], dt)).segment()
+        assert (m.op, m.flags) == (L.OP_REDUCE_INNER, L.F_REDUCE_MAX)
+        m = build(red("sum", [0], dt)).segment()
+        assert m.op == L.OP_REDUCE_OUTER
+        m = build(red("sum", [0, 1], dt, nd=3)).segment()
+        assert m.op == L.OP_REDUCE_OUTER
+    with pytest.raises(UnsupportedSegment):  # a reduction over a middle axis is neither
+        build(red("sum", [1], nd=3)).segment()
+    with pytest.raises(UnsupportedSegment):  # a bf16 input summed into a Float output: no kernel rounds there
+        def mixed(fd):
+            x = fd.define_tensor(shape=[-1, -1], dtype=DataType.BFloat16)
+            fd.add_output(fd.ops.sum(fd.ops.cast(x, DataType.Float), dims=[1]))
+        build(mixed).segment()
+
+    def vm(corr, outs=("var", "mean"), keep=False):
+        def f(fd):
+            x = fd.define_tensor(shape=[-1, -1], dtype=DataType.Float)
+            var, mean = fd.ops.var_mean(x, dims=[1], correction=corr, keepdim=keep)
+            for o in outs:
+                fd.add_output(var if o == "var" else mean)
+        return f
+    for corr in (0, 1, 2):
+        m = build(vm(corr)).segment()
+        assert m.op == L.OP_LAYERNORM_FWD and m.flags & L.F_NO_Y and m.flags & L.F_STAT_VAR
+        assert m.correction == corr and m.outputs == ["var", "mean"]
+    assert build(vm(1, ("mean",), keep=True)).segment().outputs == ["mean"]
+
+    def wf(fd):
+        x = fd.define_tensor(shape=[-1, -1], dtype=DataType.Float)
+        avg, m2, _ = fd.ops.welford(x, [1])
+        fd.add_output(avg)
+        fd.add_output(m2)
+    m = build(wf).segment()
+    assert m.flags & L.F_STAT_M2 and m.outputs == ["mean", "m2"]
+
+
 def test_epsilon_is_part_of_the_match():
     """A tiny epsilon (BERT-style 1e-12) must neither vanish from the normal form nor be replaced by another
     small constant of the fusion."""
