@@ -400,6 +400,21 @@ bool try_ring_plan(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, int 
   };
   if (colsum) {
     if (!pick(kFwdMaxCH)) return false;  // CH * VEC accumulators per thread; wider rows are split over a cluster
+  } else if (d.op == B200NORM_OP_REDUCE_INNER && nchunks > 128 * kFwdMaxCH && forced_tpr == 0) {
+    // Inner reductions keep no per-chunk state, so any number of chunks per thread works (looping form): prefer
+    // SEVERAL consumer groups per CTA — a lone 512-thread group exposes every row's reduction latency
+    // ([32768,12288] bf16: 204 us with one group) — as long as every group still gets two ring stages.
+    const int64_t budget = (int64_t)dev.smem_optin - 8192;
+    const int64_t row_bytes = (int64_t)align_up((uint32_t)(slice_cols * es), 128);
+    tpr = 512;
+    for (int t : {128, 256, 512}) {
+      if ((int64_t)(kConsumerThreads / t) * 2 * row_bytes <= budget) {
+        tpr = t;
+        break;
+      }
+    }
+    ch = nchunks <= tpr * kFwdMaxCH ? (nchunks + tpr - 1) / tpr : 0;
+    cached = ch > 0;
   } else if (bwd) {
     const bool force_reread = kn.bwd_reread != 0;
     if (force_reread || !pick(kBwdCacheCH)) {
@@ -497,13 +512,13 @@ bool try_ring_plan(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, int 
   // C1 16 % — 16.4 vs 14.1 us; not beyond 8192 columns: at N = 12288 the 96 KB of staged parameters
   // and their four LDS per chunk cost 10 % — 378 vs 342 us)
   // LayerNorm forward with one reduction round per row (Welford pairs merged with Chan's formula), pipelined
-  // across rows (kernels_ln_pipe.cuh): where nothing else overlaps the reduction — one consumer group per CTA
-  // (N > 8192 at 16 bits) or rows split over a cluster. Needs equal element counts per thread and one row per
-  // tile; the residual-add flavour is instantiated from 256 threads per row on. B200NORM_LN_PIPE=1 forces it
-  // wherever it can run, B200NORM_NO_LN_PIPE=1 switches it off.
+  // across rows (kernels_ln_pipe.cuh), wherever it can run: equal element counts per thread, one row per tile,
+  // at least two warps per row; the residual-add flavour is instantiated from 256 threads per row on. Measured
+  // against the two-round register kernel (bf16): [32768,12288] 343 -> 305 us, [16384,8192] 115 -> 92 us,
+  // [16384,4096] 62 -> 53 us, [16384,16384] 273 -> 182 us; fp32 [2048,4096] 15.4 -> 14.5 us.
+  // B200NORM_NO_LN_PIPE=1 switches it off.
   const bool ln_pipe = d.op == B200NORM_OP_LAYERNORM_FWD && ch > 0 && nchunks == tpr * ch && tile_rows == 1 &&
-                       tpr >= 64 && (!add || tpr >= 256) && kn.no_ln_pipe == 0 &&
-                       (C > 1 || groups == 1 || ch > kFwdMaxCH || kn.ln_pipe != 0);
+                       tpr >= 64 && (!add || tpr >= 256) && kn.no_ln_pipe == 0;
   bool want_psmem = d.op == B200NORM_OP_LAYERNORM_FWD && ch > 0 && es == 2 && slice_cols <= 8192 &&
                     kn.no_psmem == 0 && !ln_pipe;
   const uint32_t param_bytes = align_up(2u * (uint32_t)slice_cols * 4u, 128);

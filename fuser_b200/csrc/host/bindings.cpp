@@ -3,6 +3,7 @@
 #include <torch/extension.h>
 
 #include "norm_executor.h"
+#include "segment_matcher.h"
 
 namespace py = pybind11;
 using b200norm::NormExecutor;
@@ -41,6 +42,50 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def_readwrite("variant", &SegmentSpec::variant)
       .def_readwrite("cluster_size", &SegmentSpec::cluster_size)
       .def_readwrite("correction", &SegmentSpec::correction);
+
+  // the C++ segment classifier on a plain-data expression graph (segment_matcher.h): nodes are tuples
+  // (kind, dtype, is_scalar, args, dims, red_axes, correction, value, size_class)
+  m.def(
+      "match_segment",
+      [](const std::vector<std::tuple<int, int, bool, std::vector<int32_t>, std::vector<int32_t>, std::vector<int32_t>, int,
+                                      double, int>>& nodes,
+         const std::vector<int32_t>& inputs, const std::vector<int32_t>& outputs) -> py::object {
+        b200norm::ExprGraph g;
+        for (const auto& t : nodes) {
+          b200norm::ExprNode n;
+          n.kind = static_cast<b200norm::ExprKind>(std::get<0>(t));
+          n.dtype = std::get<1>(t);
+          n.is_scalar = std::get<2>(t);
+          n.args = std::get<3>(t);
+          n.dims = std::get<4>(t);
+          n.red_axes = std::get<5>(t);
+          n.correction = std::get<6>(t);
+          n.value = std::get<7>(t);
+          n.size_class = std::get<8>(t);
+          g.nodes.push_back(std::move(n));
+        }
+        g.inputs = inputs;
+        g.outputs = outputs;
+        b200norm::SegmentMatch sm;
+        std::string why;
+        py::dict d;
+        if (!b200norm::match_segment(g, &sm, &why)) {
+          d["matched"] = false;
+          d["why"] = why;
+          return d;
+        }
+        d["matched"] = true;
+        d["op"] = sm.op;
+        d["flags"] = sm.flags;
+        d["eps"] = sm.eps;
+        d["io_dtype"] = sm.io_dtype;
+        d["correction"] = sm.correction;
+        d["roles"] = sm.roles;
+        d["outputs"] = sm.outputs;
+        d["description"] = sm.description;
+        return d;
+      },
+      py::arg("nodes"), py::arg("inputs"), py::arg("outputs"));
 
   py::class_<NormExecutor>(m, "NormExecutor")
       .def(py::init<int64_t, int64_t, int64_t, int64_t>(), py::arg("fusion_id") = 0, py::arg("concrete_id") = 0,

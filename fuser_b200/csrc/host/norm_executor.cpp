@@ -102,6 +102,20 @@ bool NormExecutor::supported(const SegmentSpec& spec, at::ScalarType io_dtype, i
   return b200norm_query(&d, nullptr) == B200NORM_OK;
 }
 
+bool NormExecutor::supported(const ExprGraph& segment, SegmentSpec* spec, SegmentMatch* match, std::string* why) {
+  SegmentMatch m;
+  if (!match_segment(segment, &m, why)) return false;
+  if (spec != nullptr) {
+    *spec = SegmentSpec();
+    spec->op = m.op;
+    spec->flags = m.flags;
+    spec->eps = m.eps;
+    spec->correction = m.correction;
+  }
+  if (match != nullptr) *match = m;
+  return true;
+}
+
 void NormExecutor::compile(const SegmentSpec& spec) {
   if (spec.op < 0 || spec.op >= B200NORM_OP_COUNT_) raise_msg(B200NORM_ERR_UNSUPPORTED, "unknown segment kind");
   spec_ = spec;

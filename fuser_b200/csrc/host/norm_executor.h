@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "../../../include/b200norm.h"
+#include "segment_matcher.h"
 
 namespace b200norm {
 
@@ -43,6 +44,14 @@ class NormExecutor {
 
   // True if the kernel library has a kernel for this segment at this shape.
   static bool supported(const SegmentSpec& spec, at::ScalarType io_dtype, int64_t rows, int64_t cols);
+
+  // The classifier of ExecutorDispatch: is this segment — given as the plain-data expression graph an adapter
+  // fills from fusion->exprs() — one of the normalization / reduction ops of the
+  // kernel library, in any spelling? Side-effect free (csrc/runtime/executor_dispatch.cpp:46-59 asks every
+  // executor in turn). On success *spec is ready for compile() and *match tells which fusion input plays which
+  // role and what every fusion output is.
+  static bool supported(const ExprGraph& segment, SegmentSpec* spec, SegmentMatch* match = nullptr,
+                        std::string* why = nullptr);
 
   void compile(const SegmentSpec& spec);
   bool isCompiled() const { return compiled_; }

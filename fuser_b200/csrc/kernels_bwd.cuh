@@ -222,36 +222,53 @@ __device__ __forceinline__ void bwd_epilogue(const RowParams& p, const Group<TPR
   // ---- combine the groups' column accumulators and emit this CTA's partial row ----
   if (want_dw || want_db) {
     const int nct = p.groups * TPR;
-    float* acc_w = reinterpret_cast<float*>(smem_raw + p.off_acc);
-    float* acc_b = acc_w + p.cols_cta;
-    named_bar_sync(15, nct);  // every group is done with the ring
-    for (int gi = 0; gi < p.groups; ++gi) {
-      if (g.gid == gi) {
-        for_each_chunk<TPR, CH>(g.gtid, nchunks, [&](int j, int coff) {
-          const int c = g.gtid + coff;
-#pragma unroll
-          for (int k = 0; k < H; ++k) {
-            float2* pw = reinterpret_cast<float2*>(acc_w + c * VEC + 2 * k);
-            float2* pb = reinterpret_cast<float2*>(acc_b + c * VEC + 2 * k);
-            if (gi == 0) {
-              *pw = dw_acc[j][k];
-              if constexpr (LN) *pb = db_acc[j][k];
-            } else {
-              *pw = f2add(*pw, dw_acc[j][k]);
-              if constexpr (LN) *pb = f2add(*pb, db_acc[j][k]);
-            }
-          }
-        });
-      }
-      named_bar_sync(15, nct);
-    }
     // partials layout: [part][K][N], K = 2 for LN (dw, db), 1 for RMSNorm
     constexpr int K = LN ? 2 : 1;
     const int64_t part = blockIdx.x / g.csize;
     float* dst = p.partials + (size_t)part * K * p.cols + (size_t)g.crank * p.cols_cta;
-    for (int col = threadIdx.x * 4; col < p.cols_cta; col += nct * 4) {
-      *reinterpret_cast<float4*>(dst + col) = *reinterpret_cast<const float4*>(acc_w + col);
-      if constexpr (LN) *reinterpret_cast<float4*>(dst + p.cols + col) = *reinterpret_cast<const float4*>(acc_b + col);
+    if (p.groups == 1) {
+      // one group: the thread's accumulators ARE the CTA's column sums — straight from registers to the partial
+      // row (32 contiguous bytes per thread and chunk, a warp writes 1 KB), no shared-memory staging, no barrier
+      for_each_chunk<TPR, CH>(g.gtid, nchunks, [&](int j, int coff) {
+        float* o = dst + (size_t)(g.gtid + coff) * VEC;
+#pragma unroll
+        for (int k = 0; k < H; k += 2) {
+          *reinterpret_cast<float4*>(o + 2 * k) =
+              make_float4(dw_acc[j][k].x, dw_acc[j][k].y, dw_acc[j][k + 1].x, dw_acc[j][k + 1].y);
+          if constexpr (LN) {
+            *reinterpret_cast<float4*>(o + p.cols + 2 * k) =
+                make_float4(db_acc[j][k].x, db_acc[j][k].y, db_acc[j][k + 1].x, db_acc[j][k + 1].y);
+          }
+        }
+      });
+    } else {
+      float* acc_w = reinterpret_cast<float*>(smem_raw + p.off_acc);
+      float* acc_b = acc_w + p.cols_cta;
+      named_bar_sync(15, nct);  // every group is done with the ring
+      for (int gi = 0; gi < p.groups; ++gi) {
+        if (g.gid == gi) {
+          for_each_chunk<TPR, CH>(g.gtid, nchunks, [&](int j, int coff) {
+            const int c = g.gtid + coff;
+#pragma unroll
+            for (int k = 0; k < H; ++k) {
+              float2* pw = reinterpret_cast<float2*>(acc_w + c * VEC + 2 * k);
+              float2* pb = reinterpret_cast<float2*>(acc_b + c * VEC + 2 * k);
+              if (gi == 0) {
+                *pw = dw_acc[j][k];
+                if constexpr (LN) *pb = db_acc[j][k];
+              } else {
+                *pw = f2add(*pw, dw_acc[j][k]);
+                if constexpr (LN) *pb = f2add(*pb, db_acc[j][k]);
+              }
+            }
+          });
+        }
+        named_bar_sync(15, nct);
+      }
+      for (int col = threadIdx.x * 4; col < p.cols_cta; col += nct * 4) {
+        *reinterpret_cast<float4*>(dst + col) = *reinterpret_cast<const float4*>(acc_w + col);
+        if constexpr (LN) *reinterpret_cast<float4*>(dst + p.cols + col) = *reinterpret_cast<const float4*>(acc_b + col);
+      }
     }
     if (p.fused_finish) {
       // The launch is cooperative (every CTA is resident): one grid barrier, then every CTA

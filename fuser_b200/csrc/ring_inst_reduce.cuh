@@ -28,6 +28,8 @@ namespace b200norm {
 template <typename T>
 RingKernel ring_reduce_inner_kernel_for(int tpr, int ch) {
   if (tpr == 512 && ch == 0) return reduce_inner_ring_kernel<T, 512, 0>;
+  if (tpr == 256 && ch == 0) return reduce_inner_ring_kernel<T, 256, 0>;
+  if (tpr == 128 && ch == 0) return reduce_inner_ring_kernel<T, 128, 0>;
   B200_RED_TPR(reduce_inner_ring_kernel)
 }
 template <typename T>
