@@ -90,7 +90,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   py::class_<NormExecutor>(m, "NormExecutor")
       .def(py::init<int64_t, int64_t, int64_t, int64_t>(), py::arg("fusion_id") = 0, py::arg("concrete_id") = 0,
            py::arg("runtime_id") = 0, py::arg("group_id") = 0)
-      .def_static("supported", &NormExecutor::supported)
+      .def_static("supported", static_cast<bool (*)(const SegmentSpec&, at::ScalarType, int64_t, int64_t)>(&NormExecutor::supported))
       .def("compile", &NormExecutor::compile)
       .def("is_compiled", &NormExecutor::isCompiled)
       .def("run", &NormExecutor::run, py::arg("inputs"), py::arg("outputs") = std::vector<at::Tensor>{});
