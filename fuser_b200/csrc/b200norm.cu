@@ -370,7 +370,14 @@ bool try_ring_plan(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, int 
   if (N % C != 0) return false;
   const int64_t slice_cols = N / C;
   if ((slice_cols * es) % 16 != 0) return false;
-  if (slice_cols * es > (int64_t)100 * 1024) return false;
+  // A slice of up to 100 KB leaves room for two ring stages. Beyond that — vocabulary-size rows, e.g. softmax over
+  // N = 1048576 bf16 = 128 KB per CTA of a 16-CTA cluster, the largest size of tests/cpp/test_cluster.cpp:195-204 —
+  // a one-stream forward-type op may still run with ONE stage per CTA on the widest cluster (the next row's load
+  // only starts when the last pass over the current row is done: no overlap, but TMA + DSMEM instead of the scalar
+  // family); two-stream ops would need 2 x 128 KB and stay with the shape-agnostic family.
+  const bool single_stage_ok = C == 16 && !is_norm_bwd(d.op) && !is_add_fwd(d) && n_streams(d.op) == 1 &&
+                               d.op != B200NORM_OP_REDUCE_OUTER;
+  if (slice_cols * es > (int64_t)100 * 1024 && !(single_stage_ok && slice_cols * es <= (int64_t)200 * 1024)) return false;
   const int nchunks = (int)(slice_cols / vec);
   const bool add = is_add_fwd(d);
   const int ns = add ? 2 : n_streams(d.op);
@@ -551,7 +558,7 @@ bool try_ring_plan(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, int 
       groups = groups / 2;
       continue;
     }
-    if (depth < 2) return false;
+    if (depth < 2 && !(depth == 1 && single_stage_ok && p.slice_bytes > 100u * 1024u)) return false;
     if (depth > 4) depth = 4;  // deeper rings only scatter the DRAM streams (measured: C3 fwd 87% at 6, 93% at 3)
     if (int dd = kn.depth) {
       if (dd >= 1 && dd <= max_stages / groups) depth = dd;
