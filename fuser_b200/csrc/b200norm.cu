@@ -243,6 +243,7 @@ struct Plan {
   bool cached = false;
   bool psmem = false;      // LayerNorm fwd: weight / bias staged in shared memory as fp32
   bool pipe = false;       // backward, re-read form: split-phase reductions pipelined across rows
+  bool stats_reduce = false;  // LAYERNORM_FWD | NO_Y (var_mean / welford): runs on the inner-reduction kernel
   int nparts = 0;          // partial rows produced by the main kernel
   int rows_per_split = 0;  // generic colsum
   int n_launches = 1;
@@ -260,8 +261,9 @@ uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 // pipe: the split-phase pipelined flavours (norm backward re-read form, RMSNorm / LayerNorm forward)
 #define B200_RING_KERNEL_FOR(T, SUF)                                                                         \
   template <>                                                                                                \
-  RingKernel ring_kernel_for<T>(int op, int tpr, int ch, bool cached, bool psmem, bool add, bool pipe) {      \
-    if (op == B200NORM_OP_REDUCE_INNER) return ring_reduce_inner_kernel_##SUF(tpr, ch);                      \
+  RingKernel ring_kernel_for<T>(int op, int tpr, int ch, bool cached, bool psmem, bool add, bool pipe,       \
+                                bool red) {                                                                \
+    if (op == B200NORM_OP_REDUCE_INNER || red) return ring_reduce_inner_kernel_##SUF(tpr, ch);               \
     if (op == B200NORM_OP_REDUCE_OUTER) return ring_colsum_kernel_##SUF(tpr, ch);                            \
     if (pipe && op == B200NORM_OP_LAYERNORM_FWD) return ring_ln_pipe_kernel_##SUF(tpr, ch, add);             \
     if (add) return ring_add_kernel_##SUF(op, tpr, ch, psmem);                                               \
@@ -270,7 +272,7 @@ uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
     return is_norm_bwd(op) ? ring_bwd_kernel_##SUF(op, tpr, ch, cached) : ring_fwd_kernel_##SUF(op, tpr, ch, psmem); \
   }
 template <typename T>
-RingKernel ring_kernel_for(int op, int tpr, int ch, bool cached, bool psmem, bool add, bool pipe);
+RingKernel ring_kernel_for(int op, int tpr, int ch, bool cached, bool psmem, bool add, bool pipe, bool red);
 B200_RING_KERNEL_FOR(float, f32)
 B200_RING_KERNEL_FOR(__nv_bfloat16, bf16)
 B200_RING_KERNEL_FOR(__half, f16)
@@ -293,11 +295,11 @@ int prepare_ring_kernel(DeviceCtx& ctx, RingKernel k, int smem, int cluster) {
   return B200NORM_OK;
 }
 
-RingKernel ring_kernel_any(int dt, int op, int tpr, int ch, bool cached, bool psmem, bool add, bool pipe) {
+RingKernel ring_kernel_any(int dt, int op, int tpr, int ch, bool cached, bool psmem, bool add, bool pipe, bool red) {
   switch (dt) {
-    case B200NORM_DT_F32: return ring_kernel_for<float>(op, tpr, ch, cached, psmem, add, pipe);
-    case B200NORM_DT_BF16: return ring_kernel_for<__nv_bfloat16>(op, tpr, ch, cached, psmem, add, pipe);
-    case B200NORM_DT_F16: return ring_kernel_for<__half>(op, tpr, ch, cached, psmem, add, pipe);
+    case B200NORM_DT_F32: return ring_kernel_for<float>(op, tpr, ch, cached, psmem, add, pipe, red);
+    case B200NORM_DT_BF16: return ring_kernel_for<__nv_bfloat16>(op, tpr, ch, cached, psmem, add, pipe, red);
+    case B200NORM_DT_F16: return ring_kernel_for<__half>(op, tpr, ch, cached, psmem, add, pipe, red);
     default: return nullptr;
   }
 }
@@ -384,6 +386,9 @@ bool try_ring_plan(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, int 
   const bool bwd = is_norm_bwd(d.op);
   const bool ln_bwd = d.op == B200NORM_OP_LAYERNORM_BWD;
   const bool colsum = d.op == B200NORM_OP_REDUCE_OUTER;  // per-thread column accumulators, no per-row reduction
+  // inner reductions without an output pass: sum / max / fmax and the stand-alone statistics (var_mean, welford)
+  const bool inner_red = d.op == B200NORM_OP_REDUCE_INNER ||
+                         (d.op == B200NORM_OP_LAYERNORM_FWD && (d.flags & B200NORM_F_NO_Y) != 0);
 
   // Threads per row slice and chunks per thread. Forward-type kernels: the smallest group
   // that keeps the slice in registers at <= kFwdMaxCH chunks per thread (fewer, fatter
@@ -407,7 +412,7 @@ bool try_ring_plan(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, int 
   };
   if (colsum) {
     if (!pick(kFwdMaxCH)) return false;  // CH * VEC accumulators per thread; wider rows are split over a cluster
-  } else if (d.op == B200NORM_OP_REDUCE_INNER && nchunks > 128 * kFwdMaxCH && forced_tpr == 0) {
+  } else if (inner_red && nchunks > 128 * kFwdMaxCH && forced_tpr == 0) {
     // Inner reductions keep no per-chunk state, so any number of chunks per thread works (looping form): prefer
     // SEVERAL consumer groups per CTA — a lone 512-thread group exposes every row's reduction latency
     // ([32768,12288] bf16: 204 us with one group) — as long as every group still gets two ring stages.
@@ -520,14 +525,14 @@ bool try_ring_plan(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, int 
   // and their four LDS per chunk cost 10 % — 378 vs 342 us)
   // LayerNorm forward with one reduction round per row (Welford pairs merged with Chan's formula), pipelined
   // across rows (kernels_ln_pipe.cuh), wherever it can run: equal element counts per thread, one row per tile,
-  // at least two warps per row; the residual-add flavour is instantiated from 256 threads per row on. Measured
+  // at least two warps per row. Measured
   // against the two-round register kernel (bf16): [32768,12288] 343 -> 305 us, [16384,8192] 115 -> 92 us,
   // [16384,4096] 62 -> 53 us, [16384,16384] 273 -> 182 us; fp32 [2048,4096] 15.4 -> 14.5 us.
   // B200NORM_NO_LN_PIPE=1 switches it off.
-  const bool ln_pipe = d.op == B200NORM_OP_LAYERNORM_FWD && ch > 0 && nchunks == tpr * ch && tile_rows == 1 &&
-                       tpr >= 64 && (!add || tpr >= 256) && kn.no_ln_pipe == 0;
+  const bool ln_pipe = d.op == B200NORM_OP_LAYERNORM_FWD && !inner_red && ch > 0 && nchunks == tpr * ch && tile_rows == 1 &&
+                       tpr >= 64 && kn.no_ln_pipe == 0;
   bool want_psmem = d.op == B200NORM_OP_LAYERNORM_FWD && ch > 0 && es == 2 && slice_cols <= 8192 &&
-                    kn.no_psmem == 0 && !ln_pipe;
+                    kn.no_psmem == 0 && !ln_pipe && !inner_red;
   const uint32_t param_bytes = align_up(2u * (uint32_t)slice_cols * 4u, 128);
 
   // Ring depth D (stages per group); the ring is group-major, stage (g*D + s).
@@ -582,6 +587,7 @@ bool try_ring_plan(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, int 
   // CTA the groups already overlap each other and the second smem pass only costs (N = 8192: 85 vs 95 us).
   // (16-bit only: the fp32 single-group kernel is at the roofline already, 163 vs 182 us at N = 8192)
   if (ln_pipe) p.pipe = true;
+  p.stats_reduce = inner_red && d.op == B200NORM_OP_LAYERNORM_FWD;
   if (d.op == B200NORM_OP_RMSNORM_FWD && !add &&
       (C > 1 || (tpr == 512 && es == 2 && ch == 3 && (nchunks + 255) / 256 == 6) || kn.pipe != 0) && ch > 0 &&
       tile_rows == 1 && tpr >= 64 && (ch <= 4 || tpr >= 256) && kn.no_pipe == 0) {
@@ -596,7 +602,7 @@ bool try_ring_plan(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, int 
   p.smem = p.off_ring + ring_bytes;
 
   const int64_t ntiles = ceil_div64(d.rows, tile_rows);
-  int64_t nclusters = max_active_clusters(ctx, ring_kernel_any(d.io_dtype, d.op, tpr, ch, cached, p.psmem, add, p.pipe), p.block,
+  int64_t nclusters = max_active_clusters(ctx, ring_kernel_any(d.io_dtype, d.op, tpr, ch, cached, p.psmem, add, p.pipe, p.stats_reduce), p.block,
                                           (int)p.smem, C);
   if (nclusters > ntiles) nclusters = ntiles;
   if (nclusters < 1) nclusters = 1;
@@ -640,7 +646,11 @@ int make_plan_uncached(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, 
       // prefer the smallest cluster that gives a register-resident slice (forward-type) or
       // per-thread column accumulators (backward) with >= 3 stages per group: a cluster costs
       // a DSMEM exchange per row and leaves SMs idle (clusters never span GPCs)
-      const bool good = (cand.cached || is_norm_bwd(d.op) || d.op == B200NORM_OP_REDUCE_INNER) && cand.depth >= 3;
+      // (an inner reduction holds a stage only while it is being summed: two stages per group are enough)
+      const bool inner_red = d.op == B200NORM_OP_REDUCE_INNER ||
+                             (d.op == B200NORM_OP_LAYERNORM_FWD && (d.flags & B200NORM_F_NO_Y) != 0);
+      const bool good = inner_red ? cand.depth >= 2
+                                                         : (cand.cached || is_norm_bwd(d.op)) && cand.depth >= 3;
       if (good || forced_c > 0) {
         best = cand;
         break;
@@ -940,7 +950,8 @@ int launch_typed(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, const 
   }
 
   // ---- ring kernels ----
-  RingKernel k = ring_kernel_for<T>(d.op, plan.tpr, plan.ch, plan.cached, plan.psmem, is_add_fwd(d), plan.pipe);
+  RingKernel k = ring_kernel_for<T>(d.op, plan.tpr, plan.ch, plan.cached, plan.psmem, is_add_fwd(d), plan.pipe,
+                                    plan.stats_reduce);
   if (k == nullptr)
     return fail(B200NORM_ERR_UNSUPPORTED, "no ring kernel for op %d tpr %d ch %d", d.op, plan.tpr, plan.ch);
   {

@@ -1,5 +1,6 @@
 // kernels_reduce.cuh — plain (non-persistent in the reference's terms) reductions on the TMA ring:
 //   reduce_inner_ring_kernel : [M, N] -> [M]   sum | max (NaN-propagating amax) | fmax (NaN-ignoring)
+//                                              | (mean, variance or M2): stand-alone var_mean / welford segments
 //   colsum_ring_kernel       : [M, N] -> [N]   sum over the rows (the shape of dgamma / dbeta: the stand-alone
 //                                              column sum the reference segments a wide backward into)
 // These are the segments nvFuser's ReductionScheduler takes (csrc/scheduler/reduction.cpp:198-360; device side:
@@ -33,6 +34,7 @@ __global__ void __launch_bounds__(kMaxBlock, 1) reduce_inner_ring_kernel(const R
   const int nchunks = p.nchunks;
   const bool is_max = (p.flags & kFlagReduceMax) != 0;
   const bool is_fmax = (p.flags & kFlagReduceFmax) != 0;
+  const bool stats = (p.flags & kFlagNoY) != 0;  // LAYERNORM_FWD | NO_Y routed here: mean + variance / M2 per row
   const bool writer = g.gtid == 0 && g.crank == 0;
   T* out = static_cast<T*>(p.out0);
 
@@ -42,6 +44,41 @@ __global__ void __launch_bounds__(kMaxBlock, 1) reduce_inner_ring_kernel(const R
     const uint8_t* xrow = smem_raw + ring.stage_off + 16u * (uint32_t)g.gtid;
     for (int r = 0; r < nrows; ++r, xrow += p.slice_bytes) {
       float res;
+      if (stats) {
+        // stand-alone var_mean / welford (kFlagNoY): per thread sums of (x - K) and (x - K)^2 around K = the
+        // thread's own first element — the cancellation in M2_t = S2 - S1^2 / n_t is then bounded by the handful
+        // of elements a thread holds (S2 / M2_t <= n_t + 1) — turned into a Welford triple and merged exactly.
+        float2 s1 = f2(0.f), s2 = f2(0.f);
+        float cnt = 0.f, shift = 0.f;
+        bool first = true;
+        for_each_chunk<TPR, CH>(g.gtid, nchunks, [&](int, int coff) {
+          float2 t[H];
+          IO<T>::unpack2(ld_smem_u4(xrow + 16 * coff), t);
+          if (first) {
+            shift = t[0].x;
+            first = false;
+          }
+          const float2 nk = f2(-shift);
+#pragma unroll
+          for (int k = 0; k < H; ++k) {
+            const float2 dv = f2add(t[k], nk);
+            s1 = f2add(s1, dv);
+            s2 = f2fma(dv, dv, s2);
+          }
+          cnt += (float)VEC;
+        });
+        const float S1 = s1.x + s1.y, S2 = s2.x + s2.y;
+        const float inv = cnt > 0.f ? rcp_fast(cnt) : 0.f;
+        float mean = fmaf(S1, inv, shift);
+        float m2 = fmaxf(fmaf(-S1 * inv, S1, S2), 0.f);
+        g.welford_allreduce(cnt, mean, m2);
+        if (r == nrows - 1) ring.refill();
+        if (writer) {
+          if (p.stat0 != nullptr) p.stat0[ring.row0 + r] = mean;
+          if (p.stat1 != nullptr) p.stat1[ring.row0 + r] = ln_second_stat(p, m2, rsqrt_fast(m2 * p.inv_n + p.eps));
+        }
+        continue;
+      }
       if (is_max) {
         float m[1] = {-INFINITY};
         for_each_chunk<TPR, CH>(g.gtid, nchunks, [&](int, int coff) {

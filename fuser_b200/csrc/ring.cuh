@@ -228,6 +228,72 @@ struct Group {
     }
   }
 
+  // Welford triples (count, mean, M2) of arbitrary partial sets -> the triple of the whole row slice of the group
+  // (and of the cluster), merged with Chan's formula (runtime/welford.cu:52-68 is the reference's combine):
+  //     n = na + nb,  mean = ma + (mb - ma) * nb / n,  M2 = M2a + M2b + (mb - ma)^2 * na * nb / n.
+  // Lanes merge by xor shuffles, warps and cluster ranks sequentially in index order from shared-memory slots, so
+  // every thread ends with the same bits. Acts as a barrier for the group, like allreduce().
+  __device__ __forceinline__ static void chan_merge(float& n, float& mean, float& m2, float on, float om, float o2) {
+    const float tot = n + on;
+    const float w = tot > 0.f ? on * rcp_fast(tot) : 0.f;
+    const float d = om - mean;
+    mean = fmaf(d, w, mean);
+    m2 = fmaf(d * d, n * w, m2 + o2);
+    n = tot;
+  }
+  __device__ __forceinline__ void welford_allreduce(float& n, float& mean, float& m2) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const float on = __shfl_xor_sync(0xffffffffu, n, off);
+      const float om = __shfl_xor_sync(0xffffffffu, mean, off);
+      const float o2 = __shfl_xor_sync(0xffffffffu, m2, off);
+      chan_merge(n, mean, m2, on, om, o2);
+    }
+    if constexpr (TPR > 32) {
+      float* slots = reinterpret_cast<float*>(smem_raw + red_off);
+      if (lane == 0) {
+        slots[warp] = n;
+        slots[kMaxWarpsPerGroup + warp] = mean;
+        slots[2 * kMaxWarpsPerGroup + warp] = m2;
+      }
+      named_bar_sync(1 + gid, TPR);
+      n = slots[0];
+      mean = slots[kMaxWarpsPerGroup];
+      m2 = slots[2 * kMaxWarpsPerGroup];
+#pragma unroll
+      for (int w = 1; w < WPG; ++w) {
+        chan_merge(n, mean, m2, slots[w], slots[kMaxWarpsPerGroup + w], slots[2 * kMaxWarpsPerGroup + w]);
+      }
+      red_off ^= (uint32_t)kRedSetBytes;
+    } else {
+      // one warp: take lane 0's triple so that every lane holds the same bits
+      n = __shfl_sync(0xffffffffu, n, 0);
+      mean = __shfl_sync(0xffffffffu, mean, 0);
+      m2 = __shfl_sync(0xffffffffu, m2, 0);
+    }
+    if (csize > 1) {
+      const uint32_t par = cl_phase & 1u;
+      const uint32_t set = par * kClsSetBytes;
+      if (gtid == 0) mbar_arrive_expect_tx(clbar, csize * 3 * 4);
+      if ((uint32_t)gtid < csize) {
+        const uint32_t r = (uint32_t)gtid;
+        const uint32_t rbar = map_to_cta(clbar, r);
+        st_async_f32(map_to_cta(cls_addr + set + (crank * kRedNV + 0) * 4, r), n, rbar);
+        st_async_f32(map_to_cta(cls_addr + set + (crank * kRedNV + 1) * 4, r), mean, rbar);
+        st_async_f32(map_to_cta(cls_addr + set + (crank * kRedNV + 2) * 4, r), m2, rbar);
+      }
+      mbar_wait(clbar, par);
+      const volatile float* slots = reinterpret_cast<const volatile float*>(smem_raw + cls_off + set);
+      n = slots[0];
+      mean = slots[1];
+      m2 = slots[2];
+      for (uint32_t r = 1; r < csize; ++r) {
+        chan_merge(n, mean, m2, slots[r * kRedNV + 0], slots[r * kRedNV + 1], slots[r * kRedNV + 2]);
+      }
+      cl_phase += 1u;
+    }
+  }
+
   // All-reduce NV floats across the group's TPR threads and, when the row is
   // split over a cluster, across the peer CTAs' same-numbered groups. Every
   // thread returns the same bits (fixed combination order). Acts as a barrier
@@ -570,6 +636,7 @@ __device__ __forceinline__ void for_each_chunk(int gtid, int nchunks, F&& f) {
       if (j < CH - 1 || gtid + j * TPR < nchunks) f(j, j * TPR);
     }
   } else {
+#pragma unroll 4
     for (int c = 0; gtid + c < nchunks; c += TPR) f(0, c);
   }
 }

@@ -19,6 +19,8 @@ RingKernel ring_ln_pipe_kernel_for(int tpr, int ch, bool add) {
   }
   if (add) {
     switch (tpr) {
+      case 64: B200_LNPIPE_CH(64, true)
+      case 128: B200_LNPIPE_CH(128, true)
       case 256: B200_LNPIPE_CH(256, true)
       case 512: B200_LNPIPE_CH(512, true)
       default: return nullptr;

@@ -273,10 +273,10 @@ def _ln_fwd(m, n, dt, seed, expect, residual=False, shift=0.0):
     if residual:
         r = gpu_randn(m, n, dt, seed + 3)
         y, mean, invstd, s = ops.layer_norm_fwd(x, w, b, EPS, residual=r, want_sum=True, round_sum=dt != torch.float32)
-        se = AO.residual_sum(xc, r.cpu(), dt != torch.float32)
-        assert torch.equal(s.cpu(), se.to(dt)), "x + residual must be bit-exact"
-        ye, me, ie = AO.add_layer_norm_fwd(xc, r.cpu(), wc, bc, EPS, round_sum=dt != torch.float32)
-        y64, m64, i64 = CO.layer_norm_fwd(se, wc, bc, EPS)
+        seen, se = AO.residual_sum(xc, r.cpu(), dt != torch.float32)  # (what the norm sees, the sum in the io dtype)
+        assert torch.equal(s.cpu(), se), "x + residual must be bit-exact"
+        ye, me, ie, _ = AO.add_layer_norm_fwd(xc, r.cpu(), wc, bc, EPS, round_sum=dt != torch.float32)
+        y64, m64, i64 = CO.layer_norm_fwd(seen, wc, bc, EPS)
     else:
         y, mean, invstd = ops.layer_norm_fwd(x, w, b, EPS)
         ye, me, ie = AO.layer_norm_fwd(xc, wc, bc, EPS)
