@@ -54,6 +54,9 @@ WORKLOADS = {
     # (benchmarks/python/normalization.py, test_batchnorm_{fwd,bwd}.py viewed as [N*H*W, C])
     "o2": ("batch norm fwd+bwd bf16 [8192,18432] (statistics over dim 0, outer-persistent)", 8192, 18432, torch.bfloat16,
            "outer_norm_fwd_bwd"),
+    # plain Reduction segments and stand-alone variance_mean on the fast path
+    "r1": ("row sum + var_mean + column sum bf16 [32768,12288] (Reduction / Welford segments)", 32768, 12288, torch.bfloat16,
+           "reductions"),
 }
 EPS = 1e-5
 L2_BYTES = 126 * 1024 * 1024
@@ -71,6 +74,8 @@ def iobytes(kind: str, m: int, n: int, s: int) -> dict:
         return {"bwd": s * 3 * (m * n + n) + 4 * 2 * m}
     if kind == "layernorm_fwd":
         return {"fwd": s * 2 * (m * n + n) + 4 * 2 * m}
+    if kind == "reductions":  # fwd: row sum + var_mean of x (two reads of x); bwd: column sum of dy
+        return {"fwd": s * (m * n + m) + s * m * n + 8 * m, "bwd": s * (m * n + n)}
     raise KeyError(kind)
 
 
@@ -222,6 +227,9 @@ class Step:
             return ops.outer_norm_fwd(x, self.w, self.w, EPS)
         if self.kind == "layernorm_fwd":
             return ops.layer_norm_fwd(x, self.w, self.w, EPS)
+        if self.kind == "reductions":
+            var, mean = ops.var_mean(x, 1)
+            return ops.reduce_inner(x, "sum"), var, mean
         return None
 
     def bwd(self, i, fwd_out=None):
@@ -244,6 +252,8 @@ class Step:
         if self.kind == "outer_norm_fwd_bwd":
             mean, invstd = (fwd_out[1], fwd_out[2]) if fwd_out is not None else saved
             return ops.outer_norm_bwd(dy, x, mean, invstd, self.w)
+        if self.kind == "reductions":
+            return (ops.reduce_outer(dy),)
         if self.kind == "layernorm_bwd":
             mean, invstd = saved
             if self.world > 1:
@@ -355,6 +365,9 @@ class E2E:
             self.rv = torch.ones(n, device=device)
         elif kind == "layernorm_bwd":
             self.fd_fwd, self.fd_bwd = define(F.layernorm_fwd_py, EPS), define(F.layernorm_bwd_py)
+        elif kind == "reductions":
+            self.fd_fwd, self.fd_bwd = define(F.reduce_py, "sum", [1]), define(F.reduce_py, "sum", [0])
+            self.fd_vm = define(F.var_mean_py, 1)
         else:
             self.fd_fwd = define(F.layernorm_fwd_py, EPS)
         self.s_in, self.s_c, self.s_out = (torch.cuda.Stream(device=device) for _ in range(3))
@@ -382,6 +395,11 @@ class E2E:
             y, mean, invstd = self.fd_fwd.execute([x, w, w, self.rm, self.rv])
             dx, dw, db = self.fd_bwd.execute([x, dy, w, self.rm, self.rv, mean, invstd])
             return [y, mean, invstd, dx, dw, db]
+        if k == "reductions":
+            (rs,) = self.fd_fwd.execute([x])
+            var, mean = self.fd_vm.execute([x])
+            (cs,) = self.fd_bwd.execute([dy])
+            return [rs, var, mean, cs]
         if k == "layernorm_bwd":
             # the config is the backward; the saved statistics come from the forward definition
             y, mean, invstd = self.fd_fwd.execute([x, w, w])
@@ -442,6 +460,8 @@ def cpu_step_fn(kind, dtype):
         if kind == "layernorm_bwd":
             _, mean, invstd = AO.layer_norm_fwd(x, None, None, EPS)
             return AO.layer_norm_bwd_python(x, dy, mean.view(-1), invstd, w)
+        if kind == "reductions":
+            return AO.reduce_inner(x, "sum"), AO.var_mean(x, 1), AO.reduce_outer(dy)
         return AO.layer_norm_fwd(x, w, w, EPS)
 
     return fn
@@ -522,6 +542,12 @@ def validate_step(step, kind, world, device):
         xc, dyc = x.cpu().float(), dy.cpu().float()
         col_sums("dgamma", cols[0], (dyc * ((xc - mean.cpu()) * invstd.cpu())).sum(0))
         col_sums("dbeta", cols[1], dyc.sum(0))
+    elif kind == "reductions":
+        close(f[0][rd], AO.reduce_inner(xs, "sum"), n, "row sum")
+        ve, me = AO.var_mean(xs, 1)
+        close(f[1].view(-1)[rd], ve, n, "var")
+        close(f[2].view(-1)[rd], me, n, "mean")
+        close(b[0], AO.reduce_outer(dy.cpu()), m, "column sum")
     else:  # layernorm_fwd
         for name, a, e in zip(("y", "mean", "invstd"), f, AO.layer_norm_fwd(x.cpu(), wc, wc, EPS)):
             close(a, e, n, name)

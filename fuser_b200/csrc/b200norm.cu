@@ -122,7 +122,7 @@ const DeviceInfo& device_info() { return device_ctx().info; }
 struct Knobs {
   int tpr = 0, groups = 0, depth = 0, tile_rows = 0, cluster = 0, bwd_reread = 0, pipe = 0, no_pipe = 0, no_psmem = 0;
   int no_fused_finish = 0, no_pdl = 0, coop = 0, static_sched = 0, pool = 0, debug = 0, peer_timeout_s = -1;
-  int ln_pipe = 0, no_ln_pipe = 0, no_guard = 0;
+  int ln_pipe = 0, no_ln_pipe = 0, no_guard = 0, no_lean = 0;
   bool any = false;
   uint64_t hash = 0;  // of the planner-relevant values (plan cache key)
 };
@@ -135,7 +135,7 @@ Knobs read_knobs() {
       {"NO_PSMEM", &Knobs::no_psmem}, {"NO_FUSED_FINISH", &Knobs::no_fused_finish}, {"NO_PDL", &Knobs::no_pdl},
       {"COOP", &Knobs::coop}, {"STATIC", &Knobs::static_sched}, {"POOL", &Knobs::pool}, {"DEBUG", &Knobs::debug},
       {"PEER_TIMEOUT_S", &Knobs::peer_timeout_s}, {"LN_PIPE", &Knobs::ln_pipe}, {"NO_LN_PIPE", &Knobs::no_ln_pipe},
-      {"NO_GUARD", &Knobs::no_guard}};
+      {"NO_GUARD", &Knobs::no_guard}, {"NO_LEAN", &Knobs::no_lean}};
   if (::environ == nullptr) return k;
   for (char** e = ::environ; *e != nullptr; ++e) {
     if (strncmp(*e, "B200NORM_", 9) != 0) continue;
@@ -153,7 +153,7 @@ Knobs read_knobs() {
   }
   if (k.any) {
     const int vals[] = {k.tpr, k.groups, k.depth, k.tile_rows, k.cluster, k.bwd_reread, k.pipe, k.no_pipe, k.no_psmem,
-                        k.ln_pipe, k.no_ln_pipe};
+                        k.ln_pipe, k.no_ln_pipe, k.no_lean};
     uint64_t h = 1469598103934665603ull;
     for (int v : vals) h = (h ^ (uint64_t)(uint32_t)v) * 1099511628211ull;
     k.hash = h | 1ull;
@@ -243,6 +243,7 @@ struct Plan {
   bool cached = false;
   bool psmem = false;      // LayerNorm fwd: weight / bias staged in shared memory as fp32
   bool pipe = false;       // backward, re-read form: split-phase reductions pipelined across rows
+  bool lean = false;       // RMSNorm backward without the centring term on the instruction-trimmed pipe kernel
   bool stats_reduce = false;  // LAYERNORM_FWD | NO_Y (var_mean / welford): runs on the inner-reduction kernel
   int nparts = 0;          // partial rows produced by the main kernel
   int rows_per_split = 0;  // generic colsum
@@ -262,17 +263,17 @@ uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 #define B200_RING_KERNEL_FOR(T, SUF)                                                                         \
   template <>                                                                                                \
   RingKernel ring_kernel_for<T>(int op, int tpr, int ch, bool cached, bool psmem, bool add, bool pipe,       \
-                                bool red) {                                                                \
+                                bool red, bool lean) {                                                     \
     if (op == B200NORM_OP_REDUCE_INNER || red) return ring_reduce_inner_kernel_##SUF(tpr, ch);               \
     if (op == B200NORM_OP_REDUCE_OUTER) return ring_colsum_kernel_##SUF(tpr, ch);                            \
     if (pipe && op == B200NORM_OP_LAYERNORM_FWD) return ring_ln_pipe_kernel_##SUF(tpr, ch, add);             \
     if (add) return ring_add_kernel_##SUF(op, tpr, ch, psmem);                                               \
-    if (is_norm_bwd(op) && !cached && pipe) return ring_bwd_pipe_kernel_##SUF(op, tpr, ch);                  \
+    if (is_norm_bwd(op) && !cached && pipe) return ring_bwd_pipe_kernel_##SUF(op, tpr, ch, lean);            \
     if (op == B200NORM_OP_RMSNORM_FWD && pipe) return ring_fwd_pipe_kernel_##SUF(op, tpr, ch);               \
     return is_norm_bwd(op) ? ring_bwd_kernel_##SUF(op, tpr, ch, cached) : ring_fwd_kernel_##SUF(op, tpr, ch, psmem); \
   }
 template <typename T>
-RingKernel ring_kernel_for(int op, int tpr, int ch, bool cached, bool psmem, bool add, bool pipe, bool red);
+RingKernel ring_kernel_for(int op, int tpr, int ch, bool cached, bool psmem, bool add, bool pipe, bool red, bool lean);
 B200_RING_KERNEL_FOR(float, f32)
 B200_RING_KERNEL_FOR(__nv_bfloat16, bf16)
 B200_RING_KERNEL_FOR(__half, f16)
@@ -295,11 +296,12 @@ int prepare_ring_kernel(DeviceCtx& ctx, RingKernel k, int smem, int cluster) {
   return B200NORM_OK;
 }
 
-RingKernel ring_kernel_any(int dt, int op, int tpr, int ch, bool cached, bool psmem, bool add, bool pipe, bool red) {
+RingKernel ring_kernel_any(int dt, int op, int tpr, int ch, bool cached, bool psmem, bool add, bool pipe, bool red,
+                           bool lean) {
   switch (dt) {
-    case B200NORM_DT_F32: return ring_kernel_for<float>(op, tpr, ch, cached, psmem, add, pipe, red);
-    case B200NORM_DT_BF16: return ring_kernel_for<__nv_bfloat16>(op, tpr, ch, cached, psmem, add, pipe, red);
-    case B200NORM_DT_F16: return ring_kernel_for<__half>(op, tpr, ch, cached, psmem, add, pipe, red);
+    case B200NORM_DT_F32: return ring_kernel_for<float>(op, tpr, ch, cached, psmem, add, pipe, red, lean);
+    case B200NORM_DT_BF16: return ring_kernel_for<__nv_bfloat16>(op, tpr, ch, cached, psmem, add, pipe, red, lean);
+    case B200NORM_DT_F16: return ring_kernel_for<__half>(op, tpr, ch, cached, psmem, add, pipe, red, lean);
     default: return nullptr;
   }
 }
@@ -588,6 +590,8 @@ bool try_ring_plan(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, int 
   // (16-bit only: the fp32 single-group kernel is at the roofline already, 163 vs 182 us at N = 8192)
   if (ln_pipe) p.pipe = true;
   p.stats_reduce = inner_red && d.op == B200NORM_OP_LAYERNORM_FWD;
+  p.lean = p.pipe && d.op == B200NORM_OP_RMSNORM_BWD && !(d.flags & B200NORM_F_RMS_BWD_CENTERED) && tpr >= 256 &&
+           kn.no_lean == 0;
   if (d.op == B200NORM_OP_RMSNORM_FWD && !add &&
       (C > 1 || (tpr == 512 && es == 2 && ch == 3 && (nchunks + 255) / 256 == 6) || kn.pipe != 0) && ch > 0 &&
       tile_rows == 1 && tpr >= 64 && (ch <= 4 || tpr >= 256) && kn.no_pipe == 0) {
@@ -602,7 +606,7 @@ bool try_ring_plan(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, int 
   p.smem = p.off_ring + ring_bytes;
 
   const int64_t ntiles = ceil_div64(d.rows, tile_rows);
-  int64_t nclusters = max_active_clusters(ctx, ring_kernel_any(d.io_dtype, d.op, tpr, ch, cached, p.psmem, add, p.pipe, p.stats_reduce), p.block,
+  int64_t nclusters = max_active_clusters(ctx, ring_kernel_any(d.io_dtype, d.op, tpr, ch, cached, p.psmem, add, p.pipe, p.stats_reduce, p.lean), p.block,
                                           (int)p.smem, C);
   if (nclusters > ntiles) nclusters = ntiles;
   if (nclusters < 1) nclusters = 1;
@@ -951,7 +955,7 @@ int launch_typed(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, const 
 
   // ---- ring kernels ----
   RingKernel k = ring_kernel_for<T>(d.op, plan.tpr, plan.ch, plan.cached, plan.psmem, is_add_fwd(d), plan.pipe,
-                                    plan.stats_reduce);
+                                    plan.stats_reduce, plan.lean);
   if (k == nullptr)
     return fail(B200NORM_ERR_UNSUPPORTED, "no ring kernel for op %d tpr %d ch %d", d.op, plan.tpr, plan.ch);
   {

@@ -22,10 +22,11 @@ RingKernel ring_add_kernel_f16(int op, int tpr, int ch, bool psmem);
 RingKernel ring_bwd_kernel_f32(int op, int tpr, int ch, bool cached);
 RingKernel ring_bwd_kernel_bf16(int op, int tpr, int ch, bool cached);
 RingKernel ring_bwd_kernel_f16(int op, int tpr, int ch, bool cached);
-// pipelined re-read backward (split-phase reductions overlapped across rows): ch in {3,4}, tpr in {64..512}
-RingKernel ring_bwd_pipe_kernel_f32(int op, int tpr, int ch);
-RingKernel ring_bwd_pipe_kernel_bf16(int op, int tpr, int ch);
-RingKernel ring_bwd_pipe_kernel_f16(int op, int tpr, int ch);
+// pipelined re-read backward (split-phase reductions overlapped across rows): ch in {3,4}, tpr in {64..512};
+// lean: RMSNorm without the centring term on the instruction-trimmed kernel (tpr 256 / 512)
+RingKernel ring_bwd_pipe_kernel_f32(int op, int tpr, int ch, bool lean);
+RingKernel ring_bwd_pipe_kernel_bf16(int op, int tpr, int ch, bool lean);
+RingKernel ring_bwd_pipe_kernel_f16(int op, int tpr, int ch, bool lean);
 // pipelined RMSNorm forward (cluster rows)
 RingKernel ring_fwd_pipe_kernel_f32(int op, int tpr, int ch);
 RingKernel ring_fwd_pipe_kernel_bf16(int op, int tpr, int ch);

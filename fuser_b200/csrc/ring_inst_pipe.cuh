@@ -3,15 +3,22 @@
 
 #include "../../include/b200norm.h"
 #include "kernels_bwd.cuh"
+#include "kernels_bwd_lean.cuh"
 #include "kernels_fwd.cuh"
 #include "ring_dispatch.cuh"
 
 namespace b200norm {
 
 template <typename T>
-RingKernel ring_bwd_pipe_kernel_for(int op, int tpr, int ch) {
+RingKernel ring_bwd_pipe_kernel_for(int op, int tpr, int ch, bool lean) {
   const bool ln = op == B200NORM_OP_LAYERNORM_BWD;
   if (!ln && op != B200NORM_OP_RMSNORM_BWD) return nullptr;
+  if (lean && !ln) {  // RMSNorm backward without the centring term: the lean kernel (kernels_bwd_lean.cuh)
+    if (tpr == 512 && ch == 4) return rms_bwd_pipe_lean_kernel<T, 512, 4>;
+    if (tpr == 512 && ch == 3) return rms_bwd_pipe_lean_kernel<T, 512, 3>;
+    if (tpr == 256 && ch == 4) return rms_bwd_pipe_lean_kernel<T, 256, 4>;
+    if (tpr == 256 && ch == 3) return rms_bwd_pipe_lean_kernel<T, 256, 3>;
+  }
 #define B200_PIPE_CASE(TPR)                                                   \
   case TPR:                                                                   \
     if (ch == 3) return ln ? norm_bwd_pipe_kernel<T, TPR, 3, true> : norm_bwd_pipe_kernel<T, TPR, 3, false>; \

@@ -420,3 +420,19 @@ def thunder_rms_norm_bwd_cpp(fd, dtype, weight=True):
     if weight:
         dw = fd.ops.sum(fd.ops.mul(dyf, fd.ops.mul(xf, fd.ops.reciprocal(rms))), dims=[0])
         fd.add_output(_down(fd, dw, dtype))
+
+
+def reduce_py(fd, dtype, kind="sum", dims=(1,)):
+    """A plain Reduction segment (csrc/scheduler/reduction.cpp): sum / max over the last axis, or the sum over
+    the outer axes; reduced-precision inputs are cast up first and the result cast back, as every benchmark does."""
+    x = fd.define_tensor(shape=[-1, -1], contiguity=[True, True], dtype=dtype)
+    r = (fd.ops.sum if kind == "sum" else fd.ops.max)(_up(fd, x, dtype), dims=list(dims))
+    fd.add_output(_down(fd, r, dtype))
+
+
+def var_mean_py(fd, dtype, correction=1):
+    """Stand-alone variance_mean over the last axis (csrc/ops/normalization.cpp:93-158): fp32 statistics."""
+    x = fd.define_tensor(shape=[-1, -1], contiguity=[True, True], dtype=dtype)
+    var, mean = fd.ops.var_mean(_up(fd, x, dtype), dims=[1], correction=correction, keepdim=False)
+    fd.add_output(var)
+    fd.add_output(mean)
