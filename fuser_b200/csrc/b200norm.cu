@@ -590,7 +590,7 @@ bool try_ring_plan(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, int 
   // (16-bit only: the fp32 single-group kernel is at the roofline already, 163 vs 182 us at N = 8192)
   if (ln_pipe) p.pipe = true;
   p.stats_reduce = inner_red && d.op == B200NORM_OP_LAYERNORM_FWD;
-  p.lean = p.pipe && d.op == B200NORM_OP_RMSNORM_BWD && !(d.flags & B200NORM_F_RMS_BWD_CENTERED) && tpr >= 256 &&
+  p.lean = p.pipe && d.op == B200NORM_OP_RMSNORM_BWD && !(d.flags & B200NORM_F_RMS_BWD_CENTERED) && tpr == 512 &&
            kn.no_lean == 0;
   if (d.op == B200NORM_OP_RMSNORM_FWD && !add &&
       (C > 1 || (tpr == 512 && es == 2 && ch == 3 && (nchunks + 255) / 256 == 6) || kn.pipe != 0) && ch > 0 &&
@@ -605,6 +605,10 @@ bool try_ring_plan(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, int 
   }
   p.smem = p.off_ring + ring_bytes;
 
+  // only the plans the planner emits are instantiated (ring_inst_*.cuh): a combination forced through the tuning
+  // knobs may have no kernel — then this cluster size is simply not feasible
+  if (ring_kernel_any(d.io_dtype, d.op, tpr, ch, cached, p.psmem, add, p.pipe, p.stats_reduce, p.lean) == nullptr)
+    return false;
   const int64_t ntiles = ceil_div64(d.rows, tile_rows);
   int64_t nclusters = max_active_clusters(ctx, ring_kernel_any(d.io_dtype, d.op, tpr, ch, cached, p.psmem, add, p.pipe, p.stats_reduce, p.lean), p.block,
                                           (int)p.smem, C);

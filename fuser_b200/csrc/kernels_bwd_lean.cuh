@@ -49,8 +49,15 @@ __global__ void __launch_bounds__(kMaxBlock, 1) rms_bwd_pipe_lean_kernel(const R
   const bool want_dw = (p.flags & kFlagOutDw) != 0;
   const bool stat_rms = (p.flags & kFlagStatIsRms) != 0;
   const size_t col0_bytes = (size_t)g.crank * p.slice_bytes;
-  uint4 wq[CH];
-  load_params_to_regs<T, TPR, CH>(p.weight, col0_bytes, g.gtid, nchunks, 1.0f, wq);
+  // the weight stays UNPACKED (fp32 pairs) in registers: both passes of every row use it, and unpacking it
+  // there costs 16 ALU operations per chunk and row (the ncu capture showed the compiler doing exactly that)
+  float2 wf[CH][H];
+  {
+    uint4 wq[CH];
+    load_params_to_regs<T, TPR, CH>(p.weight, col0_bytes, g.gtid, nchunks, 1.0f, wq);
+#pragma unroll
+    for (int j = 0; j < CH; ++j) IO<T>::unpack2(wq[j], wf[j]);
+  }
 
   float2 dw_acc[CH][H];
   float2 none[1][H];
@@ -100,14 +107,13 @@ __global__ void __launch_bounds__(kMaxBlock, 1) rms_bwd_pipe_lean_kernel(const R
     const float2 is2 = f2(stat_rms ? rcp_fast(st) : st);
     float2 s = f2(0.f);
     for_each_chunk<TPR, CH>(g.gtid, nchunks, [&](int j, int coff) {
-      float2 dy[H], x[H], w[H];
+      float2 dy[H], x[H];
       IO<T>::unpack2(ld_smem_u4(dyrow + 16 * coff), dy);
       IO<T>::unpack2(ld_smem_u4(xrow + 16 * coff), x);
-      IO<T>::unpack2(wq[j], w);
 #pragma unroll
       for (int k = 0; k < H; ++k) {
         const float2 pr = f2mul(dy[k], x[k]);
-        s = f2fma(pr, w[k], s);
+        s = f2fma(pr, wf[j][k], s);
         dw_acc[j][k] = f2fma(pr, is2, dw_acc[j][k]);
       }
     });
@@ -169,12 +175,11 @@ __global__ void __launch_bounds__(kMaxBlock, 1) rms_bwd_pipe_lean_kernel(const R
       const uint8_t* dyrow = smem_raw + c2_off + 16u * (uint32_t)g.gtid;
       const uint8_t* xrow = dyrow + stream_bytes;
       for_each_chunk<TPR, CH>(g.gtid, nchunks, [&](int j, int coff) {
-        float2 dy[H], x[H], w[H], dx[H];
+        float2 dy[H], x[H], dx[H];
         IO<T>::unpack2(ld_smem_u4(dyrow + 16 * coff), dy);
         IO<T>::unpack2(ld_smem_u4(xrow + 16 * coff), x);
-        IO<T>::unpack2(wq[j], w);
 #pragma unroll
-        for (int q = 0; q < H; ++q) dx[q] = f2fma(A, f2mul(dy[q], w[q]), f2mul(Bx, x[q]));
+        for (int q = 0; q < H; ++q) dx[q] = f2fma(A, f2mul(dy[q], wf[j][q]), f2mul(Bx, x[q]));
         st_global_stream(dxrow + 16 * coff, IO<T>::pack2(dx));
       });
     }

@@ -16,15 +16,25 @@ namespace b200norm {
     case 4: return K<T, TPR, 4, ##__VA_ARGS__>;         \
     default: return nullptr;                            \
   }
+#ifdef B200NORM_ALL_KERNELS
+#define B200_ADD_CH_SWITCH_HI B200_ADD_CH_SWITCH
+#else  // from 64 threads per row on the planner only emits 3 or 4 chunks per thread (see ring_inst_fwd.cuh)
+#define B200_ADD_CH_SWITCH_HI(K, TPR, ...)              \
+  switch (ch) {                                         \
+    case 3: return K<T, TPR, 3, ##__VA_ARGS__>;         \
+    case 4: return K<T, TPR, 4, ##__VA_ARGS__>;         \
+    default: return nullptr;                            \
+  }
+#endif
 #define B200_ADD_TPR_SWITCH(K, ...)                                       \
   switch (tpr) {                                                          \
     case 32: B200_ADD_CH_SWITCH(K, 32, ##__VA_ARGS__)                     \
-    case 64: B200_ADD_CH_SWITCH(K, 64, ##__VA_ARGS__)                     \
-    case 128: B200_ADD_CH_SWITCH(K, 128, ##__VA_ARGS__)                   \
-    case 256: B200_ADD_CH_SWITCH(K, 256, ##__VA_ARGS__)                   \
+    case 64: B200_ADD_CH_SWITCH_HI(K, 64, ##__VA_ARGS__)                  \
+    case 128: B200_ADD_CH_SWITCH_HI(K, 128, ##__VA_ARGS__)                \
+    case 256: B200_ADD_CH_SWITCH_HI(K, 256, ##__VA_ARGS__)                \
     case 512:                                                             \
       if (ch == 0) return K<T, 512, 0, ##__VA_ARGS__>;                    \
-      B200_ADD_CH_SWITCH(K, 512, ##__VA_ARGS__)                           \
+      B200_ADD_CH_SWITCH_HI(K, 512, ##__VA_ARGS__)                        \
     default: return nullptr;                                              \
   }
 
@@ -41,6 +51,7 @@ RingKernel ring_add_kernel_for(int op, int tpr, int ch, bool psmem) {
   }
 }
 #undef B200_ADD_TPR_SWITCH
+#undef B200_ADD_CH_SWITCH_HI
 #undef B200_ADD_CH_SWITCH
 
 }  // namespace b200norm

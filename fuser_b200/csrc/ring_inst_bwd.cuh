@@ -7,9 +7,14 @@
 
 namespace b200norm {
 
+// Only what the planner can emit is instantiated (-DB200NORM_ALL_KERNELS: the full cross product, for tuning with
+// B200NORM_TPR / B200NORM_BWD_REREAD): the cached form takes the smallest group that holds the slice at <= 2 chunks
+// per thread — so from 64 threads on it is always 2 —, and the re-read form is only chosen when 512 threads x 2 chunks
+// do not hold the slice, i.e. at 512 threads per row.
 template <typename T, bool LN>
 RingKernel ring_bwd_kernel_sel(int tpr, int ch, bool cached) {
-#define B200_BWD_CASE(TPR)                                                          \
+#ifdef B200NORM_ALL_KERNELS
+#define B200_BWD_CASE(TPR, LOW, REREAD)                                             \
   case TPR:                                                                         \
     if (cached) {                                                                   \
       if (ch == 1) return norm_bwd_ring_kernel<T, TPR, 1, LN, true>;                \
@@ -19,12 +24,24 @@ RingKernel ring_bwd_kernel_sel(int tpr, int ch, bool cached) {
       if (ch == 4 && !LN) return norm_bwd_ring_kernel<T, TPR, 4, false, false>;     \
     }                                                                               \
     return nullptr;
+#else
+#define B200_BWD_CASE(TPR, LOW, REREAD)                                             \
+  case TPR:                                                                         \
+    if (cached) {                                                                   \
+      if (LOW && ch == 1) return norm_bwd_ring_kernel<T, TPR, LOW ? 1 : 2, LN, true>; \
+      if (ch == 2) return norm_bwd_ring_kernel<T, TPR, 2, LN, true>;                \
+    } else if (REREAD) {                                                            \
+      if (ch == 3) return norm_bwd_ring_kernel<T, TPR, 3, LN, !REREAD>;             \
+      if (ch == 4 && !LN) return norm_bwd_ring_kernel<T, TPR, REREAD ? 4 : 3, false, !REREAD>; \
+    }                                                                               \
+    return nullptr;
+#endif
   switch (tpr) {
-    B200_BWD_CASE(32)
-    B200_BWD_CASE(64)
-    B200_BWD_CASE(128)
-    B200_BWD_CASE(256)
-    B200_BWD_CASE(512)
+    B200_BWD_CASE(32, true, false)
+    B200_BWD_CASE(64, false, false)
+    B200_BWD_CASE(128, false, false)
+    B200_BWD_CASE(256, false, false)
+    B200_BWD_CASE(512, false, true)
     default: return nullptr;
   }
 #undef B200_BWD_CASE

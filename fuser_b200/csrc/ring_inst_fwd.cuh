@@ -7,6 +7,17 @@
 
 namespace b200norm {
 
+// Only the (threads per row, chunks per thread) pairs the planner can emit are instantiated: it picks the SMALLEST
+// group size whose threads hold the slice at <= 4 chunks each, so from 64 threads on a thread owns 3 or 4 chunks
+// (1 or 2 would have fit the next smaller group). -DB200NORM_ALL_KERNELS restores the full cross product for
+// tuning with B200NORM_TPR.
+#ifdef B200NORM_ALL_KERNELS
+#define B200_LOW_CH(K, TPR, ...)                        \
+    case 1: return K<T, TPR, 1, ##__VA_ARGS__>;         \
+    case 2: return K<T, TPR, 2, ##__VA_ARGS__>;
+#else
+#define B200_LOW_CH(K, TPR, ...)
+#endif
 #define B200_CH_SWITCH(K, TPR, ...)                     \
   switch (ch) {                                         \
     case 1: return K<T, TPR, 1, ##__VA_ARGS__>;         \
@@ -15,12 +26,18 @@ namespace b200norm {
     case 4: return K<T, TPR, 4, ##__VA_ARGS__>;         \
     default: return nullptr;                            \
   }
+#define B200_CH_SWITCH_HI(K, TPR, ...)                  \
+  switch (ch) {                                         \
+    B200_LOW_CH(K, TPR, ##__VA_ARGS__)                  \
+    case 3: return K<T, TPR, 3, ##__VA_ARGS__>;         \
+    case 4: return K<T, TPR, 4, ##__VA_ARGS__>;         \
+    default: return nullptr;                            \
+  }
 // CH 5 / 6 (TPR 256 / 512 only): kernels whose per-chunk register state is just x keep two
 // consumer groups per CTA at N = 10240 / 12288 instead of one 512-thread group.
 #define B200_CH_SWITCH_WIDE(K, TPR, ...)                \
   switch (ch) {                                         \
-    case 1: return K<T, TPR, 1, ##__VA_ARGS__>;         \
-    case 2: return K<T, TPR, 2, ##__VA_ARGS__>;         \
+    B200_LOW_CH(K, TPR, ##__VA_ARGS__)                  \
     case 3: return K<T, TPR, 3, ##__VA_ARGS__>;         \
     case 4: return K<T, TPR, 4, ##__VA_ARGS__>;         \
     case 5: return K<T, TPR, 5, ##__VA_ARGS__>;         \
@@ -30,8 +47,8 @@ namespace b200norm {
 #define B200_TPR_SWITCH_WIDE(K, ...)                                      \
   switch (tpr) {                                                          \
     case 32: B200_CH_SWITCH(K, 32, ##__VA_ARGS__)                         \
-    case 64: B200_CH_SWITCH(K, 64, ##__VA_ARGS__)                         \
-    case 128: B200_CH_SWITCH(K, 128, ##__VA_ARGS__)                       \
+    case 64: B200_CH_SWITCH_HI(K, 64, ##__VA_ARGS__)                      \
+    case 128: B200_CH_SWITCH_HI(K, 128, ##__VA_ARGS__)                    \
     case 256: B200_CH_SWITCH_WIDE(K, 256, ##__VA_ARGS__)                  \
     case 512:                                                             \
       if (ch == 0) return K<T, 512, 0, ##__VA_ARGS__>;                    \
@@ -41,12 +58,12 @@ namespace b200norm {
 #define B200_TPR_SWITCH(K, ...)                                           \
   switch (tpr) {                                                          \
     case 32: B200_CH_SWITCH(K, 32, ##__VA_ARGS__)                         \
-    case 64: B200_CH_SWITCH(K, 64, ##__VA_ARGS__)                         \
-    case 128: B200_CH_SWITCH(K, 128, ##__VA_ARGS__)                       \
-    case 256: B200_CH_SWITCH(K, 256, ##__VA_ARGS__)                       \
+    case 64: B200_CH_SWITCH_HI(K, 64, ##__VA_ARGS__)                      \
+    case 128: B200_CH_SWITCH_HI(K, 128, ##__VA_ARGS__)                    \
+    case 256: B200_CH_SWITCH_HI(K, 256, ##__VA_ARGS__)                    \
     case 512:                                                             \
       if (ch == 0) return K<T, 512, 0, ##__VA_ARGS__>;                    \
-      B200_CH_SWITCH(K, 512, ##__VA_ARGS__)                               \
+      B200_CH_SWITCH_HI(K, 512, ##__VA_ARGS__)                            \
     default: return nullptr;                                              \
   }
 
@@ -69,6 +86,8 @@ RingKernel ring_fwd_kernel_for(int op, int tpr, int ch, bool psmem) {
 #undef B200_TPR_SWITCH
 #undef B200_TPR_SWITCH_WIDE
 #undef B200_CH_SWITCH_WIDE
+#undef B200_CH_SWITCH_HI
 #undef B200_CH_SWITCH
+#undef B200_LOW_CH
 
 }  // namespace b200norm

@@ -9,10 +9,17 @@ namespace b200norm {
 
 template <typename T>
 RingKernel ring_ln_pipe_kernel_for(int tpr, int ch, bool add) {
+// (3 or 4 chunks per thread: what the planner emits from 64 threads per row on, see ring_inst_fwd.cuh)
+#ifdef B200NORM_ALL_KERNELS
+#define B200_LNPIPE_LOW(TPR, ADD)                                     \
+    case 1: return layernorm_fwd_pipe_kernel<T, TPR, 1, ADD>;         \
+    case 2: return layernorm_fwd_pipe_kernel<T, TPR, 2, ADD>;
+#else
+#define B200_LNPIPE_LOW(TPR, ADD)
+#endif
 #define B200_LNPIPE_CH(TPR, ADD)                                      \
   switch (ch) {                                                       \
-    case 1: return layernorm_fwd_pipe_kernel<T, TPR, 1, ADD>;         \
-    case 2: return layernorm_fwd_pipe_kernel<T, TPR, 2, ADD>;         \
+    B200_LNPIPE_LOW(TPR, ADD)                                         \
     case 3: return layernorm_fwd_pipe_kernel<T, TPR, 3, ADD>;         \
     case 4: return layernorm_fwd_pipe_kernel<T, TPR, 4, ADD>;         \
     default: return nullptr;                                          \
@@ -37,6 +44,7 @@ RingKernel ring_ln_pipe_kernel_for(int tpr, int ch, bool add) {
     default: return nullptr;
   }
 #undef B200_LNPIPE_CH
+#undef B200_LNPIPE_LOW
 }
 
 }  // namespace b200norm

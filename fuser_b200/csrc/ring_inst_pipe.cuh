@@ -16,18 +16,19 @@ RingKernel ring_bwd_pipe_kernel_for(int op, int tpr, int ch, bool lean) {
   if (lean && !ln) {  // RMSNorm backward without the centring term: the lean kernel (kernels_bwd_lean.cuh)
     if (tpr == 512 && ch == 4) return rms_bwd_pipe_lean_kernel<T, 512, 4>;
     if (tpr == 512 && ch == 3) return rms_bwd_pipe_lean_kernel<T, 512, 3>;
-    if (tpr == 256 && ch == 4) return rms_bwd_pipe_lean_kernel<T, 256, 4>;
-    if (tpr == 256 && ch == 3) return rms_bwd_pipe_lean_kernel<T, 256, 3>;
   }
 #define B200_PIPE_CASE(TPR)                                                   \
   case TPR:                                                                   \
     if (ch == 3) return ln ? norm_bwd_pipe_kernel<T, TPR, 3, true> : norm_bwd_pipe_kernel<T, TPR, 3, false>; \
     if (ch == 4 && !ln) return norm_bwd_pipe_kernel<T, TPR, 4, false>;        \
     return nullptr;
+  // (the re-read form is only chosen when 512 threads x 2 chunks do not hold the slice: 512 threads per row)
   switch (tpr) {
+#ifdef B200NORM_ALL_KERNELS
     B200_PIPE_CASE(64)
     B200_PIPE_CASE(128)
     B200_PIPE_CASE(256)
+#endif
     B200_PIPE_CASE(512)
     default: return nullptr;
   }
@@ -38,10 +39,16 @@ RingKernel ring_bwd_pipe_kernel_for(int op, int tpr, int ch, bool lean) {
 template <typename T>
 RingKernel ring_fwd_pipe_kernel_for(int op, int tpr, int ch) {
   if (op != B200NORM_OP_RMSNORM_FWD) return nullptr;
+#ifdef B200NORM_ALL_KERNELS
+#define B200_FPIPE_LOW(TPR)                                                   \
+    case 1: return rmsnorm_fwd_pipe_kernel<T, TPR, 1>;                        \
+    case 2: return rmsnorm_fwd_pipe_kernel<T, TPR, 2>;
+#else
+#define B200_FPIPE_LOW(TPR)
+#endif
 #define B200_FPIPE_CH(TPR, MAXCH)                                              \
   switch (ch) {                                                               \
-    case 1: return rmsnorm_fwd_pipe_kernel<T, TPR, 1>;                        \
-    case 2: return rmsnorm_fwd_pipe_kernel<T, TPR, 2>;                        \
+    B200_FPIPE_LOW(TPR)                                                       \
     case 3: return rmsnorm_fwd_pipe_kernel<T, TPR, 3>;                        \
     case 4: return rmsnorm_fwd_pipe_kernel<T, TPR, 4>;                        \
     case 5: if (MAXCH >= 5) return rmsnorm_fwd_pipe_kernel<T, TPR, (MAXCH >= 5 ? 5 : 1)>; return nullptr; \
@@ -56,6 +63,7 @@ RingKernel ring_fwd_pipe_kernel_for(int op, int tpr, int ch) {
     default: return nullptr;
   }
 #undef B200_FPIPE_CH
+#undef B200_FPIPE_LOW
 }
 
 }  // namespace b200norm

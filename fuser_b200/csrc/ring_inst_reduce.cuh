@@ -15,13 +15,23 @@ namespace b200norm {
     case 4: return K<T, TPR, 4>;               \
     default: return nullptr;                   \
   }
+#ifdef B200NORM_ALL_KERNELS
+#define B200_RED_CH_HI B200_RED_CH
+#else  // from 64 threads per row on the planner only emits 3 or 4 chunks per thread (see ring_inst_fwd.cuh)
+#define B200_RED_CH_HI(K, TPR)                 \
+  switch (ch) {                                \
+    case 3: return K<T, TPR, 3>;               \
+    case 4: return K<T, TPR, 4>;               \
+    default: return nullptr;                   \
+  }
+#endif
 #define B200_RED_TPR(K)                        \
   switch (tpr) {                               \
     case 32: B200_RED_CH(K, 32)                \
-    case 64: B200_RED_CH(K, 64)                \
-    case 128: B200_RED_CH(K, 128)              \
-    case 256: B200_RED_CH(K, 256)              \
-    case 512: B200_RED_CH(K, 512)              \
+    case 64: B200_RED_CH_HI(K, 64)             \
+    case 128: B200_RED_CH_HI(K, 128)           \
+    case 256: B200_RED_CH_HI(K, 256)           \
+    case 512: B200_RED_CH_HI(K, 512)           \
     default: return nullptr;                   \
   }
 
@@ -37,6 +47,7 @@ RingKernel ring_colsum_kernel_for(int tpr, int ch) {
   B200_RED_TPR(colsum_ring_kernel)
 }
 #undef B200_RED_TPR
+#undef B200_RED_CH_HI
 #undef B200_RED_CH
 
 }  // namespace b200norm
