@@ -243,7 +243,7 @@ struct Plan {
   bool cached = false;
   bool psmem = false;      // LayerNorm fwd: weight / bias staged in shared memory as fp32
   bool pipe = false;       // backward, re-read form: split-phase reductions pipelined across rows
-  bool lean = false;       // RMSNorm backward without the centring term on the instruction-trimmed pipe kernel
+  bool lean = false;       // RMSNorm backward without the centring term: kernels specialised for it
   bool stats_reduce = false;  // LAYERNORM_FWD | NO_Y (var_mean / welford): runs on the inner-reduction kernel
   int nparts = 0;          // partial rows produced by the main kernel
   int rows_per_split = 0;  // generic colsum
@@ -270,7 +270,8 @@ uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
     if (add) return ring_add_kernel_##SUF(op, tpr, ch, psmem);                                               \
     if (is_norm_bwd(op) && !cached && pipe) return ring_bwd_pipe_kernel_##SUF(op, tpr, ch, lean);            \
     if (op == B200NORM_OP_RMSNORM_FWD && pipe) return ring_fwd_pipe_kernel_##SUF(op, tpr, ch);               \
-    return is_norm_bwd(op) ? ring_bwd_kernel_##SUF(op, tpr, ch, cached) : ring_fwd_kernel_##SUF(op, tpr, ch, psmem); \
+    return is_norm_bwd(op) ? ring_bwd_kernel_##SUF(op, tpr, ch, cached, !lean)                                 \
+                           : ring_fwd_kernel_##SUF(op, tpr, ch, psmem);                                    \
   }
 template <typename T>
 RingKernel ring_kernel_for(int op, int tpr, int ch, bool cached, bool psmem, bool add, bool pipe, bool red, bool lean);
@@ -590,8 +591,9 @@ bool try_ring_plan(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, int 
   // (16-bit only: the fp32 single-group kernel is at the roofline already, 163 vs 182 us at N = 8192)
   if (ln_pipe) p.pipe = true;
   p.stats_reduce = inner_red && d.op == B200NORM_OP_LAYERNORM_FWD;
-  p.lean = p.pipe && d.op == B200NORM_OP_RMSNORM_BWD && !(d.flags & B200NORM_F_RMS_BWD_CENTERED) && tpr == 512 &&
-           kn.no_lean == 0;
+  // RMSNorm backward without the centring term: the instantiations that neither accumulate sum(g) nor reduce it
+  // (ring kernels), and the instruction-trimmed pipe kernel (kernels_bwd_lean.cuh)
+  p.lean = d.op == B200NORM_OP_RMSNORM_BWD && !(d.flags & B200NORM_F_RMS_BWD_CENTERED) && kn.no_lean == 0;
   if (d.op == B200NORM_OP_RMSNORM_FWD && !add &&
       (C > 1 || (tpr == 512 && es == 2 && ch == 3 && (nchunks + 255) / 256 == 6) || kn.pipe != 0) && ch > 0 &&
       tile_rows == 1 && tpr >= 64 && (ch <= 4 || tpr >= 256) && kn.no_pipe == 0) {

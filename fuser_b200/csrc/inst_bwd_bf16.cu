@@ -1,7 +1,7 @@
 // Instantiations of the norm-backward ring kernels for __nv_bfloat16 (see ring_inst_bwd.cuh).
 #include "ring_inst_bwd.cuh"
 namespace b200norm {
-RingKernel ring_bwd_kernel_bf16(int op, int tpr, int ch, bool cached) {
-  return ring_bwd_kernel_for<__nv_bfloat16>(op, tpr, ch, cached);
+RingKernel ring_bwd_kernel_bf16(int op, int tpr, int ch, bool cached, bool centered) {
+  return ring_bwd_kernel_for<__nv_bfloat16>(op, tpr, ch, cached, centered);
 }
 }  // namespace b200norm

@@ -19,9 +19,9 @@ RingKernel ring_add_kernel_f32(int op, int tpr, int ch, bool psmem);
 RingKernel ring_add_kernel_bf16(int op, int tpr, int ch, bool psmem);
 RingKernel ring_add_kernel_f16(int op, int tpr, int ch, bool psmem);
 // norm backward: cached (g / xc in registers, ch in {1,2}) or re-read (ch in {3,4}, tpr 512... any tpr).
-RingKernel ring_bwd_kernel_f32(int op, int tpr, int ch, bool cached);
-RingKernel ring_bwd_kernel_bf16(int op, int tpr, int ch, bool cached);
-RingKernel ring_bwd_kernel_f16(int op, int tpr, int ch, bool cached);
+RingKernel ring_bwd_kernel_f32(int op, int tpr, int ch, bool cached, bool centered);
+RingKernel ring_bwd_kernel_bf16(int op, int tpr, int ch, bool cached, bool centered);
+RingKernel ring_bwd_kernel_f16(int op, int tpr, int ch, bool cached, bool centered);
 // pipelined re-read backward (split-phase reductions overlapped across rows): ch in {3,4}, tpr in {64..512};
 // lean: RMSNorm without the centring term on the instruction-trimmed kernel (tpr 256 / 512)
 RingKernel ring_bwd_pipe_kernel_f32(int op, int tpr, int ch, bool lean);

@@ -11,28 +11,28 @@ namespace b200norm {
 // B200NORM_TPR / B200NORM_BWD_REREAD): the cached form takes the smallest group that holds the slice at <= 2 chunks
 // per thread — so from 64 threads on it is always 2 —, and the re-read form is only chosen when 512 threads x 2 chunks
 // do not hold the slice, i.e. at 512 threads per row.
-template <typename T, bool LN>
+template <typename T, bool LN, bool CEN>
 RingKernel ring_bwd_kernel_sel(int tpr, int ch, bool cached) {
 #ifdef B200NORM_ALL_KERNELS
 #define B200_BWD_CASE(TPR, LOW, REREAD)                                             \
   case TPR:                                                                         \
     if (cached) {                                                                   \
-      if (ch == 1) return norm_bwd_ring_kernel<T, TPR, 1, LN, true>;                \
-      if (ch == 2) return norm_bwd_ring_kernel<T, TPR, 2, LN, true>;                \
+      if (ch == 1) return norm_bwd_ring_kernel<T, TPR, 1, LN, true, CEN>;                \
+      if (ch == 2) return norm_bwd_ring_kernel<T, TPR, 2, LN, true, CEN>;                \
     } else {                                                                        \
-      if (ch == 3) return norm_bwd_ring_kernel<T, TPR, 3, LN, false>;               \
-      if (ch == 4 && !LN) return norm_bwd_ring_kernel<T, TPR, 4, false, false>;     \
+      if (ch == 3) return norm_bwd_ring_kernel<T, TPR, 3, LN, false, CEN>;               \
+      if (ch == 4 && !LN) return norm_bwd_ring_kernel<T, TPR, 4, false, false, CEN>;     \
     }                                                                               \
     return nullptr;
 #else
 #define B200_BWD_CASE(TPR, LOW, REREAD)                                             \
   case TPR:                                                                         \
     if (cached) {                                                                   \
-      if (LOW && ch == 1) return norm_bwd_ring_kernel<T, TPR, LOW ? 1 : 2, LN, true>; \
-      if (ch == 2) return norm_bwd_ring_kernel<T, TPR, 2, LN, true>;                \
+      if (LOW && ch == 1) return norm_bwd_ring_kernel<T, TPR, LOW ? 1 : 2, LN, true, CEN>; \
+      if (ch == 2) return norm_bwd_ring_kernel<T, TPR, 2, LN, true, CEN>;                \
     } else if (REREAD) {                                                            \
-      if (ch == 3) return norm_bwd_ring_kernel<T, TPR, 3, LN, !REREAD>;             \
-      if (ch == 4 && !LN) return norm_bwd_ring_kernel<T, TPR, REREAD ? 4 : 3, false, !REREAD>; \
+      if (ch == 3) return norm_bwd_ring_kernel<T, TPR, 3, LN, !REREAD, CEN>;             \
+      if (ch == 4 && !LN) return norm_bwd_ring_kernel<T, TPR, REREAD ? 4 : 3, false, !REREAD, CEN>; \
     }                                                                               \
     return nullptr;
 #endif
@@ -47,11 +47,14 @@ RingKernel ring_bwd_kernel_sel(int tpr, int ch, bool cached) {
 #undef B200_BWD_CASE
 }
 
+// centered: the dx formula keeps -sum(g) (always for LayerNorm; B200NORM_F_RMS_BWD_CENTERED for RMSNorm)
 template <typename T>
-RingKernel ring_bwd_kernel_for(int op, int tpr, int ch, bool cached) {
+RingKernel ring_bwd_kernel_for(int op, int tpr, int ch, bool cached, bool centered) {
   switch (op) {
-    case B200NORM_OP_LAYERNORM_BWD: return ring_bwd_kernel_sel<T, true>(tpr, ch, cached);
-    case B200NORM_OP_RMSNORM_BWD: return ring_bwd_kernel_sel<T, false>(tpr, ch, cached);
+    case B200NORM_OP_LAYERNORM_BWD: return ring_bwd_kernel_sel<T, true, true>(tpr, ch, cached);
+    case B200NORM_OP_RMSNORM_BWD:
+      return centered ? ring_bwd_kernel_sel<T, false, true>(tpr, ch, cached)
+                      : ring_bwd_kernel_sel<T, false, false>(tpr, ch, cached);
     default: return nullptr;
   }
 }
