@@ -270,7 +270,7 @@ uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
     if (add) return ring_add_kernel_##SUF(op, tpr, ch, psmem);                                               \
     if (is_norm_bwd(op) && !cached && pipe) return ring_bwd_pipe_kernel_##SUF(op, tpr, ch, lean);            \
     if (op == B200NORM_OP_RMSNORM_FWD && pipe) return ring_fwd_pipe_kernel_##SUF(op, tpr, ch);               \
-    return is_norm_bwd(op) ? ring_bwd_kernel_##SUF(op, tpr, ch, cached, !lean)                                 \
+    return is_norm_bwd(op) ? ring_bwd_kernel_##SUF(op, tpr, ch, cached, !(lean && !cached))                    \
                            : ring_fwd_kernel_##SUF(op, tpr, ch, psmem);                                    \
   }
 template <typename T>
@@ -591,8 +591,10 @@ bool try_ring_plan(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, int 
   // (16-bit only: the fp32 single-group kernel is at the roofline already, 163 vs 182 us at N = 8192)
   if (ln_pipe) p.pipe = true;
   p.stats_reduce = inner_red && d.op == B200NORM_OP_LAYERNORM_FWD;
-  // RMSNorm backward without the centring term: the instantiations that neither accumulate sum(g) nor reduce it
-  // (ring kernels), and the instruction-trimmed pipe kernel (kernels_bwd_lean.cuh)
+  // RMSNorm backward without the centring term: the re-read instantiations that neither accumulate sum(g) nor
+  // reduce it ([32768,12288] bf16 382 -> 368 us, [16384,8192] 137 -> 132 us; the CACHED form measured slower
+  // specialised — C2 72 -> 75 us — and keeps the general instantiation), and the instruction-trimmed pipe kernel
+  // (kernels_bwd_lean.cuh: C5 332 -> 290 us)
   p.lean = d.op == B200NORM_OP_RMSNORM_BWD && !(d.flags & B200NORM_F_RMS_BWD_CENTERED) && kn.no_lean == 0;
   if (d.op == B200NORM_OP_RMSNORM_FWD && !add &&
       (C > 1 || (tpr == 512 && es == 2 && ch == 3 && (nchunks + 255) / 256 == 6) || kn.pipe != 0) && ch > 0 &&

@@ -6,7 +6,7 @@ import pytest
 import torch
 
 from fuser_b200 import _lib as L
-from fuser_b200.frontend import DataType, FusionDefinition
+from fuser_b200.frontend import DataType, FusionDefinition, torch_dtype_to_nvfuser_dtype
 from oracle import aten_oracle as AO
 from oracle import fusion_eval
 from tests import fusions as F
@@ -96,3 +96,34 @@ def test_fused_residual_add_fusions_execute_and_validate(shape, dt):
     ye, se = AO.rmsnorm_add_eager(x.cpu(), w.cpu(), r.cpu())
     assert torch.equal(s.cpu(), se), "residual stream must be bit-exact"
     AO.assert_close(y, ye, n, "rmsnorm_add vs eager")
+
+
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float32], ids=["bf16", "f32"])
+@pytest.mark.parametrize("shape", [(216, 1024), (300, 4096), (64, 12288), (40, 65536), (19, 1987)], ids=lambda s: f"{s[0]}x{s[1]}")
+def test_thunder_rms_norm_backward_as_written(shape, dt):
+    """csrc/ops/normalization.cpp:487-535 literally (projection x 1/2; used by
+    tests/cpp/test_combined_inner_outer_reduction.cpp:1197): through FusionDefinition and through ops, against the
+    ATen replay of the builder's text — and NOT equal to the textbook backward."""
+    from fuser_b200 import ops
+    m, n = shape
+    g = torch.Generator().manual_seed(m + n)
+    x = torch.randn(m, n, generator=g).to(dt)
+    dy = torch.randn(m, n, generator=g).to(dt)
+    w = torch.randn(n, generator=g).to(dt)
+    _, rms = AO.rms_norm_fwd_python(x, w, 1e-5)
+    dxe, dwe = AO.thunder_rms_norm_bwd(dy, x, rms, w)
+    nv = torch_dtype_to_nvfuser_dtype(dt)
+    with FusionDefinition() as fd:
+        F.thunder_rms_norm_bwd_cpp(fd, nv)
+    assert fd.segment().flags & L.F_RMS_BWD_HALF_PROJ
+    dx, dw = fd.execute([dy.cuda(), x.cuda(), rms.cuda(), w.cuda()])
+    torch.cuda.synchronize()
+    AO.assert_close(dx, dxe, n, "thunder dx")
+    AO.assert_close(dw, dwe, m, "thunder dw")
+    for variant in (L.VARIANT_AUTO, L.VARIANT_GENERIC):
+        dx2, dw2 = ops.rms_norm_bwd(dy.cuda(), x.cuda(), rms.cuda(), w.cuda(), stat_is_rms=True, half_projection=True,
+                                    variant=variant)
+        AO.assert_close(dx2, dxe, n, "thunder dx (ops)")
+        AO.assert_close(dw2, dwe, m, "thunder dw (ops)")
+    textbook, _ = AO.rms_norm_bwd_python(x, rms, dy, w)
+    assert not torch.allclose(dxe.float(), textbook.float(), rtol=1e-2, atol=1e-2), "the two forms differ by design"
