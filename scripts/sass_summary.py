@@ -60,8 +60,8 @@ def main():
     # whole library
     lib = os.path.join(ROOT, "fuser_b200", "lib", "libb200norm.so")
     sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
-    print("\n# whole library (" + f"{os.path.getsize(lib) / 1e6:.1f} MB): " + ", ".join(
-        f"{k} {len(re.findall(r'\\b' + re.escape(k), sass))}" for k in ["UBLKCP", "UTMALDG", "SYNCS", "STAS", "UCGABAR", "FFMA2"]))
+    counts = {k: len(re.findall(r"\b" + re.escape(k), sass)) for k in ["UBLKCP", "UTMALDG", "SYNCS", "STAS", "UCGABAR", "FFMA2"]}
+    print(f"\n# whole library ({os.path.getsize(lib) / 1e6:.1f} MB): " + ", ".join(f"{k} {v}" for k, v in counts.items()))
     print("# tensor-core instructions (HMMA / UTCMMA / tcgen05): " + str(len(re.findall(r"\b(HMMA|UTC[A-Z]*MMA|QMMA)", sass))) +
           " — nothing on this path is a contraction")
 
