@@ -1239,6 +1239,15 @@ int b200norm_query(const b200norm_desc* desc, b200norm_plan* plan) {
         plan->tile_rows = op.rows_cta;
         plan->smem_bytes = (int32_t)op.smem;
         plan->n_launches = 1;
+      } else if (int rg = 1, rpi = 1; outer_rows_shape(oa, &rg, &rpi)) {
+        // few columns, many rows (outer_rows.cuh): one cooperative kernel, a block of rows per CTA
+        plan->variant = B200NORM_VARIANT_GENERIC;
+        plan->cluster_size = 1;
+        plan->grid_x = rg;
+        plan->block_x = 512;
+        plan->threads_per_row = 512 / rpi;  // 16-byte chunks of one row
+        plan->tile_rows = rpi;
+        plan->n_launches = 1;
       } else {
         // shape-agnostic family (outer_generic.cuh): statistics / merge / apply kernels over (column blocks x row splits)
         int gx = 1, ns = 1, rps = 1;

@@ -25,6 +25,7 @@
 //     backward dx = y*dy - y*sum(y*dy) or dy - exp(y)*sum(dy) (csrc/ops/normalization.cpp:169-249).
 //     HBM traffic is the algorithmic minimum: every input element is read once, every output written once.
 #include "outer.cuh"
+#include "outer_rows.cuh"
 
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -1128,7 +1129,9 @@ size_t outer_generic_workspace_bytes(const OuterArgs& a) {
   if (a.M <= 0 || a.N <= 0) return B200NORM_WS_HEADER_BYTES;
   int gx = 1, ns = 1, rps = 1;
   outer_generic_plan(a, &gx, &ns, &rps);
-  return (size_t)B200NORM_WS_HEADER_BYTES + ((size_t)ns + 1u) * 2u * (size_t)a.N * 4u;  // partials + merged values
+  const size_t gen = ((size_t)ns + 1u) * 2u * (size_t)a.N * 4u;                    // partials + merged values
+  const size_t rows = ((size_t)a.sm_count * 3u + 2u) * (size_t)a.N * 4u;          // outer_rows.cuh: per-CTA triples + results
+  return (size_t)B200NORM_WS_HEADER_BYTES + (gen > rows ? gen : rows);
 }
 
 namespace {
@@ -1197,7 +1200,97 @@ int outer_generic_launch(const OuterArgs& a, int kind, void* stream_v, char* err
   return B200NORM_OK;
 }
 
+// Few columns, many rows (outer_rows.cuh): one persistent cooperative kernel. Returns B200NORM_ERR_UNSUPPORTED when
+// the shape / layout is not its own (the caller then takes the three-kernel family).
+template <typename T>
+cudaError_t launch_outer_rows_typed(const OuterRowsParams& p, bool bwd, int grid, size_t smem, cudaStream_t stream) {
+  const void* k = bwd ? (const void*)outer_rows_kernel<T, true> : (const void*)outer_rows_kernel<T, false>;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kOuterRowsThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeCooperative;  // two in-kernel grid barriers: the driver guarantees co-residency
+  attr.val.cooperative = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = 1;
+  void* args[] = {const_cast<OuterRowsParams*>(&p)};
+  return cudaLaunchKernelExC(&cfg, k, args);
+}
+
+int outer_rows_launch(const OuterArgs& a, void* stream_v, char* err, size_t errlen) {
+  const int es = a.dtype == B200NORM_DT_F32 ? 4 : 2;
+  const int64_t row_bytes = a.N * es;
+  auto al = [](const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15u) == 0; };
+  int grid = 1, rpi = 1;
+  if (!outer_rows_shape(a, &grid, &rpi)) return B200NORM_ERR_UNSUPPORTED;
+  if (a.in0_stride != a.N || (a.bwd && a.in1_stride != a.N) || (a.out != nullptr && a.out_stride != a.N))
+    return B200NORM_ERR_UNSUPPORTED;
+  if (!al(a.in0) || (a.bwd && !al(a.in1)) || (a.out != nullptr && !al(a.out))) return B200NORM_ERR_UNSUPPORTED;
+  OuterRowsParams p;
+  memset(&p, 0, sizeof(p));
+  p.in0 = a.in0;
+  p.in1 = a.in1;
+  p.out = a.out;
+  p.M = a.M;
+  p.N = (int32_t)a.N;
+  p.nchunks = (int32_t)(row_bytes / 16);
+  p.rpi = rpi;
+  p.active = p.rpi * p.nchunks;
+  p.rows_per_cta = (a.M + grid - 1) / grid;
+  const size_t need = (size_t)B200NORM_WS_HEADER_BYTES + ((size_t)grid * 3u + 2u) * (size_t)a.N * 4u;
+  if (a.workspace == nullptr || a.workspace_bytes < need || (reinterpret_cast<uintptr_t>(a.workspace) & 255u) != 0)
+    return set_err(err, errlen, B200NORM_ERR_WORKSPACE, "outer rows kernel: workspace %zu bytes, need %zu", a.workspace_bytes, need);
+  p.sync_word = reinterpret_cast<uint32_t*>(a.workspace);
+  p.part = reinterpret_cast<float*>(static_cast<uint8_t*>(a.workspace) + B200NORM_WS_HEADER_BYTES);
+  p.fin = p.part + (size_t)grid * 3u * (size_t)a.N;
+  p.weight = a.weight;
+  p.bias = a.bias;
+  p.mean_out = a.mean_out;
+  p.invstd_out = a.invstd_out;
+  p.mean_in = a.mean_in;
+  p.invstd_in = a.invstd_in;
+  p.dw_out = a.dw_out;
+  p.db_out = a.db_out;
+  p.inv_m = (float)(1.0 / (double)a.M);
+  p.eps = (float)a.eps;
+  const int vec = 16 / es;
+  const size_t smem = (size_t)p.active * vec * 3 * sizeof(float);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  cudaError_t e;
+  switch (a.dtype) {
+    case B200NORM_DT_F32: e = launch_outer_rows_typed<float>(p, a.bwd != 0, grid, smem, stream); break;
+    case B200NORM_DT_BF16: e = launch_outer_rows_typed<__nv_bfloat16>(p, a.bwd != 0, grid, smem, stream); break;
+    case B200NORM_DT_F16: e = launch_outer_rows_typed<__half>(p, a.bwd != 0, grid, smem, stream); break;
+    default: return B200NORM_ERR_UNSUPPORTED;
+  }
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    return set_err(err, errlen, B200NORM_ERR_CUDA + (int)e, "outer rows launch failed: %s", cudaGetErrorString(e));
+  }
+  return B200NORM_OK;
+}
+
 }  // namespace
+
+bool outer_rows_shape(const OuterArgs& a, int* grid_out, int* rows_per_iter) {
+  const int es = a.dtype == B200NORM_DT_F32 ? 4 : 2;
+  const int64_t row_bytes = a.N * es;
+  if (!a.norm || a.force_generic || row_bytes % 16 != 0 || row_bytes / 16 > kOuterRowsThreads || a.M < 2048) return false;
+  if (env_int_outer("B200NORM_NO_OUTER_ROWS") != 0) return false;
+  const int rpi = kOuterRowsThreads / (int)(row_bytes / 16);
+  int grid = a.sm_count;
+  const int64_t min_rows = (int64_t)rpi * 4;  // at least four iterations per CTA
+  if ((int64_t)grid * min_rows > a.M) grid = (int)((a.M + min_rows - 1) / min_rows);
+  if (grid < 1) grid = 1;
+  const int64_t rows_per_cta = (a.M + grid - 1) / grid;
+  grid = (int)((a.M + rows_per_cta - 1) / rows_per_cta);
+  *grid_out = grid;
+  *rows_per_iter = rpi;
+  return true;
+}
 
 int outer_launch(const OuterArgs& a, void* stream_v, char* err, size_t errlen) {
   const int kind = a.norm ? (a.bwd ? 5 : 4) : (a.bwd ? 2 : 0) + (a.log ? 1 : 0);
@@ -1220,7 +1313,19 @@ int outer_launch(const OuterArgs& a, void* stream_v, char* err, size_t errlen) {
   g_outer_last_launches = persistent ? 1 : 3;
   if (!persistent && a.force_persistent)
     return set_err(err, errlen, B200NORM_ERR_UNSUPPORTED, "requested kernel family cannot run this outer segment: %s", why);
-  if (!persistent) return outer_generic_launch(a, kind, stream_v, err, errlen);
+  if (!persistent) {
+    // few columns, many rows (ResNet-size batch norms): the single-kernel row-block family; anything it declines
+    // (and B200NORM_VARIANT_GENERIC) goes to the three-kernel family
+    if (!a.force_generic && a.norm) {
+      const int rc = outer_rows_launch(a, stream_v, err, errlen);
+      if (rc == B200NORM_OK) {
+        g_outer_last_launches = 1;
+        return rc;
+      }
+      if (rc != B200NORM_ERR_UNSUPPORTED) return rc;
+    }
+    return outer_generic_launch(a, kind, stream_v, err, errlen);
+  }
 
   OuterKernel k = outer_kernel_for(a.dtype, kind);
   if (k == nullptr) return set_err(err, errlen, B200NORM_ERR_UNSUPPORTED, "outer-persistent: dtype %d", a.dtype);

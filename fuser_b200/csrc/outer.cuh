@@ -79,4 +79,8 @@ int outer_launch(const OuterArgs& a, void* stream, char* err, size_t errlen);
 // Kernels the last outer_launch of this thread enqueued (1 persistent, 3 shape-agnostic).
 int outer_last_launches();
 
+// The row-block kernel (outer_rows.cuh) takes this segment when its operands are 16-byte aligned and its rows
+// contiguous: shape-only test + launch geometry (used by b200norm_query; the launch re-checks the pointers).
+bool outer_rows_shape(const OuterArgs& a, int* grid, int* rows_per_iter);
+
 }  // namespace b200norm

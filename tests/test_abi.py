@@ -191,6 +191,12 @@ def test_outer_normalization_descs():
     for bad in (f_bwd | L.F_PARTIALS_F32, f_bwd | L.F_PEER_REDUCE):
         with pytest.raises(L.UnsupportedSegment):
             L.query(L.make_desc(L.OP_LAYERNORM_BWD, L.DT_BF16, 512, 4096, 0.0, bad, L.VARIANT_AUTO, 0))
-    # ResNet-size N*H*W: beyond a 16-CTA cluster -> the shape-agnostic family, many row splits for few columns
+    # ResNet-size N*H*W: beyond a 16-CTA cluster -> the row-block kernel (one cooperative launch, a block of rows per
+    # CTA, 512 threads = 16 rows x 32 chunks); rows that are not a whole number of 16-byte chunks, or a forced generic
+    # variant -> the shape-agnostic three-kernel family, many row splits for few columns
     p = L.query(L.make_desc(L.OP_LAYERNORM_FWD, L.DT_BF16, 100352, 256, 1e-5, f_fwd, L.VARIANT_AUTO, 0)).as_dict()
-    assert p["variant"] == "generic" and p["n_launches"] == 3 and p["grid"] % 2 == 0 and p["grid"] >= 2 * 256
+    assert p["variant"] == "generic" and p["n_launches"] == 1 and p["block"] == 512 and p["threads_per_row"] == 32, p
+    assert p["workspace_bytes"] >= 256 + (p["grid"] * 3 + 2) * 256 * 4
+    for cols, variant in ((256, L.VARIANT_GENERIC), (250, L.VARIANT_AUTO)):
+        p = L.query(L.make_desc(L.OP_LAYERNORM_FWD, L.DT_BF16, 100352, cols, 1e-5, f_fwd, variant, 0)).as_dict()
+        assert p["variant"] == "generic" and p["n_launches"] == 3 and p["grid"] % 2 == 0 and p["grid"] >= 2 * 256

@@ -7,6 +7,8 @@ compared with (a) the ATen oracle under the validator's tolerances and (b) the f
 Shapes cover one CTA per slab, every cluster size (rows split along M with the DSMEM exchange),
 ragged row counts, slabs cut by the matrix edge, strided rows and the NaN / Inf semantics.
 """
+import os
+
 import pytest
 import torch
 
@@ -424,6 +426,87 @@ def test_outer_generic_semantics_and_resnet_shape():
     AO.assert_close(dx, dxe, m, "ResNet-size batch norm dx")
     AO.assert_close(dw, dwe, m, "dweight")
     AO.assert_close(db, dbe, m, "dbias")
+
+
+ROWS_SHAPES = [(100352, 256, torch.bfloat16), (50000, 64, torch.float16), (30001, 96, torch.float32), (20000, 1024, torch.bfloat16),
+               (60000, 128, torch.float32), (40000, 24, torch.bfloat16), (401408, 64, torch.bfloat16), (70000, 2048, torch.float32),
+               (66000, 4096, torch.bfloat16)]
+
+
+@pytest.mark.parametrize("shape", ROWS_SHAPES, ids=lambda s: f"{s[0]}x{s[1]}-{str(s[2]).split('.')[-1]}")
+def test_outer_rows_family(shape):
+    """Few columns, many rows — the batch norms of convolutional nets in channels-last view ([N*H*W, C]) that no cluster
+    holds on chip: the single-kernel row-block family (outer_rows.cuh), forward and backward against both oracles,
+    chunk counts that divide the CTA (256 columns), leave idle threads (24 -> 3 chunks), fill it (4096 bf16 / 2048 f32);
+    the output masks; the three-kernel family on the same inputs (B200NORM_NO_OUTER_ROWS) as a cross-check."""
+    m, n, dt = shape
+    x, dy, w, b = make_inputs(m, n, dt, seed=m + n)
+    x = (x.float() * 1.5 + 0.75).to(dt)  # a non-zero column mean
+    eps = 1e-5
+    plan = ops.plan_for(L.OP_LAYERNORM_FWD, dt, m, n, flags=L.F_OUTER | L.F_HAS_WEIGHT | L.F_HAS_BIAS)
+    assert plan["variant"] == "generic" and plan["n_launches"] == 1 and plan["block_x"] == 512, plan
+    xg, dyg, wg, bg = x.cuda(), dy.cuda(), w.cuda(), b.cuda()
+    ye, me, ie = AO.outer_norm_fwd(x, w, b, eps)
+    yc, mc, ic = c_outer_norm_fwd(x, w, b, eps)
+    n0 = L.launch_count()
+    y, mean, invstd = ops.outer_norm_fwd(xg, wg, bg, eps)
+    assert L.launch_count() - n0 == 1
+    fl = 1.0 if dt == torch.float32 else 1e-2
+    check(y, ye, yc, m, "rows outer norm y", fl)
+    check(mean, me, mc, m, "rows outer norm mean", 1.0)
+    check(invstd, ie, ic, m, "rows outer norm invstd", 1e-3)
+    y2, mean2, invstd2 = ops.outer_norm_fwd(xg, None, None, eps)
+    ye2, _, _ = AO.outer_norm_fwd(x, None, None, eps)
+    AO.assert_close(y2, ye2, m, "rows outer norm without affine")
+    assert torch.equal(mean2, mean) and torch.equal(invstd2, invstd)
+    # run-to-run determinism (fixed merge order over threads and CTAs)
+    y3, mean3, invstd3 = ops.outer_norm_fwd(xg, wg, bg, eps)
+    assert torch.equal(y3, y) and torch.equal(mean3, mean) and torch.equal(invstd3, invstd)
+
+    dx, dw, db = ops.outer_norm_bwd(dyg, xg, me.cuda(), ie.cuda(), wg)
+    dxe, dwe, dbe = AO.outer_norm_bwd(dy, x, me, ie, w)
+    dxc, dwc, dbc = AO.outer_norm_bwd(dy.double(), x.double(), me.double(), ie.double(), w.double())
+    check(dx, dxe, dxc, m, "rows outer norm dx", 1.0 if dt == torch.float32 else 1e-1)
+    check(dw, dwe, dwc, m, "rows outer norm dw", m ** 0.5)
+    check(db, dbe, dbc, m, "rows outer norm db", m ** 0.5)
+    dx2, dw2, db2 = ops.outer_norm_bwd(dyg, xg, me.cuda(), ie.cuda(), wg, (True, False, False))
+    assert dw2 is None and db2 is None and torch.equal(dx2, dx)
+    dx3, dw3, db3 = ops.outer_norm_bwd(dyg, xg, me.cuda(), ie.cuda(), wg, (False, True, True))
+    assert dx3 is None and torch.equal(dw3, dw) and torch.equal(db3, db)
+
+    os.environ["B200NORM_NO_OUTER_ROWS"] = "1"
+    try:
+        assert ops.plan_for(L.OP_LAYERNORM_FWD, dt, m, n, flags=L.F_OUTER | L.F_HAS_WEIGHT | L.F_HAS_BIAS)["n_launches"] == 3
+        yg, mg, ig = ops.outer_norm_fwd(xg, wg, bg, eps)
+        dxg, dwg, dbg = ops.outer_norm_bwd(dyg, xg, me.cuda(), ie.cuda(), wg)
+        torch.cuda.synchronize()
+    finally:
+        del os.environ["B200NORM_NO_OUTER_ROWS"]
+    AO.assert_close(y, yg.cpu(), m, "rows vs three-kernel family y")
+    AO.assert_close(dx, dxg.cpu(), m, "rows vs three-kernel family dx")
+    assert torch.allclose(mean, mg, atol=1e-5) and torch.allclose(invstd, ig, rtol=1e-4)
+
+
+def test_outer_rows_unaligned_falls_back():
+    """A view whose rows are not contiguous, or whose base is not 16-byte aligned, goes to the three-kernel family
+    (the row-block kernel declines at launch time); results agree with the oracle either way."""
+    dt = torch.bfloat16
+    m, n = 30000, 64
+    base = torch.randn(m, n + 8).to(dt)
+    w, b = torch.randn(n).to(dt), torch.randn(n).to(dt)
+    xg = base.cuda()[:, :n]          # row stride n + 8
+    n0 = L.launch_count()
+    y, mean, invstd = ops.outer_norm_fwd(xg, w.cuda(), b.cuda(), 1e-5)
+    assert L.launch_count() - n0 == 3
+    ye, me, ie = AO.outer_norm_fwd(base[:, :n].contiguous(), w, b, 1e-5)
+    AO.assert_close(y, ye, m, "strided rows: three-kernel family")
+    flat = torch.randn(m * n + 4).to(dt).cuda()
+    xo = flat[4:].view(m, n)         # base 8 bytes off a 16-byte boundary
+    n0 = L.launch_count()
+    y, mean, invstd = ops.outer_norm_fwd(xo, w.cuda(), b.cuda(), 1e-5)
+    assert L.launch_count() - n0 == 3
+    ye, me, ie = AO.outer_norm_fwd(xo.cpu(), w, b, 1e-5)
+    AO.assert_close(y, ye, m, "misaligned base: three-kernel family")
 
 
 @pytest.mark.parametrize("variant", [L.VARIANT_AUTO, L.VARIANT_GENERIC], ids=["auto", "generic"])
