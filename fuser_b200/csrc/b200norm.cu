@@ -1532,6 +1532,7 @@ int b200norm_launch(const b200norm_desc* desc, const b200norm_tensor* inputs, in
     OuterArgs a = outer_args_from(d);
     a.workspace = workspace;
     a.workspace_bytes = workspace_bytes;
+    a.timeline = g_timeline.load();
     a.in0 = rp.in0;
     a.in1 = rp.in1;
     a.out = rp.out0;

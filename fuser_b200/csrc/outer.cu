@@ -1205,10 +1205,12 @@ int outer_generic_launch(const OuterArgs& a, int kind, void* stream_v, char* err
 template <typename T>
 cudaError_t launch_outer_rows_typed(const OuterRowsParams& p, bool bwd, int grid, size_t smem, cudaStream_t stream) {
   const void* k = bwd ? (const void*)outer_rows_kernel<T, true> : (const void*)outer_rows_kernel<T, false>;
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(kOuterRowsThreads);
+  cfg.blockDim = dim3(kOuterRowsBlock);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr;
@@ -1256,8 +1258,17 @@ int outer_rows_launch(const OuterArgs& a, void* stream_v, char* err, size_t errl
   p.db_out = a.db_out;
   p.inv_m = (float)(1.0 / (double)a.M);
   p.eps = (float)a.eps;
+  p.timeline = a.timeline;
   const int vec = 16 / es;
-  const size_t smem = (size_t)p.active * vec * 3 * sizeof(float);
+  p.tile_bytes = (uint32_t)kOuterRowsU * (uint32_t)p.active * 16u;
+  p.ring_off = (uint32_t)kOuterRowsBarBytes + (((uint32_t)p.active * vec * 8u + 127u) & ~127u);
+  const uint32_t slot = (a.bwd ? 2u : 1u) * p.tile_bytes;
+  int depth = (int)(((uint32_t)a.smem_optin - p.ring_off) / slot);
+  if (depth > kOuterRowsMaxDepth) depth = kOuterRowsMaxDepth;
+  if (int dd = env_int_outer("B200NORM_OUTER_ROWS_DEPTH"); dd > 0 && dd < depth) depth = dd;
+  if (depth < 2) return B200NORM_ERR_UNSUPPORTED;
+  p.depth = depth;
+  const size_t smem = (size_t)p.ring_off + (size_t)depth * slot;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   cudaError_t e;
   switch (a.dtype) {
@@ -1313,6 +1324,15 @@ int outer_launch(const OuterArgs& a, void* stream_v, char* err, size_t errlen) {
   g_outer_last_launches = persistent ? 1 : 3;
   if (!persistent && a.force_persistent)
     return set_err(err, errlen, B200NORM_ERR_UNSUPPORTED, "requested kernel family cannot run this outer segment: %s", why);
+  if (persistent && !a.force_generic && a.norm && env_int_outer("B200NORM_OUTER_ROWS") != 0) {
+    // tuning: the row-block kernel wherever it can run, also where a cluster would hold the rows
+    const int rc = outer_rows_launch(a, stream_v, err, errlen);
+    if (rc == B200NORM_OK) {
+      g_outer_last_launches = 1;
+      return rc;
+    }
+    if (rc != B200NORM_ERR_UNSUPPORTED) return rc;
+  }
   if (!persistent) {
     // few columns, many rows (ResNet-size batch norms): the single-kernel row-block family; anything it declines
     // (and B200NORM_VARIANT_GENERIC) goes to the three-kernel family

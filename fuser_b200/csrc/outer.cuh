@@ -38,6 +38,7 @@ struct OuterArgs {
   double eps = 0.0;
   int round_sum = 0;       // backward: round the column sum through the io dtype (B200NORM_F_ROUND_ROWSUM)
   int cluster_forced = 0;  // 0 = planner's choice, else 1,2,4,8,16
+  unsigned long long* timeline = nullptr;  // tuning aid: per-CTA time marks of the row-block kernel
   int force_generic = 0;   // 1: the shape-agnostic family (outer_generic.cuh: stats / merge / apply) whatever the shape
   int force_persistent = 0;  // 1: a persistent family was requested: no fall-back
   void* workspace = nullptr;  // caller's workspace (generic family: fp32 partials behind the 256-byte header)

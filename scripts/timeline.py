@@ -20,7 +20,7 @@ from fuser_b200 import _lib as L  # noqa: E402
 from fuser_b200 import ops  # noqa: E402
 
 KEYS = ["B200NORM_TPR", "B200NORM_GROUPS", "B200NORM_DEPTH", "B200NORM_TILE_ROWS", "B200NORM_CLUSTER",
-        "B200NORM_BWD_REREAD", "B200NORM_NO_FUSED_FINISH", "B200NORM_NO_PDL", "B200NORM_NO_PSMEM", "B200NORM_COOP", "B200NORM_STATIC", "B200NORM_POOL", "B200NORM_NO_PIPE", "B200NORM_PIPE"]
+        "B200NORM_BWD_REREAD", "B200NORM_NO_FUSED_FINISH", "B200NORM_NO_PDL", "B200NORM_NO_PSMEM", "B200NORM_COOP", "B200NORM_STATIC", "B200NORM_POOL", "B200NORM_NO_PIPE", "B200NORM_PIPE", "B200NORM_OUTER_ROWS", "B200NORM_OUTER_ROWS_DEPTH"]
 DT = {"bf16": torch.bfloat16, "f32": torch.float32, "f16": torch.float16}
 NAMES = ["entry", "setup", "first", "loop", "partial", "gbar", "exit", None, "finish", "collect"]
 SLOTS = 12
@@ -58,6 +58,11 @@ def main():
         elif op == "sm_bwd":
             ys = [ops.softmax_fwd(x) for x in xs]
             fn = lambda i: ops.softmax_bwd(dys[i], ys[i])  # noqa: E731
+        elif op == "onorm_fwd":
+            fn = lambda i: ops.outer_norm_fwd(xs[i], w, w, 1e-5)  # noqa: E731
+        elif op == "onorm_bwd":
+            st = [ops.outer_norm_fwd(x, w, w, 1e-5)[1:] for x in xs]
+            fn = lambda i: ops.outer_norm_bwd(dys[i], xs[i], st[i][0], st[i][1], w)  # noqa: E731
         else:
             raise SystemExit(f"unknown op {op}")
         for i in range(3):

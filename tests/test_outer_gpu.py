@@ -428,8 +428,8 @@ def test_outer_generic_semantics_and_resnet_shape():
     AO.assert_close(db, dbe, m, "dbias")
 
 
-ROWS_SHAPES = [(100352, 256, torch.bfloat16), (50000, 64, torch.float16), (30001, 96, torch.float32), (20000, 1024, torch.bfloat16),
-               (60000, 128, torch.float32), (40000, 24, torch.bfloat16), (401408, 64, torch.bfloat16), (70000, 2048, torch.float32),
+ROWS_SHAPES = [(100352, 256, torch.bfloat16), (150000, 64, torch.float16), (120001, 96, torch.float32), (105000, 1024, torch.bfloat16),
+               (60000, 128, torch.float32), (130001, 24, torch.bfloat16), (401408, 64, torch.bfloat16), (70000, 2048, torch.float32),
                (66000, 4096, torch.bfloat16)]
 
 
@@ -444,7 +444,9 @@ def test_outer_rows_family(shape):
     x = (x.float() * 1.5 + 0.75).to(dt)  # a non-zero column mean
     eps = 1e-5
     plan = ops.plan_for(L.OP_LAYERNORM_FWD, dt, m, n, flags=L.F_OUTER | L.F_HAS_WEIGHT | L.F_HAS_BIAS)
-    assert plan["variant"] == "generic" and plan["n_launches"] == 1 and plan["block_x"] == 512, plan
+    assert plan["variant"] == "generic" and plan["n_launches"] == 1 and plan["block"] == 512, plan
+    bplan = ops.plan_for(L.OP_LAYERNORM_BWD, dt, m, n, flags=L.F_OUTER | L.F_HAS_WEIGHT | L.F_OUT_DX | L.F_OUT_DW | L.F_OUT_DB)
+    assert bplan["variant"] == "generic" and bplan["n_launches"] == 1, bplan
     xg, dyg, wg, bg = x.cuda(), dy.cuda(), w.cuda(), b.cuda()
     ye, me, ie = AO.outer_norm_fwd(x, w, b, eps)
     yc, mc, ic = c_outer_norm_fwd(x, w, b, eps)
@@ -474,6 +476,18 @@ def test_outer_rows_family(shape):
     dx3, dw3, db3 = ops.outer_norm_bwd(dyg, xg, me.cuda(), ie.cuda(), wg, (False, True, True))
     assert dx3 is None and torch.equal(dw3, dw) and torch.equal(db3, db)
 
+    # a two-slot ring (every tile but the last two goes through a refilled slot, phase 2 reloads almost everything):
+    # same arithmetic in the same order, bit-equal results
+    os.environ["B200NORM_OUTER_ROWS_DEPTH"] = "2"
+    try:
+        y4, mean4, invstd4 = ops.outer_norm_fwd(xg, wg, bg, eps)
+        dx4, dw4, db4 = ops.outer_norm_bwd(dyg, xg, me.cuda(), ie.cuda(), wg)
+        torch.cuda.synchronize()
+    finally:
+        del os.environ["B200NORM_OUTER_ROWS_DEPTH"]
+    assert torch.equal(y4, y) and torch.equal(mean4, mean) and torch.equal(invstd4, invstd)
+    assert torch.equal(dx4, dx) and torch.equal(dw4, dw) and torch.equal(db4, db)
+
     os.environ["B200NORM_NO_OUTER_ROWS"] = "1"
     try:
         assert ops.plan_for(L.OP_LAYERNORM_FWD, dt, m, n, flags=L.F_OUTER | L.F_HAS_WEIGHT | L.F_HAS_BIAS)["n_launches"] == 3
@@ -491,7 +505,7 @@ def test_outer_rows_unaligned_falls_back():
     """A view whose rows are not contiguous, or whose base is not 16-byte aligned, goes to the three-kernel family
     (the row-block kernel declines at launch time); results agree with the oracle either way."""
     dt = torch.bfloat16
-    m, n = 30000, 64
+    m, n = 150000, 64  # beyond the cluster-persistent family
     base = torch.randn(m, n + 8).to(dt)
     w, b = torch.randn(n).to(dt), torch.randn(n).to(dt)
     xg = base.cuda()[:, :n]          # row stride n + 8
