@@ -122,7 +122,7 @@ const DeviceInfo& device_info() { return device_ctx().info; }
 struct Knobs {
   int tpr = 0, groups = 0, depth = 0, tile_rows = 0, cluster = 0, bwd_reread = 0, pipe = 0, no_pipe = 0, no_psmem = 0;
   int no_fused_finish = 0, no_pdl = 0, coop = 0, static_sched = 0, pool = 0, debug = 0, peer_timeout_s = -1;
-  int ln_pipe = 0, no_ln_pipe = 0, no_guard = 0, no_lean = 0;
+  int ln_pipe = 0, no_ln_pipe = 0, no_guard = 0, no_lean = 0, sm_two_exch = 0;
   bool any = false;
   uint64_t hash = 0;  // of the planner-relevant values (plan cache key)
 };
@@ -135,7 +135,7 @@ Knobs read_knobs() {
       {"NO_PSMEM", &Knobs::no_psmem}, {"NO_FUSED_FINISH", &Knobs::no_fused_finish}, {"NO_PDL", &Knobs::no_pdl},
       {"COOP", &Knobs::coop}, {"STATIC", &Knobs::static_sched}, {"POOL", &Knobs::pool}, {"DEBUG", &Knobs::debug},
       {"PEER_TIMEOUT_S", &Knobs::peer_timeout_s}, {"LN_PIPE", &Knobs::ln_pipe}, {"NO_LN_PIPE", &Knobs::no_ln_pipe},
-      {"NO_GUARD", &Knobs::no_guard}, {"NO_LEAN", &Knobs::no_lean}};
+      {"NO_GUARD", &Knobs::no_guard}, {"NO_LEAN", &Knobs::no_lean}, {"SM_TWO_EXCH", &Knobs::sm_two_exch}};
   if (::environ == nullptr) return k;
   for (char** e = ::environ; *e != nullptr; ++e) {
     if (strncmp(*e, "B200NORM_", 9) != 0) continue;
@@ -787,6 +787,7 @@ int check_desc(const b200norm_desc* d) {
   if (d->op < 0 || d->op >= B200NORM_OP_COUNT_) return fail(B200NORM_ERR_UNSUPPORTED, "unknown op %d", d->op);
   if (d->io_dtype < 0 || d->io_dtype > B200NORM_DT_F16)
     return fail(B200NORM_ERR_UNSUPPORTED, "unsupported io dtype %d", d->io_dtype);
+  if (d->flags >> 23) return fail(B200NORM_ERR_BAD_ARG, "unknown flag bits 0x%x", d->flags & ~((1u << 23) - 1u));
   if (d->rows < 0 || d->cols < 0) return fail(B200NORM_ERR_BAD_ARG, "negative extent");
   if (d->cols > 0x7fffffffLL) return fail(B200NORM_ERR_UNSUPPORTED, "cols %lld exceeds int32", (long long)d->cols);
   if (d->cluster_size != 0 && d->cluster_size != 1 && d->cluster_size != 2 && d->cluster_size != 4 &&
@@ -1225,7 +1226,8 @@ int b200norm_query(const b200norm_desc* desc, b200norm_plan* plan) {
     }
     OuterPlan op;
     char msg[256] = "";
-    const bool persistent = !oa.force_generic && outer_make_plan(oa, &op, msg, sizeof(msg));
+    bool persistent = !oa.force_generic && outer_make_plan(oa, &op, msg, sizeof(msg));
+    if (persistent && !oa.force_persistent && outer_prefers_rows(oa)) persistent = false;
     if (!persistent && (desc->variant == B200NORM_VARIANT_TMA || desc->variant == B200NORM_VARIANT_CLUSTER))
       return fail(B200NORM_ERR_UNSUPPORTED, "requested kernel family cannot run this outer segment: %s", msg);
     if (plan != nullptr) {
@@ -1313,6 +1315,7 @@ int b200norm_launch(const b200norm_desc* desc, const b200norm_tensor* inputs, in
     rp.var_scale = (float)(1.0 / (denom > 0.0 ? denom : 0.0));
   }
   rp.flags = d.flags;
+  if (kn.sm_two_exch != 0) rp.flags |= kFlagTwoExchange;
   void* dw = nullptr;
   void* db = nullptr;
   float* sums_f32 = nullptr;
@@ -1550,6 +1553,8 @@ int b200norm_launch(const b200norm_desc* desc, const b200norm_tensor* inputs, in
       a.mean_out = rp.stat0;
       a.invstd_out = rp.stat1;
     }
+    if (int rg = 0, rpi = 0; kn.coop == 0 && kn.no_guard == 0 && outer_rows_shape(a, &rg, &rpi))
+      barrier_guard(ctx, static_cast<cudaStream_t>(stream_v));  // the row-block kernel spins on a grid barrier
     char msg[256] = "";
     rc = outer_launch(a, stream_v, msg, sizeof(msg));
     if (rc != B200NORM_OK) return fail(rc, "%s", msg);

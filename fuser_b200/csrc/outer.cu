@@ -1200,12 +1200,27 @@ int outer_generic_launch(const OuterArgs& a, int kind, void* stream_v, char* err
   return B200NORM_OK;
 }
 
-// Few columns, many rows (outer_rows.cuh): one persistent cooperative kernel. Returns B200NORM_ERR_UNSUPPORTED when
+// cudaFuncSetAttribute once per (device, kernel, size)
+cudaError_t outer_set_max_smem(const void* k, size_t smem) {
+  static std::mutex mu;
+  static std::unordered_map<uint64_t, size_t> done;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const uint64_t key = (uint64_t)reinterpret_cast<uintptr_t>(k) ^ ((uint64_t)dev << 56);
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = done.find(key);
+  if (it != done.end() && it->second >= smem) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) done[key] = smem;
+  return e;
+}
+
+// Few columns, many rows (outer_rows.cuh): one persistent kernel with two grid barriers. Returns B200NORM_ERR_UNSUPPORTED when
 // the shape / layout is not its own (the caller then takes the three-kernel family).
 template <typename T>
 cudaError_t launch_outer_rows_typed(const OuterRowsParams& p, bool bwd, int grid, size_t smem, cudaStream_t stream) {
   const void* k = bwd ? (const void*)outer_rows_kernel<T, true> : (const void*)outer_rows_kernel<T, false>;
-  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = outer_set_max_smem(k, smem);
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -1213,9 +1228,18 @@ cudaError_t launch_outer_rows_typed(const OuterRowsParams& p, bool bwd, int grid
   cfg.blockDim = dim3(kOuterRowsBlock);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
+  // Two in-kernel grid barriers need every CTA resident: the grid is at most one CTA per SM and the kernels of this
+  // library that spin on a grid barrier are serialised across streams by the caller (barrier_guard in b200norm.cu),
+  // as for the fused backward kernels; B200NORM_COOP=1 asks the driver for the formal guarantee instead (other
+  // processes under MPS) and gives up the overlap of the prologue with the predecessor's tail.
   cudaLaunchAttribute attr;
-  attr.id = cudaLaunchAttributeCooperative;  // two in-kernel grid barriers: the driver guarantees co-residency
-  attr.val.cooperative = 1;
+  if (env_int_outer("B200NORM_COOP") != 0) {
+    attr.id = cudaLaunchAttributeCooperative;
+    attr.val.cooperative = 1;
+  } else {
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = env_int_outer("B200NORM_NO_PDL") == 0 ? 1 : 0;
+  }
   cfg.attrs = &attr;
   cfg.numAttrs = 1;
   void* args[] = {const_cast<OuterRowsParams*>(&p)};
@@ -1286,6 +1310,19 @@ int outer_rows_launch(const OuterArgs& a, void* stream_v, char* err, size_t errl
 
 }  // namespace
 
+// Where both families can run: the row-block kernel for rows of at most 2 KB and at least 32 MB of input. Measured
+// (profiles/r02h_outer_rows.txt, forward | backward, cluster-persistent vs row-block): bf16 [25088,1024] 37.2 vs 35.4 |
+// 55.9 vs 48.0 us, [50176,512] 41.7 vs 33.3 | 46.1 vs 46.6; wider rows go the other way ([12544,2048] 35.7 vs 39.9,
+// [8192,4096] 38.5 vs 55.7: the cross-CTA merge of thousands of columns), and so do small matrices ([25088,256] 16.4
+// vs 18.7, [50000,64] 13.0 vs 16.5: two grid barriers against none).
+bool outer_prefers_rows(const OuterArgs& a) {
+  int grid = 0, rpi = 0;
+  if (!outer_rows_shape(a, &grid, &rpi)) return false;
+  if (env_int_outer("B200NORM_OUTER_ROWS") != 0) return true;
+  const int es = a.dtype == B200NORM_DT_F32 ? 4 : 2;
+  return a.N * es <= 2048 && a.M * a.N * es >= (32ll << 20);
+}
+
 bool outer_rows_shape(const OuterArgs& a, int* grid_out, int* rows_per_iter) {
   const int es = a.dtype == B200NORM_DT_F32 ? 4 : 2;
   const int64_t row_bytes = a.N * es;
@@ -1324,8 +1361,9 @@ int outer_launch(const OuterArgs& a, void* stream_v, char* err, size_t errlen) {
   g_outer_last_launches = persistent ? 1 : 3;
   if (!persistent && a.force_persistent)
     return set_err(err, errlen, B200NORM_ERR_UNSUPPORTED, "requested kernel family cannot run this outer segment: %s", why);
-  if (persistent && !a.force_generic && a.norm && env_int_outer("B200NORM_OUTER_ROWS") != 0) {
-    // tuning: the row-block kernel wherever it can run, also where a cluster would hold the rows
+  if (persistent && !a.force_persistent && outer_prefers_rows(a)) {
+    // narrow rows and a matrix of tens of MB: the row-block kernel beats the cluster-persistent family (measured,
+    // see outer_prefers_rows); B200NORM_OUTER_ROWS=1 takes it wherever it can run
     const int rc = outer_rows_launch(a, stream_v, err, errlen);
     if (rc == B200NORM_OK) {
       g_outer_last_launches = 1;

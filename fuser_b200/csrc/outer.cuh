@@ -83,5 +83,7 @@ int outer_last_launches();
 // The row-block kernel (outer_rows.cuh) takes this segment when its operands are 16-byte aligned and its rows
 // contiguous: shape-only test + launch geometry (used by b200norm_query; the launch re-checks the pointers).
 bool outer_rows_shape(const OuterArgs& a, int* grid, int* rows_per_iter);
+// ... and is preferred to the cluster-persistent family where that one can run too (narrow rows, tens of MB).
+bool outer_prefers_rows(const OuterArgs& a);
 
 }  // namespace b200norm

@@ -146,6 +146,7 @@ __global__ void __launch_bounds__(kOuterRowsBlock, 1) outer_rows_kernel(const Ou
     fence_mbar_init();
   }
   __syncthreads();
+  pdl_wait();  // programmatic dependent launch: the predecessor's results (and its use of the workspace) are complete
   orows_mark(p, 1);
 
   // producer side (lane 0 of the last warp): tile t -> slot t % depth
@@ -267,28 +268,50 @@ __global__ void __launch_bounds__(kOuterRowsBlock, 1) outer_rows_kernel(const Ou
     }
   }
   __syncthreads();
-  // one thread per COLUMN merges the rpi row subsets in order and writes the CTA's partial; row subset s of a block
-  // of nrows rows holds nrows / rpi rows, one more for s < nrows % rpi
+  // g threads per COLUMN (a power of two inside one warp) merge the rpi row subsets — each every g-th subset in
+  // order, then a shuffle tree: the order depends on N and rpi only — and write the CTA's partial. Row subset s of a
+  // block of nrows rows holds nrows / rpi rows, one more for s < nrows % rpi.
   {
     float* my_part = p.part + (size_t)blockIdx.x * 3 * p.N;
     const float cnt_lo = (float)(nrows / p.rpi);
     const int extra = (int)(nrows % p.rpi);
-    for (int c = tid; c < p.N; c += kOuterRowsBlock) {
-      const float2* src = reinterpret_cast<const float2*>(sm) + c;  // element e of chunk cc: (cc * VEC + e) = c
-      const size_t stride = (size_t)p.nchunks * VEC;
-      float n = 0.f, m = 0.f, q = 0.f;
-      for (int s = 0; s < p.rpi; ++s) {
-        const float2 t = src[s * stride];
-        if constexpr (!BWD) {
-          chan_merge3(n, m, q, cnt_lo + (s < extra ? 1.f : 0.f), t.x, t.y);
-        } else {
-          n += t.x;
-          m += t.y;
+    int g = 1;
+    while (g < 32 && 2 * g * p.N <= kOuterRowsThreads && 2 * g <= p.rpi) g *= 2;
+    const int cols_per_pass = kOuterRowsThreads / g;
+    const int j = tid % g;
+    const size_t stride = (size_t)p.nchunks * VEC;
+    if (tid < kOuterRowsThreads) {
+      for (int base = 0; base < p.N; base += cols_per_pass) {
+        const int c = base + tid / g;
+        float n = 0.f, m = 0.f, q = 0.f;
+        if (c < p.N) {
+          const float2* src = reinterpret_cast<const float2*>(sm) + c;  // element e of chunk cc: cc * VEC + e = c
+          for (int s = j; s < p.rpi; s += g) {
+            const float2 t = src[s * stride];
+            if constexpr (!BWD) {
+              chan_merge3(n, m, q, cnt_lo + (s < extra ? 1.f : 0.f), t.x, t.y);
+            } else {
+              n += t.x;
+              m += t.y;
+            }
+          }
+        }
+        for (int off = g >> 1; off > 0; off >>= 1) {
+          const float tn = __shfl_down_sync(0xffffffffu, n, off), tm = __shfl_down_sync(0xffffffffu, m, off);
+          if constexpr (!BWD) {
+            const float tq = __shfl_down_sync(0xffffffffu, q, off);
+            chan_merge3(n, m, q, tn, tm, tq);
+          } else {
+            n += tn;
+            m += tm;
+          }
+        }
+        if (j == 0 && c < p.N) {
+          my_part[c] = n;
+          my_part[p.N + c] = m;
+          if constexpr (!BWD) my_part[2 * (size_t)p.N + c] = q;
         }
       }
-      my_part[c] = n;
-      my_part[p.N + c] = m;
-      if constexpr (!BWD) my_part[2 * (size_t)p.N + c] = q;
     }
   }
   orows_mark(p, 4);
@@ -304,16 +327,26 @@ __global__ void __launch_bounds__(kOuterRowsBlock, 1) outer_rows_kernel(const Ou
     const int warp = tid >> 5;
     for (int c = c_begin + warp; c < c_end; c += kOuterRowsBlock / 32) {
       float n = 0.f, m = 0.f, q = 0.f;
-#pragma unroll 5
-      for (unsigned b = lane; b < gridDim.x; b += 32) {
-        const float* t = p.part + (size_t)b * 3 * p.N;
-        const float tn = __ldcg(t + c), tm = __ldcg(t + p.N + c);
-        if constexpr (!BWD) {
-          const float tq = __ldcg(t + 2 * (size_t)p.N + c);
-          chan_merge3(n, m, q, tn, tm, tq);
-        } else {
-          n += tn;
-          m += tm;
+      for (unsigned b0 = 0; b0 < gridDim.x; b0 += 160) {
+        // all the loads first (one L2 round trip), then the merges
+        float tn[5], tm[5], tq[5];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+          const unsigned bb = b0 + (unsigned)lane + 32u * (unsigned)i;
+          const bool ok = bb < gridDim.x;
+          const float* t = p.part + (size_t)(ok ? bb : 0u) * 3 * p.N + c;
+          tn[i] = ok ? __ldcg(t) : 0.f;
+          tm[i] = ok ? __ldcg(t + p.N) : 0.f;
+          tq[i] = (ok && !BWD) ? __ldcg(t + 2 * (size_t)p.N) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+          if constexpr (!BWD) {
+            chan_merge3(n, m, q, tn[i], tm[i], tq[i]);
+          } else {
+            n += tn[i];
+            m += tm[i];
+          }
         }
       }
 #pragma unroll
@@ -347,6 +380,7 @@ __global__ void __launch_bounds__(kOuterRowsBlock, 1) outer_rows_kernel(const Ou
   if (p.out == nullptr) return;  // backward without dx: nothing left (every CTA takes this branch together)
   outer_rows_grid_barrier(p.sync_word);
   orows_mark(p, 9);
+  pdl_launch_dependents();  // the successor's CTAs may take the SMs as ours exit
 
   // ------------------------------------------------------------------ phase 2: apply, last tile first
   if (producer) {

@@ -61,6 +61,8 @@ constexpr uint32_t kFlagRoundSum = 1u << 15;
 constexpr uint32_t kFlagNoY = 1u << 20;
 constexpr uint32_t kFlagStatVar = 1u << 21;
 constexpr uint32_t kFlagStatM2 = 1u << 22;
+// internal (never set through the ABI: check_desc refuses unknown bits), tuning knobs of the launch
+constexpr uint32_t kFlagTwoExchange = 1u << 31;  // cluster softmax forward: maximum and sum in two exchanges (B200NORM_SM_TWO_EXCH)
 
 struct RowParams {
   // streamed operands (row-major, unit inner stride)
@@ -290,6 +292,64 @@ struct Group {
       for (uint32_t r = 1; r < csize; ++r) {
         chan_merge(n, mean, m2, slots[r * kRedNV + 0], slots[r * kRedNV + 1], slots[r * kRedNV + 2]);
       }
+      cl_phase += 1u;
+    }
+  }
+
+  // Online-softmax pairs (m = maximum, s = sum of exp(x - m) over a partial set) -> the pair of the whole row:
+  //     m = max(ma, mb),   s = sa * exp(ma - m) + sb * exp(mb - m)
+  // in ONE exchange (the two-reduction form — maximum, then sum — costs a row split over a cluster two DSMEM round
+  // trips; the pair costs one). The maximum is exact, so every level takes the maximum first and rescales each
+  // partial sum once; equal maxima (also -inf with -inf: an all -inf partial set has s = 0) scale by exactly 1, NaN
+  // propagates through MaxOp. Fixed order: every thread ends with the same bits. A barrier for the group.
+  template <typename T>
+  __device__ __forceinline__ static float softmax_rescale(float m_part, float m_all) {
+    return m_part == m_all ? 1.f : exp_for<T>(m_part - m_all);
+  }
+  template <typename T>
+  __device__ __forceinline__ void softmax_allreduce(float& m, float& s) {
+    float wm = m;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) wm = MaxOp::apply(wm, __shfl_xor_sync(0xffffffffu, wm, off));
+    s *= softmax_rescale<T>(m, wm);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    m = wm;
+    if constexpr (TPR > 32) {
+      float* slots = reinterpret_cast<float*>(smem_raw + red_off);
+      if (lane == 0) {
+        slots[warp] = m;
+        slots[kMaxWarpsPerGroup + warp] = s;
+      }
+      named_bar_sync(1 + gid, TPR);
+      float gm = slots[0];
+#pragma unroll
+      for (int w = 1; w < WPG; ++w) gm = MaxOp::apply(gm, slots[w]);
+      float gs = 0.f;
+#pragma unroll
+      for (int w = 0; w < WPG; ++w) gs = fmaf(slots[kMaxWarpsPerGroup + w], softmax_rescale<T>(slots[w], gm), gs);
+      m = gm;
+      s = gs;
+      red_off ^= (uint32_t)kRedSetBytes;
+    }
+    if (csize > 1) {
+      const uint32_t par = cl_phase & 1u;
+      const uint32_t set = par * kClsSetBytes;
+      if (gtid == 0) mbar_arrive_expect_tx(clbar, csize * 2 * 4);
+      if ((uint32_t)gtid < csize) {
+        const uint32_t r = (uint32_t)gtid;
+        const uint32_t rbar = map_to_cta(clbar, r);
+        st_async_f32(map_to_cta(cls_addr + set + (crank * kRedNV + 0) * 4, r), m, rbar);
+        st_async_f32(map_to_cta(cls_addr + set + (crank * kRedNV + 1) * 4, r), s, rbar);
+      }
+      mbar_wait(clbar, par);
+      const volatile float* slots = reinterpret_cast<const volatile float*>(smem_raw + cls_off + set);
+      float cm = slots[0];
+      for (uint32_t r = 1; r < csize; ++r) cm = MaxOp::apply(cm, slots[r * kRedNV]);
+      float cs = 0.f;
+      for (uint32_t r = 0; r < csize; ++r) cs = fmaf(slots[r * kRedNV + 1], softmax_rescale<T>(slots[r * kRedNV], cm), cs);
+      m = cm;
+      s = cs;
       cl_phase += 1u;
     }
   }
