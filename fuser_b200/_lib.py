@@ -71,6 +71,7 @@ F_RMS_BWD_HALF_PROJ = 1 << 19
 F_NO_Y = 1 << 20
 F_STAT_VAR = 1 << 21
 F_STAT_M2 = 1 << 22
+F_DROPOUT = 1 << 23
 
 VARIANT_AUTO, VARIANT_GENERIC, VARIANT_TMA, VARIANT_CLUSTER = 0, 1, 2, 3
 FORM_CACHED, FORM_PIPE, FORM_PSMEM, FORM_FUSED_FINISH = 1, 2, 4, 8
@@ -230,7 +231,8 @@ def _raise(code: int):
     raise B200NormError(code, msg)
 
 
-def make_desc(op, io_dtype, rows, cols, eps=0.0, flags=0, variant=VARIANT_AUTO, cluster_size=0, correction=0) -> Desc:
+def make_desc(op, io_dtype, rows, cols, eps=0.0, flags=0, variant=VARIANT_AUTO, cluster_size=0, correction=0,
+              dropout_keep=1.0) -> Desc:
     d = Desc()
     d.abi_version = ABI_VERSION
     d.op = op
@@ -242,6 +244,11 @@ def make_desc(op, io_dtype, rows, cols, eps=0.0, flags=0, variant=VARIANT_AUTO, 
     d.flags = flags
     d.cluster_size = cluster_size
     d.reserved[0] = correction
+    if flags & F_DROPOUT:  # keep probability 1 - p: the double's low and high words
+        import struct
+
+        lo, hi = struct.unpack("<ii", struct.pack("<d", float(dropout_keep)))
+        d.reserved[1], d.reserved[2] = lo, hi
     return d
 
 

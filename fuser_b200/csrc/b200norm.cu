@@ -122,7 +122,7 @@ const DeviceInfo& device_info() { return device_ctx().info; }
 struct Knobs {
   int tpr = 0, groups = 0, depth = 0, tile_rows = 0, cluster = 0, bwd_reread = 0, pipe = 0, no_pipe = 0, no_psmem = 0;
   int no_fused_finish = 0, no_pdl = 0, coop = 0, static_sched = 0, pool = 0, debug = 0, peer_timeout_s = -1;
-  int ln_pipe = 0, no_ln_pipe = 0, no_guard = 0, no_lean = 0, sm_two_exch = 0;
+  int ln_pipe = 0, no_ln_pipe = 0, no_guard = 0, no_lean = 0, sm_one_exch = 0;
   bool any = false;
   uint64_t hash = 0;  // of the planner-relevant values (plan cache key)
 };
@@ -135,7 +135,7 @@ Knobs read_knobs() {
       {"NO_PSMEM", &Knobs::no_psmem}, {"NO_FUSED_FINISH", &Knobs::no_fused_finish}, {"NO_PDL", &Knobs::no_pdl},
       {"COOP", &Knobs::coop}, {"STATIC", &Knobs::static_sched}, {"POOL", &Knobs::pool}, {"DEBUG", &Knobs::debug},
       {"PEER_TIMEOUT_S", &Knobs::peer_timeout_s}, {"LN_PIPE", &Knobs::ln_pipe}, {"NO_LN_PIPE", &Knobs::no_ln_pipe},
-      {"NO_GUARD", &Knobs::no_guard}, {"NO_LEAN", &Knobs::no_lean}, {"SM_TWO_EXCH", &Knobs::sm_two_exch}};
+      {"NO_GUARD", &Knobs::no_guard}, {"NO_LEAN", &Knobs::no_lean}, {"SM_ONE_EXCH", &Knobs::sm_one_exch}};
   if (::environ == nullptr) return k;
   for (char** e = ::environ; *e != nullptr; ++e) {
     if (strncmp(*e, "B200NORM_", 9) != 0) continue;
@@ -201,7 +201,8 @@ uint64_t algorithmic_bytes(const b200norm_desc& d) {
       // + the residual read and the sum write of the fused-add variants (every tensor the fusion
       // reads or writes, as benchmarks/python/core.py:compute_total_iobytes counts them)
       const uint64_t extra = ((d.flags & B200NORM_F_ADD_RESIDUAL) ? s * M * N : 0) +
-                             ((d.flags & B200NORM_F_ADD_RESIDUAL) && (d.flags & B200NORM_F_OUT_SUM) ? s * M * N : 0);
+                             ((d.flags & B200NORM_F_ADD_RESIDUAL) && (d.flags & B200NORM_F_OUT_SUM) ? s * M * N : 0) +
+                             ((d.flags & B200NORM_F_DROPOUT) ? M * N : 0);  // + the bool mask (dropout_*_fwd_iobytes)
       if (d.op == B200NORM_OP_LAYERNORM_FWD && (d.flags & B200NORM_F_NO_Y)) {
         // var_mean / welford: the input once, one fp32 value per requested statistic and row
         const uint64_t nstat = ((d.flags & B200NORM_F_OUT_MEAN) ? 1 : 0) + ((d.flags & B200NORM_F_OUT_INVSTD) ? 1 : 0);
@@ -213,8 +214,10 @@ uint64_t algorithmic_bytes(const b200norm_desc& d) {
     }
     case B200NORM_OP_LAYERNORM_BWD:
       if (d.flags & B200NORM_F_OUTER) return s * 3 * (M * N + N) + 4 * 2 * N;
-      return s * 3 * (M * N + N) + 4 * 2 * M;
-    case B200NORM_OP_RMSNORM_BWD: return s * (3 * M * N + 2 * N) + 4 * M;
+      // dropout: + residual in, d residual out, the mask (dropout_layernorm_bwd_iobytes)
+      return s * 3 * (M * N + N) + 4 * 2 * M + ((d.flags & B200NORM_F_DROPOUT) ? s * 2 * M * N + M * N : 0);
+    case B200NORM_OP_RMSNORM_BWD:
+      return s * (3 * M * N + 2 * N) + 4 * M + ((d.flags & B200NORM_F_DROPOUT) ? s * 2 * M * N + M * N : 0);
     case B200NORM_OP_SOFTMAX_FWD:
     case B200NORM_OP_LOGSOFTMAX_FWD: return s * 2 * M * N;
     case B200NORM_OP_SOFTMAX_BWD:
@@ -641,7 +644,9 @@ int make_plan_uncached(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, 
   }
 
   bool ring_ok = false;
-  if (is_row_op(d.op) && aligned && d.variant != B200NORM_VARIANT_GENERIC && d.rows > 0 && d.cols > 0) {
+  const bool ring_has_dropout = false;  // the ring kernels do not draw / apply a dropout mask yet
+  if (is_row_op(d.op) && aligned && d.variant != B200NORM_VARIANT_GENERIC && d.rows > 0 && d.cols > 0 &&
+      (!(d.flags & B200NORM_F_DROPOUT) || ring_has_dropout)) {
     const int forced_c = d.cluster_size != 0 ? d.cluster_size : kn.cluster;
     static const int cs[] = {1, 2, 4, 8, 16};
     Plan best;
@@ -780,6 +785,38 @@ OuterArgs outer_args_from(const b200norm_desc& d) {
   return a;
 }
 
+double dropout_keep_prob(const b200norm_desc& d) {
+  const uint64_t bits = (uint64_t)(uint32_t)d.reserved[1] | ((uint64_t)(uint32_t)d.reserved[2] << 32);
+  double keep;
+  memcpy(&keep, &bits, sizeof(keep));
+  return keep;
+}
+
+// uniformf of the reference (runtime/random_numbers.cu:66-88) before the 1.0 -> 0 wrap: fl(fl(w) * 2^-32 + 2^-33)
+float dropout_raw_uniform(uint32_t w) {
+  const float scale = 2.3283064365386963e-10f;  // 2^-32
+  return (float)w * scale + 0.5f * scale;
+}
+
+// keep <=> uniformf(w) < keep (float against the fusion's double)  <=>  w <= t1 || w >= t2: the raw value is
+// monotone in w, and from t2 on it rounds to 1.0, which uniformf maps to 0 (< keep for every keep > 0).
+void dropout_thresholds(double keep, uint32_t* t1, uint32_t* t2) {
+  uint64_t a = 0, b = 1ull << 32;  // first w whose raw value is 1.0f
+  while (a < b) {
+    const uint64_t mid = (a + b) / 2;
+    if (dropout_raw_uniform((uint32_t)mid) >= 1.0f) b = mid; else a = mid + 1;
+  }
+  const uint64_t wrap = a;
+  *t2 = (uint32_t)(wrap < (1ull << 32) ? wrap : 0xffffffffull);
+  a = 0;  // first w below the wrap with raw >= keep (w = 0 gives 2^-33 < keep for every accepted keep)
+  b = wrap;
+  while (a < b) {
+    const uint64_t mid = (a + b) / 2;
+    if ((double)dropout_raw_uniform((uint32_t)mid) < keep) a = mid + 1; else b = mid;
+  }
+  *t1 = (uint32_t)(a > 0 ? a - 1 : 0);
+}
+
 int check_desc(const b200norm_desc* d) {
   if (d == nullptr) return fail(B200NORM_ERR_BAD_ARG, "null desc");
   if (d->abi_version != B200NORM_ABI_VERSION)
@@ -787,7 +824,19 @@ int check_desc(const b200norm_desc* d) {
   if (d->op < 0 || d->op >= B200NORM_OP_COUNT_) return fail(B200NORM_ERR_UNSUPPORTED, "unknown op %d", d->op);
   if (d->io_dtype < 0 || d->io_dtype > B200NORM_DT_F16)
     return fail(B200NORM_ERR_UNSUPPORTED, "unsupported io dtype %d", d->io_dtype);
-  if (d->flags >> 23) return fail(B200NORM_ERR_BAD_ARG, "unknown flag bits 0x%x", d->flags & ~((1u << 23) - 1u));
+  if (d->flags >> 24) return fail(B200NORM_ERR_BAD_ARG, "unknown flag bits 0x%x", d->flags & ~((1u << 24) - 1u));
+  if (d->flags & B200NORM_F_DROPOUT) {
+    const bool fwd = d->op == B200NORM_OP_LAYERNORM_FWD || d->op == B200NORM_OP_RMSNORM_FWD;
+    const bool bwd = d->op == B200NORM_OP_LAYERNORM_BWD || d->op == B200NORM_OP_RMSNORM_BWD;
+    if (!fwd && !bwd) return fail(B200NORM_ERR_UNSUPPORTED, "B200NORM_F_DROPOUT applies to the LayerNorm / RMSNorm ops");
+    if (fwd && !(d->flags & B200NORM_F_ADD_RESIDUAL))
+      return fail(B200NORM_ERR_UNSUPPORTED, "dropout forward is norm(residual + dropout(x)): ADD_RESIDUAL is required");
+    if (d->flags & (B200NORM_F_OUTER | B200NORM_F_NO_Y | B200NORM_F_ROUND_SUM | B200NORM_F_PARTIALS_F32 |
+                    B200NORM_F_PEER_REDUCE | B200NORM_F_PEER_PUBLISH))
+      return fail(B200NORM_ERR_UNSUPPORTED, "B200NORM_F_DROPOUT excludes OUTER, NO_Y, ROUND_SUM, PARTIALS_F32 and the peer flags");
+    const double keep = dropout_keep_prob(*d);
+    if (!(keep > 1e-6) || keep > 1.0) return fail(B200NORM_ERR_BAD_ARG, "dropout keep probability %g outside (0, 1]", keep);
+  }
   if (d->rows < 0 || d->cols < 0) return fail(B200NORM_ERR_BAD_ARG, "negative extent");
   if (d->cols > 0x7fffffffLL) return fail(B200NORM_ERR_UNSUPPORTED, "cols %lld exceeds int32", (long long)d->cols);
   if (d->cluster_size != 0 && d->cluster_size != 1 && d->cluster_size != 2 && d->cluster_size != 4 &&
@@ -1315,7 +1364,13 @@ int b200norm_launch(const b200norm_desc* desc, const b200norm_tensor* inputs, in
     rp.var_scale = (float)(1.0 / (denom > 0.0 ? denom : 0.0));
   }
   rp.flags = d.flags;
-  if (kn.sm_two_exch != 0) rp.flags |= kFlagTwoExchange;
+  if (kn.sm_one_exch != 0) rp.flags |= kFlagOneExchange;
+  const bool dropout = (d.flags & B200NORM_F_DROPOUT) != 0;
+  if (dropout) {
+    const double keep = dropout_keep_prob(d);
+    dropout_thresholds(keep, &rp.drop_t1, &rp.drop_t2);
+    rp.drop_scale = (float)(1.0 / keep);
+  }
   void* dw = nullptr;
   void* db = nullptr;
   float* sums_f32 = nullptr;
@@ -1347,6 +1402,21 @@ int b200norm_launch(const b200norm_desc* desc, const b200norm_tensor* inputs, in
   auto bind_vec = [&](const b200norm_tensor& t, int64_t n, int dtype, const char* name, void** ptr) -> int {
     int r = check_vector(t, n, dtype, name);
     if (r != B200NORM_OK) return r;
+    *ptr = t.data;
+    return B200NORM_OK;
+  };
+
+  // dropout mask: [M,N] bytes with contiguous rows (the dtype field is not interpreted)
+  auto bind_mask = [&](const b200norm_tensor& t, const char* name, void** ptr) -> int {
+    if (t.data == nullptr) return fail(B200NORM_ERR_BAD_ARG, "%s: null data", name);
+    int64_t numel = 1;
+    for (int i = 0; i < t.ndim; ++i) numel *= t.sizes[i];
+    if (numel != d.rows * d.cols) return fail(B200NORM_ERR_BAD_ARG, "%s: %lld elements, expected %lld", name, (long long)numel, (long long)(d.rows * d.cols));
+    int64_t expect = 1;
+    for (int i = t.ndim - 1; i >= 0; --i) {
+      if (t.sizes[i] != 1 && t.strides[i] != expect) return fail(B200NORM_ERR_UNSUPPORTED, "%s must be contiguous", name);
+      expect *= t.sizes[i];
+    }
     *ptr = t.data;
     return B200NORM_OK;
   };
@@ -1402,6 +1472,15 @@ int b200norm_launch(const b200norm_desc* desc, const b200norm_tensor* inputs, in
         CHECK(bind_vec(outputs[oi++], d.rows, B200NORM_DT_F32, "stat", &m));
         rp.stat1 = static_cast<float*>(m);
       }
+      if (dropout) {
+        NEED_IN(1);
+        NEED_OUT(1);
+        const b200norm_tensor& rng = inputs[ii++];
+        if (rng.data == nullptr || (reinterpret_cast<uintptr_t>(rng.data) & 7u) != 0)
+          return fail(B200NORM_ERR_BAD_ARG, "rng: a device tensor of two int64 {seed, offset} is required");
+        rp.rng = static_cast<const unsigned long long*>(rng.data);
+        CHECK(bind_mask(outputs[oi++], "mask", reinterpret_cast<void**>(&rp.mask_out)));
+      }
       break;
     }
     case B200NORM_OP_LAYERNORM_BWD:
@@ -1427,9 +1506,20 @@ int b200norm_launch(const b200norm_desc* desc, const b200norm_tensor* inputs, in
         rp.weight = w;
         if (!is_aligned16(w)) aligned = false;
       }
+      if (dropout) {
+        NEED_IN(2);
+        CHECK(bind_in_matrix(&rp.in2, &rp.in2_stride, "residual"));
+        void* m = nullptr;
+        CHECK(bind_mask(inputs[ii++], "mask", &m));
+        rp.mask_in = static_cast<const uint8_t*>(m);
+      }
       if (d.flags & B200NORM_F_OUT_DX) {
         NEED_OUT(1);
         CHECK(bind_out_matrix(&rp.out0, &rp.out_stride, "dx"));
+        if (dropout) {
+          NEED_OUT(1);
+          CHECK(bind_out_matrix(&rp.out1, &rp.out1_stride, "dresidual"));
+        }
       }
       const bool want_dw = (d.flags & B200NORM_F_OUT_DW) != 0;
       const bool want_db = ln && (d.flags & B200NORM_F_OUT_DB) != 0;

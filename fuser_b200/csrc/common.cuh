@@ -459,6 +459,45 @@ __device__ __forceinline__ float exp_for(float x) {
   }
 }
 
+// ----------------------------------------------------------------------------
+// Philox4x32-10 and the uniform -> keep decision of a fused dropout, bit-compatible with the reference's runtime
+// (runtime/random_numbers.cu:8-58 philox; :66-88 raw_uniform_float / uniformf; the lowering
+// device_lower/pass/rng.cpp:95-127 gives element i of a Float uniform() word (i mod 4) of philox(seed, i / 4, offset)).
+//   key = seed, counter = (offset lo, offset hi, subsequence lo, subsequence hi); ten rounds of
+//   (hi(B*c2) ^ c1 ^ k0, lo(B*c2), hi(A*c0) ^ c3 ^ k1, lo(A*c0)), the key bumped by the Weyl constants between rounds.
+// uniformf(w) = fl(fl(w) * 2^-32 + 2^-33), with 1.0 mapped to 0 — monotone in w up to that wrap, so the test
+// uniformf(w) < keep (a float against the fusion's double scalar) is two integer compares against thresholds the
+// host derives once (dropout_thresholds in b200norm.cu): keep  <=>  w <= t1 || w >= t2.
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(unsigned long long seed, unsigned long long subsequence,
+                                               unsigned long long offset) {
+  constexpr uint32_t kA = 0xD2511F53u, kB = 0xCD9E8D57u, kW0 = 0x9E3779B9u, kW1 = 0xBB67AE85u;
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  uint32_t c0 = (uint32_t)offset, c1 = (uint32_t)(offset >> 32);
+  uint32_t c2 = (uint32_t)subsequence, c3 = (uint32_t)(subsequence >> 32);
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(kA, c0), lo0 = kA * c0;
+    const uint32_t hi1 = __umulhi(kB, c2), lo1 = kB * c2;
+    c0 = hi1 ^ c1 ^ k0;
+    c1 = lo1;
+    c2 = hi0 ^ c3 ^ k1;
+    c3 = lo0;
+    k0 += kW0;
+    k1 += kW1;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+__device__ __forceinline__ bool dropout_keep_word(uint32_t w, uint32_t t1, uint32_t t2) { return w <= t1 || w >= t2; }
+// element i (any i): one Philox call, one word of it
+__device__ __forceinline__ bool dropout_keep_at(unsigned long long seed, unsigned long long offset,
+                                                unsigned long long i, uint32_t t1, uint32_t t2) {
+  const uint4 r = philox4x32_10(seed, i >> 2, offset);
+  const uint32_t c = (uint32_t)i & 3u;
+  const uint32_t w = c == 0 ? r.x : (c == 1 ? r.y : (c == 2 ? r.z : r.w));
+  return dropout_keep_word(w, t1, t2);
+}
+
 __host__ __device__ __forceinline__ constexpr int64_t ceil_div64(int64_t a, int64_t b) {
   return (a + b - 1) / b;
 }

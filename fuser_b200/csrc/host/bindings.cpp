@@ -24,7 +24,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   });
 
   py::class_<SegmentSpec>(m, "SegmentSpec")
-      .def(py::init([](int op, uint32_t flags, double eps, int variant, int cluster_size, int correction) {
+      .def(py::init([](int op, uint32_t flags, double eps, int variant, int cluster_size, int correction, double dropout_keep) {
              SegmentSpec s;
              s.op = op;
              s.flags = flags;
@@ -32,16 +32,18 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
              s.variant = variant;
              s.cluster_size = cluster_size;
              s.correction = correction;
+             s.dropout_keep = dropout_keep;
              return s;
            }),
            py::arg("op"), py::arg("flags") = 0, py::arg("eps") = 0.0, py::arg("variant") = 0,
-           py::arg("cluster_size") = 0, py::arg("correction") = 0)
+           py::arg("cluster_size") = 0, py::arg("correction") = 0, py::arg("dropout_keep") = 1.0)
       .def_readwrite("op", &SegmentSpec::op)
       .def_readwrite("flags", &SegmentSpec::flags)
       .def_readwrite("eps", &SegmentSpec::eps)
       .def_readwrite("variant", &SegmentSpec::variant)
       .def_readwrite("cluster_size", &SegmentSpec::cluster_size)
-      .def_readwrite("correction", &SegmentSpec::correction);
+      .def_readwrite("correction", &SegmentSpec::correction)
+      .def_readwrite("dropout_keep", &SegmentSpec::dropout_keep);
 
   // the C++ segment classifier on a plain-data expression graph (segment_matcher.h): nodes are tuples
   // (kind, dtype, is_scalar, args, dims, red_axes, correction, value, size_class)

@@ -4,6 +4,7 @@
 #include <ATen/cuda/CUDAContext.h>
 #include <c10/cuda/CUDAGuard.h>
 
+#include <cstring>
 #include <map>
 #include <mutex>
 #include <sstream>
@@ -44,6 +45,13 @@ b200norm_desc make_desc(const SegmentSpec& s, int dt, int64_t rows, int64_t cols
   d.flags = s.flags;
   d.cluster_size = s.cluster_size;
   d.reserved[0] = s.correction;
+  if (s.flags & B200NORM_F_DROPOUT) {
+    uint64_t bits;
+    static_assert(sizeof(bits) == sizeof(s.dropout_keep), "double is 64 bits");
+    memcpy(&bits, &s.dropout_keep, sizeof(bits));
+    d.reserved[1] = (int32_t)(uint32_t)bits;
+    d.reserved[2] = (int32_t)(uint32_t)(bits >> 32);
+  }
   return d;
 }
 
@@ -141,11 +149,13 @@ std::vector<at::Tensor> NormExecutor::allocateOutputs(const std::vector<at::Tens
       if ((f & B200NORM_F_ADD_RESIDUAL) && (f & B200NORM_F_OUT_SUM)) out.push_back(at::empty(first.sizes(), opts));
       if (f & B200NORM_F_OUT_MEAN) out.push_back(at::empty(stat_shape(first), f32));
       if (f & B200NORM_F_OUT_INVSTD) out.push_back(at::empty(stat_shape(first), f32));
+      if (f & B200NORM_F_DROPOUT) out.push_back(at::empty(first.sizes(), opts.dtype(at::kBool)));  // the mask
       break;
     case B200NORM_OP_RMSNORM_FWD:
       out.push_back(at::empty(first.sizes(), opts));
       if ((f & B200NORM_F_ADD_RESIDUAL) && (f & B200NORM_F_OUT_SUM)) out.push_back(at::empty(first.sizes(), opts));
       out.push_back(at::empty(stat_shape(first), f32));
+      if (f & B200NORM_F_DROPOUT) out.push_back(at::empty(first.sizes(), opts.dtype(at::kBool)));  // the mask
       break;
     case B200NORM_OP_SOFTMAX_FWD:
     case B200NORM_OP_LOGSOFTMAX_FWD:
@@ -159,6 +169,7 @@ std::vector<at::Tensor> NormExecutor::allocateOutputs(const std::vector<at::Tens
     case B200NORM_OP_RMSNORM_BWD: {
       const bool ln = spec_.op == B200NORM_OP_LAYERNORM_BWD;
       if (f & B200NORM_F_OUT_DX) out.push_back(at::empty(in.at(1).sizes(), opts));
+      if ((f & B200NORM_F_OUT_DX) && (f & B200NORM_F_DROPOUT)) out.push_back(at::empty(in.at(1).sizes(), opts));  // d residual
       const bool want_dw = (f & B200NORM_F_OUT_DW) != 0;
       const bool want_db = ln && (f & B200NORM_F_OUT_DB) != 0;
       if ((want_dw || want_db) && !(f & B200NORM_F_PEER_PUBLISH)) {  // a publish leaves the sums in the exchange slot
@@ -245,8 +256,12 @@ std::vector<at::Tensor> NormExecutor::run(const std::vector<at::Tensor>& inputs,
   std::vector<b200norm_tensor> in_args, out_args;
   in_args.reserve(inputs.size());
   out_args.reserve(outputs.size());
+  // fused dropout, backward: the residual matrix (and the mask) follow the per-row / per-column vectors
+  const bool drop_bwd = is_norm_bwd(spec_.op) && (spec_.flags & B200NORM_F_DROPOUT);
+  const size_t residual_at = drop_bwd && inputs.size() >= 2 ? inputs.size() - 2 : (size_t)-1;
   for (size_t i = 0; i < inputs.size() && spec_.op != B200NORM_OP_PEER_COMBINE; ++i) {
-    keep.push_back((int)i < n_mat_in ? as_rows(inputs[i], cols) : inputs[i].reshape({-1}));
+    const bool mat = (int)i < n_mat_in || i == residual_at;
+    keep.push_back(mat ? as_rows(inputs[i], cols) : inputs[i].reshape({-1}));
     in_args.push_back(as_arg(keep.back()));
   }
   int n_mat_out = 0;
@@ -264,7 +279,7 @@ std::vector<at::Tensor> NormExecutor::run(const std::vector<at::Tensor>& inputs,
       break;
     case B200NORM_OP_LAYERNORM_BWD:
     case B200NORM_OP_RMSNORM_BWD:
-      n_mat_out = (spec_.flags & B200NORM_F_OUT_DX) ? 1 : 0;
+      n_mat_out = (spec_.flags & B200NORM_F_OUT_DX) ? (drop_bwd ? 2 : 1) : 0;
       break;
     default:
       n_mat_out = 0;
@@ -286,7 +301,6 @@ std::vector<at::Tensor> NormExecutor::run(const std::vector<at::Tensor>& inputs,
   const int rc = b200norm_launch(&d, in_args.data(), (int)in_args.size(), out_args.data(), (int)out_args.size(),
                                  ws_ptr, ws_n, (void*)stream);
   if (rc != B200NORM_OK) raise(rc);
-  (void)is_norm_bwd;
   return outputs;
 }
 

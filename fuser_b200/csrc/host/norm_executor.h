@@ -35,6 +35,7 @@ struct SegmentSpec {
   int32_t variant = 0;     // b200norm_variant (0 = planner's choice)
   int32_t cluster_size = 0;
   int32_t correction = 0;  // var_mean's correction (B200NORM_F_STAT_VAR), travels in desc.reserved[0]
+  double dropout_keep = 1.0;  // B200NORM_F_DROPOUT: keep probability 1 - p, travels in desc.reserved[1..2]
 };
 
 class NormExecutor {

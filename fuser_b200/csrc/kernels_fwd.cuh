@@ -252,7 +252,9 @@ __global__ void __launch_bounds__(kMaxBlock, 1) softmax_fwd_ring_kernel(const Ro
   const int nchunks = p.nchunks;
 
   const size_t out_row_bytes = (size_t)p.out_stride * sizeof(T);
-  const bool online = g.csize > 1 && (p.flags & kFlagTwoExchange) == 0;
+  // Measured slower than the two-reduction form on every cluster plan (bf16 [4096,131072] 755 vs 704 us, fp32
+  // [2048,131072] 1138 vs 708 us: the rescaling costs more than the saved DSMEM round trip) — a tuning knob only.
+  const bool online = g.csize > 1 && (p.flags & kFlagOneExchange) != 0;
   for (; ring.acquire(); ring.advance()) {
     if (ring.k == 0) tl_mark(p, 2);
     const int nrows = ring.cur_nrows;

@@ -69,17 +69,42 @@ __global__ void __launch_bounds__(kGenericThreads) generic_row_kernel(const RowP
     // the io dtype when the fusion does so; the sum is written out once if requested
     const bool add_res = (OP == G_RMSNORM_FWD || OP == G_LAYERNORM_FWD) && (p.flags & kFlagAddResidual) != 0;
     const bool round_sum = (p.flags & kFlagRoundSum) != 0;
+    // fused dropout (benchmarks/python/test_dropout_{layernorm,rmsnorm}_fwd.py: norm(input2 + dropout(input1))):
+    // the mask is drawn once (Philox, element index row * N + c), written out, and read back by the later passes
+    // — every thread re-reads exactly the bytes it wrote
+    const bool drop_fwd = add_res && (p.flags & kFlagDropout) != 0;
+    uint8_t* mrow = drop_fwd ? p.mask_out + (size_t)row * (size_t)N : nullptr;
+    if (drop_fwd) {
+      const unsigned long long seed = p.rng[0], offset = p.rng[1];
+      for (int c = tid; c < N; c += kGenericThreads)
+        mrow[c] = dropout_keep_at(seed, offset, (unsigned long long)row * (unsigned long long)N + (unsigned long long)c,
+                                  p.drop_t1, p.drop_t2) ? 1 : 0;
+    }
     auto xin = [&](int c) -> float {
       float x = IO<T>::to_f32(a[c]);
+      if (drop_fwd) x = mrow[c] ? x * p.drop_scale : 0.f;
       if (add_res) {
         x += IO<T>::to_f32(b[c]);
         if (round_sum) x = IO<T>::round_trip(x);
       }
       return x;
     };
+    // backward of the same: x_eff = residual + dropout(x) rebuilt from the saved mask
+    const bool drop_bwd = (OP == G_RMSNORM_BWD || OP == G_LAYERNORM_BWD) && (p.flags & kFlagDropout) != 0;
+    const T* res_b = drop_bwd ? static_cast<const T*>(p.in2) + row * p.in2_stride : nullptr;
+    const uint8_t* mrow_b = drop_bwd ? p.mask_in + (size_t)row * (size_t)N : nullptr;
+    auto xeff = [&](int c) -> float {
+      float x = IO<T>::to_f32(b[c]);
+      if (drop_bwd) x = IO<T>::to_f32(res_b[c]) + (mrow_b[c] ? x * p.drop_scale : 0.f);
+      return x;
+    };
     if ((OP == G_RMSNORM_FWD || OP == G_LAYERNORM_FWD) && add_res && p.out1 != nullptr) {
       T* so = static_cast<T*>(p.out1) + row * p.out1_stride;
-      for (int c = tid; c < N; c += kGenericThreads) so[c] = IO<T>::from_f32(IO<T>::to_f32(a[c]) + IO<T>::to_f32(b[c]));
+      for (int c = tid; c < N; c += kGenericThreads) {
+        float x = IO<T>::to_f32(a[c]);
+        if (drop_fwd) x = mrow[c] ? x * p.drop_scale : 0.f;
+        so[c] = IO<T>::from_f32(x + IO<T>::to_f32(b[c]));
+      }
     }
 
     if constexpr (OP == G_RMSNORM_FWD) {
@@ -164,7 +189,7 @@ __global__ void __launch_bounds__(kGenericThreads) generic_row_kernel(const RowP
       const float invstd = (!LN && (p.flags & kFlagStatIsRms)) ? __frcp_rn(st) : st;
       float s[2] = {0.f, 0.f};
       for (int c = tid; c < N; c += kGenericThreads) {
-        const float xh = (IO<T>::to_f32(b[c]) - mean) * invstd;
+        const float xh = (xeff(c) - mean) * invstd;
         float gg = IO<T>::to_f32(a[c]);
         if (wgt != nullptr) gg *= IO<T>::to_f32(wgt[c]);
         s[0] += gg;
@@ -173,11 +198,19 @@ __global__ void __launch_bounds__(kGenericThreads) generic_row_kernel(const RowP
       block_allreduce<SumOp, 2>(s, red, phase);
       const float s1 = centered ? s[0] : 0.f;
       const float aa = invstd * p.inv_n;
+      T* o1 = drop_bwd && p.out1 != nullptr ? static_cast<T*>(p.out1) + row * p.out1_stride : nullptr;
       for (int c = tid; c < N; c += kGenericThreads) {
-        const float xh = (IO<T>::to_f32(b[c]) - mean) * invstd;
+        const float xh = (xeff(c) - mean) * invstd;
         float gg = IO<T>::to_f32(a[c]);
         if (wgt != nullptr) gg *= IO<T>::to_f32(wgt[c]);
-        o[c] = IO<T>::from_f32(aa * ((p.n_f * gg - s1) - xh * (s[1] * p.proj_scale)));
+        const float dxe = aa * ((p.n_f * gg - s1) - xh * (s[1] * p.proj_scale));
+        if (drop_bwd) {
+          // d residual = d x_eff; d x = d x_eff * scale * mask (test_dropout_layernorm_bwd.py:100-101)
+          if (o1 != nullptr) o1[c] = IO<T>::from_f32(dxe);
+          if (o != nullptr) o[c] = IO<T>::from_f32(mrow_b[c] ? dxe * p.drop_scale : 0.f);
+        } else {
+          o[c] = IO<T>::from_f32(dxe);
+        }
       }
     } else if constexpr (OP == G_REDUCE_INNER) {
       // sum / amax / fmax over the row -> stat1-less: result goes to out0[row] (io dtype)
@@ -236,7 +269,11 @@ __global__ void __launch_bounds__(128) generic_colsum_kernel(const RowParams p, 
       const float mean = MODE == 1 ? p.stat0[r] : 0.f;
       const float st = p.stat1[r];
       const float invstd = (MODE == 2 && (p.flags & kFlagStatIsRms)) ? __frcp_rn(st) : st;
-      const float xh = (IO<T>::to_f32(in1[r * p.in1_stride + col]) - mean) * invstd;
+      float x = IO<T>::to_f32(in1[r * p.in1_stride + col]);
+      if (p.flags & kFlagDropout)
+        x = IO<T>::to_f32(static_cast<const T*>(p.in2)[r * p.in2_stride + col]) +
+            (p.mask_in[(size_t)r * (size_t)p.cols + col] ? x * p.drop_scale : 0.f);
+      const float xh = (x - mean) * invstd;
       acc_w = fmaf(a, xh, acc_w);
       acc_b += a;
     }

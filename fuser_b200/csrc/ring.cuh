@@ -61,8 +61,9 @@ constexpr uint32_t kFlagRoundSum = 1u << 15;
 constexpr uint32_t kFlagNoY = 1u << 20;
 constexpr uint32_t kFlagStatVar = 1u << 21;
 constexpr uint32_t kFlagStatM2 = 1u << 22;
+constexpr uint32_t kFlagDropout = 1u << 23;
 // internal (never set through the ABI: check_desc refuses unknown bits), tuning knobs of the launch
-constexpr uint32_t kFlagTwoExchange = 1u << 31;  // cluster softmax forward: maximum and sum in two exchanges (B200NORM_SM_TWO_EXCH)
+constexpr uint32_t kFlagOneExchange = 1u << 31;  // cluster softmax forward: (max, sum) pairs in ONE exchange (B200NORM_SM_ONE_EXCH)
 
 struct RowParams {
   // streamed operands (row-major, unit inner stride)
@@ -71,6 +72,15 @@ struct RowParams {
   void* out0;       // y (forward) | dx (backward)
   void* out1;       // forward with a fused residual add: x + residual (nullptr = not requested)
   int64_t in0_stride, in1_stride, out_stride, out1_stride;  // row strides in elements
+  // fused dropout (kFlagDropout): forward norm(residual + dropout(x)) draws the mask and writes it out; backward
+  // reads it back, rebuilds residual + dropout(x) and produces both input gradients (out0 = d x, out1 = d residual)
+  const void* in2;              // backward: residual
+  int64_t in2_stride;
+  const uint8_t* mask_in;       // backward: [M,N] bytes, contiguous rows
+  uint8_t* mask_out;            // forward:  [M,N] bytes, contiguous rows
+  const unsigned long long* rng;  // forward: device {seed, offset} of the Philox stream
+  uint32_t drop_t1, drop_t2;    // keep <=> word <= t1 || word >= t2
+  float drop_scale;             // 1 / keep probability
   const void* weight;  // [N] io dtype or nullptr
   const void* bias;    // [N] io dtype or nullptr
   float* stat0;        // fwd: mean out (LN) ; bwd: mean in (LN)

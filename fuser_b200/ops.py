@@ -46,20 +46,20 @@ def _dtype_id(t: torch.Tensor) -> int:
 
 
 def _run(op: int, flags: int, eps: float, variant: int, cluster_size: int, ins: Sequence[torch.Tensor],
-         outs: Sequence[torch.Tensor] = (), correction: int = 0):
+         outs: Sequence[torch.Tensor] = (), correction: int = 0, dropout_keep: float = 1.0):
     """Hand the segment to the C++ NormExecutor (csrc/host/norm_executor.cpp): it allocates
     the outputs, sizes the workspace and launches on the current stream."""
     if variant == L.VARIANT_AUTO:
         variant = _forced_variant
     if cluster_size == 0:
         cluster_size = _forced_cluster
-    return H.run(op, flags, float(eps), variant, cluster_size, ins, outs, correction)
+    return H.run(op, flags, float(eps), variant, cluster_size, ins, outs, correction, float(dropout_keep))
 
 
 def plan_for(op: int, dtype: torch.dtype, rows: int, cols: int, flags: int = 0, eps: float = 0.0,
-             variant: int = L.VARIANT_AUTO, cluster_size: int = 0, correction: int = 0) -> dict:
+             variant: int = L.VARIANT_AUTO, cluster_size: int = 0, correction: int = 0, dropout_keep: float = 1.0) -> dict:
     """Dispatch decision for a segment (no launch): the launch_param dump of this library."""
-    d = L.make_desc(op, _DT[dtype], rows, cols, eps, flags, variant, cluster_size, correction)
+    d = L.make_desc(op, _DT[dtype], rows, cols, eps, flags, variant, cluster_size, correction, dropout_keep)
     return L.query(d).as_dict()
 
 
@@ -273,3 +273,68 @@ def reduce_outer(x, *, partials_f32=False, variant=L.VARIANT_AUTO):
     flags = L.F_PARTIALS_F32 if partials_f32 else 0
     (r,) = _run(L.OP_REDUCE_OUTER, flags, 0.0, variant, 0, [x])
     return r
+
+
+# ---------------------------------------------------------------------------
+# fused dropout: norm(residual + dropout(x)) and its backward
+# (benchmarks/python/test_dropout_{layernorm,rmsnorm}_{fwd,bwd}.py)
+# ---------------------------------------------------------------------------
+def philox_state(seed: int, offset: int, device) -> torch.Tensor:
+    """{seed, offset} of the Philox stream as the two-element int64 device tensor the kernels read (the
+    reference passes the same pair as kernel arguments: csrc/runtime/executor.cpp computeArgs' philox seed /
+    offset taken from the ATen generator)."""
+    to_i64 = lambda v: v - (1 << 64) if v >= (1 << 63) else v  # noqa: E731
+    return torch.tensor([to_i64(seed & ((1 << 64) - 1)), to_i64(offset & ((1 << 64) - 1))], dtype=torch.int64, device=device)
+
+
+def dropout_layer_norm_fwd(x, residual, weight, bias, eps: float, p: float, rng: torch.Tensor, *, want_sum=False,
+                           variant=L.VARIANT_AUTO, cluster_size=0):
+    """y, mean, invstd, mask (and the sum with ``want_sum``) of layer_norm(residual + dropout(x, p)); ``rng`` is
+    :func:`philox_state`. mask is the bool tensor the backward takes."""
+    flags = (L.F_HAS_WEIGHT if weight is not None else 0) | (L.F_HAS_BIAS if bias is not None else 0)
+    flags |= L.F_OUT_MEAN | L.F_OUT_INVSTD | L.F_ADD_RESIDUAL | L.F_DROPOUT | (L.F_OUT_SUM if want_sum else 0)
+    ins = [x, residual] + [t for t in (weight, bias) if t is not None] + [rng]
+    outs = iter(_run(L.OP_LAYERNORM_FWD, flags, eps, variant, cluster_size, ins, dropout_keep=1.0 - p))
+    y = next(outs)
+    s = next(outs) if want_sum else None
+    mean, invstd, mask = next(outs), next(outs), next(outs)
+    return (y, mean, invstd, mask, s) if want_sum else (y, mean, invstd, mask)
+
+
+def dropout_rms_norm_fwd(x, residual, weight, eps: float, p: float, rng: torch.Tensor, *, stat_is_rms=True,
+                         variant=L.VARIANT_AUTO, cluster_size=0):
+    """y, stat, mask of rms_norm(residual + dropout(x, p)); stat = rms (the benchmark's spelling) or invstd."""
+    flags = (L.F_HAS_WEIGHT if weight is not None else 0) | (L.F_STAT_IS_RMS if stat_is_rms else 0)
+    flags |= L.F_ADD_RESIDUAL | L.F_DROPOUT
+    ins = [x, residual] + ([weight] if weight is not None else []) + [rng]
+    y, stat, mask = _run(L.OP_RMSNORM_FWD, flags, eps, variant, cluster_size, ins, dropout_keep=1.0 - p)
+    return y, stat, mask
+
+
+def dropout_layer_norm_bwd(dy, x, residual, mask, mean, invstd, weight, p: float,
+                           output_mask=(True, True, True), *, variant=L.VARIANT_AUTO, cluster_size=0):
+    """dx (grad of the dropped branch), dresidual, dweight, dbias of layer_norm(residual + dropout(x, p))."""
+    want_dx, want_dw, want_db = output_mask
+    flags = (L.F_HAS_WEIGHT if weight is not None else 0) | L.F_DROPOUT
+    flags |= (L.F_OUT_DX if want_dx else 0) | (L.F_OUT_DW if want_dw else 0) | (L.F_OUT_DB if want_db else 0)
+    ins = [dy, x, mean, invstd] + ([weight] if weight is not None else []) + [residual, mask]
+    outs = iter(_run(L.OP_LAYERNORM_BWD, flags, 0.0, variant, cluster_size, ins, dropout_keep=1.0 - p))
+    dx = next(outs) if want_dx else None
+    dres = next(outs) if want_dx else None
+    dw = next(outs) if want_dw else None
+    db = next(outs) if want_db else None
+    return dx, dres, dw, db
+
+
+def dropout_rms_norm_bwd(dy, x, residual, mask, stat, weight, p: float, *, stat_is_rms=True,
+                         output_mask=(True, True), variant=L.VARIANT_AUTO, cluster_size=0):
+    """dx, dresidual, dweight of rms_norm(residual + dropout(x, p)) (textbook form, as the benchmark traces it)."""
+    want_dx, want_dw = output_mask
+    flags = (L.F_HAS_WEIGHT if weight is not None else 0) | (L.F_STAT_IS_RMS if stat_is_rms else 0) | L.F_DROPOUT
+    flags |= (L.F_OUT_DX if want_dx else 0) | (L.F_OUT_DW if want_dw else 0)
+    ins = [dy, x, stat] + ([weight] if weight is not None else []) + [residual, mask]
+    outs = iter(_run(L.OP_RMSNORM_BWD, flags, 0.0, variant, cluster_size, ins, dropout_keep=1.0 - p))
+    dx = next(outs) if want_dx else None
+    dres = next(outs) if want_dx else None
+    dw = next(outs) if want_dw else None
+    return dx, dres, dw

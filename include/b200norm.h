@@ -175,7 +175,17 @@ enum {
    * M2 = sum((x - mean)^2) itself (welford's var_sum). Without either it stays invstd = rsqrt(M2 / N + eps). */
   B200NORM_F_NO_Y = 1u << 20,
   B200NORM_F_STAT_VAR = 1u << 21,
-  B200NORM_F_STAT_M2 = 1u << 22
+  B200NORM_F_STAT_M2 = 1u << 22,
+  /* Fused dropout — the prologue of benchmarks/python/test_dropout_{layernorm,rmsnorm}_{fwd,bwd}.py:
+   *     y = norm(residual + dropout(x, p)),  dropout(x) = x * mask / (1 - p),  mask = uniform(0,1) < 1 - p.
+   * Forward (needs ADD_RESIDUAL): the library draws the mask from the reference's own Philox4x32-10 stream
+   * (runtime/random_numbers.cu:8-88; element i of the [M,N] tensor takes word i mod 4 of philox(seed, i / 4, offset),
+   * device_lower/pass/rng.cpp:95-127) with {seed, offset} read from a two-element int64 DEVICE tensor that follows
+   * the other inputs, and returns the mask as the last output ([M,N] bytes, 1 = kept, contiguous rows).
+   * Backward: residual[M,N] and mask[M,N] follow the other inputs; x_eff = residual + dropout(x) is rebuilt, and the
+   * outputs are d x (= d x_eff * mask / (1 - p)), then d residual (= d x_eff), then dweight / dbias.
+   * The keep probability 1 - p (the double scalar of the fusion) travels in desc.reserved[1..2] (low, high word). */
+  B200NORM_F_DROPOUT = 1u << 23
 };
 
 /* desc.variant: 0 lets the library choose (the dispatch rule mirrors the accept
@@ -243,12 +253,14 @@ typedef struct {
 
 /*
  * Tensor order per op (absent optional tensors are simply left out):
- *   LAYERNORM_FWD  in : x[M,N], residual[M,N]?, weight[N]?, bias[N]?
- *                  out: y[M,N] (absent with NO_Y), sum[M,N]?, mean[M]?, invstd | var | M2 [M]?
- *   LAYERNORM_BWD  in : dy[M,N], x[M,N], mean[M], invstd[M], weight[N]?
- *                  out: dx[M,N]?, dweight[N]?, dbias[N]?
- *   RMSNORM_FWD    in : x[M,N], residual[M,N]?, weight[N]?   out: y[M,N], sum[M,N]?, stat[M]
- *   RMSNORM_BWD    in : dy[M,N], x[M,N], stat[M], weight[N]? out: dx[M,N]?, dweight[N]?
+ *   LAYERNORM_FWD  in : x[M,N], residual[M,N]?, weight[N]?, bias[N]?, rng[2] (DROPOUT)
+ *                  out: y[M,N] (absent with NO_Y), sum[M,N]?, mean[M]?, invstd | var | M2 [M]?, mask[M,N] (DROPOUT)
+ *   LAYERNORM_BWD  in : dy[M,N], x[M,N], mean[M], invstd[M], weight[N]?, residual[M,N] + mask[M,N] (DROPOUT)
+ *                  out: dx[M,N]?, dresidual[M,N] (DROPOUT), dweight[N]?, dbias[N]?
+ *   RMSNORM_FWD    in : x[M,N], residual[M,N]?, weight[N]?, rng[2] (DROPOUT)
+ *                  out: y[M,N], sum[M,N]?, stat[M], mask[M,N] (DROPOUT)
+ *   RMSNORM_BWD    in : dy[M,N], x[M,N], stat[M], weight[N]?, residual[M,N] + mask[M,N] (DROPOUT)
+ *                  out: dx[M,N]?, dresidual[M,N] (DROPOUT), dweight[N]?
  *   SOFTMAX_FWD / LOGSOFTMAX_FWD   in : x[M,N]               out: y[M,N]
  *   SOFTMAX_BWD / LOGSOFTMAX_BWD   in : dy[M,N], y[M,N]      out: dx[M,N]
  *       (with B200NORM_F_OUTER the four softmax ops reduce over M instead of N; same tensors)

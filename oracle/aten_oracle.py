@@ -477,3 +477,92 @@ def welford(x):
     xf = _up(x)
     var, mean = torch.var_mean(xf, dim=[-1], unbiased=False, keepdim=False)
     return mean, var * xf.shape[-1]
+
+
+# ---------------------------------------------------------------------------
+# fused dropout (benchmarks/python/test_dropout_{layernorm,rmsnorm}_{fwd,bwd}.py)
+# ---------------------------------------------------------------------------
+def philox4x32_10(seed: int, subsequence, offset: int):
+    """Philox4x32-10 as the reference's runtime evaluates it (runtime/random_numbers.cu:8-58): key = seed,
+    counter = (offset lo, offset hi, subsequence lo, subsequence hi). numpy, vectorised over ``subsequence``;
+    returns the four output words. Pinned to the Random123 known-answer vectors in tests/test_dropout.py."""
+    import numpy as np
+
+    a, b, m32 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0xFFFFFFFF)
+    sub = np.asarray(subsequence, dtype=np.uint64)
+    k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
+    c0 = np.full(sub.shape, offset & 0xFFFFFFFF, dtype=np.uint64)
+    c1 = np.full(sub.shape, (offset >> 32) & 0xFFFFFFFF, dtype=np.uint64)
+    c2, c3 = sub & m32, sub >> np.uint64(32)
+    for _ in range(10):
+        p0, p1 = a * c0, b * c2
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & m32, p1 >> np.uint64(32), p1 & m32
+        c0, c1, c2, c3 = hi1 ^ c1 ^ np.uint64(k0), lo1, hi0 ^ c3 ^ np.uint64(k1), lo0
+        k0, k1 = (k0 + 0x9E3779B9) & 0xFFFFFFFF, (k1 + 0xBB67AE85) & 0xFFFFFFFF
+    return c0.astype(np.uint32), c1.astype(np.uint32), c2.astype(np.uint32), c3.astype(np.uint32)
+
+
+def uniformf(words):
+    """runtime/random_numbers.cu:66-88: fl(fl(w) * 2^-32 + 2^-33) in float32, with 1.0 mapped to 0."""
+    import numpy as np
+
+    scale = np.float32(2.0 ** -32)
+    u = words.astype(np.float32) * scale + np.float32(0.5) * scale
+    return np.where(u == np.float32(1.0), np.float32(0.0), u).astype(np.float32)
+
+
+def dropout_mask(seed: int, offset: int, shape, keep: float) -> torch.Tensor:
+    """mask = uniform(0, 1) < keep for a Float uniform() of ``shape``: element i takes word i mod 4 of
+    philox(seed, i / 4, offset) (device_lower/pass/rng.cpp:95-127); the comparison promotes the float to the
+    fusion's double scalar."""
+    import numpy as np
+
+    n = 1
+    for s in shape:
+        n *= int(s)
+    nsub = (n + 3) // 4
+    w = np.stack(philox4x32_10(seed, np.arange(nsub, dtype=np.uint64), offset), axis=1).reshape(-1)[:n]
+    return torch.from_numpy(uniformf(w).astype(np.float64) < float(keep)).view(*shape)
+
+
+def dropout_sum(x, residual, mask, keep: float):
+    """residual + dropout(x): T13 = x * mask, T15 = T13 * (1 / keep), T16 = residual + T15, all in Float
+    (test_dropout_layernorm_fwd.py:47-56; the double scalar is applied in the tensor's float arithmetic)."""
+    scale = torch.tensor(1.0 / keep, dtype=torch.float32)
+    return _up(residual) + (_up(x) * mask.to(torch.float32)) * scale
+
+
+def dropout_layer_norm_fwd(x, residual, weight, bias, eps: float, mask, keep: float):
+    """(y, mean, invstd) of layer_norm(residual + dropout(x)) for a given mask."""
+    y, mean, invstd = layer_norm_fwd(dropout_sum(x, residual, mask, keep), weight, bias, eps)
+    return y.to(x.dtype), mean, invstd
+
+
+def dropout_rms_norm_fwd(x, residual, weight, eps: float, mask, keep: float, python: bool = False):
+    """(y, stat) of rms_norm(residual + dropout(x)); ``python``: the Thunder spelling (rms statistic)."""
+    s = dropout_sum(x, residual, mask, keep)
+    if python:
+        w = weight if weight is not None else torch.ones(x.shape[-1], dtype=x.dtype)
+        y, stat = rms_norm_fwd_python(s, w, eps)
+    else:
+        y, stat = rms_norm_fwd(s, weight, eps)
+    return y.to(x.dtype), stat
+
+
+def dropout_norm_bwd(kind: str, dy, x, residual, mask, mean, stat, weight, keep: float, stat_is_rms: bool = False):
+    """Backward of the two: x_eff = residual + dropout(x) rebuilt from the mask, the plain norm backward on it,
+    d residual = d x_eff, d x = d x_eff * (1 / keep) * mask (test_dropout_layernorm_bwd.py:57-101). Returns
+    (dx, dresidual, dweight, dbias | None) in the io dtype."""
+    io = dy.dtype
+    s = dropout_sum(x, residual, mask, keep)
+    if kind == "ln":
+        dxe, dw, db = layer_norm_bwd(dy, s, mean, stat, weight)  # s is Float: nothing is rounded in between
+    else:
+        rms = stat if stat_is_rms else 1.0 / stat
+        dxe, dw = rms_norm_bwd_python(s, rms, dy, weight)  # the textbook form of test_dropout_rmsnorm_bwd.py
+        db = None
+    dxe = _up(dxe)
+    scale = torch.tensor(1.0 / keep, dtype=torch.float32)
+    dx = (dxe * scale) * mask.to(torch.float32)
+    cast = lambda t: None if t is None else t.to(io)  # noqa: E731
+    return dx.to(io), dxe.to(io), cast(dw), cast(db)
