@@ -266,7 +266,8 @@ uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 #define B200_RING_KERNEL_FOR(T, SUF)                                                                         \
   template <>                                                                                                \
   RingKernel ring_kernel_for<T>(int op, int tpr, int ch, bool cached, bool psmem, bool add, bool pipe,       \
-                                bool red, bool lean) {                                                     \
+                                bool red, bool lean, bool drop) {                                          \
+    if (drop && is_norm_bwd(op)) return cached ? ring_bwd_drop_kernel_##SUF(op, tpr, ch) : nullptr;          \
     if (op == B200NORM_OP_REDUCE_INNER || red) return ring_reduce_inner_kernel_##SUF(tpr, ch);               \
     if (op == B200NORM_OP_REDUCE_OUTER) return ring_colsum_kernel_##SUF(tpr, ch);                            \
     if (pipe && op == B200NORM_OP_LAYERNORM_FWD) return ring_ln_pipe_kernel_##SUF(tpr, ch, add);             \
@@ -277,7 +278,8 @@ uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
                            : ring_fwd_kernel_##SUF(op, tpr, ch, psmem);                                    \
   }
 template <typename T>
-RingKernel ring_kernel_for(int op, int tpr, int ch, bool cached, bool psmem, bool add, bool pipe, bool red, bool lean);
+RingKernel ring_kernel_for(int op, int tpr, int ch, bool cached, bool psmem, bool add, bool pipe, bool red, bool lean,
+                           bool drop);
 B200_RING_KERNEL_FOR(float, f32)
 B200_RING_KERNEL_FOR(__nv_bfloat16, bf16)
 B200_RING_KERNEL_FOR(__half, f16)
@@ -301,11 +303,11 @@ int prepare_ring_kernel(DeviceCtx& ctx, RingKernel k, int smem, int cluster) {
 }
 
 RingKernel ring_kernel_any(int dt, int op, int tpr, int ch, bool cached, bool psmem, bool add, bool pipe, bool red,
-                           bool lean) {
+                           bool lean, bool drop) {
   switch (dt) {
-    case B200NORM_DT_F32: return ring_kernel_for<float>(op, tpr, ch, cached, psmem, add, pipe, red, lean);
-    case B200NORM_DT_BF16: return ring_kernel_for<__nv_bfloat16>(op, tpr, ch, cached, psmem, add, pipe, red, lean);
-    case B200NORM_DT_F16: return ring_kernel_for<__half>(op, tpr, ch, cached, psmem, add, pipe, red, lean);
+    case B200NORM_DT_F32: return ring_kernel_for<float>(op, tpr, ch, cached, psmem, add, pipe, red, lean, drop);
+    case B200NORM_DT_BF16: return ring_kernel_for<__nv_bfloat16>(op, tpr, ch, cached, psmem, add, pipe, red, lean, drop);
+    case B200NORM_DT_F16: return ring_kernel_for<__half>(op, tpr, ch, cached, psmem, add, pipe, red, lean, drop);
     default: return nullptr;
   }
 }
@@ -388,6 +390,10 @@ bool try_ring_plan(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, int 
   if (slice_cols * es > (int64_t)100 * 1024 && !(single_stage_ok && slice_cols * es <= (int64_t)200 * 1024)) return false;
   const int nchunks = (int)(slice_cols / vec);
   const bool add = is_add_fwd(d);
+  // fused dropout: forward on the register-resident ADD kernels; backward on the cached form with two more streams
+  // per stage (residual slice + mask bytes, whose slices must be whole 16-byte chunks)
+  const bool dropout = (d.flags & B200NORM_F_DROPOUT) != 0;
+  const bool drop_bwd = dropout && is_norm_bwd(d.op);
   const int ns = add ? 2 : n_streams(d.op);
   const bool bwd = is_norm_bwd(d.op);
   const bool ln_bwd = d.op == B200NORM_OP_LAYERNORM_BWD;
@@ -511,7 +517,7 @@ bool try_ring_plan(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, int 
   // (C2 backward 80 -> 70 us); fp32 rows (memory bound already) and N = 12288 (only two stages
   // would fit) stay at one row.
   if (bwd && es == 2 && C == 1 && rows_contiguous && tile_rows == 1) {
-    const uint32_t stage2 = align_up((uint32_t)ns * 2u * p.slice_bytes, 128);
+    const uint32_t stage2 = align_up((uint32_t)(ns + (drop_bwd ? 1 : 0)) * 2u * p.slice_bytes + (drop_bwd ? 2u * (uint32_t)slice_cols : 0u), 128);
     const int64_t budget = (int64_t)dev.smem_optin - 4096;
     if (budget / stage2 / groups >= 3 && ceil_div64(d.rows, 2) >= (int64_t)dev.sm_count * groups * 2) tile_rows = 2;
   }
@@ -522,7 +528,8 @@ bool try_ring_plan(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, int 
   p.contiguous = (C == 1 && rows_contiguous) ? 1 : 0;
   if (tile_rows == 1) p.contiguous = 1;  // a one-row tile is always one copy per stream
   p.stream_bytes = (uint32_t)tile_rows * p.slice_bytes;
-  p.stage_bytes = align_up((uint32_t)ns * p.stream_bytes, 128);
+  p.stage_bytes = align_up((uint32_t)ns * p.stream_bytes + (drop_bwd ? p.stream_bytes + (uint32_t)tile_rows * (uint32_t)slice_cols : 0u), 128);
+  if (drop_bwd && slice_cols % 16 != 0) return false;
 
   // LayerNorm forward keeps fp32 copies of weight and bias in shared memory when the ring
   // still gets >= 3 stages per group next to them.
@@ -535,8 +542,10 @@ bool try_ring_plan(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, int 
   // against the two-round register kernel (bf16): [32768,12288] 343 -> 305 us, [16384,8192] 115 -> 92 us,
   // [16384,4096] 62 -> 53 us, [16384,16384] 273 -> 182 us; fp32 [2048,4096] 15.4 -> 14.5 us.
   // B200NORM_NO_LN_PIPE=1 switches it off.
+  // (fused dropout: the register-resident forward kernels only — the row must not be rebuilt a second time)
+  if (dropout && (!cached || ch == 0)) return false;
   const bool ln_pipe = d.op == B200NORM_OP_LAYERNORM_FWD && !inner_red && ch > 0 && nchunks == tpr * ch && tile_rows == 1 &&
-                       tpr >= 64 && kn.no_ln_pipe == 0;
+                       tpr >= 64 && kn.no_ln_pipe == 0 && !dropout;
   bool want_psmem = d.op == B200NORM_OP_LAYERNORM_FWD && ch > 0 && es == 2 && slice_cols <= 8192 &&
                     kn.no_psmem == 0 && !ln_pipe && !inner_red;
   const uint32_t param_bytes = align_up(2u * (uint32_t)slice_cols * 4u, 128);
@@ -585,7 +594,7 @@ bool try_ring_plan(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, int 
   // first pass: C5 335 -> 320 us) and fp32 rows ([16384,8192] 273 -> 248 us); the 16-bit
   // single-CTA case is bound by instruction issue, not by the reduction latency, and loses 4 %
   // (C4 420 -> 440 us), so it keeps the plain kernel. B200NORM_PIPE=1 / B200NORM_NO_PIPE=1 force it.
-  p.pipe = bwd && !cached && tile_rows == 1 && tpr >= 64 && kn.no_pipe == 0 &&
+  p.pipe = bwd && !cached && !dropout && tile_rows == 1 && tpr >= 64 && kn.no_pipe == 0 &&
            (C > 1 || es == 4 || kn.pipe != 0);
   // RMSNorm forward over a cluster: the same pipeline (the row is read twice from its stage instead
   // of being held in registers, so the next row's sum of squares overlaps the DSMEM exchange)
@@ -614,10 +623,10 @@ bool try_ring_plan(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, int 
 
   // only the plans the planner emits are instantiated (ring_inst_*.cuh): a combination forced through the tuning
   // knobs may have no kernel — then this cluster size is simply not feasible
-  if (ring_kernel_any(d.io_dtype, d.op, tpr, ch, cached, p.psmem, add, p.pipe, p.stats_reduce, p.lean) == nullptr)
+  if (ring_kernel_any(d.io_dtype, d.op, tpr, ch, cached, p.psmem, add, p.pipe, p.stats_reduce, p.lean, dropout) == nullptr)
     return false;
   const int64_t ntiles = ceil_div64(d.rows, tile_rows);
-  int64_t nclusters = max_active_clusters(ctx, ring_kernel_any(d.io_dtype, d.op, tpr, ch, cached, p.psmem, add, p.pipe, p.stats_reduce, p.lean), p.block,
+  int64_t nclusters = max_active_clusters(ctx, ring_kernel_any(d.io_dtype, d.op, tpr, ch, cached, p.psmem, add, p.pipe, p.stats_reduce, p.lean, dropout), p.block,
                                           (int)p.smem, C);
   if (nclusters > ntiles) nclusters = ntiles;
   if (nclusters < 1) nclusters = 1;
@@ -644,9 +653,7 @@ int make_plan_uncached(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, 
   }
 
   bool ring_ok = false;
-  const bool ring_has_dropout = false;  // the ring kernels do not draw / apply a dropout mask yet
-  if (is_row_op(d.op) && aligned && d.variant != B200NORM_VARIANT_GENERIC && d.rows > 0 && d.cols > 0 &&
-      (!(d.flags & B200NORM_F_DROPOUT) || ring_has_dropout)) {
+  if (is_row_op(d.op) && aligned && d.variant != B200NORM_VARIANT_GENERIC && d.rows > 0 && d.cols > 0) {
     const int forced_c = d.cluster_size != 0 ? d.cluster_size : kn.cluster;
     static const int cs[] = {1, 2, 4, 8, 16};
     Plan best;
@@ -1013,7 +1020,7 @@ int launch_typed(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, const 
 
   // ---- ring kernels ----
   RingKernel k = ring_kernel_for<T>(d.op, plan.tpr, plan.ch, plan.cached, plan.psmem, is_add_fwd(d), plan.pipe,
-                                    plan.stats_reduce, plan.lean);
+                                    plan.stats_reduce, plan.lean, (d.flags & B200NORM_F_DROPOUT) != 0);
   if (k == nullptr)
     return fail(B200NORM_ERR_UNSUPPORTED, "no ring kernel for op %d tpr %d ch %d", d.op, plan.tpr, plan.ch);
   {
@@ -1418,6 +1425,7 @@ int b200norm_launch(const b200norm_desc* desc, const b200norm_tensor* inputs, in
       expect *= t.sizes[i];
     }
     *ptr = t.data;
+    if (!is_aligned16(t.data) || d.cols % 16 != 0) aligned = false;  // the ring kernels move the mask in 16-byte chunks
     return B200NORM_OK;
   };
 
@@ -1682,6 +1690,7 @@ int b200norm_launch(const b200norm_desc* desc, const b200norm_tensor* inputs, in
   rp.tile_rows = plan.tile_rows;
   rp.cols_cta = plan.cluster > 0 ? (int32_t)(d.cols / plan.cluster) : (int32_t)d.cols;
   rp.nstreams = is_add_fwd(d) ? 2 : n_streams(d.op);
+  rp.drop_streams = (dropout && is_norm_bwd(d.op)) ? 1 : 0;
   rp.contiguous = plan.contiguous;
   rp.slice_bytes = plan.slice_bytes;
   rp.stream_bytes = plan.stream_bytes;

@@ -4,4 +4,5 @@ namespace b200norm {
 RingKernel ring_bwd_kernel_f16(int op, int tpr, int ch, bool cached, bool centered) {
   return ring_bwd_kernel_for<__half>(op, tpr, ch, cached, centered);
 }
+RingKernel ring_bwd_drop_kernel_f16(int op, int tpr, int ch) { return ring_bwd_drop_kernel_for<__half>(op, tpr, ch); }
 }  // namespace b200norm

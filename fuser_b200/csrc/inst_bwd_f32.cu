@@ -4,4 +4,5 @@ namespace b200norm {
 RingKernel ring_bwd_kernel_f32(int op, int tpr, int ch, bool cached, bool centered) {
   return ring_bwd_kernel_for<float>(op, tpr, ch, cached, centered);
 }
+RingKernel ring_bwd_drop_kernel_f32(int op, int tpr, int ch) { return ring_bwd_drop_kernel_for<float>(op, tpr, ch); }
 }  // namespace b200norm

@@ -324,8 +324,12 @@ __device__ __forceinline__ void bwd_epilogue(const RowParams& p, const Group<TPR
 // CEN: the dx formula keeps the centring term -sum(g) (LayerNorm always; RMSNorm as the C++ rms_norm_backward
 // builder writes it). CEN = false is the textbook RMSNorm backward: no sum(g) accumulation and ONE reduced value
 // per row instead of two (about 8 % fewer instructions in the cached form the C2 config runs).
-template <typename T, int TPR, int CH, bool LN, bool CACHE, bool CEN = true>
+// DROP (cached form only): the fused-dropout backward of benchmarks/python/test_dropout_{layernorm,rmsnorm}_bwd.py.
+// Every stage carries dy | x | residual | mask bytes; x_eff = residual + (mask ? x / keep : 0) replaces x, and the
+// row's gradient goes out twice: d residual = d x_eff (out1) and d x = mask ? d x_eff / keep : 0 (out0).
+template <typename T, int TPR, int CH, bool LN, bool CACHE, bool CEN = true, bool DROP = false>
 __global__ void __launch_bounds__(kMaxBlock, 1) norm_bwd_ring_kernel(const RowParams p) {
+  static_assert(!DROP || CACHE, "the fused-dropout backward keeps g / x_hat (and the mask bits) in registers");
   constexpr int VEC = IO<T>::VEC;
   constexpr int H = VEC / 2;
   static_assert(CH > 0, "column accumulators need a fixed chunk ownership");
@@ -370,13 +374,17 @@ __global__ void __launch_bounds__(kMaxBlock, 1) norm_bwd_ring_kernel(const RowPa
   uint8_t* out_tile = out_row_ptr<T>(p, ring.row0, g.crank, g.gtid);
   const size_t out_row_bytes = (size_t)p.out_stride * sizeof(T);
   const size_t out_tile_bytes = (size_t)ring.row_step * out_row_bytes;
-  for (; ring.more(); ring.advance(), out_tile += out_tile_bytes) {
+  uint8_t* out1_tile = DROP && p.out1 != nullptr ? out1_row_ptr<T>(p, ring.row0, g.crank, g.gtid) : nullptr;
+  const size_t out1_row_bytes = (size_t)p.out1_stride * sizeof(T);
+  const size_t out1_tile_bytes = (size_t)ring.row_step * out1_row_bytes;
+  for (; ring.more(); ring.advance(), out_tile += out_tile_bytes, out1_tile += out1_tile_bytes) {
     ring.wait();
     if (ring.k == 0) tl_mark(p, 2);
     const int nrows = ring.nrows();
     const uint8_t* dyrow = smem_raw + ring.stage_off + 16u * (uint32_t)g.gtid;
     uint8_t* dxrow = out_tile;
-    for (int r = 0; r < nrows; ++r, dyrow += p.slice_bytes, dxrow += out_row_bytes) {
+    uint8_t* drrow = out1_tile;
+    for (int r = 0; r < nrows; ++r, dyrow += p.slice_bytes, dxrow += out_row_bytes, drrow += out1_row_bytes) {
       const uint8_t* xrow = dyrow + p.stream_bytes;
       const float mean = nxt_mean;
       const float st = nxt_stat;
@@ -408,12 +416,28 @@ __global__ void __launch_bounds__(kMaxBlock, 1) norm_bwd_ring_kernel(const RowPa
       };
       float2 gv[CACHE ? CH : 1][H];
       float2 xv[CACHE ? CH : 1][H];
+      uint32_t mbits[DROP ? CH : 1][VEC / 4];  // the chunk's mask bytes (VEC of them), kept for the output pass
+      const uint8_t* mrow = smem_raw + ring.stage_off + 3u * p.stream_bytes + (uint32_t)r * (uint32_t)p.cols_cta +
+                            (uint32_t)(g.gtid * VEC);
       float2 s1 = f2(0.f), s2 = f2(0.f);
       for_each_chunk<TPR, CH>(g.gtid, nchunks, [&](int j, int coff) {
         float2 dy[H], x[H], w[H];
         IO<T>::unpack2(ld_smem_u4(dyrow + 16 * coff), dy);
         IO<T>::unpack2(ld_smem_u4(xrow + 16 * coff), x);
         IO<T>::unpack2(wq[j], w);
+        if constexpr (DROP) {
+          float2 rs[H];
+          IO<T>::unpack2(ld_smem_u4(xrow + p.stream_bytes + 16 * coff), rs);
+#pragma unroll
+          for (int q = 0; q < VEC / 4; ++q) {
+            const uint32_t mb = *reinterpret_cast<const uint32_t*>(mrow + VEC * coff + 4 * q);
+            mbits[j][q] = mb;
+            x[2 * q].x = rs[2 * q].x + ((mb & 0xffu) ? x[2 * q].x * p.drop_scale : 0.f);
+            x[2 * q].y = rs[2 * q].y + ((mb & 0xff00u) ? x[2 * q].y * p.drop_scale : 0.f);
+            x[2 * q + 1].x = rs[2 * q + 1].x + ((mb & 0xff0000u) ? x[2 * q + 1].x * p.drop_scale : 0.f);
+            x[2 * q + 1].y = rs[2 * q + 1].y + ((mb & 0xff000000u) ? x[2 * q + 1].y * p.drop_scale : 0.f);
+          }
+        }
 #pragma unroll
         for (int k = 0; k < H; ++k) {
           const float2 gg = f2mul(dy[k], w[k]);
@@ -466,6 +490,17 @@ __global__ void __launch_bounds__(kMaxBlock, 1) norm_bwd_ring_kernel(const RowPa
               } else {
                 dx[k] = f2fma(A, f2mul(dy[k], w[k]), f2fma(B, x_hat(x[k]), C));
               }
+            }
+          }
+          if constexpr (DROP) {
+            st_global_stream(drrow + 16 * coff, IO<T>::pack2(dx));  // d residual = d x_eff
+#pragma unroll
+            for (int q = 0; q < VEC / 4; ++q) {
+              const uint32_t mb = mbits[j][q];
+              dx[2 * q].x = (mb & 0xffu) ? dx[2 * q].x * p.drop_scale : 0.f;
+              dx[2 * q].y = (mb & 0xff00u) ? dx[2 * q].y * p.drop_scale : 0.f;
+              dx[2 * q + 1].x = (mb & 0xff0000u) ? dx[2 * q + 1].x * p.drop_scale : 0.f;
+              dx[2 * q + 1].y = (mb & 0xff000000u) ? dx[2 * q + 1].y * p.drop_scale : 0.f;
             }
           }
           st_global_stream(dxrow + 16 * coff, IO<T>::pack2(dx));

@@ -45,6 +45,9 @@ __global__ void __launch_bounds__(kMaxBlock, 1) rmsnorm_fwd_ring_kernel(const Ro
   const bool stat_writer = g.gtid == 0 && g.crank == 0 && p.stat1 != nullptr;
   const bool round_sum = ADD && (p.flags & kFlagRoundSum) != 0;
   const bool out_sum = ADD && p.out1 != nullptr;
+  // fused dropout of the x stream (cached form only: the planner never pairs kFlagDropout with CH == 0)
+  const bool drop = ADD && CH > 0 && (p.flags & kFlagDropout) != 0;
+  const unsigned long long drop_seed = drop ? p.rng[0] : 0ull, drop_offset = drop ? p.rng[1] : 0ull;
 
   const size_t out_row_bytes = (size_t)p.out_stride * sizeof(T);
   const size_t sum_row_bytes = (size_t)p.out1_stride * sizeof(T);
@@ -57,10 +60,14 @@ __global__ void __launch_bounds__(kMaxBlock, 1) rmsnorm_fwd_ring_kernel(const Ro
     for (int r = 0; r < nrows; ++r, xrow += p.slice_bytes, yrow += out_row_bytes, srow += sum_row_bytes) {
       float2 x[NC][H];
       float2 acc = f2(0.f);
+      // fused dropout: linear index of the row's first element of this CTA's slice
+      const unsigned long long drop_lin =
+          (unsigned long long)(ring.row0 + r) * (unsigned long long)p.cols + (unsigned long long)(g.crank * (uint32_t)p.cols_cta);
       for_each_chunk<TPR, CH>(g.gtid, nchunks, [&](int j, int coff) {
         float2 t[H];
         IO<T>::unpack2(ld_smem_u4(xrow + 16 * coff), t);
         if constexpr (ADD) {
+          if (drop) dropout_chunk<T, H>(t, p, drop_seed, drop_offset, drop_lin + (unsigned long long)((g.gtid + coff) * VEC));
           add_residual_chunk<T, H>(t, xrow + p.stream_bytes + 16 * coff, round_sum, out_sum ? srow + 16 * coff : nullptr);
         }
 #pragma unroll
@@ -142,6 +149,9 @@ __global__ void __launch_bounds__(kMaxBlock, 1) layernorm_fwd_ring_kernel(const 
   const bool no_y = (p.flags & kFlagNoY) != 0;  // stand-alone var_mean / welford: statistics only
   const bool round_sum = ADD && (p.flags & kFlagRoundSum) != 0;
   const bool out_sum = ADD && p.out1 != nullptr;
+  // fused dropout of the x stream (cached form only: the planner never pairs kFlagDropout with CH == 0)
+  const bool drop = ADD && CH > 0 && (p.flags & kFlagDropout) != 0;
+  const unsigned long long drop_seed = drop ? p.rng[0] : 0ull, drop_offset = drop ? p.rng[1] : 0ull;
 
   const size_t out_row_bytes = (size_t)p.out_stride * sizeof(T);
   const size_t sum_row_bytes = (size_t)p.out1_stride * sizeof(T);
@@ -154,10 +164,14 @@ __global__ void __launch_bounds__(kMaxBlock, 1) layernorm_fwd_ring_kernel(const 
     for (int r = 0; r < nrows; ++r, xrow += p.slice_bytes, yrow += out_row_bytes, srow += sum_row_bytes) {
       float2 x[NC][H];
       float2 acc = f2(0.f);
+      // fused dropout: linear index of the row's first element of this CTA's slice
+      const unsigned long long drop_lin =
+          (unsigned long long)(ring.row0 + r) * (unsigned long long)p.cols + (unsigned long long)(g.crank * (uint32_t)p.cols_cta);
       for_each_chunk<TPR, CH>(g.gtid, nchunks, [&](int j, int coff) {
         float2 t[H];
         IO<T>::unpack2(ld_smem_u4(xrow + 16 * coff), t);
         if constexpr (ADD) {
+          if (drop) dropout_chunk<T, H>(t, p, drop_seed, drop_offset, drop_lin + (unsigned long long)((g.gtid + coff) * VEC));
           add_residual_chunk<T, H>(t, xrow + p.stream_bytes + 16 * coff, round_sum, out_sum ? srow + 16 * coff : nullptr);
         }
 #pragma unroll

@@ -81,6 +81,7 @@ struct RowParams {
   const unsigned long long* rng;  // forward: device {seed, offset} of the Philox stream
   uint32_t drop_t1, drop_t2;    // keep <=> word <= t1 || word >= t2
   float drop_scale;             // 1 / keep probability
+  int32_t drop_streams;         // backward ring kernels: every stage also carries the residual slice and the mask bytes
   const void* weight;  // [N] io dtype or nullptr
   const void* bias;    // [N] io dtype or nullptr
   float* stat0;        // fwd: mean out (LN) ; bwd: mean in (LN)
@@ -471,6 +472,8 @@ struct Ring {
   // producer side
   const uint8_t* base0;
   const uint8_t* base1;
+  const uint8_t* base2;   // fused-dropout backward: the residual stream (third slot of a stage) ...
+  const uint8_t* base_m;  // ... and the mask bytes (behind it), one byte per element
 
   __device__ __forceinline__ Ring(const RowParams& p_, uint32_t smem0_, const Group<TPR>& g_)
       : p(p_), g(g_), smem0(smem0_) {
@@ -516,6 +519,8 @@ struct Ring {
     const size_t col0_bytes = (size_t)g.crank * p.slice_bytes;
     base0 = static_cast<const uint8_t*>(p.in0) + col0_bytes;
     base1 = static_cast<const uint8_t*>(p.in1) + col0_bytes;
+    base2 = static_cast<const uint8_t*>(p.in2) + col0_bytes;
+    base_m = p.mask_in + (size_t)g.crank * (size_t)p.cols_cta;
   }
 
   __device__ __forceinline__ int nrows_of(int32_t kk) const { return kk == ntiles_g - 1 ? last_nrows : p.tile_rows; }
@@ -527,18 +532,26 @@ struct Ring {
     const uint32_t bytes = (uint32_t)nr * p.slice_bytes;
     const uint32_t dst = smem0 + off;
     const uint64_t policy = l2_policy_evict_first();
+    // fused-dropout backward (p.drop_streams): dy | x | residual | mask bytes in one stage
+    const bool extra = p.drop_streams != 0;
+    const uint32_t mbytes_row = (uint32_t)p.cols_cta;
+    const uint32_t total = bytes * (uint32_t)p.nstreams + (extra ? bytes + (uint32_t)nr * mbytes_row : 0u);
     // No proxy fence is needed for this write-after-read: every reader consumed its loads
     // (the values fed the reduction) before the group barrier that precedes refill().
     if (p.contiguous) {
       if (g.lane == 0) {
-        mbar_arrive_expect_tx(b, bytes * (uint32_t)p.nstreams);
+        mbar_arrive_expect_tx(b, total);
         bulk_g2s(dst, base0 + (size_t)r0 * p.in0_stride * sizeof(T), bytes, b, policy);
         if (p.nstreams > 1) {
           bulk_g2s(dst + p.stream_bytes, base1 + (size_t)r0 * p.in1_stride * sizeof(T), bytes, b, policy);
         }
+        if (extra) {
+          bulk_g2s(dst + 2u * p.stream_bytes, base2 + (size_t)r0 * p.in2_stride * sizeof(T), bytes, b, policy);
+          bulk_g2s(dst + 3u * p.stream_bytes, base_m + (size_t)r0 * (size_t)p.cols, (uint32_t)nr * mbytes_row, b, policy);
+        }
       }
     } else {
-      if (g.lane == 0) mbar_arrive_expect_tx(b, bytes * (uint32_t)p.nstreams);
+      if (g.lane == 0) mbar_arrive_expect_tx(b, total);
       __syncwarp();
       for (int r = g.lane; r < nr; r += 32) {
         bulk_g2s(dst + (uint32_t)r * p.slice_bytes, base0 + (size_t)(r0 + r) * p.in0_stride * sizeof(T),
@@ -546,6 +559,12 @@ struct Ring {
         if (p.nstreams > 1) {
           bulk_g2s(dst + p.stream_bytes + (uint32_t)r * p.slice_bytes,
                    base1 + (size_t)(r0 + r) * p.in1_stride * sizeof(T), p.slice_bytes, b, policy);
+        }
+        if (extra) {
+          bulk_g2s(dst + 2u * p.stream_bytes + (uint32_t)r * p.slice_bytes,
+                   base2 + (size_t)(r0 + r) * p.in2_stride * sizeof(T), p.slice_bytes, b, policy);
+          bulk_g2s(dst + 3u * p.stream_bytes + (uint32_t)r * mbytes_row, base_m + (size_t)(r0 + r) * (size_t)p.cols,
+                   mbytes_row, b, policy);
         }
       }
     }
@@ -805,6 +824,34 @@ __device__ __forceinline__ void add_residual_chunk(float2 (&t)[H], const uint8_t
       if (sum_out != nullptr) st_global_stream(sum_out, q);
       if (round_sum) IO<T>::unpack2(q, t);
     }
+  }
+}
+
+// Fused dropout of one 16-byte chunk (VEC = 2 * H consecutive elements starting at linear index `lin` of the [M,N]
+// tensor, lin a multiple of 4): VEC / 4 Philox calls give the VEC words in element order (word i mod 4 of
+// subsequence i / 4: device_lower/pass/rng.cpp:95-127), kept elements are scaled by 1 / keep, dropped ones become 0
+// (x * mask * scale, benchmarks/python/test_dropout_layernorm_fwd.py:47-50), and the mask bytes are streamed out.
+template <typename T, int H>
+__device__ __forceinline__ void dropout_chunk(float2 (&t)[H], const RowParams& p, unsigned long long seed,
+                                              unsigned long long offset, unsigned long long lin) {
+  constexpr int VEC = 2 * H;
+  uint32_t bytes[VEC / 4];
+#pragma unroll
+  for (int q = 0; q < VEC / 4; ++q) {
+    const uint4 r = philox4x32_10(seed, (lin >> 2) + (unsigned long long)q, offset);
+    const bool k0 = dropout_keep_word(r.x, p.drop_t1, p.drop_t2), k1 = dropout_keep_word(r.y, p.drop_t1, p.drop_t2);
+    const bool k2 = dropout_keep_word(r.z, p.drop_t1, p.drop_t2), k3 = dropout_keep_word(r.w, p.drop_t1, p.drop_t2);
+    t[2 * q].x = k0 ? t[2 * q].x * p.drop_scale : 0.f;
+    t[2 * q].y = k1 ? t[2 * q].y * p.drop_scale : 0.f;
+    t[2 * q + 1].x = k2 ? t[2 * q + 1].x * p.drop_scale : 0.f;
+    t[2 * q + 1].y = k3 ? t[2 * q + 1].y * p.drop_scale : 0.f;
+    bytes[q] = (k0 ? 1u : 0u) | (k1 ? 0x100u : 0u) | (k2 ? 0x10000u : 0u) | (k3 ? 0x1000000u : 0u);
+  }
+  uint8_t* dst = p.mask_out + lin;
+  if constexpr (VEC == 8) {
+    asm volatile("st.global.cs.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(bytes[0]), "r"(bytes[1]) : "memory");
+  } else {
+    asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(dst), "r"(bytes[0]) : "memory");
   }
 }
 

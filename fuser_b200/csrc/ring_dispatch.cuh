@@ -22,6 +22,10 @@ RingKernel ring_add_kernel_f16(int op, int tpr, int ch, bool psmem);
 RingKernel ring_bwd_kernel_f32(int op, int tpr, int ch, bool cached, bool centered);
 RingKernel ring_bwd_kernel_bf16(int op, int tpr, int ch, bool cached, bool centered);
 RingKernel ring_bwd_kernel_f16(int op, int tpr, int ch, bool cached, bool centered);
+// fused-dropout backward (cached form): dy | x | residual | mask per stage, two gradient outputs
+RingKernel ring_bwd_drop_kernel_f32(int op, int tpr, int ch);
+RingKernel ring_bwd_drop_kernel_bf16(int op, int tpr, int ch);
+RingKernel ring_bwd_drop_kernel_f16(int op, int tpr, int ch);
 // pipelined re-read backward (split-phase reductions overlapped across rows): ch in {3,4}, tpr in {64..512};
 // lean: RMSNorm without the centring term on the instruction-trimmed kernel (tpr 256 / 512)
 RingKernel ring_bwd_pipe_kernel_f32(int op, int tpr, int ch, bool lean);

@@ -60,4 +60,25 @@ RingKernel ring_bwd_kernel_for(int op, int tpr, int ch, bool cached, bool center
   }
 }
 
+// fused-dropout backward (cached form; the (tpr, ch) pairs of the cached table above)
+template <typename T, bool LN>
+RingKernel ring_bwd_drop_kernel_sel(int tpr, int ch) {
+  switch (tpr) {
+    case 32:
+      if (ch == 1) return norm_bwd_ring_kernel<T, 32, 1, LN, true, true, true>;
+      if (ch == 2) return norm_bwd_ring_kernel<T, 32, 2, LN, true, true, true>;
+      return nullptr;
+    case 64: return ch == 2 ? norm_bwd_ring_kernel<T, 64, 2, LN, true, true, true> : nullptr;
+    case 128: return ch == 2 ? norm_bwd_ring_kernel<T, 128, 2, LN, true, true, true> : nullptr;
+    case 256: return ch == 2 ? norm_bwd_ring_kernel<T, 256, 2, LN, true, true, true> : nullptr;
+    case 512: return ch == 2 ? norm_bwd_ring_kernel<T, 512, 2, LN, true, true, true> : nullptr;
+    default: return nullptr;
+  }
+}
+template <typename T>
+RingKernel ring_bwd_drop_kernel_for(int op, int tpr, int ch) {
+  return op == B200NORM_OP_LAYERNORM_BWD ? ring_bwd_drop_kernel_sel<T, true>(tpr, ch)
+                                         : ring_bwd_drop_kernel_sel<T, false>(tpr, ch);
+}
+
 }  // namespace b200norm

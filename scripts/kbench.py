@@ -26,7 +26,10 @@ def algbytes(op, m, n, s):
             "copy": s * 2 * m * n, "red_sum": s * (m * n + m), "red_max": s * (m * n + m), "colsum": s * (m * n + n),
             "var_mean": s * m * n + 8 * m, "rms_fwd": s * (2 * m * n + n) + 4 * m, "ln_fwd": s * 2 * (m * n + n) + 8 * m, "sm_fwd": s * 2 * m * n, "osm_fwd": s * 2 * m * n, "onorm_fwd": s * 2 * (m * n + n) + 8 * n, "onorm_bwd": s * 3 * (m * n + n) + 8 * n, "osm_bwd": s * 3 * m * n,
             "sm_bwd": s * 3 * m * n, "rms_bwd": s * (3 * m * n + 2 * n) + 4 * m, "rms_bwd_dx": s * (3 * m * n + 2 * n) + 4 * m,
-            "ln_bwd": s * 3 * (m * n + n) + 8 * m, "ln_bwd_dx": s * 3 * (m * n + n) + 8 * m}[op]
+            "ln_bwd": s * 3 * (m * n + n) + 8 * m, "ln_bwd_dx": s * 3 * (m * n + n) + 8 * m,
+            # fused dropout (dropout_{layernorm,rmsnorm}_{fwd,bwd}_iobytes): + residual, + the bool mask, + d residual
+            "drop_ln_fwd": s * (3 * m * n + 2 * n) + 8 * m + m * n, "drop_rms_fwd": s * (3 * m * n + n) + 4 * m + m * n,
+            "drop_ln_bwd": s * (5 * m * n + 3 * n) + 8 * m + m * n, "drop_rms_bwd": s * (5 * m * n + 2 * n) + 4 * m + m * n}[op]
 
 
 def main():
@@ -67,6 +70,11 @@ def main():
                 aux["osm"] = [torch.softmax(x.float(), 0).to(dtype) for x in xs]
             if op == "onorm_bwd" and "onorm" not in aux:
                 aux["onorm"] = [ops.outer_norm_fwd(x, w, w, 1e-5)[1:] for x in xs]
+            if op.startswith("drop_") and "drop" not in aux:
+                rng = ops.philox_state(17, 0, dev)
+                aux["rng"] = rng
+                aux["drop"] = [ops.dropout_layer_norm_fwd(x, dy, w, w, 1e-5, 0.2, rng) for x, dy in zip(xs, dys)]
+                aux["droprms"] = [ops.dropout_rms_norm_fwd(x, dy, w, 1e-5, 0.2, rng) for x, dy in zip(xs, dys)]
             if op == "copy" and "out" not in aux:
                 aux["out"] = torch.empty_like(xs[0])
             fns = {
@@ -87,6 +95,12 @@ def main():
                 "sm_bwd": lambda i: ops.softmax_bwd(dys[i], aux["sm"][i]),
                 "rms_bwd": lambda i: ops.rms_norm_bwd(dys[i], xs[i], aux["rms"][i], w),
                 "rms_bwd_dx": lambda i: ops.rms_norm_bwd(dys[i], xs[i], aux["rms"][i], w, (True, False)),
+                "drop_ln_fwd": lambda i: ops.dropout_layer_norm_fwd(xs[i], dys[i], w, w, 1e-5, 0.2, aux["rng"]),
+                "drop_rms_fwd": lambda i: ops.dropout_rms_norm_fwd(xs[i], dys[i], w, 1e-5, 0.2, aux["rng"]),
+                "drop_ln_bwd": lambda i: ops.dropout_layer_norm_bwd(dys[(i + 1) % nsets], xs[i], dys[i], aux["drop"][i][3],
+                                                                    aux["drop"][i][1], aux["drop"][i][2], w, 0.2),
+                "drop_rms_bwd": lambda i: ops.dropout_rms_norm_bwd(dys[(i + 1) % nsets], xs[i], dys[i], aux["droprms"][i][2],
+                                                                   aux["droprms"][i][1], w, 0.2),
                 "ln_bwd": lambda i: ops.layer_norm_bwd(dys[i], xs[i], aux["ln"][i][0], aux["ln"][i][1], w),
                 "ln_bwd_dx": lambda i: ops.layer_norm_bwd(dys[i], xs[i], aux["ln"][i][0], aux["ln"][i][1], w,
                                                           (True, False, False)),
