@@ -60,7 +60,7 @@ class FusionDefinition:
 
     Supported surface (what the hot path's fusions use): ``define_tensor``, ``define_scalar``,
     ``add_output``, ``fd.ops.{cast, add, sub, mul, div, neg, pow, exp, log, sqrt, rsqrt, reciprocal,
-    sum, max, var_mean, welford, broadcast, broadcast_in_dim}``, ``Tensor.shape()/size()``.
+    sum, max, var_mean, welford, broadcast, broadcast_in_dim, uniform, lt}``, ``Tensor.shape()/size()``.
     """
 
     def __init__(self):
@@ -71,6 +71,7 @@ class FusionDefinition:
         self.ops = Ops(self)
         self._match: Optional[Match] = None
         self._match_error: Optional[Exception] = None
+        self._last_rng = None
         self._defined = False
 
     # -- context manager (python/nvfuser_direct/__init__.py:165-204) ------------------------------
@@ -135,12 +136,14 @@ class FusionDefinition:
     def _check_output_dtypes(self, m: Match):
         for node, role in zip(self._outputs, m.outputs):
             want = DataType.Float if role in ("mean", "invstd", "rms", "var", "m2") else m.io_dtype
+            if role == "mask":
+                want = DataType.Bool
             if node.dtype != want:
                 raise Unmatchable(f"output '{role}' has dtype {node.dtype.name}; the kernels produce {want.name}")
 
     # -- execution (python/nvfuser_direct/__init__.py:319-376) -----------------------------------
     def execute(self, inputs, *, device=None, save_repro_inputs=False, _enable_options: list[str] = [],
-                _disable_options: list[str] = []) -> list[torch.Tensor]:
+                _disable_options: list[str] = [], _rng=None) -> list[torch.Tensor]:
         if not self._outputs:
             raise NotImplementedError("Fusion is empty!")
         m = self.segment()
@@ -163,9 +166,13 @@ class FusionDefinition:
             kw["variant"] = L.VARIANT_GENERIC
         res: dict = {}
         want = set(m.outputs)
-        if m.flags & L.F_ADD_RESIDUAL:  # norm(x + residual), optional sum output
+        if m.flags & L.F_DROPOUT:
+            res = self._execute_dropout(m, r, want, kw, _rng)
+        elif m.flags & L.F_ADD_RESIDUAL:  # norm(x + residual), optional sum output
             kw.update(residual=r["r"], want_sum="sum" in want, round_sum=bool(m.flags & L.F_ROUND_SUM))
-        if m.op == L.OP_LAYERNORM_FWD and m.flags & L.F_NO_Y:  # stand-alone var_mean / welford
+        if m.flags & L.F_DROPOUT:
+            pass
+        elif m.op == L.OP_LAYERNORM_FWD and m.flags & L.F_NO_Y:  # stand-alone var_mean / welford
             if m.flags & L.F_STAT_M2:
                 avg, m2 = K.welford(r["x"], **kw)
                 res = {"mean": avg, "m2": m2}
@@ -215,6 +222,41 @@ class FusionDefinition:
                 t = t.squeeze(-1)
             outs.append(t)
         return outs
+
+    def last_rng(self):
+        """(seed, offset) handed to the kernels by the last execute() of a fusion with uniform()."""
+        return self._last_rng
+
+    def _execute_dropout(self, m: Match, r: dict, want: set, kw: dict, rng):
+        """norm(residual + dropout(x)) and its backward. Forward: the Philox arguments are the reference's — seed of
+        the default CUDA generator, offset = its offset / 4 (+ the RNG op's index, 0 here), and the generator moves on
+        by 4 per launch (csrc/rng.cpp:55-67,73-81)."""
+        keep = m.dropout_keep
+        if m.op in (L.OP_LAYERNORM_FWD, L.OP_RMSNORM_FWD):
+            dev = r["x"].device
+            if rng is None:
+                gen = torch.cuda.default_generators[dev.index if dev.index is not None else torch.cuda.current_device()]
+                off = int(gen.get_offset())
+                rng = (int(gen.initial_seed()), off // 4)
+                gen.set_offset(off + 4)
+            self._last_rng = (int(rng[0]), int(rng[1]))
+            state = K.philox_state(self._last_rng[0], self._last_rng[1], dev)
+            if m.op == L.OP_LAYERNORM_FWD:
+                o = K.dropout_layer_norm_fwd(r["x"], r["r"], r.get("w"), r.get("b"), m.eps, 0.0, state, keep=keep,
+                                             want_sum="sum" in want, **kw)
+                return {"y": o[0], "mean": o[1], "invstd": o[2], "mask": o[3], "sum": o[4] if len(o) > 4 else None}
+            y, stat, mask = K.dropout_rms_norm_fwd(r["x"], r["r"], r.get("w"), m.eps, 0.0, state, keep=keep,
+                                                   stat_is_rms=bool(m.flags & L.F_STAT_IS_RMS), **kw)
+            return {"y": y, "rms": stat, "invstd": stat, "mask": mask}
+        want_dx = "dx" in want or "dres" in want
+        if m.op == L.OP_LAYERNORM_BWD:
+            dx, dres, dw, db = K.dropout_layer_norm_bwd(r["dy"], r["x"], r["r"], r["mask"], r["mean"], r["stat"], r.get("w"), 0.0,
+                                                        (want_dx, "dw" in want, "db" in want), keep=keep, **kw)
+            return {"dx": dx, "dres": dres, "dw": dw, "db": db}
+        dx, dres, dw = K.dropout_rms_norm_bwd(r["dy"], r["x"], r["r"], r["mask"], r["stat"], r.get("w"), 0.0,
+                                              stat_is_rms=bool(m.flags & L.F_STAT_IS_RMS),
+                                              output_mask=(want_dx, "dw" in want), keep=keep, **kw)
+        return {"dx": dx, "dres": dres, "dw": dw}
 
     # -- validation (python/nvfuser_direct/__init__.py:539-645) ---------------------------------
     def reduction_sizes(self, inputs) -> list[int]:

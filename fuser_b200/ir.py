@@ -231,6 +231,30 @@ class Ops:
     def truediv(self, a, b): return self._binary("div", a, b)
     def pow(self, a, b): return self._binary("pow", a, b)
 
+    # -- random numbers / comparisons (the dropout prologue) -----------------
+    def uniform(self, minval, maxval, shape: Sequence, dtype: DataType = DataType.Float, rng_seed=None, rng_offset=None):
+        """ops.uniform (python_direct/ops.cpp random ops): a tensor of ``shape`` drawn from U[minval, maxval) with the
+        Philox stream of the run (csrc/rng.cpp). Only the [0, 1) Float flavour feeding a dropout mask is on the hot
+        path; the shape entries are extents of input tensors (``T.shape()``)."""
+        fd = self._fd
+        if rng_seed is not None or rng_offset is not None:
+            raise ValueError("uniform: explicit rng_seed / rng_offset are not supported (the stream comes from the CUDA generator)")
+        lo, hi = self._scalar(minval), self._scalar(maxval)
+        dims = []
+        for s_ in shape:
+            if isinstance(s_, Scalar) and s_.dim is not None:
+                dims.append(s_.dim)
+            else:
+                raise ValueError("uniform: the shape must be extents of input tensors")
+        return Tensor(fd, "uniform", [lo, hi], {}, dtype, dims)
+
+    def lt(self, a, b):
+        """Element-wise a < b -> Bool."""
+        r = self._binary("lt", a, b)
+        if isinstance(r, Tensor):
+            r.dtype = DataType.Bool
+        return r
+
     # -- reductions --------------------------------------------------------
     def _reduce(self, name, arg: Tensor, dims, keepdim, dtype):
         if not isinstance(arg, Tensor):

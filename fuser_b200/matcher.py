@@ -154,6 +154,9 @@ class Canon:
             return self.axes_of_key[atom[2]] - atom[1]
         if kind in ("exp", "log", "expr"):
             return self.axes_of_key[atom[1]]
+        if kind == "keep":  # the dropout mask uniform() < keep: spans the axes of the uniform tensor
+            t = self.fd._vals[atom[1]]
+            return frozenset(self.cls(d) for d in t.dims if d is not None)
         raise KeyError(kind)
 
     def poly_axes(self, p: Poly) -> frozenset:
@@ -243,6 +246,14 @@ class Canon:
             return Poly.atom(("in", t.id))
         if op in ("cast", "broadcast", "broadcast_in_dim"):
             return self.value(t.args[0])
+        if op == "lt":
+            # only as the dropout mask: uniform(0, 1) < constant (benchmarks/python/test_dropout_layernorm_fwd.py:38-41)
+            u, c = t.args
+            if (isinstance(u, Tensor) and u.op == "uniform" and isinstance(c, Scalar) and c.value is not None
+                    and isinstance(u.args[0], Scalar) and isinstance(u.args[1], Scalar)
+                    and u.args[0].value == 0.0 and u.args[1].value == 1.0 and u.dtype == DataType.Float):
+                return Poly.atom(("keep", u.id))
+            raise Unmatchable("lt outside a dropout mask")
         if op == "neg":
             return -self.value(t.args[0])
         if op == "reciprocal":
@@ -427,6 +438,7 @@ class Match:
     outputs: list              # per fusion output: role name (y, mean, invstd, rms, dx, dw, db)
     norm_ndim: int = 1
     correction: int = 0        # var_mean (F_STAT_VAR)
+    dropout_keep: float = 1.0  # F_DROPOUT: the keep probability 1 - p (the fusion's double scalar)
     description: str = ""
     notes: list = field(default_factory=list)
 
@@ -515,6 +527,10 @@ def match_fusion(fd) -> Match:
     if col_cls in row_cls:
         raise Unmatchable("square symbolic shapes: rows and cols were unified")
     mats = [(i, t) for i, t in mats if t.ndim == nd and tuple(cls(d) for d in t.dims) == row_cls + (col_cls,)]
+    masks = [(i, t) for i, t in mats if t.dtype == DataType.Bool]  # a saved dropout mask (backward)
+    mats = [(i, t) for i, t in mats if t.dtype != DataType.Bool]
+    if not mats:
+        raise Unmatchable("no [rows, cols] input")
     vecs = [(i, t) for i, t in tin if t.ndim == 1 and cls(t.dims[0]) == col_cls]
     io0 = mats[0][1].dtype
     # fp32 per-COLUMN statistics next to reduced-precision activations (saved mean / invstd of the outer
@@ -524,7 +540,7 @@ def match_fusion(fd) -> Match:
     stats = [(i, t) for i, t in tin
              if (t.ndim == nd - 1 and tuple(cls(d) for d in t.dims) == row_cls)
              or (t.ndim == nd and t.dims[-1] is None and tuple(cls(d) for d in t.dims[:-1]) == row_cls)]
-    used = {i for i, _ in mats} | {i for i, _ in vecs} | {i for i, _ in stats} | {i for i, _ in cstats}
+    used = {i for i, _ in mats} | {i for i, _ in vecs} | {i for i, _ in stats} | {i for i, _ in cstats} | {i for i, _ in masks}
     if len(used) != len(tin):
         raise Unmatchable("an input is neither [rows, cols], [cols] nor a per-row statistic")
     io = mats[0][1].dtype
@@ -645,6 +661,100 @@ def match_fusion(fd) -> Match:
                     return Match(L.OP_LAYERNORM_FWD, flags, eps, io, roles, names,
                                  description="batch_norm forward (statistics over the outer axes, channels last)")
         raise Unmatchable("single-input fusion is not rms_norm / layer_norm / softmax")
+
+    # ---- fused dropout (benchmarks/python/test_dropout_{layernorm,rmsnorm}_{fwd,bwd}.py) ----
+    keep_nodes = [v for v in fd._vals if isinstance(v, Tensor) and v.op == "lt" and isinstance(v.args[0], Tensor)
+                  and v.args[0].op == "uniform"]
+    if keep_nodes:
+        if len(keep_nodes) != 1 or masks or n_m != 2 or n_s != 0 or n_v > 2:
+            raise Unmatchable("dropout: one mask over norm(residual + dropout(x)) expected")
+        knode = keep_nodes[0]
+        keep = float(knode.args[1].value)
+        if not (0.0 < keep <= 1.0):
+            raise Unmatchable(f"dropout keep probability {keep}")
+        dflags = L.F_ADD_RESIDUAL | L.F_DROPOUT
+        for x, res in ((mats[0], mats[1]), (mats[1], mats[0])):
+            def with_drop(build):
+                s_ = ops.add(T(res), ops.mul(ops.mul(T(x), ops.cast(knode, DataType.Float)), 1.0 / keep))
+                out = build(s_)
+                out["sum"] = s_
+                out["mask"] = knode
+                return out
+
+            for eps in eps_list:
+                e = ops._scalar(float(eps))
+                if n_v <= 1:
+                    w = vecs[0] if n_v == 1 else None
+                    names = try_candidate(lambda: with_drop(lambda s_: def_rms_norm_fwd(ops, s_, T(w) if w else None, e)), {})
+                    if names and "y" in names:
+                        if "rms" in names and "invstd" in names:
+                            raise Unmatchable("both rms and invstd requested")
+                        flags = dflags | (L.F_HAS_WEIGHT if w else 0) | (L.F_STAT_IS_RMS if "rms" in names else 0)
+                        flags |= L.F_OUT_SUM if "sum" in names else 0
+                        roles = {"x": I(x), "r": I(res)}
+                        if w:
+                            roles["w"] = I(w)
+                        return Match(L.OP_RMSNORM_FWD, flags, eps, io, roles, names, dropout_keep=keep,
+                                     description="rms_norm(residual + dropout(x))")
+                combos = [(None, None)]
+                if n_v == 1:
+                    combos = [(vecs[0], None)]
+                elif n_v == 2:
+                    combos = [(vecs[0], vecs[1]), (vecs[1], vecs[0])]
+                for w, b in combos:
+                    names = try_candidate(lambda: with_drop(
+                        lambda s_: def_layer_norm_fwd(ops, s_, T(w) if w else None, T(b) if b else None, e)), {})
+                    if names and "y" in names:
+                        flags = dflags | (L.F_HAS_WEIGHT if w else 0) | (L.F_HAS_BIAS if b else 0)
+                        flags |= L.F_OUT_SUM if "sum" in names else 0
+                        roles = {"x": I(x), "r": I(res)}
+                        if w:
+                            roles["w"] = I(w)
+                        if b:
+                            roles["b"] = I(b)
+                        return Match(L.OP_LAYERNORM_FWD, flags, eps, io, roles, names, dropout_keep=keep,
+                                     description="layer_norm(residual + dropout(x))")
+        raise Unmatchable("a dropout mask outside norm(residual + dropout(x))")
+    if masks:
+        # backward: dy, x (dropped branch), residual + the saved mask; the scale 1 / keep is one of the constants
+        if len(masks) != 1 or n_m != 3 or n_v > 1 or n_s not in (1, 2):
+            raise Unmatchable("dropout backward: dy, x, residual, one mask and the saved statistics expected")
+        mk = masks[0]
+        w = vecs[0] if n_v == 1 else None
+        scales = sorted({float(v.value) for v in fd._vals if isinstance(v, Scalar) and v.value is not None and v.dim is None
+                         and isinstance(v.value, float) and 1.0 <= float(v.value) <= 1e6 and float(v.value) not in (2.0, 3.0)})
+        for scale in scales:
+            for dy_, x_, r_ in itertools.permutations(mats):
+                def with_drop_bwd(mean, st, stat_is_rms, centered, half):
+                    mf = ops.cast(mk[1], DataType.Float)
+                    xe = ops.add(T(r_), ops.mul(ops.mul(T(x_), mf), scale))
+                    out = def_norm_bwd(ops, T(dy_), xe, mean, st, T(w) if w else None, stat_is_rms, centered, half)
+                    out["dres"] = out["dx"]
+                    out["dx"] = ops.mul(ops.mul(out["dres"], scale), mf)
+                    return out
+
+                if n_s == 1:
+                    for stat_is_rms, centered in ((True, False), (False, False), (True, True), (False, True)):
+                        names = try_candidate(lambda: with_drop_bwd(None, T(stats[0]), stat_is_rms, centered, False), {})
+                        if names and "db" not in names and ("dx" in names or "dres" in names):
+                            flags = L.F_DROPOUT | (L.F_HAS_WEIGHT if w else 0) | (L.F_STAT_IS_RMS if stat_is_rms else 0)
+                            flags |= L.F_RMS_BWD_CENTERED if centered else 0
+                            roles = {"dy": I(dy_), "x": I(x_), "r": I(r_), "mask": I(mk), "stat": I(stats[0])}
+                            if w:
+                                roles["w"] = I(w)
+                            return Match(L.OP_RMSNORM_BWD, flags, 0.0, io, roles, names, dropout_keep=1.0 / scale,
+                                         description="backward of rms_norm(residual + dropout(x))")
+                else:
+                    for mean, st in ((stats[0], stats[1]), (stats[1], stats[0])):
+                        names = try_candidate(lambda: with_drop_bwd(T(mean), T(st), False, True, False), {})
+                        if names and ("dx" in names or "dres" in names):
+                            flags = L.F_DROPOUT | (L.F_HAS_WEIGHT if w else 0)
+                            roles = {"dy": I(dy_), "x": I(x_), "r": I(r_), "mask": I(mk), "mean": I(mean), "stat": I(st)}
+                            if w:
+                                roles["w"] = I(w)
+                            return Match(L.OP_LAYERNORM_BWD, flags, 0.0, io, roles, names, dropout_keep=1.0 / scale,
+                                         description="backward of layer_norm(residual + dropout(x))")
+        raise Unmatchable("a Bool matrix input outside a dropout backward")
 
     # ---- forward norms with a fused residual add: two matrix inputs, no statistics ----
     if n_m == 2 and n_s == 0 and n_v <= 2:

@@ -287,14 +287,19 @@ def philox_state(seed: int, offset: int, device) -> torch.Tensor:
     return torch.tensor([to_i64(seed & ((1 << 64) - 1)), to_i64(offset & ((1 << 64) - 1))], dtype=torch.int64, device=device)
 
 
+def _keep(p: float, keep) -> float:
+    """The keep probability as the fusion's own double (1 - p as the definition computed it) when given."""
+    return float(keep) if keep is not None else 1.0 - float(p)
+
+
 def dropout_layer_norm_fwd(x, residual, weight, bias, eps: float, p: float, rng: torch.Tensor, *, want_sum=False,
-                           variant=L.VARIANT_AUTO, cluster_size=0):
+                           keep=None, variant=L.VARIANT_AUTO, cluster_size=0):
     """y, mean, invstd, mask (and the sum with ``want_sum``) of layer_norm(residual + dropout(x, p)); ``rng`` is
     :func:`philox_state`. mask is the bool tensor the backward takes."""
     flags = (L.F_HAS_WEIGHT if weight is not None else 0) | (L.F_HAS_BIAS if bias is not None else 0)
     flags |= L.F_OUT_MEAN | L.F_OUT_INVSTD | L.F_ADD_RESIDUAL | L.F_DROPOUT | (L.F_OUT_SUM if want_sum else 0)
     ins = [x, residual] + [t for t in (weight, bias) if t is not None] + [rng]
-    outs = iter(_run(L.OP_LAYERNORM_FWD, flags, eps, variant, cluster_size, ins, dropout_keep=1.0 - p))
+    outs = iter(_run(L.OP_LAYERNORM_FWD, flags, eps, variant, cluster_size, ins, dropout_keep=_keep(p, keep)))
     y = next(outs)
     s = next(outs) if want_sum else None
     mean, invstd, mask = next(outs), next(outs), next(outs)
@@ -302,23 +307,23 @@ def dropout_layer_norm_fwd(x, residual, weight, bias, eps: float, p: float, rng:
 
 
 def dropout_rms_norm_fwd(x, residual, weight, eps: float, p: float, rng: torch.Tensor, *, stat_is_rms=True,
-                         variant=L.VARIANT_AUTO, cluster_size=0):
+                         keep=None, variant=L.VARIANT_AUTO, cluster_size=0):
     """y, stat, mask of rms_norm(residual + dropout(x, p)); stat = rms (the benchmark's spelling) or invstd."""
     flags = (L.F_HAS_WEIGHT if weight is not None else 0) | (L.F_STAT_IS_RMS if stat_is_rms else 0)
     flags |= L.F_ADD_RESIDUAL | L.F_DROPOUT
     ins = [x, residual] + ([weight] if weight is not None else []) + [rng]
-    y, stat, mask = _run(L.OP_RMSNORM_FWD, flags, eps, variant, cluster_size, ins, dropout_keep=1.0 - p)
+    y, stat, mask = _run(L.OP_RMSNORM_FWD, flags, eps, variant, cluster_size, ins, dropout_keep=_keep(p, keep))
     return y, stat, mask
 
 
 def dropout_layer_norm_bwd(dy, x, residual, mask, mean, invstd, weight, p: float,
-                           output_mask=(True, True, True), *, variant=L.VARIANT_AUTO, cluster_size=0):
+                           output_mask=(True, True, True), *, keep=None, variant=L.VARIANT_AUTO, cluster_size=0):
     """dx (grad of the dropped branch), dresidual, dweight, dbias of layer_norm(residual + dropout(x, p))."""
     want_dx, want_dw, want_db = output_mask
     flags = (L.F_HAS_WEIGHT if weight is not None else 0) | L.F_DROPOUT
     flags |= (L.F_OUT_DX if want_dx else 0) | (L.F_OUT_DW if want_dw else 0) | (L.F_OUT_DB if want_db else 0)
     ins = [dy, x, mean, invstd] + ([weight] if weight is not None else []) + [residual, mask]
-    outs = iter(_run(L.OP_LAYERNORM_BWD, flags, 0.0, variant, cluster_size, ins, dropout_keep=1.0 - p))
+    outs = iter(_run(L.OP_LAYERNORM_BWD, flags, 0.0, variant, cluster_size, ins, dropout_keep=_keep(p, keep)))
     dx = next(outs) if want_dx else None
     dres = next(outs) if want_dx else None
     dw = next(outs) if want_dw else None
@@ -327,13 +332,13 @@ def dropout_layer_norm_bwd(dy, x, residual, mask, mean, invstd, weight, p: float
 
 
 def dropout_rms_norm_bwd(dy, x, residual, mask, stat, weight, p: float, *, stat_is_rms=True,
-                         output_mask=(True, True), variant=L.VARIANT_AUTO, cluster_size=0):
+                         output_mask=(True, True), keep=None, variant=L.VARIANT_AUTO, cluster_size=0):
     """dx, dresidual, dweight of rms_norm(residual + dropout(x, p)) (textbook form, as the benchmark traces it)."""
     want_dx, want_dw = output_mask
     flags = (L.F_HAS_WEIGHT if weight is not None else 0) | (L.F_STAT_IS_RMS if stat_is_rms else 0) | L.F_DROPOUT
     flags |= (L.F_OUT_DX if want_dx else 0) | (L.F_OUT_DW if want_dw else 0)
     ins = [dy, x, stat] + ([weight] if weight is not None else []) + [residual, mask]
-    outs = iter(_run(L.OP_RMSNORM_BWD, flags, 0.0, variant, cluster_size, ins, dropout_keep=1.0 - p))
+    outs = iter(_run(L.OP_RMSNORM_BWD, flags, 0.0, variant, cluster_size, ins, dropout_keep=_keep(p, keep)))
     dx = next(outs) if want_dx else None
     dres = next(outs) if want_dx else None
     dw = next(outs) if want_dw else None

@@ -17,13 +17,21 @@ import torch
 from fuser_b200.ir import DataType, Scalar, Tensor, nvfuser_dtype_to_torch
 
 
-def evaluate(fd, inputs, device="cpu"):
-    """Return the fusion's outputs computed node by node with ATen on ``device``."""
+def evaluate(fd, inputs, device="cpu", rng=None):
+    """Return the fusion's outputs computed node by node with ATen on ``device``. ``rng`` = (seed, offset) of the
+    Philox stream a ``uniform`` node draws from (the arguments the reference hands its kernels: csrc/rng.cpp)."""
     env: dict[int, object] = {}
     it = iter(inputs)
     for node in fd._inputs:
         v = next(it)
         env[node.id] = v.to(device) if isinstance(v, torch.Tensor) else v
+
+    ext = {}
+    for node, t in zip(fd._inputs, inputs):
+        if isinstance(t, torch.Tensor) and hasattr(node, "dims"):
+            for ax, d in enumerate(node.dims):
+                if d is not None:
+                    ext[fd._uf.find(d)] = int(t.shape[ax])
 
     def val(n):
         if n.id in env:
@@ -46,6 +54,23 @@ def evaluate(fd, inputs, device="cpu"):
                     "rsqrt": lambda: a[0] ** -0.5, "add": lambda: a[0] + a[1], "sub": lambda: a[0] - a[1],
                     "mul": lambda: a[0] * a[1], "div": lambda: a[0] / a[1], "pow": lambda: a[0] ** a[1]}[op]()
         a = [val(x) for x in n.args]
+        if op == "uniform":
+            from oracle import aten_oracle as AO
+            import numpy as np
+
+            if rng is None:
+                raise ValueError("a fusion with uniform() needs rng=(seed, offset)")
+            if float(a[0]) != 0.0 or float(a[1]) != 1.0:
+                raise NotImplementedError("uniform(minval, maxval) other than [0, 1)")
+            shape = [ext[fd._uf.find(d)] for d in n.dims]
+            numel = int(np.prod(shape))
+            w = np.stack(AO.philox4x32_10(rng[0], np.arange((numel + 3) // 4, dtype=np.uint64), rng[1]), axis=1).reshape(-1)[:numel]
+            return torch.from_numpy(AO.uniformf(w)).view(*shape).to(device)
+        if op == "lt":
+            x, y = a
+            if isinstance(x, torch.Tensor) and not isinstance(y, torch.Tensor):
+                return x.double() < float(y) if x.dtype == torch.float32 else x < y  # float tensor against a double scalar
+            return x < y
         if op == "cast":
             return a[0].to(nvfuser_dtype_to_torch(n.attrs["dtype"]))
         if op == "neg":

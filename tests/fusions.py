@@ -436,3 +436,148 @@ def var_mean_py(fd, dtype, correction=1):
     var, mean = fd.ops.var_mean(_up(fd, x, dtype), dims=[1], correction=correction, keepdim=False)
     fd.add_output(var)
     fd.add_output(mean)
+
+
+# ---------------------------------------------------------------------------
+# fused dropout: norm(input2 + dropout(input1)) and the backward
+# (the op sequences of benchmarks/python/test_dropout_{layernorm,rmsnorm}_{fwd,bwd}.py)
+# ---------------------------------------------------------------------------
+def _dropout_sum(fd, dtype, p, x1, x2, mask_f):
+    """input2 + (input1 * mask) * 1 / (1 - p), in Float."""
+    scale = fd.define_scalar(1 / (1 - p), dtype=DataType.Double)
+    return fd.ops.add(x2, fd.ops.mul(fd.ops.mul(x1, mask_f), scale)), scale
+
+
+def _draw_mask(fd, like, p):
+    lo = fd.define_scalar(0.0, dtype=DataType.Double)
+    hi = fd.define_scalar(1.0, dtype=DataType.Double)
+    u = fd.ops.uniform(lo, hi, shape=like.shape(), dtype=DataType.Float)
+    keep = fd.ops.lt(u, fd.define_scalar(1 - p, dtype=DataType.Double))
+    return keep, fd.ops.cast(keep, dtype=DataType.Float)
+
+
+def dropout_layernorm_fwd_py(fd, dtype, p=0.2, eps=1e-5):
+    """inputs: input1, input2, weights, bias; outputs: y, mean, invstd, mask (test_dropout_layernorm_fwd.py:19-78)."""
+    x1 = fd.define_tensor(shape=[-1, -1], contiguity=[True, True], dtype=dtype, is_cpu=False)
+    x2 = fd.define_tensor(shape=[-1, -1], contiguity=[True, True], dtype=dtype, is_cpu=False)
+    w = fd.define_tensor(shape=[-1], contiguity=[True], dtype=dtype, is_cpu=False)
+    b = fd.define_tensor(shape=[-1], contiguity=[True], dtype=dtype, is_cpu=False)
+    keep, keep_f = _draw_mask(fd, x1, p)
+    x1f, x2f, wf, bf = (_up(fd, t, dtype) for t in (x1, x2, w, b))
+    s, _ = _dropout_sum(fd, dtype, p, x1f, x2f, keep_f)
+    var, mean = fd.ops.var_mean(s, dims=[1], correction=0, keepdim=False)
+    var_b = fd.ops.broadcast_in_dim(var, shape=[x1.size(0), 1], broadcast_dims=[0])
+    mean_b = fd.ops.broadcast_in_dim(mean, shape=[x1.size(0), 1], broadcast_dims=[0])
+    invstd = fd.ops.rsqrt(fd.ops.add(var_b, fd.define_scalar(eps, dtype=DataType.Double)))
+    xc = fd.ops.sub(s, fd.ops.broadcast_in_dim(mean_b, shape=x1.shape(), broadcast_dims=[0, 1]))
+    xh = fd.ops.mul(xc, fd.ops.broadcast_in_dim(invstd, shape=x1.shape(), broadcast_dims=[0, 1]))
+    y = fd.ops.mul(xh, fd.ops.broadcast_in_dim(wf, shape=x1.shape(), broadcast_dims=[1]))
+    y = fd.ops.add(y, fd.ops.broadcast_in_dim(bf, shape=x1.shape(), broadcast_dims=[1]))
+    fd.add_output(_down(fd, y, dtype))
+    fd.add_output(mean)
+    fd.add_output(invstd)
+    fd.add_output(keep)
+
+
+def dropout_rmsnorm_fwd_py(fd, dtype, p=0.2, eps=1e-5):
+    """inputs: input1, input2, weights; outputs: y, mask, rms (test_dropout_rmsnorm_fwd.py:19-82)."""
+    x1 = fd.define_tensor(shape=[-1, -1], contiguity=[True, True], dtype=dtype, is_cpu=False)
+    x2 = fd.define_tensor(shape=[-1, -1], contiguity=[True, True], dtype=dtype, is_cpu=False)
+    w = fd.define_tensor(shape=[-1], contiguity=[True], dtype=dtype, is_cpu=False)
+    keep, keep_f = _draw_mask(fd, x1, p)
+    x1f, wf, x2f = (_up(fd, t, dtype) for t in (x1, w, x2))
+    s, _ = _dropout_sum(fd, dtype, p, x1f, x2f, keep_f)
+    sq = fd.ops.sum(fd.ops.pow(s, fd.define_scalar(2.0, dtype=DataType.Double)), dims=[1], keepdim=False, dtype=DataType.Null)
+    sq_b = fd.ops.broadcast_in_dim(sq, shape=[x1.size(0), 1], broadcast_dims=[0])
+    ms = fd.ops.mul(sq_b, fd.ops.reciprocal(x1.size(1)))
+    rms = fd.ops.sqrt(fd.ops.add(ms, fd.define_scalar(eps, dtype=DataType.Double)))
+    xh = fd.ops.mul(s, fd.ops.reciprocal(fd.ops.broadcast_in_dim(rms, shape=x1.shape(), broadcast_dims=[0, 1])))
+    y = fd.ops.mul(fd.ops.broadcast_in_dim(wf, shape=x1.shape(), broadcast_dims=[1]), xh)
+    fd.add_output(_down(fd, y, dtype))
+    fd.add_output(keep)
+    fd.add_output(rms)
+
+
+def dropout_layernorm_bwd_py(fd, dtype, p=0.2):
+    """inputs: mask, mean [M], invstd [M,1], grads, weights, input1, input2; outputs: d input1, d input2, dweight, dbias
+    (test_dropout_layernorm_bwd.py:18-119)."""
+    mask = fd.define_tensor(shape=[-1, -1], contiguity=[True, True], dtype=DataType.Bool, is_cpu=False)
+    mean = fd.define_tensor(shape=[-1], contiguity=[True], dtype=DataType.Float, is_cpu=False)
+    invstd = fd.define_tensor(shape=[-1, 1], contiguity=[True, None], dtype=DataType.Float, is_cpu=False)
+    dy = fd.define_tensor(shape=[-1, -1], contiguity=[True, True], dtype=dtype, is_cpu=False)
+    w = fd.define_tensor(shape=[-1], contiguity=[True], dtype=dtype, is_cpu=False)
+    x1 = fd.define_tensor(shape=[-1, -1], contiguity=[True, True], dtype=dtype, is_cpu=False)
+    x2 = fd.define_tensor(shape=[-1, -1], contiguity=[True, True], dtype=dtype, is_cpu=False)
+    size0, shp = x1.size(0), x1.shape()
+    mask_f = fd.ops.cast(mask, dtype=DataType.Float) if dtype in PROMOTE else mask
+    dyf, wf, x1f, x2f = (_up(fd, t, dtype) for t in (dy, w, x1, x2))
+    s, scale = _dropout_sum(fd, dtype, p, x1f, x2f, mask_f)
+    mean_b = fd.ops.broadcast_in_dim(fd.ops.broadcast_in_dim(mean, shape=[size0, 1], broadcast_dims=[0]), shape=shp,
+                                     broadcast_dims=[0, 1])
+    xc = fd.ops.sub(s, mean_b)
+    is_b = fd.ops.broadcast_in_dim(invstd, shape=shp, broadcast_dims=[0, 1])
+    xh = fd.ops.mul(xc, is_b)
+    w_b = fd.ops.broadcast_in_dim(wf, shape=shp, broadcast_dims=[1])
+    db = fd.ops.sum(dyf, dims=[0], keepdim=False, dtype=DataType.Null)
+    g = fd.ops.mul(dyf, w_b)
+    dw = fd.ops.sum(fd.ops.mul(dyf, xh), dims=[0], keepdim=False, dtype=DataType.Null)
+    g_is = fd.ops.mul(g, is_b)
+    t43 = fd.ops.sum(fd.ops.mul(g, xc), dims=[1], keepdim=False, dtype=DataType.Null)
+    t47 = fd.ops.broadcast_in_dim(t43, shape=[size0, 1], broadcast_dims=[0])
+    t49 = fd.ops.sum(fd.ops.neg(g_is), dims=[1], keepdim=False, dtype=DataType.Null)
+    t53 = fd.ops.broadcast_in_dim(t49, shape=[size0, 1], broadcast_dims=[0])
+    t55 = fd.ops.mul(fd.define_scalar(-0.5, dtype=DataType.Double), t47)
+    t58 = fd.ops.mul(t55, fd.ops.pow(invstd, fd.define_scalar(3.0, dtype=DataType.Double)))
+    t61 = fd.ops.sum(t53, dims=[1], keepdim=False, dtype=DataType.Null)
+    t62 = fd.ops.sum(t58, dims=[1], keepdim=False, dtype=DataType.Null)
+    t70 = fd.ops.broadcast_in_dim(fd.ops.broadcast_in_dim(t62, shape=[size0, 1], broadcast_dims=[0]), shape=shp,
+                                  broadcast_dims=[0, 1])
+    t80 = fd.ops.mul(fd.define_scalar(2.0, dtype=DataType.Double), t70)
+    t82 = fd.ops.mul(t80, fd.ops.sub(s, mean_b))
+    inv_n = fd.ops.reciprocal(x1.size(1))
+    t85 = fd.ops.mul(t82, inv_n)
+    t93 = fd.ops.broadcast_in_dim(fd.ops.broadcast_in_dim(t61, shape=[size0, 1], broadcast_dims=[0]), shape=shp,
+                                  broadcast_dims=[0, 1])
+    t96 = fd.ops.add(t85, fd.ops.mul(inv_n, t93))
+    dres = fd.ops.add(g_is, t96)
+    dx = fd.ops.mul(fd.ops.mul(dres, scale), mask_f)
+    fd.add_output(_down(fd, dx, dtype))
+    fd.add_output(_down(fd, dres, dtype))
+    fd.add_output(_down(fd, dw, dtype))
+    fd.add_output(_down(fd, db, dtype))
+
+
+def dropout_rmsnorm_bwd_py(fd, dtype, p=0.2):
+    """inputs: input1, input2, mask, rms [M,1], grads, weights; outputs: d input1, d input2, dweight
+    (test_dropout_rmsnorm_bwd.py:20-108)."""
+    x1 = fd.define_tensor(shape=[-1, -1], contiguity=[True, True], dtype=dtype, is_cpu=False)
+    x2 = fd.define_tensor(shape=[-1, -1], contiguity=[True, True], dtype=dtype, is_cpu=False)
+    mask = fd.define_tensor(shape=[-1, -1], contiguity=[True, True], dtype=DataType.Bool, is_cpu=False)
+    rms = fd.define_tensor(shape=[-1, 1], contiguity=[True, None], dtype=DataType.Float, is_cpu=False)
+    dy = fd.define_tensor(shape=[-1, -1], contiguity=[True, True], dtype=dtype, is_cpu=False)
+    w = fd.define_tensor(shape=[-1], contiguity=[True], dtype=dtype, is_cpu=False)
+    shp = x1.shape()
+    mask_f = fd.ops.cast(mask, dtype=DataType.Float) if dtype in PROMOTE else mask
+    x2f, x1f, dyf, wf = (_up(fd, t, dtype) for t in (x2, x1, dy, w))
+    s, scale = _dropout_sum(fd, dtype, p, x1f, x2f, mask_f)
+    rms_b = fd.ops.broadcast_in_dim(rms, shape=shp, broadcast_dims=[0, 1])
+    inv = fd.ops.reciprocal(rms_b)
+    xh = fd.ops.mul(s, inv)
+    w_b = fd.ops.broadcast_in_dim(wf, shape=shp, broadcast_dims=[1])
+    g = fd.ops.mul(dyf, w_b)
+    dw = fd.ops.sum(fd.ops.mul(dyf, xh), dims=[0], keepdim=False, dtype=DataType.Null)
+    g_inv = fd.ops.mul(g, inv)
+    two = fd.define_scalar(2.0, dtype=DataType.Double)
+    t41 = fd.ops.mul(fd.ops.mul(fd.ops.neg(g), s), fd.ops.reciprocal(fd.ops.pow(rms_b, two)))
+    t42 = fd.ops.sum(t41, dims=[1], keepdim=False, dtype=DataType.Null)
+    t47 = fd.ops.broadcast_in_dim(t42, shape=[x1.size(0), 1], broadcast_dims=[0])
+    t52 = fd.ops.mul(t47, fd.ops.reciprocal(fd.ops.mul(two, rms)))
+    t56 = fd.ops.mul(t52, fd.ops.reciprocal(x1.size(1)))
+    t57 = fd.ops.sum(t56, dims=[1], keepdim=False, dtype=DataType.Null)
+    t65 = fd.ops.broadcast_in_dim(fd.ops.broadcast_in_dim(t57, shape=[x1.size(0), 1], broadcast_dims=[0]), shape=shp,
+                                  broadcast_dims=[0, 1])
+    dres = fd.ops.add(g_inv, fd.ops.mul(fd.ops.mul(t65, two), s))
+    dx = fd.ops.mul(fd.ops.mul(dres, scale), mask_f)
+    fd.add_output(_down(fd, dx, dtype))
+    fd.add_output(_down(fd, dres, dtype))
+    fd.add_output(_down(fd, dw, dtype))

@@ -328,3 +328,67 @@ def test_batchnorm_bwd_matches_as_outer_norm(dt):
     assert torch.allclose(outs[1].float(), r[1], atol=0.2 if td == torch.bfloat16 else 1e-4, rtol=3e-2)
     # the inner backward spellings keep their classification
     assert not build(F.layernorm_bwd_py, dt).segment().flags & L.F_OUTER
+
+
+@pytest.mark.parametrize("dt", [DataType.Float, DataType.BFloat16, DataType.Half], ids=lambda d: d.name)
+def test_dropout_fusions_are_matched(dt):
+    """benchmarks/python/test_dropout_{layernorm,rmsnorm}_{fwd,bwd}.py: norm(input2 + dropout(input1)) and its
+    backward — the mask (uniform() < 1 - p) is a segment output forward and a Bool input backward."""
+    with FusionDefinition() as fd:
+        F.dropout_layernorm_fwd_py(fd, dt, 0.2)
+    m = fd.segment()
+    assert m.op == L.OP_LAYERNORM_FWD and m.flags & L.F_DROPOUT and m.flags & L.F_ADD_RESIDUAL
+    assert m.roles == {"x": 0, "r": 1, "w": 2, "b": 3} and m.outputs == ["y", "mean", "invstd", "mask"]
+    assert m.dropout_keep == 1 - 0.2 and m.eps == 1e-5
+    with FusionDefinition() as fd:
+        F.dropout_rmsnorm_fwd_py(fd, dt, 0.1)
+    m = fd.segment()
+    assert m.op == L.OP_RMSNORM_FWD and m.flags & L.F_DROPOUT and m.flags & L.F_STAT_IS_RMS
+    assert m.roles == {"x": 0, "r": 1, "w": 2} and m.outputs == ["y", "mask", "rms"] and m.dropout_keep == 1 - 0.1
+    with FusionDefinition() as fd:
+        F.dropout_layernorm_bwd_py(fd, dt, 0.2)
+    m = fd.segment()
+    assert m.op == L.OP_LAYERNORM_BWD and m.flags & L.F_DROPOUT
+    assert m.roles == {"dy": 3, "x": 5, "r": 6, "mask": 0, "mean": 1, "stat": 2, "w": 4}
+    assert m.outputs == ["dx", "dres", "dw", "db"] and abs(m.dropout_keep - 0.8) < 1e-12
+    with FusionDefinition() as fd:
+        F.dropout_rmsnorm_bwd_py(fd, dt, 0.2)
+    m = fd.segment()
+    assert m.op == L.OP_RMSNORM_BWD and m.flags & L.F_DROPOUT and m.flags & L.F_STAT_IS_RMS
+    assert not m.flags & L.F_RMS_BWD_CENTERED and m.outputs == ["dx", "dres", "dw"]
+    assert m.roles == {"dy": 4, "x": 0, "r": 1, "mask": 2, "stat": 3, "w": 5}
+
+
+def test_dropout_near_misses_are_refused():
+    def mask_only(fd):  # the mask alone is not a normalization segment
+        x = fd.define_tensor(shape=[-1, -1], dtype=DataType.Float)
+        u = fd.ops.uniform(0.0, 1.0, shape=x.shape(), dtype=DataType.Float)
+        fd.add_output(fd.ops.mul(x, fd.ops.cast(fd.ops.lt(u, 0.8), DataType.Float)))
+
+    def wrong_range(fd):  # uniform(0, 2) < keep is not the dropout mask
+        x1 = fd.define_tensor(shape=[-1, -1], dtype=DataType.Float)
+        x2 = fd.define_tensor(shape=[-1, -1], dtype=DataType.Float)
+        u = fd.ops.uniform(0.0, 2.0, shape=x1.shape(), dtype=DataType.Float)
+        k = fd.ops.cast(fd.ops.lt(u, 0.8), DataType.Float)
+        s = fd.ops.add(x2, fd.ops.mul(fd.ops.mul(x1, k), 1.25))
+        var, mean = fd.ops.var_mean(s, dims=[1], correction=0, keepdim=True)
+        fd.add_output(fd.ops.mul(fd.ops.sub(s, mean), fd.ops.rsqrt(fd.ops.add(var, 1e-5))))
+
+    def wrong_scale(fd):  # kept elements scaled by something else than 1 / keep
+        x1 = fd.define_tensor(shape=[-1, -1], dtype=DataType.Float)
+        x2 = fd.define_tensor(shape=[-1, -1], dtype=DataType.Float)
+        u = fd.ops.uniform(0.0, 1.0, shape=x1.shape(), dtype=DataType.Float)
+        k = fd.ops.cast(fd.ops.lt(u, 0.8), DataType.Float)
+        s = fd.ops.add(x2, fd.ops.mul(fd.ops.mul(x1, k), 1.5))
+        var, mean = fd.ops.var_mean(s, dims=[1], correction=0, keepdim=True)
+        fd.add_output(fd.ops.mul(fd.ops.sub(s, mean), fd.ops.rsqrt(fd.ops.add(var, 1e-5))))
+
+    for f in (mask_only, wrong_range, wrong_scale):
+        with FusionDefinition() as fd:
+            f(fd)
+        with pytest.raises(UnsupportedSegment):
+            fd.segment()
+    with pytest.raises(ValueError):
+        with FusionDefinition() as fd:
+            x = fd.define_tensor(shape=[-1, -1], dtype=DataType.Float)
+            fd.ops.uniform(0.0, 1.0, shape=[4, 5], dtype=DataType.Float)

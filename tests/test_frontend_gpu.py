@@ -127,3 +127,66 @@ def test_thunder_rms_norm_backward_as_written(shape, dt):
         AO.assert_close(dw2, dwe, m, "thunder dw (ops)")
     textbook, _ = AO.rms_norm_bwd_python(x, rms, dy, w)
     assert not torch.allclose(dxe.float(), textbook.float(), rtol=1e-2, atol=1e-2), "the two forms differ by design"
+
+
+@pytest.mark.parametrize("dt", list(DT), ids=lambda d: d.name)
+@pytest.mark.parametrize("shape", [(64, 768), (33, 4096), (7, 1987), (300, 2048)], ids=lambda s: f"{s[0]}x{s[1]}")
+def test_dropout_fusions_execute_and_validate(shape, dt):
+    """benchmarks/python/test_dropout_{layernorm,rmsnorm}_{fwd,bwd}.py through FusionDefinition with p = 0.2: the
+    expectation is the fusion evaluated node by node with ATen on the SAME Philox stream (uniform() restated from
+    runtime/random_numbers.cu), so the mask is compared bit for bit and the values under the validator's tolerances.
+    The benchmark itself validates at p = 0 only (its uniform stream is not reproducible outside nvFuser)."""
+    m, n = shape
+    td = DT[dt]
+    g = torch.Generator().manual_seed(m * 5 + n)
+    x1 = torch.randn(m, n, generator=g).to(td).cuda()
+    x2 = torch.randn(m, n, generator=g).to(td).cuda()
+    dy = torch.randn(m, n, generator=g).to(td).cuda()
+    w = torch.randn(n, generator=g).to(td).cuda()
+    b = torch.randn(n, generator=g).to(td).cuda()
+    rng = (1234 + m, 7 * n)
+
+    def run(fd, inputs):
+        ref = fusion_eval.evaluate(fd, [t.cpu() for t in inputs], rng=rng)
+        before = L.launch_count()
+        outs = fd.validate(inputs, ref, _rng=rng)
+        assert L.launch_count() > before
+        return outs
+
+    fd = build(F.dropout_layernorm_fwd_py, dt, 0.2)
+    assert fd.segment().flags & L.F_DROPOUT and fd.segment().dropout_keep == 1 - 0.2
+    y, mean, invstd, mask = run(fd, [x1, x2, w, b])
+    assert mask.dtype == torch.bool and 0.7 < mask.float().mean().item() < 0.9 and mean.shape == (m,) and invstd.shape == (m, 1)
+    dx1, dx2, dw, db = run(build(F.dropout_layernorm_bwd_py, dt, 0.2), [mask, mean, invstd, dy, w, x1, x2])
+    assert torch.equal(dx1[~mask], torch.zeros_like(dx1[~mask]))
+    y, mask_r, rms = run(build(F.dropout_rmsnorm_fwd_py, dt, 0.2), [x1, x2, w])
+    assert torch.equal(mask_r, mask), "same stream, same shape: the same mask"
+    run(build(F.dropout_rmsnorm_bwd_py, dt, 0.2), [x1, x2, mask_r, rms, dy, w])
+
+
+def test_dropout_stream_follows_the_cuda_generator():
+    """Without an explicit stream the Philox arguments come from the default CUDA generator the way the reference
+    takes them (csrc/rng.cpp:55-81): seed = the generator's seed, offset = its offset / 4, and the generator advances
+    by 4 per launch — two launches differ, re-seeding reproduces the first."""
+    dt = DataType.BFloat16
+    m, n = 128, 1024
+    x1, x2 = torch.randn(m, n, device="cuda").bfloat16(), torch.randn(m, n, device="cuda").bfloat16()
+    w, b = torch.ones(n, device="cuda").bfloat16(), torch.zeros(n, device="cuda").bfloat16()
+    fd = build(F.dropout_layernorm_fwd_py, dt, 0.3)
+    gen = torch.cuda.default_generators[torch.cuda.current_device()]
+    torch.cuda.manual_seed(4242)
+    off0 = gen.get_offset()
+    m1 = fd.execute([x1, x2, w, b])[3]
+    assert fd.last_rng() == (4242, off0 // 4) and gen.get_offset() == off0 + 4
+    m2 = fd.execute([x1, x2, w, b])[3]
+    assert fd.last_rng() == (4242, off0 // 4 + 1) and not torch.equal(m1, m2)
+    torch.cuda.manual_seed(4242)
+    m3 = fd.execute([x1, x2, w, b])[3]
+    assert torch.equal(m1, m3)
+    assert torch.equal(m1.cpu(), AO.dropout_mask(4242, off0 // 4, (m, n), 1 - 0.3))
+    # p = 0: every element kept, and the result is the fused add's (the benchmark's own validation point)
+    fd0 = build(F.dropout_layernorm_fwd_py, dt, 0.0)
+    y0, mean0, invstd0, mask0 = fd0.execute([x1, x2, w, b])
+    assert mask0.all()
+    ye, me, ie, _ = AO.add_layer_norm_fwd(x1.cpu(), x2.cpu(), w.cpu(), b.cpu(), 1e-5)
+    AO.assert_close(y0, ye, n, "p = 0")
