@@ -9,8 +9,8 @@ from .ir import DataType, Scalar, Tensor
 # ExprKind of segment_matcher.h
 KIND = {"input": 0, "const": 1, "size": 2, "cast": 3, "broadcast": 4, "broadcast_in_dim": 4, "neg": 5, "reciprocal": 6,
         "sqrt": 7, "rsqrt": 8, "exp": 9, "log": 10, "add": 11, "sub": 12, "mul": 13, "div": 14, "pow": 15, "sum": 16,
-        "max": 17, "mean": 18, "var": 19, "m2": 20}
-DTYPE = {DataType.Float: 0, DataType.BFloat16: 1, DataType.Half: 2}
+        "max": 17, "mean": 18, "var": 19, "m2": 20, "uniform": 21, "lt": 22}
+DTYPE = {DataType.Float: 0, DataType.BFloat16: 1, DataType.Half: 2, DataType.Bool: 5}
 
 
 def export_graph(fd):

@@ -82,6 +82,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         d["eps"] = sm.eps;
         d["io_dtype"] = sm.io_dtype;
         d["correction"] = sm.correction;
+        d["dropout_keep"] = sm.dropout_keep;
         d["roles"] = sm.roles;
         d["outputs"] = sm.outputs;
         d["description"] = sm.description;

@@ -119,6 +119,7 @@ bool NormExecutor::supported(const ExprGraph& segment, SegmentSpec* spec, Segmen
     spec->flags = m.flags;
     spec->eps = m.eps;
     spec->correction = m.correction;
+    spec->dropout_keep = m.dropout_keep;
   }
   if (match != nullptr) *match = m;
   return true;

@@ -149,10 +149,10 @@ Poly mul(const Poly& a, const Poly& b) {
 // ---------------------------------------------------------------------------------------------
 // canonicaliser
 // ---------------------------------------------------------------------------------------------
-enum AtomKind { A_IN, A_DIM, A_SUM, A_MAX, A_EXP, A_LOG, A_EXPR };
+enum AtomKind { A_IN, A_DIM, A_SUM, A_MAX, A_EXP, A_LOG, A_EXPR, A_KEEP };
 struct AtomInfo {
   int kind;
-  int32_t a;               // A_IN: node index; A_DIM: extent class
+  int32_t a;               // A_IN: node index; A_DIM: extent class; A_KEEP: node index of the uniform() tensor
   std::set<int32_t> red;   // A_SUM / A_MAX: reduced extent classes
   int32_t key;             // A_SUM / A_MAX / A_EXP / A_LOG / A_EXPR: id of the canonical inner expression
 };
@@ -202,6 +202,7 @@ struct Canon {
     std::set<int32_t> r;
     switch (a.kind) {
       case A_IN:
+      case A_KEEP:  // the dropout mask uniform() < keep spans the axes of the uniform tensor
         for (int32_t d : nodes[a.a].dims)
           if (d >= 0) r.insert(d);
         return r;
@@ -327,6 +328,17 @@ struct Canon {
       case ExprKind::Log: {
         const int32_t k = reg(arg(0));
         return Poly::atom(ctx.intern(AtomInfo{n.kind == ExprKind::Exp ? A_EXP : A_LOG, 0, {}, k}));
+      }
+      case ExprKind::Uniform: throw Unmatchable("uniform() outside a dropout mask");
+      case ExprKind::Lt: {
+        // only as the dropout mask: uniform(0, 1) < constant (benchmarks/python/test_dropout_layernorm_fwd.py:38-41)
+        const ExprNode& u = nodes.at(n.args.at(0));
+        const ExprNode& c = nodes.at(n.args.at(1));
+        if (u.kind == ExprKind::Uniform && !u.is_scalar && u.dtype == kF32 && c.kind == ExprKind::Constant &&
+            u.args.size() == 2 && nodes.at(u.args[0]).kind == ExprKind::Constant && nodes.at(u.args[0]).value == 0.0 &&
+            nodes.at(u.args[1]).kind == ExprKind::Constant && nodes.at(u.args[1]).value == 1.0)
+          return Poly::atom(ctx.intern(AtomInfo{A_KEEP, n.args[0], {}, -1}));
+        throw Unmatchable("lt outside a dropout mask");
       }
       case ExprKind::Add: return add(arg(0), arg(1));
       case ExprKind::Sub: return sub(arg(0), arg(1));
@@ -662,12 +674,16 @@ static void match_impl(const ExprGraph& g, SegmentMatch* out) {
   const std::vector<int32_t> row_cls(x_like.dims.begin(), x_like.dims.end() - 1);
   if (std::find(row_cls.begin(), row_cls.end(), col_cls) != row_cls.end())
     throw Unmatchable("square symbolic shapes: rows and cols were unified");
+  std::vector<In> masks;  // a saved dropout mask (Bool matrix, backward)
   {
     std::vector<In> keep;
-    for (const In& i : mats)
-      if (N(i).dims == x_like.dims) keep.push_back(i);
+    for (const In& i : mats) {
+      if (N(i).dims != x_like.dims) continue;
+      (N(i).dtype == kBool ? masks : keep).push_back(i);
+    }
     mats = keep;
   }
+  if (mats.empty()) throw Unmatchable("no [rows, cols] input");
   const int32_t io = N(mats[0]).dtype;
   std::vector<In> vecs, cstats, stats;
   for (const In& i : tin) {
@@ -685,7 +701,7 @@ static void match_impl(const ExprGraph& g, SegmentMatch* out) {
                            std::vector<int32_t>(n.dims.begin(), n.dims.end() - 1) == row_cls;
     if (rows_only || rows_keep) stats.push_back(i);
   }
-  if (mats.size() + vecs.size() + cstats.size() + stats.size() != tin.size())
+  if (mats.size() + masks.size() + vecs.size() + cstats.size() + stats.size() != tin.size())
     throw Unmatchable("an input is neither [rows, cols], [cols] nor a per-row statistic");
   if (io != kF32 && io != kF16 && io != kBF16) throw Unmatchable("io dtype");
   for (const In& i : mats)
@@ -813,6 +829,134 @@ static void match_impl(const ExprGraph& g, SegmentMatch* out) {
       }
     }
     throw Unmatchable("single-input fusion is not rms_norm / layer_norm / softmax / a reduction");
+  }
+
+  // ---- fused dropout (benchmarks/python/test_dropout_{layernorm,rmsnorm}_{fwd,bwd}.py) ----
+  {
+    std::vector<int32_t> keep_nodes;
+    for (size_t i = 0; i < g.nodes.size(); ++i) {
+      const ExprNode& n = g.nodes[i];
+      if (n.kind == ExprKind::Lt && !n.is_scalar && !g.nodes[n.args.at(0)].is_scalar &&
+          g.nodes[n.args[0]].kind == ExprKind::Uniform)
+        keep_nodes.push_back((int32_t)i);
+    }
+    if (!keep_nodes.empty()) {
+      if (keep_nodes.size() != 1 || !masks.empty() || n_m != 2 || n_s != 0 || n_v > 2)
+        throw Unmatchable("dropout: one mask over norm(residual + dropout(x)) expected");
+      const int32_t knode = keep_nodes[0];
+      const ExprNode& kc = g.nodes[g.nodes[knode].args.at(1)];
+      if (kc.kind != ExprKind::Constant || !(kc.value > 0.0) || kc.value > 1.0) throw Unmatchable("dropout keep probability");
+      const double keep = kc.value;
+      const uint32_t dflags = B200NORM_F_ADD_RESIDUAL | B200NORM_F_DROPOUT;
+      for (int order = 0; order < 2; ++order) {
+        const In &x = mats[order], &res = mats[1 - order];
+        auto drop_sum = [&](Builder& b) { return b.add(res.node, b.mul(b.mul(x.node, knode), b.constant(1.0 / keep))); };
+        for (double eps : eps_list) {
+          if (n_v <= 1) {
+            const In* w = n_v == 1 ? &vecs[0] : nullptr;
+            if (try_candidate([&](Builder& b) {
+                  const int32_t s = drop_sum(b);
+                  Outs o = def_rms_norm_fwd(b, s, opt(w), b.constant(eps));
+                  o["sum"] = s;
+                  o["mask"] = knode;
+                  return o;
+                }) &&
+                has("y")) {
+              if (has("rms") && has("invstd")) throw Unmatchable("both rms and invstd requested");
+              std::map<std::string, int32_t> roles{{"x", x.idx}, {"r", res.idx}};
+              put(roles, "w", w);
+              finish(B200NORM_OP_RMSNORM_FWD,
+                     dflags | (w ? B200NORM_F_HAS_WEIGHT : 0) | (has("rms") ? B200NORM_F_STAT_IS_RMS : 0) |
+                         (has("sum") ? B200NORM_F_OUT_SUM : 0),
+                     eps, roles, "rms_norm(residual + dropout(x))");
+              out->dropout_keep = keep;
+              return;
+            }
+          }
+          std::vector<std::pair<const In*, const In*>> combos{{nullptr, nullptr}};
+          if (n_v == 1) combos = {{&vecs[0], nullptr}};
+          if (n_v == 2) combos = {{&vecs[0], &vecs[1]}, {&vecs[1], &vecs[0]}};
+          for (const auto& wb : combos) {
+            const In *w = wb.first, *bi = wb.second;
+            if (try_candidate([&](Builder& b) {
+                  const int32_t s = drop_sum(b);
+                  Outs o = def_layer_norm_fwd(b, s, opt(w), opt(bi), b.constant(eps));
+                  o["sum"] = s;
+                  o["mask"] = knode;
+                  return o;
+                }) &&
+                has("y")) {
+              std::map<std::string, int32_t> roles{{"x", x.idx}, {"r", res.idx}};
+              put(roles, "w", w);
+              put(roles, "b", bi);
+              finish(B200NORM_OP_LAYERNORM_FWD,
+                     dflags | (w ? B200NORM_F_HAS_WEIGHT : 0) | (bi ? B200NORM_F_HAS_BIAS : 0) |
+                         (has("sum") ? B200NORM_F_OUT_SUM : 0),
+                     eps, roles, "layer_norm(residual + dropout(x))");
+              out->dropout_keep = keep;
+              return;
+            }
+          }
+        }
+      }
+      throw Unmatchable("a dropout mask outside norm(residual + dropout(x))");
+    }
+    if (!masks.empty()) {
+      // backward: dy, x (the dropped branch), residual + the saved mask; the scale 1 / keep is one of the constants
+      if (masks.size() != 1 || n_m != 3 || n_v > 1 || (n_s != 1 && n_s != 2))
+        throw Unmatchable("dropout backward: dy, x, residual, one mask and the saved statistics expected");
+      const In& mk = masks[0];
+      const In* w = n_v == 1 ? &vecs[0] : nullptr;
+      std::set<double> scales;
+      for (const auto& n : g.nodes)
+        if (n.kind == ExprKind::Constant && n.dtype != kInt && n.value >= 1.0 && n.value <= 1e6)
+          scales.insert(n.value);
+      for (double sc : scales) {
+        std::vector<int> perm{0, 1, 2};
+        do {
+          const In &dy_ = mats[perm[0]], &x_ = mats[perm[1]], &r_ = mats[perm[2]];
+          auto build = [&](Builder& b, int32_t mean, int32_t st, bool rms, bool centered) {
+            const int32_t scn = b.constant(sc);
+            const int32_t xe = b.add(r_.node, b.mul(b.mul(x_.node, mk.node), scn));
+            Outs o = def_norm_bwd(b, dy_.node, xe, mean, st, opt(w), rms, centered, false);
+            o["dres"] = o["dx"];
+            o["dx"] = b.mul(b.mul(o["dres"], scn), mk.node);
+            return o;
+          };
+          if (n_s == 1) {
+            const struct { bool rms, centered; } forms[] = {{true, false}, {false, false}, {true, true}, {false, true}};
+            for (const auto& f : forms)
+              if (try_candidate([&](Builder& b) { return build(b, kNone, stats[0].node, f.rms, f.centered); }) && !has("db") &&
+                  (has("dx") || has("dres"))) {
+                std::map<std::string, int32_t> roles{{"dy", dy_.idx}, {"x", x_.idx}, {"r", r_.idx}, {"mask", mk.idx},
+                                                     {"stat", stats[0].idx}};
+                put(roles, "w", w);
+                finish(B200NORM_OP_RMSNORM_BWD,
+                       B200NORM_F_DROPOUT | (w ? B200NORM_F_HAS_WEIGHT : 0) | (f.rms ? B200NORM_F_STAT_IS_RMS : 0) |
+                           (f.centered ? B200NORM_F_RMS_BWD_CENTERED : 0),
+                       0.0, roles, "backward of rms_norm(residual + dropout(x))");
+                out->dropout_keep = 1.0 / sc;
+                return;
+              }
+          } else {
+            for (int so = 0; so < 2; ++so) {
+              const In &mean = stats[so], &st = stats[1 - so];
+              if (try_candidate([&](Builder& b) { return build(b, mean.node, st.node, false, true); }) &&
+                  (has("dx") || has("dres"))) {
+                std::map<std::string, int32_t> roles{{"dy", dy_.idx}, {"x", x_.idx}, {"r", r_.idx}, {"mask", mk.idx},
+                                                     {"mean", mean.idx}, {"stat", st.idx}};
+                put(roles, "w", w);
+                finish(B200NORM_OP_LAYERNORM_BWD, B200NORM_F_DROPOUT | (w ? B200NORM_F_HAS_WEIGHT : 0), 0.0, roles,
+                       "backward of layer_norm(residual + dropout(x))");
+                out->dropout_keep = 1.0 / sc;
+                return;
+              }
+            }
+          }
+        } while (std::next_permutation(perm.begin(), perm.end()));
+      }
+      throw Unmatchable("a Bool matrix input outside a dropout backward");
+    }
   }
 
   // ---- forward norms with a fused residual add: two matrix inputs, no statistics ----
@@ -957,7 +1101,7 @@ bool match_segment(const ExprGraph& graph, SegmentMatch* out, std::string* why) 
     for (size_t k = 0; k < graph.outputs.size(); ++k) {
       const std::string& role = m.outputs.at(k);
       const bool stat = role == "mean" || role == "invstd" || role == "rms" || role == "var" || role == "m2";
-      const int32_t want = stat ? kF32 : m.io_dtype;
+      const int32_t want = role == "mask" ? (int32_t)kBool : stat ? (int32_t)kF32 : m.io_dtype;
       if (graph.nodes[graph.outputs[k]].dtype != want)
         throw Unmatchable("output '" + role + "' has a dtype the kernels do not produce");
     }

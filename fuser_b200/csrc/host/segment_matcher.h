@@ -32,10 +32,12 @@ enum class ExprKind : int32_t {
   Neg, Reciprocal, Sqrt, Rsqrt, Exp, Log,
   Add, Sub, Mul, Div, Pow,
   Sum, Max,    // reductions over red_axes of args[0]
-  Mean, Var, M2  // WelfordOp outputs: avg, var (with correction), var_sum
+  Mean, Var, M2,  // WelfordOp outputs: avg, var (with correction), var_sum
+  Uniform,        // RNGOp uniform(args[0], args[1]) of the tensor's shape (the dropout prologue)
+  Lt              // BinaryOp lt -> Bool; only uniform(0, 1) < constant (the dropout mask) is understood
 };
 
-enum ExprDtype : int32_t { kF32 = 0, kBF16 = 1, kF16 = 2, kOtherFloat = 3, kInt = 4 };
+enum ExprDtype : int32_t { kF32 = 0, kBF16 = 1, kF16 = 2, kOtherFloat = 3, kInt = 4, kBool = 5 };
 
 struct ExprNode {
   ExprKind kind = ExprKind::Input;
@@ -63,8 +65,9 @@ struct SegmentMatch {
   double eps = 0.0;
   int32_t io_dtype = kF32;
   int32_t correction = 0;
-  std::map<std::string, int32_t> roles;  // "x", "dy", "y", "w", "b", "r", "mean", "stat" -> index into graph.inputs
-  std::vector<std::string> outputs;      // "y", "mean", "invstd", "rms", "sum", "dx", "dw", "db", "r", "var", "m2"
+  double dropout_keep = 1.0;  // B200NORM_F_DROPOUT: the keep probability 1 - p
+  std::map<std::string, int32_t> roles;  // "x", "dy", "y", "w", "b", "r", "mean", "stat", "mask" -> index into graph.inputs
+  std::vector<std::string> outputs;      // "y", "mean", "invstd", "rms", "sum", "dx", "dw", "db", "r", "var", "m2", "mask", "dres"
   std::string description;
 };
 

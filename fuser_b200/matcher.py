@@ -722,7 +722,7 @@ def match_fusion(fd) -> Match:
         mk = masks[0]
         w = vecs[0] if n_v == 1 else None
         scales = sorted({float(v.value) for v in fd._vals if isinstance(v, Scalar) and v.value is not None and v.dim is None
-                         and isinstance(v.value, float) and 1.0 <= float(v.value) <= 1e6 and float(v.value) not in (2.0, 3.0)})
+                         and isinstance(v.value, float) and 1.0 <= float(v.value) <= 1e6})
         for scale in scales:
             for dy_, x_, r_ in itertools.permutations(mats):
                 def with_drop_bwd(mean, st, stat_is_rms, centered, half):

@@ -30,6 +30,7 @@ def agree(fd):
     assert c["matched"], f"C++ refused ({c.get('why')}) what Python matched as {m.description}"
     assert (c["op"], c["flags"], c["eps"], c["correction"]) == (m.op, m.flags, m.eps, m.correction), (c, m)
     assert c["roles"] == m.roles and c["outputs"] == m.outputs and c["io_dtype"] == IO[m.io_dtype], (c, m)
+    assert c["dropout_keep"] == m.dropout_keep, (c, m)
     return m
 
 
@@ -64,6 +65,10 @@ SPELLINGS = [
     ("rmsnorm_add_thunder", lambda dt: (F.rmsnorm_add_thunder, (dt,))),
     ("thunder_rms_norm_bwd_cpp", lambda dt: (F.thunder_rms_norm_bwd_cpp, (dt,))),
     ("thunder_rms_norm_bwd_cpp_noweight", lambda dt: (lambda fd, d: F.thunder_rms_norm_bwd_cpp(fd, d, weight=False), (dt,))),
+    ("dropout_layernorm_fwd_py", lambda dt: (F.dropout_layernorm_fwd_py, (dt, 0.2))),
+    ("dropout_rmsnorm_fwd_py", lambda dt: (F.dropout_rmsnorm_fwd_py, (dt, 0.1))),
+    ("dropout_layernorm_bwd_py", lambda dt: (F.dropout_layernorm_bwd_py, (dt, 0.2))),
+    ("dropout_rmsnorm_bwd_py", lambda dt: (F.dropout_rmsnorm_bwd_py, (dt, 0.5))),
 ]
 
 
