@@ -54,6 +54,9 @@ WORKLOADS = {
     # (benchmarks/python/normalization.py, test_batchnorm_{fwd,bwd}.py viewed as [N*H*W, C])
     "o2": ("batch norm fwd+bwd bf16 [8192,18432] (statistics over dim 0, outer-persistent)", 8192, 18432, torch.bfloat16,
            "outer_norm_fwd_bwd"),
+    # ... and at the ResNet-50 size N*H*W = 32*56*56, C = 256, beyond what a cluster holds: the row-block kernel
+    "o3": ("batch norm fwd+bwd bf16 [100352,256] (statistics over dim 0, row-block kernel)", 100352, 256, torch.bfloat16,
+           "outer_norm_fwd_bwd"),
     # plain Reduction segments and stand-alone variance_mean on the fast path
     "r1": ("row sum + var_mean + column sum bf16 [32768,12288] (Reduction / Welford segments)", 32768, 12288, torch.bfloat16,
            "reductions"),

@@ -268,6 +268,7 @@ uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
   RingKernel ring_kernel_for<T>(int op, int tpr, int ch, bool cached, bool psmem, bool add, bool pipe,       \
                                 bool red, bool lean, bool drop) {                                          \
     if (drop && is_norm_bwd(op)) return cached ? ring_bwd_drop_kernel_##SUF(op, tpr, ch) : nullptr;          \
+    if (drop) return (add && !pipe && !psmem) ? ring_drop_kernel_##SUF(op, tpr, ch) : nullptr;               \
     if (op == B200NORM_OP_REDUCE_INNER || red) return ring_reduce_inner_kernel_##SUF(tpr, ch);               \
     if (op == B200NORM_OP_REDUCE_OUTER) return ring_colsum_kernel_##SUF(tpr, ch);                            \
     if (pipe && op == B200NORM_OP_LAYERNORM_FWD) return ring_ln_pipe_kernel_##SUF(tpr, ch, add);             \
@@ -547,7 +548,7 @@ bool try_ring_plan(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, int 
   const bool ln_pipe = d.op == B200NORM_OP_LAYERNORM_FWD && !inner_red && ch > 0 && nchunks == tpr * ch && tile_rows == 1 &&
                        tpr >= 64 && kn.no_ln_pipe == 0 && !dropout;
   bool want_psmem = d.op == B200NORM_OP_LAYERNORM_FWD && ch > 0 && es == 2 && slice_cols <= 8192 &&
-                    kn.no_psmem == 0 && !ln_pipe && !inner_red;
+                    kn.no_psmem == 0 && !ln_pipe && !inner_red && !dropout;
   const uint32_t param_bytes = align_up(2u * (uint32_t)slice_cols * 4u, 128);
 
   // Ring depth D (stages per group); the ring is group-major, stage (g*D + s).

@@ -24,8 +24,11 @@ namespace b200norm {
 // RMSNorm forward: stat = rsqrt(mean(x^2)+eps) (or sqrt(...) with STAT_IS_RMS),
 // y = x * invstd * w.
 // ---------------------------------------------------------------------------
-template <typename T, int TPR, int CH, bool ADD = false>
+// DROP (with ADD, cached form): the x stream goes through a fused dropout before the residual is added
+// (dropout_chunk, ring.cuh); its own instantiations, so that the plain kernels keep their register budget.
+template <typename T, int TPR, int CH, bool ADD = false, bool DROP = false>
 __global__ void __launch_bounds__(kMaxBlock, 1) rmsnorm_fwd_ring_kernel(const RowParams p) {
+  static_assert(!DROP || (ADD && CH > 0), "fused dropout: norm(residual + dropout(x)) on the register-resident form");
   constexpr int VEC = IO<T>::VEC;
   constexpr int H = VEC / 2;
   constexpr int NC = CH > 0 ? CH : 1;
@@ -45,8 +48,7 @@ __global__ void __launch_bounds__(kMaxBlock, 1) rmsnorm_fwd_ring_kernel(const Ro
   const bool stat_writer = g.gtid == 0 && g.crank == 0 && p.stat1 != nullptr;
   const bool round_sum = ADD && (p.flags & kFlagRoundSum) != 0;
   const bool out_sum = ADD && p.out1 != nullptr;
-  // fused dropout of the x stream (cached form only: the planner never pairs kFlagDropout with CH == 0)
-  const bool drop = ADD && CH > 0 && (p.flags & kFlagDropout) != 0;
+  constexpr bool drop = DROP;
   const unsigned long long drop_seed = drop ? p.rng[0] : 0ull, drop_offset = drop ? p.rng[1] : 0ull;
 
   const size_t out_row_bytes = (size_t)p.out_stride * sizeof(T);
@@ -67,7 +69,7 @@ __global__ void __launch_bounds__(kMaxBlock, 1) rmsnorm_fwd_ring_kernel(const Ro
         float2 t[H];
         IO<T>::unpack2(ld_smem_u4(xrow + 16 * coff), t);
         if constexpr (ADD) {
-          if (drop) dropout_chunk<T, H>(t, p, drop_seed, drop_offset, drop_lin + (unsigned long long)((g.gtid + coff) * VEC));
+          if constexpr (drop) dropout_chunk<T, H>(t, p, drop_seed, drop_offset, drop_lin + (unsigned long long)((g.gtid + coff) * VEC));
           add_residual_chunk<T, H>(t, xrow + p.stream_bytes + 16 * coff, round_sum, out_sum ? srow + 16 * coff : nullptr);
         }
 #pragma unroll
@@ -119,8 +121,9 @@ __global__ void __launch_bounds__(kMaxBlock, 1) rmsnorm_fwd_ring_kernel(const Ro
 // instead of packed in registers (16 unpack ops per chunk and 8*CH registers) — LayerNorm is
 // the one forward with two per-column parameters, and unpacking both costs more issue slots
 // than the row math itself.
-template <typename T, int TPR, int CH, bool PSMEM = false, bool ADD = false>
+template <typename T, int TPR, int CH, bool PSMEM = false, bool ADD = false, bool DROP = false>
 __global__ void __launch_bounds__(kMaxBlock, 1) layernorm_fwd_ring_kernel(const RowParams p) {
+  static_assert(!DROP || (ADD && CH > 0), "fused dropout: norm(residual + dropout(x)) on the register-resident form");
   constexpr int VEC = IO<T>::VEC;
   constexpr int H = VEC / 2;
   constexpr int NC = CH > 0 ? CH : 1;
@@ -149,8 +152,7 @@ __global__ void __launch_bounds__(kMaxBlock, 1) layernorm_fwd_ring_kernel(const 
   const bool no_y = (p.flags & kFlagNoY) != 0;  // stand-alone var_mean / welford: statistics only
   const bool round_sum = ADD && (p.flags & kFlagRoundSum) != 0;
   const bool out_sum = ADD && p.out1 != nullptr;
-  // fused dropout of the x stream (cached form only: the planner never pairs kFlagDropout with CH == 0)
-  const bool drop = ADD && CH > 0 && (p.flags & kFlagDropout) != 0;
+  constexpr bool drop = DROP;
   const unsigned long long drop_seed = drop ? p.rng[0] : 0ull, drop_offset = drop ? p.rng[1] : 0ull;
 
   const size_t out_row_bytes = (size_t)p.out_stride * sizeof(T);
@@ -171,7 +173,7 @@ __global__ void __launch_bounds__(kMaxBlock, 1) layernorm_fwd_ring_kernel(const 
         float2 t[H];
         IO<T>::unpack2(ld_smem_u4(xrow + 16 * coff), t);
         if constexpr (ADD) {
-          if (drop) dropout_chunk<T, H>(t, p, drop_seed, drop_offset, drop_lin + (unsigned long long)((g.gtid + coff) * VEC));
+          if constexpr (drop) dropout_chunk<T, H>(t, p, drop_seed, drop_offset, drop_lin + (unsigned long long)((g.gtid + coff) * VEC));
           add_residual_chunk<T, H>(t, xrow + p.stream_bytes + 16 * coff, round_sum, out_sum ? srow + 16 * coff : nullptr);
         }
 #pragma unroll

@@ -18,6 +18,10 @@ RingKernel ring_fwd_kernel_f16(int op, int tpr, int ch, bool psmem);
 RingKernel ring_add_kernel_f32(int op, int tpr, int ch, bool psmem);
 RingKernel ring_add_kernel_bf16(int op, int tpr, int ch, bool psmem);
 RingKernel ring_add_kernel_f16(int op, int tpr, int ch, bool psmem);
+// ... and with the fused dropout of x (benchmarks/python/test_dropout_*_fwd.py): ch in {1..4}, parameters in registers
+RingKernel ring_drop_kernel_f32(int op, int tpr, int ch);
+RingKernel ring_drop_kernel_bf16(int op, int tpr, int ch);
+RingKernel ring_drop_kernel_f16(int op, int tpr, int ch);
 // norm backward: cached (g / xc in registers, ch in {1,2}) or re-read (ch in {3,4}, tpr 512... any tpr).
 RingKernel ring_bwd_kernel_f32(int op, int tpr, int ch, bool cached, bool centered);
 RingKernel ring_bwd_kernel_bf16(int op, int tpr, int ch, bool cached, bool centered);

@@ -38,6 +38,16 @@ namespace b200norm {
     default: return nullptr;                                              \
   }
 
+#define B200_ADD_TPR_SWITCH_NOLOOP(K, ...)                                \
+  switch (tpr) {                                                          \
+    case 32: B200_ADD_CH_SWITCH(K, 32, ##__VA_ARGS__)                     \
+    case 64: B200_ADD_CH_SWITCH_HI(K, 64, ##__VA_ARGS__)                  \
+    case 128: B200_ADD_CH_SWITCH_HI(K, 128, ##__VA_ARGS__)                \
+    case 256: B200_ADD_CH_SWITCH_HI(K, 256, ##__VA_ARGS__)                \
+    case 512: B200_ADD_CH_SWITCH_HI(K, 512, ##__VA_ARGS__)                \
+    default: return nullptr;                                              \
+  }
+
 template <typename T>
 RingKernel ring_add_kernel_for(int op, int tpr, int ch, bool psmem) {
   switch (op) {
@@ -50,6 +60,17 @@ RingKernel ring_add_kernel_for(int op, int tpr, int ch, bool psmem) {
     default: return nullptr;
   }
 }
+// ... with the fused dropout of the x stream (register-resident form, parameters in registers)
+template <typename T>
+RingKernel ring_drop_kernel_for(int op, int tpr, int ch) {
+  if (ch <= 0) return nullptr;
+  switch (op) {
+    case B200NORM_OP_RMSNORM_FWD: B200_ADD_TPR_SWITCH_NOLOOP(rmsnorm_fwd_ring_kernel, true, true)
+    case B200NORM_OP_LAYERNORM_FWD: B200_ADD_TPR_SWITCH_NOLOOP(layernorm_fwd_ring_kernel, false, true, true)
+    default: return nullptr;
+  }
+}
+#undef B200_ADD_TPR_SWITCH_NOLOOP
 #undef B200_ADD_TPR_SWITCH
 #undef B200_ADD_CH_SWITCH_HI
 #undef B200_ADD_CH_SWITCH
