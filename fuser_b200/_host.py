@@ -37,22 +37,22 @@ def load():
 
 
 def executor(op: int, flags: int = 0, eps: float = 0.0, variant: int = 0, cluster_size: int = 0, correction: int = 0,
-             dropout_keep: float = 1.0):
+             dropout_keep: float = 1.0, ignore_index: int = -100):
     """Compiled ``NormExecutor`` for a segment spec (cached like FusionKernelRuntime::executors_)."""
-    key = (op, flags, eps, variant, cluster_size, correction, dropout_keep)
+    key = (op, flags, eps, variant, cluster_size, correction, dropout_keep, ignore_index)
     ex = _executors.get(key)
     if ex is None:
         m = load()
         ex = m.NormExecutor(0, 0, 0, len(_executors))
-        ex.compile(m.SegmentSpec(op, flags, eps, variant, cluster_size, correction, dropout_keep))
+        ex.compile(m.SegmentSpec(op, flags, eps, variant, cluster_size, correction, dropout_keep, ignore_index))
         _executors[key] = ex
     return ex
 
 
 def run(op: int, flags: int, eps: float, variant: int, cluster_size: int, inputs, outputs=(), correction: int = 0,
-        dropout_keep: float = 1.0):
+        dropout_keep: float = 1.0, ignore_index: int = -100):
     """Launch a segment; library status codes come back as B200NormError / UnsupportedSegment."""
-    ex = executor(op, flags, eps, variant, cluster_size, correction, dropout_keep)
+    ex = executor(op, flags, eps, variant, cluster_size, correction, dropout_keep, ignore_index)
     try:
         return ex.run(list(inputs), list(outputs))
     except _mod.NormError as e:

@@ -30,7 +30,8 @@ OK, ERR_UNSUPPORTED, ERR_BAD_ARG, ERR_NO_DEVICE, ERR_WORKSPACE, ERR_CUDA = 0, 1,
     OP_REDUCE_OUTER,
     OP_FINALIZE_PARTIALS,
     OP_PEER_COMBINE,
-) = range(12)
+    OP_NLL_SOFTMAX_BWD,
+) = range(13)
 OP_NAMES = [
     "layernorm_fwd",
     "layernorm_bwd",
@@ -44,6 +45,7 @@ OP_NAMES = [
     "reduce_outer",
     "finalize_partials",
     "peer_combine",
+    "nll_softmax_bwd",
 ]
 
 DT_F32, DT_BF16, DT_F16 = 0, 1, 2
@@ -72,6 +74,7 @@ F_NO_Y = 1 << 20
 F_STAT_VAR = 1 << 21
 F_STAT_M2 = 1 << 22
 F_DROPOUT = 1 << 23
+F_REDUCE_NLL = 1 << 24
 
 VARIANT_AUTO, VARIANT_GENERIC, VARIANT_TMA, VARIANT_CLUSTER = 0, 1, 2, 3
 FORM_CACHED, FORM_PIPE, FORM_PSMEM, FORM_FUSED_FINISH = 1, 2, 4, 8
@@ -232,7 +235,7 @@ def _raise(code: int):
 
 
 def make_desc(op, io_dtype, rows, cols, eps=0.0, flags=0, variant=VARIANT_AUTO, cluster_size=0, correction=0,
-              dropout_keep=1.0) -> Desc:
+              dropout_keep=1.0, ignore_index=-100) -> Desc:
     d = Desc()
     d.abi_version = ABI_VERSION
     d.op = op
@@ -244,6 +247,7 @@ def make_desc(op, io_dtype, rows, cols, eps=0.0, flags=0, variant=VARIANT_AUTO, 
     d.flags = flags
     d.cluster_size = cluster_size
     d.reserved[0] = correction
+    d.reserved[3] = ignore_index
     if flags & F_DROPOUT:  # keep probability 1 - p: the double's low and high words
         import struct
 

@@ -222,7 +222,10 @@ uint64_t algorithmic_bytes(const b200norm_desc& d) {
     case B200NORM_OP_LOGSOFTMAX_FWD: return s * 2 * M * N;
     case B200NORM_OP_SOFTMAX_BWD:
     case B200NORM_OP_LOGSOFTMAX_BWD: return s * 3 * M * N;
-    case B200NORM_OP_REDUCE_INNER: return s * (M * N + M);
+    case B200NORM_OP_REDUCE_INNER:
+      if (d.flags & B200NORM_F_REDUCE_NLL) return s * M * N + 8 * M + 2 * 4 * M;  // logits, int64 targets; loss + lse
+      return s * (M * N + M);
+    case B200NORM_OP_NLL_SOFTMAX_BWD: return s * 2 * M * N + 8 * M + 4 * M + 4;
     case B200NORM_OP_REDUCE_OUTER: return s * (M * N + N);
     case B200NORM_OP_FINALIZE_PARTIALS: return 4 * M * N + s * M * N;
     default: return 0;
@@ -709,6 +712,12 @@ int make_plan_uncached(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, 
       p.n_launches = 2;
       p.block = 128;
     }
+    if (d.op == B200NORM_OP_NLL_SOFTMAX_BWD) {  // pointwise streaming kernel: (row, block of chunks) work items
+      p.block = kCeThreads;
+      const int64_t items = d.rows * ceil_div64(ceil_div64(d.cols, 16 / elem_size(d.io_dtype)), kCeThreads * kCeU);
+      const int64_t capg = (int64_t)dev.sm_count * 8;
+      p.grid = (int)(items < capg ? (items < 1 ? 1 : items) : capg);
+    }
     if (d.op == B200NORM_OP_FINALIZE_PARTIALS) {
       p.block = 256;
       p.grid = (int)ceil_div64(d.cols, 32);
@@ -832,7 +841,13 @@ int check_desc(const b200norm_desc* d) {
   if (d->op < 0 || d->op >= B200NORM_OP_COUNT_) return fail(B200NORM_ERR_UNSUPPORTED, "unknown op %d", d->op);
   if (d->io_dtype < 0 || d->io_dtype > B200NORM_DT_F16)
     return fail(B200NORM_ERR_UNSUPPORTED, "unsupported io dtype %d", d->io_dtype);
-  if (d->flags >> 24) return fail(B200NORM_ERR_BAD_ARG, "unknown flag bits 0x%x", d->flags & ~((1u << 24) - 1u));
+  if (d->flags >> 25) return fail(B200NORM_ERR_BAD_ARG, "unknown flag bits 0x%x", d->flags & ~((1u << 25) - 1u));
+  if (d->flags & B200NORM_F_REDUCE_NLL) {
+    if (d->op != B200NORM_OP_REDUCE_INNER)
+      return fail(B200NORM_ERR_UNSUPPORTED, "B200NORM_F_REDUCE_NLL is a flavour of REDUCE_INNER");
+    if (d->flags & (B200NORM_F_REDUCE_MAX | B200NORM_F_REDUCE_FMAX | B200NORM_F_OUTER))
+      return fail(B200NORM_ERR_BAD_ARG, "B200NORM_F_REDUCE_NLL excludes REDUCE_MAX / REDUCE_FMAX / OUTER");
+  }
   if (d->flags & B200NORM_F_DROPOUT) {
     const bool fwd = d->op == B200NORM_OP_LAYERNORM_FWD || d->op == B200NORM_OP_RMSNORM_FWD;
     const bool bwd = d->op == B200NORM_OP_LAYERNORM_BWD || d->op == B200NORM_OP_RMSNORM_BWD;
@@ -1198,6 +1213,36 @@ int check_vector(const b200norm_tensor& t, int64_t n, int dtype, const char* nam
 // ---------------------------------------------------------------------------
 // exported C ABI
 // ---------------------------------------------------------------------------
+namespace {
+int ce_bwd_grid(const CeBwdParams& q, int vec, int sm_count) {
+  const int64_t units = (q.cols + vec - 1) / vec;
+  const int64_t items = q.rows * ((units + kCeThreads * kCeU - 1) / (kCeThreads * kCeU));
+  const int64_t cap = (int64_t)sm_count * 8;  // eight 256-thread CTAs per SM: 128 KB of loads in flight
+  return (int)(items < cap ? (items < 1 ? 1 : items) : cap);
+}
+template <typename T>
+int launch_ce_bwd_typed(const CeBwdParams& q, bool aligned, int sm_count, cudaStream_t stream) {
+  const bool vec = aligned && q.cols % IO<T>::VEC == 0;
+  if (vec) {
+    cross_entropy_bwd_kernel<T, true><<<ce_bwd_grid(q, IO<T>::VEC, sm_count), kCeThreads, 0, stream>>>(q);
+  } else {
+    cross_entropy_bwd_kernel<T, false><<<ce_bwd_grid(q, 1, sm_count), kCeThreads, 0, stream>>>(q);
+  }
+  const cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return fail(B200NORM_ERR_CUDA + (int)err, "launch failed: %s", cudaGetErrorString(err));
+  g_launches++;
+  return B200NORM_OK;
+}
+int launch_ce_bwd(int dt, const CeBwdParams& q, bool aligned, int sm_count, cudaStream_t stream) {
+  switch (dt) {
+    case B200NORM_DT_F32: return launch_ce_bwd_typed<float>(q, aligned, sm_count, stream);
+    case B200NORM_DT_BF16: return launch_ce_bwd_typed<__nv_bfloat16>(q, aligned, sm_count, stream);
+    case B200NORM_DT_F16: return launch_ce_bwd_typed<__half>(q, aligned, sm_count, stream);
+    default: return fail(B200NORM_ERR_UNSUPPORTED, "dtype %d", dt);
+  }
+}
+}  // namespace
+
 extern "C" {
 
 int b200norm_abi_version(void) { return B200NORM_ABI_VERSION; }
@@ -1414,6 +1459,17 @@ int b200norm_launch(const b200norm_desc* desc, const b200norm_tensor* inputs, in
     return B200NORM_OK;
   };
 
+  // int64 vector (class indices): n contiguous elements, 8-byte aligned (the dtype field is not interpreted)
+  auto bind_i64 = [&](const b200norm_tensor& t, int64_t n, const char* name, void** ptr) -> int {
+    if (t.data == nullptr || (reinterpret_cast<uintptr_t>(t.data) & 7u) != 0) return fail(B200NORM_ERR_BAD_ARG, "%s: null or misaligned int64 data", name);
+    int64_t numel = 1;
+    for (int i = 0; i < t.ndim; ++i) numel *= t.sizes[i];
+    if (numel != n) return fail(B200NORM_ERR_BAD_ARG, "%s: %lld elements, expected %lld", name, (long long)numel, (long long)n);
+    for (int i = 0; i < t.ndim; ++i)
+      if (t.sizes[i] > 1 && t.strides[i] != 1 && t.sizes[i] == numel) return fail(B200NORM_ERR_UNSUPPORTED, "%s must be contiguous", name);
+    *ptr = t.data;
+    return B200NORM_OK;
+  };
   // dropout mask: [M,N] bytes with contiguous rows (the dtype field is not interpreted)
   auto bind_mask = [&](const b200norm_tensor& t, const char* name, void** ptr) -> int {
     if (t.data == nullptr) return fail(B200NORM_ERR_BAD_ARG, "%s: null data", name);
@@ -1574,10 +1630,48 @@ int b200norm_launch(const b200norm_desc* desc, const b200norm_tensor* inputs, in
       NEED_IN(1);
       NEED_OUT(1);
       CHECK(bind_in_matrix(&rp.in0, &rp.in0_stride, "x"));
+      if (d.flags & B200NORM_F_REDUCE_NLL) {  // cross-entropy forward: + target[M] int64; loss[M], lse[M] fp32
+        NEED_IN(1);
+        NEED_OUT(2);
+        void* tg = nullptr;
+        CHECK(bind_i64(inputs[ii++], d.rows, "target", &tg));
+        rp.target = static_cast<const long long*>(tg);
+        rp.ignore_index = d.reserved[3];
+        void* v = nullptr;
+        CHECK(bind_vec(outputs[oi++], d.rows, B200NORM_DT_F32, "loss", &v));
+        rp.stat1 = static_cast<float*>(v);
+        CHECK(bind_vec(outputs[oi++], d.rows, B200NORM_DT_F32, "lse", &v));
+        rp.stat0 = static_cast<float*>(v);
+        break;
+      }
       void* r = nullptr;
       CHECK(bind_vec(outputs[oi++], d.rows, dt, "result", &r));
       rp.out0 = r;
       break;
+    }
+    case B200NORM_OP_NLL_SOFTMAX_BWD: {
+      NEED_IN(4);
+      NEED_OUT(1);
+      CeBwdParams q;
+      memset(&q, 0, sizeof(q));
+      const void* xin = nullptr;
+      CHECK(bind_in_matrix(&xin, &q.x_stride, "x"));
+      q.x = xin;
+      void* v = nullptr;
+      CHECK(bind_i64(inputs[ii++], d.rows, "target", &v));
+      q.target = static_cast<const long long*>(v);
+      CHECK(bind_vec(inputs[ii++], d.rows, B200NORM_DT_F32, "lse", &v));
+      q.lse = static_cast<const float*>(v);
+      CHECK(bind_vec(inputs[ii++], 1, B200NORM_DT_F32, "g", &v));
+      q.gscale = static_cast<const float*>(v);
+      void* dxp = nullptr;
+      CHECK(bind_out_matrix(&dxp, &q.dx_stride, "dx"));
+      q.dx = dxp;
+      q.rows = d.rows;
+      q.cols = (int32_t)d.cols;
+      q.ignore_index = d.reserved[3];
+      if (d.rows == 0 || d.cols == 0) return B200NORM_OK;
+      return launch_ce_bwd(dt, q, aligned, dev.sm_count, stream);
     }
     case B200NORM_OP_REDUCE_OUTER: {
       NEED_IN(1);

@@ -24,7 +24,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   });
 
   py::class_<SegmentSpec>(m, "SegmentSpec")
-      .def(py::init([](int op, uint32_t flags, double eps, int variant, int cluster_size, int correction, double dropout_keep) {
+      .def(py::init([](int op, uint32_t flags, double eps, int variant, int cluster_size, int correction, double dropout_keep, int ignore_index) {
              SegmentSpec s;
              s.op = op;
              s.flags = flags;
@@ -33,10 +33,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
              s.cluster_size = cluster_size;
              s.correction = correction;
              s.dropout_keep = dropout_keep;
+             s.ignore_index = ignore_index;
              return s;
            }),
            py::arg("op"), py::arg("flags") = 0, py::arg("eps") = 0.0, py::arg("variant") = 0,
-           py::arg("cluster_size") = 0, py::arg("correction") = 0, py::arg("dropout_keep") = 1.0)
+           py::arg("cluster_size") = 0, py::arg("correction") = 0, py::arg("dropout_keep") = 1.0, py::arg("ignore_index") = -100)
       .def_readwrite("op", &SegmentSpec::op)
       .def_readwrite("flags", &SegmentSpec::flags)
       .def_readwrite("eps", &SegmentSpec::eps)

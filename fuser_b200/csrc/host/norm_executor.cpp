@@ -45,6 +45,7 @@ b200norm_desc make_desc(const SegmentSpec& s, int dt, int64_t rows, int64_t cols
   d.flags = s.flags;
   d.cluster_size = s.cluster_size;
   d.reserved[0] = s.correction;
+  d.reserved[3] = s.ignore_index;
   if (s.flags & B200NORM_F_DROPOUT) {
     uint64_t bits;
     static_assert(sizeof(bits) == sizeof(s.dropout_keep), "double is 64 bits");
@@ -185,9 +186,17 @@ std::vector<at::Tensor> NormExecutor::allocateOutputs(const std::vector<at::Tens
     }
     case B200NORM_OP_REDUCE_INNER: {
       std::vector<int64_t> s(first.sizes().begin(), first.sizes().end() - 1);
-      out.push_back(at::empty(s, opts));
+      if (f & B200NORM_F_REDUCE_NLL) {  // cross-entropy forward: per-row loss and log-sum-exp, fp32
+        out.push_back(at::empty(s, f32));
+        out.push_back(at::empty(s, f32));
+      } else {
+        out.push_back(at::empty(s, opts));
+      }
       break;
     }
+    case B200NORM_OP_NLL_SOFTMAX_BWD:
+      out.push_back(at::empty(first.sizes(), opts));
+      break;
     case B200NORM_OP_REDUCE_OUTER:
       out.push_back(at::empty({cols}, (f & B200NORM_F_PARTIALS_F32) ? f32 : opts));
       break;
@@ -276,6 +285,7 @@ std::vector<at::Tensor> NormExecutor::run(const std::vector<at::Tensor>& inputs,
     case B200NORM_OP_LOGSOFTMAX_FWD:
     case B200NORM_OP_SOFTMAX_BWD:
     case B200NORM_OP_LOGSOFTMAX_BWD:
+    case B200NORM_OP_NLL_SOFTMAX_BWD:
       n_mat_out = 1;
       break;
     case B200NORM_OP_LAYERNORM_BWD:

@@ -36,6 +36,7 @@ struct SegmentSpec {
   int32_t cluster_size = 0;
   int32_t correction = 0;  // var_mean's correction (B200NORM_F_STAT_VAR), travels in desc.reserved[0]
   double dropout_keep = 1.0;  // B200NORM_F_DROPOUT: keep probability 1 - p, travels in desc.reserved[1..2]
+  int32_t ignore_index = -100;  // cross-entropy (REDUCE_NLL / NLL_SOFTMAX_BWD): at::nll_loss's ignore_index, desc.reserved[3]
 };
 
 class NormExecutor {

@@ -215,7 +215,21 @@ __global__ void __launch_bounds__(kGenericThreads) generic_row_kernel(const RowP
     } else if constexpr (OP == G_REDUCE_INNER) {
       // sum / amax / fmax over the row -> stat1-less: result goes to out0[row] (io dtype)
       T* r = static_cast<T*>(p.out0);
-      if (p.flags & (kFlagReduceMax | kFlagReduceFmax)) {
+      if (p.flags & kFlagReduceNll) {  // cross-entropy forward (see reduce_inner_ring_kernel)
+        float m[1] = {-INFINITY};
+        for (int c = tid; c < N; c += kGenericThreads) m[0] = MaxOp::apply(m[0], IO<T>::to_f32(a[c]));
+        block_allreduce<MaxOp, 1>(m, red, phase);
+        float s[1] = {0.f};
+        for (int c = tid; c < N; c += kGenericThreads) s[0] += exp_for<T>(IO<T>::to_f32(a[c]) - m[0]);
+        block_allreduce<SumOp, 1>(s, red, phase);
+        if (tid == 0) {
+          const long long t = p.target[row];
+          const bool valid = t != (long long)p.ignore_index && t >= 0 && t < (long long)N;
+          const float lse = m[0] + logf(s[0]);
+          if (p.stat1 != nullptr) p.stat1[row] = valid ? lse - IO<T>::to_f32(a[t]) : 0.f;
+          if (p.stat0 != nullptr) p.stat0[row] = lse;
+        }
+      } else if (p.flags & (kFlagReduceMax | kFlagReduceFmax)) {
         const bool nan_prop = (p.flags & kFlagReduceMax) != 0;
         float m[2] = {-INFINITY, 0.f};  // m[1] counts non-NaN elements (for all-NaN rows under fmax)
         if (nan_prop) {
@@ -242,6 +256,84 @@ __global__ void __launch_bounds__(kGenericThreads) generic_row_kernel(const RowP
         for (int c = tid; c < N; c += kGenericThreads) s[0] += IO<T>::to_f32(a[c]);
         block_allreduce<SumOp, 1>(s, red, phase);
         if (tid == 0) r[row] = IO<T>::from_f32(s[0]);
+      }
+    }
+  }
+}
+
+// Cross-entropy backward (B200NORM_OP_NLL_SOFTMAX_BWD): dx = (exp(x - lse) - onehot(target)) * g, zero rows where the
+// target is ignored. Pointwise given the saved log-sum-exp: no ring, no reduction — a work item is (row, block of
+// kCeU * 256 chunks); every thread keeps kCeU 16-byte loads in flight. VEC = 1 is the element-wise form for rows
+// that are not whole aligned chunks.
+constexpr int kCeThreads = 256;
+constexpr int kCeU = 4;
+struct CeBwdParams {
+  const void* x;
+  void* dx;
+  int64_t x_stride, dx_stride;  // elements
+  const long long* target;
+  const float* lse;
+  const float* gscale;  // device scalar
+  int64_t rows;
+  int32_t cols;
+  int32_t ignore_index;
+};
+template <typename T, bool VECTOR>
+__global__ void __launch_bounds__(kCeThreads) cross_entropy_bwd_kernel(const CeBwdParams p) {
+  constexpr int VEC = VECTOR ? IO<T>::VEC : 1;
+  const int units_per_row = (p.cols + VEC - 1) / VEC;                     // 16-byte chunks (or elements)
+  const int items_per_row = (units_per_row + kCeThreads * kCeU - 1) / (kCeThreads * kCeU);
+  const int64_t items = p.rows * (int64_t)items_per_row;
+  const float g0 = __ldg(p.gscale);
+  for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+    const int64_t row = item / items_per_row;
+    const int cb = (int)(item - row * items_per_row);
+    const long long t = __ldg(p.target + row);
+    const bool valid = t != (long long)p.ignore_index && t >= 0 && t < (long long)p.cols;
+    const float gs = valid ? g0 : 0.f;
+    const float lse = __ldg(p.lse + row);
+    const T* xr = static_cast<const T*>(p.x) + row * p.x_stride;
+    T* dr = static_cast<T*>(p.dx) + row * p.dx_stride;
+    const int u0 = cb * kCeThreads * kCeU + (int)threadIdx.x;
+    if constexpr (VECTOR) {
+      constexpr int H = VEC / 2;
+      uint4 q[kCeU];
+#pragma unroll
+      for (int u = 0; u < kCeU; ++u) {
+        const int unit = u0 + u * kCeThreads;
+        if (unit < units_per_row) q[u] = ldg_128_nc(reinterpret_cast<const uint8_t*>(xr) + 16 * (size_t)unit);
+      }
+#pragma unroll
+      for (int u = 0; u < kCeU; ++u) {
+        const int unit = u0 + u * kCeThreads;
+        if (unit >= units_per_row) continue;
+        float2 v[H];
+        IO<T>::unpack2(q[u], v);
+        const int c0 = unit * VEC;
+#pragma unroll
+        for (int k = 0; k < H; ++k) {
+          v[k].x = exp_for<T>(v[k].x - lse) * gs;
+          v[k].y = exp_for<T>(v[k].y - lse) * gs;
+        }
+        if (valid && t >= c0 && t < c0 + VEC) {
+          const int e = (int)(t - c0);
+#pragma unroll
+          for (int k = 0; k < H; ++k) {
+            if (e == 2 * k) v[k].x -= gs;
+            if (e == 2 * k + 1) v[k].y -= gs;
+          }
+        }
+        stg_128_stream(reinterpret_cast<uint8_t*>(dr) + 16 * (size_t)unit, IO<T>::pack2(v));
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < kCeU; ++u) {
+        const int c = u0 + u * kCeThreads;
+        if (c < p.cols) {
+          float y = exp_for<T>(IO<T>::to_f32(xr[c]) - lse) * gs;
+          if (valid && c == t) y -= gs;
+          dr[c] = IO<T>::from_f32(y);
+        }
       }
     }
   }

@@ -35,6 +35,7 @@ __global__ void __launch_bounds__(kMaxBlock, 1) reduce_inner_ring_kernel(const R
   const bool is_max = (p.flags & kFlagReduceMax) != 0;
   const bool is_fmax = (p.flags & kFlagReduceFmax) != 0;
   const bool stats = (p.flags & kFlagNoY) != 0;  // LAYERNORM_FWD | NO_Y routed here: mean + variance / M2 per row
+  const bool nll = (p.flags & kFlagReduceNll) != 0;  // cross-entropy forward: log-sum-exp and the target's logit
   const bool writer = g.gtid == 0 && g.crank == 0;
   T* out = static_cast<T*>(p.out0);
 
@@ -76,6 +77,63 @@ __global__ void __launch_bounds__(kMaxBlock, 1) reduce_inner_ring_kernel(const R
         if (writer) {
           if (p.stat0 != nullptr) p.stat0[ring.row0 + r] = mean;
           if (p.stat1 != nullptr) p.stat1[ring.row0 + r] = ln_second_stat(p, m2, rsqrt_fast(m2 * p.inv_n + p.eps));
+        }
+        continue;
+      }
+      if (nll) {
+        // cross-entropy forward: lse = max + log(sum exp(x - max)), loss = lse - x[target]. The target's logit is
+        // read from the stage before the stage can be refilled, by the first thread of the CTA whose slice holds it.
+        const long long t = p.target[ring.row0 + r];
+        const bool valid = t != (long long)p.ignore_index && t >= 0 && t < (long long)p.cols;
+        const uint32_t owner = valid ? (uint32_t)(t / p.cols_cta) : 0u;
+        float xt = 0.f;
+        if (g.gtid == 0 && valid && g.crank == owner)
+          xt = IO<T>::to_f32(reinterpret_cast<const T*>(xrow)[t - (long long)owner * p.cols_cta]);
+        // ONE pass over the stage and ONE exchange per row: every thread keeps an online (max, sum of exp) pair over
+        // its chunks — the sum is rescaled when a chunk raises the maximum — and the pairs are merged exactly
+        // (Group::softmax_allreduce). Nothing is written per element, so unlike the softmax forward (where this form
+        // measured slower) the rescaling is per chunk and thread, not per output.
+        float mt = -INFINITY, st = 0.f;
+        for_each_chunk<TPR, CH>(g.gtid, nchunks, [&](int, int coff) {
+          float2 tt[H];
+          IO<T>::unpack2(ld_smem_u4(xrow + 16 * coff), tt);
+          // (plain fmaxf: a NaN logit reaches the result through exp(NaN) in the sum, no NaN-aware maximum needed)
+          float cm = fmaxf(tt[0].x, tt[0].y);
+#pragma unroll
+          for (int k = 1; k < H; ++k) cm = fmaxf(cm, fmaxf(tt[k].x, tt[k].y));
+          const float mn = fmaxf(mt, cm);
+          float2 acc = f2(0.f);
+          if constexpr (sizeof(T) == 2) {
+            // exp(x - m) = 2^(x * log2e - m * log2e): one packed FMA per pair in front of the MUFU
+            constexpr float kLog2e = 1.4426950408889634f;
+            const float2 nm = f2(mn == -INFINITY ? 0.f : -mn * kLog2e);  // all -inf so far: 2^(-inf - 0) = 0, not 2^NaN
+            const float2 l2 = f2(kLog2e);
+#pragma unroll
+            for (int k = 0; k < H; ++k) {
+              const float2 d = f2fma(tt[k], l2, nm);
+              float e0, e1;
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(d.x));
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(d.y));
+              acc = f2add(acc, make_float2(e0, e1));
+            }
+          } else {
+            const float2 nm = f2(mn == -INFINITY ? 0.f : -mn);
+#pragma unroll
+            for (int k = 0; k < H; ++k) {
+              const float2 d = f2add(tt[k], nm);
+              acc = f2add(acc, make_float2(exp_for<T>(d.x), exp_for<T>(d.y)));
+            }
+          }
+          st = fmaf(st, Group<TPR>::template softmax_rescale<T>(mt, mn), acc.x + acc.y);
+          mt = mn;
+        });
+        g.template softmax_allreduce<T>(mt, st);
+        float m[1] = {mt}, s[1] = {st};
+        if (r == nrows - 1) ring.refill();
+        const float lse = m[0] + logf(s[0]);
+        if (g.gtid == 0 && g.crank == owner) {
+          if (p.stat1 != nullptr) p.stat1[ring.row0 + r] = valid ? lse - xt : 0.f;
+          if (p.stat0 != nullptr) p.stat0[ring.row0 + r] = lse;
         }
         continue;
       }

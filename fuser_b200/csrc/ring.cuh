@@ -62,6 +62,7 @@ constexpr uint32_t kFlagNoY = 1u << 20;
 constexpr uint32_t kFlagStatVar = 1u << 21;
 constexpr uint32_t kFlagStatM2 = 1u << 22;
 constexpr uint32_t kFlagDropout = 1u << 23;
+constexpr uint32_t kFlagReduceNll = 1u << 24;
 // internal (never set through the ABI: check_desc refuses unknown bits), tuning knobs of the launch
 constexpr uint32_t kFlagOneExchange = 1u << 31;  // cluster softmax forward: (max, sum) pairs in ONE exchange (B200NORM_SM_ONE_EXCH)
 
@@ -82,6 +83,9 @@ struct RowParams {
   uint32_t drop_t1, drop_t2;    // keep <=> word <= t1 || word >= t2
   float drop_scale;             // 1 / keep probability
   int32_t drop_streams;         // backward ring kernels: every stage also carries the residual slice and the mask bytes
+  // cross-entropy (kFlagReduceNll): per-row targets; stat0 = lse out, stat1 = loss out
+  const long long* target;
+  int32_t ignore_index;
   const void* weight;  // [N] io dtype or nullptr
   const void* bias;    // [N] io dtype or nullptr
   float* stat0;        // fwd: mean out (LN) ; bwd: mean in (LN)

@@ -46,20 +46,21 @@ def _dtype_id(t: torch.Tensor) -> int:
 
 
 def _run(op: int, flags: int, eps: float, variant: int, cluster_size: int, ins: Sequence[torch.Tensor],
-         outs: Sequence[torch.Tensor] = (), correction: int = 0, dropout_keep: float = 1.0):
+         outs: Sequence[torch.Tensor] = (), correction: int = 0, dropout_keep: float = 1.0, ignore_index: int = -100):
     """Hand the segment to the C++ NormExecutor (csrc/host/norm_executor.cpp): it allocates
     the outputs, sizes the workspace and launches on the current stream."""
     if variant == L.VARIANT_AUTO:
         variant = _forced_variant
     if cluster_size == 0:
         cluster_size = _forced_cluster
-    return H.run(op, flags, float(eps), variant, cluster_size, ins, outs, correction, float(dropout_keep))
+    return H.run(op, flags, float(eps), variant, cluster_size, ins, outs, correction, float(dropout_keep), int(ignore_index))
 
 
 def plan_for(op: int, dtype: torch.dtype, rows: int, cols: int, flags: int = 0, eps: float = 0.0,
-             variant: int = L.VARIANT_AUTO, cluster_size: int = 0, correction: int = 0, dropout_keep: float = 1.0) -> dict:
+             variant: int = L.VARIANT_AUTO, cluster_size: int = 0, correction: int = 0, dropout_keep: float = 1.0,
+             ignore_index: int = -100) -> dict:
     """Dispatch decision for a segment (no launch): the launch_param dump of this library."""
-    d = L.make_desc(op, _DT[dtype], rows, cols, eps, flags, variant, cluster_size, correction, dropout_keep)
+    d = L.make_desc(op, _DT[dtype], rows, cols, eps, flags, variant, cluster_size, correction, dropout_keep, ignore_index)
     return L.query(d).as_dict()
 
 
@@ -343,3 +344,46 @@ def dropout_rms_norm_bwd(dy, x, residual, mask, stat, weight, p: float, *, stat_
     dres = next(outs) if want_dx else None
     dw = next(outs) if want_dw else None
     return dx, dres, dw
+
+
+# ---------------------------------------------------------------------------
+# cross-entropy over vocabulary-size rows: fused log-softmax + NLL, and its backward
+# (benchmarks/python/cross_entropy_loss.py: F.cross_entropy(logits.view(-1, V), labels.view(-1)))
+# ---------------------------------------------------------------------------
+def nll_softmax_fwd(logits, target, ignore_index: int = -100, *, variant=L.VARIANT_AUTO, cluster_size=0):
+    """Per-row loss = logsumexp(x) - x[target] (0 where target == ignore_index) and the saved log-sum-exp, both fp32
+    of shape ``logits.shape[:-1]``: one read of the logits, the log-probabilities are never materialised."""
+    loss, lse = _run(L.OP_REDUCE_INNER, L.F_REDUCE_NLL, 0.0, variant, cluster_size, [logits, target],
+                     ignore_index=ignore_index)
+    return loss, lse
+
+
+def nll_softmax_bwd(logits, target, lse, grad_scale, ignore_index: int = -100, *, variant=L.VARIANT_AUTO):
+    """dx = (softmax(x) - onehot(target)) * grad_scale (a device fp32 scalar: dloss / count), zero rows where the
+    target is ignored."""
+    (dx,) = _run(L.OP_NLL_SOFTMAX_BWD, 0, 0.0, variant, 0, [logits, target, lse, grad_scale], ignore_index=ignore_index)
+    return dx
+
+
+def cross_entropy_fwd(logits, target, ignore_index: int = -100, reduction: str = "mean", **kw):
+    """F.cross_entropy(logits, target, ignore_index=..., reduction=...) -> (loss, lse, count). The per-row losses come
+    from :func:`nll_softmax_fwd`; their sum is one more row reduction of this library (fp32, [1, M])."""
+    rows, lse = nll_softmax_fwd(logits, target, ignore_index, **kw)
+    if reduction == "none":
+        return rows, lse, None
+    total = reduce_inner(rows.reshape(1, -1), "sum").reshape(())
+    count = (target != ignore_index).sum()
+    if reduction == "sum":
+        return total, lse, count
+    if reduction != "mean":
+        raise ValueError(f"reduction {reduction!r}")
+    return total / count.to(total.dtype), lse, count
+
+
+def cross_entropy_bwd(logits, target, lse, count=None, grad_output=None, ignore_index: int = -100, **kw):
+    """Gradient of :func:`cross_entropy_fwd` w.r.t. the logits: ``count`` given = mean reduction (g = grad / count),
+    absent = sum reduction."""
+    g = torch.ones((), dtype=torch.float32, device=logits.device) if grad_output is None else grad_output.to(torch.float32)
+    if count is not None:
+        g = g / count.to(torch.float32)
+    return nll_softmax_bwd(logits, target, lse, g.reshape(1).contiguous(), ignore_index, **kw)

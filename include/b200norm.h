@@ -79,6 +79,7 @@ typedef enum {
   B200NORM_OP_REDUCE_OUTER = 9, /* [M,N] -> [N]   sum (the dgamma/dbeta shape) */
   B200NORM_OP_FINALIZE_PARTIALS = 10, /* fp32 [K,N] sums -> io dtype (after allreduce) */
   B200NORM_OP_PEER_COMBINE = 11, /* finish the oldest outstanding PEER_PUBLISH: K tensors [N] io dtype */
+  B200NORM_OP_NLL_SOFTMAX_BWD = 12, /* backward of REDUCE_INNER | B200NORM_F_REDUCE_NLL (cross-entropy backward) */
   B200NORM_OP_COUNT_
 } b200norm_op;
 
@@ -185,7 +186,15 @@ enum {
    * Backward: residual[M,N] and mask[M,N] follow the other inputs; x_eff = residual + dropout(x) is rebuilt, and the
    * outputs are d x (= d x_eff * mask / (1 - p)), then d residual (= d x_eff), then dweight / dbias.
    * The keep probability 1 - p (the double scalar of the fusion) travels in desc.reserved[1..2] (low, high word). */
-  B200NORM_F_DROPOUT = 1u << 23
+  B200NORM_F_DROPOUT = 1u << 23,
+  /* REDUCE_INNER: the fused log-softmax + NLL of a cross-entropy loss over vocabulary-size rows (SURVEY 8f rank 2:
+   * benchmarks/python/cross_entropy_loss.py; log_softmax csrc/ops/normalization.cpp:212-231 followed by the gather of
+   * the target's entry): per row  lse = log(sum exp(x)),  loss = lse - x[target]  (0 where target == ignore_index,
+   * desc.reserved[3]; at::nll_loss semantics). One read of the logits, two fp32 values per row out; the [M,N]
+   * log-probabilities are never written. Backward: B200NORM_OP_NLL_SOFTMAX_BWD,
+   *     dx[i,j] = (exp(x[i,j] - lse[i]) - [j == target[i]]) * g,   g = a device fp32 scalar (dloss / count),
+   * zero rows where target == ignore_index. */
+  B200NORM_F_REDUCE_NLL = 1u << 24
 };
 
 /* desc.variant: 0 lets the library choose (the dispatch rule mirrors the accept
@@ -265,6 +274,8 @@ typedef struct {
  *   SOFTMAX_BWD / LOGSOFTMAX_BWD   in : dy[M,N], y[M,N]      out: dx[M,N]
  *       (with B200NORM_F_OUTER the four softmax ops reduce over M instead of N; same tensors)
  *   REDUCE_INNER   in : x[M,N]                               out: r[M]   (io dtype)
+ *       with REDUCE_NLL: in : x[M,N], target[M] (int64)        out: loss[M] fp32, lse[M] fp32
+ *   NLL_SOFTMAX_BWD in: x[M,N], target[M] (int64), lse[M] fp32, g[1] fp32   out: dx[M,N]
  *   REDUCE_OUTER   in : x[M,N]                               out: r[N]   (io dtype, or fp32 with PARTIALS_F32)
  *   FINALIZE_PARTIALS in: p[K,N] fp32 (rows=K)               out: K tensors [N] io dtype
  *   PEER_COMBINE   in : -  (rows=K, cols=N)                  out: K tensors [N] io dtype

@@ -566,3 +566,25 @@ def dropout_norm_bwd(kind: str, dy, x, residual, mask, mean, stat, weight, keep:
     dx = (dxe * scale) * mask.to(torch.float32)
     cast = lambda t: None if t is None else t.to(io)  # noqa: E731
     return dx.to(io), dxe.to(io), cast(dw), cast(db)
+
+
+# ---------------------------------------------------------------------------
+# cross-entropy (benchmarks/python/cross_entropy_loss.py: torch.nn.functional.cross_entropy on the logits)
+# ---------------------------------------------------------------------------
+def nll_softmax_fwd(logits, target, ignore_index: int = -100):
+    """(per-row loss, log-sum-exp) in fp32: log_softmax (csrc/ops/normalization.cpp:212-231 on the Float upcast)
+    followed by at::nll_loss(reduction='none')."""
+    xf = _up(logits)
+    lse = torch.logsumexp(xf, dim=-1)
+    loss = torch.nn.functional.nll_loss(torch.log_softmax(xf, dim=-1).reshape(-1, xf.shape[-1]), target.reshape(-1),
+                                        ignore_index=ignore_index, reduction="none").reshape(target.shape)
+    return loss, lse
+
+
+def cross_entropy_bwd(logits, target, ignore_index: int = -100, reduction: str = "mean"):
+    """d loss / d logits through autograd on the Float upcast, cast to the io dtype."""
+    xf = _up(logits).clone().requires_grad_(True)
+    loss = torch.nn.functional.cross_entropy(xf.reshape(-1, xf.shape[-1]), target.reshape(-1), ignore_index=ignore_index,
+                                             reduction=reduction)
+    loss.backward()
+    return xf.grad.to(logits.dtype), loss.detach()
