@@ -75,6 +75,7 @@ F_STAT_VAR = 1 << 21
 F_STAT_M2 = 1 << 22
 F_DROPOUT = 1 << 23
 F_REDUCE_NLL = 1 << 24
+F_ROW_AFFINE = 1 << 25
 
 VARIANT_AUTO, VARIANT_GENERIC, VARIANT_TMA, VARIANT_CLUSTER = 0, 1, 2, 3
 FORM_CACHED, FORM_PIPE, FORM_PSMEM, FORM_FUSED_FINISH = 1, 2, 4, 8

@@ -170,6 +170,7 @@ bool is_row_op(int op) {  // ops with a TMA-ring kernel family
 // ops that keep per-thread column accumulators and finish fp32 column sums (dgamma / dbeta, plain column sums)
 bool has_column_sums(const b200norm_desc& d) {
   if (d.op == B200NORM_OP_REDUCE_OUTER) return true;
+  if (d.flags & B200NORM_F_ROW_AFFINE) return false;  // instance norm: per-row sums, written by the row kernel itself
   return (d.op == B200NORM_OP_LAYERNORM_BWD || d.op == B200NORM_OP_RMSNORM_BWD) &&
          (d.flags & (B200NORM_F_OUT_DW | B200NORM_F_OUT_DB)) != 0;
 }
@@ -551,7 +552,7 @@ bool try_ring_plan(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, int 
   const bool ln_pipe = d.op == B200NORM_OP_LAYERNORM_FWD && !inner_red && ch > 0 && nchunks == tpr * ch && tile_rows == 1 &&
                        tpr >= 64 && kn.no_ln_pipe == 0 && !dropout;
   bool want_psmem = d.op == B200NORM_OP_LAYERNORM_FWD && ch > 0 && es == 2 && slice_cols <= 8192 &&
-                    kn.no_psmem == 0 && !ln_pipe && !inner_red && !dropout;
+                    kn.no_psmem == 0 && !ln_pipe && !inner_red && !dropout && !(d.flags & B200NORM_F_ROW_AFFINE);
   const uint32_t param_bytes = align_up(2u * (uint32_t)slice_cols * 4u, 128);
 
   // Ring depth D (stages per group); the ring is group-major, stage (g*D + s).
@@ -598,7 +599,7 @@ bool try_ring_plan(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, int 
   // first pass: C5 335 -> 320 us) and fp32 rows ([16384,8192] 273 -> 248 us); the 16-bit
   // single-CTA case is bound by instruction issue, not by the reduction latency, and loses 4 %
   // (C4 420 -> 440 us), so it keeps the plain kernel. B200NORM_PIPE=1 / B200NORM_NO_PIPE=1 force it.
-  p.pipe = bwd && !cached && !dropout && tile_rows == 1 && tpr >= 64 && kn.no_pipe == 0 &&
+  p.pipe = bwd && !cached && !dropout && !(d.flags & B200NORM_F_ROW_AFFINE) && tile_rows == 1 && tpr >= 64 && kn.no_pipe == 0 &&
            (C > 1 || es == 4 || kn.pipe != 0);
   // RMSNorm forward over a cluster: the same pipeline (the row is read twice from its stage instead
   // of being held in registers, so the next row's sum of squares overlaps the DSMEM exchange)
@@ -841,7 +842,16 @@ int check_desc(const b200norm_desc* d) {
   if (d->op < 0 || d->op >= B200NORM_OP_COUNT_) return fail(B200NORM_ERR_UNSUPPORTED, "unknown op %d", d->op);
   if (d->io_dtype < 0 || d->io_dtype > B200NORM_DT_F16)
     return fail(B200NORM_ERR_UNSUPPORTED, "unsupported io dtype %d", d->io_dtype);
-  if (d->flags >> 25) return fail(B200NORM_ERR_BAD_ARG, "unknown flag bits 0x%x", d->flags & ~((1u << 25) - 1u));
+  if (d->flags >> 26) return fail(B200NORM_ERR_BAD_ARG, "unknown flag bits 0x%x", d->flags & ~((1u << 26) - 1u));
+  if (d->flags & B200NORM_F_ROW_AFFINE) {
+    if (d->op != B200NORM_OP_LAYERNORM_FWD && d->op != B200NORM_OP_LAYERNORM_BWD)
+      return fail(B200NORM_ERR_UNSUPPORTED, "B200NORM_F_ROW_AFFINE (instance norm) applies to the LayerNorm ops");
+    if (d->flags & (B200NORM_F_OUTER | B200NORM_F_NO_Y | B200NORM_F_ADD_RESIDUAL | B200NORM_F_DROPOUT | B200NORM_F_PARTIALS_F32 |
+                    B200NORM_F_PEER_REDUCE | B200NORM_F_PEER_PUBLISH))
+      return fail(B200NORM_ERR_UNSUPPORTED, "B200NORM_F_ROW_AFFINE excludes OUTER, NO_Y, ADD_RESIDUAL, DROPOUT, PARTIALS_F32 and the peer flags");
+    if (d->reserved[3] < 1 || (d->rows % d->reserved[3]) != 0)
+      return fail(B200NORM_ERR_BAD_ARG, "instance norm: rows (%lld) must be a multiple of the channel count (%d)", (long long)d->rows, d->reserved[3]);
+  }
   if (d->flags & B200NORM_F_REDUCE_NLL) {
     if (d->op != B200NORM_OP_REDUCE_INNER)
       return fail(B200NORM_ERR_UNSUPPORTED, "B200NORM_F_REDUCE_NLL is a flavour of REDUCE_INNER");
@@ -1011,7 +1021,7 @@ int launch_typed(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, const 
     } else if (d.op == B200NORM_OP_FINALIZE_PARTIALS) {
       launch_finalize<T>(static_cast<const float*>(rp.in0), 1, (int)d.rows, (int)d.cols, dw, db, nullptr, stream);
     } else {
-      const bool need_rows = !is_norm_bwd(d.op) || (d.flags & B200NORM_F_OUT_DX);
+      const bool need_rows = !is_norm_bwd(d.op) || (d.flags & (B200NORM_F_OUT_DX | B200NORM_F_ROW_AFFINE));
       if (need_rows) {
         RingKernel k = generic_kernel_for<T>(d.op);
         if (k == nullptr) return fail(B200NORM_ERR_UNSUPPORTED, "no generic kernel for op %d", d.op);
@@ -1418,6 +1428,8 @@ int b200norm_launch(const b200norm_desc* desc, const b200norm_tensor* inputs, in
   }
   rp.flags = d.flags;
   if (kn.sm_one_exch != 0) rp.flags |= kFlagOneExchange;
+  const bool row_aff = (d.flags & B200NORM_F_ROW_AFFINE) != 0;
+  rp.channels = row_aff ? d.reserved[3] : 0;
   const bool dropout = (d.flags & B200NORM_F_DROPOUT) != 0;
   if (dropout) {
     const double keep = dropout_keep_prob(d);
@@ -1498,15 +1510,15 @@ int b200norm_launch(const b200norm_desc* desc, const b200norm_tensor* inputs, in
       if (add) CHECK(bind_in_matrix(&rp.in1, &rp.in1_stride, "residual"));
       if (has_w) {
         void* w = nullptr;
-        CHECK(bind_vec(inputs[ii++], d.cols, dt, "weight", &w));
+        CHECK(bind_vec(inputs[ii++], row_aff ? (int64_t)rp.channels : d.cols, dt, "weight", &w));
         rp.weight = w;
-        if (!is_aligned16(w)) aligned = false;
+        if (!row_aff && !is_aligned16(w)) aligned = false;
       }
       if (ln && has_b) {
         void* b = nullptr;
-        CHECK(bind_vec(inputs[ii++], d.cols, dt, "bias", &b));
+        CHECK(bind_vec(inputs[ii++], row_aff ? (int64_t)rp.channels : d.cols, dt, "bias", &b));
         rp.bias = b;
-        if (!is_aligned16(b)) aligned = false;
+        if (!row_aff && !is_aligned16(b)) aligned = false;
       }
       const bool no_y = ln && (d.flags & B200NORM_F_NO_Y) != 0;
       if (!no_y) {
@@ -1567,9 +1579,9 @@ int b200norm_launch(const b200norm_desc* desc, const b200norm_tensor* inputs, in
       }
       if (has_w) {
         void* w = nullptr;
-        CHECK(bind_vec(inputs[ii++], d.cols, dt, "weight", &w));
+        CHECK(bind_vec(inputs[ii++], row_aff ? (int64_t)rp.channels : d.cols, dt, "weight", &w));
         rp.weight = w;
-        if (!is_aligned16(w)) aligned = false;
+        if (!row_aff && !is_aligned16(w)) aligned = false;
       }
       if (dropout) {
         NEED_IN(2);
@@ -1588,7 +1600,20 @@ int b200norm_launch(const b200norm_desc* desc, const b200norm_tensor* inputs, in
       }
       const bool want_dw = (d.flags & B200NORM_F_OUT_DW) != 0;
       const bool want_db = ln && (d.flags & B200NORM_F_OUT_DB) != 0;
-      if ((want_dw || want_db) && (d.flags & B200NORM_F_PEER_PUBLISH)) {
+      if (row_aff) {  // instance norm: per-row sums (fp32 [M]) instead of column sums
+        void* v = nullptr;
+        if (want_dw) {
+          NEED_OUT(1);
+          CHECK(bind_vec(outputs[oi++], d.rows, B200NORM_DT_F32, "rowsum(dy * x_hat)", &v));
+          rp.rowsum_dyxh = static_cast<float*>(v);
+        }
+        if (want_db) {
+          NEED_OUT(1);
+          CHECK(bind_vec(outputs[oi++], d.rows, B200NORM_DT_F32, "rowsum(dy)", &v));
+          rp.rowsum_dy = static_cast<float*>(v);
+        }
+        rp.flags &= ~(uint32_t)(B200NORM_F_OUT_DW | B200NORM_F_OUT_DB);  // the kernels' column accumulators stay off
+      } else if ((want_dw || want_db) && (d.flags & B200NORM_F_PEER_PUBLISH)) {
         if (d.flags & (B200NORM_F_PARTIALS_F32 | B200NORM_F_PEER_REDUCE))
           return fail(B200NORM_ERR_BAD_ARG, "PEER_PUBLISH excludes PARTIALS_F32 and PEER_REDUCE");
         // the sums go to the exchange slot only; OP_PEER_COMBINE produces the tensors

@@ -141,6 +141,7 @@ std::vector<at::Tensor> NormExecutor::allocateOutputs(const std::vector<at::Tens
   const auto f32 = opts.dtype(at::kFloat);
   auto stat_shape = [&](const at::Tensor& x) {
     if (f & B200NORM_F_OUTER) return std::vector<int64_t>{cols};  // one statistic per column (keepdim = false)
+    if (f & B200NORM_F_ROW_AFFINE) return std::vector<int64_t>{x.size(0), (int64_t)spec_.ignore_index};  // [B, C]
     std::vector<int64_t> s(x.sizes().begin(), x.sizes().end());
     s.back() = 1;
     return s;
@@ -174,7 +175,10 @@ std::vector<at::Tensor> NormExecutor::allocateOutputs(const std::vector<at::Tens
       if ((f & B200NORM_F_OUT_DX) && (f & B200NORM_F_DROPOUT)) out.push_back(at::empty(in.at(1).sizes(), opts));  // d residual
       const bool want_dw = (f & B200NORM_F_OUT_DW) != 0;
       const bool want_db = ln && (f & B200NORM_F_OUT_DB) != 0;
-      if ((want_dw || want_db) && !(f & B200NORM_F_PEER_PUBLISH)) {  // a publish leaves the sums in the exchange slot
+      if (f & B200NORM_F_ROW_AFFINE) {  // instance norm: per-row sums [B, C] fp32 (the caller adds them over the batch)
+        if (want_dw) out.push_back(at::empty(stat_shape(in.at(1)), f32));
+        if (want_db) out.push_back(at::empty(stat_shape(in.at(1)), f32));
+      } else if ((want_dw || want_db) && !(f & B200NORM_F_PEER_PUBLISH)) {  // a publish leaves the sums in the exchange slot
         if (f & B200NORM_F_PARTIALS_F32) {
           out.push_back(at::empty({ln ? 2 : 1, cols}, f32));
         } else {
@@ -242,6 +246,14 @@ std::vector<at::Tensor> NormExecutor::run(const std::vector<at::Tensor>& inputs,
     cols = rows > 0 ? lead.numel() / rows : 0;
     if (rows == 0)
       for (int64_t i = 1, c = 1; i < lead.dim(); ++i) cols = (c *= lead.size(i));
+    dt = dtype_id(lead.scalar_type());
+  } else if (spec_.flags & B200NORM_F_ROW_AFFINE) {
+    // instance norm, channels first: [B, C, spatial...] -> rows = B * C (sample, channel) pairs of the spatial extent
+    const int64_t ch = spec_.ignore_index;  // the channel count travels in desc.reserved[3]
+    if (lead.dim() < 3 || ch < 1 || lead.size(1) != ch)
+      raise_msg(B200NORM_ERR_BAD_ARG, "instance norm expects [B, C, spatial...] with C = the spec's channel count");
+    rows = lead.size(0) * ch;
+    cols = rows > 0 ? lead.numel() / rows : 0;
     dt = dtype_id(lead.scalar_type());
   } else {
     cols = lead.dim() > 0 ? lead.size(-1) : 1;

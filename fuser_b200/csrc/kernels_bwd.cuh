@@ -350,8 +350,11 @@ __global__ void __launch_bounds__(kMaxBlock, 1) norm_bwd_ring_kernel(const RowPa
   const bool centered = CEN && (LN || (p.flags & kFlagRmsBwdCentered) != 0);
   const bool stat_rms = !LN && (p.flags & kFlagStatIsRms) != 0;
   const size_t col0_bytes = (size_t)g.crank * p.slice_bytes;
+  // instance norm (kFlagRowAffine, LayerNorm only): the weight belongs to the row's channel — g = dy inside, the row's
+  // weight scales the finished dx, and the row sums of dy / dy * x_hat go out instead of column sums
+  const bool row_aff = LN && (p.flags & kFlagRowAffine) != 0;
   uint4 wq[CH];
-  load_params_to_regs<T, TPR, CH>(p.weight, col0_bytes, g.gtid, nchunks, 1.0f, wq);
+  load_params_to_regs<T, TPR, CH>(row_aff ? nullptr : p.weight, col0_bytes, g.gtid, nchunks, 1.0f, wq);
 
   float2 dw_acc[CH][H];
   float2 db_acc[LN ? CH : 1][H];
@@ -397,6 +400,7 @@ __global__ void __launch_bounds__(kMaxBlock, 1) norm_bwd_ring_kernel(const RowPa
         }
       }
       const float invstd = stat_rms ? rcp_fast(st) : st;
+      const float w_row = row_aff ? row_param<T>(p.weight, ring.row0 + r, p.channels, 1.f) : 1.f;
       const float2 nmean = f2(-mean);
       const float2 is2 = f2(invstd);
       // x_hat = (x - mean) * invstd. With 16-bit inputs it is one FMA, x*invstd + (-mean*invstd): the
@@ -452,7 +456,7 @@ __global__ void __launch_bounds__(kMaxBlock, 1) norm_bwd_ring_kernel(const RowPa
           }
         }
       });
-      if (want_dx) {
+      if (want_dx || row_aff) {
         float s[2] = {s1.x + s1.y, s2.x + s2.y};  // sum(g), sum(g * x_hat)
         if constexpr (CEN) {
           g.template allreduce<SumOp, 2>(s);
@@ -461,12 +465,18 @@ __global__ void __launch_bounds__(kMaxBlock, 1) norm_bwd_ring_kernel(const RowPa
           g.template allreduce<SumOp, 1>(t1);
           s[1] = t1[0];
         }
-        if (CACHE && r == nrows - 1) ring.refill();  // g / x_hat live in registers: the stage is free
+        if (CACHE && want_dx && r == nrows - 1) ring.refill();  // g / x_hat live in registers: the stage is free
+        if (row_aff && g.gtid == 0 && g.crank == 0) {
+          if (p.rowsum_dy != nullptr) p.rowsum_dy[ring.row0 + r] = s[0];
+          if (p.rowsum_dyxh != nullptr) p.rowsum_dyxh[ring.row0 + r] = s[1];
+        }
+        if (!want_dx) continue;
         // dx = invstd * g - (invstd/N) * sum(g x_hat) * x_hat - (invstd/N) * sum(g)  =  A g + B x_hat + C
-        const float a_n = invstd * p.inv_n;
+        // (instance norm: every term times the row's weight)
+        const float a_n = invstd * p.inv_n * w_row;
         const float b_s = -(a_n * s[1]) * p.proj_scale;
         const float c_s = centered ? -(a_n * s[0]) : 0.f;
-        const float2 A = is2;
+        const float2 A = f2(invstd * w_row);
         const float2 B = f2(b_s);
         const float2 C = f2(c_s);
         // re-read form: B x_hat + C folded onto x itself where x_hat is affine in x with exact-enough

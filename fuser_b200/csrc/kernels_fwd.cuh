@@ -138,6 +138,9 @@ __global__ void __launch_bounds__(kMaxBlock, 1) layernorm_fwd_ring_kernel(const 
   const int nchunks = p.nchunks;
   const size_t col0_bytes = (size_t)g.crank * p.slice_bytes;
   uint4 wq[PSMEM ? 1 : NC], bq[PSMEM ? 1 : NC];
+  // instance norm (kFlagRowAffine; never with PSMEM): the parameter registers are refilled per row with a splat of the
+  // row's channel pair
+  const bool row_aff = !PSMEM && (p.flags & kFlagRowAffine) != 0;
   const uint32_t off_w = p.off_param;
   const uint32_t off_b = p.off_param + (uint32_t)nchunks * (uint32_t)(VEC * 4);
   if constexpr (PSMEM) {
@@ -145,8 +148,8 @@ __global__ void __launch_bounds__(kMaxBlock, 1) layernorm_fwd_ring_kernel(const 
     stage_param_smem<T>(p.bias, col0_bytes, off_b, nchunks, -0.0f);
     __syncthreads();
   } else {
-    load_params_to_regs<T, TPR, CH>(p.weight, col0_bytes, g.gtid, nchunks, 1.0f, wq);
-    load_params_to_regs<T, TPR, CH>(p.bias, col0_bytes, g.gtid, nchunks, -0.0f, bq);
+    load_params_to_regs<T, TPR, CH>(row_aff ? nullptr : p.weight, col0_bytes, g.gtid, nchunks, 1.0f, wq);
+    load_params_to_regs<T, TPR, CH>(row_aff ? nullptr : p.bias, col0_bytes, g.gtid, nchunks, -0.0f, bq);
   }
   const bool stat_writer = g.gtid == 0 && g.crank == 0;
   const bool no_y = (p.flags & kFlagNoY) != 0;  // stand-alone var_mean / welford: statistics only
@@ -166,6 +169,11 @@ __global__ void __launch_bounds__(kMaxBlock, 1) layernorm_fwd_ring_kernel(const 
     for (int r = 0; r < nrows; ++r, xrow += p.slice_bytes, yrow += out_row_bytes, srow += sum_row_bytes) {
       float2 x[NC][H];
       float2 acc = f2(0.f);
+      float w_row = 1.f, b_row = 0.f;
+      if (row_aff) {
+        w_row = row_param<T>(p.weight, ring.row0 + r, p.channels, 1.f);
+        b_row = row_param<T>(p.bias, ring.row0 + r, p.channels, 0.f);
+      }
       // fused dropout: linear index of the row's first element of this CTA's slice
       const unsigned long long drop_lin =
           (unsigned long long)(ring.row0 + r) * (unsigned long long)p.cols + (unsigned long long)(g.crank * (uint32_t)p.cols_cta);
@@ -209,6 +217,16 @@ __global__ void __launch_bounds__(kMaxBlock, 1) layernorm_fwd_ring_kernel(const 
       g.template allreduce<SumOp, 1>(m2);
       const float invstd = rsqrt_fast(m2[0] * p.inv_n + p.eps);
       const float2 is2 = f2(invstd);
+      if constexpr (!PSMEM && CH > 0) {
+        if (row_aff) {
+          const uint4 ws = splat_chunk<T>(w_row), bs = splat_chunk<T>(b_row);
+#pragma unroll
+          for (int j = 0; j < NC; ++j) {
+            wq[j] = ws;
+            bq[j] = bs;
+          }
+        }
+      }
       if (!no_y) for_each_chunk<TPR, CH>(g.gtid, nchunks, [&](int j, int coff) {
         float2 y[H], w[H], b[H];
         if constexpr (CH > 0) {
@@ -224,8 +242,8 @@ __global__ void __launch_bounds__(kMaxBlock, 1) layernorm_fwd_ring_kernel(const 
         } else {
           IO<T>::unpack2(ld_smem_u4(xrow + 16 * coff), y);
           if constexpr (ADD) add_residual_chunk<T, H>(y, xrow + p.stream_bytes + 16 * coff, round_sum, nullptr);
-          IO<T>::unpack2(load_param_chunk<T>(p.weight, col0_bytes, g.gtid + coff, 1.0f), w);
-          IO<T>::unpack2(load_param_chunk<T>(p.bias, col0_bytes, g.gtid + coff, -0.0f), b);
+          IO<T>::unpack2(row_aff ? splat_chunk<T>(w_row) : load_param_chunk<T>(p.weight, col0_bytes, g.gtid + coff, 1.0f), w);
+          IO<T>::unpack2(row_aff ? splat_chunk<T>(b_row) : load_param_chunk<T>(p.bias, col0_bytes, g.gtid + coff, -0.0f), b);
 #pragma unroll
           for (int k = 0; k < H; ++k) y[k] = f2fma(f2mul(f2add(y[k], nmean), is2), w[k], b[k]);
         }

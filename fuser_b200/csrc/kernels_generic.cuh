@@ -137,10 +137,17 @@ __global__ void __launch_bounds__(kGenericThreads) generic_row_kernel(const RowP
       block_allreduce<SumOp, 1>(m2, red, phase);
       const float invstd = __frsqrt_rn(m2[0] * p.inv_n + p.eps);
       if (o != nullptr) {  // absent for a stand-alone var_mean / welford segment (kFlagNoY)
+        const bool row_aff = (p.flags & kFlagRowAffine) != 0;  // instance norm: the row's channel pair
+        const float w_row = row_aff ? row_param<T>(p.weight, row, p.channels, 1.f) : 1.f;
+        const float b_row = row_aff ? row_param<T>(p.bias, row, p.channels, 0.f) : 0.f;
         for (int c = tid; c < N; c += kGenericThreads) {
           float y = (xin(c) - mean) * invstd;
-          if (wgt != nullptr) y *= IO<T>::to_f32(wgt[c]);
-          if (bia != nullptr) y += IO<T>::to_f32(bia[c]);
+          if (row_aff) {
+            y = fmaf(y, w_row, b_row);
+          } else {
+            if (wgt != nullptr) y *= IO<T>::to_f32(wgt[c]);
+            if (bia != nullptr) y += IO<T>::to_f32(bia[c]);
+          }
           o[c] = IO<T>::from_f32(y);
         }
       }
@@ -187,6 +194,10 @@ __global__ void __launch_bounds__(kGenericThreads) generic_row_kernel(const RowP
       const float mean = LN ? p.stat0[row] : 0.f;
       const float st = p.stat1[row];
       const float invstd = (!LN && (p.flags & kFlagStatIsRms)) ? __frcp_rn(st) : st;
+      // instance norm: g = dy (the row's weight is a common factor of dx), row sums out instead of column sums
+      const bool row_aff = (p.flags & kFlagRowAffine) != 0;
+      const float w_row = row_aff ? row_param<T>(p.weight, row, p.channels, 1.f) : 1.f;
+      if (row_aff) wgt = nullptr;
       float s[2] = {0.f, 0.f};
       for (int c = tid; c < N; c += kGenericThreads) {
         const float xh = (xeff(c) - mean) * invstd;
@@ -197,7 +208,12 @@ __global__ void __launch_bounds__(kGenericThreads) generic_row_kernel(const RowP
       }
       block_allreduce<SumOp, 2>(s, red, phase);
       const float s1 = centered ? s[0] : 0.f;
-      const float aa = invstd * p.inv_n;
+      const float aa = invstd * p.inv_n * w_row;
+      if (row_aff && tid == 0) {
+        if (p.rowsum_dy != nullptr) p.rowsum_dy[row] = s[0];
+        if (p.rowsum_dyxh != nullptr) p.rowsum_dyxh[row] = s[1];
+      }
+      if (o == nullptr && !(drop_bwd && p.out1 != nullptr)) continue;
       T* o1 = drop_bwd && p.out1 != nullptr ? static_cast<T*>(p.out1) + row * p.out1_stride : nullptr;
       for (int c = tid; c < N; c += kGenericThreads) {
         const float xh = (xeff(c) - mean) * invstd;

@@ -53,18 +53,23 @@ __global__ void __launch_bounds__(kMaxBlock, 1) layernorm_fwd_pipe_kernel(const 
   const size_t col0_bytes = (size_t)g.crank * p.slice_bytes;
   uint4 wq[UNPACKED ? 1 : CH], bq[UNPACKED ? 1 : CH];
   float2 wf[UNPACKED ? CH : 1][H], bf[UNPACKED ? CH : 1][H];
+  // instance norm (kFlagRowAffine): the parameters belong to the row's channel — the same registers are refilled
+  // with a splat of that row's pair before each output pass, the arithmetic is untouched
+  const bool row_aff = (p.flags & kFlagRowAffine) != 0;
+  const void* wcol = row_aff ? nullptr : p.weight;
+  const void* bcol = row_aff ? nullptr : p.bias;
   if constexpr (UNPACKED) {
     uint4 tw[CH], tb[CH];
-    load_params_to_regs<T, TPR, CH>(p.weight, col0_bytes, g.gtid, p.nchunks, 1.0f, tw);
-    load_params_to_regs<T, TPR, CH>(p.bias, col0_bytes, g.gtid, p.nchunks, -0.0f, tb);
+    load_params_to_regs<T, TPR, CH>(wcol, col0_bytes, g.gtid, p.nchunks, 1.0f, tw);
+    load_params_to_regs<T, TPR, CH>(bcol, col0_bytes, g.gtid, p.nchunks, -0.0f, tb);
 #pragma unroll
     for (int j = 0; j < CH; ++j) {
       IO<T>::unpack2(tw[j], wf[j]);
       IO<T>::unpack2(tb[j], bf[j]);
     }
   } else {
-    load_params_to_regs<T, TPR, CH>(p.weight, col0_bytes, g.gtid, p.nchunks, 1.0f, wq);
-    load_params_to_regs<T, TPR, CH>(p.bias, col0_bytes, g.gtid, p.nchunks, -0.0f, bq);
+    load_params_to_regs<T, TPR, CH>(wcol, col0_bytes, g.gtid, p.nchunks, 1.0f, wq);
+    load_params_to_regs<T, TPR, CH>(bcol, col0_bytes, g.gtid, p.nchunks, -0.0f, bq);
   }
   const bool stat_writer = g.gtid == 0 && g.crank == 0;
   const bool no_y = (p.flags & kFlagNoY) != 0;  // stand-alone var_mean / welford: statistics only
@@ -159,6 +164,11 @@ __global__ void __launch_bounds__(kMaxBlock, 1) layernorm_fwd_pipe_kernel(const 
     if (k == 0) tl_mark(p, 2);
     const uint32_t par = (uint32_t)(k & 1), ph = (uint32_t)((k >> 1) & 1);
     const uint32_t cl_bar = par ? cl_bar_odd : cl_bar_even;
+    float w_row = 1.f, b_row = 0.f;  // requested before the waits below: off the critical path
+    if (row_aff) {
+      w_row = row_param<T>(p.weight, row, p.channels, 1.f);
+      b_row = row_param<T>(p.bias, row, p.channels, 0.f);
+    }
     // ---- collect1(k): the warps' pairs in closed form (fixed order: every thread gets the same bits) ----
     mbar_wait(red_bar + 8u * par, ph);
     float mean, m2;
@@ -198,6 +208,24 @@ __global__ void __launch_bounds__(kMaxBlock, 1) layernorm_fwd_pipe_kernel(const 
     // ---- second pass of row k: y = (x - mean) * invstd * w + b ----
     const uint8_t* xrow = smem_raw + c2_off + 16u * (uint32_t)g.gtid;
     const float2 is2 = f2(invstd), nmean = f2(-mean), nmi = f2(-mean * invstd);
+    if (row_aff) {
+#pragma unroll
+      for (int j = 0; j < (UNPACKED ? CH : 1); ++j) {
+#pragma unroll
+        for (int q = 0; q < H; ++q) {
+          wf[j][q] = f2(w_row);
+          bf[j][q] = f2(b_row);
+        }
+      }
+      if constexpr (!UNPACKED) {
+        const uint4 ws = splat_chunk<T>(w_row), bs = splat_chunk<T>(b_row);
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+          wq[j] = ws;
+          bq[j] = bs;
+        }
+      }
+    }
 #pragma unroll
     for (int j = 0; j < CH; ++j) {
       if (no_y) break;

@@ -63,6 +63,7 @@ constexpr uint32_t kFlagStatVar = 1u << 21;
 constexpr uint32_t kFlagStatM2 = 1u << 22;
 constexpr uint32_t kFlagDropout = 1u << 23;
 constexpr uint32_t kFlagReduceNll = 1u << 24;
+constexpr uint32_t kFlagRowAffine = 1u << 25;  // instance norm: weight / bias indexed by (row mod channels)
 // internal (never set through the ABI: check_desc refuses unknown bits), tuning knobs of the launch
 constexpr uint32_t kFlagOneExchange = 1u << 31;  // cluster softmax forward: (max, sum) pairs in ONE exchange (B200NORM_SM_ONE_EXCH)
 
@@ -83,6 +84,11 @@ struct RowParams {
   uint32_t drop_t1, drop_t2;    // keep <=> word <= t1 || word >= t2
   float drop_scale;             // 1 / keep probability
   int32_t drop_streams;         // backward ring kernels: every stage also carries the residual slice and the mask bytes
+  // instance norm (kFlagRowAffine): rows are (sample, channel) pairs, the affine parameters belong to the channel;
+  // backward: the per-row sums of dy and dy * x_hat go out instead of column sums (the caller adds them over the batch)
+  int32_t channels;
+  float* rowsum_dy;     // [M] fp32 or nullptr
+  float* rowsum_dyxh;   // [M] fp32 or nullptr
   // cross-entropy (kFlagReduceNll): per-row targets; stat0 = lse out, stat1 = loss out
   const long long* target;
   int32_t ignore_index;
@@ -829,6 +835,13 @@ __device__ __forceinline__ void add_residual_chunk(float2 (&t)[H], const uint8_t
       if (round_sum) IO<T>::unpack2(q, t);
     }
   }
+}
+
+// instance norm: the row's channel parameter (weight: identity 1, bias: identity 0), read through the read-only path
+template <typename T>
+__device__ __forceinline__ float row_param(const void* gp, int64_t row, int32_t channels, float identity) {
+  if (gp == nullptr) return identity;
+  return IO<T>::to_f32(__ldg(static_cast<const T*>(gp) + (row % channels)));
 }
 
 // Fused dropout of one 16-byte chunk (VEC = 2 * H consecutive elements starting at linear index `lin` of the [M,N]

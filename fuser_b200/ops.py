@@ -387,3 +387,54 @@ def cross_entropy_bwd(logits, target, lse, count=None, grad_output=None, ignore_
     if count is not None:
         g = g / count.to(torch.float32)
     return nll_softmax_bwd(logits, target, lse, g.reshape(1).contiguous(), ignore_index, **kw)
+
+
+# ---------------------------------------------------------------------------
+# instance norm (training statistics): csrc/ops/normalization.cpp:790-950 / :952-1060,
+# benchmarks/python/test_instancenorm_{fwd,bwd}.py
+# ---------------------------------------------------------------------------
+def instance_norm_fwd(x, weight=None, bias=None, eps: float = 1e-5, *, channels_last=False, variant=L.VARIANT_AUTO):
+    """y, mean[B, C], invstd[B, C] of instance_norm(x) with the statistics of each (sample, channel) plane.
+
+    channels first ([B, C, spatial...]): ONE launch — a LayerNorm over the rows of the [B*C, spatial] view whose
+    affine pair is the row's channel's (``B200NORM_F_ROW_AFFINE``). channels last ([B, spatial..., C]): per sample an
+    outer normalization of its [spatial, C] plane (``B200NORM_F_OUTER``), one launch per sample."""
+    if channels_last:
+        ys, means, invstds = [], [], []
+        for n in range(x.shape[0]):
+            y, mean, invstd = outer_norm_fwd(x[n], weight, bias, eps, variant=variant)
+            ys.append(y)
+            means.append(mean)
+            invstds.append(invstd)
+        return torch.stack(ys), torch.stack(means), torch.stack(invstds)
+    c = x.shape[1]
+    flags = (L.F_HAS_WEIGHT if weight is not None else 0) | (L.F_HAS_BIAS if bias is not None else 0)
+    flags |= L.F_OUT_MEAN | L.F_OUT_INVSTD | L.F_ROW_AFFINE
+    ins = [x.contiguous()] + [t for t in (weight, bias) if t is not None]
+    y, mean, invstd = _run(L.OP_LAYERNORM_FWD, flags, eps, variant, 0, ins, ignore_index=c)
+    return y, mean, invstd
+
+
+def instance_norm_bwd(dy, x, mean, invstd, weight=None, output_mask=(True, True, True), *, channels_last=False,
+                      variant=L.VARIANT_AUTO):
+    """dx, dweight[C], dbias[C] of :func:`instance_norm_fwd`. channels first: one launch for dx and the per-plane sums
+    of dy * x_hat and dy, then one column sum over the batch ([B, C] -> [C]) for each requested parameter gradient."""
+    want_dx, want_dw, want_db = output_mask
+    if channels_last:
+        dxs, dws, dbs = [], [], []
+        for n in range(x.shape[0]):
+            dx, dw, db = outer_norm_bwd(dy[n], x[n], mean[n], invstd[n], weight, output_mask, variant=variant)
+            dxs.append(dx)
+            dws.append(dw)
+            dbs.append(db)
+        tot = lambda parts: reduce_outer(torch.stack(parts).float()).to(x.dtype) if parts[0] is not None else None  # noqa: E731
+        return (torch.stack(dxs) if want_dx else None), tot(dws), tot(dbs)
+    c = x.shape[1]
+    flags = (L.F_HAS_WEIGHT if weight is not None else 0) | L.F_ROW_AFFINE
+    flags |= (L.F_OUT_DX if want_dx else 0) | (L.F_OUT_DW if want_dw else 0) | (L.F_OUT_DB if want_db else 0)
+    ins = [dy.contiguous(), x.contiguous(), mean.contiguous(), invstd.contiguous()] + ([weight] if weight is not None else [])
+    outs = iter(_run(L.OP_LAYERNORM_BWD, flags, 0.0, variant, 0, ins, ignore_index=c))
+    dx = next(outs) if want_dx else None
+    dw = reduce_outer(next(outs)).to(x.dtype) if want_dw else None  # [B, C] fp32 -> [C]
+    db = reduce_outer(next(outs)).to(x.dtype) if want_db else None
+    return dx, dw, db

@@ -194,7 +194,14 @@ enum {
    * log-probabilities are never written. Backward: B200NORM_OP_NLL_SOFTMAX_BWD,
    *     dx[i,j] = (exp(x[i,j] - lse[i]) - [j == target[i]]) * g,   g = a device fp32 scalar (dloss / count),
    * zero rows where target == ignore_index. */
-  B200NORM_F_REDUCE_NLL = 1u << 24
+  B200NORM_F_REDUCE_NLL = 1u << 24,
+  /* Instance norm (csrc/ops/normalization.cpp:790-950 instance_norm, :952-1060 instance_norm_backward; training
+   * statistics, channels first): x[B, C, spatial...] viewed as [M = B*C rows, N = spatial elements] is a LayerNorm over
+   * each row whose affine parameters belong to the row's CHANNEL: weight[C] / bias[C] are indexed by (row mod C),
+   * C = desc.reserved[3]. LAYERNORM_FWD: same tensors as without the flag (weight / bias have C elements).
+   * LAYERNORM_BWD: dx as usual; with OUT_DW / OUT_DB the outputs are the per-ROW sums sum(dy * x_hat) / sum(dy) as
+   * fp32 [M] (dweight[c] / dbias[c] are their sums over the batch: one REDUCE_OUTER of the [B, C] view). */
+  B200NORM_F_ROW_AFFINE = 1u << 25
 };
 
 /* desc.variant: 0 lets the library choose (the dispatch rule mirrors the accept
@@ -266,6 +273,7 @@ typedef struct {
  *                  out: y[M,N] (absent with NO_Y), sum[M,N]?, mean[M]?, invstd | var | M2 [M]?, mask[M,N] (DROPOUT)
  *   LAYERNORM_BWD  in : dy[M,N], x[M,N], mean[M], invstd[M], weight[N]?, residual[M,N] + mask[M,N] (DROPOUT)
  *                  out: dx[M,N]?, dresidual[M,N] (DROPOUT), dweight[N]?, dbias[N]?
+ *       (ROW_AFFINE: weight / bias [C]; backward outputs dx?, rowsum(dy*x_hat)[M] fp32?, rowsum(dy)[M] fp32?)
  *   RMSNORM_FWD    in : x[M,N], residual[M,N]?, weight[N]?, rng[2] (DROPOUT)
  *                  out: y[M,N], sum[M,N]?, stat[M], mask[M,N] (DROPOUT)
  *   RMSNORM_BWD    in : dy[M,N], x[M,N], stat[M], weight[N]?, residual[M,N] + mask[M,N] (DROPOUT)

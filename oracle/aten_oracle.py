@@ -588,3 +588,52 @@ def cross_entropy_bwd(logits, target, ignore_index: int = -100, reduction: str =
                                              reduction=reduction)
     loss.backward()
     return xf.grad.to(logits.dtype), loss.detach()
+
+
+# ---------------------------------------------------------------------------
+# instance norm (csrc/ops/normalization.cpp:790-950, :952-1060; training statistics)
+# ---------------------------------------------------------------------------
+def instance_norm_fwd(x, weight, bias, eps: float, channels_last: bool = False):
+    """(y, mean[B, C], invstd[B, C]): Welford over the spatial axes of every (sample, channel) plane, var = M2 / N,
+    y = (x - mean) * invstd * weight[c] + bias[c] on the Float upcast, cast back to the io dtype."""
+    xf = _up(x)
+    nd = xf.dim()
+    c_axis = nd - 1 if channels_last else 1
+    red = [a for a in range(1, nd) if a != c_axis]
+    var, mean = torch.var_mean(xf, dim=red, correction=0, keepdim=True)
+    invstd = torch.rsqrt(var + eps)
+    shape = [1] * nd
+    shape[c_axis] = xf.shape[c_axis]
+    y = (xf - mean) * invstd
+    if weight is not None:
+        y = y * _up(weight).view(shape)
+    if bias is not None:
+        y = y + _up(bias).view(shape)
+    b, c = xf.shape[0], xf.shape[c_axis]
+    return y.to(x.dtype), mean.reshape(b, c), invstd.reshape(b, c)
+
+
+def instance_norm_bwd(dy, x, mean, invstd, weight, channels_last: bool = False):
+    """(dx, dweight[C], dbias[C]) by the builder's formula (:1014-1060): per plane
+    dx = w * invstd / N * (N dy - sum dy - x_hat sum(dy x_hat)), dweight = sum over batch and space of dy x_hat."""
+    io = x.dtype
+    dyf, xf = _up(dy), _up(x)
+    nd = xf.dim()
+    c_axis = nd - 1 if channels_last else 1
+    red = [a for a in range(1, nd) if a != c_axis]
+    n = 1.0
+    for a in red:
+        n *= xf.shape[a]
+    bshape = [xf.shape[0]] + [1] * (nd - 1)
+    bshape[c_axis] = xf.shape[c_axis]
+    cshape = [1] * nd
+    cshape[c_axis] = xf.shape[c_axis]
+    m, i = mean.view(bshape), invstd.view(bshape)
+    xh = (xf - m) * i
+    w = _up(weight).view(cshape) if weight is not None else torch.ones(cshape)
+    s_dy = torch.sum(dyf, dim=red, keepdim=True)
+    s_dyxh = torch.sum(dyf * xh, dim=red, keepdim=True)
+    dx = (w * i / n) * (n * dyf - s_dy - xh * s_dyxh)
+    dw = torch.sum(s_dyxh, dim=0).reshape(-1)
+    db = torch.sum(s_dy, dim=0).reshape(-1)
+    return dx.to(io), dw.to(io), db.to(io)

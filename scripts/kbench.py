@@ -27,6 +27,7 @@ def algbytes(op, m, n, s):
             "var_mean": s * m * n + 8 * m, "rms_fwd": s * (2 * m * n + n) + 4 * m, "ln_fwd": s * 2 * (m * n + n) + 8 * m, "sm_fwd": s * 2 * m * n, "osm_fwd": s * 2 * m * n, "onorm_fwd": s * 2 * (m * n + n) + 8 * n, "onorm_bwd": s * 3 * (m * n + n) + 8 * n, "osm_bwd": s * 3 * m * n,
             "sm_bwd": s * 3 * m * n, "rms_bwd": s * (3 * m * n + 2 * n) + 4 * m, "rms_bwd_dx": s * (3 * m * n + 2 * n) + 4 * m,
             "ln_bwd": s * 3 * (m * n + n) + 8 * m, "ln_bwd_dx": s * 3 * (m * n + n) + 8 * m,
+            "inorm_fwd": s * 2 * m * n + 8 * m, "inorm_bwd": s * 3 * m * n + 16 * m,  # rows = B * 128 channels
             "ce_fwd": s * m * n + 16 * m, "ce_bwd": s * 2 * m * n + 12 * m,
             # fused dropout (dropout_{layernorm,rmsnorm}_{fwd,bwd}_iobytes): + residual, + the bool mask, + d residual
             "drop_ln_fwd": s * (3 * m * n + 2 * n) + 8 * m + m * n, "drop_rms_fwd": s * (3 * m * n + n) + 4 * m + m * n,
@@ -76,6 +77,9 @@ def main():
                 aux["rng"] = rng
                 aux["drop"] = [ops.dropout_layer_norm_fwd(x, dy, w, w, 1e-5, 0.2, rng) for x, dy in zip(xs, dys)]
                 aux["droprms"] = [ops.dropout_rms_norm_fwd(x, dy, w, 1e-5, 0.2, rng) for x, dy in zip(xs, dys)]
+            if op.startswith("inorm") and "inorm" not in aux:
+                wc = torch.randn(128, device=dev).to(dtype)
+                aux["inorm"] = (wc, [ops.instance_norm_fwd(x.view(m // 128, 128, n), wc, wc, 1e-5)[1:] for x in xs])
             if op.startswith("ce_") and "ce" not in aux:
                 tg = [torch.randint(0, n, (m,), device=dev) for _ in xs]
                 aux["ce"] = (tg, [ops.nll_softmax_fwd(x, t)[1] for x, t in zip(xs, tg)], torch.full((1,), 1.0 / m, device=dev))
@@ -105,6 +109,9 @@ def main():
                                                                     aux["drop"][i][1], aux["drop"][i][2], w, 0.2),
                 "drop_rms_bwd": lambda i: ops.dropout_rms_norm_bwd(dys[(i + 1) % nsets], xs[i], dys[i], aux["droprms"][i][2],
                                                                    aux["droprms"][i][1], w, 0.2),
+                "inorm_fwd": lambda i: ops.instance_norm_fwd(xs[i].view(m // 128, 128, n), aux["inorm"][0], aux["inorm"][0], 1e-5),
+                "inorm_bwd": lambda i: ops.instance_norm_bwd(dys[i].view(m // 128, 128, n), xs[i].view(m // 128, 128, n),
+                                                             aux["inorm"][1][i][0], aux["inorm"][1][i][1], aux["inorm"][0]),
                 "ce_fwd": lambda i: ops.nll_softmax_fwd(xs[i], aux["ce"][0][i]),
                 "ce_bwd": lambda i: ops.nll_softmax_bwd(xs[i], aux["ce"][0][i], aux["ce"][1][i], aux["ce"][2]),
                 "ln_bwd": lambda i: ops.layer_norm_bwd(dys[i], xs[i], aux["ln"][i][0], aux["ln"][i][1], w),

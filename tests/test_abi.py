@@ -101,7 +101,7 @@ def test_bad_descriptors_are_rejected(lib):
         L.query(L.make_desc(L.OP_RMSNORM_BWD, L.DT_BF16, 4, 64, 0.0, L.F_OUT_DW))  # dweight without weight
     with pytest.raises(L.B200NormError):
         L.query(L.make_desc(L.OP_RMSNORM_FWD, L.DT_BF16, 4, 64, cluster_size=3))
-    for bit in (25, 31):  # flag bits the header does not define (the upper ones are the library's own launch knobs)
+    for bit in (26, 31):  # flag bits the header does not define (the upper ones are the library's own launch knobs)
         with pytest.raises(L.B200NormError) as e:
             L.query(L.make_desc(L.OP_SOFTMAX_FWD, L.DT_BF16, 4, 64, 0.0, 1 << bit))
         assert e.value.code == L.ERR_BAD_ARG
