@@ -38,13 +38,14 @@ namespace b200norm {
     default: return nullptr;                                              \
   }
 
+// (the dropout kernels take 1..4 chunks per thread at every group size: the planner picks <= 2 for short rows)
 #define B200_ADD_TPR_SWITCH_NOLOOP(K, ...)                                \
   switch (tpr) {                                                          \
     case 32: B200_ADD_CH_SWITCH(K, 32, ##__VA_ARGS__)                     \
-    case 64: B200_ADD_CH_SWITCH_HI(K, 64, ##__VA_ARGS__)                  \
-    case 128: B200_ADD_CH_SWITCH_HI(K, 128, ##__VA_ARGS__)                \
-    case 256: B200_ADD_CH_SWITCH_HI(K, 256, ##__VA_ARGS__)                \
-    case 512: B200_ADD_CH_SWITCH_HI(K, 512, ##__VA_ARGS__)                \
+    case 64: B200_ADD_CH_SWITCH(K, 64, ##__VA_ARGS__)                     \
+    case 128: B200_ADD_CH_SWITCH(K, 128, ##__VA_ARGS__)                   \
+    case 256: B200_ADD_CH_SWITCH(K, 256, ##__VA_ARGS__)                   \
+    case 512: B200_ADD_CH_SWITCH(K, 512, ##__VA_ARGS__)                   \
     default: return nullptr;                                              \
   }
 
