@@ -166,11 +166,19 @@ class FusionDefinition:
             kw["variant"] = L.VARIANT_GENERIC
         res: dict = {}
         want = set(m.outputs)
-        if m.flags & L.F_DROPOUT:
+        if m.flags & L.F_ROW_AFFINE:  # instance norm
+            if m.op == L.OP_LAYERNORM_FWD:
+                y, mean, invstd = K.instance_norm_fwd(r["x"], r.get("w"), r.get("b"), m.eps, channels_last=m.channels_last, **kw)
+                res = {"y": y, "mean": mean, "invstd": invstd}
+            else:
+                dx, dw, db = K.instance_norm_bwd(r["dy"], r["x"], r["mean"], r["stat"], r.get("w"),
+                                                 ("dx" in want, "dw" in want, "db" in want), channels_last=m.channels_last, **kw)
+                res = {"dx": dx, "dw": dw, "db": db}
+        elif m.flags & L.F_DROPOUT:
             res = self._execute_dropout(m, r, want, kw, _rng)
         elif m.flags & L.F_ADD_RESIDUAL:  # norm(x + residual), optional sum output
             kw.update(residual=r["r"], want_sum="sum" in want, round_sum=bool(m.flags & L.F_ROUND_SUM))
-        if m.flags & L.F_DROPOUT:
+        if m.flags & (L.F_DROPOUT | L.F_ROW_AFFINE):
             pass
         elif m.op == L.OP_LAYERNORM_FWD and m.flags & L.F_NO_Y:  # stand-alone var_mean / welford
             if m.flags & L.F_STAT_M2:

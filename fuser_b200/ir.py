@@ -196,8 +196,12 @@ class Ops:
             return Scalar(fd, name, [sa, sb], {}, promote(sa.dtype, sb.dtype), value=val)
         if ta and tb:
             if a.ndim != b.ndim:
-                raise ValueError(
-                    f"{name}: operands have {a.ndim} and {b.ndim} dims; nvFuser requires explicit broadcasts")
+                # ranks are aligned the way the reference's binary ops do it (csrc/ops/utils.cpp:22-34, 511-532
+                # maybeBroadcast): the lower-rank operand gets leading broadcast axes
+                lo, hi = (a, b) if a.ndim < b.ndim else (b, a)
+                pad = hi.ndim - lo.ndim
+                lo_b = Tensor(fd, "broadcast", [lo], {"mask": [True] * pad + [False] * lo.ndim}, lo.dtype, [None] * pad + lo.dims)
+                a, b = (lo_b, b) if a is lo else (a, lo_b)
             dims = []
             for da, db in zip(a.dims, b.dims):
                 if da is not None and db is not None:

@@ -356,6 +356,45 @@ def def_outer_norm_bwd(ops, dy, x, mean, invstd, w):
     return {"dx": dx, "dw": ops.mul(dot_p, invstd), "db": grad_sum}
 
 
+def def_instance_norm_fwd(ops, x, w, b, eps, c_axis):
+    """csrc/ops/normalization.cpp:790-950 / benchmarks/python/normalization.py:13-95 with norm = "instance_norm":
+    statistics over the spatial axes of every (sample, channel) plane, affine per channel."""
+    nd = x.ndim
+    red = [a for a in range(1, nd) if a != c_axis]
+    var, mean = ops.var_mean(x, dims=red, correction=0, keepdim=False)
+    invstd = ops.rsqrt(ops.add(var, eps))
+    smask = [a in red for a in range(nd)]
+    cmask = [a != c_axis for a in range(nd)]
+    y = ops.mul(ops.sub(x, ops.broadcast(mean, smask)), ops.broadcast(invstd, smask))
+    if w is not None:
+        y = ops.mul(y, ops.broadcast(w, cmask))
+    if b is not None:
+        y = ops.add(y, ops.broadcast(b, cmask))
+    return {"y": y, "mean": mean, "invstd": invstd}
+
+
+def def_instance_norm_bwd(ops, dy, x, mean, invstd, w, c_axis):
+    """csrc/ops/normalization.cpp:952-1060 / benchmarks/python/normalization.py:98-190 with norm = "instance_norm"."""
+    nd = x.ndim
+    red = [a for a in range(1, nd) if a != c_axis]
+    smask = [a in red for a in range(nd)]
+    cmask = [a != c_axis for a in range(nd)]
+    num = x.size(red[0])
+    for ax in red[1:]:
+        num = ops.mul(num, x.size(ax))
+    norm = ops.reciprocal(num)
+    xc = ops.sub(x, ops.broadcast(mean, smask))
+    grad_sum = ops.sum(dy, dims=red, keepdim=False)
+    dot_p = ops.sum(ops.mul(dy, xc), dims=red, keepdim=False)
+    grad_mean = ops.broadcast(ops.mul(grad_sum, norm), smask)
+    proj_scale = ops.broadcast(ops.mul(ops.mul(dot_p, norm), ops.mul(invstd, invstd)), smask)
+    grad_scale = ops.broadcast(invstd, smask)
+    if w is not None:
+        grad_scale = ops.mul(ops.broadcast(w, cmask), grad_scale)
+    dx = ops.mul(ops.sub(ops.sub(dy, ops.mul(proj_scale, xc)), grad_mean), grad_scale)
+    return {"dx": dx, "dw": ops.sum(ops.mul(dot_p, invstd), dims=[0], keepdim=False), "db": ops.sum(grad_sum, dims=[0], keepdim=False)}
+
+
 def def_rms_norm_fwd(ops, x, w, eps):
     """normalization.cpp:352-380 (+ the rms statistic of benchmarks/python/test_rmsnorm_fwd.py:26-45)"""
     last = [x.ndim - 1]
@@ -439,6 +478,7 @@ class Match:
     norm_ndim: int = 1
     correction: int = 0        # var_mean (F_STAT_VAR)
     dropout_keep: float = 1.0  # F_DROPOUT: the keep probability 1 - p (the fusion's double scalar)
+    channels_last: bool = False  # F_ROW_AFFINE (instance norm): [B, spatial..., C] instead of [B, C, spatial...]
     description: str = ""
     notes: list = field(default_factory=list)
 
@@ -501,6 +541,90 @@ def _sum_is_rounded(fd) -> bool:
     return False
 
 
+def _match_instance_norm(fd, tin, mats, cls, out_keys):
+    """Instance norm (training statistics) forward / backward on [B, C, spatial...] or [B, spatial..., C]: its
+    parameters are indexed by an axis that is neither a row nor the column of the [rows, cols] view the other segments
+    use, so it is recognised before that classification. Returns a Match or None."""
+    nd = max(t.ndim for _, t in mats)
+    mats = [(i, t) for i, t in mats if t.ndim == nd]  # the saved [B, C] statistics of the backward are rank 2
+    x_like = mats[0][1]
+    if nd < 3 or len(mats) not in (1, 2):
+        return None
+    if any(tuple(cls(d) for d in t.dims) != tuple(cls(d) for d in x_like.dims) for _, t in mats):
+        return None
+    io = x_like.dtype
+    if io not in (DataType.Float, DataType.Half, DataType.BFloat16) or any(t.dtype != io for _, t in mats):
+        return None
+    ops = fd.ops
+    others = [(i, t) for i, t in tin if (i, t) not in mats]
+
+    def T(pair):
+        t = pair[1]
+        return ops.cast(t, DataType.Float) if t.dtype in REDUCED else t
+
+    def attempt(build):
+        snap = fd._uf.snapshot()
+        nvals = len(fd._vals)
+        try:
+            cand = build()
+            c2 = Canon(fd)
+            keys = {name: c2.value(t).key() for name, t in cand.items() if t is not None}
+            if len({c2.cls(d) for d in x_like.dims}) != nd:  # the candidate merged two extents: wrong role guess
+                return None
+            c3 = Canon(fd)
+            mine = [c3.value(o).key() for o in fd._outputs]
+        except (Unmatchable, ValueError):
+            return None
+        finally:
+            del fd._vals[nvals:]
+            fd._uf.restore(snap)
+        names = []
+        for k in mine:
+            hit = [n for n, kk in keys.items() if kk == k]
+            if not hit:
+                return None
+            names.append(hit[0])
+        return names
+
+    for c_axis in (1, nd - 1):
+        ccls, bcls = cls(x_like.dims[c_axis]), cls(x_like.dims[0])
+        chan = [(i, t) for i, t in others if t.ndim == 1 and cls(t.dims[0]) == ccls and t.dtype == io]
+        plane = [(i, t) for i, t in others if t.ndim == 2 and (cls(t.dims[0]), cls(t.dims[1])) == (bcls, ccls)
+                 and t.dtype == DataType.Float]
+        if len(chan) + len(plane) != len(others):
+            continue
+        if len(mats) == 1 and not plane and len(chan) <= 2:
+            x = mats[0]
+            combos = [(None, None)] if not chan else [(chan[0], None)] if len(chan) == 1 else \
+                [(chan[0], chan[1]), (chan[1], chan[0])]
+            for eps in _eps_candidates(fd):
+                e = ops._scalar(float(eps))
+                for w, b in combos:
+                    names = attempt(lambda: def_instance_norm_fwd(ops, T(x), T(w) if w else None, T(b) if b else None, e, c_axis))
+                    if names and "y" in names:
+                        roles = {"x": x[0]}
+                        if w:
+                            roles["w"] = w[0]
+                        if b:
+                            roles["b"] = b[0]
+                        flags = L.F_ROW_AFFINE | (L.F_HAS_WEIGHT if w else 0) | (L.F_HAS_BIAS if b else 0)
+                        return Match(L.OP_LAYERNORM_FWD, flags, eps, io, roles, names, channels_last=c_axis != 1,
+                                     description="instance_norm forward" + (" (channels last)" if c_axis != 1 else ""))
+        if len(mats) == 2 and len(plane) == 2 and len(chan) <= 1:
+            w = chan[0] if chan else None
+            for dy_, x_ in ((mats[0], mats[1]), (mats[1], mats[0])):
+                for mean, st in ((plane[0], plane[1]), (plane[1], plane[0])):
+                    names = attempt(lambda: def_instance_norm_bwd(ops, T(dy_), T(x_), mean[1], st[1], T(w) if w else None, c_axis))
+                    if names and "dx" in names:
+                        roles = {"dy": dy_[0], "x": x_[0], "mean": mean[0], "stat": st[0]}
+                        if w:
+                            roles["w"] = w[0]
+                        return Match(L.OP_LAYERNORM_BWD, L.F_ROW_AFFINE | (L.F_HAS_WEIGHT if w else 0), 0.0, io, roles, names,
+                                     channels_last=c_axis != 1,
+                                     description="instance_norm backward" + (" (channels last)" if c_axis != 1 else ""))
+    return None
+
+
 def match_fusion(fd) -> Match:
     """Classify the recorded fusion or raise Unmatchable."""
     if not fd._outputs:
@@ -520,6 +644,9 @@ def match_fusion(fd) -> Match:
     mats = [(i, t) for i, t in tin if t.ndim >= 2 and all(d is not None for d in t.dims)]
     if not mats:
         raise Unmatchable("no [rows, cols] input")
+    inst = _match_instance_norm(fd, tin, mats, cls, out_keys)
+    if inst is not None:
+        return inst
     x_like = mats[0][1]
     nd = x_like.ndim
     col_cls = cls(x_like.dims[-1])

@@ -581,3 +581,76 @@ def dropout_rmsnorm_bwd_py(fd, dtype, p=0.2):
     fd.add_output(_down(fd, dx, dtype))
     fd.add_output(_down(fd, dres, dtype))
     fd.add_output(_down(fd, dw, dtype))
+
+
+def norm_fwd_py(fd, dtype, norm="instance_norm", num_dims=4, channels_last=False, eps=1e-5, momentum=0.01):
+    """benchmarks/python/normalization.py:13-95 in full: batch norm or instance norm, channels first or last."""
+    cdim = 1 if not channels_last else num_dims - 1
+    bmask = [i != cdim for i in range(num_dims)]
+    cmask = list(bmask)
+    axes = [i for i in range(num_dims) if i != cdim]
+    if norm == "instance_norm":
+        axes.remove(0)
+        bmask[0] = False
+    x = fd.define_tensor(shape=[-1] * num_dims, contiguity=[True] * num_dims, dtype=dtype, is_cpu=False)
+    weight = fd.define_tensor(shape=[-1], contiguity=[True], dtype=dtype, is_cpu=False)
+    bias = fd.define_tensor(shape=[-1], contiguity=[True], dtype=dtype, is_cpu=False)
+    running_mean = fd.define_tensor(shape=[-1], contiguity=[True], dtype=DataType.Float, is_cpu=False)
+    running_var = fd.define_tensor(shape=[-1], contiguity=[True], dtype=DataType.Float, is_cpu=False)
+    x, weight, bias = _up(fd, x, dtype), _up(fd, weight, dtype), _up(fd, bias, dtype)
+    var, mean = fd.ops.var_mean(x, dims=axes, correction=0, keepdim=False)
+    invstd = fd.ops.rsqrt(fd.ops.add(var, fd.define_scalar(eps, dtype=DataType.Double)))
+    x_norm = fd.ops.mul(fd.ops.sub(x, fd.ops.broadcast(mean, bmask)), fd.ops.broadcast(invstd, bmask))
+    out = fd.ops.add(fd.ops.mul(x_norm, fd.ops.broadcast(weight, cmask)), fd.ops.broadcast(bias, cmask))
+    rev = fd.define_scalar(1 - momentum, dtype=DataType.Double)
+    mom = fd.define_scalar(momentum, dtype=DataType.Double)
+    um = fd.ops.add(fd.ops.mul(mom, mean), fd.ops.mul(rev, running_mean))  # running-statistics updates: dead code,
+    uv = fd.ops.add(fd.ops.mul(mom, var), fd.ops.mul(rev, running_var))    # never added as outputs
+    if 0 not in axes:
+        inv_b = fd.ops.reciprocal(x.size(0))
+        fd.ops.mul(fd.ops.sum(um, 0), inv_b)
+        fd.ops.mul(fd.ops.sum(uv, 0), inv_b)
+    fd.add_output(_down(fd, out, dtype))
+    fd.add_output(mean)
+    fd.add_output(invstd)
+
+
+def norm_bwd_py(fd, dtype, norm="instance_norm", num_dims=4, channels_last=False):
+    """benchmarks/python/normalization.py:98-190 in full (inputs: input, grad, weight, running_mean, running_var,
+    mean, invstd)."""
+    from functools import reduce
+
+    cdim = 1 if not channels_last else num_dims - 1
+    bmask = [i != cdim for i in range(num_dims)]
+    cmask = list(bmask)
+    axes = [i for i in range(num_dims) if i != cdim]
+    if norm == "instance_norm":
+        axes.remove(0)
+        bmask[0] = False
+    nstat = num_dims - len(axes)
+    x = fd.define_tensor(shape=[-1] * num_dims, contiguity=[True] * num_dims, dtype=dtype, is_cpu=False)
+    grad = fd.define_tensor(shape=[-1] * num_dims, contiguity=[True] * num_dims, dtype=dtype, is_cpu=False)
+    weight = fd.define_tensor(shape=[-1], contiguity=[True], dtype=dtype, is_cpu=False)
+    fd.define_tensor(shape=[-1], contiguity=[True], dtype=DataType.Float, is_cpu=False)  # running_mean
+    fd.define_tensor(shape=[-1], contiguity=[True], dtype=DataType.Float, is_cpu=False)  # running_var
+    mean = fd.define_tensor(shape=[-1] * nstat, contiguity=[True] * nstat, dtype=DataType.Float, is_cpu=False)
+    invstd = fd.define_tensor(shape=[-1] * nstat, contiguity=[True] * nstat, dtype=DataType.Float, is_cpu=False)
+    x, grad, weight = _up(fd, x, dtype), _up(fd, grad, dtype), _up(fd, weight, dtype)
+    norm_ = fd.ops.reciprocal(reduce(fd.ops.mul, [x.size(ax) for ax in axes], 1))
+    mean_b = fd.ops.broadcast(mean, bmask)
+    grad_sum = fd.ops.sum(grad, dims=axes, keepdim=False)
+    x_sub_mean = fd.ops.sub(x, mean_b)
+    dot_p = fd.ops.sum(fd.ops.mul(grad, x_sub_mean), dims=axes, keepdim=False)
+    grad_mean = fd.ops.broadcast(fd.ops.mul(grad_sum, norm_), bmask)
+    proj_scale = fd.ops.broadcast(fd.ops.mul(fd.ops.mul(dot_p, norm_), fd.ops.mul(invstd, invstd)), bmask)
+    grad_scale = fd.ops.mul(fd.ops.broadcast(weight, cmask), fd.ops.broadcast(invstd, bmask))
+    proj = fd.ops.mul(proj_scale, x_sub_mean)
+    grad_input = fd.ops.mul(fd.ops.sub(fd.ops.sub(grad, proj), grad_mean), grad_scale)
+    grad_weight = fd.ops.mul(dot_p, invstd)
+    grad_bias = grad_sum
+    if 0 not in axes:
+        grad_weight = fd.ops.sum(grad_weight, 0, keepdim=False)
+        grad_bias = fd.ops.sum(grad_bias, 0, keepdim=False)
+    fd.add_output(_down(fd, grad_input, dtype))
+    fd.add_output(_down(fd, grad_weight, dtype))
+    fd.add_output(_down(fd, grad_bias, dtype))

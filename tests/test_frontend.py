@@ -198,8 +198,9 @@ def test_api_surface_and_errors():
         assert x.ndim == 2 and len(x.shape()) == 2 and x.size(1).is_symbolic()
         with pytest.raises(ValueError):  # same user error as csrc/ops/normalization.cpp:101-108
             fd.ops.var_mean(x, dims=[1])
-        with pytest.raises(ValueError):  # ranks must match: broadcasts are explicit in nvFuser
-            fd.ops.add(x, fd.define_tensor(shape=[-1], dtype=DataType.BFloat16))
+        # operands of different rank: the lower one gets leading broadcast axes (csrc/ops/utils.cpp:22-34, 511-532)
+        s_ = fd.ops.add(x, fd.define_tensor(shape=[-1], dtype=DataType.BFloat16))
+        assert s_.ndim == 2 and s_.args[1].op == "broadcast" and s_.args[1].dims[0] is None
     with pytest.raises(NotImplementedError):
         FusionDefinition().execute([])
     fd = build(F.rmsnorm_fwd_py, DataType.BFloat16)
@@ -392,3 +393,23 @@ def test_dropout_near_misses_are_refused():
         with FusionDefinition() as fd:
             x = fd.define_tensor(shape=[-1, -1], dtype=DataType.Float)
             fd.ops.uniform(0.0, 1.0, shape=[4, 5], dtype=DataType.Float)
+
+
+@pytest.mark.parametrize("dt", DTS, ids=lambda d: d.name)
+@pytest.mark.parametrize("nd", [3, 4, 5])
+@pytest.mark.parametrize("channels_last", [False, True], ids=["nchw", "nhwc"])
+def test_instance_norm_fusions_are_matched(dt, nd, channels_last):
+    """benchmarks/python/normalization.py with norm = "instance_norm" (test_instancenorm_{fwd,bwd}.py), both layouts,
+    3-D to 5-D: the dead running-statistics updates (which add a [B, C] tensor to a [C] one) are recorded and
+    ignored; the batch-norm flavour of the same definitions still goes to the outer normalization."""
+    fd = build(F.norm_fwd_py, dt, "instance_norm", nd, channels_last)
+    m = fd.segment()
+    assert m.op == L.OP_LAYERNORM_FWD and m.flags & L.F_ROW_AFFINE and not m.flags & L.F_OUTER
+    assert m.roles == {"x": 0, "w": 1, "b": 2} and m.outputs == ["y", "mean", "invstd"] and m.channels_last == channels_last
+    fd = build(F.norm_bwd_py, dt, "instance_norm", nd, channels_last)
+    m = fd.segment()
+    assert m.op == L.OP_LAYERNORM_BWD and m.flags & L.F_ROW_AFFINE and m.channels_last == channels_last
+    assert m.roles == {"dy": 1, "x": 0, "mean": 5, "stat": 6, "w": 2} and m.outputs == ["dx", "dw", "db"]
+    if channels_last:
+        assert build(F.norm_fwd_py, dt, "batch_norm", nd, True).segment().flags & L.F_OUTER
+        assert build(F.norm_bwd_py, dt, "batch_norm", nd, True).segment().flags & L.F_OUTER

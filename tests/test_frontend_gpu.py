@@ -190,3 +190,31 @@ def test_dropout_stream_follows_the_cuda_generator():
     assert mask0.all()
     ye, me, ie, _ = AO.add_layer_norm_fwd(x1.cpu(), x2.cpu(), w.cpu(), b.cpu(), 1e-5)
     AO.assert_close(y0, ye, n, "p = 0")
+
+
+@pytest.mark.parametrize("dt", [DataType.BFloat16, DataType.Float], ids=lambda d: d.name)
+@pytest.mark.parametrize("channels_last", [False, True], ids=["nchw", "nhwc"])
+@pytest.mark.parametrize("size", [(4, 16, 28, 28), (2, 64, 8, 8, 8), (3, 5, 1000)], ids=lambda s: "x".join(map(str, s)))
+def test_instance_norm_fusions_execute_and_validate(size, channels_last, dt):
+    """test_instancenorm_{fwd,bwd}.py through FusionDefinition: auto-inferred expectation (node-by-node ATen) and the
+    eager torch.nn.functional.instance_norm the benchmark validates against."""
+    td = DT[dt]
+    nd = len(size)
+    g = torch.Generator().manual_seed(sum(size))
+    at_x = torch.randn(*size, generator=g).to(td)
+    at_dy = torch.randn(*size, generator=g).to(td)
+    c = size[1]
+    w, b = torch.randn(c, generator=g).to(td).cuda(), torch.randn(c, generator=g).to(td).cuda()
+    rm, rv = torch.zeros(c, device="cuda"), torch.ones(c, device="cuda")
+    perm = (0, *range(2, nd), 1)
+    x = (at_x.permute(perm).contiguous() if channels_last else at_x).cuda()
+    dy = (at_dy.permute(perm).contiguous() if channels_last else at_dy).cuda()
+    fd = build(F.norm_fwd_py, dt, "instance_norm", nd, channels_last)
+    y, mean, invstd = auto_validate(fd, [x, w, b, rm, rv])
+    assert mean.shape == (size[0], c) and invstd.shape == (size[0], c)
+    eager = torch.nn.functional.instance_norm(at_x.float(), weight=w.cpu().float(), bias=b.cpu().float())
+    if channels_last:
+        eager = eager.permute(perm)
+    AO.assert_close(y, eager.to(td), at_x[0, 0].numel(), "instance norm vs eager")
+    fdb = build(F.norm_bwd_py, dt, "instance_norm", nd, channels_last)
+    auto_validate(fdb, [x, dy, w, rm, rv, mean, invstd])
