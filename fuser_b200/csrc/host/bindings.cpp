@@ -84,6 +84,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         d["io_dtype"] = sm.io_dtype;
         d["correction"] = sm.correction;
         d["dropout_keep"] = sm.dropout_keep;
+        d["channels_last"] = sm.channels_last;
         d["roles"] = sm.roles;
         d["outputs"] = sm.outputs;
         d["description"] = sm.description;

@@ -457,6 +457,16 @@ struct Builder {
     }
     return push(n);
   }
+  // ops.broadcast(t, mask): a new size-1 axis wherever mask is true
+  int32_t bcast_mask(int32_t t, const std::vector<bool>& mask) {
+    ExprNode n;
+    n.kind = ExprKind::Broadcast;
+    n.args = {t};
+    size_t k = 0;
+    for (bool m : mask) n.dims.push_back(m ? -1 : nodes[t].dims.at(k++));
+    if (k != nodes[t].dims.size()) throw Unmatchable("candidate: broadcast mask does not fit the operand");
+    return push(n);
+  }
   // [N] -> [.., N] aligned with the last axis of `like`
   int32_t bcast_last(int32_t t, int32_t like) {
     ExprNode n;
@@ -518,6 +528,49 @@ Outs def_outer_norm_bwd(Builder& b, int32_t dy, int32_t x, int32_t mean, int32_t
   if (w != kNone) grad_scale = b.mul(b.bcast_last(w, x), grad_scale);
   const int32_t dx = b.mul(b.sub(b.sub(dy, b.mul(proj_scale, xc)), grad_mean), grad_scale);
   return {{"dx", dx}, {"dw", b.mul(dot_p, invstd)}, {"db", grad_sum}};
+}
+// instance norm (csrc/ops/normalization.cpp:790-950, :952-1060; benchmarks/python/normalization.py with
+// norm = "instance_norm"): statistics over the spatial axes of every (sample, channel) plane, affine per channel
+Outs def_instance_norm_fwd(Builder& b, int32_t x, int32_t w, int32_t bias, int32_t eps, int c_axis) {
+  const int nd = b.ndim(x);
+  std::vector<int32_t> red;
+  std::vector<bool> smask(nd, false), cmask(nd, true);
+  for (int a = 1; a < nd; ++a)
+    if (a != c_axis) {
+      red.push_back(a);
+      smask[a] = true;
+    }
+  cmask[c_axis] = false;
+  const int32_t var = b.reduce(ExprKind::Var, x, red, false), mean = b.reduce(ExprKind::Mean, x, red, false);
+  const int32_t invstd = b.unary(ExprKind::Rsqrt, b.add(var, eps));
+  int32_t y = b.mul(b.sub(x, b.bcast_mask(mean, smask)), b.bcast_mask(invstd, smask));
+  if (w != kNone) y = b.mul(y, b.bcast_mask(w, cmask));
+  if (bias != kNone) y = b.add(y, b.bcast_mask(bias, cmask));
+  return {{"y", y}, {"mean", mean}, {"invstd", invstd}};
+}
+Outs def_instance_norm_bwd(Builder& b, int32_t dy, int32_t x, int32_t mean, int32_t invstd, int32_t w, int c_axis) {
+  const int nd = b.ndim(x);
+  std::vector<int32_t> red;
+  std::vector<bool> smask(nd, false), cmask(nd, true);
+  for (int a = 1; a < nd; ++a)
+    if (a != c_axis) {
+      red.push_back(a);
+      smask[a] = true;
+    }
+  cmask[c_axis] = false;
+  int32_t num = b.size(x, red.at(0));
+  for (size_t i = 1; i < red.size(); ++i) num = b.mul(num, b.size(x, red[i]));
+  const int32_t norm = b.unary(ExprKind::Reciprocal, num);
+  const int32_t xc = b.sub(x, b.bcast_mask(mean, smask));
+  const int32_t grad_sum = b.reduce(ExprKind::Sum, dy, red, false);
+  const int32_t dot_p = b.reduce(ExprKind::Sum, b.mul(dy, xc), red, false);
+  const int32_t grad_mean = b.bcast_mask(b.mul(grad_sum, norm), smask);
+  const int32_t proj_scale = b.bcast_mask(b.mul(b.mul(dot_p, norm), b.mul(invstd, invstd)), smask);
+  int32_t grad_scale = b.bcast_mask(invstd, smask);
+  if (w != kNone) grad_scale = b.mul(b.bcast_mask(w, cmask), grad_scale);
+  const int32_t dx = b.mul(b.sub(b.sub(dy, b.mul(proj_scale, xc)), grad_mean), grad_scale);
+  return {{"dx", dx}, {"dw", b.reduce(ExprKind::Sum, b.mul(dot_p, invstd), {0}, false)},
+          {"db", b.reduce(ExprKind::Sum, grad_sum, {0}, false)}};
 }
 Outs def_rms_norm_fwd(Builder& b, int32_t x, int32_t w, int32_t eps) {
   const std::vector<int32_t> last{b.ndim(x) - 1};
@@ -640,6 +693,131 @@ struct In {
   int32_t node;  // node index
 };
 
+// Instance norm (training statistics) forward / backward on [B, C, spatial...] or [B, spatial..., C]: its parameters
+// are indexed by an axis that is neither a row nor the column of the [rows, cols] view the other segments use, so it is
+// recognised before that classification (mirrors matcher.py: _match_instance_norm).
+bool match_instance_norm(const ExprGraph& g, const std::vector<In>& tin, std::vector<In> mats, Context& ctx,
+                         const std::vector<std::string>& mine, SegmentMatch* out) {
+  auto N = [&](const In& i) -> const ExprNode& { return g.nodes[i.node]; };
+  size_t nd = 0;
+  for (const In& i : mats) nd = std::max(nd, N(i).dims.size());
+  {
+    std::vector<In> keep;
+    for (const In& i : mats)
+      if (N(i).dims.size() == nd) keep.push_back(i);  // the saved [B, C] statistics of the backward are rank 2
+    mats = keep;
+  }
+  if (nd < 3 || (mats.size() != 1 && mats.size() != 2)) return false;
+  const ExprNode& x_like = N(mats[0]);
+  for (const In& i : mats)
+    if (N(i).dims != x_like.dims) return false;
+  const int32_t io = x_like.dtype;
+  if (io != kF32 && io != kF16 && io != kBF16) return false;
+  for (const In& i : mats)
+    if (N(i).dtype != io) return false;
+  {
+    std::set<int32_t> distinct(x_like.dims.begin(), x_like.dims.end());
+    if (distinct.size() != nd) return false;  // two axes share an extent class: not decidable here
+  }
+  std::vector<In> others;
+  for (const In& i : tin) {
+    bool is_mat = false;
+    for (const In& m : mats) is_mat = is_mat || m.node == i.node;
+    if (!is_mat) others.push_back(i);
+  }
+  std::vector<std::string> names;
+  auto attempt = [&](const std::function<Outs(Builder&)>& build) -> bool {
+    std::vector<ExprNode> nodes = g.nodes;
+    Builder b(nodes);
+    std::map<std::string, std::string> keys;
+    try {
+      const Outs cand = build(b);
+      Canon c(nodes, ctx);
+      for (const auto& kv : cand)
+        if (kv.second != kNone) keys[kv.first] = poly_key(c.value(kv.second));
+    } catch (const Unmatchable&) {
+      return false;
+    } catch (const std::out_of_range&) {
+      return false;
+    }
+    names.clear();
+    for (const std::string& k : mine) {
+      bool hit = false;
+      for (const auto& kv : keys)
+        if (kv.second == k) {
+          names.push_back(kv.first);
+          hit = true;
+          break;
+        }
+      if (!hit) return false;
+    }
+    return true;
+  };
+  auto has = [&](const char* nm) { return std::find(names.begin(), names.end(), nm) != names.end(); };
+  std::vector<double> eps_list = eps_candidates(g);
+  for (int c_axis : {1, (int)nd - 1}) {
+    const int32_t ccls = x_like.dims[c_axis], bcls = x_like.dims[0];
+    std::vector<In> chan, plane;
+    for (const In& i : others) {
+      const ExprNode& n = N(i);
+      if (n.dims.size() == 1 && n.dims[0] == ccls && n.dtype == io) chan.push_back(i);
+      else if (n.dims.size() == 2 && n.dims[0] == bcls && n.dims[1] == ccls && n.dtype == kF32) plane.push_back(i);
+    }
+    if (chan.size() + plane.size() != others.size()) continue;
+    if (mats.size() == 1 && plane.empty() && chan.size() <= 2) {
+      const In& x = mats[0];
+      std::vector<std::pair<const In*, const In*>> combos{{nullptr, nullptr}};
+      if (chan.size() == 1) combos = {{&chan[0], nullptr}};
+      if (chan.size() == 2) combos = {{&chan[0], &chan[1]}, {&chan[1], &chan[0]}};
+      for (double eps : eps_list)
+        for (const auto& wb : combos) {
+          const In *w = wb.first, *bi = wb.second;
+          if (attempt([&](Builder& b) {
+                return def_instance_norm_fwd(b, x.node, w ? w->node : kNone, bi ? bi->node : kNone, b.constant(eps), c_axis);
+              }) &&
+              has("y")) {
+            out->op = B200NORM_OP_LAYERNORM_FWD;
+            out->flags = B200NORM_F_ROW_AFFINE | (w ? B200NORM_F_HAS_WEIGHT : 0) | (bi ? B200NORM_F_HAS_BIAS : 0);
+            out->eps = eps;
+            out->io_dtype = io;
+            out->roles = {{"x", x.idx}};
+            if (w) out->roles["w"] = w->idx;
+            if (bi) out->roles["b"] = bi->idx;
+            out->outputs = names;
+            out->channels_last = c_axis != 1;
+            out->description = "instance_norm forward";
+            return true;
+          }
+        }
+    }
+    if (mats.size() == 2 && plane.size() == 2 && chan.size() <= 1) {
+      const In* w = chan.empty() ? nullptr : &chan[0];
+      for (int order = 0; order < 2; ++order) {
+        const In &dy_ = mats[order], &x_ = mats[1 - order];
+        for (int so = 0; so < 2; ++so) {
+          const In &mean = plane[so], &st = plane[1 - so];
+          if (attempt([&](Builder& b) {
+                return def_instance_norm_bwd(b, dy_.node, x_.node, mean.node, st.node, w ? w->node : kNone, c_axis);
+              }) &&
+              has("dx")) {
+            out->op = B200NORM_OP_LAYERNORM_BWD;
+            out->flags = B200NORM_F_ROW_AFFINE | (w ? B200NORM_F_HAS_WEIGHT : 0);
+            out->eps = 0.0;
+            out->io_dtype = io;
+            out->roles = {{"dy", dy_.idx}, {"x", x_.idx}, {"mean", mean.idx}, {"stat", st.idx}};
+            if (w) out->roles["w"] = w->idx;
+            out->outputs = names;
+            out->channels_last = c_axis != 1;
+            out->description = "instance_norm backward";
+            return true;
+          }
+        }
+      }
+    }
+  }
+  return false;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -668,6 +846,7 @@ static void match_impl(const ExprGraph& g, SegmentMatch* out) {
   for (const In& i : tin)
     if (N(i).dims.size() >= 2 && full(N(i))) mats.push_back(i);
   if (mats.empty()) throw Unmatchable("no [rows, cols] input");
+  if (match_instance_norm(g, tin, mats, ctx, mine, out)) return;
   const ExprNode& x_like = N(mats[0]);
   const size_t nd = x_like.dims.size();
   const int32_t col_cls = x_like.dims.back();

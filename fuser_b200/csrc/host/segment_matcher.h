@@ -66,6 +66,7 @@ struct SegmentMatch {
   int32_t io_dtype = kF32;
   int32_t correction = 0;
   double dropout_keep = 1.0;  // B200NORM_F_DROPOUT: the keep probability 1 - p
+  bool channels_last = false;  // B200NORM_F_ROW_AFFINE (instance norm): [B, spatial..., C] instead of [B, C, spatial...]
   std::map<std::string, int32_t> roles;  // "x", "dy", "y", "w", "b", "r", "mean", "stat", "mask" -> index into graph.inputs
   std::vector<std::string> outputs;      // "y", "mean", "invstd", "rms", "sum", "dx", "dw", "db", "r", "var", "m2", "mask", "dres"
   std::string description;

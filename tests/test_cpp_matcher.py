@@ -30,7 +30,7 @@ def agree(fd):
     assert c["matched"], f"C++ refused ({c.get('why')}) what Python matched as {m.description}"
     assert (c["op"], c["flags"], c["eps"], c["correction"]) == (m.op, m.flags, m.eps, m.correction), (c, m)
     assert c["roles"] == m.roles and c["outputs"] == m.outputs and c["io_dtype"] == IO[m.io_dtype], (c, m)
-    assert c["dropout_keep"] == m.dropout_keep, (c, m)
+    assert c["dropout_keep"] == m.dropout_keep and c["channels_last"] == m.channels_last, (c, m)
     return m
 
 
@@ -65,6 +65,13 @@ SPELLINGS = [
     ("rmsnorm_add_thunder", lambda dt: (F.rmsnorm_add_thunder, (dt,))),
     ("thunder_rms_norm_bwd_cpp", lambda dt: (F.thunder_rms_norm_bwd_cpp, (dt,))),
     ("thunder_rms_norm_bwd_cpp_noweight", lambda dt: (lambda fd, d: F.thunder_rms_norm_bwd_cpp(fd, d, weight=False), (dt,))),
+    ("instance_norm_fwd_nchw", lambda dt: (F.norm_fwd_py, (dt, "instance_norm", 4, False))),
+    ("instance_norm_fwd_nhwc", lambda dt: (F.norm_fwd_py, (dt, "instance_norm", 4, True))),
+    ("instance_norm_fwd_3d", lambda dt: (F.norm_fwd_py, (dt, "instance_norm", 3, False))),
+    ("instance_norm_bwd_nchw", lambda dt: (F.norm_bwd_py, (dt, "instance_norm", 4, False))),
+    ("instance_norm_bwd_nhwc", lambda dt: (F.norm_bwd_py, (dt, "instance_norm", 5, True))),
+    ("batch_norm_fwd_full_def", lambda dt: (F.norm_fwd_py, (dt, "batch_norm", 4, True))),
+    ("batch_norm_bwd_full_def", lambda dt: (F.norm_bwd_py, (dt, "batch_norm", 4, True))),
     ("dropout_layernorm_fwd_py", lambda dt: (F.dropout_layernorm_fwd_py, (dt, 0.2))),
     ("dropout_rmsnorm_fwd_py", lambda dt: (F.dropout_rmsnorm_fwd_py, (dt, 0.1))),
     ("dropout_layernorm_bwd_py", lambda dt: (F.dropout_layernorm_bwd_py, (dt, 0.2))),
