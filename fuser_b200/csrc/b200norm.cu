@@ -498,7 +498,16 @@ bool try_ring_plan(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, int 
     }
   }
   int groups = kConsumerThreads / tpr;
-  if (groups > 8) groups = 8;  // named-barrier ids / diminishing returns for warp-sized groups
+  // At most 8 groups (named-barrier ids) — except for 32-thread rows of the forward-type kernels, whose groups
+  // synchronise with __syncwarp: sixteen one-warp groups, each with a two-stage ring of smaller tiles, keep 512 threads
+  // per SM busy where eight left half the warps out. Measured bf16 (8 -> 16 groups): RMSNorm [32768,784] 22.0 -> 17.3 us
+  // (71 -> 91 %), LayerNorm [32768,784] 32.2 -> 24.1 us, [65536,1024] 57.2 -> 51.1 us, RMSNorm [65536,1024] 52.6 -> 49.8 us
+  // (profiles/r02n_kbench_short_rows.txt). B200NORM_GROUPS=8 restores the old plans.
+  // Two-stream kernels (softmax backward, the fused-add forwards) go the other way except for the shortest rows:
+  // [65536,1024] softmax bwd 68 -> 116 us, rms(x + residual) 91 -> 130 us, but [262144,256] 144 -> 112 / 186 -> 130 us.
+  const bool g16 = tpr == 32 && !bwd && !colsum && !inner_red && C == 1 && rows_contiguous &&
+                   (ns == 1 || slice_cols * es <= 512);
+  if (groups > 8 && !g16) groups = 8;
   if (int gmax = kn.groups) {
     if (gmax >= 1 && gmax < groups) groups = gmax;
   }
@@ -514,7 +523,7 @@ bool try_ring_plan(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, int 
   // rows per tile: aim for >= 8 KB bulk copies when rows are short and contiguous
   int tile_rows = 1;
   if (C == 1 && rows_contiguous && p.slice_bytes < 8192) {
-    tile_rows = (int)(8192 / p.slice_bytes);
+    tile_rows = (int)((groups > 8 ? 4096u / (uint32_t)ns : 8192u) / p.slice_bytes);  // 16 groups: ~4 KB stages
     if (tile_rows > 32) tile_rows = 32;
     if (tile_rows < 1) tile_rows = 1;
     // do not starve the grid: keep at least a few tiles per consumer group per SM
@@ -683,7 +692,7 @@ int make_plan_uncached(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, 
       const bool inner_red = d.op == B200NORM_OP_REDUCE_INNER ||
                              (d.op == B200NORM_OP_LAYERNORM_FWD && (d.flags & B200NORM_F_NO_Y) != 0);
       const bool good = inner_red ? cand.depth >= 2
-                                                         : (cand.cached || is_norm_bwd(d.op)) && cand.depth >= 3;
+                                                         : (cand.cached || is_norm_bwd(d.op)) && cand.depth >= (cand.groups > 8 ? 2 : 3);  // sixteen one-warp groups run two-stage rings
       if (good || forced_c > 0) {
         best = cand;
         break;
