@@ -122,7 +122,7 @@ const DeviceInfo& device_info() { return device_ctx().info; }
 struct Knobs {
   int tpr = 0, groups = 0, depth = 0, tile_rows = 0, cluster = 0, bwd_reread = 0, pipe = 0, no_pipe = 0, no_psmem = 0;
   int no_fused_finish = 0, no_pdl = 0, coop = 0, static_sched = 0, pool = 0, debug = 0, peer_timeout_s = -1;
-  int ln_pipe = 0, no_ln_pipe = 0, no_guard = 0, no_lean = 0, sm_one_exch = 0, drop_ch4 = 0;
+  int ln_pipe = 0, no_ln_pipe = 0, no_guard = 0, no_lean = 0, sm_one_exch = 0, drop_ch4 = 0, no_tile2 = 0;
   bool any = false;
   uint64_t hash = 0;  // of the planner-relevant values (plan cache key)
 };
@@ -135,7 +135,7 @@ Knobs read_knobs() {
       {"NO_PSMEM", &Knobs::no_psmem}, {"NO_FUSED_FINISH", &Knobs::no_fused_finish}, {"NO_PDL", &Knobs::no_pdl},
       {"COOP", &Knobs::coop}, {"STATIC", &Knobs::static_sched}, {"POOL", &Knobs::pool}, {"DEBUG", &Knobs::debug},
       {"PEER_TIMEOUT_S", &Knobs::peer_timeout_s}, {"LN_PIPE", &Knobs::ln_pipe}, {"NO_LN_PIPE", &Knobs::no_ln_pipe},
-      {"NO_GUARD", &Knobs::no_guard}, {"NO_LEAN", &Knobs::no_lean}, {"SM_ONE_EXCH", &Knobs::sm_one_exch}, {"DROP_CH4", &Knobs::drop_ch4}};
+      {"NO_GUARD", &Knobs::no_guard}, {"NO_LEAN", &Knobs::no_lean}, {"SM_ONE_EXCH", &Knobs::sm_one_exch}, {"DROP_CH4", &Knobs::drop_ch4}, {"NO_TILE2", &Knobs::no_tile2}};
   if (::environ == nullptr) return k;
   for (char** e = ::environ; *e != nullptr; ++e) {
     if (strncmp(*e, "B200NORM_", 9) != 0) continue;
@@ -153,7 +153,7 @@ Knobs read_knobs() {
   }
   if (k.any) {
     const int vals[] = {k.tpr, k.groups, k.depth, k.tile_rows, k.cluster, k.bwd_reread, k.pipe, k.no_pipe, k.no_psmem,
-                        k.ln_pipe, k.no_ln_pipe, k.no_lean, k.drop_ch4};
+                        k.ln_pipe, k.no_ln_pipe, k.no_lean, k.drop_ch4, k.no_tile2};
     uint64_t h = 1469598103934665603ull;
     for (int v : vals) h = (h ^ (uint64_t)(uint32_t)v) * 1099511628211ull;
     k.hash = h | 1ull;
@@ -539,6 +539,15 @@ bool try_ring_plan(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, int 
     const int64_t budget = (int64_t)dev.smem_optin - 4096;
     if (budget / stage2 / groups >= 3 && ceil_div64(d.rows, 2) >= (int64_t)dev.sm_count * groups * 2) tile_rows = 2;
   }
+  // Rows of 8-12 KB, two per tile: inner reductions (nothing is held per row, the per-tile cost dominates: bf16
+  // [65536,4096] 123.7 -> 90.8 us, [16384,4096] 32.0 -> 26.0 us, [16384,6144] 37.4 -> 33.8 us; rows of 16 KB and more
+  // measured equal or slower) and the 16-bit LayerNorm forward with the fused residual add at 8 KB (the register
+  // kernel on two-row tiles beats the pipelined one there: [16384,4096] 100.7 -> 90.0 us)
+  if (C == 1 && rows_contiguous && tile_rows == 1 && kn.no_tile2 == 0 &&
+      ((inner_red && p.slice_bytes >= 8192 && p.slice_bytes <= 12288) ||
+       (add && d.op == B200NORM_OP_LAYERNORM_FWD && !dropout && es == 2 && p.slice_bytes == 8192)) &&
+      ceil_div64(d.rows, 2) >= (int64_t)dev.sm_count * groups * 2)
+    tile_rows = 2;
   if (int tr = kn.tile_rows) {
     if (C == 1 && rows_contiguous && tr >= 1 && tr <= 64) tile_rows = tr;
   }
@@ -1080,8 +1089,11 @@ int launch_typed(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, const 
     if (it != ctx.bad_modes.end()) bad = it->second;
   }
   const int bad0 = bad;
-  const bool allow_fused = want_cols && plan.block >= 128 && kn.no_fused_finish == 0;
   const bool peer = want_cols && (d.flags & (B200NORM_F_PEER_REDUCE | B200NORM_F_PEER_PUBLISH)) != 0;
+  // Rows split over a cluster leave the column sums to the finalize kernel (launched with PDL right behind): with
+  // tens of thousands of columns the grid barrier + in-kernel finish measured 0.5-2 % slower than the extra launch
+  // (bf16 [4096,65536] 290.6 -> 288.8 us, [2048,131072] 322.7 -> 316.2 us); the peer flavours need the fused finish.
+  const bool allow_fused = want_cols && plan.block >= 128 && kn.no_fused_finish == 0 && (plan.cluster == 1 || peer);
   const bool deferred = (d.flags & B200NORM_F_PEER_PUBLISH) != 0;
   std::unique_lock<std::mutex> plock(ctx.peer_mu, std::defer_lock);
   PeerState& ps = ctx.peers;

@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(kMaxBlock, 1) norm_bwd_ring_kernel(const RowPa
   ring_setup(p, smem0);
   tl_mark(p, 1);
   Group<TPR> g(p, smem0);
-  Ring<T, TPR> ring(p, smem0, g);
+  Ring<T, TPR, false, DROP> ring(p, smem0, g);
   ring.prologue();
 
   const int nchunks = p.nchunks;

@@ -441,7 +441,9 @@ struct Group {
 // g + k*G; it lives in stage k % D — tracked as a running (stage, phase) pair.
 // All per-tile bookkeeping is 32-bit counters and running pointers.
 // ---------------------------------------------------------------------------
-template <typename T, int TPR, bool DYN = false>
+// XS: every stage also carries the residual slice and the mask bytes (fused-dropout backward) — a compile-time
+// flavour, so that the producer path of every other kernel stays as short as it was
+template <typename T, int TPR, bool DYN = false, bool XS = false>
 struct Ring {
   const RowParams& p;
   const Group<TPR>& g;
@@ -529,8 +531,13 @@ struct Ring {
     const size_t col0_bytes = (size_t)g.crank * p.slice_bytes;
     base0 = static_cast<const uint8_t*>(p.in0) + col0_bytes;
     base1 = static_cast<const uint8_t*>(p.in1) + col0_bytes;
-    base2 = static_cast<const uint8_t*>(p.in2) + col0_bytes;
-    base_m = p.mask_in + (size_t)g.crank * (size_t)p.cols_cta;
+    if constexpr (XS) {
+      base2 = static_cast<const uint8_t*>(p.in2) + col0_bytes;
+      base_m = p.mask_in + (size_t)g.crank * (size_t)p.cols_cta;
+    } else {
+      base2 = nullptr;
+      base_m = nullptr;
+    }
   }
 
   __device__ __forceinline__ int nrows_of(int32_t kk) const { return kk == ntiles_g - 1 ? last_nrows : p.tile_rows; }
@@ -542,8 +549,8 @@ struct Ring {
     const uint32_t bytes = (uint32_t)nr * p.slice_bytes;
     const uint32_t dst = smem0 + off;
     const uint64_t policy = l2_policy_evict_first();
-    // fused-dropout backward (p.drop_streams): dy | x | residual | mask bytes in one stage
-    const bool extra = p.drop_streams != 0;
+    // fused-dropout backward (XS): dy | x | residual | mask bytes in one stage
+    constexpr bool extra = XS;
     const uint32_t mbytes_row = (uint32_t)p.cols_cta;
     const uint32_t total = bytes * (uint32_t)p.nstreams + (extra ? bytes + (uint32_t)nr * mbytes_row : 0u);
     // No proxy fence is needed for this write-after-read: every reader consumed its loads
@@ -555,7 +562,7 @@ struct Ring {
         if (p.nstreams > 1) {
           bulk_g2s(dst + p.stream_bytes, base1 + (size_t)r0 * p.in1_stride * sizeof(T), bytes, b, policy);
         }
-        if (extra) {
+        if constexpr (extra) {
           bulk_g2s(dst + 2u * p.stream_bytes, base2 + (size_t)r0 * p.in2_stride * sizeof(T), bytes, b, policy);
           bulk_g2s(dst + 3u * p.stream_bytes, base_m + (size_t)r0 * (size_t)p.cols, (uint32_t)nr * mbytes_row, b, policy);
         }
@@ -570,7 +577,7 @@ struct Ring {
           bulk_g2s(dst + p.stream_bytes + (uint32_t)r * p.slice_bytes,
                    base1 + (size_t)(r0 + r) * p.in1_stride * sizeof(T), p.slice_bytes, b, policy);
         }
-        if (extra) {
+        if constexpr (extra) {
           bulk_g2s(dst + 2u * p.stream_bytes + (uint32_t)r * p.slice_bytes,
                    base2 + (size_t)(r0 + r) * p.in2_stride * sizeof(T), p.slice_bytes, b, policy);
           bulk_g2s(dst + 3u * p.stream_bytes + (uint32_t)r * mbytes_row, base_m + (size_t)(r0 + r) * (size_t)p.cols,
