@@ -122,7 +122,7 @@ const DeviceInfo& device_info() { return device_ctx().info; }
 struct Knobs {
   int tpr = 0, groups = 0, depth = 0, tile_rows = 0, cluster = 0, bwd_reread = 0, pipe = 0, no_pipe = 0, no_psmem = 0;
   int no_fused_finish = 0, no_pdl = 0, coop = 0, static_sched = 0, pool = 0, debug = 0, peer_timeout_s = -1;
-  int ln_pipe = 0, no_ln_pipe = 0, no_guard = 0, no_lean = 0, sm_one_exch = 0, drop_ch4 = 0, no_tile2 = 0;
+  int ln_pipe = 0, no_ln_pipe = 0, no_guard = 0, no_lean = 0, drop_ch4 = 0, no_tile2 = 0;
   bool any = false;
   uint64_t hash = 0;  // of the planner-relevant values (plan cache key)
 };
@@ -135,7 +135,7 @@ Knobs read_knobs() {
       {"NO_PSMEM", &Knobs::no_psmem}, {"NO_FUSED_FINISH", &Knobs::no_fused_finish}, {"NO_PDL", &Knobs::no_pdl},
       {"COOP", &Knobs::coop}, {"STATIC", &Knobs::static_sched}, {"POOL", &Knobs::pool}, {"DEBUG", &Knobs::debug},
       {"PEER_TIMEOUT_S", &Knobs::peer_timeout_s}, {"LN_PIPE", &Knobs::ln_pipe}, {"NO_LN_PIPE", &Knobs::no_ln_pipe},
-      {"NO_GUARD", &Knobs::no_guard}, {"NO_LEAN", &Knobs::no_lean}, {"SM_ONE_EXCH", &Knobs::sm_one_exch}, {"DROP_CH4", &Knobs::drop_ch4}, {"NO_TILE2", &Knobs::no_tile2}};
+      {"NO_GUARD", &Knobs::no_guard}, {"NO_LEAN", &Knobs::no_lean}, {"DROP_CH4", &Knobs::drop_ch4}, {"NO_TILE2", &Knobs::no_tile2}};
   if (::environ == nullptr) return k;
   for (char** e = ::environ; *e != nullptr; ++e) {
     if (strncmp(*e, "B200NORM_", 9) != 0) continue;
@@ -270,7 +270,8 @@ uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 #define B200_RING_KERNEL_FOR(T, SUF)                                                                         \
   template <>                                                                                                \
   RingKernel ring_kernel_for<T>(int op, int tpr, int ch, bool cached, bool psmem, bool add, bool pipe,       \
-                                bool red, bool lean, bool drop) {                                          \
+                                bool red, bool lean, bool drop, bool rowaff) {                             \
+    if (rowaff && op == B200NORM_OP_LAYERNORM_BWD) return pipe ? nullptr : ring_bwd_rowaff_kernel_##SUF(tpr, ch, cached); \
     if (drop && is_norm_bwd(op)) return cached ? ring_bwd_drop_kernel_##SUF(op, tpr, ch) : nullptr;          \
     if (drop) return (add && !pipe && !psmem) ? ring_drop_kernel_##SUF(op, tpr, ch) : nullptr;               \
     if (op == B200NORM_OP_REDUCE_INNER || red) return ring_reduce_inner_kernel_##SUF(tpr, ch);               \
@@ -284,7 +285,7 @@ uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
   }
 template <typename T>
 RingKernel ring_kernel_for(int op, int tpr, int ch, bool cached, bool psmem, bool add, bool pipe, bool red, bool lean,
-                           bool drop);
+                           bool drop, bool rowaff);
 B200_RING_KERNEL_FOR(float, f32)
 B200_RING_KERNEL_FOR(__nv_bfloat16, bf16)
 B200_RING_KERNEL_FOR(__half, f16)
@@ -308,11 +309,11 @@ int prepare_ring_kernel(DeviceCtx& ctx, RingKernel k, int smem, int cluster) {
 }
 
 RingKernel ring_kernel_any(int dt, int op, int tpr, int ch, bool cached, bool psmem, bool add, bool pipe, bool red,
-                           bool lean, bool drop) {
+                           bool lean, bool drop, bool rowaff = false) {
   switch (dt) {
-    case B200NORM_DT_F32: return ring_kernel_for<float>(op, tpr, ch, cached, psmem, add, pipe, red, lean, drop);
-    case B200NORM_DT_BF16: return ring_kernel_for<__nv_bfloat16>(op, tpr, ch, cached, psmem, add, pipe, red, lean, drop);
-    case B200NORM_DT_F16: return ring_kernel_for<__half>(op, tpr, ch, cached, psmem, add, pipe, red, lean, drop);
+    case B200NORM_DT_F32: return ring_kernel_for<float>(op, tpr, ch, cached, psmem, add, pipe, red, lean, drop, rowaff);
+    case B200NORM_DT_BF16: return ring_kernel_for<__nv_bfloat16>(op, tpr, ch, cached, psmem, add, pipe, red, lean, drop, rowaff);
+    case B200NORM_DT_F16: return ring_kernel_for<__half>(op, tpr, ch, cached, psmem, add, pipe, red, lean, drop, rowaff);
     default: return nullptr;
   }
 }
@@ -650,10 +651,10 @@ bool try_ring_plan(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, int 
 
   // only the plans the planner emits are instantiated (ring_inst_*.cuh): a combination forced through the tuning
   // knobs may have no kernel — then this cluster size is simply not feasible
-  if (ring_kernel_any(d.io_dtype, d.op, tpr, ch, cached, p.psmem, add, p.pipe, p.stats_reduce, p.lean, dropout) == nullptr)
+  if (ring_kernel_any(d.io_dtype, d.op, tpr, ch, cached, p.psmem, add, p.pipe, p.stats_reduce, p.lean, dropout, (d.flags & B200NORM_F_ROW_AFFINE) != 0) == nullptr)
     return false;
   const int64_t ntiles = ceil_div64(d.rows, tile_rows);
-  int64_t nclusters = max_active_clusters(ctx, ring_kernel_any(d.io_dtype, d.op, tpr, ch, cached, p.psmem, add, p.pipe, p.stats_reduce, p.lean, dropout), p.block,
+  int64_t nclusters = max_active_clusters(ctx, ring_kernel_any(d.io_dtype, d.op, tpr, ch, cached, p.psmem, add, p.pipe, p.stats_reduce, p.lean, dropout, (d.flags & B200NORM_F_ROW_AFFINE) != 0), p.block,
                                           (int)p.smem, C);
   if (nclusters > ntiles) nclusters = ntiles;
   if (nclusters < 1) nclusters = 1;
@@ -1068,7 +1069,8 @@ int launch_typed(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, const 
 
   // ---- ring kernels ----
   RingKernel k = ring_kernel_for<T>(d.op, plan.tpr, plan.ch, plan.cached, plan.psmem, is_add_fwd(d), plan.pipe,
-                                    plan.stats_reduce, plan.lean, (d.flags & B200NORM_F_DROPOUT) != 0);
+                                    plan.stats_reduce, plan.lean, (d.flags & B200NORM_F_DROPOUT) != 0,
+                                    (d.flags & B200NORM_F_ROW_AFFINE) != 0);
   if (k == nullptr)
     return fail(B200NORM_ERR_UNSUPPORTED, "no ring kernel for op %d tpr %d ch %d", d.op, plan.tpr, plan.ch);
   {
@@ -1452,7 +1454,6 @@ int b200norm_launch(const b200norm_desc* desc, const b200norm_tensor* inputs, in
     rp.var_scale = (float)(1.0 / (denom > 0.0 ? denom : 0.0));
   }
   rp.flags = d.flags;
-  if (kn.sm_one_exch != 0) rp.flags |= kFlagOneExchange;
   const bool row_aff = (d.flags & B200NORM_F_ROW_AFFINE) != 0;
   rp.channels = row_aff ? d.reserved[3] : 0;
   const bool dropout = (d.flags & B200NORM_F_DROPOUT) != 0;

@@ -5,4 +5,5 @@ RingKernel ring_bwd_kernel_bf16(int op, int tpr, int ch, bool cached, bool cente
   return ring_bwd_kernel_for<__nv_bfloat16>(op, tpr, ch, cached, centered);
 }
 RingKernel ring_bwd_drop_kernel_bf16(int op, int tpr, int ch) { return ring_bwd_drop_kernel_for<__nv_bfloat16>(op, tpr, ch); }
+RingKernel ring_bwd_rowaff_kernel_bf16(int tpr, int ch, bool cached) { return ring_bwd_rowaff_kernel_for<__nv_bfloat16>(tpr, ch, cached); }
 }  // namespace b200norm

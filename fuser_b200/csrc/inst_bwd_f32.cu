@@ -5,4 +5,5 @@ RingKernel ring_bwd_kernel_f32(int op, int tpr, int ch, bool cached, bool center
   return ring_bwd_kernel_for<float>(op, tpr, ch, cached, centered);
 }
 RingKernel ring_bwd_drop_kernel_f32(int op, int tpr, int ch) { return ring_bwd_drop_kernel_for<float>(op, tpr, ch); }
+RingKernel ring_bwd_rowaff_kernel_f32(int tpr, int ch, bool cached) { return ring_bwd_rowaff_kernel_for<float>(tpr, ch, cached); }
 }  // namespace b200norm

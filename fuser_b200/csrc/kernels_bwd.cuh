@@ -327,8 +327,10 @@ __device__ __forceinline__ void bwd_epilogue(const RowParams& p, const Group<TPR
 // DROP (cached form only): the fused-dropout backward of benchmarks/python/test_dropout_{layernorm,rmsnorm}_bwd.py.
 // Every stage carries dy | x | residual | mask bytes; x_eff = residual + (mask ? x / keep : 0) replaces x, and the
 // row's gradient goes out twice: d residual = d x_eff (out1) and d x = mask ? d x_eff / keep : 0 (out0).
-template <typename T, int TPR, int CH, bool LN, bool CACHE, bool CEN = true, bool DROP = false>
+// ROWAFF: instance norm (kFlagRowAffine) — its own instantiations, LayerNorm only.
+template <typename T, int TPR, int CH, bool LN, bool CACHE, bool CEN = true, bool DROP = false, bool ROWAFF = false>
 __global__ void __launch_bounds__(kMaxBlock, 1) norm_bwd_ring_kernel(const RowParams p) {
+  static_assert(!ROWAFF || (LN && !DROP), "instance norm is a LayerNorm flavour");
   static_assert(!DROP || CACHE, "the fused-dropout backward keeps g / x_hat (and the mask bits) in registers");
   constexpr int VEC = IO<T>::VEC;
   constexpr int H = VEC / 2;
@@ -352,7 +354,7 @@ __global__ void __launch_bounds__(kMaxBlock, 1) norm_bwd_ring_kernel(const RowPa
   const size_t col0_bytes = (size_t)g.crank * p.slice_bytes;
   // instance norm (kFlagRowAffine, LayerNorm only): the weight belongs to the row's channel — g = dy inside, the row's
   // weight scales the finished dx, and the row sums of dy / dy * x_hat go out instead of column sums
-  const bool row_aff = LN && (p.flags & kFlagRowAffine) != 0;
+  constexpr bool row_aff = ROWAFF;
   uint4 wq[CH];
   load_params_to_regs<T, TPR, CH>(row_aff ? nullptr : p.weight, col0_bytes, g.gtid, nchunks, 1.0f, wq);
 

@@ -286,9 +286,9 @@ __global__ void __launch_bounds__(kMaxBlock, 1) softmax_fwd_ring_kernel(const Ro
   const int nchunks = p.nchunks;
 
   const size_t out_row_bytes = (size_t)p.out_stride * sizeof(T);
-  // Measured slower than the two-reduction form on every cluster plan (bf16 [4096,131072] 755 vs 704 us, fp32
-  // [2048,131072] 1138 vs 708 us: the rescaling costs more than the saved DSMEM round trip) — a tuning knob only.
-  const bool online = g.csize > 1 && (p.flags & kFlagOneExchange) != 0;
+  // (A single-exchange form — online (max, sum) pairs, Group::softmax_allreduce — was built and measured slower on
+  // every cluster plan: bf16 [4096,131072] 755 vs 704 us, fp32 [2048,131072] 1138 vs 708 us; the cross-entropy forward,
+  // which writes nothing per element, is where that reduction pays: kernels_reduce.cuh.)
   for (; ring.acquire(); ring.advance()) {
     if (ring.k == 0) tl_mark(p, 2);
     const int nrows = ring.cur_nrows;
@@ -306,48 +306,6 @@ __global__ void __launch_bounds__(kMaxBlock, 1) softmax_fwd_ring_kernel(const Ro
           if constexpr (CH > 0) x[j][k] = t[k];
         }
       });
-      if (online) {
-        // row split over a cluster: exponentials around the THREAD's maximum, one (max, sum) exchange per row, and
-        // one scale factor per thread afterwards (Group::softmax_allreduce)
-        const float mt = m[0];
-        const float2 nmt = f2(mt == -INFINITY ? 0.f : -mt);  // an all -inf set: exp(-inf - 0) = 0, not exp(NaN)
-        float2 acc = f2(0.f);
-        for_each_chunk<TPR, CH>(g.gtid, nchunks, [&](int j, int coff) {
-          float2 t[H];
-          if constexpr (CH == 0) IO<T>::unpack2(ld_smem_u4(xrow + 16 * coff), t);
-#pragma unroll
-          for (int k = 0; k < H; ++k) {
-            const float2 d = f2add(CH > 0 ? x[j][k] : t[k], nmt);
-            const float2 e = make_float2(exp_for<T>(d.x), exp_for<T>(d.y));
-            acc = f2add(acc, e);
-            if constexpr (CH > 0) x[j][k] = LOG ? d : e;
-          }
-        });
-        float rm = mt, rs = acc.x + acc.y;
-        g.template softmax_allreduce<T>(rm, rs);
-        if (CH > 0 && r == nrows - 1) ring.refill();
-        // y = exp(x - mt) * exp(mt - m) / s   |   (x - mt) + (mt - m) - log(s)
-        const float2 fin = f2(LOG ? (mt - rm) - logf(rs) : Group<TPR>::template softmax_rescale<T>(mt, rm) * rcp_fast(rs));
-        const float2 nrm = f2(-rm);
-        const float2 inv = f2(LOG ? -logf(rs) : rcp_fast(rs));
-        for_each_chunk<TPR, CH>(g.gtid, nchunks, [&](int j, int coff) {
-          float2 y[H];
-          if constexpr (CH > 0) {
-#pragma unroll
-            for (int k = 0; k < H; ++k) y[k] = LOG ? f2add(x[j][k], fin) : f2mul(x[j][k], fin);
-          } else {
-            float2 t[H];
-            IO<T>::unpack2(ld_smem_u4(xrow + 16 * coff), t);
-#pragma unroll
-            for (int k = 0; k < H; ++k) {
-              const float2 d = f2add(t[k], nrm);
-              y[k] = LOG ? f2add(d, inv) : f2mul(make_float2(exp_for<T>(d.x), exp_for<T>(d.y)), inv);
-            }
-          }
-          st_global_stream(yrow + 16 * coff, IO<T>::pack2(y));
-        });
-        continue;
-      }
       g.template allreduce<MaxOp, 1>(m);
       if (CH > 0 && r == nrows - 1) ring.refill();  // registers hold the row: the stage is free
       const float2 nmx = f2(-m[0]);

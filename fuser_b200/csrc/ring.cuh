@@ -64,8 +64,6 @@ constexpr uint32_t kFlagStatM2 = 1u << 22;
 constexpr uint32_t kFlagDropout = 1u << 23;
 constexpr uint32_t kFlagReduceNll = 1u << 24;
 constexpr uint32_t kFlagRowAffine = 1u << 25;  // instance norm: weight / bias indexed by (row mod channels)
-// internal (never set through the ABI: check_desc refuses unknown bits), tuning knobs of the launch
-constexpr uint32_t kFlagOneExchange = 1u << 31;  // cluster softmax forward: (max, sum) pairs in ONE exchange (B200NORM_SM_ONE_EXCH)
 
 struct RowParams {
   // streamed operands (row-major, unit inner stride)

@@ -30,6 +30,10 @@ RingKernel ring_bwd_kernel_f16(int op, int tpr, int ch, bool cached, bool center
 RingKernel ring_bwd_drop_kernel_f32(int op, int tpr, int ch);
 RingKernel ring_bwd_drop_kernel_bf16(int op, int tpr, int ch);
 RingKernel ring_bwd_drop_kernel_f16(int op, int tpr, int ch);
+// instance norm backward (B200NORM_F_ROW_AFFINE)
+RingKernel ring_bwd_rowaff_kernel_f32(int tpr, int ch, bool cached);
+RingKernel ring_bwd_rowaff_kernel_bf16(int tpr, int ch, bool cached);
+RingKernel ring_bwd_rowaff_kernel_f16(int tpr, int ch, bool cached);
 // pipelined re-read backward (split-phase reductions overlapped across rows): ch in {3,4}, tpr in {64..512};
 // lean: RMSNorm without the centring term on the instruction-trimmed kernel (tpr 256 / 512)
 RingKernel ring_bwd_pipe_kernel_f32(int op, int tpr, int ch, bool lean);

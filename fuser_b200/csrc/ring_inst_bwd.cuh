@@ -75,6 +75,25 @@ RingKernel ring_bwd_drop_kernel_sel(int tpr, int ch) {
     default: return nullptr;
   }
 }
+// instance norm backward (LayerNorm with the row's channel weight, per-row sums out): the cached pairs and the
+// re-read form at 512 threads
+template <typename T>
+RingKernel ring_bwd_rowaff_kernel_for(int tpr, int ch, bool cached) {
+  if (cached) {
+    switch (tpr) {
+      case 32:
+        if (ch == 1) return norm_bwd_ring_kernel<T, 32, 1, true, true, true, false, true>;
+        if (ch == 2) return norm_bwd_ring_kernel<T, 32, 2, true, true, true, false, true>;
+        return nullptr;
+      case 64: return ch == 2 ? norm_bwd_ring_kernel<T, 64, 2, true, true, true, false, true> : nullptr;
+      case 128: return ch == 2 ? norm_bwd_ring_kernel<T, 128, 2, true, true, true, false, true> : nullptr;
+      case 256: return ch == 2 ? norm_bwd_ring_kernel<T, 256, 2, true, true, true, false, true> : nullptr;
+      case 512: return ch == 2 ? norm_bwd_ring_kernel<T, 512, 2, true, true, true, false, true> : nullptr;
+      default: return nullptr;
+    }
+  }
+  return (tpr == 512 && ch == 3) ? norm_bwd_ring_kernel<T, 512, 3, true, false, true, false, true> : nullptr;
+}
 template <typename T>
 RingKernel ring_bwd_drop_kernel_for(int op, int tpr, int ch) {
   return op == B200NORM_OP_LAYERNORM_BWD ? ring_bwd_drop_kernel_sel<T, true>(tpr, ch)

@@ -15,7 +15,7 @@ import torch  # noqa: E402
 from bench import measured_peak  # noqa: E402
 from fuser_b200 import ops  # noqa: E402
 
-KEYS = ["B200NORM_NO_TILE2", "B200NORM_DROP_CH4", "B200NORM_SM_ONE_EXCH", "B200NORM_COOP", "B200NORM_NO_OUTER_ROWS", "B200NORM_OUTER_ROWS", "B200NORM_NO_LEAN", "B200NORM_LN_PIPE", "B200NORM_NO_LN_PIPE", "B200NORM_TPR", "B200NORM_GROUPS", "B200NORM_DEPTH", "B200NORM_TILE_ROWS", "B200NORM_CLUSTER",
+KEYS = ["B200NORM_NO_TILE2", "B200NORM_DROP_CH4", "B200NORM_COOP", "B200NORM_NO_OUTER_ROWS", "B200NORM_OUTER_ROWS", "B200NORM_NO_LEAN", "B200NORM_LN_PIPE", "B200NORM_NO_LN_PIPE", "B200NORM_TPR", "B200NORM_GROUPS", "B200NORM_DEPTH", "B200NORM_TILE_ROWS", "B200NORM_CLUSTER",
         "B200NORM_BWD_REREAD", "B200NORM_NO_FUSED_FINISH", "B200NORM_NO_PDL", "B200NORM_NO_PSMEM", "B200NORM_COOP", "B200NORM_STATIC", "B200NORM_POOL", "B200NORM_NO_PIPE", "B200NORM_PIPE",
         "B200NORM_OUTER_W", "B200NORM_OUTER_DEPTH", "B200NORM_OUTER_UNITS", "B200NORM_OUTER_PER_SM", "B200NORM_OUTER_SKIP_REDUCE", "B200NORM_OUTER_PLAIN_ST", "B200NORM_OUTER_TWO_EXCH", "B200NORM_OUTER_L2PF"]
 DT = {"bf16": torch.bfloat16, "f32": torch.float32, "f16": torch.float16}

@@ -11,10 +11,10 @@ import subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HOT = [  # (object, substring of the demangled kernel name)
     ("inst_fwd_bf16.o", "rmsnorm_fwd_ring_kernel<__nv_bfloat16, 128, 4, false, false>"),
-    ("inst_bwd_bf16.o", "norm_bwd_ring_kernel<__nv_bfloat16, 256, 2, false, true, true, false>"),
+    ("inst_bwd_bf16.o", "norm_bwd_ring_kernel<__nv_bfloat16, 256, 2, false, true, true, false, false>"),
     ("inst_fwd_bf16.o", "softmax_fwd_ring_kernel<__nv_bfloat16, 256, 4, false>"),
     ("inst_fwd_bf16.o", "softmax_bwd_ring_kernel<__nv_bfloat16, 256, 4, false>"),
-    ("inst_bwd_bf16.o", "norm_bwd_ring_kernel<__nv_bfloat16, 512, 3, true, false, true, false>"),
+    ("inst_bwd_bf16.o", "norm_bwd_ring_kernel<__nv_bfloat16, 512, 3, true, false, true, false, false>"),
     ("inst_pipe_bf16.o", "rmsnorm_fwd_pipe_kernel<__nv_bfloat16, 512, 4>"),
     ("inst_pipe_bf16.o", "rms_bwd_pipe_lean_kernel<__nv_bfloat16, 512, 4>"),
     ("inst_pipe_bf16.o", "norm_bwd_pipe_kernel<__nv_bfloat16, 512, 4, false>"),
@@ -28,7 +28,7 @@ HOT = [  # (object, substring of the demangled kernel name)
     ("outer.o", "outer_rows_kernel<__nv_bfloat16, true>"),
     ("inst_drop_bf16.o", "layernorm_fwd_ring_kernel<__nv_bfloat16, 128, 4, false, true, true>"),
     ("inst_drop_bf16.o", "rmsnorm_fwd_ring_kernel<__nv_bfloat16, 128, 4, true, true>"),
-    ("inst_bwd_bf16.o", "norm_bwd_ring_kernel<__nv_bfloat16, 256, 2, true, true, true, true>"),
+    ("inst_bwd_bf16.o", "norm_bwd_ring_kernel<__nv_bfloat16, 256, 2, true, true, true, true, false>"),
     ("b200norm.o", "cross_entropy_bwd_kernel<__nv_bfloat16, true>"),
 ]
 KEYS = ["UBLKCP", "UTMALDG", "SYNCS.ARRIVE", "SYNCS.PHASECHK", "STAS", "UCGABAR", "MAPA", "FFMA2", "FADD2", "FMUL2", "IMAD.WIDE",
