@@ -280,6 +280,8 @@ uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
     if (add) return ring_add_kernel_##SUF(op, tpr, ch, psmem);                                               \
     if (is_norm_bwd(op) && !cached && pipe) return ring_bwd_pipe_kernel_##SUF(op, tpr, ch, lean);            \
     if (op == B200NORM_OP_RMSNORM_FWD && pipe) return ring_fwd_pipe_kernel_##SUF(op, tpr, ch);               \
+    if ((op == B200NORM_OP_SOFTMAX_FWD || op == B200NORM_OP_LOGSOFTMAX_FWD) && pipe)                         \
+      return ring_sm_pipe_kernel_##SUF(op, tpr, ch);                                                         \
     return is_norm_bwd(op) ? ring_bwd_kernel_##SUF(op, tpr, ch, cached, !(lean && !cached))                    \
                            : ring_fwd_kernel_##SUF(op, tpr, ch, psmem);                                    \
   }
@@ -363,6 +365,7 @@ int max_active_clusters(DeviceCtx& ctx, RingKernel k, int block, int smem, int C
 
 constexpr int kConsumerThreads = 512;
 constexpr int kFwdWideCH = 6;      // ... for kernels whose only per-chunk state is x (TPR >= 256)
+constexpr int kSmPipeMaxCH = 8;    // ... packed chunks per thread the pipelined cluster softmax keeps across its first pass
 constexpr int kFwdMaxCH = 4;       // chunks per thread kept in registers by the forward-type kernels
 constexpr int kBwdCacheCH = 2;     // backward, g / xc cached in registers
 constexpr int kBwdRereadCH_RMS = 4;  // backward re-read variant: column accumulators = CH * VEC (x2 for LayerNorm)
@@ -407,6 +410,13 @@ bool try_ring_plan(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, int 
   // inner reductions without an output pass: sum / max / fmax and the stand-alone statistics (var_mean, welford)
   const bool inner_red = d.op == B200NORM_OP_REDUCE_INNER ||
                          (d.op == B200NORM_OP_LAYERNORM_FWD && (d.flags & B200NORM_F_NO_Y) != 0);
+
+  // Softmax / log-softmax forward over a cluster: the pipelined one-exchange kernel (kernels_softmax_pipe.cuh) — the
+  // row stays in its stage, so slices of any width work as long as two stages fit; one 512-thread group per CTA.
+  // Measured against the register-resident kernel in DESIGN 4c. B200NORM_NO_PIPE=1 switches it off.
+  const bool sm_pipe = (d.op == B200NORM_OP_SOFTMAX_FWD || d.op == B200NORM_OP_LOGSOFTMAX_FWD) && C > 1 &&
+                       kn.no_pipe == 0 && (kn.tpr == 0 || kn.tpr == 512) && nchunks >= 1024 &&
+                       slice_cols * es <= (int64_t)100 * 1024;
 
   // Threads per row slice and chunks per thread. Forward-type kernels: the smallest group
   // that keeps the slice in registers at <= kFwdMaxCH chunks per thread (fewer, fatter
@@ -453,6 +463,12 @@ bool try_ring_plan(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, int 
       if (ch < 3) ch = 3;  // only CH 3 / 4 are instantiated for the re-read form
       if (ch == 4 && ln_bwd) return false;
     }
+  } else if (sm_pipe) {
+    tpr = 512;
+    ch = (nchunks + 511) / 512;
+    if (ch > kSmPipeMaxCH) ch = 0;  // looping form
+    if (ch == 1) ch = 2;
+    cached = ch > 0;
   } else if ((d.op == B200NORM_OP_RMSNORM_FWD && !add) || d.op == B200NORM_OP_SOFTMAX_FWD) {
     // x is the only per-chunk register state: up to 6 chunks per thread from TPR 256 on
     // (N = 12288 bf16 -> two 256-thread groups per CTA instead of one 512-thread group)
@@ -629,7 +645,8 @@ bool try_ring_plan(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, int 
   // ... and for rows wide enough to need one 512-thread group per CTA; with several groups per
   // CTA the groups already overlap each other and the second smem pass only costs (N = 8192: 85 vs 95 us).
   // (16-bit only: the fp32 single-group kernel is at the roofline already, 163 vs 182 us at N = 8192)
-  if (ln_pipe) p.pipe = true;
+  if (ln_pipe || sm_pipe) p.pipe = true;
+  if (sm_pipe && p.depth < 2) return false;  // pass 1 of the next row needs its own stage
   p.stats_reduce = inner_red && d.op == B200NORM_OP_LAYERNORM_FWD;
   // RMSNorm backward without the centring term: the re-read instantiations that neither accumulate sum(g) nor
   // reduce it ([32768,12288] bf16 382 -> 368 us, [16384,8192] 137 -> 132 us; the CACHED form measured slower

@@ -1,0 +1,5 @@
+// Instantiations of the pipelined cluster softmax forward for __nv_bfloat16 (see ring_inst_smpipe.cuh).
+#include "ring_inst_smpipe.cuh"
+namespace b200norm {
+RingKernel ring_sm_pipe_kernel_bf16(int op, int tpr, int ch) { return ring_sm_pipe_kernel_for<__nv_bfloat16>(op, tpr, ch); }
+}  // namespace b200norm

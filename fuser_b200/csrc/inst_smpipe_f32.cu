@@ -1,0 +1,5 @@
+// Instantiations of the pipelined cluster softmax forward for float (see ring_inst_smpipe.cuh).
+#include "ring_inst_smpipe.cuh"
+namespace b200norm {
+RingKernel ring_sm_pipe_kernel_f32(int op, int tpr, int ch) { return ring_sm_pipe_kernel_for<float>(op, tpr, ch); }
+}  // namespace b200norm

@@ -44,6 +44,11 @@ RingKernel ring_fwd_pipe_kernel_f32(int op, int tpr, int ch);
 RingKernel ring_fwd_pipe_kernel_bf16(int op, int tpr, int ch);
 RingKernel ring_fwd_pipe_kernel_f16(int op, int tpr, int ch);
 
+// pipelined softmax / log-softmax forward over cluster rows (kernels_softmax_pipe.cuh): tpr 512, ch in {2..8} or 0
+RingKernel ring_sm_pipe_kernel_f32(int op, int tpr, int ch);
+RingKernel ring_sm_pipe_kernel_bf16(int op, int tpr, int ch);
+RingKernel ring_sm_pipe_kernel_f16(int op, int tpr, int ch);
+
 // pipelined one-round LayerNorm forward (kernels_ln_pipe.cuh): tpr in {64..512}, ch in {1..4} (5, 6 at tpr 256), with or without the fused residual add
 RingKernel ring_ln_pipe_kernel_f32(int tpr, int ch, bool add);
 RingKernel ring_ln_pipe_kernel_bf16(int tpr, int ch, bool add);

@@ -102,3 +102,53 @@ def test_odd_row_sizes(base, dt):
         AO.assert_close(dbl, dbe, m, f"ln db N={n}")
         aligned = (n * x.element_size()) % 16 == 0
         assert (ops.plan_for(L.OP_SOFTMAX_FWD, dt, m, n)["variant"] != "generic") == aligned
+
+
+# The pipelined one-exchange cluster kernel (kernels_softmax_pipe.cuh) with MANY rows per cluster — ring refills,
+# mbarrier phase wraps, both slot-set parities — at natural and forced cluster sizes, register (ch > 0) and looping
+# (ch = 0) forms, and rows that hold -inf / +inf / NaN in one CTA's slice only.
+PIPE_CASES = [
+    (600, 131072, torch.bfloat16, 0),   # natural plan of the vocabulary benchmark shape
+    (600, 131072, torch.bfloat16, 8),
+    (300, 131072, torch.bfloat16, 16),
+    (700, 65536, torch.bfloat16, 2),    # 64 KB slices
+    (500, 98304, torch.bfloat16, 2),    # 96 KB slices: looping form, two stages
+    (300, 152064, torch.bfloat16, 0),
+    (400, 65536, torch.float32, 0),
+    (250, 131072, torch.float32, 0),
+    (300, 256000, torch.float16, 0),
+]
+
+
+@pytest.mark.parametrize("m,n,dt,c", PIPE_CASES, ids=lambda v: str(v).replace("torch.", ""))
+def test_cluster_softmax_pipe_many_rows(m, n, dt, c):
+    x = _x(m, n, dt, m + n)
+    x = (x.float() * 3).to(dt)
+    # special rows: one slice all -inf, a whole row -inf, +inf and NaN somewhere past the first slice
+    x[3, : n // 16] = float("-inf")
+    x[5, :] = float("-inf")
+    x[7, n - 5] = float("inf")
+    x[9, n // 2 + 1] = float("nan")
+    x[11, : n - 1] = float("-inf")
+    xd = x.cuda()
+    plan = ops.plan_for(L.OP_SOFTMAX_FWD, dt, m, n, cluster_size=c)
+    assert plan["variant"] == "cluster" and plan["pipe"], plan
+    if c:
+        assert plan["cluster_size"] == c
+    assert m > plan["stages"] * (plan["grid"] // plan["cluster_size"]) * 2  # several ring revolutions per cluster
+    lplan = ops.plan_for(L.OP_LOGSOFTMAX_FWD, dt, m, n, cluster_size=c)
+    assert lplan["pipe"], lplan
+    y = ops.softmax_fwd(xd, cluster_size=c)
+    ly = ops.softmax_fwd(xd, log=True, cluster_size=c)
+    torch.cuda.synchronize()
+    ye, lye = AO.softmax_fwd(x), AO.log_softmax_fwd(x)
+    AO.assert_close(y, ye, n * n, "softmax y")
+    AO.assert_close(ly, lye, n * n, "log_softmax y")
+    assert torch.equal(torch.isnan(y.cpu()), torch.isnan(ye)) and torch.equal(torch.isnan(ly.cpu()), torch.isnan(lye))
+    assert torch.equal(torch.isinf(ly.cpu()), torch.isinf(lye))
+    fin = torch.ones(m, dtype=torch.bool)
+    fin[[5, 7, 9]] = False
+    assert ulp_err(y.cpu()[fin], CO.softmax_fwd(x[fin]), floor=1e-7 if dt != torch.float32 else 1e-5) <= TIGHT[dt] * 2
+    assert (y.float().sum(-1)[fin.cuda()] - 1).abs().max().item() < 3e-2
+    # the same bits from run to run and against a different cluster size (the merge order is fixed per plan)
+    assert torch.equal(ops.softmax_fwd(xd, cluster_size=c).view(torch.uint8), y.view(torch.uint8))
