@@ -274,6 +274,7 @@ uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
     if (rowaff && op == B200NORM_OP_LAYERNORM_BWD) return pipe ? nullptr : ring_bwd_rowaff_kernel_##SUF(tpr, ch, cached); \
     if (drop && is_norm_bwd(op)) return cached ? ring_bwd_drop_kernel_##SUF(op, tpr, ch) : nullptr;          \
     if (drop) return (add && !pipe && !psmem) ? ring_drop_kernel_##SUF(op, tpr, ch) : nullptr;               \
+    if (op == B200NORM_OP_REDUCE_INNER && pipe) return ring_sm_pipe_kernel_##SUF(op, tpr, ch);               \
     if (op == B200NORM_OP_REDUCE_INNER || red) return ring_reduce_inner_kernel_##SUF(tpr, ch);               \
     if (op == B200NORM_OP_REDUCE_OUTER) return ring_colsum_kernel_##SUF(tpr, ch);                            \
     if (pipe && op == B200NORM_OP_LAYERNORM_FWD) return ring_ln_pipe_kernel_##SUF(tpr, ch, add);             \
@@ -414,7 +415,9 @@ bool try_ring_plan(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, int 
   // Softmax / log-softmax forward over a cluster: the pipelined one-exchange kernel (kernels_softmax_pipe.cuh) — the
   // row stays in its stage, so slices of any width work as long as two stages fit; one 512-thread group per CTA.
   // Measured against the register-resident kernel in DESIGN 4c. B200NORM_NO_PIPE=1 switches it off.
-  const bool sm_pipe = (d.op == B200NORM_OP_SOFTMAX_FWD || d.op == B200NORM_OP_LOGSOFTMAX_FWD) && C > 1 &&
+  // The cross-entropy forward (REDUCE_INNER | F_REDUCE_NLL) is the same kernel without its second pass.
+  const bool nll_red = d.op == B200NORM_OP_REDUCE_INNER && (d.flags & B200NORM_F_REDUCE_NLL) != 0;
+  const bool sm_pipe = (d.op == B200NORM_OP_SOFTMAX_FWD || d.op == B200NORM_OP_LOGSOFTMAX_FWD || nll_red) && C > 1 &&
                        kn.no_pipe == 0 && (kn.tpr == 0 || kn.tpr == 512) && nchunks >= 1024 &&
                        slice_cols * es <= (int64_t)100 * 1024;
 
@@ -438,7 +441,12 @@ bool try_ring_plan(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, int 
     }
     return false;
   };
-  if (colsum) {
+  if (sm_pipe) {
+    tpr = 512;
+    ch = (nchunks + 511) / 512;
+    if (ch > kSmPipeMaxCH) ch = 0;  // looping form
+    cached = ch > 0;
+  } else if (colsum) {
     if (!pick(kFwdMaxCH)) return false;  // CH * VEC accumulators per thread; wider rows are split over a cluster
   } else if (inner_red && nchunks > 128 * kFwdMaxCH && forced_tpr == 0) {
     // Inner reductions keep no per-chunk state, so any number of chunks per thread works (looping form): prefer
@@ -463,12 +471,6 @@ bool try_ring_plan(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, int 
       if (ch < 3) ch = 3;  // only CH 3 / 4 are instantiated for the re-read form
       if (ch == 4 && ln_bwd) return false;
     }
-  } else if (sm_pipe) {
-    tpr = 512;
-    ch = (nchunks + 511) / 512;
-    if (ch > kSmPipeMaxCH) ch = 0;  // looping form
-    if (ch == 1) ch = 2;
-    cached = ch > 0;
   } else if ((d.op == B200NORM_OP_RMSNORM_FWD && !add) || d.op == B200NORM_OP_SOFTMAX_FWD) {
     // x is the only per-chunk register state: up to 6 chunks per thread from TPR 256 on
     // (N = 12288 bf16 -> two 256-thread groups per CTA instead of one 512-thread group)
@@ -718,7 +720,12 @@ int make_plan_uncached(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, 
       // (an inner reduction holds a stage only while it is being summed: two stages per group are enough)
       const bool inner_red = d.op == B200NORM_OP_REDUCE_INNER ||
                              (d.op == B200NORM_OP_LAYERNORM_FWD && (d.flags & B200NORM_F_NO_Y) != 0);
-      const bool good = inner_red ? cand.depth >= 2
+      // (the pipelined cluster softmax reads its rows from the stage: the smallest cluster with three stages —
+      // two for the cross-entropy flavour, which releases a stage after its only pass — whatever the slice width)
+      const bool sm_pipe = cand.pipe && (d.op == B200NORM_OP_SOFTMAX_FWD || d.op == B200NORM_OP_LOGSOFTMAX_FWD ||
+                                         d.op == B200NORM_OP_REDUCE_INNER);
+      const bool good = sm_pipe ? cand.depth >= (d.op == B200NORM_OP_REDUCE_INNER ? 2 : 3)
+                        : inner_red ? cand.depth >= 2
                                                          : (cand.cached || is_norm_bwd(d.op)) && cand.depth >= (cand.groups > 8 ? 2 : 3);  // sixteen one-warp groups run two-stage rings
       if (good || forced_c > 0) {
         best = cand;

@@ -447,6 +447,13 @@ __device__ __forceinline__ float rcp_fast(float x) {
   return y;
 }
 
+// exp(x) as one MUFU.EX2 (relative error about 2^-22): sums of exponentials in any io dtype.
+__device__ __forceinline__ float exp_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+  return y;
+}
+
 // Fast exp for 16-bit outputs (one MUFU.EX2 per element); accurate expf for fp32.
 template <typename T>
 __device__ __forceinline__ float exp_for(float x) {

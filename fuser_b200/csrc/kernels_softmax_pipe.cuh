@@ -19,8 +19,13 @@
 
 namespace b200norm {
 
-template <typename T, int TPR, int CH, bool LOG>
+// MODE 0: softmax, 1: log-softmax, 2: cross-entropy forward (REDUCE_INNER | kFlagReduceNll: lse = M + log S and
+// loss = lse - x[target] per row, nothing per element — no pass 2, the stage is released after pass 1; the target's
+// logit is read from the stage by the first thread of the CTA whose slice holds it, as in kernels_reduce.cuh).
+template <typename T, int TPR, int CH, int MODE>
 __global__ void __launch_bounds__(kMaxBlock, 1) softmax_fwd_pipe_kernel(const RowParams p) {
+  constexpr bool LOG = MODE == 1;
+  constexpr bool NLL = MODE == 2;
   constexpr int VEC = IO<T>::VEC;
   constexpr int H = VEC / 2;
   constexpr int WPG = TPR / 32;
@@ -72,9 +77,27 @@ __global__ void __launch_bounds__(kMaxBlock, 1) softmax_fwd_pipe_kernel(const Ro
     for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
     m = wm;
   };
+  // cross-entropy: (target logit, owner CTA or -1 for an ignored / out-of-range target) of the row pass 1 last saw
+  float xt_next = 0.f;
+  int owner_next = -1;
+  long long t_ahead = 0;  // thread 0: the target index one row ahead of pass 1 (hides the global load)
+  if constexpr (NLL) {
+    if (g.gtid == 0 && ring.ntiles_g > 0) t_ahead = p.target[ring.row0];
+  }
   auto pass1_post = [&](int j_row) {
     mbar_wait(c1_bar, c1_phase);
     const uint8_t* xrow = smem_raw + c1_off + 16u * (uint32_t)g.gtid;
+    if constexpr (NLL) {
+      if (g.gtid == 0) {
+        const long long t = t_ahead;
+        if (j_row + 1 < ring.ntiles_g) t_ahead = p.target[ring.row0 + (int64_t)(j_row + 1) * ring.row_step];
+        const bool valid = t != (long long)p.ignore_index && t >= 0 && t < (long long)p.cols;
+        owner_next = valid ? (int)(t / p.cols_cta) : -1;
+        xt_next = 0.f;
+        if (owner_next == (int)g.crank)
+          xt_next = IO<T>::to_f32(reinterpret_cast<const T*>(xrow)[t - (long long)owner_next * p.cols_cta]);
+      }
+    }
     uint4 xq[NC];
     float m = -INFINITY;
     for_each_chunk<TPR, CH>(g.gtid, nchunks, [&](int j, int coff) {
@@ -99,8 +122,9 @@ __global__ void __launch_bounds__(kMaxBlock, 1) softmax_fwd_pipe_kernel(const Ro
       }
 #pragma unroll
       for (int k = 0; k < H; ++k) {
+        // (the SUM takes the approximate exponential for fp32 rows too: a term's relative error of 2^-22 is the sum's)
         const float2 d = f2add(t[k], nref);
-        acc = f2add(acc, make_float2(exp_for<T>(d.x), exp_for<T>(d.y)));
+        acc = f2add(acc, make_float2(exp_fast(d.x), exp_fast(d.y)));
       }
     });
     float s = acc.x + acc.y;
@@ -111,6 +135,14 @@ __global__ void __launch_bounds__(kMaxBlock, 1) softmax_fwd_pipe_kernel(const Ro
       set[g.warp] = m;
       set[kMaxWarpsPerGroup + g.warp] = s;
       mbar_arrive(red_bar + 8u * (uint32_t)(j_row & 1));
+    }
+    if constexpr (NLL) {  // nothing reads the stage again: release it, the producer warp refills it
+      __syncwarp();
+      if (g.lane == 0) mbar_arrive(free_bar + 8u * c1_s);
+      if (g.warp == 0) {
+        mbar_wait(free_bar + 8u * c1_s, c1_phase);
+        if (j_row + p.depth < n) ring.issue_rows(1, row_first + (int64_t)(j_row + p.depth) * row_step, c1_off, c1_bar);
+      }
     }
     advance(c1_off, c1_bar, c1_s, c1_phase);
   };
@@ -138,6 +170,8 @@ __global__ void __launch_bounds__(kMaxBlock, 1) softmax_fwd_pipe_kernel(const Ro
         st_async_f32(slot + 4u, S, rbar);
       }
     }
+    const float xt = xt_next;
+    const int owner = owner_next;
     if (k + 1 < n) pass1_post(k + 1);
     if (g.csize > 1) {
       mbar_wait(cl_bar, ph);
@@ -147,9 +181,17 @@ __global__ void __launch_bounds__(kMaxBlock, 1) softmax_fwd_pipe_kernel(const Ro
       S = has ? slots[g.lane * kRedNV + 1] : 0.f;
       merge_lanes(M, S);
     }
+    const int64_t row = row_first + (int64_t)k * row_step;
+    if constexpr (NLL) {
+      if (g.gtid == 0 && g.crank == (uint32_t)(owner < 0 ? 0 : owner)) {
+        const float lse = M + logf(S);
+        if (p.stat1 != nullptr) p.stat1[row] = owner >= 0 ? lse - xt : 0.f;
+        if (p.stat0 != nullptr) p.stat0[row] = lse;
+      }
+      continue;
+    }
     const float2 nmx = f2(-M);
     const float2 fin = f2(LOG ? -logf(S) : rcp_fast(S));
-    const int64_t row = row_first + (int64_t)k * row_step;
     const uint8_t* xrow = smem_raw + c2_off + 16u * (uint32_t)g.gtid;
     uint8_t* yrow = out_row_ptr<T>(p, row, g.crank, g.gtid);
     for_each_chunk<TPR, CH>(g.gtid, nchunks, [&](int, int coff) {

@@ -1,4 +1,4 @@
-// ring_inst_smpipe.cuh — instantiation table of the pipelined cluster softmax / log-softmax forward for one dtype.
+// ring_inst_smpipe.cuh — instantiation table of the pipelined cluster softmax / log-softmax / cross-entropy forward for one dtype.
 #pragma once
 
 #include "../../include/b200norm.h"
@@ -12,10 +12,14 @@ namespace b200norm {
 template <typename T>
 RingKernel ring_sm_pipe_kernel_for(int op, int tpr, int ch) {
   if (tpr != 512) return nullptr;
-  const bool log = op == B200NORM_OP_LOGSOFTMAX_FWD;
-  if (!log && op != B200NORM_OP_SOFTMAX_FWD) return nullptr;
-#define B200_SMPIPE_CASE(CH) \
-  case CH: return log ? softmax_fwd_pipe_kernel<T, 512, CH, true> : softmax_fwd_pipe_kernel<T, 512, CH, false>;
+  // REDUCE_INNER here means its cross-entropy flavour (B200NORM_F_REDUCE_NLL): the planner sets pipe for no other
+  const int mode = op == B200NORM_OP_SOFTMAX_FWD ? 0 : op == B200NORM_OP_LOGSOFTMAX_FWD ? 1 : op == B200NORM_OP_REDUCE_INNER ? 2 : -1;
+  if (mode < 0) return nullptr;
+#define B200_SMPIPE_CASE(CH)                                           \
+  case CH:                                                             \
+    return mode == 0   ? softmax_fwd_pipe_kernel<T, 512, CH, 0>        \
+           : mode == 1 ? softmax_fwd_pipe_kernel<T, 512, CH, 1>        \
+                       : softmax_fwd_pipe_kernel<T, 512, CH, 2>;
   switch (ch) {
     B200_SMPIPE_CASE(0)
     B200_SMPIPE_CASE(2)

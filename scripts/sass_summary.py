@@ -30,6 +30,8 @@ HOT = [  # (object, substring of the demangled kernel name)
     ("inst_drop_bf16.o", "rmsnorm_fwd_ring_kernel<__nv_bfloat16, 128, 4, true, true>"),
     ("inst_bwd_bf16.o", "norm_bwd_ring_kernel<__nv_bfloat16, 256, 2, true, true, true, true, false>"),
     ("b200norm.o", "cross_entropy_bwd_kernel<__nv_bfloat16, true>"),
+    ("inst_smpipe_bf16.o", "softmax_fwd_pipe_kernel<__nv_bfloat16, 512, 8, 0>"),
+    ("inst_smpipe_bf16.o", "softmax_fwd_pipe_kernel<__nv_bfloat16, 512, 8, 2>"),
 ]
 KEYS = ["UBLKCP", "UTMALDG", "SYNCS.ARRIVE", "SYNCS.PHASECHK", "STAS", "UCGABAR", "MAPA", "FFMA2", "FADD2", "FMUL2", "IMAD.WIDE",
         "F2FP", "MUFU", "LDS.128", "STG.E.EF.128", "ATOMG", "ACQBULK", "LDL", "STL"]

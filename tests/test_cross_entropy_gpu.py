@@ -114,3 +114,28 @@ def test_cross_entropy_descriptors_and_plans():
         ops.plan_for(L.OP_REDUCE_INNER, torch.bfloat16, 64, 4096, flags=L.F_REDUCE_NLL | L.F_REDUCE_MAX)
     with pytest.raises(L.UnsupportedSegment):
         ops.plan_for(L.OP_SOFTMAX_FWD, torch.bfloat16, 64, 4096, flags=L.F_REDUCE_NLL)
+
+
+@pytest.mark.parametrize("m,n,dt,c", [(700, 131072, torch.bfloat16, 0), (500, 151936, torch.bfloat16, 0),
+                                      (600, 65536, torch.bfloat16, 2), (400, 131072, torch.bfloat16, 16),
+                                      (300, 131072, torch.float32, 0), (500, 98304, torch.float16, 2)],
+                         ids=lambda v: str(v).replace("torch.", ""))
+def test_nll_softmax_pipe_many_rows(m, n, dt, c):
+    """The pipelined one-exchange cluster kernel (kernels_softmax_pipe.cuh, cross-entropy flavour) over many rows per
+    cluster: ring refills, phase wraps, the target index fetched one row ahead; slices of -inf and a NaN row (torch.logsumexp special-cases +inf, the op-by-op log-softmax of the reference does not: not compared)."""
+    x, t = _make(m, n, dt, m + n + c)
+    x[3, : n // 16] = float("-inf")
+    x[5, : n - 1] = float("-inf")
+    t[5] = n - 1
+    x[9, n - 3] = float("nan")
+    plan = ops.plan_for(L.OP_REDUCE_INNER, dt, m, n, flags=L.F_REDUCE_NLL, cluster_size=c)
+    assert plan["variant"] == "cluster" and plan["pipe"], plan
+    assert m > 2 * plan["stages"] * (plan["grid"] // plan["cluster_size"])
+    loss, lse = ops.nll_softmax_fwd(x.cuda(), t.cuda(), cluster_size=c)
+    torch.cuda.synchronize()
+    le, lsee = AO.nll_softmax_fwd(x, t)
+    AO.assert_close(lse, lsee, n, "log-sum-exp")
+    AO.assert_close(loss, le, n, "per-row loss")
+    assert torch.equal(torch.isnan(lse.cpu()), torch.isnan(lsee)) and torch.equal(torch.isinf(lse.cpu()), torch.isinf(lsee))
+    loss2, lse2 = ops.nll_softmax_fwd(x.cuda(), t.cuda(), cluster_size=c)
+    assert torch.equal(lse2.view(torch.int32), lse.view(torch.int32)), "same bits from run to run"
