@@ -19,6 +19,26 @@
 
 namespace b200norm {
 
+// A 4-byte piece of a row (two 16-bit elements or one fp32 element): the granularity of the balanced tail below.
+template <typename T>
+__device__ __forceinline__ float2 unpack_piece(uint32_t w) {
+  if constexpr (sizeof(T) == 4) {
+    return make_float2(__uint_as_float(w), __uint_as_float(w));  // both halves the same element: max / exp see it twice
+  } else if constexpr (IO<T>::DT == 1) {
+    return bf16x2_to_f2(w);
+  } else {
+    return __half22float2(*reinterpret_cast<const __half2*>(&w));
+  }
+}
+template <typename T>
+__device__ __forceinline__ uint32_t pack_piece(float2 v) {
+  if constexpr (sizeof(T) == 4) {
+    return __float_as_uint(v.x);
+  } else {
+    return IO<T>::pack2(v.x, v.y);
+  }
+}
+
 // MODE 0: softmax, 1: log-softmax, 2: cross-entropy forward (REDUCE_INNER | kFlagReduceNll: lse = M + log S and
 // loss = lse - x[target] per row, nothing per element — no pass 2, the stage is released after pass 1; the target's
 // logit is read from the stage by the first thread of the CTA whose slice holds it, as in kernels_reduce.cuh).
@@ -45,6 +65,13 @@ __global__ void __launch_bounds__(kMaxBlock, 1) softmax_fwd_pipe_kernel(const Ro
   ring.prologue();
 
   const int nchunks = p.nchunks;
+  // Balanced tail. A slice of CH * TPR + t chunks with a small t (N = 100352 over four CTAs: 6 * 512 + 64) would make
+  // t threads — the first warps, the producer warp among them — walk one more chunk than everybody else in both
+  // passes, and every row waits for them at its barriers. The planner then hands this kernel CH = floor(chunks / TPR)
+  // and the t chunks behind the full steps are walked in 4-byte pieces by ALL threads (at most kTailIters each).
+  constexpr int kTailIters = 2;  // t <= 256 chunks = 1024 pieces
+  const int tail_pieces = CH > 0 && nchunks > CH * TPR ? 4 * (nchunks - CH * TPR) : 0;
+  const uint32_t tail_off = (uint32_t)CH * TPR * 16u + 4u * (uint32_t)g.gtid;  // byte offset of this thread's first piece
   const uint32_t red_bar = smem0 + p.off_pipe + 8u * (uint32_t)(2 * g.gid);
   const uint32_t free_bar = smem0 + p.off_pipe + 8u * (uint32_t)(2 * p.groups + g.gid * p.depth);
   const uint32_t cl_bar_even = g.clbar;
@@ -108,6 +135,18 @@ __global__ void __launch_bounds__(kMaxBlock, 1) softmax_fwd_pipe_kernel(const Ro
 #pragma unroll
       for (int k = 0; k < H; ++k) m = MaxOp::apply(m, MaxOp::apply(t[k].x, t[k].y));
     });
+    uint32_t tq[kTailIters];
+    if (tail_pieces > 0) {
+      const uint8_t* trow = smem_raw + c1_off + tail_off;
+#pragma unroll
+      for (int i = 0; i < kTailIters; ++i) {
+        if (g.gtid + i * TPR < tail_pieces) {
+          tq[i] = *reinterpret_cast<const uint32_t*>(trow + 4 * i * TPR);
+          const float2 t = unpack_piece<T>(tq[i]);
+          m = MaxOp::apply(m, MaxOp::apply(t.x, t.y));
+        }
+      }
+    }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) m = MaxOp::apply(m, __shfl_xor_sync(0xffffffffu, m, off));
     // a part that holds nothing but -inf sums exp(-inf - 0) = 0 instead of exp(-inf + inf) = NaN
@@ -128,6 +167,16 @@ __global__ void __launch_bounds__(kMaxBlock, 1) softmax_fwd_pipe_kernel(const Ro
       }
     });
     float s = acc.x + acc.y;
+    if (tail_pieces > 0) {
+#pragma unroll
+      for (int i = 0; i < kTailIters; ++i) {
+        if (g.gtid + i * TPR < tail_pieces) {
+          const float2 d = f2add(unpack_piece<T>(tq[i]), nref);
+          s += exp_fast(d.x);
+          if constexpr (sizeof(T) == 2) s += exp_fast(d.y);
+        }
+      }
+    }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
     if (g.lane == 0) {
@@ -204,6 +253,18 @@ __global__ void __launch_bounds__(kMaxBlock, 1) softmax_fwd_pipe_kernel(const Ro
       }
       st_global_stream(yrow + 16 * coff, IO<T>::pack2(y));
     });
+    if (tail_pieces > 0) {
+      const uint8_t* trow = smem_raw + c2_off + tail_off;
+      uint8_t* ty = yrow - 16u * (uint32_t)g.gtid + tail_off;
+#pragma unroll
+      for (int i = 0; i < kTailIters; ++i) {
+        if (g.gtid + i * TPR < tail_pieces) {
+          const float2 d = f2add(unpack_piece<T>(*reinterpret_cast<const uint32_t*>(trow + 4 * i * TPR)), nmx);
+          const float2 y = LOG ? f2add(d, fin) : f2mul(make_float2(exp_for<T>(d.x), exp_for<T>(d.y)), fin);
+          __stcs(reinterpret_cast<uint32_t*>(ty + 4 * i * TPR), pack_piece<T>(y));
+        }
+      }
+    }
     __syncwarp();
     if (g.lane == 0) mbar_arrive(free_bar + 8u * c2_s);
     if (g.warp == 0) {

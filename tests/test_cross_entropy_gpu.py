@@ -118,7 +118,8 @@ def test_cross_entropy_descriptors_and_plans():
 
 @pytest.mark.parametrize("m,n,dt,c", [(700, 131072, torch.bfloat16, 0), (500, 151936, torch.bfloat16, 0),
                                       (600, 65536, torch.bfloat16, 2), (400, 131072, torch.bfloat16, 16),
-                                      (300, 131072, torch.float32, 0), (500, 98304, torch.float16, 2)],
+                                      (300, 131072, torch.float32, 0), (500, 98304, torch.float16, 2),
+                                      (500, 100352, torch.bfloat16, 0), (300, 100352, torch.float32, 0)],
                          ids=lambda v: str(v).replace("torch.", ""))
 def test_nll_softmax_pipe_many_rows(m, n, dt, c):
     """The pipelined one-exchange cluster kernel (kernels_softmax_pipe.cuh, cross-entropy flavour) over many rows per

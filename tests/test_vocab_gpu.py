@@ -117,6 +117,9 @@ PIPE_CASES = [
     (400, 65536, torch.float32, 0),
     (250, 131072, torch.float32, 0),
     (300, 256000, torch.float16, 0),
+    (500, 100352, torch.bfloat16, 0),   # 6 * 512 + 64 chunks per CTA: the balanced tail (4-byte pieces)
+    (300, 100352, torch.float32, 0),
+    (300, 202048, torch.float16, 0),    # 6 * 512 + 85
 ]
 
 
