@@ -417,7 +417,10 @@ bool try_ring_plan(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, int 
   // Measured against the register-resident kernel in DESIGN 4c. B200NORM_NO_PIPE=1 switches it off.
   // The cross-entropy forward (REDUCE_INNER | F_REDUCE_NLL) is the same kernel without its second pass.
   const bool nll_red = d.op == B200NORM_OP_REDUCE_INNER && (d.flags & B200NORM_F_REDUCE_NLL) != 0;
-  const bool sm_pipe = (d.op == B200NORM_OP_SOFTMAX_FWD || d.op == B200NORM_OP_LOGSOFTMAX_FWD || nll_red) && C > 1 &&
+  // Also WITHOUT a cluster for rows of more than 48 KB (N = 32000 ... 37500 at 16 bits — the 32 K vocabularies): they fit
+  // neither the registers of the register kernel nor two consumer groups, and one CTA per row keeps all 148 SMs busy.
+  const bool sm_pipe = (d.op == B200NORM_OP_SOFTMAX_FWD || d.op == B200NORM_OP_LOGSOFTMAX_FWD || nll_red) &&
+                       (C > 1 || (nchunks > 512 * kFwdWideCH && kn.pipe >= 0)) &&
                        kn.no_pipe == 0 && (kn.tpr == 0 || kn.tpr == 512) && nchunks >= 1024 &&
                        slice_cols * es <= (int64_t)100 * 1024;
 

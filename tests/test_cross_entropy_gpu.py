@@ -119,7 +119,8 @@ def test_cross_entropy_descriptors_and_plans():
 @pytest.mark.parametrize("m,n,dt,c", [(700, 131072, torch.bfloat16, 0), (500, 151936, torch.bfloat16, 0),
                                       (600, 65536, torch.bfloat16, 2), (400, 131072, torch.bfloat16, 16),
                                       (300, 131072, torch.float32, 0), (500, 98304, torch.float16, 2),
-                                      (500, 100352, torch.bfloat16, 0), (300, 100352, torch.float32, 0)],
+                                      (500, 100352, torch.bfloat16, 0), (300, 100352, torch.float32, 0),
+                                      (1500, 32064, torch.bfloat16, 1), (900, 16384, torch.float32, 1)],
                          ids=lambda v: str(v).replace("torch.", ""))
 def test_nll_softmax_pipe_many_rows(m, n, dt, c):
     """The pipelined one-exchange cluster kernel (kernels_softmax_pipe.cuh, cross-entropy flavour) over many rows per
@@ -130,7 +131,7 @@ def test_nll_softmax_pipe_many_rows(m, n, dt, c):
     t[5] = n - 1
     x[9, n - 3] = float("nan")
     plan = ops.plan_for(L.OP_REDUCE_INNER, dt, m, n, flags=L.F_REDUCE_NLL, cluster_size=c)
-    assert plan["variant"] == "cluster" and plan["pipe"], plan
+    assert plan["variant"] == ("tma" if c == 1 else "cluster") and plan["pipe"], plan
     assert m > 2 * plan["stages"] * (plan["grid"] // plan["cluster_size"])
     loss, lse = ops.nll_softmax_fwd(x.cuda(), t.cuda(), cluster_size=c)
     torch.cuda.synchronize()

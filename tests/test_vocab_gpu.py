@@ -120,6 +120,9 @@ PIPE_CASES = [
     (500, 100352, torch.bfloat16, 0),   # 6 * 512 + 64 chunks per CTA: the balanced tail (4-byte pieces)
     (300, 100352, torch.float32, 0),
     (300, 202048, torch.float16, 0),    # 6 * 512 + 85
+    (1500, 32064, torch.bfloat16, 1),   # 32 K vocabularies: the same kernel without a cluster (rows of 48-75 KB)
+    (1200, 32768, torch.float16, 1),
+    (900, 16384, torch.float32, 1),
 ]
 
 
@@ -135,9 +138,11 @@ def test_cluster_softmax_pipe_many_rows(m, n, dt, c):
     x[11, : n - 1] = float("-inf")
     xd = x.cuda()
     plan = ops.plan_for(L.OP_SOFTMAX_FWD, dt, m, n, cluster_size=c)
-    assert plan["variant"] == "cluster" and plan["pipe"], plan
+    assert plan["variant"] == ("tma" if c == 1 else "cluster") and plan["pipe"], plan
     if c:
         assert plan["cluster_size"] == c
+    if c == 1:
+        assert ops.plan_for(L.OP_SOFTMAX_FWD, dt, m, n) == plan, "the natural plan of these rows"
     assert m > plan["stages"] * (plan["grid"] // plan["cluster_size"]) * 2  # several ring revolutions per cluster
     lplan = ops.plan_for(L.OP_LOGSOFTMAX_FWD, dt, m, n, cluster_size=c)
     assert lplan["pipe"], lplan
