@@ -60,6 +60,10 @@ WORKLOADS = {
     # plain Reduction segments and stand-alone variance_mean on the fast path
     "r1": ("row sum + var_mean + column sum bf16 [32768,12288] (Reduction / Welford segments)", 32768, 12288, torch.bfloat16,
            "reductions"),
+    # vocabulary-size rows (tests/cpp/test_cluster.cpp:158-211; not a BASELINE.json config): the pipelined one-exchange
+    # softmax forward over a cluster of four, and without a cluster at a 32 K vocabulary
+    "v1": ("softmax fwd+bwd bf16 [4096,131072] (vocabulary-size rows, cluster)", 4096, 131072, torch.bfloat16, "softmax_fwd_bwd"),
+    "v2": ("softmax fwd+bwd bf16 [16384,32768] (32 K vocabulary)", 16384, 32768, torch.bfloat16, "softmax_fwd_bwd"),
 }
 EPS = 1e-5
 L2_BYTES = 126 * 1024 * 1024

@@ -419,8 +419,14 @@ bool try_ring_plan(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, int 
   const bool nll_red = d.op == B200NORM_OP_REDUCE_INNER && (d.flags & B200NORM_F_REDUCE_NLL) != 0;
   // Also WITHOUT a cluster for rows of more than 48 KB (N = 32000 ... 37500 at 16 bits — the 32 K vocabularies): they fit
   // neither the registers of the register kernel nor two consumer groups, and one CTA per row keeps all 148 SMs busy.
-  const bool sm_pipe = (d.op == B200NORM_OP_SOFTMAX_FWD || d.op == B200NORM_OP_LOGSOFTMAX_FWD || nll_red) &&
-                       (C > 1 || (nchunks > 512 * kFwdWideCH && kn.pipe >= 0)) &&
+  // ... and for the softmax rows the register kernel walks with ONE 512-thread group, where it measured faster
+  // (bf16 [16384,24576] 296 -> 262 us = 94 %, [16384,20480] 261 -> 241 us, [16384,16384] 229 -> 224 us, fp32 [16384,8192]
+  // 197 -> 183 us; not fp32 N = 12288: 128 vs 141 us; rows of 24 KB and less have several groups per CTA and win
+  // by a wide margin: [32768,12288] 247 vs 388 us). The cross-entropy mode only beyond 48 KB: up to there the
+  // multi-group reduction kernel is ahead ([16384,24576] 179 vs 208 us). profiles/r02t_kbench_pipe_no_cluster.txt
+  const bool sm_op = d.op == B200NORM_OP_SOFTMAX_FWD || d.op == B200NORM_OP_LOGSOFTMAX_FWD;
+  const bool pipe_c1 = kn.pipe >= 0 && (nchunks > 512 * kFwdWideCH || (sm_op && (es == 2 ? nchunks >= 2048 : nchunks == 2048)));
+  const bool sm_pipe = (sm_op || nll_red) && (C > 1 || pipe_c1 || kn.pipe > 0) &&
                        kn.no_pipe == 0 && (kn.tpr == 0 || kn.tpr == 512) && nchunks >= 1024 &&
                        slice_cols * es <= (int64_t)100 * 1024;
 

@@ -123,6 +123,9 @@ PIPE_CASES = [
     (1500, 32064, torch.bfloat16, 1),   # 32 K vocabularies: the same kernel without a cluster (rows of 48-75 KB)
     (1200, 32768, torch.float16, 1),
     (900, 16384, torch.float32, 1),
+    (2000, 24576, torch.bfloat16, 1),   # one-group rows of the register kernel, where the pipelined one measured faster
+    (2000, 16384, torch.float16, 1),
+    (1500, 8192, torch.float32, 1),
 ]
 
 
