@@ -521,6 +521,14 @@ bool try_ring_plan(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, int 
       // tuning: two 256-thread groups of the pipelined one-round kernel (rows of 5 / 6 chunks per thread)
       tpr = 256;
       ch = nchunks / 256;
+    } else if (d.op == B200NORM_OP_LAYERNORM_FWD && !add && !dropout && !inner_red && (forced_tpr == 0 || forced_tpr == 512) &&
+               nchunks > 512 * kFwdMaxCH && nchunks <= 512 * kFwdWideCH && nchunks % 512 == 0 && kn.no_ln_pipe == 0 &&
+               kn.ln_pipe >= 0) {
+      // rows of five / six chunks per thread at 512 threads (N = 20480 / 24576 at 16 bits, 10240 / 12288 at fp32) on the
+      // pipelined one-round kernel without a cluster: the alternative was a cluster of two with 20-24 KB slices, whose
+      // rows are shorter than the DSMEM round trip ([16384,24576] bf16: 405 us = 61 %). B200NORM_LN_PIPE=-1 restores it.
+      tpr = 512;
+      ch = nchunks / 512;
     } else {
       if (forced_tpr != 0 && forced_tpr != 512) return false;
       tpr = 512;

@@ -36,6 +36,9 @@ RingKernel ring_ln_pipe_kernel_for(int tpr, int ch, bool add) {
   // two 256-thread groups per CTA for rows of 5 / 6 chunks per thread (N = 10240 / 12288 at 16 bits)
   if (tpr == 256 && ch == 5) return layernorm_fwd_pipe_kernel<T, 256, 5, false>;
   if (tpr == 256 && ch == 6) return layernorm_fwd_pipe_kernel<T, 256, 6, false>;
+  // ... and one 512-thread group for rows of 5 / 6 chunks per thread (N = 20480 / 24576 at 16 bits) without a cluster
+  if (tpr == 512 && ch == 5) return layernorm_fwd_pipe_kernel<T, 512, 5, false>;
+  if (tpr == 512 && ch == 6) return layernorm_fwd_pipe_kernel<T, 512, 6, false>;
   switch (tpr) {
     case 64: B200_LNPIPE_CH(64, false)
     case 128: B200_LNPIPE_CH(128, false)

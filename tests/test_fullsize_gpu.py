@@ -301,6 +301,12 @@ def test_layernorm_fwd_pipelined_steady_state(monkeypatch):
     plan = _ln_fwd(700, 65536, torch.bfloat16, 108, {"variant": "cluster", "cluster_size": 4, "pipe": True})
     assert 700 / (plan["grid"] // 4) > plan["stages"]
     _ln_fwd(300, 131072, torch.bfloat16, 109, {"variant": "cluster", "pipe": True})
+    # five / six chunks per thread at 512 threads: no cluster for N = 20480 / 24576 (16 bits), 10240 / 12288 (fp32)
+    _ln_fwd(1500, 24576, torch.bfloat16, 120, dict(pipe1, chunks=6, threads_per_row=512))
+    _ln_fwd(1500, 24576, torch.bfloat16, 121, dict(pipe1, chunks=6), shift=20.0)
+    _ln_fwd(1500, 20480, torch.float16, 122, dict(pipe1, chunks=5, threads_per_row=512))
+    _ln_fwd(1500, 12288, torch.float32, 123, dict(pipe1, chunks=6, threads_per_row=512))
+    _ln_fwd(1500, 10240, torch.float32, 124, dict(pipe1, chunks=5), shift=3.0)
     # multi-group shapes (every threads-per-row class of the table)
     for m, n, dt in [(3001, 4096, torch.bfloat16), (3001, 4096, torch.float32), (2000, 2048, torch.bfloat16),
                      (2000, 1024, torch.float32), (2000, 8192, torch.bfloat16), (2000, 3072, torch.float16)]:
