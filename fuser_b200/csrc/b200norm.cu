@@ -667,6 +667,8 @@ bool try_ring_plan(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, int 
   // ... and for rows wide enough to need one 512-thread group per CTA; with several groups per
   // CTA the groups already overlap each other and the second smem pass only costs (N = 8192: 85 vs 95 us).
   // (16-bit only: the fp32 single-group kernel is at the roofline already, 163 vs 182 us at N = 8192)
+  // ... and at six chunks per thread of ONE 512-thread group (N = 24576 at 16 bits: 292 -> 268 us = 92 %; five chunks
+  // — N = 20480: 214 vs 231 us — and fp32 N = 12288 — 246 vs 269 us — stay on the register kernel)
   if (ln_pipe || sm_pipe) p.pipe = true;
   if (sm_pipe && p.depth < 2) return false;  // pass 1 of the next row needs its own stage
   p.stats_reduce = inner_red && d.op == B200NORM_OP_LAYERNORM_FWD;
@@ -676,7 +678,8 @@ bool try_ring_plan(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, int 
   // (kernels_bwd_lean.cuh: C5 332 -> 290 us)
   p.lean = d.op == B200NORM_OP_RMSNORM_BWD && !(d.flags & B200NORM_F_RMS_BWD_CENTERED) && kn.no_lean == 0;
   if (d.op == B200NORM_OP_RMSNORM_FWD && !add &&
-      (C > 1 || (tpr == 512 && es == 2 && ch == 3 && (nchunks + 255) / 256 == 6) || kn.pipe != 0) && ch > 0 &&
+      (C > 1 || (tpr == 512 && es == 2 && ch == 3 && (nchunks + 255) / 256 == 6) || (tpr == 512 && es == 2 && ch == 6) ||
+       kn.pipe != 0) && ch > 0 &&
       tile_rows == 1 && tpr >= 64 && (ch <= 4 || tpr >= 256) && kn.no_pipe == 0) {
     p.pipe = true;
   }

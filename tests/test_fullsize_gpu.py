@@ -101,6 +101,13 @@ def test_c5_rmsnorm_fwd_bwd_full_size():
                  {"variant": "cluster", "cluster_size": 4, "pipe": True, "cached": False})
 
 
+def test_rmsnorm_wide_rows_one_group():
+    """N = 24576 bf16: six chunks per thread of one 512-thread group — the pipelined forward without a cluster, ten rows
+    per CTA; the backward splits the row over a cluster of two (re-read form, pipelined)."""
+    _rms_fwd_bwd(1500, 24576, torch.bfloat16, 60, {"variant": "tma", "cluster_size": 1, "pipe": True, "chunks": 6},
+                 {"variant": "cluster", "cluster_size": 2, "pipe": True})
+
+
 # ---------------------------------------------------------------------------------------------------
 # C3 softmax forward + backward [65536, 8192] bf16
 # ---------------------------------------------------------------------------------------------------
