@@ -454,7 +454,8 @@ bool try_ring_plan(const b200norm_desc& d, DeviceCtx& ctx, const Knobs& kn, int 
     tpr = 512;
     ch = (nchunks + 511) / 512;
     // a short ragged last step (<= 256 chunks past the full ones) is walked in 4-byte pieces by all threads instead
-    // of one more chunk by a few: the kernel takes CH = floor (kernels_softmax_pipe.cuh, "balanced tail")
+    // of one more chunk by a few: the kernel takes CH = floor (kernels_softmax_pipe.cuh, "balanced tail";
+    // B200NORM_NO_TILE2=1 switches this off too, for A/B runs)
     if (nchunks % 512 != 0 && nchunks % 512 <= 256 && nchunks / 512 >= 2 && kn.no_tile2 == 0) ch = nchunks / 512;
     if (ch > kSmPipeMaxCH) ch = 0;  // looping form
     cached = ch > 0;
