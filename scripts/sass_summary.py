@@ -32,6 +32,8 @@ HOT = [  # (object, substring of the demangled kernel name)
     ("b200norm.o", "cross_entropy_bwd_kernel<__nv_bfloat16, true>"),
     ("inst_smpipe_bf16.o", "softmax_fwd_pipe_kernel<__nv_bfloat16, 512, 8, 0>"),
     ("inst_smpipe_bf16.o", "softmax_fwd_pipe_kernel<__nv_bfloat16, 512, 8, 2>"),
+    ("inst_lnpipe_bf16.o", "layernorm_fwd_pipe_kernel<__nv_bfloat16, 512, 6, false>"),
+    ("inst_pipe_bf16.o", "rmsnorm_fwd_pipe_kernel<__nv_bfloat16, 512, 6>"),
 ]
 KEYS = ["UBLKCP", "UTMALDG", "SYNCS.ARRIVE", "SYNCS.PHASECHK", "STAS", "UCGABAR", "MAPA", "FFMA2", "FADD2", "FMUL2", "IMAD.WIDE",
         "F2FP", "MUFU", "LDS.128", "STG.E.EF.128", "ATOMG", "ACQBULK", "LDL", "STL"]
